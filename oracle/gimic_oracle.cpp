@@ -1,0 +1,1060 @@
+// =============================================================================
+// gimic_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement (C++17 + OpenMP) of the grid hot path of qmcurrents/gimic,
+// written to follow the reference Fortran statement by statement.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load this library; the product (gimic_b200/) never does.
+//
+// The reference itself cannot be built in this environment (no Fortran
+// compiler), so this file is a *restatement*; it is pinned against the
+// reference's own golden outputs (tests/test_oracle_golden.py):
+//   test/c4h4/read-grid/reference/jvec.vtu            (10 digits)
+//   test/c4h4/integration/reference/stdout            (6 decimals)
+//   test/open-shell/3d/reference/*.vti                (6 digits)
+//   test/open-shell/integration/reference/stdout      (6 decimals)
+// divj/edens have no reference implementation at this commit: parity unpinned
+// for those two quantities.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// the reference root).
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---- constants: src/libgimic/globals.f90:41-63 ------------------------------
+constexpr double PII = 3.141592653589793e0;   // globals.f90:41
+constexpr double ZETA = 0.5e0;                // globals.f90:47
+constexpr double DP33 = 0.3333333e0;          // globals.f90:62  (ACID "1/3")
+constexpr double SCREEN_THRS = 1.e-6;         // globals.f90:56
+constexpr int MAX_L = 5;                      // globals.f90:30
+
+// ---- cartesian exponent tables: src/libgimic/gtodefs.f90:24-123 -------------
+struct Nlm { int n[21][3]; int ncomp; };
+static const int GT_STD[6][21][3] = {
+    {{0,0,0}},
+    {{1,0,0},{0,1,0},{0,0,1}},
+    {{2,0,0},{1,1,0},{1,0,1},{0,2,0},{0,1,1},{0,0,2}},                       // gtodefs.f90:92-93
+    {{3,0,0},{2,1,0},{2,0,1},{1,2,0},{1,1,1},{1,0,2},{0,3,0},{0,2,1},{0,1,2},{0,0,3}},  // :95-97
+    {{4,0,0},{3,1,0},{3,0,1},{2,2,0},{2,1,1},{2,0,2},{1,3,0},{1,2,1},{1,1,2},{1,0,3},
+     {0,4,0},{0,3,1},{0,2,2},{0,1,3},{0,0,4}},                               // :99-101
+    {{5,0,0},{4,1,0},{4,0,1},{3,2,0},{3,1,1},{3,0,2},{2,3,0},{2,2,1},{2,1,2},{2,0,3},
+     {1,4,0},{1,3,1},{1,2,2},{1,1,3},{1,0,4},{0,5,0},{0,4,1},{0,3,2},{0,2,3},{0,1,4},{0,0,5}}  // :103-106
+};
+static const int GT_TM[6][21][3] = {
+    {{0,0,0}},
+    {{1,0,0},{0,1,0},{0,0,1}},
+    {{2,0,0},{0,2,0},{0,0,2},{1,1,0},{1,0,1},{0,1,1}},                       // gtodefs.f90:109-110
+    {{3,0,0},{0,3,0},{0,0,3},{2,1,0},{2,0,1},{1,2,0},{0,2,1},{1,0,2},{0,1,2},{1,1,1}},  // :112-114
+    {{4,0,0},{0,4,0},{0,0,4},{3,1,0},{3,0,1},{1,3,0},{0,3,1},{1,0,3},{0,1,3},{2,2,0},
+     {2,0,2},{0,2,2},{2,1,1},{1,2,1},{1,1,2}},                               // :116-118
+    {{5,0,0},{0,5,0},{0,0,5},{4,1,0},{4,0,1},{1,4,0},{0,4,1},{1,0,4},{0,1,4},{3,2,0},
+     {3,0,2},{2,3,0},{0,3,2},{2,0,3},{0,2,3},{3,1,1},{1,3,1},{1,1,3},{2,2,1},{2,1,2},{1,2,2}}  // :120-123
+};
+static inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+
+// ---- types: globals.f90 contraction_t / basis_t / atom_t / molecule_t -------
+struct Contraction {
+    int l = 0, npf = 0, ncomp = 0, nccomp = 0, ncf = 1;
+    std::vector<double> xp, cc, ncc;
+    double thrs = 1.e10;
+};
+struct Atom {
+    double charge = 0; std::string symbol, id;
+    double coord[3] = {0, 0, 0};
+    int nshells = 0;
+    std::vector<int> nctrps;          // per shell, after de-generalisation (intgrl.f90:145)
+    std::vector<Contraction> ctr;
+    std::vector<int> pos;             // 1-based first function of contraction (basis.f90:241-244)
+    int ncgto = 0;
+};
+struct Molecule {
+    std::vector<Atom> atoms;
+    int ngto = 0, ncgto = 0;
+    bool is_turbomole = false;
+};
+struct Settings {                      // src/libgimic/settings.f90:9-36 (subset used on the path)
+    bool is_uhf = false, use_giao = true, use_diamag = true, use_paramag = true;
+};
+
+struct Ctx {
+    Molecule mol;
+    Settings s;
+    int nbf = 0;
+    // dens_t: da(:,:,0:3), db(:,:,0:3), column-major nbf x nbf (dens.f90:13-18)
+    std::vector<double> da[4], db[4];
+    std::string err;
+};
+
+// per-thread scratch == jtensor_t + bfeval_t (jtensor.F90:17-28, bfeval.f90:18-29)
+struct Scratch {
+    std::vector<double> bf, dr, db, d2, dbop, denbf, pdbf, dendb;
+    explicit Scratch(const Ctx &c) {
+        int n = c.nbf, na = (int)c.mol.atoms.size();
+        bf.assign(n, 0); dr.assign(3 * n, 0); db.assign(3 * n, 0); d2.assign(9 * n, 0);
+        dbop.assign(3 * na, 0); denbf.assign(n, 0); pdbf.assign(n, 0); dendb.assign(n, 0);
+    }
+};
+
+// ---- Fortran list-directed reading helpers ----------------------------------
+static std::vector<std::string> split_tokens(const std::string &line) {
+    std::vector<std::string> out; std::string cur;
+    for (char ch : line) {
+        if (ch == ' ' || ch == '\t' || ch == ',' || ch == '\r' || ch == '\n') { if (!cur.empty()) { out.push_back(cur); cur.clear(); } }
+        else cur.push_back(ch);
+    }
+    if (!cur.empty()) out.push_back(cur);
+    return out;
+}
+static double f2d(const std::string &tok) {   // accepts 1.d-8, 0.10E-08, -.28E-01
+    std::string t = tok;
+    for (char &ch : t) if (ch == 'd' || ch == 'D') ch = 'e';
+    return std::strtod(t.c_str(), nullptr);
+}
+struct LineReader {
+    std::vector<std::string> lines; size_t pos = 0;
+    bool load(const std::string &fname) {
+        std::ifstream f(fname); if (!f) return false;
+        std::string l; while (std::getline(f, l)) lines.push_back(l); return true;
+    }
+    bool next(std::string &l) { if (pos >= lines.size()) return false; l = lines[pos++]; return true; }
+    // read(fd,*) v(1:n): starts a new record, continues over records until n values are found
+    bool read_values(int n, std::vector<std::string> &vals) {
+        vals.clear(); std::string l;
+        while ((int)vals.size() < n) {
+            if (!next(l)) return false;
+            for (auto &t : split_tokens(l)) { if ((int)vals.size() < n) vals.push_back(t); }
+        }
+        return true;
+    }
+};
+
+// ---- MOL ("INTGRL") parser: src/libgimic/intgrl.f90:20-264 ------------------
+static bool read_intgrl(const std::string &fname, Molecule &mol, std::string &err) {
+    LineReader rd;
+    if (!rd.load(fname)) { err = "read_intgrl(): open failed: " + fname; return false; }   // intgrl.f90:31-37
+    std::string l;
+    if (!rd.next(l) || l.substr(0, 6) != "INTGRL") { err = "not an INTGRL file"; return false; }  // :39-46
+    if (!rd.next(l)) { err = "short MOL"; return false; }
+    mol.is_turbomole = (l.substr(0, 9) == "TURBOMOLE");                                  // :47-53
+    rd.next(l);                                                                          // :55
+    std::vector<std::string> v;
+    if (!rd.read_values(1, v)) { err = "short MOL"; return false; }                      // :57
+    int natoms = std::atoi(v[0].c_str());
+    rd.next(l);                                                                          // :63
+    mol.atoms.assign(natoms, Atom());
+    for (int ia = 0; ia < natoms; ++ia) {
+        Atom &a = mol.atoms[ia];
+        // read_atom: intgrl.f90:91-115.  nshells is the 3rd value; then nshells counts
+        if (!rd.next(l)) { err = "short MOL (atom header)"; return false; }
+        auto t = split_tokens(l);
+        if (t.size() < 3) { err = "bad atom header"; return false; }
+        a.charge = f2d(t[0]); a.nshells = std::atoi(t[2].c_str());
+        if (a.nshells - 1 > MAX_L) { err = "Largest allowed l-quantum number exceeded"; return false; }  // :102-107
+        if ((int)t.size() < 3 + a.nshells) { err = "bad atom header (nctrps)"; return false; }
+        std::vector<int> nctrps_in(a.nshells);
+        for (int i = 0; i < a.nshells; ++i) nctrps_in[i] = std::atoi(t[3 + i].c_str());
+        if (!rd.next(l)) { err = "short MOL (atom coord)"; return false; }
+        std::string tmp = l; tmp.resize(std::max<size_t>(tmp.size(), 4), ' ');
+        a.symbol = tmp.substr(0, 2); a.id = tmp.substr(2, 2);                             // :111-113
+        auto ct = split_tokens(tmp.substr(4));
+        if (ct.size() < 3) { err = "bad atom coordinate line"; return false; }
+        for (int k = 0; k < 3; ++k) a.coord[k] = f2d(ct[k]);                              // :114
+        // read_segs + read_contraction2: intgrl.f90:120-147, 172-216
+        a.nctrps.assign(a.nshells, 0);
+        for (int i = 0; i < a.nshells; ++i) {
+            int nctrps = 0;
+            for (int j = 0; j < nctrps_in[i]; ++j) {
+                if (!rd.read_values(2, v)) { err = "short MOL (npf ncf)"; return false; }
+                int npf = std::atoi(v[0].c_str()), ncf = std::atoi(v[1].c_str());
+                size_t base = a.ctr.size();
+                for (int c = 0; c < ncf; ++c) {
+                    Contraction ctr; ctr.l = i; ctr.npf = npf; ctr.ncf = 1;
+                    ctr.ncomp = ncart(i); ctr.nccomp = ncart(i);                          // cartesian only (spherical=off)
+                    ctr.xp.assign(npf, 0); ctr.cc.assign(npf, 0); ctr.ncc.assign(npf, 0);
+                    a.ctr.push_back(ctr);
+                }
+                a.ctr[base].ncf = ncf;                                                    // :199
+                for (int p = 0; p < npf; ++p) {
+                    if (!rd.read_values(1 + ncf, v)) { err = "short MOL (primitive)"; return false; }
+                    double xp = f2d(v[0]);
+                    for (int c = 0; c < ncf; ++c) { a.ctr[base + c].xp[p] = xp; a.ctr[base + c].cc[p] = f2d(v[1 + c]); }
+                }
+                nctrps += ncf;
+            }
+            a.nctrps[i] = nctrps;                                                         // :145
+        }
+    }
+    return true;
+}
+
+// ---- calc_basdim: src/libgimic/basis.f90:216-249 ----------------------------
+static void calc_basdim(Molecule &mol) {
+    mol.ngto = 0; mol.ncgto = 0;
+    for (auto &a : mol.atoms) {
+        a.ncgto = 0;
+        for (auto &c : a.ctr) { mol.ngto += c.npf * c.ncomp; mol.ncgto += c.ncomp; a.ncgto += c.ncomp; }
+        a.pos.assign(a.ctr.size(), 1);
+        for (size_t k = 1; k < a.ctr.size(); ++k) a.pos[k] = a.pos[k - 1] + a.ctr[k - 1].nccomp;
+    }
+}
+
+// ---- norm_ctr: src/libgimic/basis.f90:164-191 -------------------------------
+static void norm_ctr(Contraction &ctr) {
+    double j = 1.0 * (ctr.l + 1);
+    double n = 0.0;
+    for (int l = 0; l < ctr.npf; ++l) {
+        double c1 = ctr.cc[l], e1 = ctr.xp[l];
+        for (int m = 0; m <= l; ++m) {
+            double e2 = ctr.xp[m], c2 = ctr.cc[m];
+            double t = 2.0 * std::sqrt(e1 * e2) / (e1 + e2);
+            t = c1 * c2 * std::pow(t, j + 0.5);
+            n = n + t;
+            if (l != m) n = n + t;
+        }
+    }
+    n = 1.0 / std::sqrt(n);
+    for (int l = 0; l < ctr.npf; ++l) {
+        double c1 = ctr.cc[l], e1 = ctr.xp[l];
+        ctr.ncc[l] = c1 * n * std::pow(4.0 * e1, 0.5 * j + 0.25) * std::pow(0.5 / PII, 0.75);
+    }
+}
+
+// ---- setup_screening: src/libgimic/basis.f90:90-112 -------------------------
+static void setup_screening(Atom &a, double thrs) {
+    for (auto &c : a.ctr) {
+        double min_xp = 1.e15, x = 1.e15, dist = 0.0;
+        for (int j = 0; j < c.npf; ++j) if (c.xp[j] < min_xp) min_xp = c.xp[j];
+        while (x > thrs) {
+            dist = dist + 0.25;
+            x = __builtin_powi(dist, c.l) * std::exp(-min_xp * (dist * dist));
+        }
+        c.thrs = dist;
+    }
+}
+
+// ---- new_basis (after the file is parsed): src/libgimic/basis.f90:29-86 ------
+static void finish_basis(Ctx &c, double screening /* <=0: off */) {
+    calc_basdim(c.mol);
+    for (auto &a : c.mol.atoms) for (auto &ct : a.ctr) norm_ctr(ct);
+    if (screening <= 0.0) { for (auto &a : c.mol.atoms) for (auto &ct : a.ctr) ct.thrs = 1.e10; }   // :64-68
+    else for (auto &a : c.mol.atoms) setup_screening(a, screening);                                   // :74-76
+    c.nbf = c.mol.ncgto;
+}
+
+// ---- turbo_reorder + reorder_dens: reorder.f90:54-96, dens.f90:210-234 ------
+static void turbo_reorder(const Molecule &mol, std::vector<int> &sv) {
+    int ncgto = mol.ncgto;
+    std::vector<int> lvec(ncgto);
+    int q = 0;
+    for (auto &a : mol.atoms) for (auto &c : a.ctr) for (int k = 0; k < c.ncomp; ++k) lvec[q++] = c.l;
+    sv.assign(ncgto, 0);
+    int l = 0; q = 0;
+    while (q < ncgto) {
+        for (int i = 0; i < ncgto; ++i) if (lvec[i] == l) sv[q++] = i;
+        ++l;
+    }
+}
+static void reorder_matrix(const std::vector<int> &sv, std::vector<double> &m, int n) {
+    // reorder_cols then reorder_vec on every column: new(sv(i), sv(j)) = old(i, j)
+    std::vector<double> tmp((size_t)n * n);
+    for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) tmp[(size_t)sv[i] + (size_t)n * sv[j]] = m[(size_t)i + (size_t)n * j];
+    m.swap(tmp);
+}
+
+// ---- read_dens: src/libgimic/dens.f90:56-135 --------------------------------
+static bool read_dens(Ctx &c, const std::string &fname) {
+    std::ifstream f(fname);
+    if (!f) { c.err = "Density file not found: " + fname; return false; }       // dens.f90:111-116
+    size_t n = (size_t)c.nbf, nn = n * n;
+    int nspin = c.s.is_uhf ? 2 : 1;
+    std::string tok;
+    for (int isp = 0; isp < nspin; ++isp) {
+        for (int b = 0; b < 4; ++b) {
+            std::vector<double> &d = (isp == 0 ? c.da[b] : c.db[b]);
+            d.assign(nn, 0.0);
+            for (size_t i = 0; i < nn; ++i) {                                    // read_array: dens.f90:129-135
+                if (!(f >> tok)) { c.err = "XDENS too short"; return false; }
+                d[i] = f2d(tok);
+            }
+        }
+    }
+    if (c.s.is_uhf) {                                                            // dens.f90:94-98
+        for (int b = 1; b < 4; ++b) { for (auto &x : c.da[b]) x = x / 2.0; for (auto &x : c.db[b]) x = x / 2.0; }
+    }
+    if (c.mol.is_turbomole) {                                                    // dens.f90:100-106
+        std::vector<int> sv; turbo_reorder(c.mol, sv);
+        for (int b = 0; b < 4; ++b) { reorder_matrix(sv, c.da[b], c.nbf); if (c.s.is_uhf) reorder_matrix(sv, c.db[b], c.nbf); }
+    }
+    return true;
+}
+
+// ---- cao / cao2: src/libgimic/caos.f90:67-110 -------------------------------
+static inline double cao(const Contraction &cc, double rr2) {
+    double ff = 0.0;
+    for (int i = 0; i < cc.npf; ++i) ff = ff + cc.ncc[i] * std::exp(-cc.xp[i] * rr2);
+    return ff;
+}
+static inline void cao2(const Contraction &cc, double rr2, double &vcao, double &vdcao) {
+    vcao = 0.0; vdcao = 0.0;
+    for (int i = 0; i < cc.npf; ++i) {
+        double q = cc.ncc[i] * std::exp(-cc.xp[i] * rr2);
+        vcao = vcao + q; vdcao = vdcao + cc.xp[i] * q;
+    }
+}
+// product(r**f) with real exponents (caos.f90:33,60-61); pow(0,0)=1 like Fortran 0**0.0
+static inline double rpow3(const double r[3], const double f[3]) {
+    return std::pow(r[0], f[0]) * std::pow(r[1], f[1]) * std::pow(r[2], f[2]);
+}
+// ---- cgto: caos.f90:17-37 ---------------------------------------------------
+static void cgto(const double r[3], const Contraction &ctr, const int (*nlm)[3], double *val) {
+    double rr2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double q = cao(ctr, rr2);
+    for (int i = 0; i < ctr.nccomp; ++i) {
+        double f[3] = {(double)nlm[i][0], (double)nlm[i][1], (double)nlm[i][2]};
+        val[i] = rpow3(r, f) * q;
+    }
+}
+// ---- dcgto: caos.f90:39-64 --------------------------------------------------
+static void dcgto(const double r[3], const Contraction &ctr, const int (*nlm)[3], int ax, double *val) {
+    double rr2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double bfval, dbfval;
+    cao2(ctr, rr2, bfval, dbfval);
+    for (int i = 0; i < ctr.nccomp; ++i) {
+        double f[3] = {(double)nlm[i][0], (double)nlm[i][1], (double)nlm[i][2]};
+        double df[3] = {f[0], f[1], f[2]};
+        df[ax] = df[ax] - 1.0;
+        if (df[ax] < 0.0) df[ax] = 0.0;
+        double down = f[ax] * rpow3(r, df) * bfval;
+        double up = 2.0 * r[ax] * rpow3(r, f) * dbfval;
+        val[i] = down - up;
+    }
+}
+
+static inline const int (*get_gto_nlm(const Molecule &mol, int l))[3] {   // gtodefs.f90:130-171
+    return mol.is_turbomole ? GT_TM[l] : GT_STD[l];
+}
+
+// ---- calc_basis = bfeval + dfdr + mkdbop + dfdb + d2fdrdb: bfeval.f90:61-338 -
+static void calc_basis(const Ctx &c, const double r[3], Scratch &s, bool giao) {
+    const Molecule &mol = c.mol;
+    int n = c.nbf;
+    std::fill(s.bf.begin(), s.bf.end(), 0.0);                                   // bfeval.f90:97
+    std::fill(s.dr.begin(), s.dr.end(), 0.0);                                   // :311
+    int idx2 = 0;
+    for (auto &a : mol.atoms) {
+        double rr[3] = {r[0] - a.coord[0], r[1] - a.coord[1], r[2] - a.coord[2]};
+        double r2 = std::sqrt(rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2]);   // filter_screened basis.f90:127
+        for (size_t j = 0; j < a.ctr.size(); ++j) {
+            const Contraction &ctr = a.ctr[j];
+            if (!(r2 <= ctr.thrs)) continue;                                    // basis.f90:130
+            int idx = idx2 + a.pos[j] - 1;
+            const int (*nlm)[3] = get_gto_nlm(mol, ctr.l);
+            cgto(rr, ctr, nlm, &s.bf[idx]);                                     // bfeval.f90:107
+            for (int ax = 0; ax < 3; ++ax) dcgto(rr, ctr, nlm, ax, &s.dr[idx + (size_t)n * ax]);   // :324-326
+        }
+        idx2 += a.ncgto;
+    }
+    if (!giao) return;
+    // mkdbop: bfeval.f90:168-189
+    int na = (int)mol.atoms.size();
+    for (int i = 0; i < na; ++i) {
+        const double *R = mol.atoms[i].coord;
+        s.dbop[0 + 3 * i] = (r[1] * R[2] - r[2] * R[1]);
+        s.dbop[1 + 3 * i] = (r[2] * R[0] - r[0] * R[2]);
+        s.dbop[2 + 3 * i] = (r[0] * R[1] - r[1] * R[0]);
+    }
+    // dfdb: bfeval.f90:271-293 ; d2fdrdb: bfeval.f90:191-246
+    int j = 0;
+    for (int k = 0; k < na; ++k) {
+        const Atom &a = mol.atoms[k];
+        const double *dbov = &s.dbop[3 * k];
+        double ror1 = a.coord[0], ror2 = a.coord[1], ror3 = a.coord[2];
+        for (int i = 0; i < a.ncgto; ++i, ++j) {
+            double bfv = s.bf[j];
+            for (int b = 0; b < 3; ++b) s.db[j + (size_t)n * b] = dbov[b] * bfv;
+            double d1 = s.dr[j], d2v = s.dr[j + (size_t)n], d3 = s.dr[j + (size_t)2 * n];
+            double *D2 = s.d2.data();
+            D2[j + (size_t)n * 0] = d1 * dbov[0];                 // dBx: dx
+            D2[j + (size_t)n * 1] = d2v * dbov[0] + ror3 * bfv;   //      dy
+            D2[j + (size_t)n * 2] = d3 * dbov[0] - ror2 * bfv;    //      dz
+            D2[j + (size_t)n * 3] = d1 * dbov[1] - ror3 * bfv;    // dBy
+            D2[j + (size_t)n * 4] = d2v * dbov[1];
+            D2[j + (size_t)n * 5] = d3 * dbov[1] + ror1 * bfv;
+            D2[j + (size_t)n * 6] = d1 * dbov[2] + ror2 * bfv;    // dBz
+            D2[j + (size_t)n * 7] = d2v * dbov[2] - ror1 * bfv;
+            D2[j + (size_t)n * 8] = d3 * dbov[2];
+        }
+    }
+}
+
+// out(nu) = sum_mu v(mu) * M(mu,nu)  == matmul(v, M)  (jtensor.F90:167,178,184; non-BLAS/CI orientation)
+// 4 partial sums only to let the CPU pipeline the adds; column-major M so the inner loop is contiguous.
+static void vecmat(const double *v, const double *M, int n, double *out) {
+    for (int nu = 0; nu < n; ++nu) {
+        const double *col = M + (size_t)n * nu;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0; int mu = 0;
+        for (; mu + 3 < n; mu += 4) { s0 += v[mu] * col[mu]; s1 += v[mu + 1] * col[mu + 1]; s2 += v[mu + 2] * col[mu + 2]; s3 += v[mu + 3] * col[mu + 3]; }
+        for (; mu < n; ++mu) s0 += v[mu] * col[mu];
+        out[nu] = (s0 + s1) + (s2 + s3);
+    }
+}
+static double dot(const double *a, const double *b, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0; int i = 0;
+    for (; i + 3 < n; i += 4) { s0 += a[i] * b[i]; s1 += a[i + 1] * b[i + 1]; s2 += a[i + 2] * b[i + 2]; s3 += a[i + 3] * b[i + 3]; }
+    for (; i < n; ++i) s0 += a[i] * b[i];
+    return (s0 + s1) + (s2 + s3);
+}
+
+// ---- contract: src/libgimic/jtensor.F90:148-237 -----------------------------
+// ct is column-major 3x3: ct[m + 3*b] = ct(m+1,b+1).  Optionally returns diapam (= edens).
+static void contract(const Ctx &c, Scratch &s, const double rho[3], int spin, double ct[9], double *diapam_out) {
+    int n = c.nbf;
+    const std::vector<double> *dens = (spin == 2 ? c.db : c.da);
+    vecmat(s.bf.data(), dens[0].data(), n, s.denbf.data());                      // :167
+    double diapam = dot(s.denbf.data(), s.bf.data(), n);                         // :168
+    if (diapam_out) *diapam_out = diapam;
+    double dpd[3];
+    int k = 0;
+    for (int b = 0; b < 3; ++b) {
+        vecmat(s.bf.data(), dens[b + 1].data(), n, s.pdbf.data());               // :178
+        if (c.s.use_giao) vecmat(&s.db[(size_t)n * b], dens[0].data(), n, s.dendb.data());   // :184
+        dpd[b] = diapam * rho[b];                                                // :187
+        for (int m = 0; m < 3; ++m) {
+            double prsp1 = 0.0, prsp2 = 0.0;
+            if (c.s.use_giao) {
+                prsp1 = -dot(s.dendb.data(), &s.dr[(size_t)n * m], n);           // :200
+                prsp2 = dot(s.denbf.data(), &s.d2[(size_t)n * k], n);            // :201
+            }
+            double ppd = dot(s.pdbf.data(), &s.dr[(size_t)n * m], n);            // :207
+            ct[m + 3 * b] = ZETA * ppd;                                          // :209
+            if (c.s.use_giao) ct[m + 3 * b] = ct[m + 3 * b] + ZETA * (prsp1 + prsp2);   // :210
+            ++k;
+        }
+    }
+    if (!c.s.use_paramag) for (int i = 0; i < 9; ++i) ct[i] = 0.0;               // :220-223
+    if (!c.s.use_diamag) dpd[0] = dpd[1] = dpd[2] = 0.0;                         // :225-228
+    ct[0 + 3 * 1] += dpd[2];   // ct(1,2) :230
+    ct[0 + 3 * 2] -= dpd[1];   // ct(1,3)
+    ct[1 + 3 * 0] -= dpd[2];   // ct(2,1)
+    ct[1 + 3 * 2] += dpd[0];   // ct(2,3)
+    ct[2 + 3 * 0] += dpd[1];   // ct(3,1)
+    ct[2 + 3 * 1] -= dpd[0];   // ct(3,2)
+}
+
+// ---- jtensor: jtensor.F90:105-123 -------------------------------------------
+static void jtensor(const Ctx &c, Scratch &s, const double r[3], int spin, double j[9], double *edens) {
+    double rho[3] = {0.5 * r[0], 0.5 * r[1], 0.5 * r[2]};
+    calc_basis(c, r, s, c.s.use_giao);
+    contract(c, s, rho, spin, j, edens);
+}
+
+enum SpinCase { SC_ALPHA = 0, SC_BETA = 1, SC_TOTAL = 2, SC_SPINDENS = 3 };
+static int parse_spincase(const char *op) {
+    if (!std::strcmp(op, "alpha")) return SC_ALPHA;
+    if (!std::strcmp(op, "beta")) return SC_BETA;
+    if (!std::strcmp(op, "total")) return SC_TOTAL;
+    if (!std::strcmp(op, "spindens")) return SC_SPINDENS;
+    return -1;
+}
+// ---- ctensor: jtensor.F90:66-103 --------------------------------------------
+static int ctensor(const Ctx &c, Scratch &s, const double r[3], int sc, double j[9], double *edens) {
+    double jt1[9], jt2[9], e1 = 0, e2 = 0;
+    switch (sc) {
+    case SC_ALPHA: jtensor(c, s, r, 1, j, edens); return 0;
+    case SC_BETA:
+        if (!c.s.is_uhf) return -1;                                             // :74-79
+        jtensor(c, s, r, 2, j, edens); return 0;
+    case SC_TOTAL:
+        if (c.s.is_uhf) {
+            jtensor(c, s, r, 1, jt1, &e1); jtensor(c, s, r, 2, jt2, &e2);
+            for (int i = 0; i < 9; ++i) j[i] = jt1[i] + jt2[i];
+            if (edens) *edens = e1 + e2;
+        } else jtensor(c, s, r, 1, j, edens);
+        return 0;
+    case SC_SPINDENS:
+        if (!c.s.is_uhf) return -1;                                             // :92-96
+        jtensor(c, s, r, 1, jt1, &e1); jtensor(c, s, r, 2, jt2, &e2);
+        for (int i = 0; i < 9; ++i) j[i] = jt1[i] - jt2[i];
+        if (edens) *edens = e1 - e2;
+        return 0;
+    }
+    return -1;
+}
+
+// ---- get_acid: src/libgimic/acid.f90:9-45 -----------------------------------
+static double get_acid(const double t[9]) {
+    double xxmyy = (t[0] - t[4]) * (t[0] - t[4]);
+    double yymzz = (t[4] - t[8]) * (t[4] - t[8]);
+    double zzmxx = (t[8] - t[0]) * (t[8] - t[0]);
+    double xypyx = (t[3] + t[1]) * (t[3] + t[1]);
+    double xzpzx = (t[6] + t[2]) * (t[6] + t[2]);
+    double yzpzy = (t[7] + t[5]) * (t[7] + t[5]);
+    return DP33 * (xxmyy + yymzz + zzmxx) + 0.5 * (xypyx + xzpzx + yzpzy);
+}
+
+// ---- Gauss-Legendre / Lobatto: src/libgimic/gaussint.f90 --------------------
+constexpr double GEPS = 3.0e-12;          // gaussint.f90:15
+constexpr int NEWTON_MAX_ITER = 10;       // gaussint.f90:16
+static void legendrep1(double x, int n, double &y, double &dy) {       // gaussint.f90:144-179
+    y = 1.0; dy = 0.0; if (n == 0) return;
+    y = x; dy = 1.0; if (n == 1) return;
+    double yp = 1.0, dyp = 0.0;
+    for (int i = 2; i <= n; ++i) {
+        double c1 = (double)i, c2 = c1 * 2.0 - 1.0, c4 = c1 - 1.0;
+        double ym = y;
+        y = (c2 * x * y - c4 * yp) / c1;
+        yp = ym;
+        double dym = dy;
+        dy = (c2 * x * dy - c4 * dyp + c2 * yp) / c1;
+        dyp = dym;
+    }
+}
+static void legendrep2(double x, int n, double &y, double &dy, double &d2y) {   // gaussint.f90:181-222
+    y = 1.0; dy = 0.0; d2y = 0.0; if (n == 0) return;
+    y = x; dy = 1.0; d2y = 0.0; if (n == 1) return;
+    double yp = 1.0, dyp = 0.0, d2yp = 0.0;
+    for (int i = 2; i <= n; ++i) {
+        double c1 = (double)i, c2 = c1 * 2.0 - 1.0, c4 = c1 - 1.0;
+        double ym = y;
+        y = (c2 * x * y - c4 * yp) / c1;
+        yp = ym;
+        double dym = dy;
+        dy = (c2 * x * dy - c4 * dyp + c2 * yp) / c1;
+        dyp = dym;
+        double d2ym = d2y;
+        d2y = (c2 * x * d2y - c4 * d2yp + c2 * 2.0 * dyp) / c1;
+        d2yp = d2ym;
+    }
+}
+static int gaussl(double a, double b, int n, double *pts, double *weight) {      // gaussint.f90:21-59
+    int m = (n % 2 == 0) ? n / 2 : (n + 1) / 2;
+    double xm = (b + a) * 0.5, xl = (b - a) * 0.5;
+    for (int i = 1; i <= m; ++i) {
+        double z = std::cos(PII * (double)((float)i - 0.25f) / (double)((float)n + 0.5f));   // real(4) sub-expressions
+        double lp = 0, dlp = 1, z1;
+        int iter;
+        for (iter = 1; iter <= NEWTON_MAX_ITER; ++iter) {
+            legendrep1(z, n, lp, dlp);
+            z1 = z; z = z1 - lp / dlp;
+            if (std::fabs(z - z1) <= GEPS) break;
+        }
+        if (iter >= NEWTON_MAX_ITER) return -1;                                   // :46-48
+        pts[i - 1] = xm - xl * z; pts[n - i] = xm + xl * z;
+        weight[i - 1] = 2.0 * xl / ((1.0 - z * z) * dlp * dlp); weight[n - i] = weight[i - 1];
+    }
+    return 0;
+}
+static int lobattomy(double a, double b, int n, double *pts, double *weight) {   // gaussint.f90:61-112
+    double xm = (b + a) * 0.5, xl = (b - a) * 0.5;
+    pts[0] = xm - xl; pts[n - 1] = xm + xl;
+    weight[0] = 2.0 * xl / (double)(n * n - n); weight[n - 1] = weight[0];
+    for (int i = 2; i <= n - 1; ++i) {
+        double z = std::cos(PII * (double)((float)i - 0.25f) / (double)((float)n + 0.5f));
+        double lp = 0, dlp = 0, d2lp = 1, z1;
+        int iter;
+        for (iter = 1; iter <= NEWTON_MAX_ITER; ++iter) {
+            legendrep2(z, n - 1, lp, dlp, d2lp);
+            z1 = z; z = z1 - dlp / d2lp;
+            double damp = 0.5;
+            while (std::fabs(z) > 1.0) { z = z1 - dlp / d2lp * damp; damp = damp * damp; }
+            if (std::fabs(z - z1) <= GEPS) break;
+        }
+        if (iter >= NEWTON_MAX_ITER) return -1;
+        pts[i - 1] = xm - xl * z;
+        weight[i - 1] = 2.0 * xl / ((double)(n * n - n) * lp * lp);
+    }
+    return 0;
+}
+// setup_gauss_data: gaussint.f90:267-319
+static int setup_gauss_data(double a, double b, int ngp, int npts, const char *quadr, double *pts, double *wgt) {
+    if (npts == 1) { pts[0] = 0.0; wgt[0] = 1.0; return 0; }
+    if (npts % ngp != 0) return -2;
+    int nblock = npts / ngp;
+    double step = (b - a) / (double)(float)nblock;
+    double xl = step * 0.5;
+    std::vector<double> tpts(ngp), twgt(ngp);
+    int rc;
+    if (!std::strcmp(quadr, "gauss")) rc = gaussl(-1.0, 1.0, ngp, tpts.data(), twgt.data());
+    else if (!std::strcmp(quadr, "lobatto")) rc = lobattomy(-1.0, 1.0, ngp, tpts.data(), twgt.data());
+    else return -3;
+    if (rc) return rc;
+    for (auto &t : tpts) t = t + 1.0;
+    int foo = 0;
+    for (int i = 1; i <= nblock; ++i) {
+        for (int k = 0; k < ngp; ++k) { pts[foo + k] = tpts[k] * xl + (double)(float)(i - 1) * step; wgt[foo + k] = twgt[k] * xl; }
+        foo += ngp;
+    }
+    return 0;
+}
+
+// ---- grid: src/fgimic/grid.f90 ----------------------------------------------
+struct Grid {
+    int mode = 0;                     // 0 std/base, 1 bond, 2 file
+    bool gauss = false;               // grid.f90:20
+    double basv[9] = {0};             // column-major: basv[c + 3*v] = basv(c+1, v+1)
+    double l[3] = {0, 0, 0}, origin[3] = {0, 0, 0}, ortho[3] = {0, 0, 0}, step[3] = {1, 1, 1};
+    int npts[3] = {0, 0, 0};
+    std::vector<double> pts[3], wgt[3];
+    std::vector<double> xdata;        // file grid, 3 x n
+    double radius = 0.0;              // only set by bond grids (grid.f90:199); std grids leave it undefined
+    double center_bond[3] = {0, 0, 0};  // "center" line printed by setup_bond_grid (oo)
+    std::string gtype = "even";
+    std::string err;
+};
+static void cross(const double a[3], const double b[3], double c[3]) {            // tensor.f90:40-47
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void normv(const double v[3], double n[3]) {                               // grid.f90:576-584
+    double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int i = 0; i < 3; ++i) n[i] = v[i] / l;
+}
+static void normalise(double basv[9]) {                                           // grid.f90:278-288
+    for (int i = 0; i < 3; ++i) {
+        double *v = &basv[3 * i];
+        double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (nrm > 0.0) for (int k = 0; k < 3; ++k) v[k] = v[k] / nrm;
+    }
+}
+static void ortho_coordsys(Grid &g) {                                             // grid.f90:400-428
+    double *b1 = &g.basv[0], *b2 = &g.basv[3], *b3 = &g.basv[6];
+    double dpr = b1[0] * b2[0] + b1[1] * b2[1] + b1[2] * b2[2];
+    if (std::fabs(dpr) > 1.e-10) {
+        double t[3]; cross(b1, b3, t);
+        double n = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+        for (int k = 0; k < 3; ++k) b2[k] = t[k] / n;
+        normalise(g.basv);
+    }
+}
+static void matmul33(const double A[9], const double B[9], double C[9]) {         // row-major helper
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j]; C[3 * i + j] = s; }
+}
+static void rotate(Grid &g, const double angle[3], const double ref[3]) {         // grid.f90:697-769
+    double rad[3]; for (int i = 0; i < 3; ++i) rad[i] = angle[i] / 180.0 * PII;
+    double rot[9] = {0}, euler[9] = {0}, tmp[9];
+    double x = rad[2];
+    rot[0] = std::cos(x); rot[4] = std::cos(x); rot[8] = 1.0; rot[1] = std::sin(x); rot[3] = -std::sin(x);      // z-mat (row-major [r*3+c])
+    x = rad[1];
+    euler[0] = std::cos(x); euler[4] = 1.0; euler[8] = std::cos(x); euler[2] = -std::sin(x); euler[6] = std::sin(x);  // y-mat
+    matmul33(euler, rot, tmp); std::memcpy(euler, tmp, sizeof tmp);
+    x = rad[0];
+    std::memset(rot, 0, sizeof rot);
+    rot[0] = 1.0; rot[4] = std::cos(x); rot[8] = std::cos(x); rot[5] = std::sin(x); rot[7] = -std::sin(x);       // x-mat
+    matmul33(rot, euler, tmp); std::memcpy(euler, tmp, sizeof tmp);
+    double o[3]; for (int i = 0; i < 3; ++i) o[i] = g.origin[i] - ref[i];
+    double nb[9];
+    for (int v = 0; v < 3; ++v) for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += euler[3 * i + k] * g.basv[k + 3 * v]; nb[i + 3 * v] = s; }
+    std::memcpy(g.basv, nb, sizeof nb);
+    double no[3]; for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += euler[3 * i + k] * o[k]; no[i] = s; }
+    for (int i = 0; i < 3; ++i) g.origin[i] = no[i] + ref[i];
+}
+static void setup_even_grid(Grid &g) {                                            // grid.f90:351-373
+    g.gauss = false;
+    g.npts[0] = (int)std::lround(g.l[0] / g.step[0]) + 1;
+    g.npts[1] = (int)std::lround(g.l[1] / g.step[1]) + 1;
+    if (std::fabs(g.l[2]) < 2.2250738585072014e-308 || std::fabs(g.step[2]) < 2.2250738585072014e-308) g.npts[2] = 1;
+    else g.npts[2] = (int)std::lround(g.l[2] / g.step[2]) + 1;
+    for (int n = 0; n < 3; ++n) {
+        g.pts[n].assign(g.npts[n], 0); g.wgt[n].assign(g.npts[n], 1.0);
+        for (int i = 1; i <= g.npts[n]; ++i) g.pts[n][i - 1] = (double)(float)(i - 1) * g.step[n];
+    }
+}
+// setup_gauss_grid: grid.f90:291-349.  npts_in: Grid.grid_points if have_points else from spacing
+static int setup_gauss_grid(Grid &g, const char *quadr, int order, bool have_points, const int gp[3], const double spc[3]) {
+    for (int i = 0; i < 3; ++i) {
+        if (have_points) g.npts[i] = gp[i];
+        else if (std::fabs(spc[i]) < 1.e-10 || spc[i] < 0.0) g.npts[i] = 0;
+        else g.npts[i] = (int)std::lround(g.l[i] / spc[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!(g.npts[i] > 1)) g.npts[i] = 0;
+        int rem = g.npts[i] % order;
+        if (rem != 0) g.npts[i] = g.npts[i] - rem + order;
+    }
+    g.gauss = true;
+    for (int i = 0; i < 3; ++i) {
+        int rc;
+        if (g.npts[i] > 0) {
+            g.pts[i].assign(g.npts[i], 0); g.wgt[i].assign(g.npts[i], 0);
+            rc = setup_gauss_data(0.0, g.l[i], order, g.npts[i], quadr, g.pts[i].data(), g.wgt[i].data());
+        } else {
+            g.npts[i] = 1; g.pts[i].assign(1, 0); g.wgt[i].assign(1, 0);
+            rc = setup_gauss_data(0.0, g.l[i], 1, 1, quadr, g.pts[i].data(), g.wgt[i].data());
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+static void gridpoint(const Grid &g, int i, int j, int k, double r[3]) {          // grid.f90:498-511 (1-based)
+    if (g.mode == 2) { for (int c = 0; c < 3; ++c) r[c] = g.xdata[c + 3 * (size_t)(i - 1)]; return; }
+    for (int c = 0; c < 3; ++c)
+        r[c] = g.origin[c] + g.pts[0][i - 1] * g.basv[c + 0] + g.pts[1][j - 1] * g.basv[c + 3] + g.pts[2][k - 1] * g.basv[c + 6];
+}
+static void grid_center(const Grid &g, double center[3]) {                        // grid.f90:529-541
+    double v1[3], v2[3];
+    gridpoint(g, g.npts[0], 1, 1, v1); gridpoint(g, 1, g.npts[1], 1, v2);
+    for (int c = 0; c < 3; ++c) center[c] = (v1[c] + v2[c]) * 0.5;
+}
+
+// ---- get_magnet / check_field: src/fgimic/magnet.f90:11-86 ------------------
+static int get_magnet(const Grid &g, const char *axis_in, const double magnet_in[3], double mag[3]) {
+    bool ortho = false; double dir = 1.0;
+    mag[0] = mag[1] = mag[2] = 0.0;
+    std::string axis = axis_in ? axis_in : "";
+    while (!axis.empty() && axis.back() == ' ') axis.pop_back();
+    if (!axis.empty()) {
+        if (axis[0] == '-') { dir = -1.0; axis = axis.substr(1); }
+        char a = axis.empty() ? ' ' : axis[0];
+        switch (a) {
+        case 'i': for (int c = 0; c < 3; ++c) mag[c] = g.basv[c] * dir; break;
+        case 'j': for (int c = 0; c < 3; ++c) mag[c] = g.basv[c + 3] * dir; break;
+        case 'k': for (int c = 0; c < 3; ++c) mag[c] = g.basv[c + 6] * dir; break;
+        case 'x': mag[0] = 1.0 * dir; break;
+        case 'y': mag[1] = 1.0 * dir; break;
+        case 'z': mag[2] = 1.0 * dir; break;
+        case 'X': ortho = true; for (int c = 0; c < 3; ++c) mag[c] = g.ortho[c] * dir; break;
+        default: return -1;
+        }
+    } else for (int c = 0; c < 3; ++c) mag[c] = magnet_in[c];
+    if (mag[0] == 0.0 && mag[1] == 0.0 && mag[2] == 0.0) return -2;                // :52-55
+    if (!ortho) {                                                                 // :57-60, check_field :68-77
+        double x = g.basv[6] * mag[0] + g.basv[7] * mag[1] + g.basv[8] * mag[2];
+        if (x > 0.0) for (int c = 0; c < 3; ++c) mag[c] = -mag[c];
+    }
+    return 0;
+}
+
+// ---- au2si: src/libgimic/globals.f90:309-332 --------------------------------
+static double au2si(double au) {
+    double aulength = 0.52917726e-10, auspeedoflight = 137.03599e0, speedoflight = 299792458.e0;
+    double aucharge = 1.60217733e-19, hbar = 1.05457267e-34;
+    double autime = aulength * auspeedoflight / speedoflight;
+    double autesla = hbar / aucharge / aulength / aulength;
+    double audjdb = aucharge / autime / autesla;
+    return au * audjdb * 1.e+09;
+}
+
+static inline void matvec33(const double t[9], const double b[3], double v[3]) {  // matmul(reshape(t,(3,3)), b)
+    for (int m = 0; m < 3; ++m) v[m] = t[m] * b[0] + t[m + 3] * b[1] + t[m + 6] * b[2];
+}
+
+}  // namespace
+
+// =============================================================================
+// C API (loaded with ctypes from tests/ and bench.py only)
+// =============================================================================
+extern "C" {
+
+void *go_create_from_files(const char *mol, const char *xdens, int uhf, int use_screening, double screening_thrs,
+                           int giao, int diamag, int paramag, char *errbuf, int errlen) {
+    Ctx *c = new Ctx();
+    c->s.is_uhf = uhf != 0; c->s.use_giao = giao != 0; c->s.use_diamag = diamag != 0; c->s.use_paramag = paramag != 0;
+    std::string err;
+    if (!read_intgrl(mol, c->mol, err)) { if (errbuf) std::snprintf(errbuf, errlen, "%s", err.c_str()); delete c; return nullptr; }
+    finish_basis(*c, use_screening ? screening_thrs : -1.0);                     // gimic.F90:144-148
+    if (!read_dens(*c, xdens)) { if (errbuf) std::snprintf(errbuf, errlen, "%s", c->err.c_str()); delete c; return nullptr; }
+    return c;
+}
+
+// Synthetic / in-memory construction.  Shell data are flat arrays in reference order
+// (atom -> contraction); dens_a / dens_b are 4 column-major nbf x nbf matrices each in XDENS
+// order [D, Px, Py, Pz], already in atom-major AO order (no Turbomole permutation, no UHF 1/2
+// scaling is applied here -- pass what dens.f90 would hold after read_dens).
+void *go_create_from_arrays(int natoms, const double *coords, const int *nctr_per_atom, const int *ctr_l,
+                            const int *ctr_npf, const double *xp, const double *cc, int turbomole_order,
+                            int uhf, double screening_thrs, int giao, int diamag, int paramag,
+                            const double *dens_a, const double *dens_b) {
+    Ctx *c = new Ctx();
+    c->s.is_uhf = uhf != 0; c->s.use_giao = giao != 0; c->s.use_diamag = diamag != 0; c->s.use_paramag = paramag != 0;
+    c->mol.is_turbomole = turbomole_order != 0;
+    c->mol.atoms.assign(natoms, Atom());
+    size_t ic = 0, ip = 0;
+    for (int a = 0; a < natoms; ++a) {
+        Atom &A = c->mol.atoms[a];
+        for (int k = 0; k < 3; ++k) A.coord[k] = coords[3 * a + k];
+        A.symbol = "C "; A.id = "1 ";
+        for (int j = 0; j < nctr_per_atom[a]; ++j, ++ic) {
+            Contraction ct; ct.l = ctr_l[ic]; ct.npf = ctr_npf[ic]; ct.ncomp = ct.nccomp = ncart(ct.l);
+            ct.xp.assign(xp + ip, xp + ip + ct.npf); ct.cc.assign(cc + ip, cc + ip + ct.npf); ct.ncc.assign(ct.npf, 0);
+            ip += ct.npf; A.ctr.push_back(ct);
+        }
+    }
+    finish_basis(*c, screening_thrs);
+    size_t nn = (size_t)c->nbf * c->nbf;
+    for (int b = 0; b < 4; ++b) {
+        c->da[b].assign(dens_a + nn * b, dens_a + nn * (b + 1));
+        if (uhf && dens_b) c->db[b].assign(dens_b + nn * b, dens_b + nn * (b + 1));
+    }
+    return c;
+}
+
+void go_destroy(void *h) { delete (Ctx *)h; }
+int go_nbf(void *h) { return ((Ctx *)h)->nbf; }
+int go_natoms(void *h) { return (int)((Ctx *)h)->mol.atoms.size(); }
+int go_ngto(void *h) { return ((Ctx *)h)->mol.ngto; }
+int go_is_turbomole(void *h) { return ((Ctx *)h)->mol.is_turbomole ? 1 : 0; }
+int go_nctr(void *h) { int n = 0; for (auto &a : ((Ctx *)h)->mol.atoms) n += (int)a.ctr.size(); return n; }
+int go_nprim(void *h) { int n = 0; for (auto &a : ((Ctx *)h)->mol.atoms) for (auto &c : a.ctr) n += c.npf; return n; }
+void go_atom_coords(void *h, double *out) { int i = 0; for (auto &a : ((Ctx *)h)->mol.atoms) { for (int k = 0; k < 3; ++k) out[3 * i + k] = a.coord[k]; ++i; } }
+// flat shell export (for feeding the product's create_from_arrays in tests)
+void go_export_shells(void *h, int *nctr_per_atom, int *ctr_l, int *ctr_npf, double *xp, double *cc, double *ncc, double *thrs) {
+    Ctx *c = (Ctx *)h; size_t ic = 0, ip = 0; int ia = 0;
+    for (auto &a : c->mol.atoms) {
+        nctr_per_atom[ia++] = (int)a.ctr.size();
+        for (auto &ct : a.ctr) {
+            ctr_l[ic] = ct.l; ctr_npf[ic] = ct.npf; if (thrs) thrs[ic] = ct.thrs; ++ic;
+            for (int p = 0; p < ct.npf; ++p, ++ip) { xp[ip] = ct.xp[p]; cc[ip] = ct.cc[p]; if (ncc) ncc[ip] = ct.ncc[p]; }
+        }
+    }
+}
+// dens.f90 storage after read_dens: which = 0..3, spin 1|2; column-major copy
+void go_get_density(void *h, int spin, int which, double *out) {
+    Ctx *c = (Ctx *)h; const std::vector<double> &d = (spin == 2 ? c->db[which] : c->da[which]);
+    std::copy(d.begin(), d.end(), out);
+}
+
+// basis vectors at one point: bf(nbf), dr(nbf,3), db(nbf,3), d2(nbf,9), all column-major
+void go_calc_basis(void *h, const double *r, double *bf, double *dr, double *db, double *d2) {
+    Ctx *c = (Ctx *)h; Scratch s(*c);
+    calc_basis(*c, r, s, true);
+    if (bf) std::copy(s.bf.begin(), s.bf.end(), bf);
+    if (dr) std::copy(s.dr.begin(), s.dr.end(), dr);
+    if (db) std::copy(s.db.begin(), s.db.end(), db);
+    if (d2) std::copy(s.d2.begin(), s.d2.end(), d2);
+}
+
+// calc_jtensors: src/fgimic/jfield.f90:114-129 -- OpenMP static schedule over the flat point index,
+// thread-private jtensor_t scratch.  r is 3 x n, tens 9 x n (column-major), edens n (or NULL).
+int go_ctensor(void *h, long n, const double *r, const char *spincase, double *tens, double *edens, int nthreads) {
+    Ctx *c = (Ctx *)h;
+    int sc = parse_spincase(spincase); if (sc < 0) return -1;
+    if ((sc == SC_BETA || sc == SC_SPINDENS) && !c->s.is_uhf) return -2;
+    int rc = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        Scratch s(*c);
+#pragma omp for schedule(static)
+        for (long i = 0; i < n; ++i) {
+            double e = 0;
+            if (ctensor(*c, s, &r[3 * i], sc, &tens[9 * i], &e)) rc = -3;
+            if (edens) edens[i] = e;
+        }
+    }
+    return rc;
+}
+int go_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+double go_acid(const double *t9) { return get_acid(t9); }
+double go_au2si(double au) { return au2si(au); }
+
+// compute_jvectors: jfield.f90:167-184
+void go_jvectors(long n, const double *tens, const double *b, double *vec) {
+    for (long k = 0; k < n; ++k) matvec33(&tens[9 * k], b, &vec[3 * k]);
+}
+// signed modulus: jmod2_vtkplot jfield.f90:446-489
+void go_jmod_signed(long n, const double *r, const double *vec, const double *mag, double *out) {
+    for (long k = 0; k < n; ++k) {
+        const double *v = &vec[3 * k];
+        double coord[3] = {r[3 * k], r[3 * k + 1], r[3 * k + 2]};
+        double val = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        double d = mag[0] * coord[0] + mag[1] * coord[1] + mag[2] * coord[2];
+        for (int c = 0; c < 3; ++c) coord[c] = coord[c] - d * mag[c];
+        double nrm[3]; cross(mag, coord, nrm);
+        double sgn = nrm[0] * v[0] + nrm[1] * v[1] + nrm[2] * v[2];
+        if (sgn < 0.0) val = -1.0 * val;
+        out[k] = val;
+    }
+}
+void go_acid_field(long n, const double *tens, double *out) { for (long k = 0; k < n; ++k) out[k] = get_acid(&tens[9 * k]); }
+
+// gimic_get_gauss_points: src/libgimic/gausspoints.f90:13-29 (quadr = "gauss" there)
+int go_gauss_points(double a, double b, int npts, int order, const char *quadr, double *pts, double *wgts) {
+    return setup_gauss_data(a, b, order, npts, quadr, pts, wgts);
+}
+
+// ---- grids -------------------------------------------------------------------
+void *go_grid_file(long n, const double *xyz) {                                  // extgrid grid.f90:543-576
+    Grid *g = new Grid(); g->mode = 2; g->gtype = "file";
+    g->xdata.assign(xyz, xyz + 3 * n); g->npts[0] = (int)n; g->npts[1] = 1; g->npts[2] = 1;
+    for (int i = 0; i < 3; ++i) g->step[i] = 0.0;
+    return g;
+}
+static int finish_grid(Grid *g, const char *type, int gauss_order, int have_points, const int *grid_points,
+                       int have_spacing, const double *spacing, int have_rotation, const double *rotation,
+                       int have_rot_origin, const double *rot_origin, double out_len, double down_len) {
+    normalise(g->basv);                                                           // grid.f90:88
+    ortho_coordsys(*g);                                                           // :89
+    if (have_rotation) {                                                          // :92-114
+        double ref[3];
+        if (have_rot_origin) for (int c = 0; c < 3; ++c) ref[c] = rot_origin[c];
+        else for (int c = 0; c < 3; ++c) ref[c] = g->origin[c] + out_len * g->basv[c + 3] + down_len * g->basv[c + 0];
+        rotate(*g, rotation, ref);
+    }
+    g->gtype = type;
+    if (!std::strcmp(type, "even")) {
+        setup_even_grid(*g);
+    } else if (!std::strcmp(type, "gauss") || !std::strcmp(type, "lobatto")) {
+        int gp[3] = {0, 0, 0}; double sp[3] = {0, 0, 0};
+        if (have_points) for (int i = 0; i < 3; ++i) gp[i] = grid_points[i];
+        if (have_spacing) for (int i = 0; i < 3; ++i) sp[i] = spacing[i];
+        int rc = setup_gauss_grid(*g, type, gauss_order, have_points != 0, gp, sp);
+        if (rc) return rc;
+    } else return -9;
+    return 0;
+}
+// setup_std_grid: grid.f90:140-163
+void *go_grid_std(const double *origin, const double *ivec, const double *jvec, const double *lengths,
+                  const char *type, int gauss_order, int have_points, const int *grid_points,
+                  int have_spacing, const double *spacing, int have_rotation, const double *rotation,
+                  int have_rot_origin, const double *rot_origin) {
+    Grid *g = new Grid(); g->mode = 0;
+    for (int c = 0; c < 3; ++c) { g->origin[c] = origin[c]; g->basv[c] = ivec[c]; g->basv[c + 3] = jvec[c]; g->l[c] = lengths[c]; }
+    if (have_spacing) for (int c = 0; c < 3; ++c) g->step[c] = spacing[c];
+    else for (int c = 0; c < 3; ++c) g->step[c] = g->l[c] / (double)(grid_points[c] - 1);
+    cross(&g->basv[0], &g->basv[3], &g->basv[6]);
+    normv(&g->basv[6], g->ortho);
+    // rotation reference for std grids uses Grid.out/Grid.down (0 by default in the schema)
+    if (finish_grid(g, type, gauss_order, have_points, grid_points, have_spacing, spacing, have_rotation, rotation,
+                    have_rot_origin, rot_origin, 0.0, 0.0)) { delete g; return nullptr; }
+    return g;
+}
+// setup_bond_grid: grid.f90:165-276.  c1,c2 = bond atom coordinates (or coord1/coord2), fix = fixpoint coordinate.
+// hgt/wdt as given by Grid.height / Grid.width (use_hw=1) or up,down / in,out (use_hw=0).
+void *go_grid_bond(const double *c1, const double *c2, const double *fix, double distance,
+                   int use_hw, const double *hgt_in, const double *wdt_in, int have_radius, double radius,
+                   int have_magnet, const double *magnet,
+                   const char *type, int gauss_order, int have_points, const int *grid_points,
+                   int have_spacing, const double *spacing, int have_rotation, const double *rotation,
+                   int have_rot_origin, const double *rot_origin) {
+    Grid *g = new Grid(); g->mode = 1;
+    for (int c = 0; c < 3; ++c) { g->basv[c] = c1[c]; g->basv[c + 3] = c2[c]; g->origin[c] = fix[c]; }
+    g->radius = (double)1.e10f;                                                   // grid.f90:199 (real(4) literal 1.e10)
+    if (have_radius) g->radius = radius;
+    double hgt[2] = {hgt_in[0], hgt_in[1]}, wdt[2] = {wdt_in[0], wdt_in[1]};
+    if (use_hw) { hgt[0] = -hgt[0]; wdt[0] = -wdt[0]; }                           // :212-213
+    g->l[0] = hgt[0] + hgt[1]; g->l[1] = wdt[0] + wdt[1]; g->l[2] = 0.0;          // :220
+    double v1[3], v2[3], v3[3], oo[3], t[3];
+    for (int c = 0; c < 3; ++c) { v1[c] = g->basv[c] - g->origin[c]; v2[c] = g->basv[c + 3] - g->origin[c]; }   // :233-234
+    cross(v1, v2, g->ortho);
+    if (g->ortho[0] == 0.0 && g->ortho[1] == 0.0 && g->ortho[2] == 0.0) { delete g; return nullptr; }
+    normv(g->ortho, g->ortho);
+    for (int c = 0; c < 3; ++c) t[c] = v2[c] - v1[c];
+    normv(t, v3);                                                                 // :243
+    for (int c = 0; c < 3; ++c) v1[c] = -g->ortho[c];
+    cross(v3, v1, t); normv(t, v2);
+    for (int c = 0; c < 3; ++c) oo[c] = g->basv[c] + distance * v3[c];            // :246
+    for (int c = 0; c < 3; ++c) g->origin[c] = oo[c] - wdt[1] * v2[c] - hgt[1] * v1[c];
+    for (int c = 0; c < 3; ++c) { g->basv[c] = v1[c]; g->basv[c + 3] = v2[c]; g->basv[c + 6] = v3[c]; g->center_bond[c] = oo[c]; }
+    if (have_magnet) normv(magnet, g->ortho);                                     // :253-256
+    // rotation reference: height(2)/width(2) if height given, else out/down (grid.f90:101-110)
+    double down_len = hgt_in[1], out_len = wdt_in[1];
+    if (finish_grid(g, type, gauss_order, have_points, grid_points, have_spacing, spacing, have_rotation, rotation,
+                    have_rot_origin, rot_origin, out_len, down_len)) { delete g; return nullptr; }
+    return g;
+}
+void go_grid_destroy(void *g) { delete (Grid *)g; }
+void go_grid_npts(void *gv, int *npts) { Grid *g = (Grid *)gv; for (int i = 0; i < 3; ++i) npts[i] = g->npts[i]; }
+void go_grid_geometry(void *gv, double *origin, double *basv, double *lengths, double *ortho, double *center_bond, double *radius) {
+    Grid *g = (Grid *)gv;
+    for (int i = 0; i < 3; ++i) { origin[i] = g->origin[i]; lengths[i] = g->l[i]; ortho[i] = g->ortho[i]; center_bond[i] = g->center_bond[i]; }
+    for (int i = 0; i < 9; ++i) basv[i] = g->basv[i];
+    *radius = g->radius;
+}
+void go_grid_axis(void *gv, int d, double *pts, double *wgt) {
+    Grid *g = (Grid *)gv; if (g->mode == 2) return;
+    std::copy(g->pts[d].begin(), g->pts[d].end(), pts); std::copy(g->wgt[d].begin(), g->wgt[d].end(), wgt);
+}
+// all points in the flat order of calc_jtensors (get_grid_index grid.f90:478-495: i fastest)
+void go_grid_points(void *gv, double *r) {
+    Grid *g = (Grid *)gv; long n = 0;
+    for (int k = 1; k <= g->npts[2]; ++k) for (int j = 1; j <= g->npts[1]; ++j) for (int i = 1; i <= g->npts[0]; ++i) { gridpoint(*g, i, j, k, &r[3 * n]); ++n; }
+}
+void go_grid_center(void *gv, double *center) { grid_center(*(Grid *)gv, center); }
+int go_get_magnet(void *gv, const char *axis, const double *magnet_in, double *mag) { return get_magnet(*(Grid *)gv, axis, magnet_in, mag); }
+
+// ---- integrals: src/fgimic/integral.f90 --------------------------------------
+// what: 0 integrate_current (:50-186), 1 integrate_modulus (:190-324), 2 integrate_acid (:414-511)
+// out[0..2] = xsum3, psum3, nsum3 (acid: out[0] = sqrt(xsum3), out[1] = xsum3)
+int go_integrate(void *h, void *gv, const double *bb, const char *spincase, int what, double *out, int nthreads) {
+    Ctx *c = (Ctx *)h; Grid *g = (Grid *)gv;
+    int sc = parse_spincase(spincase); if (sc < 0) return -1;
+    if ((sc == SC_BETA || sc == SC_SPINDENS) && !c->s.is_uhf) return -2;
+    int p1 = g->npts[0], p2 = g->npts[1], p3 = g->npts[2];
+    double normal[3] = {g->basv[6], g->basv[7], g->basv[8]};                      // get_grid_normal grid.f90:522-527
+    double bound = g->radius, center[3];
+    grid_center(*g, center);
+    double xsum3 = 0, psum3 = 0, nsum3 = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    for (int k = 1; k <= p3; ++k) {
+        double xsum2 = 0, psum2 = 0, nsum2 = 0;
+#pragma omp parallel reduction(+ : xsum2, psum2, nsum2)
+        {
+            Scratch s(*c);
+            double sgn = 1.0, jp = 0.0;
+#pragma omp for
+            for (int j = 1; j <= p2; ++j) {
+                double xsum = 0, psum = 0, nsum = 0;
+                for (int i = 1; i <= p1; ++i) {
+                    double rr[3], tt[9], jvec[3], w;
+                    gridpoint(*g, i, j, k, rr);
+                    double r = std::sqrt((rr[0] - center[0]) * (rr[0] - center[0]) + (rr[1] - center[1]) * (rr[1] - center[1]) + (rr[2] - center[2]) * (rr[2] - center[2]));
+                    ctensor(*c, s, rr, sc, tt, nullptr);
+                    if (what == 0) {
+                        matvec33(tt, bb, jvec);
+                        if (r > bound) { w = 0.0; jp = 0.0; }
+                        else { w = g->wgt[0][i - 1]; jp = (normal[0] * jvec[0] + normal[1] * jvec[1] + normal[2] * jvec[2]) * w; }
+                        xsum = xsum + jp;
+                        if (jp > 0.0) psum = psum + jp; else nsum = nsum + jp;
+                    } else if (what == 1) {
+                        matvec33(tt, bb, jvec);
+                        if (r > bound) w = 0.0;
+                        else {
+                            w = g->wgt[0][i - 1];
+                            jp = normal[0] * jvec[0] + normal[1] * jvec[1] + normal[2] * jvec[2];
+                            if (std::fabs(jp) < 1.e-12) sgn = 0.0; else if (jp > 0) sgn = 1.0; else sgn = -1.0;
+                        }
+                        jp = sgn * std::sqrt(jvec[0] * jvec[0] + jvec[1] * jvec[1] + jvec[2] * jvec[2]);
+                        xsum = xsum + jp * w;
+                        if (jp > 0.0) psum = psum + jp * w; else nsum = nsum + jp * w;
+                    } else {
+                        double val = get_acid(tt);
+                        if (r > bound) w = 0.0; else w = g->wgt[0][i - 1];
+                        xsum = xsum + val * w;
+                    }
+                }
+                double w = g->wgt[1][j - 1];
+                xsum2 = xsum2 + xsum * w; psum2 = psum2 + psum * w; nsum2 = nsum2 + nsum * w;
+            }
+        }
+        double w = g->wgt[2][k - 1];
+        xsum3 = xsum3 + w * xsum2; psum3 = psum3 + w * psum2; nsum3 = nsum3 + w * nsum2;
+    }
+    if (what == 2) { out[0] = std::sqrt(xsum3); out[1] = xsum3; out[2] = 0.0; }
+    else { out[0] = xsum3; out[1] = psum3; out[2] = nsum3; }
+    return 0;
+}
+
+}  // extern "C"
