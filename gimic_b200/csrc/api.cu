@@ -1,0 +1,651 @@
+// Context management, batching driver and the C ABI of libgimic_b200.so (see include/gimic_b200.h).
+//
+// There is deliberately no CPU fallback: every compute entry point fails with GIMIC_B200_ECUDA when
+// no CUDA device / kernel image is available.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gimic_b200.h"
+#include "host_basis.hpp"
+#include "kernels.cuh"
+
+namespace gb { void upload_component_tables(const signed char *host_tab); }
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(GIMIC_B200_ECUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")"); \
+    } while (0)
+
+struct Buf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; } want = bytes; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct gimic_b200_ctx {
+    int device = 0, nsm = 148;
+    cudaStream_t stream = nullptr;
+    gimic_b200_opts opts{};
+    gb::HostBasis hb;
+    gb::DevBasis db{};
+    std::vector<void *> owned;
+    int *d_f2user = nullptr;
+    double *d_dens[2] = {nullptr, nullptr};   // dens_t%da / %db in the XDENS layout
+    double *d_op[4] = {nullptr, nullptr, nullptr, nullptr};   // contraction operands per spin case
+    int nq = 7, ldb = 0; long long plane_stride = 0;
+    double bbox_lo[3] = {0, 0, 0}; double inv_cell = 1.0;
+    size_t pool_max_bytes = (size_t)2 << 30;
+    // workspaces
+    Buf keys0, keys1, vals0, vals1, sorttmp, rs, geo, nraw, tiles, panel, fidx, misc, r_in, tens_tmp, f_tmp, shift, jv6, gridbuf, quad;
+    int *h_nraw = nullptr; size_t h_nraw_cap = 0;
+    gb::TileDesc *h_tiles = nullptr; size_t h_tiles_cap = 0;
+    bool profiling = false;
+    cudaEvent_t ev[6] = {};
+    gimic_b200_stats stats{};
+    std::string mol_path, xdens_path;   // for the legacy set_uhf-after-init path
+
+    ~gimic_b200_ctx() {
+        cudaSetDevice(device);
+        for (void *p : owned) cudaFree(p);
+        for (int i = 0; i < 2; ++i) if (d_dens[i]) cudaFree(d_dens[i]);
+        for (int i = 0; i < 4; ++i) if (d_op[i]) cudaFree(d_op[i]);
+        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &tiles, &panel, &fidx, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
+        if (h_nraw) cudaFreeHost(h_nraw);
+        if (h_tiles) cudaFreeHost(h_tiles);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+template <typename T>
+int upload(gimic_b200_ctx *c, const std::vector<T> &v, const T **out) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    c->owned.push_back(p);
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T *>(p);
+    return 0;
+}
+
+// Builds the device tables: shells re-ordered inside each atom by descending screening radius so
+// that a tile's active set is a per-atom prefix; functions keep their atom but follow the shells.
+int build_device_basis(gimic_b200_ctx *c) {
+    const gb::HostBasis &hb = c->hb;
+    std::vector<int> order;   // internal shell order -> reference shell index
+    std::vector<int> atom_shell_off(1, 0), atom_func_off(1, 0);
+    for (int a = 0; a < hb.natoms; ++a) {
+        std::vector<int> idx;
+        for (int s = hb.atom_shell_off[a]; s < hb.atom_shell_off[a + 1]; ++s) idx.push_back(s);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return hb.shells[x].thr > hb.shells[y].thr; });
+        order.insert(order.end(), idx.begin(), idx.end());
+        atom_shell_off.push_back((int)order.size());
+        atom_func_off.push_back(hb.atom_func_off[a + 1]);
+    }
+    const int ns = (int)order.size();
+    std::vector<int> sh_l(ns), sh_np(ns), sh_po(ns), sh_foff(ns), f2user(hb.nbf);
+    std::vector<double> sh_thr(ns), maxthr(hb.natoms, 0.0), fR(3 * (size_t)hb.nbf);
+    int f = 0;
+    for (int i = 0; i < ns; ++i) {
+        const gb::Shell &s = hb.shells[order[i]];
+        sh_l[i] = s.l; sh_np[i] = s.nprim; sh_po[i] = s.prim_off; sh_thr[i] = s.thr; sh_foff[i] = f;
+        maxthr[s.atom] = std::max(maxthr[s.atom], s.thr);
+        for (int k = 0; k < s.ncomp; ++k, ++f) {
+            f2user[f] = s.user_off + k;
+            for (int d = 0; d < 3; ++d) fR[(size_t)d * hb.nbf + f] = hb.xyz[3 * s.atom + d];
+        }
+    }
+    gb::DevBasis &d = c->db;
+    d.natoms = hb.natoms; d.nbf = hb.nbf; d.nshell = ns; d.turbomole = hb.turbomole ? 1 : 0;
+    if (int rc = upload(c, hb.xyz, &d.atom_xyz)) return rc;
+    if (int rc = upload(c, maxthr, &d.atom_maxthr)) return rc;
+    if (int rc = upload(c, atom_shell_off, &d.atom_shell_off)) return rc;
+    if (int rc = upload(c, atom_func_off, &d.atom_func_off)) return rc;
+    if (int rc = upload(c, sh_l, &d.sh_l)) return rc;
+    if (int rc = upload(c, sh_np, &d.sh_nprim)) return rc;
+    if (int rc = upload(c, sh_po, &d.sh_prim_off)) return rc;
+    if (int rc = upload(c, sh_foff, &d.sh_foff)) return rc;
+    if (int rc = upload(c, sh_thr, &d.sh_thr)) return rc;
+    if (int rc = upload(c, hb.alpha, &d.alpha)) return rc;
+    if (int rc = upload(c, hb.ncc, &d.ncc)) return rc;
+    if (int rc = upload(c, fR, &d.fR)) return rc;
+    const int *f2u = nullptr;
+    if (int rc = upload(c, f2user, &f2u)) return rc;
+    c->d_f2user = const_cast<int *>(f2u);
+
+    signed char tab[2][6][21][3];
+    std::memset(tab, 0, sizeof tab);
+    for (int tm = 0; tm < 2; ++tm)
+        for (int l = 0; l <= gb::MAX_L; ++l)
+            for (int k = 0; k < (l + 1) * (l + 2) / 2; ++k) {
+                int lmn[3]; gb::component_exponents(l, tm != 0, k, lmn);
+                for (int x = 0; x < 3; ++x) tab[tm][l][k][x] = (signed char)lmn[x];
+            }
+    gb::upload_component_tables(&tab[0][0][0][0]);
+    CUDA_TRY(cudaGetLastError());
+
+    // Morton quantisation box: molecule +- 24 bohr (beyond every screening radius in practice; farther points clamp)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int a = 0; a < hb.natoms; ++a)
+        for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], hb.xyz[3 * a + k]); hi[k] = std::max(hi[k], hb.xyz[3 * a + k]); }
+    double ext = 0;
+    for (int k = 0; k < 3; ++k) { c->bbox_lo[k] = lo[k] - 24.0; ext = std::max(ext, hi[k] - lo[k] + 48.0); }
+    c->inv_cell = 1048576.0 / ext;
+    return 0;
+}
+
+int init_device(gimic_b200_ctx *c) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(GIMIC_B200_ECUDA, "no CUDA device available: gimic-b200 has no CPU path");
+    }
+    if (c->opts.device >= 0) c->device = c->opts.device; else CUDA_TRY(cudaGetDevice(&c->device));
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    c->nsm = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    if (const char *mb = std::getenv("GIMIC_B200_POOL_MB")) { long v = std::atol(mb); if (v > 0) c->pool_max_bytes = (size_t)v << 20; }
+    return 0;
+}
+
+int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
+    const bool uhf = c->opts.uhf != 0;
+    if (!uhf) {
+        if (spincase == GIMIC_B200_BETA) return fail(GIMIC_B200_ESPIN, "ctensor(): beta current requested, but not open-shell system!");
+        if (spincase == GIMIC_B200_SPINDENS) return fail(GIMIC_B200_ESPIN, "ctensor(): spindens requested, but not open-shell system!");
+        spincase = GIMIC_B200_ALPHA;
+    }
+    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
+    if (!c->d_op[spincase]) {
+        const int nbf = c->hb.nbf;
+        void *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, (size_t)c->nq * c->plane_stride * sizeof(double)));
+        const double *A = c->d_dens[0], *Bm = nullptr; double sg = 0.0;
+        if (spincase == GIMIC_B200_BETA) A = c->d_dens[1];
+        if (spincase == GIMIC_B200_TOTAL) { Bm = c->d_dens[1]; sg = 1.0; }       // T_alpha + T_beta (jtensor.F90:86-88), by linearity in D, P
+        if (spincase == GIMIC_B200_SPINDENS) { Bm = c->d_dens[1]; sg = -1.0; }   // T_alpha - T_beta (jtensor.F90:97-99)
+        gb::launch_build_operand((double *)p, nbf, c->ldb, c->plane_stride, A, Bm, sg, c->d_f2user, c->db.fR, c->opts.giao != 0, c->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->d_op[spincase] = (double *)p;
+    }
+    *op = c->d_op[spincase];
+    return 0;
+}
+
+int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b, bool dens_on_device) {
+    gb::finalize_basis(c->hb, c->opts.screening != 0, c->opts.screening_thrs);
+    if (int rc = build_device_basis(c)) return rc;
+    const size_t nn = (size_t)c->hb.nbf * c->hb.nbf;
+    c->nq = c->opts.giao ? gb::NQ_GIAO : gb::NQ_NOGIAO;
+    c->ldb = c->hb.nbf;
+    c->plane_stride = (long long)c->hb.nbf * c->ldb;
+    for (int sp = 0; sp < (c->opts.uhf ? 2 : 1); ++sp) {
+        const double *src = sp ? dens_b : dens_a;
+        if (!src) return fail(GIMIC_B200_EINVAL, sp ? "open-shell context needs beta densities" : "densities missing");
+        CUDA_TRY(cudaMalloc((void **)&c->d_dens[sp], 4 * nn * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(c->d_dens[sp], src, 4 * nn * sizeof(double), dens_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ---- the batched tensor pipeline ------------------------------------------------------------------
+// d_r: device, 3 x n (AoS).  d_tens: device 9 x n.  d_edens: device n or null.
+int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, double *d_tens, double *d_edens) {
+    using namespace gb;
+    if (n <= 0) return 0;
+    if (n > 2000000000L) return fail(GIMIC_B200_EINVAL, "more than 2e9 points in one call");
+    const double *op = nullptr;
+    if (int rc = get_operand(c, spincase, &op)) return rc;
+    cudaStream_t st = c->stream;
+    const long ntiles_l = (n + MT - 1) / MT;
+    const int ntiles = (int)ntiles_l;
+    const bool prof = c->profiling;
+
+    if (c->keys0.ensure(n * 8) || c->keys1.ensure(n * 8) || c->vals0.ensure(n * 4) || c->vals1.ensure(n * 4) ||
+        c->rs.ensure((size_t)3 * n * 8) || c->geo.ensure((size_t)ntiles * sizeof(TileGeo)) || c->nraw.ensure((size_t)ntiles * 4) ||
+        c->tiles.ensure((size_t)ntiles * sizeof(TileDesc)) || c->misc.ensure(256))
+        return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed");
+    size_t tb = sort_temp_bytes(n);
+    if (c->sorttmp.ensure(tb)) return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (sort)");
+    if ((size_t)ntiles > c->h_nraw_cap) {
+        if (c->h_nraw) cudaFreeHost(c->h_nraw);
+        if (c->h_tiles) cudaFreeHost(c->h_tiles);
+        c->h_nraw_cap = (size_t)ntiles + ntiles / 8 + 64;
+        CUDA_TRY(cudaMallocHost((void **)&c->h_nraw, c->h_nraw_cap * sizeof(int)));
+        CUDA_TRY(cudaMallocHost((void **)&c->h_tiles, c->h_nraw_cap * sizeof(TileDesc)));
+    }
+    double *rsx = c->rs.as<double>(), *rsy = rsx + n, *rsz = rsy + n;
+    int *perm = c->vals1.as<int>();
+
+    if (prof) cudaEventRecord(c->ev[0], st);
+    launch_morton_keys(d_r, n, c->bbox_lo, c->inv_cell, c->keys0.as<uint64_t>(), c->vals0.as<int>(), st);
+    launch_sort_pairs(c->sorttmp.p, tb, c->keys0.as<uint64_t>(), c->keys1.as<uint64_t>(), c->vals0.as<int>(), perm, n, st);
+    launch_gather_points(d_r, perm, n, rsx, rsy, rsz, st);
+    if (prof) cudaEventRecord(c->ev[1], st);
+    launch_tile_count(c->db, rsx, rsy, rsz, n, ntiles, c->geo.as<TileGeo>(), c->nraw.as<int>(), st);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_nraw, c->nraw.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, st));
+    if (prof) cudaEventRecord(c->ev[2], st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->stats.launches += 5;
+
+    // host: tile descriptors, split into batches that fit the panel pool
+    size_t max_tile = 0, total = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        int nact = (c->h_nraw[t] + 15) / 16 * 16;
+        size_t d = (size_t)4 * nact * LDP;
+        max_tile = std::max(max_tile, d); total += d;
+    }
+    size_t pool_doubles = std::max(max_tile, std::min(total, c->pool_max_bytes / 8));
+    std::vector<int> batch_start(1, 0);
+    size_t off = 0, foff = 0, fidx_max = 0;
+    double sum_nact = 0, flops = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        TileDesc &td = c->h_tiles[t];
+        td.pt0 = t * MT; td.npts = (int)std::min<long>(MT, n - (long)t * MT);
+        td.nraw = c->h_nraw[t]; td.nact = (td.nraw + 15) / 16 * 16;
+        size_t d = (size_t)4 * td.nact * LDP;
+        if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); off = 0; foff = 0; }
+        td.panel_off = (long long)off; td.fidx_off = (long long)foff;
+        off += d; foff += td.nact;
+        sum_nact += td.nact; flops += 2.0 * MT * c->nq * (double)td.nact * td.nact;
+    }
+    fidx_max = std::max(fidx_max, foff);
+    batch_start.push_back(ntiles);
+    if (c->panel.ensure(std::max<size_t>(pool_doubles, 2) * 8) || c->fidx.ensure(std::max<size_t>(fidx_max, 1) * 4))
+        return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
+    CUDA_TRY(cudaMemcpyAsync(c->tiles.p, c->h_tiles, (size_t)ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+
+    float ms_basis = 0, ms_contract = 0;
+    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
+        const int t0 = batch_start[b], nb = batch_start[b + 1] - t0;
+        if (nb <= 0) continue;
+        if (prof) cudaEventRecord(c->ev[3], st);
+        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(), st);
+        if (prof) cudaEventRecord(c->ev[4], st);
+        CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
+        JtensorArgs a;
+        a.tiles = c->tiles.as<TileDesc>() + t0; a.ntiles = nb; a.counter = c->misc.as<int>();
+        a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>();
+        a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
+        a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = perm; a.tens = d_tens; a.edens = d_edens;
+        a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
+        launch_jtensor(a, c->opts.giao != 0, c->nsm, st);
+        CUDA_TRY(cudaGetLastError());
+        c->stats.launches += 2;
+        if (prof) {
+            cudaEventRecord(c->ev[5], st);
+            CUDA_TRY(cudaEventSynchronize(c->ev[5]));
+            float m1 = 0, m2 = 0;
+            cudaEventElapsedTime(&m1, c->ev[3], c->ev[4]); cudaEventElapsedTime(&m2, c->ev[4], c->ev[5]);
+            ms_basis += m1; ms_contract += m2;
+        }
+    }
+    if (prof) {
+        float m = 0;
+        cudaEventElapsedTime(&m, c->ev[0], c->ev[1]); c->stats.ms_sort += m;
+        cudaEventElapsedTime(&m, c->ev[1], c->ev[2]); c->stats.ms_tiles += m;
+        c->stats.ms_basis += ms_basis; c->stats.ms_contract += ms_contract;
+    }
+    c->stats.n_points += n; c->stats.n_tiles += ntiles; c->stats.sum_nact += sum_nact; c->stats.executed_flops += flops;
+    const double nbf = c->hb.nbf;
+    c->stats.dense_flops += (double)n * (c->opts.giao ? 14.0 * nbf * nbf + 56.0 * nbf : 8.0 * nbf * nbf + 20.0 * nbf);
+    return 0;
+}
+
+void reset_stats(gimic_b200_ctx *c) { c->stats = gimic_b200_stats{}; }
+
+// host<->device staging helpers --------------------------------------------------------------------
+int stage_in(gimic_b200_ctx *c, Buf &b, const double *src, size_t count, int flags, const double **dev) {
+    if (flags & GIMIC_B200_DEVICE_PTR) { *dev = src; return 0; }
+    if (b.ensure(std::max<size_t>(count, 1) * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (input staging)");
+    CUDA_TRY(cudaMemcpyAsync(b.p, src, count * 8, cudaMemcpyHostToDevice, c->stream));
+    *dev = b.as<double>();
+    return 0;
+}
+
+int grid_upload(gimic_b200_ctx *c, const gimic_b200_grid *g, const double **ob, const double **p0, const double **p1, const double **p2,
+                const double **w0) {
+    const long n0 = g->npts[0], n1 = g->npts[1], n2 = g->npts[2];
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) return fail(GIMIC_B200_EINVAL, "grid with no points");
+    std::vector<double> h(12 + 2 * n0 + n1 + n2);
+    for (int i = 0; i < 3; ++i) h[i] = g->origin[i];
+    for (int i = 0; i < 9; ++i) h[3 + i] = g->basv[i];
+    for (long i = 0; i < n0; ++i) { h[12 + i] = g->pts[0][i]; h[12 + n0 + n1 + n2 + i] = g->wgt[0] ? g->wgt[0][i] : 1.0; }
+    for (long i = 0; i < n1; ++i) h[12 + n0 + i] = g->pts[1][i];
+    for (long i = 0; i < n2; ++i) h[12 + n0 + n1 + i] = g->pts[2][i];
+    if (c->gridbuf.ensure(h.size() * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid)");
+    CUDA_TRY(cudaMemcpyAsync(c->gridbuf.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // h goes out of scope
+    const double *d = c->gridbuf.as<double>();
+    *ob = d; *p0 = d + 12; *p1 = d + 12 + n0; *p2 = d + 12 + n0 + n1; *w0 = d + 12 + n0 + n1 + n2;
+    return 0;
+}
+
+}  // namespace
+
+// ===================================================================================================
+extern "C" {
+
+const char *gimic_b200_last_error(void) { return g_err.c_str(); }
+const char *gimic_b200_version(void) { return "gimic-b200 0.1 (sm_100a)"; }
+
+void gimic_b200_default_opts(gimic_b200_opts *o) {
+    if (!o) return;
+    o->uhf = 0; o->giao = 1; o->diamag = 1; o->paramag = 1; o->screening = 1;
+    o->screening_thrs = 1e-6;   // SCREEN_THRS, globals.f90:56 (gimic_interface.f90:41)
+    o->device = -1; o->reserved = 0;
+}
+
+int gimic_b200_create(gimic_b200_handle *h, const char *mol, const char *xdens, const gimic_b200_opts *opts) {
+    if (!h || !mol || !xdens) return fail(GIMIC_B200_EINVAL, "null argument");
+    *h = nullptr;
+    gimic_b200_ctx *c = new gimic_b200_ctx();
+    if (opts) c->opts = *opts; else gimic_b200_default_opts(&c->opts);
+    c->mol_path = mol; c->xdens_path = xdens;
+    std::string err;
+    if (!gb::parse_mol(mol, c->hb, err)) { delete c; return fail(GIMIC_B200_EIO, err); }
+    const int nbf = c->hb.nbf, nmat = c->opts.uhf ? 8 : 4;
+    std::vector<double> dens;
+    if (!gb::read_xdens(xdens, nbf, nmat, dens, err)) { delete c; return fail(GIMIC_B200_EIO, err); }
+    const size_t nn = (size_t)nbf * nbf;
+    if (c->opts.uhf)   // "scaling perturbed densities by 0.5", dens.f90:94-98
+        for (int sp = 0; sp < 2; ++sp) for (int b = 1; b < 4; ++b) { double *m = &dens[(sp * 4 + b) * nn]; for (size_t i = 0; i < nn; ++i) m[i] /= 2.0; }
+    if (c->hb.turbomole) {   // reorder_dens, dens.f90:100-106,210-234: new(sv(i),sv(j)) = old(i,j)
+        std::vector<int> sv; gb::turbomole_permutation(c->hb, sv);
+        std::vector<double> tmp(nn);
+        for (int m = 0; m < nmat; ++m) {
+            double *src = &dens[m * nn];
+            for (int j = 0; j < nbf; ++j) for (int i = 0; i < nbf; ++i) tmp[(size_t)sv[i] + (size_t)nbf * sv[j]] = src[(size_t)i + (size_t)nbf * j];
+            std::copy(tmp.begin(), tmp.end(), src);
+        }
+    }
+    int rc = init_device(c);
+    if (!rc) rc = finish_create(c, dens.data(), c->opts.uhf ? dens.data() + 4 * nn : nullptr, false);
+    if (rc) { delete c; return rc; }
+    *h = c;
+    return 0;
+}
+
+int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double *coords, const int *nctr_per_atom, const int *ctr_l,
+                                  const int *ctr_npf, const double *xp, const double *cc, int turbomole_order, const double *dens_alpha,
+                                  const double *dens_beta, int dens_flags, const gimic_b200_opts *opts) {
+    if (!h || !coords || !nctr_per_atom || !ctr_l || !ctr_npf || !xp || !cc || !dens_alpha) return fail(GIMIC_B200_EINVAL, "null argument");
+    *h = nullptr;
+    gimic_b200_ctx *c = new gimic_b200_ctx();
+    if (opts) c->opts = *opts; else gimic_b200_default_opts(&c->opts);
+    std::string err;
+    if (!gb::basis_from_arrays(natoms, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, turbomole_order, c->hb, err)) { delete c; return fail(GIMIC_B200_EINVAL, err); }
+    int rc = init_device(c);
+    if (!rc) rc = finish_create(c, dens_alpha, dens_beta, (dens_flags & GIMIC_B200_DEVICE_PTR) != 0);
+    if (rc) { delete c; return rc; }
+    *h = c;
+    return 0;
+}
+
+int gimic_b200_destroy(gimic_b200_handle h) { delete h; return 0; }
+int gimic_b200_nbf(gimic_b200_handle h) { return h ? h->hb.nbf : fail(GIMIC_B200_EINVAL, "null handle"); }
+int gimic_b200_natoms(gimic_b200_handle h) { return h ? h->hb.natoms : fail(GIMIC_B200_EINVAL, "null handle"); }
+int gimic_b200_is_uhf(gimic_b200_handle h) { return h ? h->opts.uhf : fail(GIMIC_B200_EINVAL, "null handle"); }
+int gimic_b200_atom_coords(gimic_b200_handle h, double *xyz) {
+    if (!h || !xyz) return fail(GIMIC_B200_EINVAL, "null argument");
+    std::copy(h->hb.xyz.begin(), h->hb.xyz.end(), xyz);
+    return 0;
+}
+int gimic_b200_set_profiling(gimic_b200_handle h, int enable) { if (!h) return fail(GIMIC_B200_EINVAL, "null handle"); h->profiling = enable != 0; return 0; }
+int gimic_b200_get_stats(gimic_b200_handle h, gimic_b200_stats *out) { if (!h || !out) return fail(GIMIC_B200_EINVAL, "null argument"); *out = h->stats; return 0; }
+
+int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const double *B3, int spincase, double *tens, double *jvec,
+                           double *jmod, double *acid, double *edens, double *divj, double divj_h, int flags) {
+    if (!c || (n > 0 && !r)) return fail(GIMIC_B200_EINVAL, "null argument");
+    if ((jvec || jmod || divj) && !B3) return fail(GIMIC_B200_EINVAL, "jvec/jmod/divj need the magnetic field direction");
+    if (n < 0) return fail(GIMIC_B200_EINVAL, "negative point count");
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    if (n == 0) return 0;
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    cudaStream_t st = c->stream;
+    const double *d_r = nullptr;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    double *d_tens = tens;
+    if (!dev || !tens) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
+    // scalar/vector field outputs on the device
+    const size_t nf = (size_t)n;
+    double *d_jvec = jvec, *d_jmod = jmod, *d_acid = acid, *d_edens = edens, *d_divj = divj;
+    if (!dev) {
+        if (c->f_tmp.ensure(nf * 8 * 7)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (fields)");
+        double *f = c->f_tmp.as<double>();
+        d_jvec = jvec ? f : nullptr; d_jmod = jmod ? f + 3 * nf : nullptr; d_acid = acid ? f + 4 * nf : nullptr;
+        d_edens = edens ? f + 5 * nf : nullptr; d_divj = divj ? f + 6 * nf : nullptr;
+    }
+    if (int rc = run_tensors(c, n, d_r, spincase, d_tens, d_edens)) return rc;
+    if (c->profiling) cudaEventRecord(c->ev[0], st);
+    if (d_jvec || d_jmod || d_acid) {
+        const double zero3[3] = {0, 0, 0};
+        gb::launch_fields(n, d_r, d_tens, B3 ? B3 : zero3, d_jvec, d_jmod, d_acid, st);
+        c->stats.launches += 1;
+    }
+    if (c->profiling) { cudaEventRecord(c->ev[1], st); cudaEventSynchronize(c->ev[1]); float m = 0; cudaEventElapsedTime(&m, c->ev[0], c->ev[1]); c->stats.ms_fields += m; }
+    if (d_divj) {
+        // div J by central differences of J = T.B at r +- h e_a: 6 more tensor passes (no reference semantics at this commit)
+        const double hstep = divj_h > 0 ? divj_h : 1e-3;
+        if (c->shift.ensure((size_t)18 * n * 8) || c->jv6.ensure((size_t)(54 + 18) * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (divj)");
+        double *r6 = c->shift.as<double>(), *t6 = c->jv6.as<double>(), *v6 = t6 + (size_t)54 * n;
+        gb::launch_shift_points(n, d_r, hstep, r6, st);
+        gimic_b200_stats keep = c->stats;
+        if (int rc = run_tensors(c, 6 * n, r6, spincase, t6, nullptr)) return rc;
+        keep.launches = c->stats.launches; c->stats = keep;   // statistics describe the primary pass only
+        gb::launch_fields(6 * n, r6, t6, B3, v6, nullptr, nullptr, st);
+        gb::launch_divj(n, v6, hstep, d_divj, st);
+        c->stats.launches += 3;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) {
+        if (tens) CUDA_TRY(cudaMemcpyAsync(tens, d_tens, (size_t)9 * n * 8, cudaMemcpyDeviceToHost, st));
+        if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec, d_jvec, nf * 24, cudaMemcpyDeviceToHost, st));
+        if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod, d_jmod, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (acid) CUDA_TRY(cudaMemcpyAsync(acid, d_acid, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (edens) CUDA_TRY(cudaMemcpyAsync(edens, d_edens, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (divj) CUDA_TRY(cudaMemcpyAsync(divj, d_divj, nf * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gimic_b200_calc_jtensors(gimic_b200_handle h, long n, const double *r, int spincase, double *tens, int flags) {
+    if (!tens && n > 0) return fail(GIMIC_B200_EINVAL, "null argument");
+    return gimic_b200_calc_fields(h, n, r, nullptr, spincase, tens, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, flags);
+}
+
+int gimic_b200_fields_from_tensors(gimic_b200_handle c, long n, const double *r, const double *tens, const double *B3, double *jvec,
+                                   double *jmod, double *acid, int flags) {
+    if (!c || !tens || !B3 || (jmod && !r)) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (n <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    cudaStream_t st = c->stream;
+    const double *d_r = r, *d_t = nullptr;
+    if (r) { if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc; }
+    if (int rc = stage_in(c, c->tens_tmp, tens, (size_t)9 * n, flags, &d_t)) return rc;
+    const size_t nf = (size_t)n;
+    double *d_jvec = jvec, *d_jmod = jmod, *d_acid = acid;
+    if (!dev) {
+        if (c->f_tmp.ensure(nf * 8 * 5)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (fields)");
+        double *f = c->f_tmp.as<double>();
+        d_jvec = jvec ? f : nullptr; d_jmod = jmod ? f + 3 * nf : nullptr; d_acid = acid ? f + 4 * nf : nullptr;
+    }
+    gb::launch_fields(n, d_r, d_t, B3, d_jvec, d_jmod, d_acid, st);
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) {
+        if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec, d_jvec, nf * 24, cudaMemcpyDeviceToHost, st));
+        if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod, d_jmod, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (acid) CUDA_TRY(cudaMemcpyAsync(acid, d_acid, nf * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g, long lo, long hi, int spincase, double *tens, int flags) {
+    if (!c || !g || !tens) return fail(GIMIC_B200_EINVAL, "null argument");
+    const long ntot = (long)g->npts[0] * g->npts[1] * g->npts[2];
+    if (lo < 0 || hi > ntot || lo > hi) return fail(GIMIC_B200_EINVAL, "grid index range out of bounds");
+    const long n = hi - lo;
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    const double *ob, *p0, *p1, *p2, *w0;
+    if (int rc = grid_upload(c, g, &ob, &p0, &p1, &p2, &w0)) return rc;
+    if (c->r_in.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid points)");
+    gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], lo, hi, c->r_in.as<double>(), c->stream);
+    c->stats.launches += 1;
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    double *d_tens = tens;
+    if (!dev) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
+    if (int rc = run_tensors(c, n, c->r_in.as<double>(), spincase, d_tens, nullptr)) return rc;
+    if (!dev) CUDA_TRY(cudaMemcpyAsync(tens, d_tens, (size_t)9 * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gimic_b200_integrate(gimic_b200_handle c, const gimic_b200_grid *g, const double *B3, int spincase, int what, int jlo, int jhi,
+                         double *out7) {
+    if (!c || !g || !B3 || !out7) return fail(GIMIC_B200_EINVAL, "null argument");
+    const int p1 = g->npts[0], p2 = g->npts[1], p3 = g->npts[2];
+    if (jlo < 0 || jhi > p2 || jlo > jhi) return fail(GIMIC_B200_EINVAL, "row range out of bounds");
+    for (int k = 0; k < 7; ++k) out7[k] = 0.0;
+    const int nj = jhi - jlo, nrows = nj * p3;
+    if (nrows == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    const double *ob, *p0, *pp1, *pp2, *w0;
+    if (int rc = grid_upload(c, g, &ob, &p0, &pp1, &pp2, &w0)) return rc;
+    const long n = (long)nrows * p1;
+    if (c->r_in.ensure((size_t)3 * n * 8) || c->tens_tmp.ensure((size_t)9 * n * 8) || c->quad.ensure(((size_t)8 * nrows + 8) * 8))
+        return fail(GIMIC_B200_ENOMEM, "device allocation failed (integration)");
+    double *d_r = c->r_in.as<double>();
+    for (int k = 0; k < p3; ++k) {   // rows (k, j in [jlo,jhi)), i fastest: the loop nest of integral.f90:113-123
+        const long lo = ((long)k * p2 + jlo) * p1, hi = ((long)k * p2 + jhi) * p1;
+        gb::launch_grid_points(ob, p0, pp1, pp2, p1, p2, p3, lo, hi, d_r + 3 * (size_t)k * nj * p1, c->stream);
+    }
+    if (int rc = run_tensors(c, n, d_r, spincase, c->tens_tmp.as<double>(), nullptr)) return rc;
+    std::vector<double> wrow(nrows);
+    for (int k = 0; k < p3; ++k) for (int j = 0; j < nj; ++j)
+        wrow[(size_t)k * nj + j] = (g->wgt[1] ? g->wgt[1][jlo + j] : 1.0) * (g->wgt[2] ? g->wgt[2][k] : 1.0);
+    double *d_part = c->quad.as<double>(), *d_wrow = d_part + (size_t)7 * nrows, *d_out = d_wrow + nrows;
+    CUDA_TRY(cudaMemcpyAsync(d_wrow, wrow.data(), (size_t)nrows * 8, cudaMemcpyHostToDevice, c->stream));
+    gb::QuadArgs q;
+    q.tens = c->tens_tmp.as<double>(); q.p1 = p1; q.nrows = nrows; q.r = d_r; q.w1 = w0; q.wrow = d_wrow;
+    auto gp = [&](int i, int j, int k, double *r) {   // gridpoint, grid.f90:498-511 (0-based here)
+        for (int d = 0; d < 3; ++d) r[d] = g->origin[d] + g->pts[0][i] * g->basv[d] + g->pts[1][j] * g->basv[3 + d] + g->pts[2][k] * g->basv[6 + d];
+    };
+    double v1[3], v2[3];
+    gp(p1 - 1, 0, 0, v1); gp(0, p2 - 1, 0, v2);   // grid_center, grid.f90:529-541
+    for (int d = 0; d < 3; ++d) { q.center[d] = (v1[d] + v2[d]) * 0.5; q.B[d] = B3[d]; q.normal[d] = g->basv[6 + d]; }
+    q.radius = (g->radius > 0.0) ? g->radius : 1e300;
+    q.what = what; q.row_partials = d_part; q.out7 = d_out;
+    gb::launch_quadrature(q, c->stream);
+    c->stats.launches += 2 + p3;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out7, d_out, 7 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts) {
+    if (!pts || !wgts || npts <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
+    int rc = gb::gauss_blocks(a, b, npts, order, quadrature, pts, wgts);
+    if (rc == -1) return fail(GIMIC_B200_EINVAL, "*** integration did not converge!");
+    if (rc) return fail(GIMIC_B200_EINVAL, "gaussgrid(): npts is not dividable by ngp!");
+    return 0;
+}
+
+// ------------------------------------------------------------------------ legacy single-point boundary
+namespace {
+gimic_b200_ctx *g_default = nullptr;
+double g_magnet[3] = {0, 0, 0};
+int g_spin = GIMIC_B200_TOTAL;
+double g_screen = 1e-6;
+[[noreturn]] void legacy_stop(const char *what) {   // the Fortran side would `stop`
+    std::fprintf(stderr, " *** gimic-b200: %s: %s\n", what, g_err.c_str());
+    std::exit(1);
+}
+}  // namespace
+
+void gimic_init(const char *mol, const char *xdens) {
+    if (g_default) { delete g_default; g_default = nullptr; }
+    gimic_b200_opts o; gimic_b200_default_opts(&o);          // gimic_interface.f90:37-51
+    g_magnet[0] = g_magnet[1] = g_magnet[2] = 0.0; g_spin = GIMIC_B200_TOTAL;
+    if (gimic_b200_create(&g_default, mol, xdens, &o)) legacy_stop("gimic_init");
+}
+void gimic_finalize(void) { delete g_default; g_default = nullptr; }
+void gimic_set_uhf(int *uhf) {
+    // The reference only flips settings%is_uhf (gimic_interface.f90:80-86) and then reads unallocated beta
+    // densities; here the context is rebuilt from the same files as an open-shell one.
+    if (!g_default || !uhf) return;
+    const int want = *uhf != 0;
+    if (want == (g_default->opts.uhf != 0)) return;
+    gimic_b200_opts o = g_default->opts; o.uhf = want;
+    std::string m = g_default->mol_path, x = g_default->xdens_path;
+    delete g_default; g_default = nullptr;
+    if (gimic_b200_create(&g_default, m.c_str(), x.c_str(), &o)) legacy_stop("gimic_set_uhf");
+}
+void gimic_set_magnet(const double *b) { if (b) for (int i = 0; i < 3; ++i) g_magnet[i] = b[i]; }
+void gimic_set_spin(const char *s) {
+    if (!s) return;
+    if (!std::strcmp(s, "alpha")) g_spin = GIMIC_B200_ALPHA;
+    else if (!std::strcmp(s, "beta")) g_spin = GIMIC_B200_BETA;
+    else if (!std::strcmp(s, "total")) g_spin = GIMIC_B200_TOTAL;
+    else if (!std::strcmp(s, "spindens")) g_spin = GIMIC_B200_SPINDENS;
+    else { g_err = s; legacy_stop("Invalid spin case."); }   // gimic_interface.f90:111-112
+}
+void gimic_set_screening(const double *thrs) { if (thrs) g_screen = *thrs; }   // like the reference: stored, radii are not rebuilt (gimic_interface.f90:116-119)
+void gimic_calc_jtensor(const double *r, double *jt) {
+    if (!g_default) { g_err = "gimic_init() has not been called"; legacy_stop("gimic_calc_jtensor"); }
+    if (gimic_b200_calc_jtensors(g_default, 1, r, g_spin, jt, 0)) legacy_stop("gimic_calc_jtensor");
+}
+void gimic_calc_jvector(const double *r, double *jv) {
+    if (!g_default) { g_err = "gimic_init() has not been called"; legacy_stop("gimic_calc_jvector"); }
+    if (gimic_b200_calc_fields(g_default, 1, r, g_magnet, g_spin, nullptr, jv, nullptr, nullptr, nullptr, nullptr, 0.0, 0)) legacy_stop("gimic_calc_jvector");
+}
+void gimic_calc_modj(const double *r, double *d) {
+    // reference: stop 'gimic_calc_modj(): NOT IMPLEMENTED YET!' (gimic_interface.f90:153-163); here |J| for the stored magnet
+    if (!g_default) { g_err = "gimic_init() has not been called"; legacy_stop("gimic_calc_modj"); }
+    double jv[3];
+    if (gimic_b200_calc_fields(g_default, 1, r, g_magnet, g_spin, nullptr, jv, nullptr, nullptr, nullptr, nullptr, 0.0, 0)) legacy_stop("gimic_calc_modj");
+    *d = std::sqrt(jv[0] * jv[0] + jv[1] * jv[1] + jv[2] * jv[2]);
+}
+void gimic_get_gauss_points(double *a, double *b, int *npts, int *order, double *pts, double *wgts) {
+    if (gimic_b200_gauss_points(*a, *b, *npts, *order, 0, pts, wgts)) legacy_stop("gimic_get_gauss_points");
+}
+void mkgausspoints(double *a, double *b, int *npts, int *order, double *pts, double *wgts) { gimic_get_gauss_points(a, b, npts, order, pts, wgts); }
+
+}  // extern "C"

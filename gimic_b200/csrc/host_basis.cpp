@@ -1,0 +1,317 @@
+#include "host_basis.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace gb {
+
+namespace {
+
+// ---- tiny Fortran-list-directed tokenizer ------------------------------------------------------
+struct Records {
+    std::vector<std::string> lines;
+    size_t cur = 0;
+    bool open(const std::string &path) {
+        std::ifstream f(path);
+        if (!f) return false;
+        std::string s;
+        while (std::getline(f, s)) lines.push_back(s);
+        return true;
+    }
+    bool line(std::string &s) {
+        if (cur >= lines.size()) return false;
+        s = lines[cur++];
+        return true;
+    }
+};
+
+void tokens_of(const std::string &s, std::vector<std::string> &out) {
+    size_t i = 0, n = s.size();
+    while (i < n) {
+        while (i < n && (std::isspace((unsigned char)s[i]) || s[i] == ',')) ++i;
+        size_t j = i;
+        while (j < n && !std::isspace((unsigned char)s[j]) && s[j] != ',') ++j;
+        if (j > i) out.push_back(s.substr(i, j - i));
+        i = j;
+    }
+}
+
+double to_double(const std::string &t) {
+    char buf[64];
+    size_t n = std::min(t.size(), sizeof(buf) - 1);
+    for (size_t i = 0; i < n; ++i) buf[i] = (t[i] == 'D' || t[i] == 'd') ? 'e' : t[i];
+    buf[n] = 0;
+    return std::strtod(buf, nullptr);
+}
+
+// A list-directed READ of `want` items: begins on a fresh record and keeps consuming records until
+// satisfied; whatever is left on the last record is dropped.
+bool read_items(Records &r, size_t want, std::vector<std::string> &got) {
+    got.clear();
+    std::string s;
+    while (got.size() < want) {
+        if (!r.line(s)) return false;
+        tokens_of(s, got);
+    }
+    got.resize(want);
+    return true;
+}
+
+// component tables, generated rather than tabulated:
+// standard order = lexicographically descending (lx, ly) ; Turbomole order is tabulated.
+const int TM_D[6][3] = {{2,0,0},{0,2,0},{0,0,2},{1,1,0},{1,0,1},{0,1,1}};
+const int TM_F[10][3] = {{3,0,0},{0,3,0},{0,0,3},{2,1,0},{2,0,1},{1,2,0},{0,2,1},{1,0,2},{0,1,2},{1,1,1}};
+const int TM_G[15][3] = {{4,0,0},{0,4,0},{0,0,4},{3,1,0},{3,0,1},{1,3,0},{0,3,1},{1,0,3},{0,1,3},{2,2,0},
+                         {2,0,2},{0,2,2},{2,1,1},{1,2,1},{1,1,2}};
+const int TM_H[21][3] = {{5,0,0},{0,5,0},{0,0,5},{4,1,0},{4,0,1},{1,4,0},{0,4,1},{1,0,4},{0,1,4},{3,2,0},
+                         {3,0,2},{2,3,0},{0,3,2},{2,0,3},{0,2,3},{3,1,1},{1,3,1},{1,1,3},{2,2,1},{2,1,2},{1,2,2}};
+
+void append_shell(HostBasis &b, int atom, int l, const std::vector<double> &xp, const std::vector<double> &c) {
+    Shell s;
+    s.atom = atom; s.l = l; s.nprim = (int)xp.size(); s.prim_off = (int)b.alpha.size();
+    s.ncomp = (l + 1) * (l + 2) / 2; s.user_off = b.nbf; s.thr = 1e10;
+    b.alpha.insert(b.alpha.end(), xp.begin(), xp.end());
+    b.cc.insert(b.cc.end(), c.begin(), c.end());
+    b.shells.push_back(s);
+    b.nbf += s.ncomp;
+    b.ngto += s.nprim * s.ncomp;
+}
+
+}  // namespace
+
+void component_exponents(int l, bool turbomole, int c, int lmn[3]) {
+    if (turbomole && l >= 2) {
+        const int(*t)[3] = l == 2 ? TM_D : l == 3 ? TM_F : l == 4 ? TM_G : TM_H;
+        lmn[0] = t[c][0]; lmn[1] = t[c][1]; lmn[2] = t[c][2];
+        return;
+    }
+    // standard GIMIC order (gtodefs.f90:86-106): lx descending, then ly descending
+    int k = 0;
+    for (int lx = l; lx >= 0; --lx)
+        for (int ly = l - lx; ly >= 0; --ly, ++k)
+            if (k == c) { lmn[0] = lx; lmn[1] = ly; lmn[2] = l - lx - ly; return; }
+}
+
+bool parse_mol(const std::string &path, HostBasis &b, std::string &err) {
+    Records r;
+    if (!r.open(path)) { err = "read_intgrl(): open failed: " + path; return false; }
+    std::string s;
+    std::vector<std::string> t;
+    if (!r.line(s) || s.compare(0, 6, "INTGRL") != 0) { err = "this doesn't look like an 'INTGRL' file: " + path; return false; }
+    if (!r.line(s)) { err = "MOL file truncated"; return false; }
+    b.turbomole = s.compare(0, 9, "TURBOMOLE") == 0;
+    r.line(s);
+    if (!read_items(r, 1, t)) { err = "MOL file truncated (natoms)"; return false; }
+    b.natoms = std::atoi(t[0].c_str());
+    if (b.natoms <= 0) { err = "MOL: bad atom count"; return false; }
+    r.line(s);
+    b.atom_shell_off.assign(1, 0);
+    b.atom_func_off.assign(1, 0);
+    for (int a = 0; a < b.natoms; ++a) {
+        if (!r.line(s)) { err = "MOL file truncated (atom header)"; return false; }
+        t.clear(); tokens_of(s, t);
+        if (t.size() < 3) { err = "MOL: malformed atom header"; return false; }
+        int nsh = std::atoi(t[2].c_str());
+        if (nsh - 1 > MAX_L) { err = "Largest allowed l-quantum number in basis exceeded"; return false; }
+        if ((int)t.size() < 3 + nsh) { err = "MOL: malformed atom header (block counts)"; return false; }
+        b.charge.push_back(to_double(t[0]));
+        std::vector<int> nblk(nsh);
+        for (int i = 0; i < nsh; ++i) nblk[i] = std::atoi(t[3 + i].c_str());
+        if (!r.line(s)) { err = "MOL file truncated (atom position)"; return false; }
+        if (s.size() < 4) s.resize(4, ' ');
+        b.symbol.push_back(s.substr(0, 2));
+        t.clear(); tokens_of(s.substr(4), t);
+        if (t.size() < 3) { err = "MOL: malformed atom position"; return false; }
+        for (int k = 0; k < 3; ++k) b.xyz.push_back(to_double(t[k]));
+        for (int l = 0; l < nsh; ++l) {
+            for (int blk = 0; blk < nblk[l]; ++blk) {
+                if (!read_items(r, 2, t)) { err = "MOL file truncated (block header)"; return false; }
+                int npf = std::atoi(t[0].c_str()), ncf = std::atoi(t[1].c_str());
+                if (npf <= 0 || ncf <= 0) { err = "MOL: bad contraction block"; return false; }
+                std::vector<double> xp(npf);
+                std::vector<std::vector<double>> co(ncf, std::vector<double>(npf));
+                for (int p = 0; p < npf; ++p) {
+                    if (!read_items(r, 1 + (size_t)ncf, t)) { err = "MOL file truncated (primitives)"; return false; }
+                    xp[p] = to_double(t[0]);
+                    for (int c = 0; c < ncf; ++c) co[c][p] = to_double(t[1 + c]);
+                }
+                // a generally contracted block becomes ncf segmented contractions (intgrl.f90:172-216)
+                for (int c = 0; c < ncf; ++c) append_shell(b, a, l, xp, co[c]);
+            }
+        }
+        b.atom_shell_off.push_back((int)b.shells.size());
+        b.atom_func_off.push_back(b.nbf);
+        if (b.atom_shell_off[a + 1] - b.atom_shell_off[a] > MAX_SHELLS_PER_ATOM) { err = "more than 99 contractions on one atom"; return false; }
+    }
+    b.nprim_total = (int)b.alpha.size();
+    return true;
+}
+
+bool basis_from_arrays(int natoms, const double *coords, const int *nctr_per_atom, const int *ctr_l,
+                       const int *ctr_npf, const double *xp, const double *cc, int turbomole_order,
+                       HostBasis &b, std::string &err) {
+    if (natoms <= 0) { err = "natoms <= 0"; return false; }
+    b.turbomole = turbomole_order != 0;
+    b.natoms = natoms;
+    b.xyz.assign(coords, coords + 3 * (size_t)natoms);
+    b.charge.assign(natoms, 0.0);
+    b.symbol.assign(natoms, "X ");
+    b.atom_shell_off.assign(1, 0);
+    b.atom_func_off.assign(1, 0);
+    size_t ic = 0, ip = 0;
+    for (int a = 0; a < natoms; ++a) {
+        if (nctr_per_atom[a] > MAX_SHELLS_PER_ATOM) { err = "more than 99 contractions on one atom"; return false; }
+        for (int j = 0; j < nctr_per_atom[a]; ++j, ++ic) {
+            int l = ctr_l[ic], npf = ctr_npf[ic];
+            if (l < 0 || l > MAX_L || npf <= 0) { err = "bad shell description"; return false; }
+            append_shell(b, a, l, std::vector<double>(xp + ip, xp + ip + npf), std::vector<double>(cc + ip, cc + ip + npf));
+            ip += npf;
+        }
+        b.atom_shell_off.push_back((int)b.shells.size());
+        b.atom_func_off.push_back(b.nbf);
+    }
+    b.nprim_total = (int)b.alpha.size();
+    return true;
+}
+
+void finalize_basis(HostBasis &b, bool use_screening, double screening_thrs) {
+    const double pi = 3.141592653589793;  // PII, globals.f90:41
+    b.ncc.assign(b.alpha.size(), 0.0);
+    for (Shell &s : b.shells) {
+        const double *a = &b.alpha[s.prim_off], *c = &b.cc[s.prim_off];
+        // contraction self-overlap of the normalised primitives (basis.f90:171-184)
+        double j = 1.0 * (s.l + 1), n = 0.0;
+        for (int p = 0; p < s.nprim; ++p)
+            for (int q = 0; q <= p; ++q) {
+                double t = 2.0 * std::sqrt(a[p] * a[q]) / (a[p] + a[q]);
+                t = c[p] * c[q] * std::pow(t, j + 0.5);
+                n += (p == q) ? t : 2.0 * t;
+            }
+        n = 1.0 / std::sqrt(n);
+        for (int p = 0; p < s.nprim; ++p)
+            b.ncc[s.prim_off + p] = c[p] * n * std::pow(4.0 * a[p], 0.5 * j + 0.25) * std::pow(0.5 / pi, 0.75);
+        // screening radius: first multiple of 0.25 bohr where d^l exp(-a_min d^2) <= thrs (basis.f90:90-112)
+        if (!use_screening || screening_thrs <= 0.0) { s.thr = 1e10; continue; }
+        double amin = a[0];
+        for (int p = 1; p < s.nprim; ++p) amin = std::min(amin, a[p]);
+        double d = 0.0, x = 1e15;
+        while (x > screening_thrs) {
+            d += 0.25;
+            double dl = 1.0;
+            for (int k = 0; k < s.l; ++k) dl *= d;
+            x = dl * std::exp(-amin * d * d);
+        }
+        s.thr = d;
+    }
+}
+
+bool read_xdens(const std::string &path, int nbf, int nmat, std::vector<double> &out, std::string &err) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) { err = "Density file not found: " + path; return false; }
+    std::fseek(f, 0, SEEK_END);
+    long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
+    std::fclose(f);
+    buf[got] = 0;
+    for (size_t i = 0; i < got; ++i) if (buf[i] == 'D' || buf[i] == 'd') buf[i] = 'e';
+    size_t want = (size_t)nmat * nbf * nbf;
+    out.resize(want);
+    char *p = buf.data(), *end;
+    for (size_t i = 0; i < want; ++i) {
+        double v = std::strtod(p, &end);
+        if (end == p) { err = "XDENS too short: expected " + std::to_string(want) + " values, found " + std::to_string(i); return false; }
+        out[i] = v;
+        p = end;
+        while (*p == ',') ++p;
+    }
+    return true;
+}
+
+void turbomole_permutation(const HostBasis &b, std::vector<int> &sv) {
+    sv.clear();
+    sv.reserve(b.nbf);
+    for (int l = 0; l <= MAX_L; ++l)
+        for (const Shell &s : b.shells)
+            if (s.l == l)
+                for (int c = 0; c < s.ncomp; ++c) sv.push_back(s.user_off + c);
+}
+
+// ---- quadrature nodes ---------------------------------------------------------------------------
+namespace {
+// P_n(x) and derivatives by the three-term recurrence (gaussint.f90:144-222)
+void legendre(double x, int n, double &p, double &dp, double &d2p) {
+    if (n == 0) { p = 1; dp = 0; d2p = 0; return; }
+    double pm = 1, dpm = 0, d2pm = 0;
+    p = x; dp = 1; d2p = 0;
+    for (int i = 2; i <= n; ++i) {
+        double c1 = i, c2 = 2.0 * i - 1.0, c4 = i - 1.0;
+        double pn = (c2 * x * p - c4 * pm) / c1;
+        double dpn = (c2 * x * dp - c4 * dpm + c2 * p) / c1;
+        double d2pn = (c2 * x * d2p - c4 * d2pm + c2 * 2.0 * dp) / c1;
+        pm = p; p = pn; dpm = dp; dp = dpn; d2pm = d2p; d2p = d2pn;
+    }
+}
+const double NEWTON_EPS = 3.0e-12;  // gaussint.f90:15
+const int NEWTON_MAX = 10;
+
+int unit_nodes(int n, int quadrature, std::vector<double> &x, std::vector<double> &w) {  // on [-1, 1]
+    const double pi = 3.141592653589793;
+    x.assign(n, 0); w.assign(n, 0);
+    if (quadrature == 0) {
+        for (int i = 1; i <= (n + 1) / 2; ++i) {
+            double z = std::cos(pi * (i - 0.25) / (n + 0.5)), p, dp, d2p;
+            int it = 1;
+            for (; it <= NEWTON_MAX; ++it) {
+                legendre(z, n, p, dp, d2p);
+                double z1 = z;
+                z = z1 - p / dp;
+                if (std::fabs(z - z1) <= NEWTON_EPS) break;
+            }
+            if (it >= NEWTON_MAX) return -1;
+            x[i - 1] = -z; x[n - i] = z;
+            w[i - 1] = w[n - i] = 2.0 / ((1.0 - z * z) * dp * dp);
+        }
+    } else {
+        x[0] = -1; x[n - 1] = 1;
+        w[0] = w[n - 1] = 2.0 / (double)(n * n - n);
+        for (int i = 2; i <= n - 1; ++i) {
+            double z = std::cos(pi * (i - 0.25) / (n + 0.5)), p = 0, dp, d2p;
+            int it = 1;
+            for (; it <= NEWTON_MAX; ++it) {
+                legendre(z, n - 1, p, dp, d2p);
+                double z1 = z, damp = 0.5;
+                z = z1 - dp / d2p;
+                while (std::fabs(z) > 1.0) { z = z1 - dp / d2p * damp; damp *= damp; }
+                if (std::fabs(z - z1) <= NEWTON_EPS) break;
+            }
+            if (it >= NEWTON_MAX) return -1;
+            x[i - 1] = -z;
+            w[i - 1] = 2.0 / ((double)(n * n - n) * p * p);
+        }
+    }
+    return 0;
+}
+}  // namespace
+
+int gauss_blocks(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts) {
+    if (npts == 1) { pts[0] = 0.0; wgts[0] = 1.0; return 0; }  // collapsed axis (gaussint.f90:280-284)
+    if (order <= 0 || npts % order != 0) return -2;
+    std::vector<double> x, w;
+    if (int rc = unit_nodes(order, quadrature, x, w)) return rc;
+    int nblock = npts / order;
+    double step = (b - a) / nblock, half = 0.5 * step;
+    for (int blk = 0; blk < nblock; ++blk)
+        for (int k = 0; k < order; ++k) {
+            pts[blk * order + k] = (x[k] + 1.0) * half + blk * step;   // note: offset from 0, not from a (as the reference)
+            wgts[blk * order + k] = w[k] * half;
+        }
+    return 0;
+}
+
+}  // namespace gb

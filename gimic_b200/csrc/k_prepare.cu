@@ -1,0 +1,259 @@
+// Preparation kernels: spatial sort keys, tile active sets (screening), basis-function panels.
+//
+// k_basis replaces calc_basis of the reference (src/libgimic/bfeval.f90:61-122, 295-338 with
+// caos.f90:17-110 and basis.f90:118-136): one exp per primitive (the reference evaluates each four
+// times), integer powers by repeated multiplication, and the *same* screening test
+// sqrt(|r-R|^2) <= thr  so screened functions are exact zeros as in the reference.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+namespace gb {
+
+__constant__ signed char c_lmn[2][6][21][3];
+
+void upload_component_tables(const signed char *host_tab) { cudaMemcpyToSymbol(c_lmn, host_tab, 2 * 6 * 21 * 3); }
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread20(uint32_t v) {   // 20 bits -> every third bit of 60
+    uint64_t x = v & 0xFFFFFu;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton_keys(const double *__restrict__ r, long n, double lox, double loy, double loz, double inv_cell,
+                              uint64_t *__restrict__ keys, int *__restrict__ vals) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double qx = fmin(fmax((r[3 * i + 0] - lox) * inv_cell, 0.0), 1048575.0);
+    double qy = fmin(fmax((r[3 * i + 1] - loy) * inv_cell, 0.0), 1048575.0);
+    double qz = fmin(fmax((r[3 * i + 2] - loz) * inv_cell, 0.0), 1048575.0);
+    keys[i] = spread20((uint32_t)qx) | (spread20((uint32_t)qy) << 1) | (spread20((uint32_t)qz) << 2);
+    vals[i] = (int)i;
+}
+
+void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s) {
+    if (n <= 0) return;
+    k_morton_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, n, bbox_lo[0], bbox_lo[1], bbox_lo[2], inv_cell, keys, vals);
+}
+
+size_t sort_temp_bytes(long n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, 0, 60);
+    return bytes;
+}
+void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s) {
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 60, s);
+}
+
+__global__ void k_gather_points(const double *__restrict__ r, const int *__restrict__ perm, long n, double *__restrict__ rsx,
+                                double *__restrict__ rsy, double *__restrict__ rsz) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long p = perm[i];
+    rsx[i] = r[3 * p + 0]; rsy[i] = r[3 * p + 1]; rsz[i] = r[3 * p + 2];
+}
+void launch_gather_points(const double *r, const int *perm, long n, double *rsx, double *rsy, double *rsz, cudaStream_t s) {
+    if (n <= 0) return;
+    k_gather_points<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, perm, n, rsx, rsy, rsz);
+}
+
+// gridpoint() of src/fgimic/grid.f90:498-511 for the flat index range [lo,hi), i fastest (grid.f90:478-495)
+__global__ void k_grid_points(const double *__restrict__ ob, const double *__restrict__ p0, const double *__restrict__ p1,
+                              const double *__restrict__ p2, int n0, int n1, int n2, long lo, long hi, double *__restrict__ r) {
+    long idx = lo + blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (idx >= hi) return;
+    long n01 = (long)n0 * n1;
+    int k = (int)(idx / n01);
+    int j = (int)((idx - k * n01) / n0);
+    int i = (int)(idx - k * n01 - (long)j * n0);
+    double a = p0[i], b = p1[j], c = p2[k];
+    long o = idx - lo;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) r[3 * o + d] = ob[d] + a * ob[3 + d] + b * ob[6 + d] + c * ob[9 + d];
+}
+void launch_grid_points(const double *ob, const double *p0, const double *p1, const double *p2, int n0, int n1, int n2, long lo, long hi,
+                        double *r, cudaStream_t s) {
+    long n = hi - lo;
+    if (n <= 0) return;
+    k_grid_points<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ob, p0, p1, p2, n0, n1, n2, lo, hi, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conservative screening of one atom against a tile's bounding sphere.  A shell can only be
+// non-zero at some point p of the tile if |p - R| <= thr; |p - R| >= |c - R| - rho, so shells with
+// thr < |c-R| - rho are dropped.  Shells are sorted by descending thr inside each atom, so the
+// active set of an atom is a prefix.  The exact per-point test is applied again in k_basis.
+__device__ __forceinline__ void atom_active(const DevBasis &B, int a, double cx, double cy, double cz, double rho, int &nsh, int &nfun) {
+    nsh = 0; nfun = 0;
+    double dx = cx - B.atom_xyz[3 * a], dy = cy - B.atom_xyz[3 * a + 1], dz = cz - B.atom_xyz[3 * a + 2];
+    double lim = sqrt(dx * dx + dy * dy + dz * dz) - rho - 1e-9;
+    if (lim > B.atom_maxthr[a]) return;
+    int s1 = B.atom_shell_off[a + 1];
+    for (int s = B.atom_shell_off[a]; s < s1; ++s) {
+        if (B.sh_thr[s] >= lim) { int l = B.sh_l[s]; nfun += (l + 1) * (l + 2) / 2; ++nsh; }
+        else break;
+    }
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce_128(T v, Op op, T *s4) {   // 128 threads; result broadcast to all
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s4[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return op(op(s4[0], s4[1]), op(s4[2], s4[3]));
+}
+
+__global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
+                                                    const double *__restrict__ rsz, long n, TileGeo *__restrict__ geo,
+                                                    int *__restrict__ nraw) {
+    __shared__ double s4[4];
+    __shared__ int i4[4];
+    long tile = blockIdx.x, pt = tile * MT + threadIdx.x;
+    bool valid = pt < n;
+    long p0 = tile * MT;
+    double x = rsx[valid ? pt : p0], y = rsy[valid ? pt : p0], z = rsz[valid ? pt : p0];
+    auto fmn = [](double a, double b) { return fmin(a, b); };
+    auto fmx = [](double a, double b) { return fmax(a, b); };
+    double cx = 0.5 * (block_reduce_128(x, fmn, s4) + block_reduce_128(x, fmx, s4));
+    double cy = 0.5 * (block_reduce_128(y, fmn, s4) + block_reduce_128(y, fmx, s4));
+    double cz = 0.5 * (block_reduce_128(z, fmn, s4) + block_reduce_128(z, fmx, s4));
+    double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
+    double rho = block_reduce_128(d, fmx, s4);
+    int cnt = 0;
+    for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, cx, cy, cz, rho, nsh, nfun); cnt += nfun; }
+    auto iadd = [](int a, int b) { return a + b; };
+    cnt = block_reduce_128(cnt, iadd, i4);
+    if (threadIdx.x == 0) { geo[tile] = TileGeo{cx, cy, cz, rho}; nraw[tile] = cnt; }
+}
+void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, int ntiles, TileGeo *geo,
+                       int *nraw, cudaStream_t s) {
+    if (ntiles <= 0) return;
+    k_tile_count<<<ntiles, 128, 0, s>>>(B, rsx, rsy, rsz, n, geo, nraw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_basis: one CTA (128 threads = 128 points) per tile.
+//  phase A: ordered compaction of the active atoms into (atom, nshell, slot0) runs + the slot->function index list
+//  phase B: every thread evaluates its point for all active shells and writes the 4 planes
+//           P0 = Phi, P1..3 = dPhi/dx,dy,dz at panel[(plane*nact + slot)*LDP + row]  (row-contiguous => coalesced)
+__global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
+                                               const double *__restrict__ rsx, const double *__restrict__ rsy,
+                                               const double *__restrict__ rsz, double *__restrict__ panel_pool,
+                                               int *__restrict__ fidx_pool) {
+    extern __shared__ int s_runs[];   // 3 ints per active atom
+    __shared__ int s_w[2][4];
+    __shared__ int s_base[2];
+    const TileDesc td = tiles[blockIdx.x];
+    if (td.nact == 0) return;
+    const TileGeo tg = geo[td.pt0 / MT];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *panel = panel_pool + td.panel_off;
+    int *fidx = fidx_pool + td.fidx_off;
+    const long plane = (long)td.nact * LDP;
+
+    if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
+    __syncthreads();
+    for (int a0 = 0; a0 < B.natoms; a0 += 128) {
+        int a = a0 + tid, nsh = 0, nfun = 0;
+        if (a < B.natoms) atom_active(B, a, tg.cx, tg.cy, tg.cz, tg.rho, nsh, nfun);
+        int flag = nfun > 0, sf = nfun, sr = flag;   // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t1 = __shfl_up_sync(0xffffffffu, sf, o), t2 = __shfl_up_sync(0xffffffffu, sr, o);
+            if (lane >= o) { sf += t1; sr += t2; }
+        }
+        if (lane == 31) { s_w[0][wid] = sf; s_w[1][wid] = sr; }
+        __syncthreads();
+        int offf = s_base[0], offr = s_base[1];
+        for (int w = 0; w < wid; ++w) { offf += s_w[0][w]; offr += s_w[1][w]; }
+        if (flag) {
+            int run = offr + sr - 1, slot0 = offf + sf - nfun;
+            s_runs[3 * run] = a; s_runs[3 * run + 1] = nsh; s_runs[3 * run + 2] = slot0;
+        }
+        __syncthreads();
+        if (tid == 127) { s_base[0] = offf + sf; s_base[1] = offr + sr; }
+        __syncthreads();
+    }
+    const int nruns = s_base[1];
+    // slot -> internal function index; pad slots point at function 0 (their Phi is zero)
+    for (int rn = 0; rn < nruns; ++rn) {
+        int a = s_runs[3 * rn], nsh = s_runs[3 * rn + 1], slot0 = s_runs[3 * rn + 2];
+        int f0 = B.atom_func_off[a];
+        int s_last = B.atom_shell_off[a] + nsh - 1, ll = B.sh_l[s_last];
+        int nfun = B.sh_foff[s_last] - f0 + (ll + 1) * (ll + 2) / 2;
+        for (int c = tid; c < nfun; c += 128) fidx[slot0 + c] = f0 + c;
+    }
+    for (int c = td.nraw + tid; c < td.nact; c += 128) fidx[c] = 0;
+
+    const int row = tid;
+    const bool valid = row < td.npts;
+    const long pt = td.pt0 + (valid ? row : 0);
+    const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
+    const signed char(*lmn_tab)[21][3] = c_lmn[B.turbomole ? 1 : 0];
+
+    for (int rn = 0; rn < nruns; ++rn) {
+        const int a = s_runs[3 * rn], nsh = s_runs[3 * rn + 1], slot0 = s_runs[3 * rn + 2];
+        const double rx = x - B.atom_xyz[3 * a], ry = y - B.atom_xyz[3 * a + 1], rz = z - B.atom_xyz[3 * a + 2];
+        const double r2 = rx * rx + ry * ry + rz * rz;
+        const double dist = sqrt(r2);                                  // filter_screened, basis.f90:127
+        double px[6], py[6], pz[6];
+        px[0] = py[0] = pz[0] = 1.0;
+#pragma unroll
+        for (int k = 1; k < 6; ++k) { px[k] = px[k - 1] * rx; py[k] = py[k - 1] * ry; pz[k] = pz[k - 1] * rz; }
+        const int sA = B.atom_shell_off[a], f0 = B.atom_func_off[a];
+        for (int s = sA; s < sA + nsh; ++s) {
+            const int l = B.sh_l[s], np = B.sh_nprim[s], po = B.sh_prim_off[s];
+            const int slot = slot0 + (B.sh_foff[s] - f0);
+            const int ncomp = (l + 1) * (l + 2) / 2;
+            double q = 0.0, qp = 0.0;
+            const bool on = valid && (dist <= B.sh_thr[s]);            // basis.f90:130
+            if (on) {
+                for (int p = 0; p < np; ++p) {                         // cao2, caos.f90:94-110 (one exp, not four)
+                    double al = B.alpha[po + p];
+                    double e = B.ncc[po + p] * exp(-al * r2);
+                    q += e; qp += al * e;
+                }
+            }
+            for (int c = 0; c < ncomp; ++c) {
+                const int lx = lmn_tab[l][c][0], ly = lmn_tab[l][c][1], lz = lmn_tab[l][c][2];
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                if (on) {
+                    const double ang = px[lx] * py[ly] * pz[lz];
+                    v0 = ang * q;                                      // cgto, caos.f90:31-36
+                    // dcgto, caos.f90:54-63:  f_a x^(f-e_a) q  -  2 x_a x^f q'
+                    const double up = ang * qp;
+                    v1 = (lx ? (double)lx * (px[lx - 1] * py[ly] * pz[lz]) * q : 0.0) - 2.0 * rx * up;
+                    v2 = (ly ? (double)ly * (px[lx] * py[ly - 1] * pz[lz]) * q : 0.0) - 2.0 * ry * up;
+                    v3 = (lz ? (double)lz * (px[lx] * py[ly] * pz[lz - 1]) * q : 0.0) - 2.0 * rz * up;
+                }
+                const long o = (long)(slot + c) * LDP + row;
+                panel[o] = v0; panel[plane + o] = v1; panel[2 * plane + o] = v2; panel[3 * plane + o] = v3;
+            }
+        }
+    }
+    for (int c = td.nraw; c < td.nact; ++c) {
+        const long o = (long)c * LDP + row;
+        panel[o] = 0.0; panel[plane + o] = 0.0; panel[2 * plane + o] = 0.0; panel[3 * plane + o] = 0.0;
+    }
+}
+
+void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
+                  const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s) {
+    if (ntiles <= 0) return;
+    size_t smem = (size_t)3 * B.natoms * sizeof(int);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool);
+}
+
+}  // namespace gb

@@ -1,0 +1,92 @@
+// Shared declarations for the gimic-b200 CUDA kernels (sm_100a).
+//
+// Data flow of one batched tensor evaluation (replaces the per-point loop of
+// src/fgimic/jfield.f90:114-129 + src/libgimic/jtensor.F90:66-237 + bfeval.f90:61-338):
+//
+//   points --k_morton_keys/sort/k_gather--> spatially sorted points, tiles of MT=128 points
+//   k_tile_count      per tile: bounding sphere + conservative active-function count (screening)
+//   k_basis           per tile: Phi, dPhi/dx,dy,dz of the active functions -> K-major panels in HBM/L2
+//   k_jtensor         per tile: DMMA contraction of the Phi panel with the gathered density
+//                     operands [D | Px | Py | Pz | D(Rv-Ru)x | D(Rv-Ru)y | D(Rv-Ru)z] and a fused
+//                     epilogue that reduces against Phi / dPhi to the 3x3 tensor (never stores X)
+//   k_fields          T -> jvec, signed |J|, ACID (HBM-bound pass)
+//   k_quad_rows/final Gauss-Legendre plane quadrature
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace gb {
+
+constexpr int MT = 128;    // points per tile (8 m16 row blocks, one per warp of k_jtensor)
+constexpr int LDP = 132;   // panel row stride in doubles: 132 = 4 (mod 16) -> conflict-free A-fragment LDS.64
+constexpr int BK = 16;     // K slots per pipeline stage
+constexpr int NV = 16;     // nu slots per accumulator chunk (2 n8 tiles per operand matrix)
+constexpr int LDB = 20;    // smem row stride of a B tile: 20 = 4 (mod 16) -> conflict-free B-fragment LDS.64
+constexpr int STAGES = 4;  // cp.async pipeline depth
+constexpr int FCAP = 8192; // active-index list cached in smem up to this many slots
+constexpr int NQ_GIAO = 7, NQ_NOGIAO = 4;
+
+struct DevBasis {
+    int natoms, nbf, nshell;
+    const double *atom_xyz;       // [natoms][3]
+    const double *atom_maxthr;    // [natoms] largest screening radius on the atom
+    const int *atom_shell_off;    // [natoms+1] into the internal (radius-sorted) shell order
+    const int *atom_func_off;     // [natoms+1] first internal function of the atom
+    const int *sh_l, *sh_nprim, *sh_prim_off, *sh_foff;   // [nshell] internal order; sh_foff = first internal function
+    const double *sh_thr;         // [nshell] screening radius (descending within an atom)
+    const double *alpha, *ncc;    // primitives
+    const double *fR;             // [3][nbf] centre coordinates of each internal function (SoA)
+    int turbomole;                // component order (gtodefs.f90:109-123) instead of the standard one
+};
+
+struct TileDesc {
+    int pt0, npts;      // range in the sorted point list
+    int nact;           // active slots, padded to a multiple of 16 (0: nothing within screening range)
+    int nraw;           // unpadded active function count
+    long long panel_off;  // doubles, into the panel pool: 4 planes x nact x LDP
+    long long fidx_off;   // ints, into the index pool
+};
+
+struct TileGeo { double cx, cy, cz, rho; };
+
+// ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
+void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s);
+void launch_gather_points(const double *r, const int *perm, long n, double *rsx, double *rsy, double *rsz, cudaStream_t s);
+void launch_grid_points(const double *origin_basv /*12 doubles, device*/, const double *p0, const double *p1, const double *p2,
+                        int n0, int n1, int n2, long lo, long hi, double *r, cudaStream_t s);
+void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, int ntiles,
+                       TileGeo *geo, int *nraw, cudaStream_t s);
+void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
+                  const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s);
+size_t sort_temp_bytes(long n);
+void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s);
+
+struct JtensorArgs {
+    const TileDesc *tiles; int ntiles; int *counter;
+    const double *panel_pool; const int *fidx_pool;
+    const double *Bop; long long plane_stride; int ldb;     // planar operands [NQ][nbf][ldb]
+    const double *fR; int nbf;
+    const double *rsx, *rsy, *rsz; const int *perm;
+    double *tens; double *edens;                            // outputs in user point order (edens may be null)
+    int paramag, diamag;
+};
+void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
+size_t jtensor_smem_bytes(bool giao);
+
+void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
+                          const int *f2user, const double *fR, bool giao, cudaStream_t s);
+
+void launch_fields(long n, const double *r, const double *tens, const double *B3 /*host values*/, double *jvec, double *jmod, double *acid, cudaStream_t s);
+void launch_divj(long n, const double *jv6 /* [6][n][3] shifted jvecs */, double h, double *divj, cudaStream_t s);
+void launch_shift_points(long n, const double *r, double h, double *r6, cudaStream_t s);
+struct QuadArgs {
+    const double *tens; int p1, nrows;            // rows = (j,k) pairs handled by this call, i fastest
+    const double *r;                              // points (3 x p1*nrows)
+    const double *w1, *wrow;                      // w_i [p1]; per-row weight w_j*w_k [nrows]
+    double B[3], normal[3], center[3], radius; int what;
+    double *row_partials;                         // [nrows][7]
+    double *out7;                                 // device, 7 doubles
+};
+void launch_quadrature(const QuadArgs &q, cudaStream_t s);
+
+}  // namespace gb

@@ -1,0 +1,166 @@
+/* gimic_b200.h -- C ABI of the B200-native GIMIC grid hot path (libgimic_b200.so).
+ *
+ * Two groups of entry points:
+ *
+ *  (1) LEGACY symbols: signature-identical to the reference's C boundary, so existing callers
+ *      (GimicInterface.cpp, gimic.pyx, gengauss.pyx, pygimic) link unchanged:
+ *        src/libgimic/gimic_interface.h:9-18   (Fortran side: gimic_interface.f90:26-163)
+ *        src/libgimic/gausspoints.h:10-13      (Fortran side: gausspoints.f90:13-29, gausspoints.c:4-7)
+ *      They operate on one hidden default context, one point per call, and -- like the Fortran
+ *      `stop` they replace -- terminate the process on error after printing the message.
+ *
+ *  (2) BATCHED, handle-based API (gimic_b200_*): what a driver should call.  It replaces the
+ *      Fortran-internal boundary the reference's grid loops use:
+ *        new_jtensor/ctensor/del_jtensor   src/libgimic/jtensor.F90:39-103
+ *        calc_jtensors / compute_jvectors  src/fgimic/jfield.f90:62-184
+ *        jmod2_vtkplot / acid_vtkplot      src/fgimic/jfield.f90:446-489, 556-582 (field arithmetic only)
+ *        integrate_current/_modulus/_acid  src/fgimic/integral.f90:50-511
+ *      All functions return 0 on success or a negative GIMIC_B200_E* code; the message is
+ *      available from gimic_b200_last_error() (thread-local).  Buffers are caller-owned, plain
+ *      pointers; host memory unless GIMIC_B200_DEVICE_PTR is set in `flags`, in which case they are
+ *      device pointers on the handle's GPU and no host<->device copy is made.
+ *
+ * Conventions (identical to the reference):
+ *   r      3 x n, point-major: r[3*i + c]                      (bohr)
+ *   tens   9 x n, point-major: tens[9*i + m + 3*b] = dJ_m/dB_b  (jtensor.F90:66-103, column-major 3x3)
+ *   jvec   3 x n: jvec[3*i + m] = sum_b tens(m,b) B_b           (jfield.f90:167-184)
+ *   densities: XDENS layout, column-major nbf x nbf, element (a,b) at a + nbf*b, matrices in the
+ *              order D, P_x, P_y, P_z (alpha) then the same four for beta (dens.f90:79-90)
+ *   AO order: atom -> contraction (file order) -> cartesian component (gtodefs.f90:86-123)
+ */
+#ifndef GIMIC_B200_H
+#define GIMIC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (1) legacy boundary -------- */
+void gimic_init(const char *mol, const char *xdens);      /* gimic_interface.h:9  */
+void gimic_finalize(void);                                /* gimic_interface.h:10 */
+void gimic_set_uhf(int *uhf);                             /* gimic_interface.h:11 */
+void gimic_set_magnet(const double *b3);                  /* gimic_interface.h:12 */
+void gimic_set_spin(const char *spincase);                /* gimic_interface.h:13 */
+void gimic_set_screening(const double *thrs);             /* gimic_interface.h:14 */
+void gimic_calc_jtensor(const double *r3, double *jt9);   /* gimic_interface.h:15 */
+void gimic_calc_jvector(const double *r3, double *jv3);   /* gimic_interface.h:16 */
+void gimic_calc_modj(const double *r3, double *modj);     /* gimic_interface.h:17 (reference: STOP 'NOT IMPLEMENTED') */
+void gimic_get_gauss_points(double *a, double *b, int *npts, int *order, double *pts, double *wgts); /* gausspoints.h:10 */
+void mkgausspoints(double *a, double *b, int *npts, int *order, double *pts, double *wgts);          /* gausspoints.h:12 */
+
+/* ------------------------------------------------------------------ (2) batched API ------------ */
+typedef struct gimic_b200_ctx *gimic_b200_handle;
+
+enum {
+    GIMIC_B200_OK = 0,
+    GIMIC_B200_EINVAL = -1,   /* bad argument */
+    GIMIC_B200_EIO = -2,      /* MOL / XDENS unreadable or malformed */
+    GIMIC_B200_ECUDA = -3,    /* CUDA runtime error (no CPU fallback exists) */
+    GIMIC_B200_ESPIN = -4,    /* beta/spindens requested on a closed-shell context (jtensor.F90:74-96) */
+    GIMIC_B200_ENOMEM = -5
+};
+
+enum { GIMIC_B200_ALPHA = 0, GIMIC_B200_BETA = 1, GIMIC_B200_TOTAL = 2, GIMIC_B200_SPINDENS = 3 };
+
+enum { GIMIC_B200_DEVICE_PTR = 1 };   /* flags: r / output buffers are device pointers */
+
+typedef struct {
+    int uhf;                 /* open shell: XDENS holds 8 matrices, P_b halved on read (dens.f90:94-98) */
+    int giao;                /* Advanced.GIAO     (jtensor.F90:115,180,194,210) */
+    int diamag;              /* Advanced.diamag   (jtensor.F90:225) */
+    int paramag;             /* Advanced.paramag  (jtensor.F90:220) */
+    int screening;           /* Advanced.screening */
+    double screening_thrs;   /* Advanced.screening_thrs; gimic_init uses 1e-6 (globals.f90:56) */
+    int device;              /* CUDA device ordinal; -1 = current device */
+    int reserved;
+} gimic_b200_opts;
+
+/* defaults of gimic_init (gimic_interface.f90:39-51): closed shell, GIAO/diamag/paramag on,
+ * screening on with 1e-6, current device */
+void gimic_b200_default_opts(gimic_b200_opts *opts);
+
+/* Reads MOL (INTGRL format, intgrl.f90) and XDENS (dens.f90), applies the Turbomole reorder and the
+ * UHF halving exactly as read_dens does, and uploads basis tables + contraction operands. */
+int gimic_b200_create(gimic_b200_handle *h, const char *mol, const char *xdens, const gimic_b200_opts *opts);
+
+/* Same, from memory.  Shell arrays are flat in AO order; dens_alpha/dens_beta point to 4 matrices
+ * each in the XDENS layout, already in atom-major AO order and (for UHF) already halved -- i.e. the
+ * contents of dens_t%da / dens_t%db (dens.f90:13-18).  dens_beta may be NULL for closed shell.
+ * dens_flags: GIMIC_B200_DEVICE_PTR if the density pointers are device memory. */
+int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double *coords, const int *nctr_per_atom,
+                                  const int *ctr_l, const int *ctr_npf, const double *xp, const double *cc,
+                                  int turbomole_order, const double *dens_alpha, const double *dens_beta,
+                                  int dens_flags, const gimic_b200_opts *opts);
+int gimic_b200_destroy(gimic_b200_handle h);
+
+int gimic_b200_nbf(gimic_b200_handle h);
+int gimic_b200_natoms(gimic_b200_handle h);
+int gimic_b200_atom_coords(gimic_b200_handle h, double *xyz /* 3 x natoms */);
+int gimic_b200_is_uhf(gimic_b200_handle h);
+
+/* calc_jtensors (jfield.f90:62-138): tens(:,i) = ctensor(r_i, spincase) for n points. */
+int gimic_b200_calc_jtensors(gimic_b200_handle h, long n, const double *r, int spincase, double *tens, int flags);
+
+/* Tensors + derived fields in one pass.  Any output may be NULL (skipped).
+ *   jvec  = T.B                       (jfield.f90:167-184)
+ *   jmod  = signed |J|                (jfield.f90:446-489: sign of (B x (r - (B.r)B)) . J)
+ *   acid  = get_acid(T)               (acid.f90:9-45, with the reference's 0.3333333)
+ *   edens = Phi^T D Phi ("diapam", jtensor.F90:168)        -- no reference run mode at this commit
+ *   divj  = div(T.B) by central differences of step divj_h  -- no reference run mode at this commit */
+int gimic_b200_calc_fields(gimic_b200_handle h, long n, const double *r, const double *B3, int spincase,
+                           double *tens, double *jvec, double *jmod, double *acid, double *edens, double *divj,
+                           double divj_h, int flags);
+
+/* Field arithmetic alone on existing tensors (the HBM-bound pass). */
+int gimic_b200_fields_from_tensors(gimic_b200_handle h, long n, const double *r, const double *tens,
+                                   const double *B3, double *jvec, double *jmod, double *acid, int flags);
+
+/* Regular grid (grid_t of src/fgimic/grid.f90:19-32 reduced to what gridpoint/get_weight need):
+ * r(i,j,k) = origin + pts[0][i] basv(:,1) + pts[1][j] basv(:,2) + pts[2][k] basv(:,3)  (grid.f90:498-511) */
+typedef struct {
+    double origin[3];
+    double basv[9];          /* basv[c + 3*v] = component c of basis vector v */
+    int npts[3];
+    const double *pts[3];    /* host arrays, npts[d] each */
+    const double *wgt[3];    /* quadrature weights (1.0 on even grids), host arrays */
+    double radius;           /* integration bound around grid_center (integral.f90:91,128); <=0 or >=1e10: none */
+} gimic_b200_grid;
+
+/* Tensors on the flat index range [lo, hi) of a regular grid (i fastest, grid.f90:478-495);
+ * points are generated on the device.  tens holds (hi-lo) tensors. */
+int gimic_b200_calc_jtensors_grid(gimic_b200_handle h, const gimic_b200_grid *g, long lo, long hi, int spincase,
+                                  double *tens, int flags);
+
+/* Plane/volume quadrature of integral.f90 over rows j in [jlo, jhi) of the grid (all i, all k):
+ *   out[0..2] = sum, positive part, negative part of  w (n.T.B)        (integrate_current)
+ *   out[3..5] = same for the signed modulus sgn(n.J)|J|               (integrate_modulus)
+ *   out[6]    = sum of w * get_acid(T)  (caller takes sqrt after reducing; integrate_acid)
+ * `what` is a bit mask: 1 current, 2 modulus, 4 acid.  With jlo=0, jhi=npts[1] this is the whole
+ * integral; a multi-GPU driver gives each rank a slab of rows and sums out[] (one all-reduce). */
+int gimic_b200_integrate(gimic_b200_handle h, const gimic_b200_grid *g, const double *B3, int spincase, int what,
+                         int jlo, int jhi, double *out7);
+
+/* Gauss-Legendre (quadrature=0) / Lobatto (1) nodes in the block layout of setup_gauss_data
+ * (gaussint.f90:267-319); host only. */
+int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);
+
+/* Last-call statistics for benches / roofline accounting. */
+typedef struct {
+    long n_points;            /* points processed */
+    long n_tiles;             /* point tiles */
+    double sum_nact;          /* sum over tiles of the padded active-function count */
+    double executed_flops;    /* 2 * MT * NQ * nact^2 summed over tiles (DMMA flops actually issued) */
+    double dense_flops;       /* n_points * (14 nbf^2 + 56 nbf), the reference's algorithmic work */
+    float ms_sort, ms_tiles, ms_basis, ms_contract, ms_fields;   /* CUDA-event times per stage */
+    long launches;            /* kernel launches issued */
+} gimic_b200_stats;
+int gimic_b200_get_stats(gimic_b200_handle h, gimic_b200_stats *out);
+int gimic_b200_set_profiling(gimic_b200_handle h, int enable);  /* per-stage CUDA-event timing (adds syncs) */
+
+const char *gimic_b200_last_error(void);
+const char *gimic_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIMIC_B200_H */

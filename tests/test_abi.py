@@ -1,0 +1,99 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, its host-only entry points agree with the oracle, and compute entry points fail loudly
+(no silent CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    import __graft_entry__ as ge
+    from gimic_b200 import _lib
+    if not os.path.exists(_lib.SO_PATH):
+        ge.build()
+    return _lib.lib()
+
+
+def test_header_symbols_exported(L):
+    from gimic_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gimic_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b((?:gimic_|mkgausspoints)\w*)\s*\(", hdr))
+    assert names, "no prototypes found"
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/gimic_b200.h but not exported"
+    assert names == set(_lib.LEGACY_SYMBOLS + _lib.API_SYMBOLS)
+
+
+def test_legacy_signatures_match_reference_header():
+    # src/libgimic/gimic_interface.h:9-18 and gausspoints.h:10-13 (names only; signatures are cited in the header)
+    want = ["gimic_init", "gimic_finalize", "gimic_set_uhf", "gimic_set_magnet", "gimic_set_spin", "gimic_set_screening",
+            "gimic_calc_jtensor", "gimic_calc_jvector", "gimic_calc_modj", "gimic_get_gauss_points", "mkgausspoints"]
+    from gimic_b200 import _lib
+    assert _lib.LEGACY_SYMBOLS == want
+
+
+@pytest.mark.parametrize("npts,order,quadr", [(36, 9, "gauss"), (7, 7, "gauss"), (30, 5, "gauss"), (1, 9, "gauss"),
+                                              (27, 9, "lobatto"), (13, 13, "lobatto")])
+def test_gauss_points_match_oracle(L, npts, order, quadr):
+    import gimic_b200
+    p = np.zeros(npts); w = np.zeros(npts)
+    gimic_b200.gausspoints(0.0, 7.25614, order, p, w, quadrature=quadr)
+    po, wo = O.gauss_points(0.0, 7.25614, npts, order, quadr)
+    assert np.allclose(p, po, rtol=0, atol=1e-14) and np.allclose(w, wo, rtol=0, atol=1e-14)
+
+
+def test_legacy_gauss_entry(L):
+    a, b, n, o = C.c_double(0.0), C.c_double(2.0), C.c_int(18), C.c_int(9)
+    p = np.zeros(18); w = np.zeros(18)
+    L.mkgausspoints(C.byref(a), C.byref(b), C.byref(n), C.byref(o), p.ctypes.data_as(C.POINTER(C.c_double)),
+                    w.ctypes.data_as(C.POINTER(C.c_double)))
+    po, wo = O.gauss_points(0.0, 2.0, 18, 9)
+    assert np.allclose(p, po, atol=1e-14) and np.allclose(w, wo, atol=1e-14)
+
+
+def test_gauss_bad_order_is_an_error(L):
+    import gimic_b200
+    with pytest.raises(gimic_b200.GimicB200Error):
+        gimic_b200.gausspoints(0.0, 1.0, 9, np.zeros(10), np.zeros(10))
+
+
+def test_io_errors_are_reported(L, cases):
+    import gimic_b200
+    with pytest.raises(gimic_b200.GimicB200Error) as e:
+        gimic_b200.Gimic(cases["c4h4"]["mol"], "/nonexistent/XDENS")
+    assert e.value.code == -2 and "Density file not found" in str(e.value)
+    with pytest.raises(gimic_b200.GimicB200Error) as e:
+        gimic_b200.Gimic(cases["c4h4"]["xdens"], cases["c4h4"]["xdens"])
+    assert e.value.code == -2 and "INTGRL" in str(e.value)
+
+
+def test_no_cpu_fallback(L, cases):
+    """Without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import gimic_b200
+    with pytest.raises(gimic_b200.GimicB200Error) as e:
+        gimic_b200.Gimic(cases["c4h4"]["mol"], cases["c4h4"]["xdens"])
+    assert e.value.code == -3 and "no CPU path" in str(e.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under gimic_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("gimic_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                    txt = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"oracle_lib|libgimic_oracle|gimic_oracle|\boracle/", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,300 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerance (BASELINE.json north_star): |gpu - ref| <= 1e-10 |ref| + 1e-12 in FP64.
+The oracle itself is pinned to the reference's goldens in test_oracle_golden.py; the goldens that
+are runnable are checked here directly as well.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-10, 1e-12
+
+
+def scaled_err(a, ref):
+    return float((np.abs(a - ref) / (RTOL * np.abs(ref) + ATOL)).max()) if a.size else 0.0
+
+
+def assert_close(a, ref, what=""):
+    e = scaled_err(np.asarray(a), np.asarray(ref))
+    assert e <= 1.0, f"{what}: max |a-ref| / (1e-10|ref| + 1e-12) = {e:.3g}"
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import gimic_b200
+    return gimic_b200
+
+
+@pytest.fixture(scope="module")
+def c4h4(gb, cases):
+    m, x = cases["c4h4"]["mol"], cases["c4h4"]["xdens"]
+    return gb.Gimic(m, x, screening_thrs=1e-8), O.Oracle.from_files(m, x, screening_thrs=1e-8)
+
+
+@pytest.fixture(scope="module")
+def opensh(gb, cases):
+    m, x = cases["open_shell"]["mol"], cases["open_shell"]["xdens"]
+    return gb.Gimic(m, x, uhf=True, screening_thrs=1e-8), O.Oracle.from_files(m, x, uhf=True, screening_thrs=1e-8)
+
+
+def to_product_grid(gb, og):
+    pts, wgt = zip(*[og.axis(d) for d in range(3)])
+    return gb.Grid(og.origin, og.basv, pts, wgt, radius=og.radius)
+
+
+# ---- config 1/2: c4h4 (closed shell, Turbomole order) ------------------------------------------------
+def test_c4h4_read_grid_tensors_and_golden(c4h4):
+    g, o = c4h4
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+    r, B = gold["grid"], gold["magnet"]
+    out = g.fields(r, B, "total", tens=True, jvec=True, jmod=True, acid=True, edens=True)
+    ref, ed = o.ctensor(r, "total", want_edens=True)
+    assert_close(out["tens"], ref, "tensors")
+    assert_close(out["edens"], ed, "edens")
+    jv = O.jvectors(ref, B)
+    assert_close(out["jvec"], jv, "jvec")
+    assert_close(out["acid"], O.acid_field(ref), "acid")
+    jm = O.jmod_signed(r, jv, B)
+    assert_close(np.abs(out["jmod"]), np.abs(jm), "|jmod|")
+    assert (np.sign(out["jmod"]) != np.sign(jm)).mean() < 1e-3
+    # the reference's own golden (10 printed digits)
+    gj = gold["jvec"]
+    big = np.abs(gj) > 1e-3 * np.abs(gj).max()
+    assert (np.abs(out["jvec"] - gj)[big] / np.abs(gj)[big]).max() < 2e-9
+
+
+def test_c4h4_integration_golden(gb, c4h4):
+    g, o = c4h4
+    xyz = o.atom_coords()
+    assert np.allclose(g.atom_coords(), xyz)
+    og = O.grid_bond(xyz[1], xyz[0], xyz[3], 1.48794, height=[-5.0, 5.0], width=[-1.25614, 6.0], type="gauss",
+                     gauss_order=9, grid_points=[30, 30, 0], rotation=[0.0, 0.0, 0.0])
+    bb = og.magnet("z")
+    grid = to_product_grid(gb, og)
+    out = g.integrate(grid, bb, "total", what=7)
+    cur = o.integrate(og, bb, "total", 0); mod = o.integrate(og, bb, "total", 1); acid = o.integrate(og, bb, "total", 2)
+    assert_close(out[0:3], cur, "current"); assert_close(out[3:6], mod, "modulus"); assert_close(out[6], acid[1], "acid")
+    gold = fixtures.golden_json("c4h4_integration.json")["blocks"]
+    for blk in gold:
+        got = out[3:6] if blk["section"] == "modulus" else out[0:3]
+        assert abs(got[0] - blk["au"]) < 1.01e-6 and abs(got[1] - blk["pos"]) < 1.01e-6 and abs(got[2] - blk["neg"]) < 1.01e-6
+    # row slabs add up (what a multi-GPU run all-reduces)
+    parts = sum(g.integrate(grid, bb, "total", 7, lo, hi) for lo, hi in [(0, 11), (11, 30), (30, 36)])
+    assert np.allclose(parts, out, rtol=1e-12, atol=1e-14)
+
+
+def test_c4h4_radius_mask(gb, c4h4):
+    g, o = c4h4
+    xyz = o.atom_coords()
+    og = O.grid_bond(xyz[1], xyz[0], xyz[3], 1.48794, height=[-5.0, 5.0], width=[-1.25614, 6.0], type="gauss",
+                     gauss_order=9, grid_points=[18, 18, 0], radius=3.0)
+    bb = og.magnet("z")
+    out = g.integrate(to_product_grid(gb, og), bb, "total", what=7)
+    assert_close(out[0:3], o.integrate(og, bb, "total", 0)); assert_close(out[3:6], o.integrate(og, bb, "total", 1))
+    assert_close(out[6], o.integrate(og, bb, "total", 2)[1])
+
+
+@pytest.mark.parametrize("kw", [dict(giao=False), dict(diamag=False), dict(paramag=False), dict(screening=False),
+                                dict(screening_thrs=1e-6), dict(giao=False, diamag=False)])
+def test_c4h4_option_switches(gb, cases, kw):
+    m, x = cases["c4h4"]["mol"], cases["c4h4"]["xdens"]
+    okw = dict(screening_thrs=1e-8); okw.update(kw)
+    g = gb.Gimic(m, x, **okw)
+    o = O.Oracle.from_files(m, x, **okw)
+    r = fixtures.golden_npz("c4h4_readgrid.npz")["grid"][::9]
+    assert_close(g.jtensors(r), o.ctensor(r), str(kw))
+    g.close()
+
+
+def test_edge_cases(c4h4):
+    g, o = c4h4
+    assert g.jtensors(np.zeros((0, 3))).shape == (0, 9)                      # empty
+    r1 = np.array([[0.3, -0.2, 0.7]])
+    assert_close(g.jtensors(r1), o.ctensor(r1), "single point")
+    rng = np.random.default_rng(5)
+    r = rng.uniform(-6, 6, size=(129, 3))                                    # ragged: one full tile + 1 point
+    assert_close(g.jtensors(r), o.ctensor(r), "ragged")
+    far = np.array([[200.0, 0, 0], [0, -300.0, 5.0], [1e4, 1e4, 1e4]])      # everything screened -> exact zeros
+    t = g.jtensors(far)
+    assert (t == 0).all() and (o.ctensor(far) == 0).all()
+    mix = np.vstack([far, r[:5], far])                                       # zeros and non-zeros in one tile
+    assert_close(g.jtensors(mix), o.ctensor(mix), "mixed")
+    dup = np.repeat(r[:3], 50, axis=0)                                       # duplicates / collisions
+    td = g.jtensors(dup)
+    assert_close(td, o.ctensor(dup), "duplicates")
+    on_atom = o.atom_coords()                                                # points on nuclei (0**0 = 1 paths)
+    assert_close(g.jtensors(on_atom), o.ctensor(on_atom), "on nuclei")
+    plane = r.copy(); plane[:, 2] = 0.0                                      # molecular plane: exact zeros of odd-z functions
+    assert_close(g.jtensors(plane), o.ctensor(plane), "nuclear plane")
+
+
+def test_point_order_invariance(c4h4):
+    g, _ = c4h4
+    rng = np.random.default_rng(11)
+    r = rng.uniform(-7, 7, size=(1000, 3))
+    t = g.jtensors(r)
+    p = rng.permutation(1000)
+    t2 = g.jtensors(r[p])
+    assert_close(t2, t[p], "permuted points")
+    t3 = g.jtensors(r)
+    assert (t3 == t).all(), "same input twice must be bit-identical (deterministic reduction order)"
+
+
+def test_legacy_single_point_api(gb, cases, c4h4):
+    _, o = c4h4
+    from gimic_b200 import _lib
+    L = _lib.lib()
+    L.gimic_init(cases["c4h4"]["mol"].encode(), cases["c4h4"]["xdens"].encode())
+    o6 = O.Oracle.from_files(cases["c4h4"]["mol"], cases["c4h4"]["xdens"], screening_thrs=1e-6)   # gimic_init uses 1e-6
+    b = np.array([0.0, 0.0, 1.0]); r = np.array([0.5, 0.25, 1.0]); jt = np.zeros(9); jv = np.zeros(3); mj = C.c_double()
+    dp = C.POINTER(C.c_double)
+    L.gimic_set_magnet(b.ctypes.data_as(dp))
+    L.gimic_set_spin(b"total")
+    L.gimic_calc_jtensor(r.ctypes.data_as(dp), jt.ctypes.data_as(dp))
+    L.gimic_calc_jvector(r.ctypes.data_as(dp), jv.ctypes.data_as(dp))
+    L.gimic_calc_modj(r.ctypes.data_as(dp), C.byref(mj))
+    ref = o6.ctensor(r[None])[0]
+    assert_close(jt, ref, "legacy jtensor")
+    assert_close(jv, O.jvectors(ref[None], b)[0], "legacy jvector")
+    assert abs(mj.value - np.linalg.norm(jv)) < 1e-15
+    L.gimic_finalize()
+    # the Cython-class mirror
+    g = gb.Gimic(cases["c4h4"]["mol"], cases["c4h4"]["xdens"])
+    g.set_property("magnet", [0.0, 0.0, 1.0])
+    assert_close(np.array(g.jvector(r)), O.jvectors(ref[None], b)[0], "Gimic.jvector")
+    assert_close(g.jtensor(r), ref, "Gimic.jtensor")
+    with pytest.raises(ValueError):
+        g.set_spin("gamma")
+    g.close()
+
+
+# ---- config 3: open shell ----------------------------------------------------------------------------
+def test_open_shell_spin_cases_and_golden(gb, opensh):
+    g, o = opensh
+    gold = fixtures.golden_npz("open_shell_3d.npz")
+    og = O.grid_std([-8.0, -8.0, -8.0], [1.0, 0, 0], [0, 1.0, 0], [16.0, 16.0, 16.0], type="even", spacing=[0.5, 0.5, 0.5])
+    bb = og.magnet("X")
+    grid = to_product_grid(gb, og)
+    assert grid.n == 35937
+    r_all = og.points()
+    assert np.allclose(grid.points(), r_all, atol=1e-14)
+    idx = gold["index"]
+    for tag, sc in (("", "total"), ("alpha", "alpha"), ("beta", "beta"), ("spindens", "spindens")):
+        tens = g.jtensors_grid(grid, 0, grid.n, sc)                      # device-generated grid points, full 33^3
+        ref = o.ctensor(r_all[idx], sc)
+        assert_close(tens[idx], ref, f"open-shell {sc}")
+        f = g.fields_from_tensors(r_all, tens, bb, jvec=True, jmod=True)
+        gj = gold["jvec" + tag]
+        tol = 1e-5 * np.abs(gj) + 1e-9 * np.abs(gj).max()
+        assert (np.abs(f["jvec"][idx] - gj) <= tol).all(), tag
+        gm = gold["jmod" + tag]
+        assert (np.abs(np.abs(f["jmod"][idx]) - np.abs(gm)) <= 1e-5 * np.abs(gm) + 1e-9 * np.abs(gm).max()).all(), tag
+
+
+def test_open_shell_integration_golden(gb, opensh):
+    g, o = opensh
+    xyz = o.atom_coords()
+    og = O.grid_bond(xyz[0], xyz[1], xyz[3], 1.32, height=[-5.0, 5.0], width=[-2.2, 5.0], type="gauss", gauss_order=9,
+                     grid_points=[30, 30, 0])
+    bb = og.magnet("X")
+    grid = to_product_grid(gb, og)
+    gold = fixtures.golden_json("open_shell_integration.json")["blocks"]
+    res = {sc: g.integrate(grid, bb, sc, what=3) for sc in ("total", "alpha", "beta", "spindens")}
+    for blk in gold:
+        got = res[blk["spin"]][3:6] if blk["section"] == "modulus" else res[blk["spin"]][0:3]
+        assert abs(got[0] - blk["au"]) < 1.01e-6 and abs(got[1] - blk["pos"]) < 1.01e-6 and abs(got[2] - blk["neg"]) < 1.01e-6, blk
+    assert_close(res["alpha"][0:3], o.integrate(og, bb, "alpha", 0), "alpha current vs oracle")
+    assert_close(res["spindens"][3:6], o.integrate(og, bb, "spindens", 1), "spindens modulus vs oracle")
+
+
+def test_closed_shell_rejects_beta(gb, c4h4):
+    g, _ = c4h4
+    with pytest.raises(gb.GimicB200Error) as e:
+        g.jtensors(np.zeros((1, 3)), "beta")
+    assert e.value.code == -4
+
+
+# ---- config 4/5 shape: synthetic carbon flakes --------------------------------------------------------
+@pytest.mark.parametrize("natoms,npts,general_p", [(6, 700, False), (14, 500, True), (42, 300, False)])
+def test_synthetic_flake_vs_oracle(gb, natoms, npts, general_p):
+    sh, dens, nbf = fixtures.synthetic_case(natoms, "flake", general_p=general_p)
+    flat = fixtures.dens_to_colmajor(dens)
+    g = gb.Gimic.from_arrays(dens_alpha=flat, **sh)
+    o = O.Oracle.from_arrays(dens_a=flat, **sh)
+    assert g.nbf == nbf == o.nbf
+    rng = np.random.default_rng(3)
+    lo, hi = sh["coords"].min(0) - 6.0, sh["coords"].max(0) + 6.0
+    r = rng.uniform(lo, hi, size=(npts, 3)); r[:, 2] = rng.uniform(-4, 4, size=npts)
+    ref, ed = o.ctensor(r, want_edens=True)
+    out = g.fields(r, [0, 0, 1.0], tens=True, edens=True)
+    assert_close(out["tens"], ref, f"flake nbf={nbf}")
+    assert_close(out["edens"], ed, "edens")
+    st = g.stats()
+    assert st["n_points"] == npts and st["executed_flops"] > 0 and st["executed_flops"] <= 1.2 * st["dense_flops"] * 128
+    g.close()
+
+
+def test_synthetic_ring_far_origin(gb):
+    """atoms ~120 bohr from the origin: the gauge-difference operand must not lose digits"""
+    sh, dens, nbf = fixtures.synthetic_case(10, "ring")
+    flat = fixtures.dens_to_colmajor(dens)
+    g = gb.Gimic.from_arrays(dens_alpha=flat, **sh)
+    o = O.Oracle.from_arrays(dens_a=flat, **sh)
+    rng = np.random.default_rng(4)
+    r = sh["coords"][rng.integers(0, 10, 400)] + rng.uniform(-5, 5, size=(400, 3))
+    assert_close(g.jtensors(r), o.ctensor(r), "ring")
+    g.close()
+
+
+def test_linearity_in_density(gb):
+    """size-independent property: T is linear in (D, P): T[a X + b Y] = a T[X] + b T[Y]"""
+    sh, d1, nbf = fixtures.synthetic_case(20, "flake", seed=1)
+    d2 = fixtures.synthetic_density(nbf, seed=2, general_p=True)
+    rng = np.random.default_rng(8)
+    r = rng.uniform(-12, 12, size=(4000, 3)); r[:, 2] *= 0.3
+    ts = []
+    for d in (d1, d2, 0.5 * d1 - 2.0 * d2):
+        g = gb.Gimic.from_arrays(dens_alpha=fixtures.dens_to_colmajor(d), **sh)
+        ts.append(g.jtensors(r)); g.close()
+    comb = 0.5 * ts[0] - 2.0 * ts[1]
+    scale = np.abs(ts[0]).max() + np.abs(ts[1]).max()
+    assert np.abs(ts[2] - comb).max() < 1e-12 * scale
+
+
+def test_uhf_total_is_alpha_plus_beta(gb):
+    sh, da, nbf = fixtures.synthetic_case(8, "flake", seed=5)
+    db = fixtures.synthetic_density(nbf, seed=6)
+    fa, fb = fixtures.dens_to_colmajor(da), fixtures.dens_to_colmajor(db)
+    g = gb.Gimic.from_arrays(dens_alpha=fa, dens_beta=fb, **sh)
+    o = O.Oracle.from_arrays(dens_a=fa, dens_b=fb, **sh)
+    rng = np.random.default_rng(9)
+    r = rng.uniform(-8, 8, size=(600, 3))
+    for sc in ("alpha", "beta", "total", "spindens"):
+        assert_close(g.jtensors(r, sc), o.ctensor(r, sc), sc)
+    g.close()
+
+
+def test_divj_small_for_giao_and_device_pointers(gb, c4h4):
+    """no reference semantics for divj at this commit (parity unpinned): self-test that the central-difference
+    divergence of J = T.B matches an independent finite-difference of the oracle's J; and the torch zero-copy path."""
+    import torch
+    g, o = c4h4
+    rng = np.random.default_rng(21)
+    r = rng.uniform(-3, 3, size=(64, 3))
+    B = np.array([0.0, 0.0, 1.0]); h = 1e-3
+    out = g.fields(r, B, divj=True, jvec=True, divj_h=h)
+    div = np.zeros(64)
+    for ax in range(3):
+        e = np.zeros(3); e[ax] = h
+        div += (O.jvectors(o.ctensor(r + e), B)[:, ax] - O.jvectors(o.ctensor(r - e), B)[:, ax]) / (2 * h)
+    assert np.abs(out["divj"] - div).max() < 1e-9
+    rt = torch.from_numpy(r).cuda()
+    tt = g.jtensors(rt)
+    assert tt.is_cuda and tt.shape == (64, 9)
+    assert_close(tt.cpu().numpy(), o.ctensor(r), "device-pointer path")
