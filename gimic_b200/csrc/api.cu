@@ -57,13 +57,17 @@ struct gimic_b200_ctx {
     double *d_op[4] = {nullptr, nullptr, nullptr, nullptr};   // contraction operands per spin case
     int nq = 7, ldb = 0; long long plane_stride = 0;
     double bbox_lo[3] = {0, 0, 0}; double inv_cell = 1.0;
-    size_t pool_max_bytes = (size_t)2 << 30;
+    size_t pool_max_bytes = (size_t)8 << 30;
     // workspaces
-    Buf keys0, keys1, vals0, vals1, sorttmp, rs, geo, nraw, tiles, panel, fidx, misc, r_in, tens_tmp, f_tmp, shift, jv6, gridbuf, quad;
-    int *h_nraw = nullptr; size_t h_nraw_cap = 0;
-    gb::TileDesc *h_tiles = nullptr; size_t h_tiles_cap = 0;
+    Buf keys0, keys1, vals0, vals1, sorttmp, rs, geo, nraw, segs, tiles, panel, fidx, misc, r_in, tens_tmp, f_tmp, shift, jv6, gridbuf, quad;
+    gb::TileInfo *h_info = nullptr; size_t h_info_cap = 0;
+    gb::TileSeg *h_segs = nullptr;
+    double split_radius = 2.5;   // bohr: tiles wider than this are cut at their largest consecutive gap if that shrinks them
+    gb::TileDesc *h_tiles = nullptr;
     bool profiling = false;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_call[2] = {};
+    std::vector<cudaEvent_t> evpool;   // per-batch (basis, contract) stamps, resolved at the end of a call
     gimic_b200_stats stats{};
     std::string mol_path, xdens_path;   // for the legacy set_uhf-after-init path
 
@@ -72,10 +76,13 @@ struct gimic_b200_ctx {
         for (void *p : owned) cudaFree(p);
         for (int i = 0; i < 2; ++i) if (d_dens[i]) cudaFree(d_dens[i]);
         for (int i = 0; i < 4; ++i) if (d_op[i]) cudaFree(d_op[i]);
-        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &tiles, &panel, &fidx, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
-        if (h_nraw) cudaFreeHost(h_nraw);
+        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &segs, &tiles, &panel, &fidx, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
+        if (h_info) cudaFreeHost(h_info);
+        if (h_segs) cudaFreeHost(h_segs);
         if (h_tiles) cudaFreeHost(h_tiles);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &e : evpool) cudaEventDestroy(e);
+        for (auto &e : ev_call) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -155,7 +162,7 @@ int build_device_basis(gimic_b200_ctx *c) {
         for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], hb.xyz[3 * a + k]); hi[k] = std::max(hi[k], hb.xyz[3 * a + k]); }
     double ext = 0;
     for (int k = 0; k < 3; ++k) { c->bbox_lo[k] = lo[k] - 24.0; ext = std::max(ext, hi[k] - lo[k] + 48.0); }
-    c->inv_cell = 1048576.0 / ext;
+    c->inv_cell = 65536.0 / ext;
     return 0;
 }
 
@@ -172,6 +179,7 @@ int init_device(gimic_b200_ctx *c) {
     c->nsm = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : c->ev_call) CUDA_TRY(cudaEventCreate(&e));
     if (const char *mb = std::getenv("GIMIC_B200_POOL_MB")) { long v = std::atol(mb); if (v > 0) c->pool_max_bytes = (size_t)v << 20; }
     return 0;
 }
@@ -226,23 +234,14 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     const double *op = nullptr;
     if (int rc = get_operand(c, spincase, &op)) return rc;
     cudaStream_t st = c->stream;
-    const long ntiles_l = (n + MT - 1) / MT;
-    const int ntiles = (int)ntiles_l;
+    int ntiles = (int)((n + MT - 1) / MT);
     const bool prof = c->profiling;
 
     if (c->keys0.ensure(n * 8) || c->keys1.ensure(n * 8) || c->vals0.ensure(n * 4) || c->vals1.ensure(n * 4) ||
-        c->rs.ensure((size_t)3 * n * 8) || c->geo.ensure((size_t)ntiles * sizeof(TileGeo)) || c->nraw.ensure((size_t)ntiles * 4) ||
-        c->tiles.ensure((size_t)ntiles * sizeof(TileDesc)) || c->misc.ensure(256))
+        c->rs.ensure((size_t)3 * n * 8) || c->misc.ensure(256))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed");
     size_t tb = sort_temp_bytes(n);
     if (c->sorttmp.ensure(tb)) return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (sort)");
-    if ((size_t)ntiles > c->h_nraw_cap) {
-        if (c->h_nraw) cudaFreeHost(c->h_nraw);
-        if (c->h_tiles) cudaFreeHost(c->h_tiles);
-        c->h_nraw_cap = (size_t)ntiles + ntiles / 8 + 64;
-        CUDA_TRY(cudaMallocHost((void **)&c->h_nraw, c->h_nraw_cap * sizeof(int)));
-        CUDA_TRY(cudaMallocHost((void **)&c->h_tiles, c->h_nraw_cap * sizeof(TileDesc)));
-    }
     double *rsx = c->rs.as<double>(), *rsy = rsx + n, *rsz = rsy + n;
     int *perm = c->vals1.as<int>();
 
@@ -251,17 +250,54 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     launch_sort_pairs(c->sorttmp.p, tb, c->keys0.as<uint64_t>(), c->keys1.as<uint64_t>(), c->vals0.as<int>(), perm, n, st);
     launch_gather_points(d_r, perm, n, rsx, rsy, rsz, st);
     if (prof) cudaEventRecord(c->ev[1], st);
-    launch_tile_count(c->db, rsx, rsy, rsz, n, ntiles, c->geo.as<TileGeo>(), c->nraw.as<int>(), st);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(c->h_nraw, c->nraw.p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, st));
+    c->stats.launches += 4;
+
+    // Tiles: runs of MT consecutive points along the Hilbert curve.  A run that straddles a re-entry of the
+    // curve (thin / planar point sets, cluster boundaries) is cut at its largest consecutive gap; a few rounds.
+    std::vector<TileSeg> segs(ntiles);
+    for (int t = 0; t < ntiles; ++t) segs[t] = TileSeg{t * MT, (int)std::min<long>(MT, n - (long)t * MT)};
+    for (int round = 0; round < 8; ++round) {
+        ntiles = (int)segs.size();
+        if ((size_t)ntiles > c->h_info_cap) {
+            if (c->h_info) cudaFreeHost(c->h_info);
+            if (c->h_segs) cudaFreeHost(c->h_segs);
+            if (c->h_tiles) cudaFreeHost(c->h_tiles);
+            c->h_info_cap = (size_t)ntiles + ntiles / 4 + 64;
+            CUDA_TRY(cudaMallocHost((void **)&c->h_info, c->h_info_cap * sizeof(TileInfo)));
+            CUDA_TRY(cudaMallocHost((void **)&c->h_segs, c->h_info_cap * sizeof(TileSeg)));
+            CUDA_TRY(cudaMallocHost((void **)&c->h_tiles, c->h_info_cap * sizeof(TileDesc)));
+        }
+        if (c->geo.ensure((size_t)ntiles * sizeof(TileGeo)) || c->nraw.ensure((size_t)ntiles * sizeof(TileInfo)) ||
+            c->segs.ensure((size_t)ntiles * sizeof(TileSeg)) || c->tiles.ensure((size_t)ntiles * sizeof(TileDesc)))
+            return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tiles)");
+        std::copy(segs.begin(), segs.end(), c->h_segs);
+        CUDA_TRY(cudaMemcpyAsync(c->segs.p, c->h_segs, (size_t)ntiles * sizeof(TileSeg), cudaMemcpyHostToDevice, st));
+        launch_tile_count(c->db, rsx, rsy, rsz, c->segs.as<TileSeg>(), ntiles, c->geo.as<TileGeo>(), c->nraw.as<TileInfo>(), st);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(c->h_info, c->nraw.p, (size_t)ntiles * sizeof(TileInfo), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        c->stats.launches += 1;
+        std::vector<TileSeg> next;
+        next.reserve(segs.size() + 16);
+        bool any = false;
+        for (int t = 0; t < ntiles; ++t) {
+            const TileInfo &ti = c->h_info[t];
+            const TileSeg &sg = segs[t];
+            if (round < 7 && sg.npts >= 16 && ti.nraw > 0 && ti.rho > c->split_radius && ti.gmax > 0.5f * ti.rho) {
+                next.push_back(TileSeg{sg.pt0, ti.imax + 1});
+                next.push_back(TileSeg{sg.pt0 + ti.imax + 1, sg.npts - ti.imax - 1});
+                any = true;
+            } else next.push_back(sg);
+        }
+        if (!any) break;
+        segs.swap(next);
+    }
     if (prof) cudaEventRecord(c->ev[2], st);
-    CUDA_TRY(cudaStreamSynchronize(st));
-    c->stats.launches += 5;
 
     // host: tile descriptors, split into batches that fit the panel pool
     size_t max_tile = 0, total = 0;
     for (int t = 0; t < ntiles; ++t) {
-        int nact = (c->h_nraw[t] + 15) / 16 * 16;
+        int nact = (c->h_info[t].nraw + 15) / 16 * 16;
         size_t d = (size_t)4 * nact * LDP;
         max_tile = std::max(max_tile, d); total += d;
     }
@@ -271,8 +307,8 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     double sum_nact = 0, flops = 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc &td = c->h_tiles[t];
-        td.pt0 = t * MT; td.npts = (int)std::min<long>(MT, n - (long)t * MT);
-        td.nraw = c->h_nraw[t]; td.nact = (td.nraw + 15) / 16 * 16;
+        td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.pad_ = 0;
+        td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 15) / 16 * 16;
         size_t d = (size_t)4 * td.nact * LDP;
         if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); off = 0; foff = 0; }
         td.panel_off = (long long)off; td.fidx_off = (long long)foff;
@@ -281,17 +317,22 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     }
     fidx_max = std::max(fidx_max, foff);
     batch_start.push_back(ntiles);
+    // inside a batch the contraction kernel pulls tiles from an atomic counter: longest first (cost ~ nact^2)
+    for (size_t b = 0; b + 1 < batch_start.size(); ++b)
+        std::stable_sort(c->h_tiles + batch_start[b], c->h_tiles + batch_start[b + 1],
+                         [](const TileDesc &x, const TileDesc &y) { return x.nact > y.nact; });
     if (c->panel.ensure(std::max<size_t>(pool_doubles, 2) * 8) || c->fidx.ensure(std::max<size_t>(fidx_max, 1) * 4))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
     CUDA_TRY(cudaMemcpyAsync(c->tiles.p, c->h_tiles, (size_t)ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
 
-    float ms_basis = 0, ms_contract = 0;
-    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
+    const size_t nbatch = batch_start.size() - 1;
+    if (prof) while (c->evpool.size() < 3 * nbatch) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); c->evpool.push_back(e); }
+    for (size_t b = 0; b < nbatch; ++b) {
         const int t0 = batch_start[b], nb = batch_start[b + 1] - t0;
         if (nb <= 0) continue;
-        if (prof) cudaEventRecord(c->ev[3], st);
+        if (prof) cudaEventRecord(c->evpool[3 * b], st);
         launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(), st);
-        if (prof) cudaEventRecord(c->ev[4], st);
+        if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
         JtensorArgs a;
         a.tiles = c->tiles.as<TileDesc>() + t0; a.ntiles = nb; a.counter = c->misc.as<int>();
@@ -302,19 +343,19 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         launch_jtensor(a, c->opts.giao != 0, c->nsm, st);
         CUDA_TRY(cudaGetLastError());
         c->stats.launches += 2;
-        if (prof) {
-            cudaEventRecord(c->ev[5], st);
-            CUDA_TRY(cudaEventSynchronize(c->ev[5]));
-            float m1 = 0, m2 = 0;
-            cudaEventElapsedTime(&m1, c->ev[3], c->ev[4]); cudaEventElapsedTime(&m2, c->ev[4], c->ev[5]);
-            ms_basis += m1; ms_contract += m2;
-        }
+        c->stats.contract_launches += 1;
+        if (prof) cudaEventRecord(c->evpool[3 * b + 2], st);
     }
     if (prof) {
+        CUDA_TRY(cudaStreamSynchronize(st));
         float m = 0;
         cudaEventElapsedTime(&m, c->ev[0], c->ev[1]); c->stats.ms_sort += m;
         cudaEventElapsedTime(&m, c->ev[1], c->ev[2]); c->stats.ms_tiles += m;
-        c->stats.ms_basis += ms_basis; c->stats.ms_contract += ms_contract;
+        for (size_t b = 0; b < nbatch; ++b) {
+            if (batch_start[b + 1] - batch_start[b] <= 0) continue;
+            cudaEventElapsedTime(&m, c->evpool[3 * b], c->evpool[3 * b + 1]); c->stats.ms_basis += m;
+            cudaEventElapsedTime(&m, c->evpool[3 * b + 1], c->evpool[3 * b + 2]); c->stats.ms_contract += m;
+        }
     }
     c->stats.n_points += n; c->stats.n_tiles += ntiles; c->stats.sum_nact += sum_nact; c->stats.executed_flops += flops;
     const double nbf = c->hb.nbf;
@@ -434,6 +475,7 @@ int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const d
     if (n == 0) return 0;
     const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
     cudaStream_t st = c->stream;
+    cudaEventRecord(c->ev_call[0], st);
     const double *d_r = nullptr;
     if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
     double *d_tens = tens;
@@ -477,7 +519,9 @@ int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const d
         if (edens) CUDA_TRY(cudaMemcpyAsync(edens, d_edens, nf * 8, cudaMemcpyDeviceToHost, st));
         if (divj) CUDA_TRY(cudaMemcpyAsync(divj, d_divj, nf * 8, cudaMemcpyDeviceToHost, st));
     }
+    cudaEventRecord(c->ev_call[1], st);
     CUDA_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->stats.ms_total, c->ev_call[0], c->ev_call[1]);
     return 0;
 }
 

@@ -15,24 +15,40 @@ __constant__ signed char c_lmn[2][6][21][3];
 void upload_component_tables(const signed char *host_tab) { cudaMemcpyToSymbol(c_lmn, host_tab, 2 * 6 * 21 * 3); }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t spread20(uint32_t v) {   // 20 bits -> every third bit of 60
-    uint64_t x = v & 0xFFFFFu;
-    x = (x | (x << 32)) & 0x1F00000000FFFFull;
-    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
-    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
-    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
-    x = (x | (x << 2)) & 0x1249249249249249ull;
+__device__ __forceinline__ uint64_t spread16(uint32_t v) {   // 16 bits -> every third bit of 48
+    uint64_t x = v & 0xFFFFu;
+    x = (x | (x << 16)) & 0x0000FF0000FFull;
+    x = (x | (x << 8)) & 0x00F00F00F00Full;
+    x = (x | (x << 4)) & 0x0C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x249249249249ull;
     return x;
 }
 
+// 48-bit 3-D Hilbert index (16 bits per axis, Skilling's axes-to-transpose).  A Hilbert curve is
+// continuous, so any run of 128 consecutive sorted points is spatially compact; a Morton (Z) curve
+// jumps, and the few tiles straddling a jump get a huge bounding sphere => nact ~ nbf => one CTA
+// runs 100x longer than the rest (measured: SMs 5.7% active, profiles/r01_ncu_jtensor_a.txt).
 __global__ void k_morton_keys(const double *__restrict__ r, long n, double lox, double loy, double loz, double inv_cell,
                               uint64_t *__restrict__ keys, int *__restrict__ vals) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double qx = fmin(fmax((r[3 * i + 0] - lox) * inv_cell, 0.0), 1048575.0);
-    double qy = fmin(fmax((r[3 * i + 1] - loy) * inv_cell, 0.0), 1048575.0);
-    double qz = fmin(fmax((r[3 * i + 2] - loz) * inv_cell, 0.0), 1048575.0);
-    keys[i] = spread20((uint32_t)qx) | (spread20((uint32_t)qy) << 1) | (spread20((uint32_t)qz) << 2);
+    uint32_t X[3];
+    X[0] = (uint32_t)fmin(fmax((r[3 * i + 0] - lox) * inv_cell, 0.0), 65535.0);
+    X[1] = (uint32_t)fmin(fmax((r[3 * i + 1] - loy) * inv_cell, 0.0), 65535.0);
+    X[2] = (uint32_t)fmin(fmax((r[3 * i + 2] - loz) * inv_cell, 0.0), 65535.0);
+    for (uint32_t Q = 1u << 15; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (X[d] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[d]) & P; X[0] ^= t; X[d] ^= t; }
+        }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = 1u << 15; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    keys[i] = (spread16(X[0]) << 2) | (spread16(X[1]) << 1) | spread16(X[2]);
     vals[i] = (int)i;
 }
 
@@ -43,11 +59,11 @@ void launch_morton_keys(const double *r, long n, const double *bbox_lo, double i
 
 size_t sort_temp_bytes(long n) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, 0, 60);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, 0, 48);
     return bytes;
 }
 void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s) {
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 60, s);
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 48, s);
 }
 
 __global__ void k_gather_points(const double *__restrict__ r, const int *__restrict__ perm, long n, double *__restrict__ rsx,
@@ -111,31 +127,43 @@ __device__ __forceinline__ T block_reduce_128(T v, Op op, T *s4) {   // 128 thre
 }
 
 __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
-                                                    const double *__restrict__ rsz, long n, TileGeo *__restrict__ geo,
-                                                    int *__restrict__ nraw) {
+                                                    const double *__restrict__ rsz, const TileSeg *__restrict__ segs,
+                                                    TileGeo *__restrict__ geo, TileInfo *__restrict__ info) {
     __shared__ double s4[4];
     __shared__ int i4[4];
-    long tile = blockIdx.x, pt = tile * MT + threadIdx.x;
-    bool valid = pt < n;
-    long p0 = tile * MT;
-    double x = rsx[valid ? pt : p0], y = rsy[valid ? pt : p0], z = rsz[valid ? pt : p0];
+    __shared__ unsigned long long u4[4];
+    const TileSeg sg = segs[blockIdx.x];
+    const bool valid = threadIdx.x < sg.npts;
+    const long pt = sg.pt0 + (valid ? threadIdx.x : 0);
+    const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
     auto fmn = [](double a, double b) { return fmin(a, b); };
     auto fmx = [](double a, double b) { return fmax(a, b); };
-    double cx = 0.5 * (block_reduce_128(x, fmn, s4) + block_reduce_128(x, fmx, s4));
-    double cy = 0.5 * (block_reduce_128(y, fmn, s4) + block_reduce_128(y, fmx, s4));
-    double cz = 0.5 * (block_reduce_128(z, fmn, s4) + block_reduce_128(z, fmx, s4));
-    double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
-    double rho = block_reduce_128(d, fmx, s4);
+    const double cx = 0.5 * (block_reduce_128(x, fmn, s4) + block_reduce_128(x, fmx, s4));
+    const double cy = 0.5 * (block_reduce_128(y, fmn, s4) + block_reduce_128(y, fmx, s4));
+    const double cz = 0.5 * (block_reduce_128(z, fmn, s4) + block_reduce_128(z, fmx, s4));
+    const double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
+    const double rho = block_reduce_128(d, fmx, s4);
+    // largest gap between consecutive points of the sorted run (where a curve jump would be cut)
+    unsigned long long gi = 0;
+    if ((int)threadIdx.x + 1 < sg.npts) {
+        const double ex = rsx[pt + 1] - x, ey = rsy[pt + 1] - y, ez = rsz[pt + 1] - z;
+        gi = ((unsigned long long)__float_as_uint((float)sqrt(ex * ex + ey * ey + ez * ez)) << 32) | threadIdx.x;
+    }
+    auto umx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
+    gi = block_reduce_128(gi, umx, u4);
     int cnt = 0;
     for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, cx, cy, cz, rho, nsh, nfun); cnt += nfun; }
     auto iadd = [](int a, int b) { return a + b; };
     cnt = block_reduce_128(cnt, iadd, i4);
-    if (threadIdx.x == 0) { geo[tile] = TileGeo{cx, cy, cz, rho}; nraw[tile] = cnt; }
+    if (threadIdx.x == 0) {
+        geo[blockIdx.x] = TileGeo{cx, cy, cz, rho};
+        info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt};
+    }
 }
-void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, int ntiles, TileGeo *geo,
-                       int *nraw, cudaStream_t s) {
+void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
+                       TileGeo *geo, TileInfo *info, cudaStream_t s) {
     if (ntiles <= 0) return;
-    k_tile_count<<<ntiles, 128, 0, s>>>(B, rsx, rsy, rsz, n, geo, nraw);
+    k_tile_count<<<ntiles, 128, 0, s>>>(B, rsx, rsy, rsz, segs, geo, info);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,7 +180,7 @@ __global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__res
     __shared__ int s_base[2];
     const TileDesc td = tiles[blockIdx.x];
     if (td.nact == 0) return;
-    const TileGeo tg = geo[td.pt0 / MT];
+    const TileGeo tg = geo[td.geo];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *panel = panel_pool + td.panel_off;
     int *fidx = fidx_pool + td.fidx_off;

@@ -43,19 +43,22 @@ struct TileDesc {
     int pt0, npts;      // range in the sorted point list
     int nact;           // active slots, padded to a multiple of 16 (0: nothing within screening range)
     int nraw;           // unpadded active function count
+    int geo, pad_;      // index into the TileGeo array
     long long panel_off;  // doubles, into the panel pool: 4 planes x nact x LDP
     long long fidx_off;   // ints, into the index pool
 };
 
 struct TileGeo { double cx, cy, cz, rho; };
+struct TileSeg { int pt0, npts; };                         // a tile = npts <= MT consecutive points of the sorted list
+struct TileInfo { float rho, gmax; int imax, nraw; };      // radius, largest consecutive gap (and where), active functions
 
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
 void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s);
 void launch_gather_points(const double *r, const int *perm, long n, double *rsx, double *rsy, double *rsz, cudaStream_t s);
 void launch_grid_points(const double *origin_basv /*12 doubles, device*/, const double *p0, const double *p1, const double *p2,
                         int n0, int n1, int n2, long lo, long hi, double *r, cudaStream_t s);
-void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, int ntiles,
-                       TileGeo *geo, int *nraw, cudaStream_t s);
+void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
+                       TileGeo *geo, TileInfo *info, cudaStream_t s);
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s);
 size_t sort_temp_bytes(long n);
