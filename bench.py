@@ -5,9 +5,10 @@ Workload (configs[4], "nanoring-size synthetic"): 278 carbon-like centres x 36 c
 (def2-TZVP carbon shells) = 10 008 basis functions, compact hexagonal flake, seeded random symmetric D
 and antisymmetric P_x,P_y,P_z; cdens tensors on a 256^3 even grid over the bounding box + 8 bohr.
 One STEP = one pass of the whole hot path (spatial sort -> tile screening -> basis panels -> DMMA
-contraction + fused tensor epilogue) over one slab of that grid: the 32 k-planes {k : k mod 8 == rank mod 8}
-(2 097 152 points), so that 8 ranks cover the full grid once per step and every rank does equal work
-(weak scaling; there is no data-path collective in cdens mode).
+contraction + fused tensor epilogue) over one brick of that grid: octant (rank mod 8) = a contiguous
+128^3 sub-grid at full resolution (2 097 152 points), so that 8 ranks cover the full grid once per step.
+The flake is (approximately) mirror-symmetric in x, y and z, so the octants carry near-equal work; the
+reported time is the max over ranks (weak scaling; there is no data-path collective in cdens mode).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU (oracle port)
@@ -40,10 +41,13 @@ def build_workload(natoms, grid_n):
 
 
 def slab_points(origin, basv, pts, slab, nslab=NSLAB):
-    """points of the k-planes {k : k mod nslab == slab}, i fastest (grid.f90:478-511)"""
-    ks = np.arange(slab, len(pts[2]), nslab)
-    x = origin[0] + pts[0]; y = origin[1] + pts[1]; z = origin[2] + pts[2][ks]
-    r = np.empty((len(ks), len(y), len(x), 3))
+    """points of octant `slab` of the grid (bit 0: upper x half, bit 1: upper y half, bit 2: upper z half),
+    i fastest inside the brick like the reference's flat index (grid.f90:478-511)"""
+    assert nslab == 8
+    h = [len(p) // 2 for p in pts]
+    sel = [np.arange(h[d]) + (h[d] if (slab >> d) & 1 else 0) for d in range(3)]
+    x = origin[0] + pts[0][sel[0]]; y = origin[1] + pts[1][sel[1]]; z = origin[2] + pts[2][sel[2]]
+    r = np.empty((len(z), len(y), len(x), 3))
     r[..., 0] = x[None, None, :]; r[..., 1] = y[None, :, None]; r[..., 2] = z[:, None, None]
     return r.reshape(-1, 3)
 
@@ -144,7 +148,7 @@ def main():
     K = max(args.steps, 1)
 
     cfg = {"workload": f"synthetic hex flake {args.natoms} C-like centres x 36 fn (nbf={args.natoms * 36}), cdens J^B tensors, "
-                       f"{args.grid}^3 even grid over bbox+8 bohr, step = k-planes (k mod 8 == rank) = {args.grid ** 3 // NSLAB} points/GPU",
+                       f"{args.grid}^3 even grid over bbox+8 bohr, step = octant (rank mod 8) = {args.grid ** 3 // NSLAB} points/GPU",
            "nbf": args.natoms * 36, "grid": [args.grid] * 3, "points_per_step_per_gpu": args.grid ** 3 // NSLAB,
            "spincase": "total (closed shell)", "giao": True, "screening_thrs": 1e-8,
            "cache": "inputs larger than L2 (contraction operand 7*nbf^2*8 B = %.1f GB, panels streamed)" % (7 * (args.natoms * 36) ** 2 * 8 / 1e9),

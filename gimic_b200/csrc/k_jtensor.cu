@@ -19,7 +19,7 @@
 // Screened functions are exact zeros in the reference, so restricting mu, nu to the tile's active
 // set changes nothing but the order of summation.
 //
-// Mapping: 256 threads = 8 warps; warp w owns rows 16w..16w+15 of the tile and all 7x2 n8 tiles of
+// Mapping: 8 consumer warps + 1 producer warp; consumer warp w owns rows 16w..16w+15 of the tile and all 7x2 n8 tiles of
 // the current 16-wide nu chunk (56 fp64 accumulators / thread), so the per-point epilogue sums stay
 // in registers for the whole tile and need only a 4-lane shuffle reduction at the end.
 // mma.sync.m16n8k8.f64 lowers to 4 DMMA.8x8x4 on sm_100a (there is no FP64 tcgen05 kind).
@@ -32,51 +32,122 @@ __device__ __forceinline__ void mma_16x8x8_f64(double (&c)[4], double a0, double
                  : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
                  : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
 }
-__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+// ---- async-copy / mbarrier primitives (sm_90+ PTX; SASS: LDGSTS, UBLKCP, SYNCS) ---------------------
+__device__ __forceinline__ void cp_async_8(uint32_t smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t mbar) {   // arrive when this thread's prior cp.async land
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+// 1-D bulk TMA copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void *gmem, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gmem), "r"(bytes), "r"(mbar) : "memory");
+}
+
+constexpr int NCONSUMER_WARPS = 8;
+constexpr int NPRODUCER_WARPS = 4;   // one warpgroup, so that setmaxnreg can hand its registers to the consumers
+constexpr int NTHREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
+constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 = 64512 <= 65536
 
 template <int NQ>
 struct Smem {
     static constexpr int A_DOUBLES = BK * LDP;
     static constexpr int B_DOUBLES = NQ * BK * LDB;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
-    static constexpr size_t BYTES = (size_t)STAGES * STAGE_DOUBLES * 8 + (size_t)FCAP * 4 + 16;
+    static constexpr size_t BAR_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;
+    static constexpr size_t BYTES = BAR_OFF + 2 * STAGES * 8 + 16;
 };
 
+// Tile bookkeeping shared by both roles: every thread of the CTA calls this once per tile (two CTA barriers).
+__device__ __forceinline__ int next_tile(const JtensorArgs &a, int *s_tile) {
+    __syncthreads();                                  // everybody is done with the previous tile (and with *s_tile)
+    if (threadIdx.x == 0) *s_tile = atomicAdd(a.counter, 1);
+    __syncthreads();
+    return *s_tile;
+}
+
 template <bool GIAO>
-__global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
+__device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_base, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
     constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
     using SM = Smem<NQ>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_stage = reinterpret_cast<double *>(smem_raw);
-    int *s_fidx = reinterpret_cast<int *>(smem_raw + (size_t)STAGES * SM::STAGE_DOUBLES * 8);
-    int *s_tile = s_fidx + FCAP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t git = 0;
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        if (td.nact == 0) continue;
+        const int nact = td.nact;
+        const int nkc = (nact + BK - 1) / BK, nvc = nact / NV;
+        const uint32_t NIT = (uint32_t)nkc * nvc;
+        const double *panel = a.panel_pool + td.panel_off;
+        const int *fidx = a.fidx_pool + td.fidx_off;
+        {
+        // ===================================== producer warps =====================================
+        const int pw = warp - NCONSUMER_WARPS;
+        const int ldn = lane & 15, ldk0 = (lane >> 4) + 2 * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0+8, ...
+        int kc = 0, vc = 0;
+        long nu = fidx[ldn];
+        for (uint32_t itl = 0; itl < NIT; ++itl) {
+            const uint32_t gi = git + itl, s = gi % STAGES, ph = (gi / STAGES) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            const int kcnt = min(BK, nact - kc * BK);
+            const uint32_t sA = s_base + (uint32_t)(s * SM::STAGE_DOUBLES * 8), sB = sA + SM::A_DOUBLES * 8;
+            if (pw == 0 && lane == 0) {
+                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kcnt * LDP * 8));
+                tma_bulk_g2s(sA, panel + (long)kc * BK * LDP, (uint32_t)(kcnt * LDP * 8), bar_full + 8 * s);
+            }
+            const double *srcB = a.Bop + nu;
+            const uint32_t dstB = sB + (uint32_t)(ldn * 8);
+#pragma unroll 4
+            for (int k = ldk0; k < kcnt; k += 2 * NPRODUCER_WARPS) {
+                const long mu = fidx[kc * BK + k];
+                const double *src = srcB + mu * a.ldb;
+                const uint32_t dst = dstB + (uint32_t)(k * LDB * 8);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) cp_async_8(dst + (uint32_t)(q * BK * LDB * 8), src + q * a.plane_stride);
+            }
+            cp_async_arrive_noinc(bar_full + 8 * s);
+            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[vc * NV + ldn]; }
+        }
+        }
+        git += NIT;
+    }
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <bool GIAO>
+__device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double *s_stage, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
+    constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
+    using SM = Smem<NQ>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = warp * 16;
-    // loader roles
-    const int ldn = tid & 15, ldk = tid >> 4;   // B gather: this thread fetches element (k = ldk, nu = ldn) of all NQ planes
-
+    uint32_t git = 0;
     for (;;) {
-        __syncthreads();
-        if (tid == 0) *s_tile = atomicAdd(a.counter, 1);
-        __syncthreads();
-        const int tile = *s_tile;
+        const int tile = next_tile(a, s_tile);
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
         const int rowA = row0 + g, rowB = row0 + g + 8;
         const bool vA = rowA < td.npts, vB = rowB < td.npts;
-
         if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
             if (t == 0) {
                 if (vA) { long o = a.perm[td.pt0 + rowA]; for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
@@ -85,18 +156,13 @@ __global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
             continue;
         }
         const int nact = td.nact;
-        const int nkc = nact / BK, nvc = nact / NV;
-        const long NIT = (long)nkc * nvc;
+        const int nkc = (nact + BK - 1) / BK, nvc = nact / NV;
+        const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
         const long plane = (long)nact * LDP;
-        const int *gfidx = a.fidx_pool + td.fidx_off;
-        const int *fidx = gfidx;
-        if (nact <= FCAP) {
-            for (int i = tid; i < nact; i += 256) s_fidx[i] = gfidx[i];
-            fidx = s_fidx;
-        }
-        __syncthreads();
-
+        const int *fidx = a.fidx_pool + td.fidx_off;
+        {
+        // ===================================== consumer warps =====================================
         // coordinates of this thread's two points (absolute, as r enters jtensor.F90:112 and bfeval.f90:168-189)
         const long pA = td.pt0 + (vA ? rowA : 0), pB = td.pt0 + (vB ? rowB : 0);
         const double rAx = a.rsx[pA], rAy = a.rsy[pA], rAz = a.rsz[pA];
@@ -105,38 +171,10 @@ __global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
         double eA[13], eB[13];   // Tp(m,b) at [m + 3b], V_d at [9 + d], rho at [12]
 #pragma unroll
         for (int i = 0; i < 13; ++i) { eA[i] = 0.0; eB[i] = 0.0; }
-
-        auto issue = [&](long itl) {
-            if (itl < NIT) {
-                const int vc = (int)(itl / nkc), kc = (int)(itl - (long)vc * nkc);
-                double *sA = s_stage + (size_t)(itl % STAGES) * SM::STAGE_DOUBLES;
-                double *sB = sA + SM::A_DOUBLES;
-                // A: Phi plane rows [kc*BK, kc*BK+BK) x 128 points, 16 B chunks
-                const double *srcA = panel + (long)kc * BK * LDP;
-#pragma unroll
-                for (int i = 0; i < (BK * MT / 2) / 256; ++i) {
-                    int c = tid + 256 * i, k = c >> 6, c2 = (c & 63) * 2;
-                    cp_async_16(sA + k * LDP + c2, srcA + (long)k * LDP + c2);
-                }
-                // B: gathered element (mu, nu) of every operand plane
-                const long mu = fidx[kc * BK + ldk], nu = fidx[vc * NV + ldn];
-                const double *srcB = a.Bop + mu * a.ldb + nu;
-                double *dstB = sB + ldk * LDB + ldn;
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) cp_async_8(dstB + q * BK * LDB, srcB + q * a.plane_stride);
-            }
-            cp_async_commit();
-        };
-
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) issue(s);
-
         double acc[NQ][2][4];
         int kc = 0, vc = 0;
-        for (long it = 0; it < NIT; ++it) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads();
-            issue(it + STAGES - 1);
+        for (uint32_t it = 0; it < NIT; ++it) {
+            const uint32_t gi = git + it, s = gi % STAGES, ph = (gi / STAGES) & 1;
             if (kc == 0) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
@@ -145,10 +183,12 @@ __global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
             }
-            const double *sA = s_stage + (size_t)(it % STAGES) * SM::STAGE_DOUBLES;
+            const int nks = min(BK, nact - kc * BK) / 8;
+            const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
-#pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
+            mbar_wait(bar_full + 8 * s, ph);
+#pragma unroll 2
+            for (int ks = 0; ks < nks; ++ks) {
                 const double *pa = sA + (ks * 8 + t) * LDP + row0 + g;
                 const double a0 = pa[0], a1 = pa[8], a2 = pa[4 * LDP], a3 = pa[4 * LDP + 8];
                 const double *pb = sB + (ks * 8 + t) * LDB + g;
@@ -160,8 +200,10 @@ __global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
                         mma_16x8x8_f64(acc[q][h], a0, a1, a2, a3, b0, b1);
                     }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
             if (++kc == nkc) {
-                // ---- fused epilogue for nu chunk vc -------------------------------------------------
+                // ---- fused epilogue for nu chunk vc ---------------------------------------------
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -195,7 +237,6 @@ __global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
                 kc = 0; ++vc;
             }
         }
-        cp_async_wait<0>();
 
         // ---- reduce over the 4 lanes of a quad (they hold different nu), finalise, store ----------
 #pragma unroll
@@ -230,6 +271,37 @@ __global__ void __launch_bounds__(256, 1) k_jtensor(JtensorArgs a) {
                 if (a.edens) a.edens[o] = rho;
             }
         }
+        }
+        git += NIT;
+    }
+}
+
+// Pipeline: warps 8-11 are producers.  Per stage they (1) wait for the slot to be released by the 8 consumer warps
+// (empty barrier), (2) issue ONE bulk-TMA copy of the contiguous Phi panel rows [kc*BK, +kcnt) x 132 doubles
+// (expect_tx on the full barrier) and (3) gather the density elements B_q[fidx[k]][fidx[nu]] of all NQ planes with
+// 8-byte cp.async, whose completion arrives on the same full barrier.  Consumer warps only wait(full) -> LDS + DMMA ->
+// arrive(empty); nobody executes a CTA-wide barrier inside a tile.  The two roles are separate code paths so that
+// setmaxnreg can give the consumers 232 registers (ptxas budgets each path by the setmaxnreg that dominates it).
+template <bool GIAO>
+__global__ void __launch_bounds__(NTHREADS, 1) k_jtensor(JtensorArgs a) {
+    constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
+    using SM = Smem<NQ>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_stage = reinterpret_cast<double *>(smem_raw);
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bar_full = s_base + (uint32_t)SM::BAR_OFF, bar_empty = bar_full + STAGES * 8;
+    int *s_tile = reinterpret_cast<int *>(smem_raw + SM::BAR_OFF + 2 * STAGES * 8);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, NPRODUCER_WARPS * 32 + 1); mbar_init(bar_empty + 8 * s, NCONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ((threadIdx.x >> 5) >= NCONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        producer_role<GIAO>(a, s_base, bar_full, bar_empty, s_tile);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+        consumer_role<GIAO>(a, s_stage, bar_full, bar_empty, s_tile);
     }
 }
 
@@ -244,8 +316,8 @@ void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
         configured = true;
     }
     int grid = a.ntiles < nsm ? a.ntiles : nsm;
-    if (giao) k_jtensor<true><<<grid, 256, Smem<NQ_GIAO>::BYTES, s>>>(a);
-    else k_jtensor<false><<<grid, 256, Smem<NQ_NOGIAO>::BYTES, s>>>(a);
+    if (giao) k_jtensor<true><<<grid, NTHREADS, Smem<NQ_GIAO>::BYTES, s>>>(a);
+    else k_jtensor<false><<<grid, NTHREADS, Smem<NQ_NOGIAO>::BYTES, s>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------------

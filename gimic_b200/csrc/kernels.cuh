@@ -19,11 +19,10 @@ namespace gb {
 
 constexpr int MT = 128;    // points per tile (8 m16 row blocks, one per warp of k_jtensor)
 constexpr int LDP = 132;   // panel row stride in doubles: 132 = 4 (mod 16) -> conflict-free A-fragment LDS.64
-constexpr int BK = 16;     // K slots per pipeline stage
+constexpr int BK = 32;     // K slots per pipeline stage (the last stage of a K sweep may hold 16)
 constexpr int NV = 16;     // nu slots per accumulator chunk (2 n8 tiles per operand matrix)
 constexpr int LDB = 20;    // smem row stride of a B tile: 20 = 4 (mod 16) -> conflict-free B-fragment LDS.64
-constexpr int STAGES = 4;  // cp.async pipeline depth
-constexpr int FCAP = 8192; // active-index list cached in smem up to this many slots
+constexpr int STAGES = 3;  // mbarrier pipeline depth (3 x 69.6 KB)
 constexpr int NQ_GIAO = 7, NQ_NOGIAO = 4;
 
 struct DevBasis {

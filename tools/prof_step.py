@@ -16,8 +16,7 @@ a = ap.parse_args()
 sh, dens, nbf, origin, basv, pts = bench.build_workload(a.natoms, a.grid)
 g = gimic_b200.Gimic.from_arrays(dens_alpha=synthetic.dens_to_colmajor(dens), **sh)
 r = bench.slab_points(origin, basv, pts, 0)
-mid = r.shape[0] // 2
-r = np.ascontiguousarray(r[mid - a.points // 2: mid + a.points // 2])
+r = np.ascontiguousarray(r[-a.points:])   # the planes of octant 0 closest to the molecular plane
 g.set_profiling(True)
 for i in range(a.reps):
     t0 = time.perf_counter(); t = g.jtensors(r); dt = time.perf_counter() - t0
