@@ -22,15 +22,18 @@
 // Mapping: 8 consumer warps + 1 producer warp; consumer warp w owns rows 16w..16w+15 of the tile and all 7x2 n8 tiles of
 // the current 16-wide nu chunk (56 fp64 accumulators / thread), so the per-point epilogue sums stay
 // in registers for the whole tile and need only a 4-lane shuffle reduction at the end.
-// mma.sync.m16n8k8.f64 lowers to 4 DMMA.8x8x4 on sm_100a (there is no FP64 tcgen05 kind).
+// mma.sync.m16n8k4.f64 lowers to 2 DMMA.8x8x4 on sm_100a (there is no FP64 tcgen05 kind).
 #include "kernels.cuh"
 
 namespace gb {
 
-__device__ __forceinline__ void mma_16x8x8_f64(double (&c)[4], double a0, double a1, double a2, double a3, double b0, double b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+// m16n8k4 = two independent DMMA.8x8x4 (rows 0-7 / 8-15).  The k8 form expands to four DMMAs of which the second pair
+// depends on the first through the accumulator, back to back (measured: 37% fixed-latency "wait" stalls); with k4 the
+// dependent pair is a separate instruction 14 accumulator tiles later.
+__device__ __forceinline__ void mma_16x8x4_f64(double (&c)[4], double a0, double a1, double b0) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                  : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
-                 : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+                 : "d"(a0), "d"(a1), "d"(b0));
 }
 // ---- async-copy / mbarrier primitives (sm_90+ PTX; SASS: LDGSTS, UBLKCP, SYNCS) ---------------------
 __device__ __forceinline__ void cp_async_8(uint32_t smem, const void *gmem) {
@@ -63,6 +66,7 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void *gmem
                  ::"r"(smem_dst), "l"(gmem), "r"(bytes), "r"(mbar) : "memory");
 }
 
+constexpr int ROWLD = 17;   // doubles per row-table entry: 13 sums + 3 coordinates, padded to an odd stride (bank-conflict-free)
 constexpr int NCONSUMER_WARPS = 8;
 constexpr int NPRODUCER_WARPS = 4;   // one warpgroup, so that setmaxnreg can hand its registers to the consumers
 constexpr int NTHREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
@@ -73,7 +77,8 @@ struct Smem {
     static constexpr int A_DOUBLES = BK * LDP;
     static constexpr int B_DOUBLES = NQ * BK * LDB;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
-    static constexpr size_t BAR_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;
+    static constexpr size_t ROW_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;        // per-row epilogue sums + point coordinates
+    static constexpr size_t BAR_OFF = ROW_OFF + (size_t)MT * ROWLD * 8;
     static constexpr size_t BYTES = BAR_OFF + 2 * STAGES * 8 + 16;
 };
 
@@ -135,7 +140,7 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
 }
 
 template <bool GIAO>
-__device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double *s_stage, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
+__device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double *s_stage, double *s_rows, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
     constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
     using SM = Smem<NQ>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -163,14 +168,17 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
         const int *fidx = a.fidx_pool + td.fidx_off;
         {
         // ===================================== consumer warps =====================================
-        // coordinates of this thread's two points (absolute, as r enters jtensor.F90:112 and bfeval.f90:168-189)
-        const long pA = td.pt0 + (vA ? rowA : 0), pB = td.pt0 + (vB ? rowB : 0);
-        const double rAx = a.rsx[pA], rAy = a.rsy[pA], rAz = a.rsz[pA];
-        const double rBx = a.rsx[pB], rBy = a.rsy[pB], rBz = a.rsz[pB];
-
-        double eA[13], eB[13];   // Tp(m,b) at [m + 3b], V_d at [9 + d], rho at [12]
+        // Row table: lane t=0 of a quad owns row A, lane t=1 row B.  [0..12] running sums Tp(m,b) at [m+3b], V_d at [9+d],
+        // rho at [12]; [13..15] the point's absolute coordinates (as r enters jtensor.F90:112 and bfeval.f90:168-189).
+        double *rowA_s = s_rows + rowA * ROWLD, *rowB_s = s_rows + rowB * ROWLD;
+        if (t < 2) {
+            double *rs = t ? rowB_s : rowA_s;
+            const long p = td.pt0 + ((t ? vB : vA) ? (t ? rowB : rowA) : 0);
 #pragma unroll
-        for (int i = 0; i < 13; ++i) { eA[i] = 0.0; eB[i] = 0.0; }
+            for (int i = 0; i < 13; ++i) rs[i] = 0.0;
+            rs[13] = a.rsx[p]; rs[14] = a.rsy[p]; rs[15] = a.rsz[p];
+        }
+        __syncwarp();
         double acc[NQ][2][4];
         int kc = 0, vc = 0;
         for (uint32_t it = 0; it < NIT; ++it) {
@@ -183,27 +191,30 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
             }
-            const int nks = min(BK, nact - kc * BK) / 8;
+            const int nks = min(BK, nact - kc * BK) / 4;
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
             mbar_wait(bar_full + 8 * s, ph);
-#pragma unroll 2
+#pragma unroll 4
             for (int ks = 0; ks < nks; ++ks) {
-                const double *pa = sA + (ks * 8 + t) * LDP + row0 + g;
-                const double a0 = pa[0], a1 = pa[8], a2 = pa[4 * LDP], a3 = pa[4 * LDP + 8];
-                const double *pb = sB + (ks * 8 + t) * LDB + g;
+                // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
+                const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
+                const double a0 = pa[0], a1 = pa[8];
+                const double *pb = sB + (ks * 4 + t) * LDB + g;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const double b0 = pb[q * BK * LDB + h * 8], b1 = pb[q * BK * LDB + 4 * LDB + h * 8];
-                        mma_16x8x8_f64(acc[q][h], a0, a1, a2, a3, b0, b1);
-                    }
+                    for (int h = 0; h < 2; ++h) mma_16x8x4_f64(acc[q][h], a0, a1, pb[q * BK * LDB + h * 8]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
             if (++kc == nkc) {
                 // ---- fused epilogue for nu chunk vc ---------------------------------------------
+                double eA[13], eB[13];
+#pragma unroll
+                for (int i = 0; i < 13; ++i) { eA[i] = 0.0; eB[i] = 0.0; }
+                const double rAx = rowA_s[13], rAy = rowA_s[14], rAz = rowA_s[15];
+                const double rBx = rowB_s[13], rBy = rowB_s[14], rBz = rowB_s[15];
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -234,21 +245,27 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                             e[6] += zz * e1; e[7] += zz * e2; e[8] += zz * e3;
                         }
                     }
+                // reduce over the 4 lanes of the quad (they hold different nu) and add into the row table
+#pragma unroll
+                for (int i = 0; i < 13; ++i) {
+                    eA[i] += __shfl_xor_sync(0xffffffffu, eA[i], 1); eA[i] += __shfl_xor_sync(0xffffffffu, eA[i], 2);
+                    eB[i] += __shfl_xor_sync(0xffffffffu, eB[i], 1); eB[i] += __shfl_xor_sync(0xffffffffu, eB[i], 2);
+                }
+                if (t < 2) {
+                    double *rs = t ? rowB_s : rowA_s;
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) rs[i] += t ? eB[i] : eA[i];
+                }
                 kc = 0; ++vc;
             }
         }
 
-        // ---- reduce over the 4 lanes of a quad (they hold different nu), finalise, store ----------
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-            eA[i] += __shfl_xor_sync(0xffffffffu, eA[i], 1); eA[i] += __shfl_xor_sync(0xffffffffu, eA[i], 2);
-            eB[i] += __shfl_xor_sync(0xffffffffu, eB[i], 1); eB[i] += __shfl_xor_sync(0xffffffffu, eB[i], 2);
-        }
+        // ---- finalise and store ---------------------------------------------------------------------
         if (t < 2) {
             const bool v = t ? vB : vA;
             if (v) {
-                const double *e = t ? eB : eA;
-                const double px = t ? rBx : rAx, py = t ? rBy : rAy, pz = t ? rBz : rAz;
+                const double *e = t ? rowB_s : rowA_s;
+                const double px = e[13], py = e[14], pz = e[15];
                 double ct[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) ct[i] = e[i];
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_jtensor(JtensorArgs a) {
         producer_role<GIAO>(a, s_base, bar_full, bar_empty, s_tile);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-        consumer_role<GIAO>(a, s_stage, bar_full, bar_empty, s_tile);
+        consumer_role<GIAO>(a, s_stage, reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), bar_full, bar_empty, s_tile);
     }
 }
 
