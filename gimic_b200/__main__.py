@@ -1,0 +1,3 @@
+import sys
+from .driver import main
+sys.exit(main())

@@ -1,0 +1,256 @@
+"""Native driver: gimic.inp -> basis/densities on the GPU -> grid + magnetic field -> cdens | integral | edens | divj,
+writing the reference's files and stdout report.  Replaces, for the hot path, `program gimic`
+(src/fgimic/gimic.F90:60-261: initialize, driver, run_cdens, run_integral), jvector_plots
+(src/fgimic/jfield.f90:250-443) and the report printing of src/fgimic/integral.f90:167-183,306-322,502-510.
+
+    python -m gimic_b200 gimic.inp [--workdir DIR]
+
+Under torch.distributed (torchrun, one process per GPU) cdens splits the flat point index into contiguous slabs and
+gathers the tensors on rank 0 (which writes the files, like the reference's MPI path, jfield.f90:90-137); integral mode
+splits plane rows and all-reduces the partial sums.
+"""
+import os
+import sys
+import numpy as np
+
+from . import inp as _inp
+from . import grids, writers
+from .gimic import Gimic, integrate_distributed, slab
+
+SPIN_LABEL = {"total": "total", "alpha": "alpha", "beta": "beta", "spindens": "spin"}
+
+
+def au2si(au):
+    """au2si, globals.f90:309-332 (nA/T per atomic unit of dJ/dB)"""
+    aulength, auspeedoflight, speedoflight = 0.52917726e-10, 137.03599e0, 299792458.0
+    aucharge, hbar = 1.60217733e-19, 1.05457267e-34
+    autime = aulength * auspeedoflight / speedoflight
+    autesla = hbar / aucharge / aulength / aulength
+    return au * (aucharge / autime / autesla) * 1.0e9
+
+
+def read_mol_geometry(mol):
+    """atom symbols and coordinates (bohr) of an INTGRL/MOL file (intgrl.f90:91-115); host-only helper"""
+    with open(mol) as f:
+        lines = f.read().split("\n")
+    natoms = int(lines[3].split()[0])
+    syms, xyz, i = [], [], 5
+    for _ in range(natoms):
+        hdr = lines[i].split()
+        nsh = int(hdr[2]); nblk = [int(x) for x in hdr[3:3 + nsh]]
+        syms.append(lines[i + 1][:2]); xyz.append([float(v.replace("D", "E").replace("d", "e")) for v in lines[i + 1][4:].split()[:3]])
+        i += 2
+        for nb in nblk:
+            for _b in range(nb):
+                npf, ncf = (int(x) for x in lines[i].split()[:2])
+                i += 1
+                for _p in range(npf):          # a primitive's 1+ncf values may wrap over several lines
+                    got = 0
+                    while got < 1 + ncf:
+                        got += len(lines[i].split()); i += 1
+    return syms, np.array(xyz)
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return None, 0, 1
+
+
+class Driver:
+    def __init__(self, inpfile, workdir=None, out=None, device=-1):
+        self.workdir = workdir or os.path.dirname(os.path.abspath(inpfile))
+        self.inp = _inp.parse_file(inpfile)
+        self.dist, self.rank, self.world = _dist()
+        self.out = out if out is not None else sys.stdout
+        I = self.inp
+        if I.get("Advanced.spherical"):
+            raise _inp.InputError("spherical=on is not supported (the reference marks it experts-only/buggy, cao2sao.f90:158); "
+                                  "set Advanced.spherical=off")
+        self.uhf = bool(I.get("openshell"))
+        path = lambda n: n if os.path.isabs(n) else os.path.join(self.workdir, n)
+        self.g = Gimic(path(I.get("basis")), path(I.get("xdens")), uhf=self.uhf, giao=I.get("Advanced.GIAO"),
+                       diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"),
+                       screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device)
+        self.xyz = self.g.atom_coords()
+        self.symbols = self._symbols(path(I.get("basis")))
+        self.grid = grids.from_input(I, self.xyz, self.workdir)
+        self.magnet = grids.get_magnet(self.grid, I.get("magnet_axis"), I.get("magnet"))
+
+    @staticmethod
+    def _symbols(mol):
+        return read_mol_geometry(mol)[0]
+
+    def say(self, s=""):
+        if self.rank == 0:
+            self.out.write(" " + s + "\n" if s else "\n")
+
+    # -------------------------------------------------------------------------------------------------
+    def run(self):
+        I = self.inp
+        if self.rank == 0:
+            writers.write_mol_xyz(os.path.join(self.workdir, "mol.xyz"), self.symbols, self.xyz)
+            writers.write_grid_xyz(os.path.join(self.workdir, "grid.xyz"), self.grid, self.symbols, self.xyz)
+        self.say("   Magnetic field <x,y,z> =" + "".join(f"{b:10.5f}" for b in self.magnet))
+        self.say()
+        self.say("INFO: " + ("Open-shell calculation" if self.uhf else "Closed-shell calculation"))
+        self.say()
+        if I.get("dryrun"):
+            self.say("*** Dry run, not calculating ...")
+            return
+        calc = I.get("calc")
+        if calc == "cdens":
+            self.run_cdens()
+        elif calc == "integral":
+            self.run_integral()
+        elif calc in ("edens", "divj"):
+            self.run_scalar(calc)
+
+    def _tensors(self, spincase):
+        """calc_jtensors (jfield.f90:62-138): slab of the flat index per rank, gathered on rank 0"""
+        grid, n = self.grid, self.grid.n
+        lo, hi = slab(n, self.rank, self.world)
+        if grid.mode == "file":
+            part = self.g.jtensors(grid.points()[lo:hi], spincase)
+        else:
+            part = self.g.jtensors_grid(grid, lo, hi, spincase)
+        if self.world == 1:
+            return part
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        sizes = [slab(n, r, self.world) for r in range(self.world)]
+        mx = max(b - a for a, b in sizes)
+        buf = torch.zeros((mx, 9), dtype=torch.float64, device=dev)
+        buf[: hi - lo] = torch.from_numpy(part).to(dev)
+        gathered = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
+        self.dist.gather(buf, gathered, dst=0)
+        if self.rank != 0:
+            return None
+        return np.concatenate([gathered[r][: b - a].cpu().numpy() for r, (a, b) in enumerate(sizes)])
+
+    def run_cdens(self):
+        """run_cdens (gimic.F90:196-220) + jvector_plots (jfield.f90:250-443)"""
+        self.say("Calculating current density")
+        self.say("*****************************************")
+        cases = [("total", "")] + ([("alpha", "alpha"), ("beta", "beta"), ("spindens", "spindens")] if self.uhf else [])
+        grid, wd, I = self.grid, self.workdir, self.inp
+        for sc, tag in cases:
+            tens = self._tensors(sc)
+            if self.rank != 0:
+                continue
+            r = grid.points()
+            f = self.g.fields_from_tensors(r, tens, self.magnet, jvec=True, jmod=bool(I.get("Essential.jmod")) and grid.is_3d(),
+                                           acid=bool(I.get("Essential.acid")) and grid.is_3d())
+            self.out.write(" magnetic field\n " + "".join(writers._ld_real(b) for b in self.magnet) + "\n \n")
+            jv = f["jvec"]
+            regular = grid.mode in ("std", "base", "bond")
+            if grid.gauss and grid.mode != "file":
+                writers.write_jmod_txt(os.path.join(wd, f"jmod{tag}.txt"), grid, jv, regular=regular and
+                                       (grid.mode == "bond" or grid.gtype == "even"))
+            if grid.is_3d():
+                if I.get("Essential.acid"):
+                    writers.write_vti_scalar(os.path.join(wd, "acid.vti"), grid, f["acid"])
+                if I.get("Essential.jmod"):
+                    writers.write_vti_scalar(os.path.join(wd, f"jmod{tag}.vti"), grid, f["jmod"])
+            if grid.mode in ("std", "base", "bond") and grid.gtype == "even":
+                writers.write_vti_vector(os.path.join(wd, f"jvec{tag}.vti"), grid, jv)
+            elif (grid.mode in ("std", "base") and grid.gauss) or grid.mode == "file":
+                ele = os.path.join(wd, "grid.1.ele")
+                if os.path.exists(ele):
+                    writers.write_vtu_vector(os.path.join(wd, "jvec.vtu"), r, jv, writers.read_ele(ele))
+                else:
+                    self.out.write(" not writing a vtu file, because the file grid.1.ele was not found.\n")
+
+    def _note_spin(self, sc):
+        if self.uhf:
+            self.say(f"*** Integrating {SPIN_LABEL[sc]} density")
+
+    def run_integral(self):
+        """run_integral (gimic.F90:222-261) with the report formats of integral.f90:167-183,306-322,502-510"""
+        I = self.inp
+        self.say("Integrating current density")
+        self.say("*****************************************")
+        cases = ["total"] + (["alpha", "beta", "spindens"] if self.uhf else [])
+        what = 1 | (2 if I.get("Essential.jmod") else 0) | (4 if I.get("Essential.acid") else 0)
+        res = {sc: integrate_distributed(self.g, self.grid, self.magnet, sc, what if sc == "total" else (what & 3)) for sc in cases}
+        self.results = res
+        bar = "*" * 60
+        bound = self.grid.radius
+        def field_line():
+            self.say("   Magnetic field <x,y,z> =" + "".join(f"{b:10.5f}" for b in self.magnet))
+            self.say()
+        def block(lbl_au, lbl_si, x, p, n):
+            self.say()
+            self.say(bar)
+            self.say(f"{lbl_au}{x:13.6f}")
+            self.say(f"      Positive contribution:{p:13.6f}  ({au2si(p):11.6f} )")
+            self.say(f"      Negative contribution:{n:13.6f}  ({au2si(n):11.6f} )")
+            self.say()
+            self.say(f"{lbl_si}{au2si(x):13.6f}")
+            self.say(f"      (conversion factor)  :{au2si(1.0):13.6f}")
+            self.say(bar)
+            self.say()
+        if I.get("Essential.jmod"):
+            self.say("*** Integrating |J|")
+            for sc in cases:
+                self._note_spin(sc)
+                field_line()
+                if bound < 1.0e10:
+                    self.say(f" Integration bound set to radius {bound}")
+                block("Induced mod current (au)   :", "Induced mod current (nA/T) :", *res[sc][3:6])
+            self.say()
+        else:
+            self.out.write("  Jmod integration skipped.\n")
+        self.say("*** Integrating current")
+        for sc in cases:
+            self._note_spin(sc)
+            field_line()
+            if bound < 1.0e10:
+                self.say(f" Integration bound set to radius {bound}")
+            block("   Induced current (au)    :", "   Induced current (nA/T)  :", *res[sc][0:3])
+        self.say()
+        if I.get("Essential.acid"):
+            self.say("*** Integrating ACID density")
+            acid = float(np.sqrt(res["total"][6]))
+            self.say()
+            self.say(bar)
+            self.say(f"   ACID (au) sqrt(delta J^2):{acid:13.6f}")
+            self.say(f"   ACID (nA/T)              :{au2si(acid):13.6f}")
+            self.say()
+            self.say(bar)
+            self.say()
+
+    def run_scalar(self, calc):
+        """edens / divj: whitelisted by the reference front-end (src/gimic.in:267) but not implemented at this commit.
+        Defined here as rho = Phi^T D Phi and div(T.B) (central differences); written as <calc>.vti on 3-D even grids and
+        <calc>.txt ('x y z value', bohr) otherwise.  No reference output exists: parity unpinned."""
+        grid = self.grid
+        r = grid.points()
+        f = self.g.fields(r, self.magnet, "total", edens=(calc == "edens"), divj=(calc == "divj"))
+        if self.rank != 0:
+            return
+        if grid.mode != "file" and grid.gtype == "even" and grid.npts[0] > 1 and grid.npts[1] > 1:
+            writers.write_vti_scalar(os.path.join(self.workdir, f"{calc}.vti"), grid, f[calc])
+        else:
+            np.savetxt(os.path.join(self.workdir, f"{calc}.txt"), np.column_stack([r, f[calc]]), fmt="%20.12e")
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(prog="gimic_b200", description="GIMIC grid hot path on B200 (cdens / integral / edens / divj)")
+    ap.add_argument("infile", nargs="?", default="gimic.inp")
+    ap.add_argument("--workdir", default=None)
+    a = ap.parse_args(argv)
+    device = -1
+    if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        import torch.distributed as dist
+        device = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    Driver(a.infile, a.workdir, device=device).run()
+    return 0

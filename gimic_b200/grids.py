@@ -1,0 +1,220 @@
+"""Grid geometry and magnetic-field direction: host-side counterpart of src/fgimic/grid.f90 and magnet.f90.
+
+Builds the `Grid` objects (origin, basis vectors, axis points and weights, radius) that the C ABI consumes:
+std/base grids (grid.f90:140-163), bond grids (grid.f90:165-276), file grids (grid.f90:543-576), even / gauss /
+lobatto point distributions (grid.f90:291-373), rotation (grid.f90:697-769), grid_center (grid.f90:529-541) and
+get_magnet / check_field (magnet.f90:11-86).  Quadrature nodes come from the library (gimic_b200_gauss_points).
+"""
+import math
+import numpy as np
+
+from .gimic import Grid
+from .gengauss import gausspoints
+
+PII = 3.141592653589793  # globals.f90:41
+
+
+def _unit(v):
+    v = np.asarray(v, dtype=np.float64)
+    return v / math.sqrt(float(np.dot(v, v)))
+
+
+class GridSpec(Grid):
+    """Grid + what the driver needs beyond gridpoint/get_weight: mode, type, ortho (bond-plane normal), bond centre."""
+
+    def __init__(self, origin, basv, pts, wgt, radius, mode, gtype, ortho, lengths, center_bond=None, xdata=None):
+        super().__init__(origin, basv, pts, wgt, radius)
+        self.mode, self.gtype, self.gauss = mode, gtype, gtype in ("gauss", "lobatto")
+        self.ortho = np.asarray(ortho, dtype=np.float64)
+        self.lengths = np.asarray(lengths, dtype=np.float64)
+        self.center_bond = center_bond
+        self.xdata = xdata            # file grids: explicit points (n, 3)
+        if xdata is not None:
+            self.npts = (int(xdata.shape[0]), 1, 1)
+
+    def points(self):
+        if self.xdata is not None:
+            return np.ascontiguousarray(self.xdata)
+        return super().points()
+
+    def gridpoint(self, i, j, k):
+        """0-based gridpoint(), grid.f90:498-511"""
+        if self.xdata is not None:
+            return self.xdata[i].copy()
+        return self.origin + self.pts[0][i] * self.basv[0] + self.pts[1][j] * self.basv[1] + self.pts[2][k] * self.basv[2]
+
+    def center(self):
+        """grid_center, grid.f90:529-541"""
+        return (self.gridpoint(self.npts[0] - 1, 0, 0) + self.gridpoint(0, self.npts[1] - 1, 0)) * 0.5
+
+    def is_3d(self):
+        return all(n > 1 for n in self.npts)
+
+
+def _rotation_matrix(angle_deg):
+    """R = R_x . R_y . R_z with the sign conventions of grid.f90:716-757"""
+    rx, ry, rz = (a / 180.0 * PII for a in angle_deg)
+    Rz = np.array([[math.cos(rz), math.sin(rz), 0.0], [-math.sin(rz), math.cos(rz), 0.0], [0.0, 0.0, 1.0]])
+    Ry = np.array([[math.cos(ry), 0.0, -math.sin(ry)], [0.0, 1.0, 0.0], [math.sin(ry), 0.0, math.cos(ry)]])
+    Rx = np.array([[1.0, 0.0, 0.0], [0.0, math.cos(rx), math.sin(rx)], [0.0, -math.sin(rx), math.cos(rx)]])
+    return Rx @ (Ry @ Rz)
+
+
+def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order=7):
+    pts, wgt = [], []
+    if gtype == "even":                                  # setup_even_grid, grid.f90:351-373
+        for d in range(3):
+            if d == 2 and (abs(lengths[2]) < 2.2250738585072014e-308 or abs(step[2]) < 2.2250738585072014e-308):
+                n = 1
+            else:
+                n = int(math.floor(lengths[d] / step[d] + 0.5)) + 1      # nint
+            pts.append(np.arange(n, dtype=np.float64) * step[d])
+            wgt.append(np.ones(n))
+        return pts, wgt
+    if gtype not in ("gauss", "lobatto"):
+        raise ValueError("Unknown grid type: " + gtype)
+    npts = [0, 0, 0]                                     # setup_gauss_grid, grid.f90:291-349
+    for d in range(3):
+        if grid_points is not None:
+            npts[d] = int(grid_points[d])
+        elif abs(spacing[d]) < 1e-10 or spacing[d] < 0.0:
+            npts[d] = 0
+        else:
+            npts[d] = int(math.floor(lengths[d] / spacing[d] + 0.5))
+        if not npts[d] > 1:
+            npts[d] = 0
+        rem = npts[d] % gauss_order
+        if rem != 0:
+            npts[d] = npts[d] - rem + gauss_order
+    for d in range(3):
+        n = npts[d] if npts[d] > 0 else 1
+        p, w = np.zeros(n), np.zeros(n)
+        gausspoints(0.0, float(lengths[d]), gauss_order if npts[d] > 0 else 1, p, w, quadrature=gtype)
+        pts.append(p); wgt.append(w)
+    return pts, wgt
+
+
+def _finish(origin, basv, lengths, mode, gtype, ortho, radius, step, grid_points, spacing, gauss_order, rotation,
+            rotation_origin, out_len, down_len, center_bond=None):
+    basv = np.array(basv, dtype=np.float64)
+    for v in range(3):                                   # normalise, grid.f90:278-288
+        n = math.sqrt(float(np.dot(basv[v], basv[v])))
+        if n > 0.0:
+            basv[v] = basv[v] / n
+    if abs(float(np.dot(basv[0], basv[1]))) > 1e-10:     # ortho_coordsys, grid.f90:400-428
+        t = np.cross(basv[0], basv[2])
+        basv[1] = t / math.sqrt(float(np.dot(t, t)))
+        for v in range(3):
+            n = math.sqrt(float(np.dot(basv[v], basv[v])))
+            if n > 0.0:
+                basv[v] = basv[v] / n
+    origin = np.array(origin, dtype=np.float64)
+    if rotation is not None:                             # grid.f90:92-114
+        ref = np.array(rotation_origin, dtype=np.float64) if rotation_origin is not None else \
+            origin + out_len * basv[1] + down_len * basv[0]
+        R = _rotation_matrix(rotation)
+        basv = np.array([R @ basv[v] for v in range(3)])
+        origin = R @ (origin - ref) + ref
+    pts, wgt = _axes(lengths, gtype, step, grid_points, spacing, gauss_order)
+    return GridSpec(origin, basv, pts, wgt, radius, mode, gtype, ortho, lengths, center_bond)
+
+
+def std_grid(origin, ivec, jvec, lengths, gtype="even", spacing=None, grid_points=None, gauss_order=7, rotation=None,
+             rotation_origin=None, mode="std"):
+    """setup_std_grid, grid.f90:140-163"""
+    lengths = np.asarray(lengths, dtype=np.float64)
+    step = np.asarray(spacing, dtype=np.float64) if spacing is not None else lengths / (np.asarray(grid_points) - 1)
+    b3 = np.cross(np.asarray(ivec, float), np.asarray(jvec, float))
+    return _finish(origin, [ivec, jvec, b3], lengths, mode, gtype, _unit(b3), -1.0, step, grid_points, spacing, gauss_order,
+                   rotation, rotation_origin, 0.0, 0.0)
+
+
+def bond_grid(c1, c2, fix, distance, height, width, gtype="even", spacing=None, grid_points=None, gauss_order=7,
+              radius=None, magnet=None, rotation=None, rotation_origin=None):
+    """setup_bond_grid, grid.f90:165-276 (height/width as in the input file; the first entries are negated, :212-213)"""
+    c1, c2, fix = (np.asarray(v, dtype=np.float64) for v in (c1, c2, fix))
+    hgt = np.array([-height[0], height[1]], dtype=np.float64)
+    wdt = np.array([-width[0], width[1]], dtype=np.float64)
+    lengths = np.array([hgt.sum(), wdt.sum(), 0.0])
+    if wdt.sum() < 0.0 or hgt.sum() < 0.0:
+        raise ValueError("Grid width/height < 0!")
+    v1, v2 = c1 - fix, c2 - fix
+    ortho = np.cross(v1, v2)
+    if not ortho.any():
+        raise ValueError("Basis vectors are linearly dependent, field direction undefined!")
+    ortho = _unit(ortho)
+    v3 = _unit(v2 - v1)
+    v1 = -ortho
+    v2 = _unit(np.cross(v3, v1))
+    oo = c1 + distance * v3
+    origin = oo - wdt[1] * v2 - hgt[1] * v1
+    if magnet is not None:                               # top-level `magnet` keyword overrides the plane normal, :253-256
+        ortho = _unit(magnet)
+    rad = float(np.float32(1.0e10)) if radius is None else float(radius)    # 1.e10 is a real(4) literal, grid.f90:199
+    # Reference quirk, replicated: setup_bond_grid never reads Grid.spacing / Grid.grid_points into grid%step, so an
+    # *even* bond grid always has the default step of 1 bohr (new_grid sets step=1.d0, grid.f90:66; the golden
+    # test/benzene/int-grid-bond-even has 11 x 8 points for grid_points=[40,40,0]).  Gauss grids do use grid_points.
+    step = np.ones(3)
+    return _finish(origin, [v1, v2, v3], lengths, "bond", gtype, ortho, rad, step, grid_points, spacing, gauss_order, rotation,
+                   rotation_origin, float(width[1]), float(height[1]), center_bond=oo)
+
+
+def file_grid(xyz):
+    """extgrid, grid.f90:543-576: an explicit point list; basis vectors are zero (so get_magnet never flips B)"""
+    xyz = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+    return GridSpec(np.zeros(3), np.zeros((3, 3)), [np.zeros(1)] * 3, [np.ones(1)] * 3, -1.0, "file", "file", np.zeros(3),
+                    np.zeros(3), xdata=xyz)
+
+
+def get_magnet(grid, magnet_axis="", magnet=(0.0, 0.0, 0.0)):
+    """get_magnet + check_field, magnet.f90:11-86"""
+    axis = (magnet_axis or "").strip()
+    ortho, d = False, 1.0
+    if axis:
+        if axis[0] == "-":
+            d, axis = -1.0, axis[1:]
+        a = axis[:1]
+        if a in "ijk" and a:
+            mag = grid.basv["ijk".index(a)] * d
+        elif a in "xyz" and a:
+            mag = np.eye(3)["xyz".index(a)] * d
+        elif a == "X":
+            ortho, mag = True, grid.ortho * d
+        else:
+            raise ValueError("Invalid axis specifier: " + axis)
+    else:
+        mag = np.asarray(magnet, dtype=np.float64).copy()
+    if not np.asarray(mag).any():
+        raise ValueError("Magnetic field is zero, not wasting more CPU.")
+    mag = np.array(mag, dtype=np.float64)
+    if not ortho and float(np.dot(grid.basv[2], mag)) > 0.0:   # left handed coordinate system, reversing magnetic field
+        mag = -mag
+    return mag
+
+
+def from_input(inp, atom_coords, workdir="."):
+    """new_grid, grid.f90:50-138, driven by a parsed gimic.inp (gimic_b200.inp.Input)"""
+    import os
+    G = lambda k: inp.get("Grid." + k)
+    S = lambda k: inp.is_set("Grid." + k)
+    mode = inp.grid_arg
+    if mode == "file":
+        path = os.path.join(workdir, G("file")) if S("file") else os.path.join(workdir, "GRIDDATA")
+        return file_grid(np.loadtxt(path).reshape(-1, 3))
+    gtype = G("type")
+    rot = G("rotation") if S("rotation") else None
+    rot0 = G("rotation_origin") if S("rotation_origin") else None
+    gp = G("grid_points") if S("grid_points") else None
+    sp = G("spacing") if S("spacing") else None
+    if mode in ("std", "base"):
+        return std_grid(G("origin"), G("ivec"), G("jvec"), G("lengths"), gtype, sp, gp, G("gauss_order"), rot, rot0, mode)
+    if mode == "bond":
+        if S("bond"):
+            b = G("bond")
+            c1, c2 = atom_coords[b[0] - 1], atom_coords[b[1] - 1]
+        else:
+            c1, c2 = G("coord1"), G("coord2")
+        fix = atom_coords[G("fixpoint") - 1] if S("fixpoint") else G("fixcoord")
+        return bond_grid(c1, c2, fix, G("distance"), G("height"), G("width"), gtype, sp, gp, G("gauss_order"),
+                         G("radius") if S("radius") else None, inp.get("magnet") if inp.is_set("magnet") else None, rot, rot0)
+    raise ValueError("Unknown grid type: " + mode)

@@ -1,0 +1,184 @@
+"""Output files in the reference's formats (src/fgimic/vtkplot.f90, jfield.f90:356-364,540, basis.f90 write_xyz,
+grid.f90:586-672).  Numbers use Fortran edit descriptors (e14.6, 3e20.10, 6f11.7, f16.10); headers that the
+reference writes list-directed are emitted with gfortran-like spacing (the reference's own tests compare numeric
+tokens only, test/benzene/3d/test:15-23)."""
+import numpy as np
+
+AU2A = float(np.float32(0.52917726))     # globals.f90:51 is a single-precision literal
+
+
+def fortran_e(x, w, d):
+    """Fortran Ew.d: 0.dddddE+ee"""
+    x = float(x)
+    if x == 0.0:
+        s = "0." + "0" * d + "E+00"
+    else:
+        m, e = f"{abs(x):.{d - 1}E}".split("E")
+        digits = m.replace(".", "")
+        e = int(e) + 1
+        s = ("-" if x < 0 else "") + "0." + digits + f"E{e:+03d}"
+    return s.rjust(w)
+
+
+def _ld_real(x):
+    """gfortran list-directed real(8): 17 significant digits, F form for 1e-1 <= |x| < 1e16"""
+    x = float(x)
+    ax = abs(x)
+    if ax != 0.0 and not (0.1 <= ax < 1e16):
+        m, e = f"{ax:.16E}".split("E")
+        s = ("-" if x < 0 else "") + m + f"E{int(e):+04d}"
+        return "  " + s + " "
+    nint = len(str(int(ax))) if ax >= 1.0 else 0
+    dec = 17 - max(nint, 0) if ax >= 1.0 else 17
+    s = f"{ax:.{dec}f}"
+    if ax < 1.0:
+        s = s  # 0.ddddddddddddddddd
+    s = ("-" if x < 0 else "") + s
+    return s.rjust(21) + "     "
+
+
+def _ld_int(i):
+    return f"{int(i):12d}"
+
+
+def _vti_header(f, npts, qmin, step, name, ncomp):
+    ext = "".join(_ld_int(v) for v in (0, npts[0] - 1, 0, npts[1] - 1, 0, npts[2] - 1))
+    f.write('<?xml version="1.0"?>\n')
+    f.write(' <VTKFile type="ImageData" version="0.1" byte_order="LittleEndian">\n')
+    f.write('   <ImageData WholeExtent="' + ext + ' " Origin="' + "".join(_ld_real(v) for v in qmin) + '" Spacing="'
+            + "".join(_ld_real(v) for v in step) + '">\n')
+    f.write('   <Piece Extent="' + ext + ' ">\n')
+    f.write('   <PointData Scalars="scalars">\n')
+    f.write(f'   <DataArray Name="{name}" type="Float64" NumberOfComponents="{ncomp}" Format="ascii">\n')
+
+
+def _vti_geometry(grid):
+    npts = grid.npts
+    qmin = grid.gridpoint(0, 0, 0)
+    qmax = grid.gridpoint(npts[0] - 1, npts[1] - 1, npts[2] - 1)
+    step = qmax - qmin                                          # vtkplot.f90:33-38
+    for i in range(3):
+        if step[i] > 1e-8:
+            step[i] = step[i] / (npts[i] - 1)
+    return qmin, step
+
+
+def write_vti_scalar(path, grid, values):
+    """write_vtk_imagedata, vtkplot.f90:14-86: values[i + p1*(j + p2*k)], e14.6, line break when mod(l,4)==0"""
+    qmin, step = _vti_geometry(grid)
+    v = np.asarray(values, dtype=np.float64).ravel()
+    with open(path, "w") as f:
+        _vti_header(f, grid.npts, qmin, step, "scalars", 1)
+        out = []
+        for l, x in enumerate(v):
+            out.append(fortran_e(x, 14, 6))
+            if l % 4 == 0:
+                out.append("\n")
+        f.write("".join(out))
+        f.write("\n    </DataArray>\n    </PointData>\n    </Piece>\n    </ImageData>\n </VTKFile>\n")
+
+
+def write_vti_vector(path, grid, vec):
+    """write_vtk_vector_imagedata, vtkplot.f90:88-234: 3e14.6 per point + CellData of cell-averaged |J|"""
+    qmin, step = _vti_geometry(grid)
+    p1, p2, p3 = grid.npts
+    v = np.asarray(vec, dtype=np.float64).reshape(p3, p2, p1, 3)
+    with open(path, "w") as f:
+        _vti_header(f, grid.npts, qmin, step, "vectors", 3)
+        f.write("".join(fortran_e(a, 14, 6) + fortran_e(b, 14, 6) + fortran_e(c, 14, 6) + "\n" for a, b, c in v.reshape(-1, 3)))
+        f.write("\n    </DataArray>\n    </PointData>\n    <CellData Scalars=\"foo\">\n")
+        sl = [slice(0, -1), slice(1, None)]
+        if p1 > 1 and p2 > 1 and p3 > 1:
+            avg = sum(v[a, b, c] for a in sl for b in sl for c in sl) / 8.0
+        elif p1 > 1 and p2 > 1 and p3 == 1:
+            avg = sum(v[0:1, b, c] for b in sl for c in sl) / 4.0
+        elif p1 > 1 and p2 == 1 and p3 > 1:
+            avg = sum(v[a, 0:1, c] for a in sl for c in sl) / 4.0
+        elif p1 == 1 and p2 > 1 and p3 > 1:
+            avg = sum(v[a, b, 0:1] for a in sl for b in sl) / 4.0
+        else:
+            avg = None
+        if avg is not None:
+            nrm = np.sqrt((avg ** 2).sum(-1)).ravel()
+            f.write("".join(fortran_e(x, 14, 6) + "\n" for x in nrm))
+        f.write("    </CellData>\n    </Piece>\n    </ImageData>\n </VTKFile>\n")
+
+
+def read_ele(path):
+    """TetGen .ele: first line 'ncells 4 0', then 'idx n1 n2 n3 n4' (jfield.f90:421-431)"""
+    with open(path) as f:
+        ncells = int(f.readline().split()[0])
+        cells = np.loadtxt(f, dtype=np.int64, max_rows=ncells).reshape(-1, 5)[:, 1:5]
+    return cells
+
+
+def write_vtu_vector(path, points, vec, cells):
+    """write_vtk_vector_unstructuredgrid, vtkplot.f90:241-312"""
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    v = np.asarray(vec, dtype=np.float64).reshape(-1, 3)
+    nc = cells.shape[0]
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n  <UnstructuredGrid>\n')
+        f.write(f'    <Piece NumberOfPoints="{pts.shape[0]:10d}" NumberOfCells="{nc:10d}">\n      <Points>\n')
+        f.write('        <DataArray type="Float32" NumberOfComponents="3" Format="ascii">\n')
+        f.write("".join("        " + "".join(fortran_e(x, 20, 10) for x in p) + "\n" for p in pts))
+        f.write('        </DataArray>\n      </Points>\n      <PointData Scalars="scalars">\n')
+        f.write('        <DataArray Name="vectors" type="Float64" NumberOfComponents="3" Format="ascii">\n')
+        f.write("".join("        " + "".join(fortran_e(x, 20, 10) for x in p) + "\n" for p in v))
+        f.write('        </DataArray>\n      </PointData>\n      <Cells>\n        <DataArray type="Int32" Name="connectivity" Format="ascii">\n')
+        f.write("".join("        " + "".join(f"{int(i) - 1:10d}" for i in c) + "\n" for c in cells))
+        f.write('        </DataArray>\n        <DataArray type="Int32" Name="offsets" Format="ascii">\n        ')
+        f.write("".join(f"{4 * (c + 1):10d}" for c in range(nc)) + "\n")
+        f.write('        </DataArray>\n        <DataArray type="Int32" Name="types" Format="ascii">\n        ')
+        f.write("".join(f"{10:5d}" for _ in range(nc)) + "\n")
+        f.write('        </DataArray>\n      </Cells>\n      <CellData Scalars="foo">\n        ')
+        f.write("".join(" 0.0" for _ in range(nc)) + "\n")
+        f.write("      </CellData>\n    </Piece>\n  </UnstructuredGrid>\n</VTKFile>\n")
+
+
+def write_jmod_txt(path, grid, vec, regular=True):
+    """jmod<tag>.txt on Gauss grids (jfield.f90:294-301,356-376,531-541): '(6f11.7)' of coord*AU2A and |J|;
+    a blank line after each i-row on regular grids"""
+    v = np.asarray(vec, dtype=np.float64).reshape(-1, 3)
+    r = grid.points() * AU2A
+    jm = np.sqrt((v ** 2).sum(1))
+    p1 = grid.npts[0]
+    with open(path, "w") as f:
+        for n in range(v.shape[0]):
+            f.write("".join(f"{x:11.7f}" for x in (*r[n], jm[n])) + "\n")
+            if regular and (n + 1) % p1 == 0:
+                f.write("\n")
+
+
+def write_mol_xyz(path, symbols, coords):
+    """write_xyz (basis.f90): natoms, blank, 'sym x y z' in Angstrom"""
+    with open(path, "w") as f:
+        f.write(f"{len(symbols):12d}\n\n")
+        for s, c in zip(symbols, coords):
+            f.write(f"{s}" + "".join(f"{x * AU2A:16.10f}" for x in c) + "\n")
+
+
+def write_grid_xyz(path, grid, symbols, coords):
+    """plot_grid_xyz, grid.f90:586-672: atoms + grid corners ('X') + field-direction marker ('Be')"""
+    p1, p2, p3 = grid.npts
+    if grid.mode == "file":
+        corners = []
+    elif p3 > 1:
+        idx = [(0, 0, 0), (p1 - 1, 0, 0), (0, p2 - 1, 0), (0, 0, p3 - 1), (p1 - 1, p2 - 1, 0), (p1 - 1, 0, p3 - 1), (0, p2 - 1, p3 - 1),
+               (p1 - 1, p2 - 1, p3 - 1)]
+        corners = [grid.gridpoint(*i) for i in idx]
+    else:
+        corners = [grid.gridpoint(*i) for i in [(0, 0, 0), (p1 - 1, 0, 0), (0, p2 - 1, 0), (p1 - 1, p2 - 1, 0)]]
+    marker = None
+    if grid.mode in ("std", "base"):
+        marker = grid.origin + grid.basv[2] * 2.0
+    elif grid.mode == "bond":
+        marker = grid.origin + grid.ortho * 2.0
+    with open(path, "w") as f:
+        f.write(f"{len(symbols) + len(corners) + 1:12d}\n\n")
+        for s, c in zip(symbols, coords):
+            f.write(f"{s}" + "".join(f"{x * AU2A:16.10f}" for x in c) + "\n")
+        for c in corners:
+            f.write("X " + "".join(f"{x * AU2A:16.10f}" for x in c) + "\n")
+        if marker is not None:
+            f.write("Be " + "".join(f"{x * AU2A:16.10f}" for x in marker) + "\n")

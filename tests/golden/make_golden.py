@@ -124,6 +124,27 @@ def main():
         assert jv.shape == (n, 3) and jm.shape == (n,), (jv.shape, jm.shape)
         d[f"jvec{tag}"] = jv[idx]; d[f"jmod{tag}"] = jm[idx]
     np.savez_compressed(os.path.join(OUT, "open_shell_3d.npz"), **d)
+    # grid geometry / point counts / field direction printed by the reference for the benzene keyword tests
+    # (their XDENS is a stripped blob, but these lines only depend on MOL + gimic.inp)
+    grids = {}
+    for name in ("int-grid-bond-even", "keyword-rotation", "keyword-rotation_origin", "keyword-radius", "keyword-spacing",
+                 "keyword-magnet", "integration-lobatto", "integration-gauss", "int-cdens", "3d", "2d", "3d-keyword-magnet",
+                 "2d-keyword-magnet", "vectors"):
+        path = os.path.join(t, "benzene", name, "reference", "stdout")
+        if not os.path.exists(path):
+            continue
+        txt = open(path, encoding="utf-8", errors="replace").read()
+        d = parse_integral_stdout(path)
+        m = re.search(r"Number of grid points <v1,v2>:\s*(\d+)\s+(\d+)\s+(\d+)", txt)
+        g = dict(geometry=d["geometry"], blocks=d["blocks"])
+        if m:
+            g["npts"] = [int(m.group(i)) for i in (1, 2, 3)]
+        m = re.findall(r"Magnetic field <x,y,z> =\s*([-\d.]+)\s+([-\d.]+)\s+([-\d.]+)", txt)
+        if m:
+            g["magnet"] = [float(v) for v in m[0]]
+        grids[name] = g
+        shutil.copyfile(os.path.join(t, "benzene", name, "gimic.inp"), os.path.join(OUT, "inputs", f"benzene_{name}.inp"))
+    json.dump(grids, open(os.path.join(OUT, "benzene_grids.json"), "w"), indent=1)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f:32s} {os.path.getsize(os.path.join(OUT, f)):9d} B")

@@ -1,0 +1,146 @@
+"""CPU tests of the native driver pieces: gimic.inp reader, grid geometry and magnet
+against the oracle AND against what the reference printed for its benzene keyword tests, output formatting."""
+import io
+import json
+import os
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_lib as O
+
+GOLD = fixtures.GOLD
+INPUTS = os.path.join(GOLD, "inputs")
+
+
+def _inp(name):
+    from gimic_b200 import inp
+    return inp.parse_file(os.path.join(INPUTS, name + ".inp"))
+
+
+def test_parser_reads_reference_inputs():
+    names = sorted(f[:-4] for f in os.listdir(INPUTS))
+    assert len(names) >= 14
+    for n in names:
+        I = _inp(n)
+        assert I.get("calc") in ("cdens", "integral")
+        assert I.get("Advanced.spherical") is False and I.get("Advanced.screening") is True
+        assert abs(I.get("Advanced.screening_thrs") - 1e-8) < 1e-20          # written as 1.d-8
+    I = _inp("c4h4_integration")
+    assert I.grid_arg == "bond" and I.get("Grid.bond") == [2, 1] and I.get("Grid.fixpoint") == 4
+    assert I.get("Grid.width") == [-1.25614, 6.0] and I.is_set("Grid.rotation") and not I.is_set("Grid.radius")
+    assert I.get("magnet_axis") == "z" and not I.is_set("magnet")
+    I = _inp("c4h4_read-grid")
+    assert I.grid_arg == "file" and I.get("Grid.file") == "gridfile.grd" and I.get("magnet") == [0.0, 0.0, -1.0]
+    I = _inp("open-shell_3d")
+    assert I.get("openshell") is True and I.get("Essential.jmod") is True and I.get("Grid.spacing") == [0.5, 0.5, 0.5]
+
+
+def test_parser_rejects_bad_input():
+    from gimic_b200 import inp
+    base = 'calc=cdens\nmagnet_axis=z\nGrid(std){ origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[0.5,0.5,0.5] }\n'
+    assert inp.parse_text(base).get("Grid.lengths") == [1.0, 1.0, 1.0]
+    for bad in (base.replace("calc=cdens", "calc=foo"), base.replace("magnet_axis=z", ""), base + "magnet=[0,0,1]\n",
+                base.replace("spacing=[0.5,0.5,0.5]", ""), base.replace("Grid(std)", "Grid(cube)"),
+                base.replace("spacing=", "grid_points=[3,3,3]\n spacing=")):
+        with pytest.raises(inp.InputError):
+            inp.parse_text(bad)
+    assert inp.parse_text(base.replace("calc=cdens", "calc=cdens # comment\ntitle=\"a # b\"")).get("title") == "a # b"
+
+
+def _grid_from(name, coords):
+    from gimic_b200 import grids
+    I = _inp(name)
+    g = grids.from_input(I, coords, INPUTS)
+    return I, g, grids.get_magnet(g, I.get("magnet_axis"), I.get("magnet"))
+
+
+def _oracle_grid(I, coords):
+    G = lambda k: I.get("Grid." + k)
+    S = lambda k: I.is_set("Grid." + k)
+    kw = dict(type=G("type"), gauss_order=G("gauss_order"), grid_points=G("grid_points") if S("grid_points") else None,
+              spacing=G("spacing") if S("spacing") else None, rotation=G("rotation") if S("rotation") else None,
+              rotation_origin=G("rotation_origin") if S("rotation_origin") else None)
+    if I.grid_arg == "bond":
+        b = G("bond")
+        return O.grid_bond(coords[b[0] - 1], coords[b[1] - 1], coords[G("fixpoint") - 1], G("distance"), height=G("height"),
+                           width=G("width"), radius=G("radius") if S("radius") else None,
+                           magnet=I.get("magnet") if I.is_set("magnet") else None, **kw)
+    return O.grid_std(G("origin"), G("ivec"), G("jvec"), G("lengths"), **kw)
+
+
+@pytest.mark.parametrize("name,mol", [("c4h4_integration", "c4h4_MOL"), ("open-shell_integration", "open_shell_MOL"),
+                                      ("open-shell_3d", "open_shell_MOL"), ("benzene_int-grid-bond-even", "benzene_MOL"),
+                                      ("benzene_keyword-rotation", "benzene_MOL"), ("benzene_keyword-rotation_origin", "benzene_MOL"),
+                                      ("benzene_keyword-radius", "benzene_MOL"), ("benzene_keyword-spacing", "benzene_MOL"),
+                                      ("benzene_keyword-magnet", "benzene_MOL"), ("benzene_integration-lobatto", "benzene_MOL"),
+                                      ("benzene_3d", "benzene_MOL"), ("benzene_2d", "benzene_MOL"), ("benzene_int-cdens", "benzene_MOL")])
+def test_grid_and_magnet_match_oracle(name, mol):
+    from gimic_b200.driver import read_mol_geometry
+    _, coords = read_mol_geometry(os.path.join(GOLD, mol))
+    I, g, mag = _grid_from(name, coords)
+    og = _oracle_grid(I, coords)
+    assert g.npts == og.npts
+    assert np.allclose(g.origin, og.origin, rtol=0, atol=1e-13) and np.allclose(g.basv, og.basv, rtol=0, atol=1e-14)
+    for d in range(3):
+        p, w = og.axis(d)
+        assert np.allclose(g.pts[d], p, rtol=0, atol=1e-13) and np.allclose(g.wgt[d], w, rtol=0, atol=1e-14)
+    assert np.allclose(g.points(), og.points(), rtol=0, atol=1e-12)
+    assert np.allclose(mag, og.magnet(I.get("magnet_axis"), I.get("magnet")), rtol=0, atol=1e-14)
+    if I.grid_arg == "bond":
+        assert g.radius == og.radius and np.allclose(g.center(), og.center(), atol=1e-13)
+
+
+def test_grid_matches_what_the_reference_printed():
+    """'Integration grid data' block, point counts and field direction of the reference's benzene stdout goldens"""
+    from gimic_b200.driver import read_mol_geometry
+    _, coords = read_mol_geometry(os.path.join(GOLD, "benzene_MOL"))
+    gold = json.load(open(os.path.join(GOLD, "benzene_grids.json")))
+    checked = 0
+    for name, ref in gold.items():
+        if not os.path.exists(os.path.join(INPUTS, f"benzene_{name}.inp")):
+            continue
+        I, g, mag = _grid_from(f"benzene_{name}", coords)
+        if "npts" in ref:
+            assert list(g.npts) == ref["npts"], name
+        if ref.get("magnet"):
+            assert np.allclose(mag, ref["magnet"], atol=1e-5), name
+        geo = ref["geometry"]
+        if geo and not I.is_set("Grid.rotation"):      # the block is printed before the rotation is applied
+            assert np.allclose(g.center_bond, geo["center"], atol=1e-6), name
+            assert np.allclose(g.origin, geo["origin"], atol=1e-6), name
+            for v in range(3):
+                assert np.allclose(g.basv[v], geo[f"basv{v + 1}"], atol=1e-6), name
+            assert np.allclose(g.lengths, geo["lenghts"], atol=1e-6), name
+        checked += 1
+    assert checked >= 8
+
+
+def test_fortran_number_formats():
+    from gimic_b200.writers import fortran_e, _ld_real
+    assert fortran_e(0.648806e-13, 14, 6) == "  0.648806E-13" and fortran_e(-0.671910e-13, 14, 6) == " -0.671910E-13"
+    assert fortran_e(0.0, 14, 6) == "  0.000000E+00" and fortran_e(-6.480976, 20, 10) == "   -0.6480976000E+01"
+    assert fortran_e(9.9999996e-5, 14, 6) == "  0.100000E-03"                       # rounding carries into the exponent
+    assert _ld_real(-8.0) == "  -8.0000000000000000     " and _ld_real(0.5) == "  0.50000000000000000     "
+
+
+def test_vti_writers_roundtrip(tmp_path):
+    """files written in the reference's layout parse back (with the reference-golden parser) to the same numbers"""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import read_vti
+    from gimic_b200 import grids, writers
+    g = grids.std_grid([-1, -1, -1], [1, 0, 0], [0, 1, 0], [2, 2, 2], "even", spacing=[0.5, 1.0, 2.0])
+    assert g.npts == (5, 3, 2)
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=(g.n, 3)) * 1e-3
+    s = rng.normal(size=g.n)
+    writers.write_vti_vector(tmp_path / "jvec.vti", g, v)
+    writers.write_vti_scalar(tmp_path / "jmod.vti", g, s)
+    assert np.allclose(read_vti(str(tmp_path / "jvec.vti")), v, rtol=1e-5, atol=0)
+    assert np.allclose(read_vti(str(tmp_path / "jmod.vti")), s, rtol=1e-5, atol=0)
+    txt = open(tmp_path / "jvec.vti").read()
+    assert 'WholeExtent="           0           4           0           2           0           1 "' in txt
+    assert txt.count("\n") == 6 + g.n + 4 + (4 * 2 * 1) + 4          # header, vectors, CellData of (p1-1)(p2-1)(p3-1) cells, footer
+    head = open(os.path.join(GOLD, "..", "golden", "open_shell_MOL")).readline()
+    assert head.startswith("INTGRL")

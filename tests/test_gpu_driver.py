@@ -1,0 +1,115 @@
+"""End-to-end drop-in check on the GPU: `python -m gimic_b200 gimic.inp` semantics (driver -> files / stdout report)
+compared the way the reference's own runtest scripts compare them (numeric tokens of the whole output file, or the
+anchored stdout window)."""
+import io
+import os
+import re
+import shutil
+import sys
+import numpy as np
+import pytest
+
+import fixtures
+
+pytestmark = pytest.mark.gpu
+GOLD = fixtures.GOLD
+INPUTS = os.path.join(GOLD, "inputs")
+sys.path.insert(0, GOLD)
+
+
+def _workdir(tmp_path, cases, case, inp_name):
+    d = tmp_path / inp_name
+    d.mkdir()
+    shutil.copy(cases[case]["mol"], d / "MOL")
+    shutil.copy(cases[case]["xdens"], d / "XDENS")
+    shutil.copy(os.path.join(INPUTS, inp_name + ".inp"), d / "gimic.inp")
+    return d
+
+
+def test_c4h4_read_grid_vtu(tmp_path, cases):
+    """test/c4h4/read-grid/test: whole jvec.vtu, rel_tolerance 1e-8 (the golden has 10 printed digits)"""
+    from make_golden import read_vtu_vectors
+    from gimic_b200.driver import Driver
+    d = _workdir(tmp_path, cases, "c4h4", "c4h4_read-grid")
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+    np.savetxt(d / "gridfile.grd", gold["grid"], fmt="%.6f")
+    with open(d / "grid.1.ele", "w") as f:          # a 3-tetrahedron stand-in for the TetGen mesh (743 KB in the reference)
+        f.write("3  4  0\n    1    1475  1730  1474  1717\n    2     100     8   112   245\n    3     5     6     7     8\n")
+    out = io.StringIO()
+    Driver(str(d / "gimic.inp"), out=out).run()
+    pts, vec = read_vtu_vectors(str(d / "jvec.vtu"))
+    assert pts.shape == vec.shape == (4110, 3)
+    assert np.allclose(pts, gold["grid"], atol=1e-9)
+    ref = gold["jvec"]
+    big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    assert (np.abs(vec - ref)[big] / np.abs(ref)[big]).max() < 4e-9          # two roundings at 10 digits
+    assert np.abs(vec - ref).max() < 1e-9 * np.abs(ref).max() + 1e-14
+    assert os.path.exists(d / "mol.xyz") and os.path.exists(d / "grid.xyz")
+    assert "Closed-shell calculation" in out.getvalue()
+
+
+def _window(text, anchor, n=10):
+    lines = text.split("\n")
+    i = next(k for k, l in enumerate(lines) if l.startswith(anchor))
+    return [float(t) for l in lines[i:i + n] for t in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", l)]
+
+
+@pytest.mark.parametrize("case,inp_name,anchor,ref_path", [
+    ("c4h4", "c4h4_integration", " *** Integrating current", "c4h4/integration"),
+    ("open_shell", "open-shell_integration", " *** Integrating current", "open-shell/integration")])
+def test_integration_stdout_window(tmp_path, cases, case, inp_name, anchor, ref_path):
+    """test/*/integration/test: 10 lines after ' *** Integrating current' (rel 1e-8 on 6-decimal numbers)"""
+    from gimic_b200.driver import Driver
+    d = _workdir(tmp_path, cases, case, inp_name)
+    out = io.StringIO()
+    Driver(str(d / "gimic.inp"), out=out).run()
+    got = out.getvalue()
+    gold = fixtures.golden_json(("c4h4" if case == "c4h4" else "open_shell") + "_integration.json")["blocks"]
+    cur = [b for b in gold if b["section"] == "current"]
+    nums = _window(got, anchor, 12 if case == "c4h4" else 80)
+    # every current block: au, pos, pos_si, neg, neg_si, si, conversion factor
+    flat = []
+    for b in cur:
+        flat += [b["au"], b["pos"], b["pos_si"], b["neg"], b["neg_si"], b["si"], 28.179409]
+    mine = [x for x in nums if abs(x) not in (0.0, 1.0)][: len(flat)]     # drop the 'Magnetic field' echo
+    assert len(mine) == len(flat), got
+    assert np.allclose(mine, flat, rtol=0, atol=2.1e-5), (mine, flat)
+    if os.path.isdir("/root/reference/test"):
+        ref_txt = open(f"/root/reference/test/{ref_path}/reference/stdout", encoding="utf-8", errors="replace").read()
+        refnums = _window(ref_txt, anchor if case == "c4h4" else " *** Integrating current", 12)
+        assert np.allclose(_window(got, anchor, 12)[: len(refnums)], refnums, rtol=0, atol=2.1e-5)
+
+
+def test_open_shell_3d_files(tmp_path, cases):
+    """test/open-shell/3d/test: eight .vti files, rel_tolerance 1e-7 on 6-digit numbers"""
+    from make_golden import read_vti
+    from gimic_b200.driver import Driver
+    d = _workdir(tmp_path, cases, "open_shell", "open-shell_3d")
+    Driver(str(d / "gimic.inp"), out=io.StringIO()).run()
+    gold = fixtures.golden_npz("open_shell_3d.npz")
+    idx = gold["index"]
+    for tag in ("", "alpha", "beta", "spindens"):
+        jv = read_vti(str(d / f"jvec{tag}.vti"))
+        jm = read_vti(str(d / f"jmod{tag}.vti"))
+        assert jv.shape == (35937, 3) and jm.shape == (35937,)
+        gj, gm = gold["jvec" + tag], gold["jmod" + tag]
+        assert (np.abs(jv[idx] - gj) <= 2e-6 * np.abs(gj) + 1e-9 * np.abs(gj).max()).all(), tag
+        assert (np.abs(np.abs(jm[idx]) - np.abs(gm)) <= 2e-6 * np.abs(gm) + 1e-9 * np.abs(gm).max()).all(), tag
+    assert not os.path.exists(d / "acid.vti")
+
+
+def test_edens_and_divj_modes(tmp_path, cases):
+    from gimic_b200.driver import Driver
+    from make_golden import read_vti
+    d = _workdir(tmp_path, cases, "c4h4", "c4h4_integration")
+    txt = open(d / "gimic.inp").read().replace("calc=integral", "calc=edens")
+    txt = re.sub(r"Grid\(bond\) \{.*?\n\}", "Grid(base) {\n type=even\n origin=[-4.0,-3.0,-1.0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n"
+                 " lengths=[3.0,3.0,1.0]\n spacing=[0.5,0.5,0.5]\n}", txt, flags=re.S)
+    open(d / "gimic.inp", "w").write(txt)
+    Driver(str(d / "gimic.inp"), out=io.StringIO()).run()
+    rho = read_vti(str(d / "edens.vti"))
+    assert rho.shape == (7 * 7 * 3,) and (rho > 0).all()          # an electron density
+    open(d / "gimic.inp", "w").write(txt.replace("calc=edens", "calc=divj"))
+    Driver(str(d / "gimic.inp"), out=io.StringIO()).run()
+    dj = read_vti(str(d / "divj.vti"))
+    assert dj.shape == rho.shape and np.isfinite(dj).all()
