@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -318,9 +319,20 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     fidx_max = std::max(fidx_max, foff);
     batch_start.push_back(ntiles);
     // inside a batch the contraction kernel pulls tiles from an atomic counter: longest first (cost ~ nact^2)
-    for (size_t b = 0; b + 1 < batch_start.size(); ++b)
-        std::stable_sort(c->h_tiles + batch_start[b], c->h_tiles + batch_start[b + 1],
-                         [](const TileDesc &x, const TileDesc &y) { return x.nact > y.nact; });
+    static const int sched = [] { const char *e = std::getenv("GIMIC_B200_SCHED"); return e ? std::atoi(e) : 0; }();
+    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
+        TileDesc *t0 = c->h_tiles + batch_start[b], *t1 = c->h_tiles + batch_start[b + 1];
+        if (sched == 0) {          // longest first
+            std::stable_sort(t0, t1, [](const TileDesc &x, const TileDesc &y) { return x.nact > y.nact; });
+        } else if (sched == 2) {   // Hilbert order, except that the heaviest 1/8 of the tiles go first (tail protection)
+            std::vector<int> v; for (TileDesc *t = t0; t < t1; ++t) v.push_back(t->nact);
+            if (!v.empty()) {
+                std::nth_element(v.begin(), v.begin() + v.size() / 8, v.end(), std::greater<int>());
+                const int cut = v[v.size() / 8];
+                std::stable_partition(t0, t1, [cut](const TileDesc &x) { return x.nact > cut; });
+            }
+        }                          // sched == 1: plain Hilbert order
+    }
     if (c->panel.ensure(std::max<size_t>(pool_doubles, 2) * 8) || c->fidx.ensure(std::max<size_t>(fidx_max, 1) * 4))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
     CUDA_TRY(cudaMemcpyAsync(c->tiles.p, c->h_tiles, (size_t)ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
