@@ -118,7 +118,8 @@ def run_cpu(sh, dens, r, nthreads, repeats=1):
     if o is None:
         o = O.Oracle.from_arrays(dens_a=synthetic.dens_to_colmajor(dens), **sh)
         run_cpu.cache["o"] = o
-    cores = nthreads or O.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core it can
+    cores = nthreads or max(O.max_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     best = 1e300
     for _ in range(repeats):
         t0 = time.perf_counter()
