@@ -636,6 +636,31 @@ int gimic_b200_integrate(gimic_b200_handle c, const gimic_b200_grid *g, const do
     return 0;
 }
 
+int gimic_b200_calc_basis(gimic_b200_handle c, long n, const double *r, double *bf, double *dr, int flags) {
+    if (!c || (n > 0 && !r) || (!bf && !dr)) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (n <= 0) return 0;
+    if (n > 2147483647L) return fail(GIMIC_B200_EINVAL, "too many points");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    const size_t nb = (size_t)c->hb.nbf;
+    const double *d_r = nullptr;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    double *d_bf = bf, *d_dr = dr;
+    if (!dev) {
+        if (c->f_tmp.ensure((size_t)n * nb * 4 * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (basis vectors)");
+        d_bf = bf ? c->f_tmp.as<double>() : nullptr;
+        d_dr = dr ? c->f_tmp.as<double>() + (size_t)n * nb : nullptr;
+    }
+    gb::launch_basis_dense(c->db, c->d_f2user, n, d_r, d_bf, d_dr, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) {
+        if (bf) CUDA_TRY(cudaMemcpyAsync(bf, d_bf, (size_t)n * nb * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (dr) CUDA_TRY(cudaMemcpyAsync(dr, d_dr, (size_t)n * nb * 24, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts) {
     if (!pts || !wgts || npts <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
     int rc = gb::gauss_blocks(a, b, npts, order, quadrature, pts, wgts);

@@ -272,6 +272,46 @@ __global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__res
     }
 }
 
+// Dense evaluation for callers that want the basis vectors themselves (bfeval / dfdr of the reference,
+// bfeval.f90:81-122,295-338): bf[i][f], dr[i][m][f] in the reference AO order, exact zeros where screened.
+// One thread per (point, shell); not on the tensor hot path.
+__global__ void k_basis_dense(DevBasis B, const int *__restrict__ f2user, long n, const double *__restrict__ r,
+                              double *__restrict__ bf, double *__restrict__ dr) {
+    const long i = blockIdx.x;
+    const signed char(*lmn_tab)[21][3] = c_lmn[B.turbomole ? 1 : 0];
+    for (int s = threadIdx.x; s < B.nshell; s += blockDim.x) {
+        int a = 0;   // atom of shell s (binary search in atom_shell_off)
+        { int lo = 0, hi = B.natoms; while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (B.atom_shell_off[mid] <= s) lo = mid; else hi = mid; } a = lo; }
+        const double rx = r[3 * i] - B.atom_xyz[3 * a], ry = r[3 * i + 1] - B.atom_xyz[3 * a + 1], rz = r[3 * i + 2] - B.atom_xyz[3 * a + 2];
+        const double r2 = rx * rx + ry * ry + rz * rz;
+        const int l = B.sh_l[s], ncomp = (l + 1) * (l + 2) / 2;
+        double q = 0.0, qp = 0.0;
+        const bool on = sqrt(r2) <= B.sh_thr[s];
+        if (on) for (int p = 0; p < B.sh_nprim[s]; ++p) { const double al = B.alpha[B.sh_prim_off[s] + p]; const double e = B.ncc[B.sh_prim_off[s] + p] * exp(-al * r2); q += e; qp += al * e; }
+        double px[6], py[6], pz[6];
+        px[0] = py[0] = pz[0] = 1.0;
+        for (int k = 1; k < 6; ++k) { px[k] = px[k - 1] * rx; py[k] = py[k - 1] * ry; pz[k] = pz[k - 1] * rz; }
+        for (int c = 0; c < ncomp; ++c) {
+            const int lx = lmn_tab[l][c][0], ly = lmn_tab[l][c][1], lz = lmn_tab[l][c][2];
+            double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (on) {
+                const double ang = px[lx] * py[ly] * pz[lz], up = ang * qp;
+                v0 = ang * q;
+                v1 = (lx ? (double)lx * (px[lx - 1] * py[ly] * pz[lz]) * q : 0.0) - 2.0 * rx * up;
+                v2 = (ly ? (double)ly * (px[lx] * py[ly - 1] * pz[lz]) * q : 0.0) - 2.0 * ry * up;
+                v3 = (lz ? (double)lz * (px[lx] * py[ly] * pz[lz - 1]) * q : 0.0) - 2.0 * rz * up;
+            }
+            const long f = f2user[B.sh_foff[s] + c], nb = B.nbf;
+            if (bf) bf[i * nb + f] = v0;
+            if (dr) { dr[(i * 3 + 0) * nb + f] = v1; dr[(i * 3 + 1) * nb + f] = v2; dr[(i * 3 + 2) * nb + f] = v3; }
+        }
+    }
+}
+void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s) {
+    if (n <= 0) return;
+    k_basis_dense<<<(unsigned)n, 128, 0, s>>>(B, f2user, n, r, bf, dr);
+}
+
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s) {
     if (ntiles <= 0) return;

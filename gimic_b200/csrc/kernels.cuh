@@ -60,6 +60,7 @@ void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, 
                        TileGeo *geo, TileInfo *info, cudaStream_t s);
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s);
+void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s);
 size_t sort_temp_bytes(long n);
 void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s);
 

@@ -168,6 +168,15 @@ class Gimic:
         _lib.check(_lib.lib().gimic_b200_atom_coords(self._h, _dptr(out)))
         return out
 
+    def basis(self, r, want_dr=True):
+        """Phi[i, f] and dPhi[i, m, f] in the reference AO order (calc_basis, bfeval.f90:61-122,295-338)."""
+        r = _host(r).reshape(-1, 3)
+        n = r.shape[0]
+        bf = np.empty((n, self.nbf)); dr = np.empty((n, 3, self.nbf)) if want_dr else None
+        _lib.check(_lib.lib().gimic_b200_calc_basis(self._h, n, C.c_void_p(r.ctypes.data), C.c_void_p(bf.ctypes.data),
+                                                    C.c_void_p(dr.ctypes.data) if want_dr else None, 0))
+        return (bf, dr) if want_dr else bf
+
     def jtensors(self, r, spincase="total", out=None):
         """tens[i, m + 3*b] for points r[i, :]  (calc_jtensors, jfield.f90:62-138)."""
         L = _lib.lib()

@@ -111,6 +111,11 @@ int gimic_b200_calc_fields(gimic_b200_handle h, long n, const double *r, const d
                            double *tens, double *jvec, double *jmod, double *acid, double *edens, double *divj,
                            double divj_h, int flags);
 
+/* Basis vectors themselves (calc_basis / bfeval / dfdr, src/libgimic/bfeval.f90:61-122,295-338), reference AO order,
+ * exact zeros where a contraction is screened:  bf[i*nbf + f] = Phi_f(r_i),  dr[(3*i + m)*nbf + f] = dPhi_f/dr_m.
+ * Either output may be NULL.  (The London/GIAO vectors db, d2 are products of these with r x R_A, bfeval.f90:168-293.) */
+int gimic_b200_calc_basis(gimic_b200_handle h, long n, const double *r, double *bf, double *dr, int flags);
+
 /* Field arithmetic alone on existing tensors (the HBM-bound pass). */
 int gimic_b200_fields_from_tensors(gimic_b200_handle h, long n, const double *r, const double *tens,
                                    const double *B3, double *jvec, double *jmod, double *acid, int flags);

@@ -174,6 +174,19 @@ def test_legacy_single_point_api(gb, cases, c4h4):
     g.close()
 
 
+def test_basis_vectors_vs_oracle(c4h4, opensh):
+    """rows A1-A3 of the scope table on their own: Phi, dPhi/dr and exact screening zeros (bfeval.f90, caos.f90, basis.f90:118-136)"""
+    for (g, o), seed in ((c4h4, 1), (opensh, 2)):       # Turbomole and standard component order
+        rng = np.random.default_rng(seed)
+        r = np.vstack([rng.uniform(-7, 7, size=(40, 3)), o.atom_coords()[:2], [[0.3, -0.2, 0.0]], [[30.0, 0, 0]]])
+        bf, dr = g.basis(r)
+        for i, p in enumerate(r):
+            obf, odr, _, _ = o.calc_basis(p)
+            assert_close(bf[i], obf, "bf"); assert_close(dr[i], odr, "dr")
+            assert ((bf[i] == 0) == (obf == 0)).all(), "screening pattern differs"
+        assert (bf[-1] == 0).all() and (dr[-1] == 0).all()
+
+
 # ---- config 3: open shell ----------------------------------------------------------------------------
 def test_open_shell_spin_cases_and_golden(gb, opensh):
     g, o = opensh
