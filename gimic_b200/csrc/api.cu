@@ -196,7 +196,7 @@ int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
     if (!c->d_op[spincase]) {
         const int nbf = c->hb.nbf;
         void *p = nullptr;
-        CUDA_TRY(cudaMalloc(&p, (size_t)c->nq * c->plane_stride * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&p, (size_t)((c->nq + 1) / 2) * c->plane_stride * sizeof(double)));
         const double *A = c->d_dens[0], *Bm = nullptr; double sg = 0.0;
         if (spincase == GIMIC_B200_BETA) A = c->d_dens[1];
         if (spincase == GIMIC_B200_TOTAL) { Bm = c->d_dens[1]; sg = 1.0; }       // T_alpha + T_beta (jtensor.F90:86-88), by linearity in D, P
@@ -216,7 +216,7 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
     const size_t nn = (size_t)c->hb.nbf * c->hb.nbf;
     c->nq = c->opts.giao ? gb::NQ_GIAO : gb::NQ_NOGIAO;
     c->ldb = c->hb.nbf;
-    c->plane_stride = (long long)c->hb.nbf * c->ldb;
+    c->plane_stride = 2LL * c->hb.nbf * c->ldb;          // doubles per pair-plane [nbf][ldb][2]
     for (int sp = 0; sp < (c->opts.uhf ? 2 : 1); ++sp) {
         const double *src = sp ? dens_b : dens_a;
         if (!src) return fail(GIMIC_B200_EINVAL, sp ? "open-shell context needs beta densities" : "densities missing");

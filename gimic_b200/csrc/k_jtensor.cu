@@ -36,8 +36,8 @@ __device__ __forceinline__ void mma_16x8x4_f64(double (&c)[4], double a0, double
                  : "d"(a0), "d"(a1), "d"(b0));
 }
 // ---- async-copy / mbarrier primitives (sm_90+ PTX; SASS: LDGSTS, UBLKCP, SYNCS) ---------------------
-__device__ __forceinline__ void cp_async_8(uint32_t smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem));
+__device__ __forceinline__ void cp_async_16(uint32_t smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t mbar) {   // arrive when this thread's prior cp.async land
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar));
@@ -75,7 +75,9 @@ constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 
 template <int NQ>
 struct Smem {
     static constexpr int A_DOUBLES = BK * LDP;
-    static constexpr int B_DOUBLES = NQ * BK * LDB;
+    static constexpr int NPP = (NQ + 1) / 2;                 // pair-planes: (q0,q1) (q2,q3) (q4,q5) (q6,-)
+    static constexpr int PP_DOUBLES = BK * LDB2;             // one pair-plane of a stage: [k][16 nu x 2 + pad]
+    static constexpr int B_DOUBLES = NPP * PP_DOUBLES;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
     static constexpr size_t ROW_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;        // per-row epilogue sums + point coordinates
     static constexpr size_t BAR_OFF = ROW_OFF + (size_t)MT * ROWLD * 8;
@@ -121,15 +123,15 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
                 mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kcnt * LDP * 8));
                 tma_bulk_g2s(sA, panel + (long)kc * BK * LDP, (uint32_t)(kcnt * LDP * 8), bar_full + 8 * s);
             }
-            const double *srcB = a.Bop + nu;
-            const uint32_t dstB = sB + (uint32_t)(ldn * 8);
+            const double *srcB = a.Bop + 2 * nu;
+            const uint32_t dstB = sB + (uint32_t)(ldn * 16);
 #pragma unroll 4
             for (int k = ldk0; k < kcnt; k += 2 * NPRODUCER_WARPS) {
                 const long mu = fidx[kc * BK + k];
-                const double *src = srcB + mu * a.ldb;
-                const uint32_t dst = dstB + (uint32_t)(k * LDB * 8);
+                const double *src = srcB + 2 * mu * a.ldb;
+                const uint32_t dst = dstB + (uint32_t)(k * LDB2 * 8);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) cp_async_8(dst + (uint32_t)(q * BK * LDB * 8), src + q * a.plane_stride);
+                for (int pp = 0; pp < SM::NPP; ++pp) cp_async_16(dst + (uint32_t)(pp * SM::PP_DOUBLES * 8), src + pp * a.plane_stride);
             }
             cp_async_arrive_noinc(bar_full + 8 * s);
             if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[vc * NV + ldn]; }
@@ -200,11 +202,15 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                 // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
                 const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
                 const double a0 = pa[0], a1 = pa[8];
-                const double *pb = sB + (ks * 4 + t) * LDB + g;
+                const double2 *pb = reinterpret_cast<const double2 *>(sB + (ks * 4 + t) * LDB2) + g;   // one LDS.128 = both planes of a pair
 #pragma unroll
-                for (int q = 0; q < NQ; ++q)
+                for (int pp = 0; pp < SM::NPP; ++pp)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) mma_16x8x4_f64(acc[q][h], a0, a1, pb[q * BK * LDB + h * 8]);
+                    for (int h = 0; h < 2; ++h) {
+                        const double2 b = pb[pp * (SM::PP_DOUBLES / 2) + h * 8];
+                        mma_16x8x4_f64(acc[2 * pp][h], a0, a1, b.x);
+                        if (2 * pp + 1 < NQ) mma_16x8x4_f64(acc[2 * pp + 1][h], a0, a1, b.y);
+                    }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
@@ -338,8 +344,9 @@ void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Contraction operands in the internal (per-atom radius-sorted) function order, row-major [mu][nu]:
-// planes 0..3 = D, Px, Py, Pz (optionally alpha +/- beta), planes 4..6 = D (R_nu - R_mu)_d.
+// Contraction operands in the internal (per-atom radius-sorted) function order as PAIR-PLANES, row-major [mu][nu][2]:
+// pair 0 = (D, Px), pair 1 = (Py, Pz), pair 2 = (D(Rv-Ru)_x, D(Rv-Ru)_y), pair 3 = (D(Rv-Ru)_z, 0); optionally alpha +/- beta.
+// One (mu,nu) element of a pair is a 16-byte unit: one cp.async.cg per gather, and runs of >=4 nu fill whole 64 B HBM atoms.
 // src is the dens.f90 layout: element (a,b) at a + nbf*b.
 __global__ void k_build_operand(double *__restrict__ out, int nbf, int ldb, long long plane_stride, const double *__restrict__ srcA,
                                 const double *__restrict__ srcB, double signB, const int *__restrict__ f2user,
@@ -348,19 +355,18 @@ __global__ void k_build_operand(double *__restrict__ out, int nbf, int ldb, long
     if (nu >= nbf) return;
     const long un = f2user[nu], um = f2user[mu];
     const long src = um + (long)nbf * un, nn = (long)nbf * nbf;
-    const long dst = (long)mu * ldb + nu;
-    double d0 = 0;
+    const long dst = 2 * ((long)mu * ldb + nu);
+    double v[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        double v = srcA[q * nn + src];
-        if (srcB) v += signB * srcB[q * nn + src];
-        out[q * plane_stride + dst] = v;
-        if (q == 0) d0 = v;
+        v[q] = srcA[q * nn + src];
+        if (srcB) v[q] += signB * srcB[q * nn + src];
     }
-    if (giao) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) out[(4 + d) * plane_stride + dst] = d0 * (fR[d * nbf + nu] - fR[d * nbf + mu]);
-    }
+    for (int d = 0; d < 3; ++d) v[4 + d] = v[0] * (fR[d * nbf + nu] - fR[d * nbf + mu]);
+    v[7] = 0.0;
+    const int npp = giao ? 4 : 2;
+    for (int pp = 0; pp < npp; ++pp) *reinterpret_cast<double2 *>(out + pp * plane_stride + dst) = make_double2(v[2 * pp], v[2 * pp + 1]);
 }
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
                           const int *f2user, const double *fR, bool giao, cudaStream_t s) {

@@ -21,7 +21,7 @@ constexpr int MT = 128;    // points per tile (8 m16 row blocks, one per warp of
 constexpr int LDP = 132;   // panel row stride in doubles: 132 = 4 (mod 16) -> conflict-free A-fragment LDS.64
 constexpr int BK = 32;     // K slots per pipeline stage (the last stage of a K sweep may hold 16)
 constexpr int NV = 16;     // nu slots per accumulator chunk (2 n8 tiles per operand matrix)
-constexpr int LDB = 20;    // smem row stride of a B tile: 20 = 4 (mod 16) -> conflict-free B-fragment LDS.64
+constexpr int LDB2 = 36;   // smem row stride (doubles) of a pair-plane B tile: 16 nu x 2 + 4 pad = 18 16-byte units = 2 (mod 8) -> conflict-free LDS.128
 constexpr int STAGES = 3;  // mbarrier pipeline depth (3 x 69.6 KB)
 constexpr int NQ_GIAO = 7, NQ_NOGIAO = 4;
 
@@ -67,7 +67,7 @@ void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint6
 struct JtensorArgs {
     const TileDesc *tiles; int ntiles; int *counter;
     const double *panel_pool; const int *fidx_pool;
-    const double *Bop; long long plane_stride; int ldb;     // planar operands [NQ][nbf][ldb]
+    const double *Bop; long long plane_stride; int ldb;     // pair-plane operands [(NQ+1)/2][nbf][ldb][2]; plane_stride in doubles
     const double *fR; int nbf;
     const double *rsx, *rsy, *rsz; const int *perm;
     double *tens; double *edens;                            // outputs in user point order (edens may be null)
