@@ -298,7 +298,7 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     // host: tile descriptors, split into batches that fit the panel pool
     size_t max_tile = 0, total = 0;
     for (int t = 0; t < ntiles; ++t) {
-        int nact = (c->h_info[t].nraw + 15) / 16 * 16;
+        int nact = (c->h_info[t].nraw + 7) / 8 * 8;
         size_t d = (size_t)4 * nact * LDP;
         max_tile = std::max(max_tile, d); total += d;
     }
@@ -309,12 +309,12 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     for (int t = 0; t < ntiles; ++t) {
         TileDesc &td = c->h_tiles[t];
         td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.pad_ = 0;
-        td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 15) / 16 * 16;
+        td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 7) / 8 * 8;
         size_t d = (size_t)4 * td.nact * LDP;
         if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); off = 0; foff = 0; }
         td.panel_off = (long long)off; td.fidx_off = (long long)foff;
         off += d; foff += td.nact;
-        sum_nact += td.nact; flops += 2.0 * MT * c->nq * (double)td.nact * td.nact;
+        sum_nact += td.nact; flops += 2.0 * MT * c->nq * (double)td.nact * td.nact;   // K and N both run over nact slots (multiples of 8)
     }
     fidx_max = std::max(fidx_max, foff);
     batch_start.push_back(ntiles);

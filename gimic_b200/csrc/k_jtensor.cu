@@ -104,7 +104,7 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
         const TileDesc td = a.tiles[tile];
         if (td.nact == 0) continue;
         const int nact = td.nact;
-        const int nkc = (nact + BK - 1) / BK, nvc = nact / NV;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nact + NV - 1) / NV;   // nact is a multiple of 8: the last nu chunk may hold 8 slots
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
         const int *fidx = a.fidx_pool + td.fidx_off;
@@ -113,7 +113,7 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
         const int pw = warp - NCONSUMER_WARPS;
         const int ldn = lane & 15, ldk0 = (lane >> 4) + 2 * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0+8, ...
         int kc = 0, vc = 0;
-        long nu = fidx[ldn];
+        long nu = fidx[min(ldn, nact - 1)];
         for (uint32_t itl = 0; itl < NIT; ++itl) {
             const uint32_t gi = git + itl, s = gi % STAGES, ph = (gi / STAGES) & 1;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -123,10 +123,11 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
                 mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kcnt * LDP * 8));
                 tma_bulk_g2s(sA, panel + (long)kc * BK * LDP, (uint32_t)(kcnt * LDP * 8), bar_full + 8 * s);
             }
+            const bool nu_ok = vc * NV + ldn < nact;
             const double *srcB = a.Bop + 2 * nu;
             const uint32_t dstB = sB + (uint32_t)(ldn * 16);
 #pragma unroll 4
-            for (int k = ldk0; k < kcnt; k += 2 * NPRODUCER_WARPS) {
+            for (int k = ldk0; k < (nu_ok ? kcnt : 0); k += 2 * NPRODUCER_WARPS) {
                 const long mu = fidx[kc * BK + k];
                 const double *src = srcB + 2 * mu * a.ldb;
                 const uint32_t dst = dstB + (uint32_t)(k * LDB2 * 8);
@@ -134,7 +135,7 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
                 for (int pp = 0; pp < SM::NPP; ++pp) cp_async_16(dst + (uint32_t)(pp * SM::PP_DOUBLES * 8), src + pp * a.plane_stride);
             }
             cp_async_arrive_noinc(bar_full + 8 * s);
-            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[vc * NV + ldn]; }
+            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[min(vc * NV + ldn, nact - 1)]; }
         }
         }
         git += NIT;
@@ -163,7 +164,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
             continue;
         }
         const int nact = td.nact;
-        const int nkc = (nact + BK - 1) / BK, nvc = nact / NV;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nact + NV - 1) / NV;   // nact is a multiple of 8: the last nu chunk may hold 8 slots
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
         const long plane = (long)nact * LDP;
@@ -194,6 +195,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                         for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
             }
             const int nks = min(BK, nact - kc * BK) / 4;
+            const bool h1 = vc * NV + 8 < nact;                     // second n8 tile of this chunk holds real slots
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
             mbar_wait(bar_full + 8 * s, ph);
@@ -207,6 +209,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                 for (int pp = 0; pp < SM::NPP; ++pp)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !h1) continue;
                         const double2 b = pb[pp * (SM::PP_DOUBLES / 2) + h * 8];
                         mma_16x8x4_f64(acc[2 * pp][h], a0, a1, b.x);
                         if (2 * pp + 1 < NQ) mma_16x8x4_f64(acc[2 * pp + 1][h], a0, a1, b.y);
@@ -225,6 +228,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
+                        if (h == 1 && !h1) continue;
                         const int slot = vc * NV + h * 8 + 2 * t + j;
                         const double *pe = panel + (long)slot * LDP;
                         double Rx = 0, Ry = 0, Rz = 0;

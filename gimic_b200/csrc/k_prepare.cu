@@ -100,14 +100,16 @@ void launch_grid_points(const double *ob, const double *p0, const double *p1, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Conservative screening of one atom against a tile's bounding sphere.  A shell can only be
-// non-zero at some point p of the tile if |p - R| <= thr; |p - R| >= |c - R| - rho, so shells with
-// thr < |c-R| - rho are dropped.  Shells are sorted by descending thr inside each atom, so the
-// active set of an atom is a prefix.  The exact per-point test is applied again in k_basis.
-__device__ __forceinline__ void atom_active(const DevBasis &B, int a, double cx, double cy, double cz, double rho, int &nsh, int &nfun) {
+// Conservative screening of one atom against a tile's axis-aligned bounding box.  A shell can only be non-zero at some
+// point p of the tile if |p - R| <= thr, and |p - R| >= dist(R, box); so shells with thr < dist(R, box) are dropped.
+// Shells are sorted by descending thr inside each atom, so the active set of an atom is a prefix.  The exact per-point
+// test is applied again in k_basis.
+__device__ __forceinline__ void atom_active(const DevBasis &B, int a, const TileGeo &tg, int &nsh, int &nfun) {
     nsh = 0; nfun = 0;
-    double dx = cx - B.atom_xyz[3 * a], dy = cy - B.atom_xyz[3 * a + 1], dz = cz - B.atom_xyz[3 * a + 2];
-    double lim = sqrt(dx * dx + dy * dy + dz * dz) - rho - 1e-9;
+    const double x = B.atom_xyz[3 * a], y = B.atom_xyz[3 * a + 1], z = B.atom_xyz[3 * a + 2];
+    const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
+                 dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
+    const double lim = sqrt(dx * dx + dy * dy + dz * dz) - 1e-9;
     if (lim > B.atom_maxthr[a]) return;
     int s1 = B.atom_shell_off[a + 1];
     for (int s = B.atom_shell_off[a]; s < s1; ++s) {
@@ -138,11 +140,14 @@ __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__
     const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
     auto fmn = [](double a, double b) { return fmin(a, b); };
     auto fmx = [](double a, double b) { return fmax(a, b); };
-    const double cx = 0.5 * (block_reduce_128(x, fmn, s4) + block_reduce_128(x, fmx, s4));
-    const double cy = 0.5 * (block_reduce_128(y, fmn, s4) + block_reduce_128(y, fmx, s4));
-    const double cz = 0.5 * (block_reduce_128(z, fmn, s4) + block_reduce_128(z, fmx, s4));
+    TileGeo tg;
+    tg.lox = block_reduce_128(x, fmn, s4); tg.hix = block_reduce_128(x, fmx, s4);
+    tg.loy = block_reduce_128(y, fmn, s4); tg.hiy = block_reduce_128(y, fmx, s4);
+    tg.loz = block_reduce_128(z, fmn, s4); tg.hiz = block_reduce_128(z, fmx, s4);
+    const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
     const double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
     const double rho = block_reduce_128(d, fmx, s4);
+    tg.rho = rho; tg.pad_ = 0.0;
     // largest gap between consecutive points of the sorted run (where a curve jump would be cut)
     unsigned long long gi = 0;
     if ((int)threadIdx.x + 1 < sg.npts) {
@@ -152,11 +157,11 @@ __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__
     auto umx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
     gi = block_reduce_128(gi, umx, u4);
     int cnt = 0;
-    for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, cx, cy, cz, rho, nsh, nfun); cnt += nfun; }
+    for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, tg, nsh, nfun); cnt += nfun; }
     auto iadd = [](int a, int b) { return a + b; };
     cnt = block_reduce_128(cnt, iadd, i4);
     if (threadIdx.x == 0) {
-        geo[blockIdx.x] = TileGeo{cx, cy, cz, rho};
+        geo[blockIdx.x] = tg;
         info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt};
     }
 }
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__res
     __syncthreads();
     for (int a0 = 0; a0 < B.natoms; a0 += 128) {
         int a = a0 + tid, nsh = 0, nfun = 0;
-        if (a < B.natoms) atom_active(B, a, tg.cx, tg.cy, tg.cz, tg.rho, nsh, nfun);
+        if (a < B.natoms) atom_active(B, a, tg, nsh, nfun);
         int flag = nfun > 0, sf = nfun, sr = flag;   // inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

@@ -40,14 +40,14 @@ struct DevBasis {
 
 struct TileDesc {
     int pt0, npts;      // range in the sorted point list
-    int nact;           // active slots, padded to a multiple of 16 (0: nothing within screening range)
+    int nact;           // active slots, padded to a multiple of 8 (0: nothing within screening range)
     int nraw;           // unpadded active function count
     int geo, pad_;      // index into the TileGeo array
     long long panel_off;  // doubles, into the panel pool: 4 planes x nact x LDP
     long long fidx_off;   // ints, into the index pool
 };
 
-struct TileGeo { double cx, cy, cz, rho; };
+struct TileGeo { double lox, loy, loz, hix, hiy, hiz, rho, pad_; };   // axis-aligned bounding box of the tile's points (+ radius about its centre)
 struct TileSeg { int pt0, npts; };                         // a tile = npts <= MT consecutive points of the sorted list
 struct TileInfo { float rho, gmax; int imax, nraw; };      // radius, largest consecutive gap (and where), active functions
 
