@@ -100,17 +100,26 @@ void launch_grid_points(const double *ob, const double *p0, const double *p1, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Conservative screening of one atom against a tile's axis-aligned bounding box.  A shell can only be non-zero at some
-// point p of the tile if |p - R| <= thr, and |p - R| >= dist(R, box); so shells with thr < dist(R, box) are dropped.
-// Shells are sorted by descending thr inside each atom, so the active set of an atom is a prefix.  The exact per-point
-// test is applied again in k_basis.
-__device__ __forceinline__ void atom_active(const DevBasis &B, int a, const TileGeo &tg, int &nsh, int &nfun) {
+// Screening of one atom against a tile: a shell can only be non-zero at some point p of the tile if |p - R| <= thr.
+// Cheap reject by the distance to the tile's bounding box, then the exact minimum distance over the tile's points
+// (staged in shared memory), so the active set is the exact union over the 128 points at shell granularity.  Shells are
+// sorted by descending thr inside each atom, so the active set of an atom is a prefix.  k_tile_count and k_basis call this
+// with identical inputs (same arithmetic => same counts); the per-point test sqrt(r2) <= thr is applied again in k_basis.
+__device__ __forceinline__ void atom_active(const DevBasis &B, int a, const TileGeo &tg, const double *sx, const double *sy,
+                                            const double *sz, int npts, int &nsh, int &nfun) {
     nsh = 0; nfun = 0;
     const double x = B.atom_xyz[3 * a], y = B.atom_xyz[3 * a + 1], z = B.atom_xyz[3 * a + 2];
     const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
                  dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
-    const double lim = sqrt(dx * dx + dy * dy + dz * dz) - 1e-9;
-    if (lim > B.atom_maxthr[a]) return;
+    const double mx = B.atom_maxthr[a];
+    if (sqrt(dx * dx + dy * dy + dz * dz) - 1e-9 > mx) return;
+    double d2 = 1e300;
+    for (int p = 0; p < npts; ++p) {
+        const double ex = sx[p] - x, ey = sy[p] - y, ez = sz[p] - z;
+        d2 = fmin(d2, ex * ex + ey * ey + ez * ez);
+    }
+    const double lim = sqrt(d2) - 1e-9;
+    if (lim > mx) return;
     int s1 = B.atom_shell_off[a + 1];
     for (int s = B.atom_shell_off[a]; s < s1; ++s) {
         if (B.sh_thr[s] >= lim) { int l = B.sh_l[s]; nfun += (l + 1) * (l + 2) / 2; ++nsh; }
@@ -134,10 +143,12 @@ __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__
     __shared__ double s4[4];
     __shared__ int i4[4];
     __shared__ unsigned long long u4[4];
+    __shared__ double sx[MT], sy[MT], sz[MT];
     const TileSeg sg = segs[blockIdx.x];
     const bool valid = threadIdx.x < sg.npts;
     const long pt = sg.pt0 + (valid ? threadIdx.x : 0);
     const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
+    sx[threadIdx.x] = x; sy[threadIdx.x] = y; sz[threadIdx.x] = z;
     auto fmn = [](double a, double b) { return fmin(a, b); };
     auto fmx = [](double a, double b) { return fmax(a, b); };
     TileGeo tg;
@@ -157,7 +168,8 @@ __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__
     auto umx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
     gi = block_reduce_128(gi, umx, u4);
     int cnt = 0;
-    for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, tg, nsh, nfun); cnt += nfun; }
+    __syncthreads();
+    for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, tg, sx, sy, sz, sg.npts, nsh, nfun); cnt += nfun; }
     auto iadd = [](int a, int b) { return a + b; };
     cnt = block_reduce_128(cnt, iadd, i4);
     if (threadIdx.x == 0) {
@@ -191,11 +203,13 @@ __global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__res
     int *fidx = fidx_pool + td.fidx_off;
     const long plane = (long)td.nact * LDP;
 
+    __shared__ double sx[MT], sy[MT], sz[MT];
+    { const long p = td.pt0 + (tid < td.npts ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
     if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
     __syncthreads();
     for (int a0 = 0; a0 < B.natoms; a0 += 128) {
         int a = a0 + tid, nsh = 0, nfun = 0;
-        if (a < B.natoms) atom_active(B, a, tg, nsh, nfun);
+        if (a < B.natoms) atom_active(B, a, tg, sx, sy, sz, td.npts, nsh, nfun);
         int flag = nfun > 0, sf = nfun, sr = flag;   // inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
