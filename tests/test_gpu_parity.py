@@ -311,3 +311,35 @@ def test_divj_small_for_giao_and_device_pointers(gb, c4h4):
     tt = g.jtensors(rt)
     assert tt.is_cuda and tt.shape == (64, 9)
     assert_close(tt.cpu().numpy(), o.ctensor(r), "device-pointer path")
+
+
+def test_full_size_nbf10008_properties(gb):
+    """BASELINE.json's full basis size (278 centres, nbf = 10 008): oracle parity on a sample the CPU finishes in seconds,
+    and size-independent properties on 20 000 points: linearity (UHF total = alpha + beta, spindens = alpha - beta through
+    three different operand sets), independence of point order / tiling, grid-slab consistency."""
+    sh, da, nbf = fixtures.synthetic_case(278, "flake", seed=1234)
+    assert nbf == 10008
+    db = fixtures.synthetic_density(nbf, seed=99, general_p=True)
+    fa, fb = fixtures.dens_to_colmajor(da), fixtures.dens_to_colmajor(db)
+    g = gb.Gimic.from_arrays(dens_alpha=fa, dens_beta=fb, **sh)
+    rng = np.random.default_rng(12)
+    lo, hi = sh["coords"].min(0) - 6.0, sh["coords"].max(0) + 6.0
+    r = rng.uniform(lo, hi, size=(20000, 3)); r[:, 2] = rng.uniform(-5, 5, size=20000)
+    ta, tb, tt, ts = (g.jtensors(r, sc) for sc in ("alpha", "beta", "total", "spindens"))
+    scale = np.abs(ta).max() + np.abs(tb).max()
+    assert np.abs(tt - (ta + tb)).max() < 1e-12 * scale
+    assert np.abs(ts - (ta - tb)).max() < 1e-12 * scale
+    p = rng.permutation(20000)
+    assert_close(g.jtensors(r[p], "alpha"), ta[p], "point order")
+    # regular grid: device-generated slab == explicit points
+    from gimic_b200 import synthetic
+    origin, basv, pts = synthetic.box_grid(sh["coords"], (32, 32, 8))
+    grid = gb.Grid(origin, basv, pts)
+    tg = g.jtensors_grid(grid, 1000, 5000, "alpha")
+    assert_close(tg, g.jtensors(grid.points()[1000:5000], "alpha"), "grid slab")
+    # oracle (dense 7 GEMV per point, 5.6 GB streamed per point): 48 points
+    o = O.Oracle.from_arrays(dens_a=fa, dens_b=fb, **sh)
+    idx = rng.choice(20000, 48, replace=False)
+    assert_close(ta[idx], o.ctensor(r[idx], "alpha"), "alpha vs oracle at nbf=10008")
+    assert_close(tt[idx[:16]], o.ctensor(r[idx[:16]], "total"), "total vs oracle at nbf=10008")
+    g.close()
