@@ -661,6 +661,30 @@ int gimic_b200_calc_basis(gimic_b200_handle c, long n, const double *r, double *
     return 0;
 }
 
+int gimic_b200_property(gimic_b200_handle c, long n, const double *r, const double *w, const double *tens, int natoms,
+                        const double *coords, int nseg, const long *seg_end, double *part, int flags) {
+    if (!c || !r || !w || !tens || !coords || !seg_end || !part || natoms < 0 || nseg <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
+    if (seg_end[nseg - 1] != n) return fail(GIMIC_B200_EINVAL, "segment ends must be cumulative and finish at n");
+    for (int i = 1; i < nseg; ++i) if (seg_end[i] < seg_end[i - 1]) return fail(GIMIC_B200_EINVAL, "segment ends must be non-decreasing");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const double *d_r, *d_t, *d_w;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    if (int rc = stage_in(c, c->tens_tmp, tens, (size_t)9 * n, flags, &d_t)) return rc;
+    if (int rc = stage_in(c, c->f_tmp, w, (size_t)n, flags, &d_w)) return rc;
+    const size_t nout = (size_t)(natoms + 1) * nseg * 5;
+    if (c->quad.ensure((nout + 3 * (size_t)natoms + 1) * 8 + (size_t)nseg * 8 + 64)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (property)");
+    double *d_out = c->quad.as<double>(), *d_xyz = d_out + nout;
+    long *d_seg = reinterpret_cast<long *>(d_xyz + 3 * (size_t)natoms + 1);
+    if (natoms) CUDA_TRY(cudaMemcpyAsync(d_xyz, coords, (size_t)3 * natoms * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_seg, seg_end, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
+    gb::launch_property(n, d_r, d_w, d_t, natoms, d_xyz, nseg, d_seg, d_out, st);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(part, d_out, nout * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts) {
     if (!pts || !wgts || npts <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
     int rc = gb::gauss_blocks(a, b, npts, order, quadrature, pts, wgts);

@@ -143,6 +143,48 @@ __global__ void __launch_bounds__(256) k_quad_final(const double *__restrict__ p
         __syncthreads();
     }
 }
+// ---------------------------------------------------------------------------------------------
+// get_property (src/fgimic/jfield.f90:584-929): Biot-Savart shielding sigma_K at every nucleus and the magnetizability chi
+// from the tensor field on a weighted point set (NumGrid).  Block (seg, k): partial sums over point segment `seg`
+// (the per-atom grid blocks of nelpts.info) for nucleus k; k == natoms is the magnetizability.  Fixed-order tree => deterministic.
+//   out[(k*nseg + seg)*5 + {0,1,2}] = sum w * integrand_{xx,yy,zz},  [3] = sum of positive w*(xx+yy+zz), [4] = negative
+__global__ void __launch_bounds__(256) k_property(long n, const double *__restrict__ r, const double *__restrict__ w,
+                                                  const double *__restrict__ tens, int natoms, const double *__restrict__ coords,
+                                                  int nseg, const long *__restrict__ seg_end, double *__restrict__ out) {
+    __shared__ double red[256];
+    const int seg = blockIdx.x, k = blockIdx.y;
+    const long lo = seg ? seg_end[seg - 1] : 0, hi = seg_end[seg];
+    double acc[5] = {0, 0, 0, 0, 0};
+    const bool chi = (k == natoms);
+    const double cx = chi ? 0.0 : coords[3 * k], cy = chi ? 0.0 : coords[3 * k + 1], cz = chi ? 0.0 : coords[3 * k + 2];
+    for (long i = lo + threadIdx.x; i < hi; i += 256) {
+        const double dx = r[3 * i] - cx, dy = r[3 * i + 1] - cy, dz = r[3 * i + 2] - cz;
+        const double *t = tens + 9 * i;
+        double f;
+        if (chi) f = 0.5;                                                                   // jfield.f90:834
+        else f = 1.0e6 * (-1.0 / pow(dx * dx + dy * dy + dz * dz, 1.5) / (137.0359998 * 137.0359998));   // jfield.f90:702
+        // jvec = T.(-e_b) = -T(:,b)   (jfield.f90:704-725)
+        const double ixx = f * (dy * (-t[2]) - dz * (-t[1]));
+        const double iyy = f * (dz * (-t[3]) - dx * (-t[5]));
+        const double izz = f * (dx * (-t[7]) - dy * (-t[6]));
+        const double wi = w[i], pd = ixx + iyy + izz;
+        acc[0] += wi * ixx; acc[1] += wi * iyy; acc[2] += wi * izz;
+        if (pd >= 0.0) acc[3] += pd * wi; else acc[4] += pd * wi;
+    }
+    for (int q = 0; q < 5; ++q) {
+        red[threadIdx.x] = acc[q];
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) out[((long)k * nseg + seg) * 5 + q] = red[0];
+        __syncthreads();
+    }
+}
+void launch_property(long n, const double *r, const double *w, const double *tens, int natoms, const double *coords, int nseg,
+                     const long *seg_end, double *out, cudaStream_t s) {
+    if (nseg <= 0) return;
+    k_property<<<dim3(nseg, natoms + 1), 256, 0, s>>>(n, r, w, tens, natoms, coords, nseg, seg_end, out);
+}
+
 void launch_quadrature(const QuadArgs &q, cudaStream_t s) {
     if (q.nrows <= 0) { cudaMemsetAsync(q.out7, 0, 7 * sizeof(double), s); return; }
     k_quad_rows<<<(q.nrows + 3) / 4, 128, 0, s>>>(q);

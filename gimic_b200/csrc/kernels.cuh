@@ -91,5 +91,7 @@ struct QuadArgs {
     double *out7;                                 // device, 7 doubles
 };
 void launch_quadrature(const QuadArgs &q, cudaStream_t s);
+void launch_property(long n, const double *r, const double *w, const double *tens, int natoms, const double *coords, int nseg,
+                     const long *seg_end, double *out, cudaStream_t s);
 
 }  // namespace gb

@@ -138,8 +138,17 @@ class Driver:
         self.say("*****************************************")
         cases = [("total", "")] + ([("alpha", "alpha"), ("beta", "beta"), ("spindens", "spindens")] if self.uhf else [])
         grid, wd, I = self.grid, self.workdir, self.inp
+        cache = {}
+        if self.uhf:
+            # the tensor is linear in the densities: alpha and beta are evaluated once, total = alpha + beta and
+            # spindens = alpha - beta exactly as ctensor combines them (jtensor.F90:86-99); the reference re-evaluates
+            # everything for each of the four spin cases (6 tensor passes per point, gimic.F90:206-217)
+            cache["alpha"], cache["beta"] = self._tensors("alpha"), self._tensors("beta")
+            if self.rank == 0:
+                cache["total"] = cache["alpha"] + cache["beta"]
+                cache["spindens"] = cache["alpha"] - cache["beta"]
         for sc, tag in cases:
-            tens = self._tensors(sc)
+            tens = cache[sc] if self.uhf and (self.rank == 0) else (None if self.uhf else self._tensors(sc))
             if self.rank != 0:
                 continue
             r = grid.points()
@@ -156,6 +165,8 @@ class Driver:
                     writers.write_vti_scalar(os.path.join(wd, "acid.vti"), grid, f["acid"])
                 if I.get("Essential.jmod"):
                     writers.write_vti_scalar(os.path.join(wd, f"jmod{tag}.vti"), grid, f["jmod"])
+            if I.get("Essential.prop"):
+                self.run_property(tens)
             if grid.mode in ("std", "base", "bond") and grid.gtype == "even":
                 writers.write_vti_vector(os.path.join(wd, f"jvec{tag}.vti"), grid, jv)
             elif (grid.mode in ("std", "base") and grid.gauss) or grid.mode == "file":
@@ -164,6 +175,57 @@ class Driver:
                     writers.write_vtu_vector(os.path.join(wd, "jvec.vtu"), r, jv, writers.read_ele(ele))
                 else:
                     self.out.write(" not writing a vtu file, because the file grid.1.ele was not found.\n")
+
+    def run_property(self, tens):
+        """get_property (jfield.f90:584-929): needs coord.au, gridfile.grd, grid_w.grd (and nelpts.info) in the work dir;
+        the tensor field must have been computed on the points of gridfile.grd (Grid(file))."""
+        wd, w = self.workdir, self.out.write
+        need = [os.path.join(wd, f) for f in ("coord.au", "gridfile.grd", "grid_w.grd")]
+        if not all(os.path.exists(f) for f in need):
+            w(" at least one of the files coord.au, gridfile.grd, and grid_w.grd is missing.Therefore any property calculation is skipped.\n")
+            return
+        coord = np.loadtxt(need[0]).reshape(-1, 3)
+        grd = np.loadtxt(need[1]).reshape(-1, 3)
+        wg = np.loadtxt(need[2]).ravel()
+        nel = os.path.join(wd, "nelpts.info")
+        counts = np.loadtxt(nel, dtype=np.int64).reshape(-1, 2)[:, 1] if os.path.exists(nel) else np.array([grd.shape[0]])
+        if counts.sum() != grd.shape[0]:
+            counts = np.array([grd.shape[0]])
+        res = self.g.property(grd, wg, tens, coord, counts)
+        self.property_results = res
+        w(f" npts{grd.shape[0]:12d}\n")
+        def table(contrib):
+            w("  \n atom contributions, total, positive, negative\n")
+            for l, c in enumerate(contrib):
+                w(f"atom {l + 1:5d}{c[0]:14.6f}{c[1]:14.6f}{c[2]:14.6f}\n")
+            cs = contrib.sum(0)
+            w(f"{'sum ':>10s}{cs[0]:14.6f}{cs[1]:14.6f}{cs[2]:14.6f}\n")
+            w(" ****************************************************\n")
+        for k in range(coord.shape[0]):
+            sg = res["sigma"][k]
+            w(f" atom {k + 1:11d}\n in ppm\n")
+            for lbl, v in zip(("sigma_xx ", "sigma_yy ", "sigma_zz "), sg):
+                w(f" {lbl:>10s}  {v:14.6f}\n")
+            w(f"{'shielding constant    = ':>30s}  {res['sigma_iso'][k]:14.6f}\n")
+            w(f"{'positive contribution = ':>30s}  {res['sigma_pos'][k]:14.6f}\n")
+            w(f"{'negative contribution = ':>30s}  {res['sigma_neg'][k]:14.6f}\n")
+            w(f"{'sum = ':>30s}  {res['sigma_pos'][k] + res['sigma_neg'][k]:14.6f}\n")
+            table(res["sigma_atoms"][k])
+        w(" \n \n")
+        for lbl, v in zip(("chi_xx ", "chi_yy ", "chi_zz "), res["chi"]):
+            w(f" {lbl:>7s}  {v:14.8f}\n")
+        w(" in au\n")
+        w(f" {'isotropic magnetizability chi = ':>30s}  {res['chi_iso']:14.6f}\n")
+        w(f" {'positive contribution         = ':>30s}  {res['chi_pos']:14.6f}\n")
+        w(f" {'negative contribution         = ':>30s}  {res['chi_neg']:14.6f}\n")
+        w(f" {'sum ':>30s}  {res['chi_pos'] + res['chi_neg']:14.6f}\n \n")
+        fac = 7.89104e-29                                   # fac_au2simag, jfield.f90:606
+        w(" in SI units J/T^2 \n conversion factor: 7.89104*10^-29 J/T^2 \n \n")
+        for lbl, v in (("isotropic magnetizability = ", res["chi_iso"]), ("positive contribution     = ", res["chi_pos"]),
+                       ("negative contribution     = ", res["chi_neg"]), ("sum ", res["chi_pos"] + res["chi_neg"])):
+            w(f"{lbl:>30s}  {writers.fortran_e(v * fac, 14, 6)}\n")
+        w(" ****************************************************\n")
+        table(res["chi_atoms"])
 
     def _note_spin(self, sc):
         if self.uhf:

@@ -256,6 +256,27 @@ class Gimic:
                                           int(jlo), int(jhi), _dptr(out)))
         return out
 
+    def property(self, r, w, tens, coords, seg_counts=None):
+        """Shieldings and magnetizability from a tensor field on a weighted point set (get_property, jfield.f90:584-929).
+        seg_counts: points per atom block (nelpts.info, 2nd column); default one segment.  Returns a dict with
+        sigma[k] = (xx, yy, zz) in ppm, sigma_pos/neg[k] (already /3 like the reference prints), sigma_atoms[k][s] =
+        (total, positive, negative) contribution of point block s, and the same for chi (au)."""
+        r = _host(r).reshape(-1, 3); w = _host(w).ravel(); tens = _host(tens).reshape(-1, 9); coords = _host(coords).reshape(-1, 3)
+        n, nat = r.shape[0], coords.shape[0]
+        seg = np.array([n] if seg_counts is None else np.cumsum(seg_counts), dtype=np.int64)
+        nseg = seg.size
+        part = np.zeros((nat + 1, nseg, 5))
+        _lib.check(_lib.lib().gimic_b200_property(self._h, n, C.c_void_p(r.ctypes.data), C.c_void_p(w.ctypes.data),
+                                                  C.c_void_p(tens.ctypes.data), nat, _dptr(coords), nseg,
+                                                  seg.ctypes.data_as(C.POINTER(C.c_long)), _dptr(part), 0))
+        cum = np.cumsum(part, axis=1)                                   # running sums at the segment ends (scont)
+        tot = cum[:, -1, :]
+        scont = np.stack([cum[:, :, 0:3].sum(-1) / 3.0, cum[:, :, 3] / 3.0, cum[:, :, 4] / 3.0], -1)
+        contrib = np.diff(scont, axis=1, prepend=0.0)                   # what the reference prints per atom block
+        return dict(sigma=tot[:nat, 0:3], sigma_iso=tot[:nat, 0:3].sum(1) / 3.0, sigma_pos=tot[:nat, 3] / 3.0,
+                    sigma_neg=tot[:nat, 4] / 3.0, sigma_atoms=contrib[:nat], chi=tot[nat, 0:3], chi_iso=tot[nat, 0:3].sum() / 3.0,
+                    chi_pos=tot[nat, 3] / 3.0, chi_neg=tot[nat, 4] / 3.0, chi_atoms=contrib[nat])
+
     def set_profiling(self, on=True):
         _lib.check(_lib.lib().gimic_b200_set_profiling(self._h, int(on)))
 

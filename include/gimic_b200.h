@@ -145,6 +145,15 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle h, const gimic_b200_grid *g,
 int gimic_b200_integrate(gimic_b200_handle h, const gimic_b200_grid *g, const double *B3, int spincase, int what,
                          int jlo, int jhi, double *out7);
 
+/* get_property (src/fgimic/jfield.f90:584-929): shielding and magnetizability quadrature of an existing tensor field on a
+ * weighted point set (NumGrid: r = gridfile.grd, w = grid_w.grd, coords = coord.au, segments = the per-atom grid blocks of
+ * nelpts.info as cumulative end indices).  part[(k*nseg + s)*5 + q]: for nucleus k (k == natoms: magnetizability) and point
+ * segment s the sums  q=0,1,2: w * integrand_xx,yy,zz  (sigma in ppm: 1e6 * (-1/|d|^3/c^2) (d x J_b)_b, chi: 1/2 (r x J_b)_b,
+ * J_b = T.(-e_b)),  q=3 / q=4: positive / negative part of w*(xx+yy+zz).  The reference's running totals and per-atom
+ * contributions are prefix sums of these over s.  r, w, tens: host or device (flags); coords, seg_end, part: host. */
+int gimic_b200_property(gimic_b200_handle h, long n, const double *r, const double *w, const double *tens, int natoms,
+                        const double *coords, int nseg, const long *seg_end, double *part, int flags);
+
 /* Gauss-Legendre (quadrature=0) / Lobatto (1) nodes in the block layout of setup_gauss_data
  * (gaussint.f90:267-319); host only. */
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);

@@ -1057,4 +1057,36 @@ int go_integrate(void *h, void *gv, const double *bb, const char *spincase, int 
     return 0;
 }
 
+// ---- get_property: src/fgimic/jfield.f90:584-929 (sequential running sums exactly as the reference) ----------------
+// out per nucleus k (k == natoms: magnetizability): [0..2] sigma/chi xx,yy,zz; [3] spos; [4] sneg; then scont[nseg][3]
+// (cumulative (xx+yy+zz)/3, spos/3, sneg/3 at the end of every point block)
+void go_property(long n, const double *grd, const double *wg, const double *jtens, int natoms, const double *coord, int nseg,
+                 const long *nelpts, double *out) {
+    const int stride = 5 + 3 * nseg;
+    for (int k = 0; k <= natoms; ++k) {
+        const bool chi = (k == natoms);
+        double sig[3] = {0, 0, 0}, spos = 0, sneg = 0;
+        double *o = out + (size_t)k * stride;
+        int iatom = 0; long iatom_npts = nelpts[0];
+        for (long i = 0; i < n; ++i) {
+            double d[3];
+            for (int j = 0; j < 3; ++j) d[j] = grd[3 * i + j] - (chi ? 0.0 : coord[3 * k + j]);
+            double f = chi ? 0.5 : 1.0e6 * (-1.0 / std::pow(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1.5) / std::pow(137.0359998, 2.0));
+            const double *t = &jtens[9 * i];
+            double bb[3], jv[3], in[3];
+            bb[0] = -1; bb[1] = 0; bb[2] = 0; matvec33(t, bb, jv); in[0] = f * (d[1] * jv[2] - d[2] * jv[1]);
+            bb[0] = 0; bb[1] = -1; bb[2] = 0; matvec33(t, bb, jv); in[1] = f * (d[2] * jv[0] - d[0] * jv[2]);
+            bb[0] = 0; bb[1] = 0; bb[2] = -1; matvec33(t, bb, jv); in[2] = f * (d[0] * jv[1] - d[1] * jv[0]);
+            for (int j = 0; j < 3; ++j) sig[j] += wg[i] * in[j];
+            double pd = in[0] + in[1] + in[2];
+            if (pd >= 0.0) spos += pd * wg[i]; else sneg += pd * wg[i];
+            while (iatom < nseg && i + 1 == iatom_npts) {
+                o[5 + 3 * iatom] = (sig[0] + sig[1] + sig[2]) / 3.0; o[5 + 3 * iatom + 1] = spos / 3.0; o[5 + 3 * iatom + 2] = sneg / 3.0;
+                ++iatom; if (iatom < nseg) iatom_npts += nelpts[iatom];
+            }
+        }
+        o[0] = sig[0]; o[1] = sig[1]; o[2] = sig[2]; o[3] = spos; o[4] = sneg;
+    }
+}
+
 }  // extern "C"

@@ -56,6 +56,7 @@ def lib():
         L.go_jvectors.argtypes = [C.c_long, dp, dp, dp]
         L.go_jmod_signed.argtypes = [C.c_long, dp, dp, dp, dp]
         L.go_acid_field.argtypes = [C.c_long, dp, dp]
+        L.go_property.argtypes = [C.c_long, dp, dp, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_long), dp]
         L.go_gauss_points.restype = C.c_int
         L.go_gauss_points.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_char_p, dp, dp]
         L.go_grid_file.restype = C.c_void_p
@@ -262,6 +263,17 @@ def acid_field(tens):
     tens = _arr(tens); out = np.zeros(tens.shape[0])
     lib().go_acid_field(tens.shape[0], _p(tens), _p(out))
     return out
+
+
+def property(r, w, tens, coords, seg_counts):
+    """get_property (jfield.f90:584-929): returns totals[k] = (xx, yy, zz, spos, sneg) and scont[k][s] = cumulative
+    ((xx+yy+zz)/3, spos/3, sneg/3) at the end of point block s; k == natoms is the magnetizability"""
+    r = _arr(r); w = _arr(w); tens = _arr(tens); coords = _arr(coords)
+    seg = np.ascontiguousarray(seg_counts, dtype=np.int64)
+    nat, nseg = coords.shape[0], seg.size
+    out = np.zeros((nat + 1, 5 + 3 * nseg))
+    lib().go_property(r.shape[0], _p(r), _p(w), _p(tens), nat, _p(coords), nseg, seg.ctypes.data_as(C.POINTER(C.c_long)), _p(out))
+    return out[:, :5], out[:, 5:].reshape(nat + 1, nseg, 3)
 
 
 def gauss_points(a, b, npts, order, quadr="gauss"):

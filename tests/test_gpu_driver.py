@@ -113,3 +113,33 @@ def test_edens_and_divj_modes(tmp_path, cases):
     Driver(str(d / "gimic.inp"), out=io.StringIO()).run()
     dj = read_vti(str(d / "divj.vti"))
     assert dj.shape == rho.shape and np.isfinite(dj).all()
+
+
+def test_property_mode_report(tmp_path, cases):
+    """Essential.prop on a Grid(file) run (test/benzene/magnetizability layout: coord.au, gridfile.grd, grid_w.grd, nelpts.info):
+    the printed shielding / magnetizability blocks equal the oracle's get_property restatement at print precision."""
+    import oracle_lib as O
+    from gimic_b200.driver import Driver
+    d = _workdir(tmp_path, cases, "c4h4", "c4h4_read-grid")
+    txt = open(d / "gimic.inp").read() + "\nEssential {\n prop=on\n}\n"
+    open(d / "gimic.inp", "w").write(txt)
+    o = O.Oracle.from_files(cases["c4h4"]["mol"], cases["c4h4"]["xdens"], screening_thrs=1e-8)
+    xyz = o.atom_coords()
+    rng = np.random.default_rng(3)
+    counts = rng.integers(200, 400, size=xyz.shape[0])
+    r = np.vstack([xyz[a] + rng.normal(scale=1.2, size=(c, 3)) for a, c in enumerate(counts)])
+    w = rng.uniform(0.0, 0.05, size=r.shape[0])
+    np.savetxt(d / "gridfile.grd", r, fmt="%.10f"); np.savetxt(d / "grid_w.grd", w, fmt="%.12e"); np.savetxt(d / "coord.au", xyz, fmt="%.12f")
+    np.savetxt(d / "nelpts.info", np.column_stack([np.arange(1, len(counts) + 1), counts]), fmt="%d")
+    out = io.StringIO()
+    drv = Driver(str(d / "gimic.inp"), out=out)
+    drv.run()
+    r2 = np.loadtxt(d / "gridfile.grd"); w2 = np.loadtxt(d / "grid_w.grd"); c2 = np.loadtxt(d / "coord.au")
+    tot, scont = O.property(r2, w2, o.ctensor(r2), c2, counts)
+    got = out.getvalue()
+    m = re.findall(r"shielding constant    =\s+([-\d.]+)", got)
+    assert len(m) == xyz.shape[0]
+    assert np.allclose([float(x) for x in m], tot[:-1, 0:3].sum(1) / 3.0, atol=1.1e-6)
+    chi = re.search(r"isotropic magnetizability chi =\s+([-\d.]+)", got)
+    assert abs(float(chi.group(1)) - tot[-1, 0:3].sum() / 3.0) < 1.1e-6
+    assert "atom contributions, total, positive, negative" in got and "in SI units J/T^2" in got

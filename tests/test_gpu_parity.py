@@ -313,6 +313,28 @@ def test_divj_small_for_giao_and_device_pointers(gb, c4h4):
     assert_close(tt.cpu().numpy(), o.ctensor(r), "device-pointer path")
 
 
+def test_property_quadrature_vs_oracle(c4h4):
+    """get_property (row A16 / N3): shieldings at all nuclei + magnetizability on a weighted point set with per-atom
+    point blocks.  The reference's golden (benzene/magnetizability) has no runnable inputs, so this pins GPU == oracle."""
+    g, o = c4h4
+    xyz = o.atom_coords()
+    rng = np.random.default_rng(31)
+    counts = rng.integers(300, 900, size=xyz.shape[0])
+    r = np.vstack([xyz[a] + rng.normal(scale=1.5, size=(c, 3)) for a, c in enumerate(counts)])
+    w = rng.uniform(0.0, 0.05, size=r.shape[0])
+    tens = g.jtensors(r)
+    assert_close(tens, o.ctensor(r), "tensors on the numgrid-like point set")
+    got = g.property(r, w, tens, xyz, counts)
+    tot, scont = O.property(r, w, tens, xyz, counts)
+    nat = xyz.shape[0]
+    tol = lambda a, b: np.abs(a - b).max() <= 1e-10 * np.abs(b).max() + 1e-12
+    assert tol(got["sigma"], tot[:nat, 0:3]) and tol(got["sigma_pos"], tot[:nat, 3] / 3) and tol(got["sigma_neg"], tot[:nat, 4] / 3)
+    assert tol(got["chi"], tot[nat, 0:3]) and tol(got["chi_pos"], tot[nat, 3] / 3) and tol(got["chi_neg"], tot[nat, 4] / 3)
+    ref_contrib = np.diff(scont, axis=1, prepend=0.0)
+    assert tol(got["sigma_atoms"], ref_contrib[:nat]) and tol(got["chi_atoms"], ref_contrib[nat])
+    assert np.allclose(got["sigma_atoms"].sum(1)[:, 0], got["sigma_iso"], rtol=1e-12)
+
+
 def test_full_size_nbf10008_properties(gb):
     """BASELINE.json's full basis size (278 centres, nbf = 10 008): oracle parity on a sample the CPU finishes in seconds,
     and size-independent properties on 20 000 points: linearity (UHF total = alpha + beta, spindens = alpha - beta through
