@@ -580,6 +580,7 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g,
     reset_stats(c);
     const double *ob, *p0, *p1, *p2, *w0;
     if (int rc = grid_upload(c, g, &ob, &p0, &p1, &p2, &w0)) return rc;
+    cudaEventRecord(c->ev_call[0], c->stream);
     if (c->r_in.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid points)");
     gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], lo, hi, c->r_in.as<double>(), c->stream);
     c->stats.launches += 1;
@@ -588,7 +589,9 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g,
     if (!dev) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
     if (int rc = run_tensors(c, n, c->r_in.as<double>(), spincase, d_tens, nullptr)) return rc;
     if (!dev) CUDA_TRY(cudaMemcpyAsync(tens, d_tens, (size_t)9 * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    cudaEventRecord(c->ev_call[1], c->stream);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->stats.ms_total, c->ev_call[0], c->ev_call[1]);
     return 0;
 }
 
