@@ -336,12 +336,9 @@ size_t jtensor_smem_bytes(bool giao) { return giao ? Smem<NQ_GIAO>::BYTES : Smem
 
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_jtensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<NQ_GIAO>::BYTES);
-        cudaFuncSetAttribute(k_jtensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<NQ_NOGIAO>::BYTES);
-        configured = true;
-    }
+    // per-device function attribute (a process may hold contexts on several GPUs): cheap enough to set on every launch
+    if (giao) cudaFuncSetAttribute(k_jtensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<NQ_GIAO>::BYTES);
+    else cudaFuncSetAttribute(k_jtensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<NQ_NOGIAO>::BYTES);
     int grid = a.ntiles < nsm ? a.ntiles : nsm;
     if (giao) k_jtensor<true><<<grid, NTHREADS, Smem<NQ_GIAO>::BYTES, s>>>(a);
     else k_jtensor<false><<<grid, NTHREADS, Smem<NQ_NOGIAO>::BYTES, s>>>(a);

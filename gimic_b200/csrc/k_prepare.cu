@@ -335,11 +335,7 @@ void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const Ti
                   const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s) {
     if (ntiles <= 0) return;
     size_t smem = (size_t)3 * B.natoms * sizeof(int);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
     k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool);
 }
 

@@ -313,6 +313,69 @@ def test_divj_small_for_giao_and_device_pointers(gb, c4h4):
     assert_close(tt.cpu().numpy(), o.ctensor(r), "device-pointer path")
 
 
+@pytest.mark.parametrize("turbomole", [False, True])
+def test_high_angular_momentum_shells(gb, turbomole):
+    """s..h shells (l = 0..5, MAX_L of globals.f90:30) in the standard and the Turbomole component order (gtodefs.f90:86-123)"""
+    rng = np.random.default_rng(17)
+    coords = np.array([[0.0, 0.0, 0.0], [1.9, 0.4, -0.3], [-0.7, 2.1, 0.8]])
+    shells = [(0, [3.1, 0.7], [0.4, 0.7]), (1, [1.3], [1.0]), (2, [0.9, 0.35], [0.6, 0.5]), (3, [0.8], [1.0]), (4, [0.7], [1.0]), (5, [0.6], [1.0])]
+    nat = coords.shape[0]
+    sh = dict(coords=coords, nctr_per_atom=np.full(nat, len(shells), np.int32), ctr_l=np.array([s[0] for s in shells] * nat, np.int32),
+              ctr_npf=np.array([len(s[1]) for s in shells] * nat, np.int32), xp=np.array([x for s in shells for x in s[1]] * nat),
+              cc=np.array([x for s in shells for x in s[2]] * nat))
+    nbf = nat * sum((l + 1) * (l + 2) // 2 for l, _, _ in shells)
+    assert nbf == 3 * 56
+    flat = fixtures.dens_to_colmajor(fixtures.synthetic_density(nbf, seed=3, general_p=True))
+    g = gb.Gimic.from_arrays(dens_alpha=flat, turbomole_order=turbomole, **sh)
+    o = O.Oracle.from_arrays(dens_a=flat, turbomole_order=turbomole, **sh)
+    r = rng.uniform(-3, 4, size=(300, 3))
+    bf, dr = g.basis(r[:20])
+    for i in range(20):
+        obf, odr, _, _ = o.calc_basis(r[i])
+        assert_close(bf[i], obf, "bf l<=5"); assert_close(dr[i], odr, "dr l<=5")
+    assert_close(g.jtensors(r), o.ctensor(r), f"l<=5 turbomole={turbomole}")
+    g.close()
+
+
+def test_general_contraction_mol_file(gb, tmp_path):
+    """INTGRL blocks with ncf > 1 (general contractions are split into segmented ones, intgrl.f90:172-216) and
+    primitive lines that wrap over several records (list-directed reads)"""
+    mol = tmp_path / "MOL"
+    mol.write_text("""INTGRL        1    0    1    0    0    0    0    0    0
+CFOUR
+              hand-written general contraction test
+2    0            0.10E-08              0    0
+9999.00      3.00
+8.0    1 2  1  1
+O 1      0.000000000000      0.000000000000      0.200000000000
+     4   3
+    130.7093200000    0.1543289700    0.0000000000    0.0100000000
+     23.8088610000    0.5353281400    0.0000000000    0.0200000000
+      6.4436083000    0.4446345400   -0.0999672300
+    0.3000000000
+      1.1695961000    0.0000000000    0.3995128300    0.7001154700
+     2   2
+      5.0331513000    0.1559162700    0.2000000000
+      1.1695961000    0.6076837200    0.9000000000
+1.0    1 1  1
+H 1      0.000000000000      1.400000000000     -0.900000000000
+     2   1
+      3.42525091D+00  0.15432897
+      0.62391373      0.53532814
+""")
+    nbf = 3 + 2 * 3 + 1            # O: 3 s + 2 p contractions; H: 1 s
+    xd = tmp_path / "XDENS"
+    dens = fixtures.synthetic_density(nbf, seed=11)
+    fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(dens))
+    g = gb.Gimic(str(mol), str(xd), screening_thrs=1e-8)
+    o = O.Oracle.from_files(str(mol), str(xd), screening_thrs=1e-8)
+    assert g.nbf == o.nbf == nbf
+    rng = np.random.default_rng(2)
+    r = rng.uniform(-2, 2, size=(200, 3))
+    assert_close(g.jtensors(r), o.ctensor(r), "general contraction")
+    g.close()
+
+
 def test_property_quadrature_vs_oracle(c4h4):
     """get_property (row A16 / N3): shieldings at all nuclei + magnetizability on a weighted point set with per-atom
     point blocks.  The reference's golden (benzene/magnetizability) has no runnable inputs, so this pins GPU == oracle."""
