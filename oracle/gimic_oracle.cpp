@@ -1018,7 +1018,7 @@ int go_integrate(void *h, void *gv, const double *bb, const char *spincase, int 
             for (int j = 1; j <= p2; ++j) {
                 double xsum = 0, psum = 0, nsum = 0;
                 for (int i = 1; i <= p1; ++i) {
-                    double rr[3], tt[9], jvec[3], w;
+                    double rr[3], tt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, jvec[3], w;
                     gridpoint(*g, i, j, k, rr);
                     double r = std::sqrt((rr[0] - center[0]) * (rr[0] - center[0]) + (rr[1] - center[1]) * (rr[1] - center[1]) + (rr[2] - center[2]) * (rr[2] - center[2]));
                     ctensor(*c, s, rr, sc, tt, nullptr);
