@@ -183,12 +183,51 @@ void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, 
     k_tile_count<<<ntiles, 128, 0, s>>>(B, rsx, rsy, rsz, segs, geo, info);
 }
 
+// position in the Turbomole component order (gtodefs.f90:109-123) of the c-th component in the standard order (:86-106)
+__device__ constexpr signed char TM_POS[6][21] = {
+    {0},
+    {0,1,2},
+    {0,3,4,1,5,2},
+    {0,3,4,5,9,7,1,6,8,2},
+    {0,3,4,9,12,10,5,13,14,7,1,6,11,8,2},
+    {0,3,4,9,15,10,11,18,19,13,5,16,20,17,7,1,6,12,14,8,2}};
+
+// All components of one shell at one point, written to the 4 planes of the tile panel.  L is a template parameter so that
+// after unrolling every power index is a compile-time constant (registers); the earlier version indexed px[lx] dynamically
+// and generated 7 GB of local-memory traffic per launch (profiles/r01_ncu_final_summary.txt).
+template <int L>
+__device__ __forceinline__ void shell_to_panel(double rx, double ry, double rz, double q, double qp, bool on, bool tm,
+                                               double *__restrict__ p0, long plane) {
+    double px[L + 1], py[L + 1], pz[L + 1];
+    px[0] = py[0] = pz[0] = 1.0;
+#pragma unroll
+    for (int k = 1; k <= L; ++k) { px[k] = px[k - 1] * rx; py[k] = py[k - 1] * ry; pz[k] = pz[k - 1] * rz; }
+    int c = 0;
+#pragma unroll
+    for (int lx = L; lx >= 0; --lx)
+#pragma unroll
+        for (int ly = L - lx; ly >= 0; --ly, ++c) {
+            const int lz = L - lx - ly;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            if (on) {
+                const double ang = px[lx] * py[ly] * pz[lz];
+                v0 = ang * q;                                      // cgto, caos.f90:31-36
+                const double up = ang * qp;                        // dcgto, caos.f90:54-63: f_a x^(f-e_a) q - 2 x_a x^f q'
+                v1 = (lx ? (double)lx * (px[lx > 0 ? lx - 1 : 0] * py[ly] * pz[lz]) * q : 0.0) - 2.0 * rx * up;
+                v2 = (ly ? (double)ly * (px[lx] * py[ly > 0 ? ly - 1 : 0] * pz[lz]) * q : 0.0) - 2.0 * ry * up;
+                v3 = (lz ? (double)lz * (px[lx] * py[ly] * pz[lz > 0 ? lz - 1 : 0]) * q : 0.0) - 2.0 * rz * up;
+            }
+            const long o = (long)(tm ? TM_POS[L][c] : c) * LDP;
+            p0[o] = v0; p0[plane + o] = v1; p0[2 * plane + o] = v2; p0[3 * plane + o] = v3;
+        }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_basis: one CTA (128 threads = 128 points) per tile.
 //  phase A: ordered compaction of the active atoms into (atom, nshell, slot0) runs + the slot->function index list
 //  phase B: every thread evaluates its point for all active shells and writes the 4 planes
 //           P0 = Phi, P1..3 = dPhi/dx,dy,dz at panel[(plane*nact + slot)*LDP + row]  (row-contiguous => coalesced)
-__global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
+__global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
                                                const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                const double *__restrict__ rsz, double *__restrict__ panel_pool,
                                                int *__restrict__ fidx_pool) {
@@ -243,22 +282,17 @@ __global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__res
     const bool valid = row < td.npts;
     const long pt = td.pt0 + (valid ? row : 0);
     const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
-    const signed char(*lmn_tab)[21][3] = c_lmn[B.turbomole ? 1 : 0];
+    const bool tm = B.turbomole != 0;
 
     for (int rn = 0; rn < nruns; ++rn) {
         const int a = s_runs[3 * rn], nsh = s_runs[3 * rn + 1], slot0 = s_runs[3 * rn + 2];
         const double rx = x - B.atom_xyz[3 * a], ry = y - B.atom_xyz[3 * a + 1], rz = z - B.atom_xyz[3 * a + 2];
         const double r2 = rx * rx + ry * ry + rz * rz;
         const double dist = sqrt(r2);                                  // filter_screened, basis.f90:127
-        double px[6], py[6], pz[6];
-        px[0] = py[0] = pz[0] = 1.0;
-#pragma unroll
-        for (int k = 1; k < 6; ++k) { px[k] = px[k - 1] * rx; py[k] = py[k - 1] * ry; pz[k] = pz[k - 1] * rz; }
         const int sA = B.atom_shell_off[a], f0 = B.atom_func_off[a];
         for (int s = sA; s < sA + nsh; ++s) {
             const int l = B.sh_l[s], np = B.sh_nprim[s], po = B.sh_prim_off[s];
             const int slot = slot0 + (B.sh_foff[s] - f0);
-            const int ncomp = (l + 1) * (l + 2) / 2;
             double q = 0.0, qp = 0.0;
             const bool on = valid && (dist <= B.sh_thr[s]);            // basis.f90:130
             if (on) {
@@ -268,20 +302,14 @@ __global__ void __launch_bounds__(128) k_basis(DevBasis B, const TileDesc *__res
                     q += e; qp += al * e;
                 }
             }
-            for (int c = 0; c < ncomp; ++c) {
-                const int lx = lmn_tab[l][c][0], ly = lmn_tab[l][c][1], lz = lmn_tab[l][c][2];
-                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-                if (on) {
-                    const double ang = px[lx] * py[ly] * pz[lz];
-                    v0 = ang * q;                                      // cgto, caos.f90:31-36
-                    // dcgto, caos.f90:54-63:  f_a x^(f-e_a) q  -  2 x_a x^f q'
-                    const double up = ang * qp;
-                    v1 = (lx ? (double)lx * (px[lx - 1] * py[ly] * pz[lz]) * q : 0.0) - 2.0 * rx * up;
-                    v2 = (ly ? (double)ly * (px[lx] * py[ly - 1] * pz[lz]) * q : 0.0) - 2.0 * ry * up;
-                    v3 = (lz ? (double)lz * (px[lx] * py[ly] * pz[lz - 1]) * q : 0.0) - 2.0 * rz * up;
-                }
-                const long o = (long)(slot + c) * LDP + row;
-                panel[o] = v0; panel[plane + o] = v1; panel[2 * plane + o] = v2; panel[3 * plane + o] = v3;
+            double *p0 = panel + (long)slot * LDP + row;
+            switch (l) {
+                case 0: shell_to_panel<0>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
+                case 1: shell_to_panel<1>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
+                case 2: shell_to_panel<2>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
+                case 3: shell_to_panel<3>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
+                case 4: shell_to_panel<4>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
+                default: shell_to_panel<5>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
             }
         }
     }
