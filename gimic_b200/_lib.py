@@ -21,6 +21,7 @@ API_SYMBOLS = ["gimic_b200_default_opts", "gimic_b200_create", "gimic_b200_creat
                "gimic_b200_nbf", "gimic_b200_natoms", "gimic_b200_atom_coords", "gimic_b200_is_uhf",
                "gimic_b200_calc_jtensors", "gimic_b200_calc_basis", "gimic_b200_calc_fields", "gimic_b200_fields_from_tensors",
                "gimic_b200_calc_jtensors_grid", "gimic_b200_integrate", "gimic_b200_property", "gimic_b200_gauss_points",
+               "gimic_b200_c2s_rows",
                "gimic_b200_get_stats", "gimic_b200_set_profiling", "gimic_b200_last_error", "gimic_b200_version"]
 
 ALPHA, BETA, TOTAL, SPINDENS = 0, 1, 2, 3
@@ -30,7 +31,7 @@ DEVICE_PTR = 1
 
 class Opts(C.Structure):
     _fields_ = [("uhf", C.c_int), ("giao", C.c_int), ("diamag", C.c_int), ("paramag", C.c_int), ("screening", C.c_int),
-                ("screening_thrs", C.c_double), ("device", C.c_int), ("reserved", C.c_int)]
+                ("screening_thrs", C.c_double), ("device", C.c_int), ("spherical", C.c_int)]
 
 
 class GridStruct(C.Structure):
@@ -79,6 +80,7 @@ def lib():
     L.gimic_b200_integrate.argtypes = [vp, C.POINTER(GridStruct), dp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.gimic_b200_property.argtypes = [vp, C.c_long, vp, vp, vp, C.c_int, dp, C.c_int, C.POINTER(C.c_long), dp, C.c_int]
     L.gimic_b200_gauss_points.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp]
+    L.gimic_b200_c2s_rows.argtypes = [C.c_int, C.c_int, dp]
     L.gimic_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.gimic_b200_set_profiling.argtypes = [vp, C.c_int]
     L.gimic_b200_last_error.restype = C.c_char_p

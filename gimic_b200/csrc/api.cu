@@ -214,6 +214,21 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
     gb::finalize_basis(c->hb, c->opts.screening != 0, c->opts.screening_thrs);
     if (int rc = build_device_basis(c)) return rc;
     const size_t nn = (size_t)c->hb.nbf * c->hb.nbf;
+    std::vector<double> cart[2];
+    if (c->hb.spherical) {
+        // spherical=on: the kernels stay cartesian; the SAO densities are folded with the projection once,
+        // D_cart = po^T D_sao po (same bilinear form as projecting Phi, dPhi at every point, bfeval.f90:116-118,330-333)
+        const size_t ss = (size_t)c->hb.nbf_sph * c->hb.nbf_sph;
+        std::vector<double> stage;
+        for (int sp = 0; sp < (c->opts.uhf ? 2 : 1); ++sp) {
+            const double *src = sp ? dens_b : dens_a;
+            if (!src) return fail(GIMIC_B200_EINVAL, sp ? "open-shell context needs beta densities" : "densities missing");
+            if (dens_on_device) { stage.resize(4 * ss); CUDA_TRY(cudaMemcpy(stage.data(), src, 4 * ss * sizeof(double), cudaMemcpyDeviceToHost)); src = stage.data(); }
+            cart[sp].resize(4 * nn);
+            for (int m = 0; m < 4; ++m) gb::density_sph_to_cart(c->hb, src + m * ss, cart[sp].data() + m * nn);
+        }
+        dens_a = cart[0].data(); dens_b = c->opts.uhf ? cart[1].data() : nullptr; dens_on_device = false;
+    }
     c->nq = c->opts.giao ? gb::NQ_GIAO : gb::NQ_NOGIAO;
     c->ldb = c->hb.nbf;
     c->plane_stride = 2LL * c->hb.nbf * c->ldb;          // doubles per pair-plane [nbf][ldb][2]
@@ -416,7 +431,7 @@ void gimic_b200_default_opts(gimic_b200_opts *o) {
     if (!o) return;
     o->uhf = 0; o->giao = 1; o->diamag = 1; o->paramag = 1; o->screening = 1;
     o->screening_thrs = 1e-6;   // SCREEN_THRS, globals.f90:56 (gimic_interface.f90:41)
-    o->device = -1; o->reserved = 0;
+    o->device = -1; o->spherical = 0;
 }
 
 int gimic_b200_create(gimic_b200_handle *h, const char *mol, const char *xdens, const gimic_b200_opts *opts) {
@@ -427,14 +442,17 @@ int gimic_b200_create(gimic_b200_handle *h, const char *mol, const char *xdens, 
     c->mol_path = mol; c->xdens_path = xdens;
     std::string err;
     if (!gb::parse_mol(mol, c->hb, err)) { delete c; return fail(GIMIC_B200_EIO, err); }
-    const int nbf = c->hb.nbf, nmat = c->opts.uhf ? 8 : 4;
+    c->hb.spherical = c->opts.spherical != 0;
+    // spherical=on: XDENS is over the 2l+1 components per shell (get_ncgto, intgrl.f90:134-138)
+    const int nbf = c->hb.spherical ? c->hb.nbf_sph : c->hb.nbf, nmat = c->opts.uhf ? 8 : 4;
     std::vector<double> dens;
     if (!gb::read_xdens(xdens, nbf, nmat, dens, err)) { delete c; return fail(GIMIC_B200_EIO, err); }
     const size_t nn = (size_t)nbf * nbf;
     if (c->opts.uhf)   // "scaling perturbed densities by 0.5", dens.f90:94-98
         for (int sp = 0; sp < 2; ++sp) for (int b = 1; b < 4; ++b) { double *m = &dens[(sp * 4 + b) * nn]; for (size_t i = 0; i < nn; ++i) m[i] /= 2.0; }
     if (c->hb.turbomole) {   // reorder_dens, dens.f90:100-106,210-234: new(sv(i),sv(j)) = old(i,j)
-        std::vector<int> sv; gb::turbomole_permutation(c->hb, sv);
+        std::vector<int> sv;
+        if (c->hb.spherical) gb::turbomole_permutation_sph(c->hb, sv); else gb::turbomole_permutation(c->hb, sv);
         std::vector<double> tmp(nn);
         for (int m = 0; m < nmat; ++m) {
             double *src = &dens[m * nn];
@@ -458,6 +476,7 @@ int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double
     if (opts) c->opts = *opts; else gimic_b200_default_opts(&c->opts);
     std::string err;
     if (!gb::basis_from_arrays(natoms, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, turbomole_order, c->hb, err)) { delete c; return fail(GIMIC_B200_EINVAL, err); }
+    c->hb.spherical = c->opts.spherical != 0;
     int rc = init_device(c);
     if (!rc) rc = finish_create(c, dens_alpha, dens_beta, (dens_flags & GIMIC_B200_DEVICE_PTR) != 0);
     if (rc) { delete c; return rc; }
@@ -466,7 +485,7 @@ int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double
 }
 
 int gimic_b200_destroy(gimic_b200_handle h) { delete h; return 0; }
-int gimic_b200_nbf(gimic_b200_handle h) { return h ? h->hb.nbf : fail(GIMIC_B200_EINVAL, "null handle"); }
+int gimic_b200_nbf(gimic_b200_handle h) { return h ? (h->hb.spherical ? h->hb.nbf_sph : h->hb.nbf) : fail(GIMIC_B200_EINVAL, "null handle"); }
 int gimic_b200_natoms(gimic_b200_handle h) { return h ? h->hb.natoms : fail(GIMIC_B200_EINVAL, "null handle"); }
 int gimic_b200_is_uhf(gimic_b200_handle h) { return h ? h->opts.uhf : fail(GIMIC_B200_EINVAL, "null handle"); }
 int gimic_b200_atom_coords(gimic_b200_handle h, double *xyz) {
@@ -644,10 +663,37 @@ int gimic_b200_calc_basis(gimic_b200_handle c, long n, const double *r, double *
     if (n <= 0) return 0;
     if (n > 2147483647L) return fail(GIMIC_B200_EINVAL, "too many points");
     CUDA_TRY(cudaSetDevice(c->device));
-    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
     const size_t nb = (size_t)c->hb.nbf;
     const double *d_r = nullptr;
     if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    if (c->hb.spherical) {
+        // sbf = po . bf, sdr = po . dr (bfeval.f90:116-118, 330-333): cartesian vectors from the kernel, the block-diagonal
+        // projection on the host (this entry point is a diagnostic; the tensor path folds po into the densities instead)
+        if (dev) return fail(GIMIC_B200_EINVAL, "calc_basis with spherical=on needs host output buffers");
+        const size_t ns = (size_t)c->hb.nbf_sph;
+        if (c->f_tmp.ensure((size_t)n * nb * 4 * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (basis vectors)");
+        double *d_b = c->f_tmp.as<double>(), *d_d = d_b + (size_t)n * nb;
+        gb::launch_basis_dense(c->db, c->d_f2user, n, d_r, d_b, d_d, c->stream);
+        CUDA_TRY(cudaGetLastError());
+        std::vector<double> hc((size_t)n * nb * 4);
+        CUDA_TRY(cudaMemcpyAsync(hc.data(), d_b, hc.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        std::vector<double> po[gb::MAX_L + 1];
+        for (int l = 0; l <= gb::MAX_L; ++l) gb::c2s_rows(l, c->hb.turbomole, po[l]);
+        for (long v = 0; v < 4 * n; ++v) {   // v < n: bf rows; then dr rows (3 per point), same order as the cartesian output
+            double *out = v < n ? (bf ? bf + (size_t)v * ns : nullptr) : (dr ? dr + (size_t)(v - n) * ns : nullptr);
+            if (!out) continue;
+            const double *in = hc.data() + (size_t)v * nb;
+            for (const gb::Shell &s : c->hb.shells)
+                for (int q = 0; q < s.nsph; ++q) {
+                    double acc = 0.0;
+                    for (int k = 0; k < s.ncomp; ++k) acc += po[s.l][(size_t)q * s.ncomp + k] * in[s.user_off + k];
+                    out[s.sph_off + q] = acc;
+                }
+        }
+        return 0;
+    }
     double *d_bf = bf, *d_dr = dr;
     if (!dev) {
         if (c->f_tmp.ensure((size_t)n * nb * 4 * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (basis vectors)");
@@ -693,6 +739,14 @@ int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrat
     int rc = gb::gauss_blocks(a, b, npts, order, quadrature, pts, wgts);
     if (rc == -1) return fail(GIMIC_B200_EINVAL, "*** integration did not converge!");
     if (rc) return fail(GIMIC_B200_EINVAL, "gaussgrid(): npts is not dividable by ngp!");
+    return 0;
+}
+
+int gimic_b200_c2s_rows(int l, int turbomole_order, double *po) {
+    if (!po || l < 0 || l > gb::MAX_L) return fail(GIMIC_B200_EINVAL, "bad argument");
+    std::vector<double> rows;
+    gb::c2s_rows(l, turbomole_order != 0, rows);
+    std::copy(rows.begin(), rows.end(), po);
     return 0;
 }
 

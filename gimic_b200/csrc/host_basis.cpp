@@ -74,6 +74,8 @@ void append_shell(HostBasis &b, int atom, int l, const std::vector<double> &xp, 
     Shell s;
     s.atom = atom; s.l = l; s.nprim = (int)xp.size(); s.prim_off = (int)b.alpha.size();
     s.ncomp = (l + 1) * (l + 2) / 2; s.user_off = b.nbf; s.thr = 1e10;
+    s.nsph = 2 * l + 1; s.sph_off = b.nbf_sph;
+    b.nbf_sph += s.nsph;
     b.alpha.insert(b.alpha.end(), xp.begin(), xp.end());
     b.cc.insert(b.cc.end(), c.begin(), c.end());
     b.shells.push_back(s);
@@ -240,6 +242,84 @@ void turbomole_permutation(const HostBasis &b, std::vector<int> &sv) {
         for (const Shell &s : b.shells)
             if (s.l == l)
                 for (int c = 0; c < s.ncomp; ++c) sv.push_back(s.user_off + c);
+}
+
+void turbomole_permutation_sph(const HostBasis &b, std::vector<int> &sv) {
+    sv.clear();
+    sv.reserve(b.nbf_sph);
+    for (int l = 0; l <= MAX_L; ++l)
+        for (const Shell &s : b.shells)
+            if (s.l == l)
+                for (int c = 0; c < s.nsph; ++c) sv.push_back(s.sph_off + c);
+}
+
+// ---- spherical components (cao2sao.f90) ---------------------------------------------------------
+namespace {
+long long ifact(int n) { long long m = 1; for (int i = 2; i <= n; ++i) m *= i; return m; }
+long long ibinom(int a, int b) { return ifact(a) / (ifact(b) * ifact(a - b)); }
+long long igcd(long long a, long long b) { a = a < 0 ? -a : a; b = b < 0 ? -b : b; while (b) { long long t = a % b; a = b; b = t; } return a; }
+}  // namespace
+
+// Real solid harmonic S_lm as a polynomial (Helgaker et al., Molecular Electronic-Structure Theory, eq. 9.1.9):
+//   S_lm ~ sum_{t,u,v} (-1)^(t+v) 4^-t C(l,t) C(l-t,|m|+t) C(t,u) C(|m|,2v') x^(2t+|m|-2(u+v')) y^(2(u+v')) z^(l-2t-|m|),
+// v' = v (m >= 0) or v + 1/2 (m < 0).  Several (u,v) pairs hit the same monomial (same u+v); the reference STORES instead
+// of accumulating (cao2sao.f90:188), so the coefficient of a monomial is the term of the last pair in its loop order,
+// u = min(t, u+v).  Kept bug-compatible (affects only |m| >= 2 rows of g and h shells); the common factor N_lm drops out
+// in the reference's integer renormalisation (cao2sao.f90:201-231), which for l <= 5 yields the row divided by its gcd.
+void c2s_rows(int l, bool turbomole, std::vector<double> &po) {
+    const int nc = (l + 1) * (l + 2) / 2;
+    po.assign((size_t)(2 * l + 1) * nc, 0.0);
+    int cidx[MAX_L + 1][MAX_L + 1];   // (lx, ly) -> component
+    for (int c = 0; c < nc; ++c) { int e[3]; component_exponents(l, turbomole, c, e); cidx[e[0]][e[1]] = c; }
+    const long long scale = 1LL << (2 * (l / 2));   // 4^tmax: makes every coefficient an integer
+    for (int m = -l; m <= l; ++m) {
+        const int am = m < 0 ? -m : m, odd = m < 0 ? 1 : 0;
+        const int vmax = (am - odd) / 2;
+        std::vector<long long> row(nc, 0);
+        for (int t = 0; 2 * t <= l - am; ++t)
+            for (int s = 0; s <= t + vmax; ++s) {   // s = u + v
+                const int u = s < t ? s : t, v = s - u;
+                long long q = ibinom(l, t) * ibinom(l - t, am + t) * ibinom(t, u) * ibinom(am, 2 * v + odd) * (scale >> (2 * t));
+                if ((t + v) & 1) q = -q;
+                const int ly = 2 * s + odd, lx = 2 * t + am - ly;
+                row[cidx[lx][ly]] = q;
+            }
+        long long g = 0;
+        for (long long q : row) g = igcd(g, q);
+        for (int c = 0; c < nc; ++c) po[(size_t)(m + l) * nc + c] = g ? (double)(row[c] / g) : 0.0;
+    }
+}
+
+void density_sph_to_cart(const HostBasis &b, const double *dsph, double *dcart) {
+    const size_t ns = (size_t)b.nbf_sph, nc = (size_t)b.nbf;
+    std::vector<double> po[MAX_L + 1];
+    for (int l = 0; l <= MAX_L; ++l) c2s_rows(l, b.turbomole, po[l]);
+    // half = dsph . po  (ns x nc), then dcart = po^T . half; po is block diagonal per shell
+    std::vector<double> half(ns * nc, 0.0);
+    for (const Shell &s : b.shells) {
+        const std::vector<double> &p = po[s.l];
+        for (int k = 0; k < s.ncomp; ++k) {
+            double *out = &half[ns * (size_t)(s.user_off + k)];
+            for (int q = 0; q < s.nsph; ++q) {
+                const double w = p[(size_t)q * s.ncomp + k];
+                if (w == 0.0) continue;
+                const double *col = dsph + ns * (size_t)(s.sph_off + q);
+                for (size_t a = 0; a < ns; ++a) out[a] += w * col[a];
+            }
+        }
+    }
+    for (size_t nu = 0; nu < nc; ++nu) {
+        const double *hcol = &half[ns * nu];
+        double *out = dcart + nc * nu;
+        for (const Shell &s : b.shells) {
+            const std::vector<double> &p = po[s.l];
+            for (int k = 0; k < s.ncomp; ++k) {
+                double acc = 0.0;
+                for (int q = 0; q < s.nsph; ++q) acc += p[(size_t)q * s.ncomp + k] * hcol[s.sph_off + q];
+                out[s.user_off + k] = acc;
+            }
+        }
+    }
 }
 
 // ---- quadrature nodes ---------------------------------------------------------------------------

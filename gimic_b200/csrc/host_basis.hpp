@@ -16,12 +16,15 @@ constexpr int MAX_SHELLS_PER_ATOM = 99;  // posvec(99), src/libgimic/bfeval.f90:
 struct Shell {            // one segmented contraction, reference order (atom -> file order)
     int atom, l, nprim, prim_off, ncomp;
     int user_off;         // first function index in the reference's AO order
+    int nsph, sph_off;    // spherical=on: 2l+1 components and first index in the reference's SAO order
     double thr;           // screening radius (basis.f90:90-112); 1e10 when screening is off
 };
 
 struct HostBasis {
     bool turbomole = false;              // line 2 of MOL == "TURBOMOLE" (intgrl.f90:47-53)
+    bool spherical = false;              // Advanced.spherical: densities are given over 2l+1 components per shell
     int natoms = 0, nbf = 0, nprim_total = 0, ngto = 0;
+    int nbf_sph = 0;                     // sum of 2l+1 (get_ncgto of the reference when spherical=on)
     std::vector<double> xyz;             // 3*natoms
     std::vector<double> charge;
     std::vector<std::string> symbol;
@@ -50,6 +53,16 @@ bool read_xdens(const std::string &path, int nbf, int nmat, std::vector<double> 
 // Permutation of reorder.f90:54-96: sv[i] = atom-major index of the i-th function in Turbomole's
 // "all s, all p, ..." AO order, so that new(sv[i], sv[j]) = old(i, j).
 void turbomole_permutation(const HostBasis &b, std::vector<int> &sv);
+
+// Same permutation over the spherical components (spherical=on: reorder.f90 runs on the 2l+1 counts).
+void turbomole_permutation_sph(const HostBasis &b, std::vector<int> &sv);
+
+// Cartesian -> spherical projection rows of cao2sao.f90:163-231 for one angular momentum: po[(m+l)*ncart + c],
+// m = -l..l, c in this molecule's cartesian component order.  Integer-valued, not normalised (like the reference).
+void c2s_rows(int l, bool turbomole, std::vector<double> &po);
+// spherical=on: dcart = po^T dsph po, with po = blockdiag(c2s_rows(l_shell)) (bfeval.f90:116-118 applies po to the basis
+// vectors at every point; applying it to the densities once is the same bilinear form).  Both column-major.
+void density_sph_to_cart(const HostBasis &b, const double *dsph, double *dcart);
 
 // Gauss-Legendre / Lobatto nodes in the piecewise-block layout of setup_gauss_data
 // (src/libgimic/gaussint.f90:267-319).  quadrature: 0 = gauss, 1 = lobatto.

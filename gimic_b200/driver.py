@@ -68,14 +68,12 @@ class Driver:
         self.dist, self.rank, self.world = _dist()
         self.out = out if out is not None else sys.stdout
         I = self.inp
-        if I.get("Advanced.spherical"):
-            raise _inp.InputError("spherical=on is not supported (the reference marks it experts-only/buggy, cao2sao.f90:158); "
-                                  "set Advanced.spherical=off")
         self.uhf = bool(I.get("openshell"))
         path = lambda n: n if os.path.isabs(n) else os.path.join(self.workdir, n)
         self.g = Gimic(path(I.get("basis")), path(I.get("xdens")), uhf=self.uhf, giao=I.get("Advanced.GIAO"),
                        diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"),
-                       screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device)
+                       screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device,
+                       spherical=bool(I.get("Advanced.spherical")))
         self.xyz = self.g.atom_coords()
         self.symbols = self._symbols(path(I.get("basis")))
         self.grid = grids.from_input(I, self.xyz, self.workdir)

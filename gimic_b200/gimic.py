@@ -65,7 +65,7 @@ class Grid:
 
 class Gimic:
     def __init__(self, mol=None, xdens=None, *, uhf=False, giao=True, diamag=True, paramag=True, screening=True,
-                 screening_thrs=1e-6, device=-1, _handle=None):
+                 screening_thrs=1e-6, device=-1, spherical=False, _handle=None):
         L = _lib.lib()
         self._h = C.c_void_p()
         self._magnet = np.zeros(3)
@@ -74,24 +74,25 @@ class Gimic:
         if _handle is not None:
             self._h = _handle
         else:
-            o = self._opts(uhf, giao, diamag, paramag, screening, screening_thrs, device)
+            o = self._opts(uhf, giao, diamag, paramag, screening, screening_thrs, device, spherical)
             _lib.check(L.gimic_b200_create(C.byref(self._h), str(mol).encode(), str(xdens).encode(), C.byref(o)))
         self.nbf = L.gimic_b200_nbf(self._h)
         self.natoms = L.gimic_b200_natoms(self._h)
         self.uhf = bool(L.gimic_b200_is_uhf(self._h))
 
     @staticmethod
-    def _opts(uhf, giao, diamag, paramag, screening, screening_thrs, device):
+    def _opts(uhf, giao, diamag, paramag, screening, screening_thrs, device, spherical=False):
         o = _lib.Opts()
         o.uhf, o.giao, o.diamag, o.paramag, o.screening = int(uhf), int(giao), int(diamag), int(paramag), int(screening)
         o.screening_thrs = float(screening_thrs)
         o.device = int(device)
+        o.spherical = int(bool(spherical))   # Advanced.spherical (cao2sao.f90): densities over 2l+1 components per shell
         return o
 
     @classmethod
     def from_arrays(cls, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, dens_alpha, dens_beta=None, *,
                     turbomole_order=False, giao=True, diamag=True, paramag=True, screening=True, screening_thrs=1e-8,
-                    device=-1):
+                    device=-1, spherical=False):
         """dens_*: 4 matrices in the XDENS layout (flat, element (a,b) at a + nbf*b), numpy or CUDA torch tensor."""
         L = _lib.lib()
         coords = _host(coords)
@@ -106,7 +107,7 @@ class Gimic:
             da = _host(dens_alpha).ravel(); db = None if dens_beta is None else _host(dens_beta).ravel()
             pa = C.c_void_p(da.ctypes.data); pb = None if db is None else C.c_void_p(db.ctypes.data)
             keep = (da, db)
-        o = cls._opts(dens_beta is not None, giao, diamag, paramag, screening, screening_thrs, device)
+        o = cls._opts(dens_beta is not None, giao, diamag, paramag, screening, screening_thrs, device, spherical)
         h = C.c_void_p()
         ip = _lib.ip
         _lib.check(L.gimic_b200_create_from_arrays(C.byref(h), coords.shape[0], _dptr(coords), nca.ctypes.data_as(ip),
@@ -312,3 +313,10 @@ def slab(n, rank, world):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def c2s_rows(l, turbomole_order=False):
+    """(2l+1) x ncart(l) cartesian -> spherical projection of cao2sao.f90 (rows m = -l..l), the convention of spherical=on"""
+    out = np.zeros((2 * l + 1, (l + 1) * (l + 2) // 2))
+    _lib.check(_lib.lib().gimic_b200_c2s_rows(int(l), int(turbomole_order), _dptr(out)))
+    return out

@@ -72,7 +72,8 @@ typedef struct {
     int screening;           /* Advanced.screening */
     double screening_thrs;   /* Advanced.screening_thrs; gimic_init uses 1e-6 (globals.f90:56) */
     int device;              /* CUDA device ordinal; -1 = current device */
-    int reserved;
+    int spherical;           /* Advanced.spherical: XDENS / density arrays are over 2l+1 components per shell in the
+                                reference's (non-normalised, m = -l..l) convention of cao2sao.f90; cartesian when 0 */
 } gimic_b200_opts;
 
 /* defaults of gimic_init (gimic_interface.f90:39-51): closed shell, GIAO/diamag/paramag on,
@@ -157,6 +158,11 @@ int gimic_b200_property(gimic_b200_handle h, long n, const double *r, const doub
 /* Gauss-Legendre (quadrature=0) / Lobatto (1) nodes in the block layout of setup_gauss_data
  * (gaussint.f90:267-319); host only. */
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);
+
+/* Cartesian -> spherical projection of cao2sao.f90:163-231 for angular momentum l (0..5), as used when opts.spherical is
+ * set: po[(m + l) * ncart + c], m = -l..l, c in the standard (turbomole_order = 0) or Turbomole cartesian component order;
+ * integer-valued rows, bug-compatible with the reference (see host_basis.cpp); host only. */
+int gimic_b200_c2s_rows(int l, int turbomole_order, double *po);
 
 /* Last-call statistics for benches / roofline accounting. */
 typedef struct {

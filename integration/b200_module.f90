@@ -14,7 +14,7 @@ module b200_module
     type, bind(c) :: b200_opts
         integer(c_int) :: uhf, giao, diamag, paramag, screening
         real(c_double) :: screening_thrs
-        integer(c_int) :: device, reserved
+        integer(c_int) :: device, spherical
     end type
 
     type, bind(c) :: b200_grid          ! gimic_b200_grid: what gridpoint()/get_weight() need of grid_t

@@ -87,6 +87,7 @@ struct Molecule {
 };
 struct Settings {                      // src/libgimic/settings.f90:9-36 (subset used on the path)
     bool is_uhf = false, use_giao = true, use_diamag = true, use_paramag = true;
+    bool use_spherical = false;        // settings.f90:24 (Advanced.spherical)
 };
 
 struct Ctx {
@@ -96,13 +97,17 @@ struct Ctx {
     // dens_t: da(:,:,0:3), db(:,:,0:3), column-major nbf x nbf (dens.f90:13-18)
     std::vector<double> da[4], db[4];
     std::string err;
+    int nccgto = 0;                    // number of cartesian functions (get_nccgto)
+    std::vector<double> c2s[MAX_L + 1];   // c2s_oper(l)%po, (2l+1) x ncart(l) row-major (cao2sao.f90:23,60-70)
 };
 
 // per-thread scratch == jtensor_t + bfeval_t (jtensor.F90:17-28, bfeval.f90:18-29)
 struct Scratch {
     std::vector<double> bf, dr, db, d2, dbop, denbf, pdbf, dendb;
+    std::vector<double> cbf, cdr;      // cartesian vectors before cao2sao (spherical=on only)
     explicit Scratch(const Ctx &c) {
         int n = c.nbf, na = (int)c.mol.atoms.size();
+        if (c.s.use_spherical) { cbf.assign(c.nccgto, 0); cdr.assign(3 * (size_t)c.nccgto, 0); }
         bf.assign(n, 0); dr.assign(3 * n, 0); db.assign(3 * n, 0); d2.assign(9 * n, 0);
         dbop.assign(3 * na, 0); denbf.assign(n, 0); pdbf.assign(n, 0); dendb.assign(n, 0);
     }
@@ -201,11 +206,14 @@ static bool read_intgrl(const std::string &fname, Molecule &mol, std::string &er
 }
 
 // ---- calc_basdim: src/libgimic/basis.f90:216-249 ----------------------------
-static void calc_basdim(Molecule &mol) {
+static void calc_basdim(Molecule &mol, bool spherical) {
     mol.ngto = 0; mol.ncgto = 0;
     for (auto &a : mol.atoms) {
         a.ncgto = 0;
-        for (auto &c : a.ctr) { mol.ngto += c.npf * c.ncomp; mol.ncgto += c.ncomp; a.ncgto += c.ncomp; }
+        for (auto &c : a.ctr) {
+            c.ncomp = spherical ? 2 * c.l + 1 : ncart(c.l);                     // intgrl.f90:134-138
+            mol.ngto += c.npf * c.ncomp; mol.ncgto += c.ncomp; a.ncgto += c.ncomp;
+        }
         a.pos.assign(a.ctr.size(), 1);
         for (size_t k = 1; k < a.ctr.size(); ++k) a.pos[k] = a.pos[k - 1] + a.ctr[k - 1].nccomp;
     }
@@ -246,8 +254,12 @@ static void setup_screening(Atom &a, double thrs) {
 }
 
 // ---- new_basis (after the file is parsed): src/libgimic/basis.f90:29-86 ------
+static void setup_c2soper(Ctx &c);
 static void finish_basis(Ctx &c, double screening /* <=0: off */) {
-    calc_basdim(c.mol);
+    calc_basdim(c.mol, c.s.use_spherical);
+    c.nccgto = 0;
+    for (auto &a : c.mol.atoms) for (auto &ct : a.ctr) c.nccgto += ct.nccomp;
+    if (c.s.use_spherical) setup_c2soper(c);                                      // gimic.F90:151-154
     for (auto &a : c.mol.atoms) for (auto &ct : a.ctr) norm_ctr(ct);
     if (screening <= 0.0) { for (auto &a : c.mol.atoms) for (auto &ct : a.ctr) ct.thrs = 1.e10; }   // :64-68
     else for (auto &a : c.mol.atoms) setup_screening(a, screening);                                   // :74-76
@@ -347,25 +359,129 @@ static inline const int (*get_gto_nlm(const Molecule &mol, int l))[3] {   // gto
     return mol.is_turbomole ? GT_TM[l] : GT_STD[l];
 }
 
+// ---- cao2sao: src/libgimic/cao2sao.f90 (spherical=on; the reference calls this scheme buggy and no
+// test enables it, so there is no golden: parity for spherical=on is UNPINNED) ------------------------------
+static long fact_i(int n) {                                                       // factorial.f90:8-20 (n <= 0 -> 1)
+    if (n <= 0) return 1;
+    long m = n;
+    for (int i = n - 1; i >= 2; --i) m = m * i;
+    return m;
+}
+static long binom_i(int a, int b) { return fact_i(a) / (fact_i(b) * fact_i(a - b)); }   // factorial.f90:36-41 (integer division)
+static int gtomap(const Molecule &mol, int i, int j, int k) {                     // GTO_MAP, gtodefs.f90:155-163 (1-based)
+    int l = i + j + k;
+    const int (*nlm)[3] = get_gto_nlm(mol, l);
+    for (int c = 0; c < ncart(l); ++c) if (nlm[c][0] == i && nlm[c][1] == j && nlm[c][2] == k) return c + 1;
+    return 0;
+}
+static double nslm(int l, int am) {                                              // cao2sao.f90:128-141
+    double q = 1.0 / std::pow(2.0, am);
+    q = q / (double)fact_i(l);
+    double fac = 2.0 * (double)(fact_i(l + am) * fact_i(l - am));
+    if (am == 0) fac = fac / 2.0;
+    return q * std::sqrt(fac);
+}
+static double clmtuv(int l, int t, int u, double v, int am, double vm) {         // cao2sao.f90:143-158
+    double q = std::pow(4.0, t);
+    q = 1.0 / q;
+    if (std::fmod((double)t + v - vm, 2.0) > 0.0) q = -q;
+    long iq = binom_i(l, t) * binom_i(l - t, am + t) * binom_i(t, u) * binom_i(am, (int)(2.0 * v));
+    return q * (double)iq;
+}
+static void renorm(std::vector<double> &xop, int nrow, int ncol) {               // cao2sao.f90:201-231
+    for (int i = 0; i < nrow; ++i) {
+        double *row = &xop[(size_t)i * ncol];
+        double amin = 1.e+10;
+        for (int j = 0; j < ncol; ++j) { double ava = std::fabs(row[j]); if (ava > 0.0 && ava < amin) amin = ava; }
+        for (int j = 0; j < ncol; ++j) row[j] = row[j] / amin;
+        double sim = 1.0;
+        for (int j = 0; j < ncol; ++j) {
+            double ava = std::fabs(row[j]);
+            if (ava > 0.0) {
+                double avb = std::fmod(ava, 1.0);
+                if (avb > 1.e-10) {
+                    ava = 1.0 / avb;
+                    while (std::fmod(ava, 1.0) > 1.e-10) {
+                        avb = std::fmod(ava, 1.0);
+                        if (avb > 1.e-10) ava = ava / avb;
+                    }
+                    if (ava > sim) sim = ava;
+                }
+            }
+        }
+        for (int j = 0; j < ncol; ++j) row[j] = row[j] * sim;
+    }
+}
+static void mkc2sop(const Molecule &mol, int l, std::vector<double> &xop) {      // cao2sao.f90:163-195
+    int nc = ncart(l);
+    xop.assign((size_t)(2 * l + 1) * nc, 0.0);
+    int idx = 0;
+    for (int m = -l; m <= l; ++m) {
+        idx = idx + 1;                                                           // rows run m = -l..l (sphmap is not used, :170-171)
+        int am = std::abs(m);
+        double vm = 0.0;
+        if (m < 0) vm = 0.5;
+        double xnslm = nslm(l, am);
+        for (int t = 0; t <= (l - am) / 2; ++t)
+            for (int u = 0; u <= t; ++u)
+                for (int v = 0; v <= (int)(am * 0.5 - vm); ++v) {
+                    double vr = (double)v + vm;
+                    int i = 2 * t + am - (int)(2.0 * ((double)u + vr));
+                    int j = (int)(2.0 * ((double)u + vr));
+                    int k = l - 2 * t - am;
+                    int n = gtomap(mol, i, j, k);
+                    xop[(size_t)(idx - 1) * nc + (n - 1)] = clmtuv(l, t, u, vr, am, vm) * xnslm;   // '=' not '+=' as the reference (:188)
+                }
+    }
+    renorm(xop, 2 * l + 1, nc);
+}
+static void setup_c2soper(Ctx &c) {                                              // cao2sao.f90:37-70
+    for (int l = 0; l <= MAX_L; ++l) mkc2sop(c.mol, l, c.c2s[l]);
+}
+
 // ---- calc_basis = bfeval + dfdr + mkdbop + dfdb + d2fdrdb: bfeval.f90:61-338 -
 static void calc_basis(const Ctx &c, const double r[3], Scratch &s, bool giao) {
     const Molecule &mol = c.mol;
     int n = c.nbf;
-    std::fill(s.bf.begin(), s.bf.end(), 0.0);                                   // bfeval.f90:97
-    std::fill(s.dr.begin(), s.dr.end(), 0.0);                                   // :311
+    const bool sph = c.s.use_spherical;
+    const int ncc = sph ? c.nccgto : n;                                         // length of the cartesian vectors
+    double *bf = sph ? s.cbf.data() : s.bf.data(), *dr = sph ? s.cdr.data() : s.dr.data();
+    std::fill(bf, bf + ncc, 0.0);                                               // bfeval.f90:97
+    std::fill(dr, dr + 3 * (size_t)ncc, 0.0);                                   // :311
     int idx2 = 0;
     for (auto &a : mol.atoms) {
         double rr[3] = {r[0] - a.coord[0], r[1] - a.coord[1], r[2] - a.coord[2]};
         double r2 = std::sqrt(rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2]);   // filter_screened basis.f90:127
+        int natc = 0;
         for (size_t j = 0; j < a.ctr.size(); ++j) {
             const Contraction &ctr = a.ctr[j];
+            natc += ctr.nccomp;
             if (!(r2 <= ctr.thrs)) continue;                                    // basis.f90:130
             int idx = idx2 + a.pos[j] - 1;
             const int (*nlm)[3] = get_gto_nlm(mol, ctr.l);
-            cgto(rr, ctr, nlm, &s.bf[idx]);                                     // bfeval.f90:107
-            for (int ax = 0; ax < 3; ++ax) dcgto(rr, ctr, nlm, ax, &s.dr[idx + (size_t)n * ax]);   // :324-326
+            cgto(rr, ctr, nlm, &bf[idx]);                                       // bfeval.f90:107
+            for (int ax = 0; ax < 3; ++ax) dcgto(rr, ctr, nlm, ax, &dr[idx + (size_t)ncc * ax]);   // :324-326
         }
-        idx2 += a.ncgto;
+        idx2 += natc;   // cartesian functions of this atom (== a.ncgto when spherical=off; the reference advances by the
+                        // spherical count here, bfeval.f90:109, one of the reasons its spherical=on path is broken)
+    }
+    if (sph) {
+        // sbf = matmul(c2s%po, bf), sdr(:,axis) = matmul(c2s%po, dr(:,axis))  (bfeval.f90:116-118, 330-333;
+        // cao2sao.f90:120-126); po is block diagonal with c2s_oper(l) per contraction (cao2sao.f90:86-99)
+        int ci = 0, si = 0;
+        for (auto &a : mol.atoms)
+            for (auto &ctr : a.ctr) {
+                const std::vector<double> &po = c.c2s[ctr.l];
+                for (int q = 0; q < ctr.ncomp; ++q) {
+                    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    for (int k = 0; k < ctr.nccomp; ++k) {
+                        double w = po[(size_t)q * ctr.nccomp + k];
+                        v0 += w * bf[ci + k]; v1 += w * dr[ci + k]; v2 += w * dr[ci + k + (size_t)ncc]; v3 += w * dr[ci + k + 2 * (size_t)ncc];
+                    }
+                    s.bf[si + q] = v0; s.dr[si + q] = v1; s.dr[si + q + (size_t)n] = v2; s.dr[si + q + 2 * (size_t)n] = v3;
+                }
+                ci += ctr.nccomp; si += ctr.ncomp;
+            }
     }
     if (!giao) return;
     // mkdbop: bfeval.f90:168-189
@@ -757,9 +873,14 @@ static inline void matvec33(const double t[9], const double b[3], double v[3]) {
 // =============================================================================
 extern "C" {
 
+static int g_next_spherical = 0;
+// Advanced.spherical for the NEXT go_create_* call (then reset); keeps the create signatures stable
+void go_next_spherical(int on) { g_next_spherical = on; }
+
 void *go_create_from_files(const char *mol, const char *xdens, int uhf, int use_screening, double screening_thrs,
                            int giao, int diamag, int paramag, char *errbuf, int errlen) {
     Ctx *c = new Ctx();
+    c->s.use_spherical = g_next_spherical != 0; g_next_spherical = 0;
     c->s.is_uhf = uhf != 0; c->s.use_giao = giao != 0; c->s.use_diamag = diamag != 0; c->s.use_paramag = paramag != 0;
     std::string err;
     if (!read_intgrl(mol, c->mol, err)) { if (errbuf) std::snprintf(errbuf, errlen, "%s", err.c_str()); delete c; return nullptr; }
@@ -777,6 +898,7 @@ void *go_create_from_arrays(int natoms, const double *coords, const int *nctr_pe
                             int uhf, double screening_thrs, int giao, int diamag, int paramag,
                             const double *dens_a, const double *dens_b) {
     Ctx *c = new Ctx();
+    c->s.use_spherical = g_next_spherical != 0; g_next_spherical = 0;
     c->s.is_uhf = uhf != 0; c->s.use_giao = giao != 0; c->s.use_diamag = diamag != 0; c->s.use_paramag = paramag != 0;
     c->mol.is_turbomole = turbomole_order != 0;
     c->mol.atoms.assign(natoms, Atom());
@@ -802,6 +924,9 @@ void *go_create_from_arrays(int natoms, const double *coords, const int *nctr_pe
 
 void go_destroy(void *h) { delete (Ctx *)h; }
 int go_nbf(void *h) { return ((Ctx *)h)->nbf; }
+int go_nccgto(void *h) { return ((Ctx *)h)->nccgto; }
+// c2s_oper(l)%po as (2l+1) x ncart(l), row-major
+void go_c2s(void *h, int l, double *out) { Ctx *c = (Ctx *)h; std::vector<double> x; mkc2sop(c->mol, l, x); std::copy(x.begin(), x.end(), out); }
 int go_natoms(void *h) { return (int)((Ctx *)h)->mol.atoms.size(); }
 int go_ngto(void *h) { return ((Ctx *)h)->mol.ngto; }
 int go_is_turbomole(void *h) { return ((Ctx *)h)->mol.is_turbomole ? 1 : 0; }

@@ -39,7 +39,9 @@ def lib():
         L.go_create_from_arrays.argtypes = [C.c_int, dp, ip, ip, ip, dp, dp, C.c_int, C.c_int, C.c_double, C.c_int,
                                             C.c_int, C.c_int, dp, dp]
         L.go_destroy.argtypes = [C.c_void_p]
-        for f in ("go_nbf", "go_natoms", "go_ngto", "go_is_turbomole", "go_nctr", "go_nprim"):
+        L.go_next_spherical.argtypes = [C.c_int]
+        L.go_c2s.argtypes = [C.c_void_p, C.c_int, dp]
+        for f in ("go_nccgto", "go_nbf", "go_natoms", "go_ngto", "go_is_turbomole", "go_nctr", "go_nprim"):
             getattr(L, f).restype = C.c_int
             getattr(L, f).argtypes = [C.c_void_p]
         L.go_atom_coords.argtypes = [C.c_void_p, dp]
@@ -179,8 +181,9 @@ class Oracle:
 
     @classmethod
     def from_files(cls, mol, xdens, uhf=False, screening=True, screening_thrs=1e-8, giao=True, diamag=True,
-                   paramag=True):
+                   paramag=True, spherical=False):
         err = C.create_string_buffer(512)
+        lib().go_next_spherical(int(spherical))
         h = lib().go_create_from_files(str(mol).encode(), str(xdens).encode(), int(uhf), int(screening),
                                        float(screening_thrs), int(giao), int(diamag), int(paramag), err, 512)
         if not h:
@@ -189,7 +192,8 @@ class Oracle:
 
     @classmethod
     def from_arrays(cls, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, dens_a, dens_b=None, turbomole_order=False,
-                    screening_thrs=1e-8, giao=True, diamag=True, paramag=True):
+                    screening_thrs=1e-8, giao=True, diamag=True, paramag=True, spherical=False):
+        lib().go_next_spherical(int(spherical))
         coords = _arr(coords); nca = _arr(nctr_per_atom, np.int32); cl = _arr(ctr_l, np.int32)
         cn = _arr(ctr_npf, np.int32); xp = _arr(xp); cc = _arr(cc); da = _arr(dens_a)
         db = None if dens_b is None else _arr(dens_b)
@@ -203,6 +207,12 @@ class Oracle:
             lib().go_destroy(self.h)
         except Exception:
             pass
+
+    def c2s(self, l):
+        """c2s_oper(l)%po of cao2sao.f90 as a (2l+1) x ncart(l) array in this molecule's component order"""
+        out = np.zeros((2 * l + 1, (l + 1) * (l + 2) // 2))
+        lib().go_c2s(self.h, l, _p(out))
+        return out
 
     def atom_coords(self):
         out = np.zeros((self.natoms, 3))

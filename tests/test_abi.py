@@ -50,6 +50,22 @@ def test_gauss_points_match_oracle(L, npts, order, quadr):
     assert np.allclose(p, po, rtol=0, atol=1e-14) and np.allclose(w, wo, rtol=0, atol=1e-14)
 
 
+@pytest.mark.parametrize("turbomole", [False, True])
+def test_c2s_rows_match_oracle(L, turbomole):
+    """spherical=on projection (cao2sao.f90:163-231): the product's integer construction == the oracle's statement-by-statement
+    restatement (float coefficients + renorm), l = 0..5, both cartesian component orders; includes the reference's
+    store-instead-of-accumulate quirk in the |m| >= 2 rows of g and h shells"""
+    from gimic_b200.gimic import c2s_rows
+    sh = dict(coords=np.zeros((1, 3)), nctr_per_atom=np.array([1], np.int32), ctr_l=np.array([0], np.int32),
+              ctr_npf=np.array([1], np.int32), xp=np.array([1.0]), cc=np.array([1.0]))
+    o = O.Oracle.from_arrays(dens_a=np.zeros(4), turbomole_order=turbomole, **sh)
+    for l in range(6):
+        got, ref = c2s_rows(l, turbomole), o.c2s(l)
+        assert got.shape == ref.shape and np.array_equal(got, np.round(ref)) and np.abs(ref - np.round(ref)).max() < 1e-9, l
+    g4 = c2s_rows(4, False)   # standard order: component 3 is x^2 y^2; S_4,2 ~ (x^2-y^2)(6z^2-x^2-y^2) has no x^2y^2 term
+    assert g4[4 + 2, 3] == -1.0   # ... but the reference stores -1 there (last (u,v) term wins, cao2sao.f90:188)
+
+
 def test_legacy_gauss_entry(L):
     a, b, n, o = C.c_double(0.0), C.c_double(2.0), C.c_int(18), C.c_int(9)
     p = np.zeros(18); w = np.zeros(18)

@@ -337,6 +337,50 @@ def test_high_angular_momentum_shells(gb, turbomole):
     g.close()
 
 
+@pytest.mark.parametrize("turbomole", [False, True])
+def test_spherical_basis_vs_oracle(gb, turbomole):
+    """Advanced.spherical=on (cao2sao.f90): densities over 2l+1 components per shell.  The product folds the projection into
+    the densities once; the oracle projects the basis vectors at every point like the reference.  s..h shells."""
+    rng = np.random.default_rng(23)
+    coords = np.array([[0.0, 0.0, 0.0], [1.9, 0.4, -0.3], [-0.7, 2.1, 0.8]])
+    shells = [(0, [3.1, 0.7], [0.4, 0.7]), (1, [1.3], [1.0]), (2, [0.9, 0.35], [0.6, 0.5]), (3, [0.8], [1.0]), (4, [0.7], [1.0]), (5, [0.6], [1.0])]
+    nat = coords.shape[0]
+    sh = dict(coords=coords, nctr_per_atom=np.full(nat, len(shells), np.int32), ctr_l=np.array([s[0] for s in shells] * nat, np.int32),
+              ctr_npf=np.array([len(s[1]) for s in shells] * nat, np.int32), xp=np.array([x for s in shells for x in s[1]] * nat),
+              cc=np.array([x for s in shells for x in s[2]] * nat))
+    nsph = nat * sum(2 * l + 1 for l, _, _ in shells)
+    da = fixtures.dens_to_colmajor(fixtures.synthetic_density(nsph, seed=3, general_p=True))
+    db = fixtures.dens_to_colmajor(fixtures.synthetic_density(nsph, seed=4, general_p=True))
+    g = gb.Gimic.from_arrays(dens_alpha=da, dens_beta=db, turbomole_order=turbomole, spherical=True, **sh)
+    o = O.Oracle.from_arrays(dens_a=da, dens_b=db, turbomole_order=turbomole, spherical=True, **sh)
+    assert g.nbf == o.nbf == nsph
+    r = rng.uniform(-3, 4, size=(300, 3))
+    bf, dr = g.basis(r[:10])
+    for i in range(10):
+        obf, odr, _, _ = o.calc_basis(r[i])
+        assert_close(bf[i], obf, "spherical bf"); assert_close(dr[i], odr, "spherical dr")
+    for sc in ("alpha", "beta", "total", "spindens"):
+        assert_close(g.jtensors(r, sc), o.ctensor(r, sc), f"spherical {sc} turbomole={turbomole}")
+    g.close()
+
+
+def test_spherical_mol_xdens_files(gb, cases, tmp_path):
+    """spherical=on through the file path: a Turbomole-ordered MOL (c4h4, s p d f shells) with an XDENS over the spherical
+    components; checks the SAO-space Turbomole permutation (reorder.f90:54-96 on 2l+1 counts) and the XDENS reader sizes."""
+    o_cart = O.Oracle.from_files(cases["c4h4"]["mol"], cases["c4h4"]["xdens"], screening_thrs=1e-8)
+    sh = o_cart.export_shells()
+    nsph = int(sum(2 * l + 1 for l in sh["ctr_l"]))
+    rng = np.random.default_rng(9)
+    xd = tmp_path / "XDENS_sph"
+    np.savetxt(xd, rng.uniform(-0.3, 0.3, size=4 * nsph * nsph), fmt="%.12e")
+    g = gb.Gimic(cases["c4h4"]["mol"], str(xd), screening_thrs=1e-8, spherical=True)
+    o = O.Oracle.from_files(cases["c4h4"]["mol"], str(xd), screening_thrs=1e-8, spherical=True)
+    assert g.nbf == o.nbf == nsph
+    r = rng.uniform(-4, 4, size=(200, 3))
+    assert_close(g.jtensors(r), o.ctensor(r), "spherical MOL/XDENS")
+    g.close()
+
+
 def test_general_contraction_mol_file(gb, tmp_path):
     """INTGRL blocks with ncf > 1 (general contractions are split into segmented ones, intgrl.f90:172-216) and
     primitive lines that wrap over several records (list-directed reads)"""

@@ -150,3 +150,30 @@ def test_gauss_points_exactness():
 def test_acid_uses_truncated_third():
     t = np.array([1.0, 0, 0, 0, 2.0, 0, 0, 0, 4.0])
     assert O.acid_field(t[None])[0] == 0.3333333 * (1 + 4 + 9)  # DP33, globals.f90:62
+
+
+@pytest.mark.parametrize("turbomole", [False, True])
+def test_spherical_oracle_equals_cartesian_oracle_with_folded_density(turbomole):
+    """spherical=on (cao2sao.f90, no reference golden -> parity unpinned): projecting Phi and dPhi at every point
+    (bfeval.f90:116-118, 330-333) is the same bilinear form as the cartesian path with D_cart = po^T D_sao po.
+    Pins the oracle's spherical branch to its golden-pinned cartesian branch."""
+    rng = np.random.default_rng(5)
+    coords = np.array([[0.0, 0.0, 0.0], [1.7, -0.4, 0.6]])
+    shells = [(0, [2.1, 0.6], [0.5, 0.6]), (1, [1.1], [1.0]), (2, [0.8], [1.0]), (3, [0.7], [1.0]), (4, [0.65], [1.0]), (5, [0.6], [1.0])]
+    nat = coords.shape[0]
+    sh = dict(coords=coords, nctr_per_atom=np.full(nat, len(shells), np.int32), ctr_l=np.array([s[0] for s in shells] * nat, np.int32),
+              ctr_npf=np.array([len(s[1]) for s in shells] * nat, np.int32), xp=np.array([x for s in shells for x in s[1]] * nat),
+              cc=np.array([x for s in shells for x in s[2]] * nat))
+    nsph = nat * sum(2 * l + 1 for l, _, _ in shells); ncart = nat * sum((l + 1) * (l + 2) // 2 for l, _, _ in shells)
+    dsph = fixtures.synthetic_density(nsph, seed=11, general_p=True)
+    osph = O.Oracle.from_arrays(dens_a=fixtures.dens_to_colmajor(dsph), turbomole_order=turbomole, spherical=True, **sh)
+    assert osph.nbf == nsph
+    po = np.zeros((nsph, ncart)); a = b = 0
+    for _ in range(nat):
+        for l, _, _ in shells:
+            blk = osph.c2s(l); po[a:a + blk.shape[0], b:b + blk.shape[1]] = blk; a += blk.shape[0]; b += blk.shape[1]
+    dcart = np.einsum("am,bac,cn->bmn", po, dsph, po)
+    ocart = O.Oracle.from_arrays(dens_a=fixtures.dens_to_colmajor(dcart), turbomole_order=turbomole, **sh)
+    r = rng.uniform(-2.5, 3.5, size=(40, 3))
+    ts, tc = osph.ctensor(r), ocart.ctensor(r)
+    assert np.abs(ts - tc).max() <= 1e-11 * np.abs(tc).max()
