@@ -742,6 +742,14 @@ int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrat
     return 0;
 }
 
+int gimic_b200_convert_xdens(const char *xdens_text, int nbf, int nmat, const char *xdens_binary) {
+    if (!xdens_text || !xdens_binary || nbf <= 0 || (nmat != 4 && nmat != 8)) return fail(GIMIC_B200_EINVAL, "bad argument");
+    std::vector<double> v; std::string err;
+    if (!gb::read_xdens(xdens_text, nbf, nmat, v, err)) return fail(GIMIC_B200_EIO, err);
+    if (!gb::write_xdens_binary(xdens_binary, nbf, nmat, v.data(), err)) return fail(GIMIC_B200_EIO, err);
+    return 0;
+}
+
 int gimic_b200_c2s_rows(int l, int turbomole_order, double *po) {
     if (!po || l < 0 || l > gb::MAX_L) return fail(GIMIC_B200_EINVAL, "bad argument");
     std::vector<double> rows;

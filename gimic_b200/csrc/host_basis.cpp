@@ -1,10 +1,13 @@
 #include "host_basis.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <charconv>
 #include <fstream>
+#include <thread>
 #include <sstream>
 
 namespace gb {
@@ -211,28 +214,125 @@ void finalize_basis(HostBasis &b, bool use_screening, double screening_thrs) {
     }
 }
 
+// XDENS text: list-directed reals, one per line (dens.f90:129-135).  A 10^4-function molecule has 4e8 of them (3+ GB), so
+// the buffer is cut at line boundaries into one piece per host thread; each piece is counted, then parsed into its slot.
+// Binary cache (this project's extension, written by write_xdens_binary): "GB2XDENS" | int64 nbf | int64 nmat | doubles.
+namespace {
+const char XD_MAGIC[8] = {'G', 'B', '2', 'X', 'D', 'E', 'N', 'S'};
+
+inline bool is_sep(char ch) { return ch == ' ' || ch == '\n' || ch == '\r' || ch == '\t' || ch == ','; }
+
+size_t count_tokens(const char *p, const char *e) {
+    size_t n = 0;
+    while (p < e) {
+        while (p < e && is_sep(*p)) ++p;
+        if (p < e) ++n;
+        while (p < e && !is_sep(*p)) ++p;
+    }
+    return n;
+}
+
+// parses at most `limit` tokens of [p, e) into out; returns the number parsed, or (size_t)-1 on a malformed token
+size_t parse_tokens(const char *p, const char *e, double *out, size_t limit) {
+    size_t n = 0;
+    char tok[80];
+    while (p < e && n < limit) {
+        while (p < e && is_sep(*p)) ++p;
+        if (p >= e) break;
+        const char *q = p;
+        while (q < e && !is_sep(*q)) ++q;
+        size_t len = std::min<size_t>((size_t)(q - p), sizeof(tok) - 1);
+        const char *b = p;
+        if (*b == '+') { ++b; --len; }                       // from_chars takes no leading '+'
+        bool fortran_d = false;
+        for (size_t i = 0; i < len; ++i) { char ch = b[i]; if (ch == 'D' || ch == 'd') { ch = 'e'; fortran_d = true; } tok[i] = ch; }
+        const char *tb = fortran_d ? tok : b;
+        double v;
+        auto res = std::from_chars(tb, tb + len, v);
+        if (res.ec != std::errc() || res.ptr != tb + len) {
+            tok[len] = 0;
+            if (!fortran_d) std::memcpy(tok, b, len);
+            char *endp = nullptr;                               // forms from_chars rejects ("1.-5", ".5+3"): fall back to strtod
+            v = std::strtod(tok, &endp);
+            if (endp == tok) return (size_t)-1;
+        }
+        out[n++] = v;
+        p = q;
+    }
+    return n;
+}
+}  // namespace
+
 bool read_xdens(const std::string &path, int nbf, int nmat, std::vector<double> &out, std::string &err) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) { err = "Density file not found: " + path; return false; }
     std::fseek(f, 0, SEEK_END);
     long sz = std::ftell(f);
     std::fseek(f, 0, SEEK_SET);
+    const size_t want = (size_t)nmat * nbf * nbf;
+    char head[24] = {0};
+    size_t hgot = std::fread(head, 1, sizeof head, f);
+    if (hgot == sizeof head && std::memcmp(head, XD_MAGIC, 8) == 0) {
+        long long hn, hm;
+        std::memcpy(&hn, head + 8, 8); std::memcpy(&hm, head + 16, 8);
+        if (hn != nbf || hm < nmat) { std::fclose(f); err = "binary XDENS cache is for nbf=" + std::to_string(hn) + ", " + std::to_string(hm) + " matrices; expected nbf=" + std::to_string(nbf) + ", " + std::to_string(nmat); return false; }
+        out.resize(want);
+        size_t got = std::fread(out.data(), sizeof(double), want, f);
+        std::fclose(f);
+        if (got != want) { err = "binary XDENS cache truncated: " + path; return false; }
+        return true;
+    }
+    std::fseek(f, 0, SEEK_SET);
     std::vector<char> buf((size_t)sz + 1);
     size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
     std::fclose(f);
-    buf[got] = 0;
-    for (size_t i = 0; i < got; ++i) if (buf[i] == 'D' || buf[i] == 'd') buf[i] = 'e';
-    size_t want = (size_t)nmat * nbf * nbf;
-    out.resize(want);
-    char *p = buf.data(), *end;
-    for (size_t i = 0; i < want; ++i) {
-        double v = std::strtod(p, &end);
-        if (end == p) { err = "XDENS too short: expected " + std::to_string(want) + " values, found " + std::to_string(i); return false; }
-        out[i] = v;
-        p = end;
-        while (*p == ',') ++p;
+    buf[got] = '\n';
+    const char *base = buf.data(), *end = base + got;
+    unsigned nthr = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (got < (1u << 20)) nthr = 1;
+    std::vector<const char *> cut(nthr + 1);
+    cut[0] = base; cut[nthr] = end;
+    for (unsigned t = 1; t < nthr; ++t) {
+        const char *p = base + got / nthr * t;
+        while (p < end && !is_sep(*p)) ++p;   // never inside a token
+        cut[t] = std::max(p, cut[t - 1]);
     }
+    std::vector<size_t> cnt(nthr, 0), off(nthr + 1, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthr; ++t) th.emplace_back([&, t] { cnt[t] = count_tokens(cut[t], cut[t + 1]); });
+        cnt[0] = count_tokens(cut[0], cut[1]);
+        for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < nthr; ++t) off[t + 1] = off[t] + cnt[t];
+    if (off[nthr] < want) { err = "XDENS too short: expected " + std::to_string(want) + " values, found " + std::to_string(off[nthr]); return false; }
+    out.resize(want);
+    std::vector<int> bad(nthr, 0);
+    auto work = [&](unsigned t) {
+        if (off[t] >= want) return;
+        size_t lim = std::min(cnt[t], want - off[t]);
+        if (parse_tokens(cut[t], cut[t + 1], out.data() + off[t], lim) != lim) bad[t] = 1;
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthr; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < nthr; ++t) if (bad[t]) { err = "XDENS: malformed number in " + path; return false; }
     return true;
+}
+
+bool write_xdens_binary(const std::string &path, int nbf, int nmat, const double *vals, std::string &err) {
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) { err = "cannot write " + path; return false; }
+    long long hn = nbf, hm = nmat;
+    size_t want = (size_t)nmat * nbf * nbf;
+    bool ok = std::fwrite(XD_MAGIC, 1, 8, f) == 8 && std::fwrite(&hn, 8, 1, f) == 1 && std::fwrite(&hm, 8, 1, f) == 1 &&
+              std::fwrite(vals, sizeof(double), want, f) == want;
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) err = "short write to " + path;
+    return ok;
 }
 
 void turbomole_permutation(const HostBasis &b, std::vector<int> &sv) {

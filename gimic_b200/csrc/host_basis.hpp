@@ -49,7 +49,10 @@ void component_exponents(int l, bool turbomole, int c, int lmn[3]);
 
 // XDENS: one number per line; nmat = 4 (closed shell) or 8 (UHF) matrices of nbf*nbf values,
 // element (a,b) at a + nbf*b.  Returns them in file order.
+// The text is parsed by all host threads; a file starting with "GB2XDENS" is the binary cache written by
+// write_xdens_binary (header: magic, int64 nbf, int64 nmat; then the same values as raw doubles).
 bool read_xdens(const std::string &path, int nbf, int nmat, std::vector<double> &out, std::string &err);
+bool write_xdens_binary(const std::string &path, int nbf, int nmat, const double *vals, std::string &err);
 // Permutation of reorder.f90:54-96: sv[i] = atom-major index of the i-th function in Turbomole's
 // "all s, all p, ..." AO order, so that new(sv[i], sv[j]) = old(i, j).
 void turbomole_permutation(const HostBasis &b, std::vector<int> &sv);

@@ -320,3 +320,8 @@ def c2s_rows(l, turbomole_order=False):
     out = np.zeros((2 * l + 1, (l + 1) * (l + 2) // 2))
     _lib.check(_lib.lib().gimic_b200_c2s_rows(int(l), int(turbomole_order), _dptr(out)))
     return out
+
+
+def convert_xdens(xdens_text, nbf, xdens_binary, uhf=False):
+    """Parse a text XDENS once (all host threads) and write the binary cache Gimic(mol, xdens_binary) loads directly."""
+    _lib.check(_lib.lib().gimic_b200_convert_xdens(str(xdens_text).encode(), int(nbf), 8 if uhf else 4, str(xdens_binary).encode()))

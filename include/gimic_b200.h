@@ -159,6 +159,12 @@ int gimic_b200_property(gimic_b200_handle h, long n, const double *r, const doub
  * (gaussint.f90:267-319); host only. */
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);
 
+/* XDENS text (dens.f90:129-135: one real per line, 4 or 8 matrices of nbf x nbf) -> binary cache that gimic_b200_create
+ * recognises by its "GB2XDENS" magic (int64 nbf, int64 nmat, raw doubles in file order).  Values are stored exactly as the
+ * text reader parses them, before UHF halving / Turbomole reordering.  nbf = the dimension of the matrices in the file
+ * (spherical count when the file is over spherical components).  Host only. */
+int gimic_b200_convert_xdens(const char *xdens_text, int nbf, int nmat, const char *xdens_binary);
+
 /* Cartesian -> spherical projection of cao2sao.f90:163-231 for angular momentum l (0..5), as used when opts.spherical is
  * set: po[(m + l) * ncart + c], m = -l..l, c in the standard (turbomole_order = 0) or Turbomole cartesian component order;
  * integer-valued rows, bug-compatible with the reference (see host_basis.cpp); host only. */

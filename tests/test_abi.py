@@ -66,6 +66,36 @@ def test_c2s_rows_match_oracle(L, turbomole):
     assert g4[4 + 2, 3] == -1.0   # ... but the reference stores -1 there (last (u,v) term wins, cao2sao.f90:188)
 
 
+def test_xdens_text_parser_and_binary_cache(L, tmp_path):
+    """XDENS reader (dens.f90:129-135 list-directed reals): Fortran D exponents, leading '+', commas, blank lines, CRLF;
+    threaded parse == Python float(); the binary cache holds the parsed values bit for bit; size mismatches are errors"""
+    import gimic_b200
+    nbf = 3
+    vals = np.random.default_rng(0).uniform(-1, 1, 4 * nbf * nbf)
+    toks = []
+    for i, v in enumerate(vals):
+        toks.append(["%.14E" % v, ("%.14E" % v).replace("E", "D"), "  +%.14e" % abs(v), "%.16g," % v, "\n%.17g\r" % v,
+                     ("%.10e" % v).replace("e", "d")][i % 6])
+    (tmp_path / "X").write_text("\n".join(toks) + "\n")
+    gimic_b200.convert_xdens(tmp_path / "X", nbf, tmp_path / "X.bin")
+    raw = (tmp_path / "X.bin").read_bytes()
+    assert raw[:8] == b"GB2XDENS" and np.frombuffer(raw[8:24], np.int64).tolist() == [nbf, 4]
+    ref = np.array([float(t.replace("D", "e").replace("d", "e").replace(",", "").strip()) for t in toks])
+    assert np.array_equal(np.frombuffer(raw[24:], np.float64), ref)
+    # a file large enough to be cut into per-thread pieces
+    n = 260
+    big = np.random.default_rng(1).uniform(-1, 1, 4 * n * n)
+    (tmp_path / "B").write_text("\n".join("%.14E" % v for v in big) + "\n")
+    gimic_b200.convert_xdens(tmp_path / "B", n, tmp_path / "B.bin")
+    got = np.frombuffer((tmp_path / "B.bin").read_bytes()[24:], np.float64)
+    assert np.array_equal(got, np.array([float("%.14E" % v) for v in big]))
+    with pytest.raises(gimic_b200.GimicB200Error, match="too short"):
+        gimic_b200.convert_xdens(tmp_path / "X", nbf + 1, tmp_path / "Y.bin")
+    (tmp_path / "bad").write_text("0.1\nabc\n" * 18)
+    with pytest.raises(gimic_b200.GimicB200Error, match="malformed"):
+        gimic_b200.convert_xdens(tmp_path / "bad", nbf, tmp_path / "Y.bin")
+
+
 def test_legacy_gauss_entry(L):
     a, b, n, o = C.c_double(0.0), C.c_double(2.0), C.c_int(18), C.c_int(9)
     p = np.zeros(18); w = np.zeros(18)

@@ -381,6 +381,19 @@ def test_spherical_mol_xdens_files(gb, cases, tmp_path):
     g.close()
 
 
+def test_binary_xdens_cache_gives_identical_tensors(gb, cases, tmp_path, opensh):
+    """the binary XDENS cache (gimic_b200_convert_xdens) is read back bit for bit: UHF halving and Turbomole reorder included"""
+    g_text, _ = opensh
+    gb.convert_xdens(cases["open_shell"]["xdens"], g_text.nbf, tmp_path / "XDENS.bin", uhf=True)
+    g_bin = gb.Gimic(cases["open_shell"]["mol"], tmp_path / "XDENS.bin", uhf=True, screening_thrs=1e-8)
+    r = np.random.default_rng(2).uniform(-4, 4, size=(257, 3))
+    for sc in ("alpha", "spindens"):
+        assert np.array_equal(g_bin.jtensors(r, sc), g_text.jtensors(r, sc))
+    g_bin.close()
+    with pytest.raises(gb.GimicB200Error, match="binary XDENS cache"):
+        gb.Gimic(cases["benzene_mol"], tmp_path / "XDENS.bin", screening_thrs=1e-8)   # nbf 252 vs a cache for 168
+
+
 def test_general_contraction_mol_file(gb, tmp_path):
     """INTGRL blocks with ncf > 1 (general contractions are split into segmented ones, intgrl.f90:172-216) and
     primitive lines that wrap over several records (list-directed reads)"""
