@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 NSLAB = 8
 
 
-def build_workload(natoms, grid_n):
+def build_workload(natoms, grid_n, geometry="flake", general_p=False):
     from gimic_b200 import synthetic
-    sh, dens, nbf = synthetic.synthetic_case(natoms, "flake", seed=1234)
+    sh, dens, nbf = synthetic.synthetic_case(natoms, geometry, seed=1234, general_p=general_p)
     origin, basv, pts = synthetic.box_grid(sh["coords"], (grid_n, grid_n, grid_n))
     return sh, dens, nbf, origin, basv, pts
 
@@ -141,6 +141,9 @@ def main():
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--cpu-points", type=int, default=192, help="bounded CPU sample per step / for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--geometry", default="flake", choices=["flake", "ring"],
+                    help="flake: compact hexagonal flake (headline); ring: radius-120-bohr ring, mostly empty box (SURVEY 8d ii)")
+    ap.add_argument("--general-p", action="store_true", help="general (not antisymmetric) perturbed densities P_b")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -148,10 +151,12 @@ def main():
     W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     K = max(args.steps, 1)
 
-    cfg = {"workload": f"synthetic hex flake {args.natoms} C-like centres x 36 fn (nbf={args.natoms * 36}), cdens J^B tensors, "
+    geo = "hex flake" if args.geometry == "flake" else "ring (radius 120 bohr)"
+    cfg = {"workload": f"synthetic {geo} {args.natoms} C-like centres x 36 fn (nbf={args.natoms * 36}), cdens J^B tensors, "
                        f"{args.grid}^3 even grid over bbox+8 bohr, step = octant (rank mod 8) = {args.grid ** 3 // NSLAB} points/GPU",
            "nbf": args.natoms * 36, "grid": [args.grid] * 3, "points_per_step_per_gpu": args.grid ** 3 // NSLAB,
            "spincase": "total (closed shell)", "giao": True, "screening_thrs": 1e-8,
+           "densities": "seeded random symmetric D, " + ("general" if args.general_p else "antisymmetric") + " P_x,P_y,P_z",
            "cache": "inputs larger than L2 (contraction operand 7*nbf^2*8 B = %.1f GB, panels streamed)" % (7 * (args.natoms * 36) ** 2 * 8 / 1e9),
            "parallelism": f"grid slabs over {world} GPU(s), no data-path collective"}
 
@@ -159,7 +164,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sh, dens, nbf, origin, basv, pts = build_workload(args.natoms, args.grid)
+        sh, dens, nbf, origin, basv, pts = build_workload(args.natoms, args.grid, args.geometry, args.general_p)
         r = slab_points(origin, basv, pts, 0)
         rng = np.random.default_rng(77)
         sample = np.ascontiguousarray(r[rng.choice(r.shape[0], size=args.cpu_points, replace=False)])
@@ -196,7 +201,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    sh, dens, nbf, origin, basv, pts = build_workload(args.natoms, args.grid)
+    sh, dens, nbf, origin, basv, pts = build_workload(args.natoms, args.grid, args.geometry, args.general_p)
     flat = synthetic.dens_to_colmajor(dens)
     g = gimic_b200.Gimic.from_arrays(dens_alpha=flat, device=local_rank, **sh)
     del flat
@@ -238,9 +243,12 @@ def main():
     tot_h = run_steps(K, host=True)
     barrier()
 
+    # points with at least one unscreened basis function (all others are exact zeros and cost nothing; SURVEY 8d caveat)
+    n_active = torch.tensor([float((t_dev.abs().amax(dim=1) > 0).sum())], dtype=torch.float64, device=dev)
     ms = torch.tensor([tot["ms_total"] / K, tot_h["ms_total"] / K], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_active, op=dist.ReduceOp.SUM)
     ms_step, ms_step_h = float(ms[0]), float(ms[1])
     value = world * n / (ms_step * 1e-3)
     e2e = world * n / (ms_step_h * 1e-3)
@@ -258,6 +266,8 @@ def main():
                 "dense_equivalent_tflops": tot["dense_flops"] / (tot["ms_total"] * 1e-3) / 1e12,
                 "skip_ratio_dense_over_executed": tot["dense_flops"] / tot["executed_flops"] if tot["executed_flops"] else None,
                 "mean_active_functions_per_tile": tot["sum_nact"] / max(tot["n_tiles"], 1),
+                "frac_points_with_active_functions": float(n_active) / (world * n),
+                "active_points_per_s": float(n_active) / (ms_step * 1e-3),
                 "stage_ms_per_step": {k2: tot[k2] / K for k2 in ("ms_sort", "ms_tiles", "ms_basis", "ms_contract", "ms_total")}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
