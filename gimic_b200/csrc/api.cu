@@ -614,48 +614,105 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g,
     return 0;
 }
 
+}  // extern "C" (reopened below)
+
+// Plane / volume quadrature for `ng` grids in ONE tensor pass: the points of all grids (rows j in [jlo_g, jhi_g) of each) are
+// concatenated, run through sort -> tiles -> basis -> contraction together, and reduced per grid.  A 36x36 Gauss plane is only
+// 10 tiles -- a current-profile scan of hundreds of such planes fills the 148 SMs only when batched.
+namespace {
+int integrate_many(gimic_b200_ctx *c, int ng, const gimic_b200_grid *grids, const double *B3s, int spincase, int what,
+                   const int *jlos, const int *jhis, double *out7s) {
+    for (int k = 0; k < 7 * ng; ++k) out7s[k] = 0.0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    // layout of the grid tables: per grid [origin 3 | basv 9 | pts0 | pts1 | pts2 | wgt0]
+    std::vector<size_t> goff(ng + 1, 0), roff(ng + 1, 0), rowoff(ng + 1, 0);
+    for (int g = 0; g < ng; ++g) {
+        const gimic_b200_grid &G = grids[g];
+        const long n0 = G.npts[0], n1 = G.npts[1], n2 = G.npts[2];
+        if (n0 <= 0 || n1 <= 0 || n2 <= 0) return fail(GIMIC_B200_EINVAL, "grid with no points");
+        if (jlos[g] < 0 || jhis[g] > n1 || jlos[g] > jhis[g]) return fail(GIMIC_B200_EINVAL, "row range out of bounds");
+        const size_t nrows = (size_t)(jhis[g] - jlos[g]) * n2;
+        goff[g + 1] = goff[g] + 12 + 2 * n0 + n1 + n2;
+        rowoff[g + 1] = rowoff[g] + nrows;
+        roff[g + 1] = roff[g] + nrows * n0;
+    }
+    const size_t n = roff[ng], nrows_tot = rowoff[ng];
+    if (n == 0) return 0;
+    std::vector<double> h(goff[ng]), wrow(nrows_tot);
+    for (int g = 0; g < ng; ++g) {
+        const gimic_b200_grid &G = grids[g];
+        const long n0 = G.npts[0], n1 = G.npts[1], n2 = G.npts[2];
+        double *q = h.data() + goff[g];
+        for (int i = 0; i < 3; ++i) q[i] = G.origin[i];
+        for (int i = 0; i < 9; ++i) q[3 + i] = G.basv[i];
+        for (long i = 0; i < n0; ++i) { q[12 + i] = G.pts[0][i]; q[12 + n0 + n1 + n2 + i] = G.wgt[0] ? G.wgt[0][i] : 1.0; }
+        for (long i = 0; i < n1; ++i) q[12 + n0 + i] = G.pts[1][i];
+        for (long i = 0; i < n2; ++i) q[12 + n0 + n1 + i] = G.pts[2][i];
+        const int nj = jhis[g] - jlos[g];
+        for (int k = 0; k < n2; ++k) for (int j = 0; j < nj; ++j)
+            wrow[rowoff[g] + (size_t)k * nj + j] = (G.wgt[1] ? G.wgt[1][jlos[g] + j] : 1.0) * (G.wgt[2] ? G.wgt[2][k] : 1.0);
+    }
+    if (c->gridbuf.ensure(h.size() * 8) || c->r_in.ensure(3 * n * 8) || c->tens_tmp.ensure(9 * n * 8) ||
+        c->quad.ensure((8 * nrows_tot + 7 * (size_t)ng + 8) * 8))
+        return fail(GIMIC_B200_ENOMEM, "device allocation failed (integration)");
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(c->gridbuf.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    double *d_r = c->r_in.as<double>();
+    double *d_part = c->quad.as<double>(), *d_wrow = d_part + 7 * nrows_tot, *d_out = d_wrow + nrows_tot;
+    CUDA_TRY(cudaMemcpyAsync(d_wrow, wrow.data(), nrows_tot * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 7 * (size_t)ng * 8, st));
+    for (int g = 0; g < ng; ++g) {   // rows (k, j in [jlo,jhi)), i fastest: the loop nest of integral.f90:113-123
+        const gimic_b200_grid &G = grids[g];
+        const int p1 = G.npts[0], p2 = G.npts[1], p3 = G.npts[2], nj = jhis[g] - jlos[g];
+        const double *d = c->gridbuf.as<double>() + goff[g];
+        for (int k = 0; k < p3 && nj > 0; ++k) {
+            const long lo = ((long)k * p2 + jlos[g]) * p1, hi = ((long)k * p2 + jhis[g]) * p1;
+            gb::launch_grid_points(d, d + 12, d + 12 + p1, d + 12 + p1 + p2, p1, p2, p3, lo, hi, d_r + 3 * (roff[g] + (size_t)k * nj * p1), st);
+            c->stats.launches += 1;
+        }
+    }
+    if (int rc = run_tensors(c, (long)n, d_r, spincase, c->tens_tmp.as<double>(), nullptr)) return rc;
+    for (int g = 0; g < ng; ++g) {
+        const gimic_b200_grid &G = grids[g];
+        const int p1 = G.npts[0], p2 = G.npts[1], nrows = (int)(rowoff[g + 1] - rowoff[g]);
+        if (nrows == 0) continue;
+        gb::QuadArgs q;
+        q.tens = c->tens_tmp.as<double>() + 9 * roff[g]; q.p1 = p1; q.nrows = nrows; q.r = d_r + 3 * roff[g];
+        q.w1 = c->gridbuf.as<double>() + goff[g] + 12 + p1 + p2 + G.npts[2]; q.wrow = d_wrow + rowoff[g];
+        auto gp = [&](int i, int j, int k, double *r) {   // gridpoint, grid.f90:498-511 (0-based here)
+            for (int d = 0; d < 3; ++d) r[d] = G.origin[d] + G.pts[0][i] * G.basv[d] + G.pts[1][j] * G.basv[3 + d] + G.pts[2][k] * G.basv[6 + d];
+        };
+        double v1[3], v2[3];
+        gp(p1 - 1, 0, 0, v1); gp(0, p2 - 1, 0, v2);   // grid_center, grid.f90:529-541
+        for (int d = 0; d < 3; ++d) { q.center[d] = (v1[d] + v2[d]) * 0.5; q.B[d] = B3s[3 * g + d]; q.normal[d] = G.basv[6 + d]; }
+        q.radius = (G.radius > 0.0) ? G.radius : 1e300;
+        q.what = what; q.row_partials = d_part + 7 * rowoff[g]; q.out7 = d_out + 7 * g;
+        gb::launch_quadrature(q, st);
+        c->stats.launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out7s, d_out, 7 * (size_t)ng * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int gimic_b200_integrate(gimic_b200_handle c, const gimic_b200_grid *g, const double *B3, int spincase, int what, int jlo, int jhi,
                          double *out7) {
     if (!c || !g || !B3 || !out7) return fail(GIMIC_B200_EINVAL, "null argument");
-    const int p1 = g->npts[0], p2 = g->npts[1], p3 = g->npts[2];
-    if (jlo < 0 || jhi > p2 || jlo > jhi) return fail(GIMIC_B200_EINVAL, "row range out of bounds");
-    for (int k = 0; k < 7; ++k) out7[k] = 0.0;
-    const int nj = jhi - jlo, nrows = nj * p3;
-    if (nrows == 0) return 0;
-    CUDA_TRY(cudaSetDevice(c->device));
-    reset_stats(c);
-    const double *ob, *p0, *pp1, *pp2, *w0;
-    if (int rc = grid_upload(c, g, &ob, &p0, &pp1, &pp2, &w0)) return rc;
-    const long n = (long)nrows * p1;
-    if (c->r_in.ensure((size_t)3 * n * 8) || c->tens_tmp.ensure((size_t)9 * n * 8) || c->quad.ensure(((size_t)8 * nrows + 8) * 8))
-        return fail(GIMIC_B200_ENOMEM, "device allocation failed (integration)");
-    double *d_r = c->r_in.as<double>();
-    for (int k = 0; k < p3; ++k) {   // rows (k, j in [jlo,jhi)), i fastest: the loop nest of integral.f90:113-123
-        const long lo = ((long)k * p2 + jlo) * p1, hi = ((long)k * p2 + jhi) * p1;
-        gb::launch_grid_points(ob, p0, pp1, pp2, p1, p2, p3, lo, hi, d_r + 3 * (size_t)k * nj * p1, c->stream);
-    }
-    if (int rc = run_tensors(c, n, d_r, spincase, c->tens_tmp.as<double>(), nullptr)) return rc;
-    std::vector<double> wrow(nrows);
-    for (int k = 0; k < p3; ++k) for (int j = 0; j < nj; ++j)
-        wrow[(size_t)k * nj + j] = (g->wgt[1] ? g->wgt[1][jlo + j] : 1.0) * (g->wgt[2] ? g->wgt[2][k] : 1.0);
-    double *d_part = c->quad.as<double>(), *d_wrow = d_part + (size_t)7 * nrows, *d_out = d_wrow + nrows;
-    CUDA_TRY(cudaMemcpyAsync(d_wrow, wrow.data(), (size_t)nrows * 8, cudaMemcpyHostToDevice, c->stream));
-    gb::QuadArgs q;
-    q.tens = c->tens_tmp.as<double>(); q.p1 = p1; q.nrows = nrows; q.r = d_r; q.w1 = w0; q.wrow = d_wrow;
-    auto gp = [&](int i, int j, int k, double *r) {   // gridpoint, grid.f90:498-511 (0-based here)
-        for (int d = 0; d < 3; ++d) r[d] = g->origin[d] + g->pts[0][i] * g->basv[d] + g->pts[1][j] * g->basv[3 + d] + g->pts[2][k] * g->basv[6 + d];
-    };
-    double v1[3], v2[3];
-    gp(p1 - 1, 0, 0, v1); gp(0, p2 - 1, 0, v2);   // grid_center, grid.f90:529-541
-    for (int d = 0; d < 3; ++d) { q.center[d] = (v1[d] + v2[d]) * 0.5; q.B[d] = B3[d]; q.normal[d] = g->basv[6 + d]; }
-    q.radius = (g->radius > 0.0) ? g->radius : 1e300;
-    q.what = what; q.row_partials = d_part; q.out7 = d_out;
-    gb::launch_quadrature(q, c->stream);
-    c->stats.launches += 2 + p3;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out7, d_out, 7 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return integrate_many(c, 1, g, B3, spincase, what, &jlo, &jhi, out7);
+}
+
+int gimic_b200_integrate_batch(gimic_b200_handle c, int ngrids, const gimic_b200_grid *grids, const double *B3s, int spincase,
+                               int what, double *out7s) {
+    if (!c || !grids || !B3s || !out7s || ngrids < 0) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (ngrids == 0) return 0;
+    std::vector<int> lo(ngrids, 0), hi(ngrids);
+    for (int g = 0; g < ngrids; ++g) hi[g] = grids[g].npts[1];
+    return integrate_many(c, ngrids, grids, B3s, spincase, what, lo.data(), hi.data(), out7s);
 }
 
 int gimic_b200_calc_basis(gimic_b200_handle c, long n, const double *r, double *bf, double *dr, int flags) {

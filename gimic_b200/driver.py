@@ -62,7 +62,7 @@ def _dist():
 
 
 class Driver:
-    def __init__(self, inpfile, workdir=None, out=None, device=-1):
+    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None):
         self.workdir = workdir or os.path.dirname(os.path.abspath(inpfile))
         self.inp = _inp.parse_file(inpfile)
         self.dist, self.rank, self.world = _dist()
@@ -70,10 +70,16 @@ class Driver:
         I = self.inp
         self.uhf = bool(I.get("openshell"))
         path = lambda n: n if os.path.isabs(n) else os.path.join(self.workdir, n)
-        self.g = Gimic(path(I.get("basis")), path(I.get("xdens")), uhf=self.uhf, giao=I.get("Advanced.GIAO"),
-                       diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"),
-                       screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device,
-                       spherical=bool(I.get("Advanced.spherical")))
+        # what decides the contents of the device context; inputs that agree on it can share one (run_scan)
+        self.context_key = (os.path.realpath(path(I.get("basis"))), os.path.realpath(path(I.get("xdens"))), self.uhf,
+                            bool(I.get("Advanced.GIAO")), bool(I.get("Advanced.diamag")), bool(I.get("Advanced.paramag")),
+                            bool(I.get("Advanced.screening")), float(I.get("Advanced.screening_thrs")),
+                            bool(I.get("Advanced.spherical")))
+        self.g = gimic if gimic is not None else Gimic(
+            path(I.get("basis")), path(I.get("xdens")), uhf=self.uhf, giao=I.get("Advanced.GIAO"),
+            diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"),
+            screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device,
+            spherical=bool(I.get("Advanced.spherical")))
         self.xyz = self.g.atom_coords()
         self.symbols = self._symbols(path(I.get("basis")))
         self.grid = grids.from_input(I, self.xyz, self.workdir)
@@ -88,7 +94,7 @@ class Driver:
             self.out.write(" " + s + "\n" if s else "\n")
 
     # -------------------------------------------------------------------------------------------------
-    def run(self):
+    def run(self, integral_results=None):
         I = self.inp
         if self.rank == 0:
             writers.write_mol_xyz(os.path.join(self.workdir, "mol.xyz"), self.symbols, self.xyz)
@@ -104,7 +110,7 @@ class Driver:
         if calc == "cdens":
             self.run_cdens()
         elif calc == "integral":
-            self.run_integral()
+            self.run_integral(integral_results)
         elif calc in ("edens", "divj"):
             self.run_scalar(calc)
 
@@ -229,14 +235,21 @@ class Driver:
         if self.uhf:
             self.say(f"*** Integrating {SPIN_LABEL[sc]} density")
 
-    def run_integral(self):
-        """run_integral (gimic.F90:222-261) with the report formats of integral.f90:167-183,306-322,502-510"""
+    def integral_cases(self):
+        I = self.inp
+        cases = ["total"] + (["alpha", "beta", "spindens"] if self.uhf else [])
+        what = 1 | (2 if I.get("Essential.jmod") else 0) | (4 if I.get("Essential.acid") else 0)
+        return cases, what
+
+    def run_integral(self, res=None):
+        """run_integral (gimic.F90:222-261) with the report formats of integral.f90:167-183,306-322,502-510.
+        res: precomputed {spincase: 7 sums} (run_scan evaluates many inputs in one tensor pass)"""
         I = self.inp
         self.say("Integrating current density")
         self.say("*****************************************")
-        cases = ["total"] + (["alpha", "beta", "spindens"] if self.uhf else [])
-        what = 1 | (2 if I.get("Essential.jmod") else 0) | (4 if I.get("Essential.acid") else 0)
-        res = {sc: integrate_distributed(self.g, self.grid, self.magnet, sc, what if sc == "total" else (what & 3)) for sc in cases}
+        cases, what = self.integral_cases()
+        if res is None:
+            res = {sc: integrate_distributed(self.g, self.grid, self.magnet, sc, what if sc == "total" else (what & 3)) for sc in cases}
         self.results = res
         bar = "*" * 60
         bound = self.grid.radius
@@ -299,12 +312,62 @@ class Driver:
             np.savetxt(os.path.join(self.workdir, f"{calc}.txt"), np.column_stack([r, f[calc]]), fmt="%20.12e")
 
 
+def run_scan(infiles, device=-1, outs=None):
+    """A current-profile scan (jobscripts/src/current-profile-local-submit: `gimic gimic.N.inp > gimic.N.out` for hundreds of
+    thin slices, one process and one MOL/XDENS read each) as ONE context and ONE tensor pass per spin case: all inputs that
+    share basis, densities and Advanced settings are integrated by gimic_b200_integrate_batch.  Reports go to
+    <input stem>.out next to each input (or to the streams in `outs`).  Inputs with calc != integral run one by one on the
+    shared context.  Returns the drivers (results in .results)."""
+    drivers, opened = [], []
+    for k, f in enumerate(infiles):
+        if outs is not None:
+            out = outs[k]
+        else:
+            out = open(os.path.splitext(f)[0] + ".out", "w"); opened.append(out)
+        share = next((d.g for d in drivers if d.context_key == _context_key_of(f)), None)
+        drivers.append(Driver(f, out=out, device=device, gimic=share))
+    batch = [d for d in drivers if d.inp.get("calc") == "integral" and not d.inp.get("dryrun") and d.world == 1]
+    pre = {id(d): {} for d in batch}
+    by_ctx = {}
+    for d in batch:
+        by_ctx.setdefault(id(d.g), []).append(d)
+    for ds in by_ctx.values():
+        cases = ds[0].integral_cases()[0]
+        for sc in cases:
+            what = 0
+            for d in ds:
+                what |= d.integral_cases()[1] if sc == "total" else (d.integral_cases()[1] & 3)
+            sums = ds[0].g.integrate_batch([d.grid for d in ds], np.array([d.magnet for d in ds]), sc, what)
+            for d, row in zip(ds, sums):
+                pre[id(d)][sc] = row
+    for d in drivers:
+        d.run(pre.get(id(d)))
+    for o in opened:
+        o.close()
+    return drivers
+
+
+def _context_key_of(inpfile):
+    I = _inp.parse_file(inpfile)
+    wd = os.path.dirname(os.path.abspath(inpfile))
+    path = lambda n: n if os.path.isabs(n) else os.path.join(wd, n)
+    return (os.path.realpath(path(I.get("basis"))), os.path.realpath(path(I.get("xdens"))), bool(I.get("openshell")),
+            bool(I.get("Advanced.GIAO")), bool(I.get("Advanced.diamag")), bool(I.get("Advanced.paramag")),
+            bool(I.get("Advanced.screening")), float(I.get("Advanced.screening_thrs")), bool(I.get("Advanced.spherical")))
+
+
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(prog="gimic_b200", description="GIMIC grid hot path on B200 (cdens / integral / edens / divj)")
-    ap.add_argument("infile", nargs="?", default="gimic.inp")
+    ap.add_argument("infile", nargs="*", default=["gimic.inp"],
+                    help="one gimic.inp, or several (a current-profile scan): they share one device context, integrals are "
+                         "batched into one tensor pass, and each report is written to <input stem>.out")
     ap.add_argument("--workdir", default=None)
     a = ap.parse_args(argv)
+    if len(a.infile) > 1:
+        run_scan(a.infile)
+        return 0
+    a.infile = a.infile[0]
     device = -1
     if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch

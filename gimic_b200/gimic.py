@@ -257,6 +257,24 @@ class Gimic:
                                           int(jlo), int(jhi), _dptr(out)))
         return out
 
+    def integrate_batch(self, grids, Bs, spincase="total", what=3):
+        """The quadrature sums of integrate() for many grids in ONE tensor pass (a current-profile scan: the reference runs one
+        gimic process per slice, jobscripts/src/current-profile-local-submit).  Bs: one field direction per grid or a single
+        one for all.  Returns an (ngrids, 7) array."""
+        ng = len(grids)
+        out = np.zeros((ng, 7))
+        if ng == 0:
+            return out
+        Bs = _host(Bs)
+        Bs = np.ascontiguousarray(np.broadcast_to(Bs.reshape(-1, 3), (ng, 3)))
+        arr = (_lib.GridStruct * ng)()
+        keep = []
+        for i, g in enumerate(grids):
+            st = g.struct(); keep.append(st)
+            arr[i] = st
+        _lib.check(_lib.lib().gimic_b200_integrate_batch(self._h, ng, arr, _dptr(Bs), SPINCASES[spincase], int(what), _dptr(out)))
+        return out
+
     def property(self, r, w, tens, coords, seg_counts=None):
         """Shieldings and magnetizability from a tensor field on a weighted point set (get_property, jfield.f90:584-929).
         seg_counts: points per atom block (nelpts.info, 2nd column); default one segment.  Returns a dict with

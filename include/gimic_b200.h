@@ -146,6 +146,13 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle h, const gimic_b200_grid *g,
 int gimic_b200_integrate(gimic_b200_handle h, const gimic_b200_grid *g, const double *B3, int spincase, int what,
                          int jlo, int jhi, double *out7);
 
+/* The same quadrature for ngrids grids in one tensor pass (all rows of each grid): the points of all planes go through the
+ * sort/tile/basis/contraction pipeline together.  This is what a current-profile scan (jobscripts/src/current-profile-*:
+ * hundreds of gimic.N.inp integrals over thin slices of one plane) should call instead of ngrids separate runs.
+ * B3s: 3 doubles per grid; out7s: 7 doubles per grid, laid out as in gimic_b200_integrate. */
+int gimic_b200_integrate_batch(gimic_b200_handle h, int ngrids, const gimic_b200_grid *grids, const double *B3s, int spincase,
+                               int what, double *out7s);
+
 /* get_property (src/fgimic/jfield.f90:584-929): shielding and magnetizability quadrature of an existing tensor field on a
  * weighted point set (NumGrid: r = gridfile.grd, w = grid_w.grd, coords = coord.au, segments = the per-atom grid blocks of
  * nelpts.info as cumulative end indices).  part[(k*nseg + s)*5 + q]: for nucleus k (k == natoms: magnetizability) and point

@@ -143,3 +143,30 @@ def test_property_mode_report(tmp_path, cases):
     chi = re.search(r"isotropic magnetizability chi =\s+([-\d.]+)", got)
     assert abs(float(chi.group(1)) - tot[-1, 0:3].sum() / 3.0) < 1.1e-6
     assert "atom contributions, total, positive, negative" in got and "in SI units J/T^2" in got
+
+
+def test_current_profile_scan_equals_separate_runs(tmp_path, cases):
+    """jobscripts/src/current-profile-local-submit: one `gimic gimic.N.inp > gimic.N.out` per slice.  `python -m gimic_b200
+    gimic.0.inp gimic.1.inp ...` shares one context and integrates every slice in one tensor pass; each gimic.N.out must be
+    what a separate run prints, and the slices must add up to the undivided plane."""
+    from gimic_b200.driver import Driver, run_scan
+    d = _workdir(tmp_path, cases, "c4h4", "c4h4_integration")
+    base = open(d / "gimic.inp").read()
+    edges = np.linspace(-1.25614, 6.0, 7)
+    names = []
+    for k in range(6):
+        txt = base.replace("width=[-1.25614, 6.0]", f"width=[{edges[k]:.6f}, {edges[k + 1]:.6f}]").replace("grid_points=[30, 30, 0]", "grid_points=[30, 9, 0]")
+        (d / f"gimic.{k}.inp").write_text(txt)
+        names.append(str(d / f"gimic.{k}.inp"))
+    drivers = run_scan(names)
+    total = np.zeros(3)
+    for k, name in enumerate(names):
+        out = io.StringIO()
+        Driver(name, out=out).run()
+        scan_txt = open(os.path.splitext(name)[0] + ".out").read()
+        assert scan_txt == out.getvalue(), k
+        total += drivers[k].results["total"][0:3]
+    assert len({id(dr.g) for dr in drivers}) == 1                       # one shared device context
+    whole = io.StringIO()
+    dw = Driver(str(d / "gimic.inp"), out=whole); dw.run()
+    assert np.allclose(total, dw.results["total"][0:3], rtol=0, atol=5e-5)   # 6 x 9-point Gauss panels vs one 30-point rule

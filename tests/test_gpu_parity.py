@@ -89,6 +89,24 @@ def test_c4h4_integration_golden(gb, c4h4):
     assert np.allclose(parts, out, rtol=1e-12, atol=1e-14)
 
 
+def test_integrate_batch_equals_single_calls(gb, c4h4):
+    """current-profile scan: many thin slices of one bond plane in ONE tensor pass == one integrate() per slice == oracle"""
+    g, o = c4h4
+    xyz = o.atom_coords()
+    edges = np.linspace(-1.0, 6.0, 9)
+    ogs = [O.grid_bond(xyz[0], xyz[1], xyz[2], 1.3, height=[-3.0, 3.0], width=[edges[i], edges[i + 1]], type="gauss", gauss_order=9,
+                       spacing=[0.5, 0.5, 0.5]) for i in range(8)]
+    grids = [to_product_grid(gb, og) for og in ogs]
+    B = np.array([0.0, 0.0, 1.0])
+    batch = g.integrate_batch(grids, B, "total", what=7)
+    assert batch.shape == (8, 7)
+    for i, (og, pg) in enumerate(zip(ogs, grids)):
+        single = g.integrate(pg, B, "total", what=7)
+        assert_close(batch[i], single, f"slice {i} batch vs single")
+        assert_close(batch[i, 0:3], o.integrate(og, B, "total", what=0), f"slice {i} current vs oracle")
+    assert g.integrate_batch([], B).shape == (0, 7)
+
+
 def test_c4h4_radius_mask(gb, c4h4):
     g, o = c4h4
     xyz = o.atom_coords()
