@@ -791,6 +791,25 @@ int gimic_b200_property(gimic_b200_handle c, long n, const double *r, const doub
     return 0;
 }
 
+int gimic_b200_property_integrand(gimic_b200_handle c, long n, const double *r, const double *tens, const double *centre3,
+                                  double *out4, int flags) {
+    if (!c || !r || !tens || !out4) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (n <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    const double *d_r, *d_t;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    if (int rc = stage_in(c, c->tens_tmp, tens, (size_t)9 * n, flags, &d_t)) return rc;
+    double *d_o = out4;
+    if (!dev) { if (c->f_tmp.ensure((size_t)4 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (integrand)"); d_o = c->f_tmp.as<double>(); }
+    const double zero[3] = {0, 0, 0};
+    gb::launch_property_integrand(n, d_r, d_t, centre3 ? 0 : 1, centre3 ? centre3 : zero, d_o, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) CUDA_TRY(cudaMemcpyAsync(out4, d_o, (size_t)4 * n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts) {
     if (!pts || !wgts || npts <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
     int rc = gb::gauss_blocks(a, b, npts, order, quadrature, pts, wgts);

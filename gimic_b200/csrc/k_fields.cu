@@ -185,6 +185,29 @@ void launch_property(long n, const double *r, const double *w, const double *ten
     k_property<<<dim3(nseg, natoms + 1), 256, 0, s>>>(n, r, w, tens, natoms, coords, nseg, seg_end, out);
 }
 
+// Pointwise integrands of get_property for ONE centre (the arrays the reference plots as sigma<k>.vtu, sigma_xx<k>.vtu, ...
+// and intchi*.vtu, jfield.f90:786-808, 915-918): out[4*i + {0,1,2}] = integrand_{xx,yy,zz}, out[4*i + 3] = their sum (pdata).
+// HBM-bound: 96 B in, 32 B out per point.
+__global__ void __launch_bounds__(256) k_property_integrand(long n, const double *__restrict__ r, const double *__restrict__ tens,
+                                                            int chi, double cx, double cy, double cz, double *__restrict__ out) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double dx = r[3 * i] - cx, dy = r[3 * i + 1] - cy, dz = r[3 * i + 2] - cz;
+    const double *t = tens + 9 * i;
+    double f;
+    if (chi) f = 0.5;
+    else f = 1.0e6 * (-1.0 / pow(dx * dx + dy * dy + dz * dz, 1.5) / (137.0359998 * 137.0359998));
+    const double ixx = f * (dy * (-t[2]) - dz * (-t[1]));
+    const double iyy = f * (dz * (-t[3]) - dx * (-t[5]));
+    const double izz = f * (dx * (-t[7]) - dy * (-t[6]));
+    double4 o; o.x = ixx; o.y = iyy; o.z = izz; o.w = ixx + iyy + izz;
+    reinterpret_cast<double4 *>(out)[i] = o;
+}
+void launch_property_integrand(long n, const double *r, const double *tens, int chi, const double *c3, double *out, cudaStream_t s) {
+    if (n <= 0) return;
+    k_property_integrand<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, r, tens, chi, c3[0], c3[1], c3[2], out);
+}
+
 void launch_quadrature(const QuadArgs &q, cudaStream_t s) {
     if (q.nrows <= 0) { cudaMemsetAsync(q.out7, 0, 7 * sizeof(double), s); return; }
     k_quad_rows<<<(q.nrows + 3) / 4, 128, 0, s>>>(q);

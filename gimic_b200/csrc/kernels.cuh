@@ -94,4 +94,6 @@ void launch_quadrature(const QuadArgs &q, cudaStream_t s);
 void launch_property(long n, const double *r, const double *w, const double *tens, int natoms, const double *coords, int nseg,
                      const long *seg_end, double *out, cudaStream_t s);
 
+void launch_property_integrand(long n, const double *r, const double *tens, int chi, const double *c3, double *out, cudaStream_t s);
+
 }  // namespace gb

@@ -197,6 +197,13 @@ class Driver:
             counts = np.array([grd.shape[0]])
         res = self.g.property(grd, wg, tens, coord, counts)
         self.property_results = res
+        # integrand plots (only when the TetGen cell file is there, jfield.f90:677-686, 786-808, 911-919)
+        ele = os.path.join(wd, "grid.1.ele")
+        cells = writers.read_ele(ele) if os.path.exists(ele) else None
+        def plot_integrands(centre, names):
+            f4 = self.g.property_integrand(grd, tens, centre)
+            for col, name in zip((3, 0, 1, 2), names):
+                writers.write_vtu_scalar(os.path.join(wd, name), grd, f4[:, col], cells)
         w(f" npts{grd.shape[0]:12d}\n")
         def table(contrib):
             w("  \n atom contributions, total, positive, negative\n")
@@ -215,6 +222,11 @@ class Driver:
             w(f"{'negative contribution = ':>30s}  {res['sigma_neg'][k]:14.6f}\n")
             w(f"{'sum = ':>30s}  {res['sigma_pos'][k] + res['sigma_neg'][k]:14.6f}\n")
             table(res["sigma_atoms"][k])
+            if cells is not None:
+                names = [f"sigma{k + 1}.vtu"] + [f"sigma_{c}{k + 1}.vtu" for c in ("xx", "yy", "zz")]
+                for nm in names[1:]:
+                    w(f" {nm:<70s}\n")                      # print *, filename  (character(len=70), jfield.f90:606,801)
+                plot_integrands(coord[k], names)
         w(" \n \n")
         for lbl, v in zip(("chi_xx ", "chi_yy ", "chi_zz "), res["chi"]):
             w(f" {lbl:>7s}  {v:14.8f}\n")
@@ -230,6 +242,8 @@ class Driver:
             w(f"{lbl:>30s}  {writers.fortran_e(v * fac, 14, 6)}\n")
         w(" ****************************************************\n")
         table(res["chi_atoms"])
+        if cells is not None:
+            plot_integrands(None, ["intchi.vtu", "intchi_xx.vtu", "intchi_yy.vtu", "intchi_zz.vtu"])
 
     def _note_spin(self, sc):
         if self.uhf:

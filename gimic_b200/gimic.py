@@ -296,6 +296,16 @@ class Gimic:
                     sigma_neg=tot[:nat, 4] / 3.0, sigma_atoms=contrib[:nat], chi=tot[nat, 0:3], chi_iso=tot[nat, 0:3].sum() / 3.0,
                     chi_pos=tot[nat, 3] / 3.0, chi_neg=tot[nat, 4] / 3.0, chi_atoms=contrib[nat])
 
+    def property_integrand(self, r, tens, centre=None):
+        """(n, 4) per-point integrands xx, yy, zz and their sum for one nucleus (shielding, ppm) or centre=None (magnetizability):
+        the fields the reference plots as sigma<k>.vtu / sigma_xx<k>.vtu ... / intchi*.vtu (jfield.f90:786-808, 915-918)"""
+        r = _host(r).reshape(-1, 3); tens = _host(tens).reshape(-1, 9)
+        out = np.zeros((r.shape[0], 4))
+        c3 = None if centre is None else _dptr(_host(centre, (3,)))
+        _lib.check(_lib.lib().gimic_b200_property_integrand(self._h, r.shape[0], C.c_void_p(r.ctypes.data), C.c_void_p(tens.ctypes.data),
+                                                            c3, C.c_void_p(out.ctypes.data), 0))
+        return out
+
     def set_profiling(self, on=True):
         _lib.check(_lib.lib().gimic_b200_set_profiling(self._h, int(on)))
 

@@ -112,10 +112,9 @@ def read_ele(path):
     return cells
 
 
-def write_vtu_vector(path, points, vec, cells):
-    """write_vtk_vector_unstructuredgrid, vtkplot.f90:241-312"""
+def _vtu_write(path, points, name, ncomp, data, cells):
     pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
-    v = np.asarray(vec, dtype=np.float64).reshape(-1, 3)
+    v = np.asarray(data, dtype=np.float64).reshape(pts.shape[0], ncomp)
     nc = cells.shape[0]
     with open(path, "w") as f:
         f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n  <UnstructuredGrid>\n')
@@ -123,7 +122,7 @@ def write_vtu_vector(path, points, vec, cells):
         f.write('        <DataArray type="Float32" NumberOfComponents="3" Format="ascii">\n')
         f.write("".join("        " + "".join(fortran_e(x, 20, 10) for x in p) + "\n" for p in pts))
         f.write('        </DataArray>\n      </Points>\n      <PointData Scalars="scalars">\n')
-        f.write('        <DataArray Name="vectors" type="Float64" NumberOfComponents="3" Format="ascii">\n')
+        f.write(f'        <DataArray Name="{name}" type="Float64" NumberOfComponents="{ncomp}" Format="ascii">\n')
         f.write("".join("        " + "".join(fortran_e(x, 20, 10) for x in p) + "\n" for p in v))
         f.write('        </DataArray>\n      </PointData>\n      <Cells>\n        <DataArray type="Int32" Name="connectivity" Format="ascii">\n')
         f.write("".join("        " + "".join(f"{int(i) - 1:10d}" for i in c) + "\n" for c in cells))
@@ -134,6 +133,16 @@ def write_vtu_vector(path, points, vec, cells):
         f.write('        </DataArray>\n      </Cells>\n      <CellData Scalars="foo">\n        ')
         f.write("".join(" 0.0" for _ in range(nc)) + "\n")
         f.write("      </CellData>\n    </Piece>\n  </UnstructuredGrid>\n</VTKFile>\n")
+
+
+def write_vtu_vector(path, points, vec, cells):
+    """write_vtk_vector_unstructuredgrid, vtkplot.f90:241-312"""
+    _vtu_write(path, points, "vectors", 3, vec, cells)
+
+
+def write_vtu_scalar(path, points, values, cells):
+    """write_vtk_scalar_unstructuredgrid, vtkplot.f90:318-391"""
+    _vtu_write(path, points, "scalars", 1, values, cells)
 
 
 def write_jmod_txt(path, grid, vec, regular=True):

@@ -162,6 +162,12 @@ int gimic_b200_integrate_batch(gimic_b200_handle h, int ngrids, const gimic_b200
 int gimic_b200_property(gimic_b200_handle h, long n, const double *r, const double *w, const double *tens, int natoms,
                         const double *coords, int nseg, const long *seg_end, double *part, int flags);
 
+/* The per-point integrands of get_property for one centre -- what the reference writes as sigma<k>.vtu, sigma_xx<k>.vtu, ... and
+ * intchi*.vtu (jfield.f90:786-808, 915-918): out4[4*i + 0..2] = integrand_xx,yy,zz at point i, out4[4*i + 3] = their sum.
+ * centre3 = nucleus position (shielding, ppm) or NULL (magnetizability, au). */
+int gimic_b200_property_integrand(gimic_b200_handle h, long n, const double *r, const double *tens, const double *centre3,
+                                  double *out4, int flags);
+
 /* Gauss-Legendre (quadrature=0) / Lobatto (1) nodes in the block layout of setup_gauss_data
  * (gaussint.f90:267-319); host only. */
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);
