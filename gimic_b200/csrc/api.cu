@@ -56,11 +56,11 @@ struct gimic_b200_ctx {
     int *d_f2user = nullptr;
     double *d_dens[2] = {nullptr, nullptr};   // dens_t%da / %db in the XDENS layout
     double *d_op[4] = {nullptr, nullptr, nullptr, nullptr};   // contraction operands per spin case
-    int nq = 7, ldb = 0; long long plane_stride = 0;
+    int nq = gb::NQ, ldb = 0; long long plane_stride = 0;
     double bbox_lo[3] = {0, 0, 0}; double inv_cell = 1.0;
     size_t pool_max_bytes = (size_t)8 << 30;
     // workspaces
-    Buf keys0, keys1, vals0, vals1, sorttmp, rs, geo, nraw, segs, tiles, panel, fidx, misc, r_in, tens_tmp, f_tmp, shift, jv6, gridbuf, quad;
+    Buf keys0, keys1, vals0, vals1, sorttmp, rs, geo, nraw, segs, tiles, panel, fidx, atab, misc, r_in, tens_tmp, f_tmp, shift, jv6, gridbuf, quad;
     gb::TileInfo *h_info = nullptr; size_t h_info_cap = 0;
     gb::TileSeg *h_segs = nullptr;
     double split_radius = 2.5;   // bohr: tiles wider than this are cut at their largest consecutive gap if that shrinks them
@@ -77,7 +77,7 @@ struct gimic_b200_ctx {
         for (void *p : owned) cudaFree(p);
         for (int i = 0; i < 2; ++i) if (d_dens[i]) cudaFree(d_dens[i]);
         for (int i = 0; i < 4; ++i) if (d_op[i]) cudaFree(d_op[i]);
-        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &segs, &tiles, &panel, &fidx, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
+        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &segs, &tiles, &panel, &fidx, &atab, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
         if (h_info) cudaFreeHost(h_info);
         if (h_segs) cudaFreeHost(h_segs);
         if (h_tiles) cudaFreeHost(h_tiles);
@@ -130,6 +130,7 @@ int build_device_basis(gimic_b200_ctx *c) {
     }
     gb::DevBasis &d = c->db;
     d.natoms = hb.natoms; d.nbf = hb.nbf; d.nshell = ns; d.turbomole = hb.turbomole ? 1 : 0;
+    d.slot_align = c->opts.giao ? gb::SLOT_ALIGN_GIAO : 1;
     if (int rc = upload(c, hb.xyz, &d.atom_xyz)) return rc;
     if (int rc = upload(c, maxthr, &d.atom_maxthr)) return rc;
     if (int rc = upload(c, atom_shell_off, &d.atom_shell_off)) return rc;
@@ -201,7 +202,7 @@ int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
         if (spincase == GIMIC_B200_BETA) A = c->d_dens[1];
         if (spincase == GIMIC_B200_TOTAL) { Bm = c->d_dens[1]; sg = 1.0; }       // T_alpha + T_beta (jtensor.F90:86-88), by linearity in D, P
         if (spincase == GIMIC_B200_SPINDENS) { Bm = c->d_dens[1]; sg = -1.0; }   // T_alpha - T_beta (jtensor.F90:97-99)
-        gb::launch_build_operand((double *)p, nbf, c->ldb, c->plane_stride, A, Bm, sg, c->d_f2user, c->db.fR, c->opts.giao != 0, c->stream);
+        gb::launch_build_operand((double *)p, nbf, c->ldb, c->plane_stride, A, Bm, sg, c->d_f2user, c->stream);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->d_op[spincase] = (double *)p;
@@ -229,7 +230,7 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
         }
         dens_a = cart[0].data(); dens_b = c->opts.uhf ? cart[1].data() : nullptr; dens_on_device = false;
     }
-    c->nq = c->opts.giao ? gb::NQ_GIAO : gb::NQ_NOGIAO;
+    c->nq = gb::NQ;
     c->ldb = c->hb.nbf;
     c->plane_stride = 2LL * c->hb.nbf * c->ldb;          // doubles per pair-plane [nbf][ldb][2]
     for (int sp = 0; sp < (c->opts.uhf ? 2 : 1); ++sp) {
@@ -319,19 +320,22 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     }
     size_t pool_doubles = std::max(max_tile, std::min(total, c->pool_max_bytes / 8));
     std::vector<int> batch_start(1, 0);
-    size_t off = 0, foff = 0, fidx_max = 0;
+    size_t off = 0, foff = 0, fidx_max = 0, aoff = 0, atab_max = 0;
     double sum_nact = 0, flops = 0;
+    const bool giao = c->opts.giao != 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc &td = c->h_tiles[t];
-        td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.pad_ = 0;
+        td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.nruns = c->h_info[t].natom;
         td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 7) / 8 * 8;
         size_t d = (size_t)4 * td.nact * LDP;
-        if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); off = 0; foff = 0; }
-        td.panel_off = (long long)off; td.fidx_off = (long long)foff;
-        off += d; foff += td.nact;
-        sum_nact += td.nact; flops += 2.0 * MT * c->nq * (double)td.nact * td.nact;   // K and N both run over nact slots (multiples of 8)
+        if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff); off = 0; foff = 0; aoff = 0; }
+        td.panel_off = (long long)off; td.fidx_off = (long long)foff; td.atab_off = (long long)aoff;
+        off += d; foff += td.nact; aoff += td.nruns;
+        sum_nact += td.nact;
+        flops += 2.0 * MT * c->nq * (double)td.nact * td.nact;   // DMMA: K and N both run over nact slots (multiples of 8)
+        if (giao) flops += 2.0 * MT * 3.0 * (double)td.nact * td.nruns;   // GIAO taps: 3 DFMA per accumulator element per active atom
     }
-    fidx_max = std::max(fidx_max, foff);
+    fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff);
     batch_start.push_back(ntiles);
     // inside a batch the contraction kernel pulls tiles from an atomic counter: longest first (cost ~ nact^2)
     static const int sched = [] { const char *e = std::getenv("GIMIC_B200_SCHED"); return e ? std::atoi(e) : 0; }();
@@ -348,7 +352,8 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
             }
         }                          // sched == 1: plain Hilbert order
     }
-    if (c->panel.ensure(std::max<size_t>(pool_doubles, 2) * 8) || c->fidx.ensure(std::max<size_t>(fidx_max, 1) * 4))
+    if (c->panel.ensure(std::max<size_t>(pool_doubles, 2) * 8) || c->fidx.ensure(std::max<size_t>(fidx_max, 1) * 4) ||
+        c->atab.ensure(std::max<size_t>(atab_max, 1) * sizeof(TileAtom)))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
     CUDA_TRY(cudaMemcpyAsync(c->tiles.p, c->h_tiles, (size_t)ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
 
@@ -358,15 +363,17 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         const int t0 = batch_start[b], nb = batch_start[b + 1] - t0;
         if (nb <= 0) continue;
         if (prof) cudaEventRecord(c->evpool[3 * b], st);
-        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(), st);
+        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(),
+                     giao ? c->atab.as<TileAtom>() : nullptr, st);
         if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
         JtensorArgs a;
         a.tiles = c->tiles.as<TileDesc>() + t0; a.ntiles = nb; a.counter = c->misc.as<int>();
-        a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>();
+        a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>(); a.atab_pool = c->atab.as<TileAtom>(); a.geo = c->geo.as<TileGeo>();
         a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
         a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = perm; a.tens = d_tens; a.edens = d_edens;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
+        { static const int dbg = [] { const char *e = std::getenv("GIMIC_B200_DBG"); return e ? std::atoi(e) : 0; }(); a.dbg = dbg; }
         launch_jtensor(a, c->opts.giao != 0, c->nsm, st);
         CUDA_TRY(cudaGetLastError());
         c->stats.launches += 2;

@@ -3,24 +3,31 @@
 // Replaces `contract` of the reference (src/libgimic/jtensor.F90:148-237: 7 nbf x nbf GEMVs + 28 dot
 // products per point) by one FP64 tensor-core GEMM per tile with a fused epilogue:
 //
-//   X_q[p, nu] = sum_mu Phi[p, mu] * B_q[mu, nu],   q = 0..6,  mu/nu over the tile's ACTIVE functions
-//     B_0 = D,  B_1..3 = P_x,P_y,P_z,  B_4..6[mu,nu] = D[mu,nu] (R_nu - R_mu)_d      (d = x,y,z)
+//   X_q[p, nu] = sum_mu Phi[p, mu] * B_q[mu, nu],   q = 0..3,  mu/nu over the tile's ACTIVE functions
+//     B_0 = D,  B_1..3 = P_x,P_y,P_z
+//   Y_d[p, nu] = sum_mu Phi[p, mu] D[mu, nu] (R_nu - R_mu)_d                          (d = x,y,z; GIAO only)
 //
-// and, with e_0 = Phi, e_m = dPhi/dr_m, y = r x (X_4, X_5, X_6):
+// and, with e_0 = Phi, e_m = dPhi/dr_m, y = r x (Y_x, Y_y, Y_z):
 //
 //   Tp(m,b) = sum_nu (X_{1+b} + y_b)[nu] e_m[nu]          (ppd + prsp1 + the d_m part of prsp2)
 //   V_d     = sum_nu R_{nu,d} X_0[nu] e_0[nu]             (the (e_m x R) Phi part of prsp2, bfeval.f90:228-240)
 //   rho     = sum_nu X_0[nu] e_0[nu]                      (diapam, jtensor.F90:168)
 //   ct(m,b) = 1/2 [Tp(m,b) + sum_d eps(b,m,d) V_d]  +  eps(m,b,c) rho r_c / 2      (jtensor.F90:209-235)
 //
-// The identity behind B_4..6 (gauge-difference form of dendb/d2fvec, bfeval.f90:168-246):
+// The identity behind Y (gauge-difference form of dendb/d2fvec, bfeval.f90:168-246):
 //   -sum_nu dendb_b[nu] e_m[nu] + sum_nu denbf[nu] e_m[nu] g_{A(nu),b}
 //        = sum_nu e_m[nu] sum_{c,d} eps(b,c,d) r_c sum_mu Phi_mu D[mu,nu] (R_{nu,d} - R_{mu,d}).
+// Y costs NO extra GEMM planes: R_mu is constant over the functions of one atom and the K slots are grouped by atom
+// (each atom's run padded to whole k4 steps), so with C_A[nu] = the running D accumulator after atom A's last K step
+//   Y_d = (R_nu - c)_d X_0 - Z_d,   Z_d = sum_A (R_A - c)_d (C_A - C_{A-1}) = sum_{A<n} C_A (R_A - R_{A+1})_d + C_n (R_n - c)_d
+// (Abel summation; c = tile centre, all differences are O(screening radius) so nothing cancels for molecules far from the
+// origin).  The consumer "taps" the D accumulator at every atom boundary: 3 DFMA per accumulator element instead of the
+// 3 x K_A MMA columns the planes D(R_nu - R_mu)_d used to cost.  7 GEMM planes -> 4.
 // Screened functions are exact zeros in the reference, so restricting mu, nu to the tile's active
 // set changes nothing but the order of summation.
 //
-// Mapping: 8 consumer warps + 1 producer warp; consumer warp w owns rows 16w..16w+15 of the tile and all 7x2 n8 tiles of
-// the current 16-wide nu chunk (56 fp64 accumulators / thread), so the per-point epilogue sums stay
+// Mapping: 8 consumer warps + 4 producer warps; consumer warp w owns rows 16w..16w+15 of the tile and all 4x2 n8 tiles of
+// the current 16-wide nu chunk (32 + 24 fp64 accumulators / thread), so the per-point epilogue sums stay
 // in registers for the whole tile and need only a 4-lane shuffle reduction at the end.
 // mma.sync.m16n8k4.f64 lowers to 2 DMMA.8x8x4 on sm_100a (there is no FP64 tcgen05 kind).
 #include "kernels.cuh"
@@ -71,8 +78,9 @@ constexpr int NCONSUMER_WARPS = 8;
 constexpr int NPRODUCER_WARPS = 4;   // one warpgroup, so that setmaxnreg can hand its registers to the consumers
 constexpr int NTHREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
 constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 = 64512 <= 65536
+constexpr int ATAB_MAX = 1024;      // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
+constexpr int KMASK_WORDS = 512;    // atom-end bits for up to 16384 K steps = 65536 slots
 
-template <int NQ>
 struct Smem {
     static constexpr int A_DOUBLES = BK * LDP;
     static constexpr int NPP = (NQ + 1) / 2;                 // pair-planes: (q0,q1) (q2,q3) (q4,q5) (q6,-)
@@ -80,7 +88,9 @@ struct Smem {
     static constexpr int B_DOUBLES = NPP * PP_DOUBLES;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
     static constexpr size_t ROW_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;        // per-row epilogue sums + point coordinates
-    static constexpr size_t BAR_OFF = ROW_OFF + (size_t)MT * ROWLD * 8;
+    static constexpr size_t ATAB_OFF = ROW_OFF + (size_t)(MT * ROWLD + 4) * 8;   // (+4: tile centre)          // GIAO tap weights of the tile's atoms [ATAB_MAX][3]
+    static constexpr size_t KMASK_OFF = ATAB_OFF + (size_t)ATAB_MAX * 3 * 8;      // bit k4: K step k4 is the last of an atom
+    static constexpr size_t BAR_OFF = KMASK_OFF + (size_t)KMASK_WORDS * 4;
     static constexpr size_t BYTES = BAR_OFF + 2 * STAGES * 8 + 16;
 };
 
@@ -94,8 +104,7 @@ __device__ __forceinline__ int next_tile(const JtensorArgs &a, int *s_tile) {
 
 template <bool GIAO>
 __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_base, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
-    constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
-    using SM = Smem<NQ>;
+    using SM = Smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t git = 0;
     for (;;) {
@@ -143,9 +152,9 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
 }
 
 template <bool GIAO>
-__device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double *s_stage, double *s_rows, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
-    constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
-    using SM = Smem<NQ>;
+__device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double *s_stage, double *s_rows, double *s_atab, uint32_t *s_kmask,
+                                              uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
+    using SM = Smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = warp * 16;
@@ -181,8 +190,32 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
             for (int i = 0; i < 13; ++i) rs[i] = 0.0;
             rs[13] = a.rsx[p]; rs[14] = a.rsy[p]; rs[15] = a.rsz[p];
         }
+        if (GIAO && threadIdx.x == 0) {   // tile centre, same expression as k_basis; read in the epilogue (after the bar.sync below)
+            const TileGeo tg = a.geo[td.geo];
+            s_rows[MT * ROWLD] = 0.5 * (tg.lox + tg.hix); s_rows[MT * ROWLD + 1] = 0.5 * (tg.loy + tg.hiy); s_rows[MT * ROWLD + 2] = 0.5 * (tg.loz + tg.hiz);
+        }
         __syncwarp();
         double acc[NQ][2][4];
+        double zac[3][2][4];                                        // Z_d (GIAO taps)
+        const int nruns = td.nruns;
+        const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
+        double curx = 0, cury = 0, curz = 0;
+        int ia = 0;
+        if (GIAO) {
+            // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
+            const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
+            const int ctid = threadIdx.x, nwords = (nact / 4 + 31) / 32;
+            for (int w = ctid; w < nwords; w += NCONSUMER_WARPS * 32) s_kmask[w] = 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+            for (int r = ctid; r < nruns; r += NCONSUMER_WARPS * 32) {
+                const double2 t0 = __ldg(atab + 2 * r), t1 = __ldg(atab + 2 * r + 1);
+                if (r < ATAB_MAX) { s_atab[3 * r] = t0.x; s_atab[3 * r + 1] = t0.y; s_atab[3 * r + 2] = t1.x; }
+                const int e = __double2loint(t1.y) - 1;
+                atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+            if (nruns > ATAB_MAX) { atd = reinterpret_cast<const double *>(atab); astr = 4; }
+        }
         int kc = 0, vc = 0;
         for (uint32_t it = 0; it < NIT; ++it) {
             const uint32_t gi = git + it, s = gi % STAGES, ph = (gi / STAGES) & 1;
@@ -193,7 +226,19 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
+                if (GIAO) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zac[d][h][i] = 0.0;
+                    ia = 0;
+                    curx = atd[0]; cury = atd[1]; curz = atd[2];
+                }
             }
+            const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
+            const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
             const int nks = min(BK, nact - kc * BK) / 4;
             const bool h1 = vc * NV + 8 < nact;                     // second n8 tile of this chunk holds real slots
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
@@ -212,8 +257,23 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                         if (h == 1 && !h1) continue;
                         const double2 b = pb[pp * (SM::PP_DOUBLES / 2) + h * 8];
                         mma_16x8x4_f64(acc[2 * pp][h], a0, a1, b.x);
-                        if (2 * pp + 1 < NQ) mma_16x8x4_f64(acc[2 * pp + 1][h], a0, a1, b.y);
+                        mma_16x8x4_f64(acc[2 * pp + 1][h], a0, a1, b.y);
                     }
+                if (GIAO && ((m8 >> ks) & 1u)) {
+                    // last K step of an atom: Z_d += C_A * (R_A - R_next)_d  (see the header; C_A = acc[0] right now)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double cv = acc[0][h][i];
+                            zac[0][h][i] = fma(curx, cv, zac[0][h][i]);
+                            zac[1][h][i] = fma(cury, cv, zac[1][h][i]);
+                            zac[2][h][i] = fma(curz, cv, zac[2][h][i]);
+                        }
+                    ia = min(ia + 1, nruns - 1);
+                    const double *nx = atd + astr * ia;
+                    curx = nx[0]; cury = nx[1]; curz = nx[2];
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
@@ -245,7 +305,10 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                             double zx = acc[1][h][ci], zy = acc[2][h][ci], zz = acc[3][h][ci];
                             if (GIAO) {
                                 e[9] += Rx * t0; e[10] += Ry * t0; e[11] += Rz * t0;
-                                const double yx = acc[NQ - 3][h][ci], yy = acc[NQ - 2][h][ci], yz = acc[NQ - 1][h][ci];
+                                const double x0 = acc[0][h][ci];
+                                const double cenx = s_rows[MT * ROWLD], ceny = s_rows[MT * ROWLD + 1], cenz = s_rows[MT * ROWLD + 2];
+                                const double yx = (Rx - cenx) * x0 - zac[0][h][ci], yy = (Ry - ceny) * x0 - zac[1][h][ci],
+                                             yz = (Rz - cenz) * x0 - zac[2][h][ci];
                                 zx += py * yz - pz * yy;   // (r x Y')_x
                                 zy += pz * yx - px * yz;
                                 zz += px * yy - py * yx;
@@ -311,8 +374,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
 // setmaxnreg can give the consumers 232 registers (ptxas budgets each path by the setmaxnreg that dominates it).
 template <bool GIAO>
 __global__ void __launch_bounds__(NTHREADS, 1) k_jtensor(JtensorArgs a) {
-    constexpr int NQ = GIAO ? NQ_GIAO : NQ_NOGIAO;
-    using SM = Smem<NQ>;
+    using SM = Smem;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_stage = reinterpret_cast<double *>(smem_raw);
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -328,51 +390,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_jtensor(JtensorArgs a) {
         producer_role<GIAO>(a, s_base, bar_full, bar_empty, s_tile);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-        consumer_role<GIAO>(a, s_stage, reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), bar_full, bar_empty, s_tile);
+        consumer_role<GIAO>(a, s_stage, reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF),
+                            reinterpret_cast<uint32_t *>(smem_raw + SM::KMASK_OFF), bar_full, bar_empty, s_tile);
     }
 }
 
-size_t jtensor_smem_bytes(bool giao) { return giao ? Smem<NQ_GIAO>::BYTES : Smem<NQ_NOGIAO>::BYTES; }
+size_t jtensor_smem_bytes() { return Smem::BYTES; }
 
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;
     // per-device function attribute (a process may hold contexts on several GPUs): cheap enough to set on every launch
-    if (giao) cudaFuncSetAttribute(k_jtensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<NQ_GIAO>::BYTES);
-    else cudaFuncSetAttribute(k_jtensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<NQ_NOGIAO>::BYTES);
+    if (giao) cudaFuncSetAttribute(k_jtensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::BYTES);
+    else cudaFuncSetAttribute(k_jtensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::BYTES);
     int grid = a.ntiles < nsm ? a.ntiles : nsm;
-    if (giao) k_jtensor<true><<<grid, NTHREADS, Smem<NQ_GIAO>::BYTES, s>>>(a);
-    else k_jtensor<false><<<grid, NTHREADS, Smem<NQ_NOGIAO>::BYTES, s>>>(a);
+    if (giao) k_jtensor<true><<<grid, NTHREADS, Smem::BYTES, s>>>(a);
+    else k_jtensor<false><<<grid, NTHREADS, Smem::BYTES, s>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Contraction operands in the internal (per-atom radius-sorted) function order as PAIR-PLANES, row-major [mu][nu][2]:
-// pair 0 = (D, Px), pair 1 = (Py, Pz), pair 2 = (D(Rv-Ru)_x, D(Rv-Ru)_y), pair 3 = (D(Rv-Ru)_z, 0); optionally alpha +/- beta.
+// pair 0 = (D, Px), pair 1 = (Py, Pz); optionally alpha +/- beta.
 // One (mu,nu) element of a pair is a 16-byte unit: one cp.async.cg per gather, and runs of >=4 nu fill whole 64 B HBM atoms.
 // src is the dens.f90 layout: element (a,b) at a + nbf*b.
 __global__ void k_build_operand(double *__restrict__ out, int nbf, int ldb, long long plane_stride, const double *__restrict__ srcA,
-                                const double *__restrict__ srcB, double signB, const int *__restrict__ f2user,
-                                const double *__restrict__ fR, int giao) {
+                                const double *__restrict__ srcB, double signB, const int *__restrict__ f2user) {
     const int nu = blockIdx.x * blockDim.x + threadIdx.x, mu = blockIdx.y;
     if (nu >= nbf) return;
     const long un = f2user[nu], um = f2user[mu];
     const long src = um + (long)nbf * un, nn = (long)nbf * nbf;
     const long dst = 2 * ((long)mu * ldb + nu);
-    double v[8];
+    double v[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         v[q] = srcA[q * nn + src];
         if (srcB) v[q] += signB * srcB[q * nn + src];
     }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) v[4 + d] = v[0] * (fR[d * nbf + nu] - fR[d * nbf + mu]);
-    v[7] = 0.0;
-    const int npp = giao ? 4 : 2;
-    for (int pp = 0; pp < npp; ++pp) *reinterpret_cast<double2 *>(out + pp * plane_stride + dst) = make_double2(v[2 * pp], v[2 * pp + 1]);
+    for (int pp = 0; pp < 2; ++pp) *reinterpret_cast<double2 *>(out + pp * plane_stride + dst) = make_double2(v[2 * pp], v[2 * pp + 1]);
 }
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
-                          const int *f2user, const double *fR, bool giao, cudaStream_t s) {
+                          const int *f2user, cudaStream_t s) {
     dim3 grid((nbf + 127) / 128, nbf);
-    k_build_operand<<<grid, 128, 0, s>>>(out, nbf, ldb, plane_stride, srcA, srcB, signB, f2user, fR, giao ? 1 : 0);
+    k_build_operand<<<grid, 128, 0, s>>>(out, nbf, ldb, plane_stride, srcA, srcB, signB, f2user);
 }
 
 }  // namespace gb

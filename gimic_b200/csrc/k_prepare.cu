@@ -167,14 +167,19 @@ __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__
     }
     auto umx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
     gi = block_reduce_128(gi, umx, u4);
-    int cnt = 0;
+    int cnt = 0, nat = 0;
     __syncthreads();
-    for (int a = threadIdx.x; a < B.natoms; a += 128) { int nsh, nfun; atom_active(B, a, tg, sx, sy, sz, sg.npts, nsh, nfun); cnt += nfun; }
+    const int al = B.slot_align - 1;
+    for (int a = threadIdx.x; a < B.natoms; a += 128) {
+        int nsh, nfun; atom_active(B, a, tg, sx, sy, sz, sg.npts, nsh, nfun);
+        cnt += (nfun + al) & ~al; nat += nfun > 0;
+    }
     auto iadd = [](int a, int b) { return a + b; };
     cnt = block_reduce_128(cnt, iadd, i4);
+    nat = block_reduce_128(nat, iadd, i4);
     if (threadIdx.x == 0) {
         geo[blockIdx.x] = tg;
-        info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt};
+        info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt, nat, 0};
     }
 }
 void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
@@ -230,7 +235,7 @@ __device__ __forceinline__ void shell_to_panel(double rx, double ry, double rz, 
 __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
                                                const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                const double *__restrict__ rsz, double *__restrict__ panel_pool,
-                                               int *__restrict__ fidx_pool) {
+                                               int *__restrict__ fidx_pool, TileAtom *__restrict__ atab_pool) {
     extern __shared__ int s_runs[];   // 3 ints per active atom
     __shared__ int s_w[2][4];
     __shared__ int s_base[2];
@@ -246,9 +251,11 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
     { const long p = td.pt0 + (tid < td.npts ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
     if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
     __syncthreads();
+    const int al = B.slot_align - 1;
     for (int a0 = 0; a0 < B.natoms; a0 += 128) {
         int a = a0 + tid, nsh = 0, nfun = 0;
         if (a < B.natoms) atom_active(B, a, tg, sx, sy, sz, td.npts, nsh, nfun);
+        nfun = (nfun + al) & ~al;                    // slots of the atom's run (functions + alignment padding)
         int flag = nfun > 0, sf = nfun, sr = flag;   // inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -268,15 +275,30 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
         __syncthreads();
     }
     const int nruns = s_base[1];
-    // slot -> internal function index; pad slots point at function 0 (their Phi is zero)
+    // slot -> internal function index; pad slots point at a valid function (their Phi is zero)
     for (int rn = 0; rn < nruns; ++rn) {
         int a = s_runs[3 * rn], nsh = s_runs[3 * rn + 1], slot0 = s_runs[3 * rn + 2];
         int f0 = B.atom_func_off[a];
         int s_last = B.atom_shell_off[a] + nsh - 1, ll = B.sh_l[s_last];
-        int nfun = B.sh_foff[s_last] - f0 + (ll + 1) * (ll + 2) / 2;
-        for (int c = tid; c < nfun; c += 128) fidx[slot0 + c] = f0 + c;
+        int nfun = B.sh_foff[s_last] - f0 + (ll + 1) * (ll + 2) / 2, nslot = (nfun + al) & ~al;
+        for (int c = tid; c < nslot; c += 128) fidx[slot0 + c] = f0 + (c < nfun ? c : 0);
     }
     for (int c = td.nraw + tid; c < td.nact; c += 128) fidx[c] = 0;
+    // atom table for the GIAO taps of k_jtensor (see TileAtom)
+    if (atab_pool) {
+        TileAtom *atab = atab_pool + td.atab_off;
+        const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
+        for (int rn = tid; rn < nruns; rn += 128) {
+            const int a = s_runs[3 * rn];
+            const int slot_end = (rn + 1 < nruns) ? s_runs[3 * rn + 5] : td.nraw;
+            double nx = cx, ny = cy, nz = cz;
+            if (rn + 1 < nruns) { const int b = s_runs[3 * rn + 3]; nx = B.atom_xyz[3 * b]; ny = B.atom_xyz[3 * b + 1]; nz = B.atom_xyz[3 * b + 2]; }
+            TileAtom ta;
+            ta.dx = B.atom_xyz[3 * a] - nx; ta.dy = B.atom_xyz[3 * a + 1] - ny; ta.dz = B.atom_xyz[3 * a + 2] - nz;
+            ta.kend4 = slot_end / 4; ta.atom = a;
+            atab[rn] = ta;
+        }
+    }
 
     const int row = tid;
     const bool valid = row < td.npts;
@@ -310,6 +332,14 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
                 case 3: shell_to_panel<3>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
                 case 4: shell_to_panel<4>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
                 default: shell_to_panel<5>(rx, ry, rz, q, qp, on, tm, p0, plane); break;
+            }
+        }
+        if (al) {   // zero rows of the run's alignment padding
+            const int s_last = sA + nsh - 1, ll = B.sh_l[s_last];
+            const int nfun = B.sh_foff[s_last] - f0 + (ll + 1) * (ll + 2) / 2, nslot = (nfun + al) & ~al;
+            for (int c = nfun; c < nslot; ++c) {
+                const long o = (long)(slot0 + c) * LDP + row;
+                panel[o] = 0.0; panel[plane + o] = 0.0; panel[2 * plane + o] = 0.0; panel[3 * plane + o] = 0.0;
             }
         }
     }
@@ -360,11 +390,11 @@ void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const doub
 }
 
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
-                  const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s) {
+                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s) {
     if (ntiles <= 0) return;
     size_t smem = (size_t)3 * B.natoms * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
-    k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool);
+    k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
 }
 
 }  // namespace gb

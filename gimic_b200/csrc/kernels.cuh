@@ -7,7 +7,8 @@
 //   k_tile_count      per tile: bounding sphere + conservative active-function count (screening)
 //   k_basis           per tile: Phi, dPhi/dx,dy,dz of the active functions -> K-major panels in HBM/L2
 //   k_jtensor         per tile: DMMA contraction of the Phi panel with the gathered density
-//                     operands [D | Px | Py | Pz | D(Rv-Ru)x | D(Rv-Ru)y | D(Rv-Ru)z] and a fused
+//                     operands [D | Px | Py | Pz]; the three London/GIAO products sum_mu Phi_mu D[mu,nu] (R_nu - R_mu)_d are
+//                     taken from the running D accumulator at atom boundaries of the K loop (no extra GEMM planes); fused
 //                     epilogue that reduces against Phi / dPhi to the 3x3 tensor (never stores X)
 //   k_fields          T -> jvec, signed |J|, ACID (HBM-bound pass)
 //   k_quad_rows/final Gauss-Legendre plane quadrature
@@ -22,8 +23,9 @@ constexpr int LDP = 132;   // panel row stride in doubles: 132 = 4 (mod 16) -> c
 constexpr int BK = 32;     // K slots per pipeline stage (the last stage of a K sweep may hold 16)
 constexpr int NV = 16;     // nu slots per accumulator chunk (2 n8 tiles per operand matrix)
 constexpr int LDB2 = 36;   // smem row stride (doubles) of a pair-plane B tile: 16 nu x 2 + 4 pad = 18 16-byte units = 2 (mod 8) -> conflict-free LDS.128
-constexpr int STAGES = 3;  // mbarrier pipeline depth (3 x 69.6 KB)
-constexpr int NQ_GIAO = 7, NQ_NOGIAO = 4;
+constexpr int STAGES = 3;  // mbarrier pipeline depth (3 x 51.2 KB)
+constexpr int NQ = 4;      // GEMM operand planes: D, Px, Py, Pz (two 16-byte pair-planes)
+constexpr int SLOT_ALIGN_GIAO = 4;   // with GIAO every atom's slot run is padded to whole k4 MMA steps (atom-boundary taps)
 
 struct DevBasis {
     int natoms, nbf, nshell;
@@ -36,20 +38,27 @@ struct DevBasis {
     const double *alpha, *ncc;    // primitives
     const double *fR;             // [3][nbf] centre coordinates of each internal function (SoA)
     int turbomole;                // component order (gtodefs.f90:109-123) instead of the standard one
+    int slot_align;               // 1, or SLOT_ALIGN_GIAO: each active atom occupies a multiple of this many tile slots
 };
 
 struct TileDesc {
     int pt0, npts;      // range in the sorted point list
     int nact;           // active slots, padded to a multiple of 8 (0: nothing within screening range)
     int nraw;           // unpadded active function count
-    int geo, pad_;      // index into the TileGeo array
+    int geo, nruns;     // index into the TileGeo array; number of active atoms (slot runs)
     long long panel_off;  // doubles, into the panel pool: 4 planes x nact x LDP
     long long fidx_off;   // ints, into the index pool
+    long long atab_off;   // TileAtom entries, into the atom-table pool (nruns entries, atom order = slot order)
 };
+
+// One active atom of a tile, in slot order.  kend4 = end of its slot run in units of 4 slots (one m16n8k4 K step).
+// (dx,dy,dz) = R_A - R_next for all but the last run, R_A - tile centre for the last: the Abel-summed weights of the
+// GIAO taps in k_jtensor (sum_A (R_A - c) P_A = sum_A C_A (R_A - R_{A+1}) + C_n (R_n - c), C_A = running K sum after atom A).
+struct __align__(32) TileAtom { double dx, dy, dz; int kend4, atom; };
 
 struct TileGeo { double lox, loy, loz, hix, hiy, hiz, rho, pad_; };   // axis-aligned bounding box of the tile's points (+ radius about its centre)
 struct TileSeg { int pt0, npts; };                         // a tile = npts <= MT consecutive points of the sorted list
-struct TileInfo { float rho, gmax; int imax, nraw; };      // radius, largest consecutive gap (and where), active functions
+struct TileInfo { float rho, gmax; int imax, nraw, natom, pad_; };   // radius, largest consecutive gap (and where), active slots (atom runs aligned), active atoms
 
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
 void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s);
@@ -59,25 +68,26 @@ void launch_grid_points(const double *origin_basv /*12 doubles, device*/, const 
 void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
                        TileGeo *geo, TileInfo *info, cudaStream_t s);
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
-                  const double *rsz, double *panel_pool, int *fidx_pool, cudaStream_t s);
+                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s);
 void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s);
 size_t sort_temp_bytes(long n);
 void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s);
 
 struct JtensorArgs {
     const TileDesc *tiles; int ntiles; int *counter;
-    const double *panel_pool; const int *fidx_pool;
-    const double *Bop; long long plane_stride; int ldb;     // pair-plane operands [(NQ+1)/2][nbf][ldb][2]; plane_stride in doubles
+    const double *panel_pool; const int *fidx_pool; const TileAtom *atab_pool; const TileGeo *geo;
+    const double *Bop; long long plane_stride; int ldb;     // pair-plane operands [2][nbf][ldb][2] = (D,Px), (Py,Pz); plane_stride in doubles
     const double *fR; int nbf;
     const double *rsx, *rsy, *rsz; const int *perm;
     double *tens; double *edens;                            // outputs in user point order (edens may be null)
     int paramag, diamag;
+    int dbg;                                                // timing experiments only (GIMIC_B200_DBG): 1 = taps without DFMAs, 2 = no taps
 };
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
-size_t jtensor_smem_bytes(bool giao);
+size_t jtensor_smem_bytes();
 
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
-                          const int *f2user, const double *fR, bool giao, cudaStream_t s);
+                          const int *f2user, cudaStream_t s);
 
 void launch_fields(long n, const double *r, const double *tens, const double *B3 /*host values*/, double *jvec, double *jmod, double *acid, cudaStream_t s);
 void launch_divj(long n, const double *jv6 /* [6][n][3] shifted jvecs */, double h, double *divj, cudaStream_t s);

@@ -12,9 +12,10 @@ ap.add_argument("--natoms", type=int, default=278)
 ap.add_argument("--grid", type=int, default=256)
 ap.add_argument("--points", type=int, default=148 * 8 * 128)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--no-giao", action="store_true")
 a = ap.parse_args()
 sh, dens, nbf, origin, basv, pts = bench.build_workload(a.natoms, a.grid)
-g = gimic_b200.Gimic.from_arrays(dens_alpha=synthetic.dens_to_colmajor(dens), **sh)
+g = gimic_b200.Gimic.from_arrays(dens_alpha=synthetic.dens_to_colmajor(dens), giao=not a.no_giao, **sh)
 r = bench.slab_points(origin, basv, pts, 0)
 r = np.ascontiguousarray(r[-a.points:])   # the planes of octant 0 closest to the molecular plane
 g.set_profiling(True)
