@@ -327,13 +327,14 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         TileDesc &td = c->h_tiles[t];
         td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.nruns = c->h_info[t].natom;
         td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 7) / 8 * 8;
+        td.nreal = c->h_info[t].nreal; td.nn = (td.nreal + 7) / 8 * 8;
         size_t d = (size_t)4 * td.nact * LDP;
         if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff); off = 0; foff = 0; aoff = 0; }
         td.panel_off = (long long)off; td.fidx_off = (long long)foff; td.atab_off = (long long)aoff;
-        off += d; foff += td.nact; aoff += td.nruns;
+        off += d; foff += td.nact + td.nn; aoff += td.nruns;
         sum_nact += td.nact;
-        flops += 2.0 * MT * c->nq * (double)td.nact * td.nact;   // DMMA: K and N both run over nact slots (multiples of 8)
-        if (giao) flops += 2.0 * MT * 3.0 * (double)td.nact * td.nruns;   // GIAO taps: 3 DFMA per accumulator element per active atom
+        flops += 2.0 * MT * c->nq * (double)td.nact * td.nn;   // DMMA: K runs over the nact slots, N over the nn columns (multiples of 8)
+        if (giao) flops += 2.0 * MT * 3.0 * (double)td.nn * td.nruns;   // GIAO taps: 3 DFMA per accumulator element per active atom
     }
     fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff);
     batch_start.push_back(ntiles);

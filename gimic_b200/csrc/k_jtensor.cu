@@ -112,17 +112,17 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
         if (td.nact == 0) continue;
-        const int nact = td.nact;
-        const int nkc = (nact + BK - 1) / BK, nvc = (nact + NV - 1) / NV;   // nact is a multiple of 8: the last nu chunk may hold 8 slots
+        const int nact = td.nact, nn = td.nn;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
-        const int *fidx = a.fidx_pool + td.fidx_off;
+        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
         {
         // ===================================== producer warps =====================================
         const int pw = warp - NCONSUMER_WARPS;
         const int ldn = lane & 15, ldk0 = (lane >> 4) + 2 * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0+8, ...
         int kc = 0, vc = 0;
-        long nu = fidx[min(ldn, nact - 1)];
+        long nu = fidx[nlist[min(ldn, nn - 1)]];
         for (uint32_t itl = 0; itl < NIT; ++itl) {
             const uint32_t gi = git + itl, s = gi % STAGES, ph = (gi / STAGES) & 1;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -132,7 +132,7 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
                 mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kcnt * LDP * 8));
                 tma_bulk_g2s(sA, panel + (long)kc * BK * LDP, (uint32_t)(kcnt * LDP * 8), bar_full + 8 * s);
             }
-            const bool nu_ok = vc * NV + ldn < nact;
+            const bool nu_ok = vc * NV + ldn < nn;
             const double *srcB = a.Bop + 2 * nu;
             const uint32_t dstB = sB + (uint32_t)(ldn * 16);
 #pragma unroll 4
@@ -144,7 +144,7 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
                 for (int pp = 0; pp < SM::NPP; ++pp) cp_async_16(dst + (uint32_t)(pp * SM::PP_DOUBLES * 8), src + pp * a.plane_stride);
             }
             cp_async_arrive_noinc(bar_full + 8 * s);
-            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[min(vc * NV + ldn, nact - 1)]; }
+            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[nlist[min(vc * NV + ldn, nn - 1)]]; }
         }
         }
         git += NIT;
@@ -172,12 +172,12 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
             }
             continue;
         }
-        const int nact = td.nact;
-        const int nkc = (nact + BK - 1) / BK, nvc = (nact + NV - 1) / NV;   // nact is a multiple of 8: the last nu chunk may hold 8 slots
+        const int nact = td.nact, nn = td.nn;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
         const long plane = (long)nact * LDP;
-        const int *fidx = a.fidx_pool + td.fidx_off;
+        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
         {
         // ===================================== consumer warps =====================================
         // Row table: lane t=0 of a quad owns row A, lane t=1 row B.  [0..12] running sums Tp(m,b) at [m+3b], V_d at [9+d],
@@ -240,7 +240,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
             const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
             const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
             const int nks = min(BK, nact - kc * BK) / 4;
-            const bool h1 = vc * NV + 8 < nact;                     // second n8 tile of this chunk holds real slots
+            const bool h1 = vc * NV + 8 < nn;                       // second n8 tile of this chunk holds real columns
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
             mbar_wait(bar_full + 8 * s, ph);
@@ -289,7 +289,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         if (h == 1 && !h1) continue;
-                        const int slot = vc * NV + h * 8 + 2 * t + j;
+                        const int slot = nlist[vc * NV + h * 8 + 2 * t + j];   // K slot (= panel row) of this nu column
                         const double *pe = panel + (long)slot * LDP;
                         double Rx = 0, Ry = 0, Rz = 0;
                         if (GIAO) { const int f = fidx[slot]; Rx = a.fR[f]; Ry = a.fR[a.nbf + f]; Rz = a.fR[2 * a.nbf + f]; }

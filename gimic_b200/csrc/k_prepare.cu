@@ -167,19 +167,20 @@ __global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__
     }
     auto umx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
     gi = block_reduce_128(gi, umx, u4);
-    int cnt = 0, nat = 0;
+    int cnt = 0, nat = 0, nre = 0;
     __syncthreads();
     const int al = B.slot_align - 1;
     for (int a = threadIdx.x; a < B.natoms; a += 128) {
         int nsh, nfun; atom_active(B, a, tg, sx, sy, sz, sg.npts, nsh, nfun);
-        cnt += (nfun + al) & ~al; nat += nfun > 0;
+        cnt += (nfun + al) & ~al; nat += nfun > 0; nre += nfun;
     }
     auto iadd = [](int a, int b) { return a + b; };
     cnt = block_reduce_128(cnt, iadd, i4);
     nat = block_reduce_128(nat, iadd, i4);
+    nre = block_reduce_128(nre, iadd, i4);
     if (threadIdx.x == 0) {
         geo[blockIdx.x] = tg;
-        info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt, nat, 0};
+        info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt, nat, nre};
     }
 }
 void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
@@ -236,9 +237,10 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
                                                const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                const double *__restrict__ rsz, double *__restrict__ panel_pool,
                                                int *__restrict__ fidx_pool, TileAtom *__restrict__ atab_pool) {
-    extern __shared__ int s_runs[];   // 3 ints per active atom
-    __shared__ int s_w[2][4];
-    __shared__ int s_base[2];
+    extern __shared__ int s_runs[];   // 4 ints per active atom: atom, shells, first K slot, first N column
+    __shared__ int s_w[3][4];
+    __shared__ int s_base[3];
+    __shared__ int s_zero;            // a K slot whose panel rows are zero (padding), for the N-side padding columns
     const TileDesc td = tiles[blockIdx.x];
     if (td.nact == 0) return;
     const TileGeo tg = geo[td.geo];
@@ -249,50 +251,54 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
 
     __shared__ double sx[MT], sy[MT], sz[MT];
     { const long p = td.pt0 + (tid < td.npts ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
-    if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
+    if (tid == 0) { s_base[0] = 0; s_base[1] = 0; s_base[2] = 0; s_zero = td.nraw < td.nact ? td.nraw : 0x7fffffff; }
     __syncthreads();
     const int al = B.slot_align - 1;
     for (int a0 = 0; a0 < B.natoms; a0 += 128) {
-        int a = a0 + tid, nsh = 0, nfun = 0;
-        if (a < B.natoms) atom_active(B, a, tg, sx, sy, sz, td.npts, nsh, nfun);
-        nfun = (nfun + al) & ~al;                    // slots of the atom's run (functions + alignment padding)
-        int flag = nfun > 0, sf = nfun, sr = flag;   // inclusive warp scans
+        int a = a0 + tid, nsh = 0, nreal = 0;
+        if (a < B.natoms) atom_active(B, a, tg, sx, sy, sz, td.npts, nsh, nreal);
+        const int nfun = (nreal + al) & ~al;         // slots of the atom's run (functions + alignment padding)
+        int flag = nfun > 0, sf = nfun, sr = flag, sn = nreal;   // inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t1 = __shfl_up_sync(0xffffffffu, sf, o), t2 = __shfl_up_sync(0xffffffffu, sr, o);
-            if (lane >= o) { sf += t1; sr += t2; }
+            int t1 = __shfl_up_sync(0xffffffffu, sf, o), t2 = __shfl_up_sync(0xffffffffu, sr, o), t3 = __shfl_up_sync(0xffffffffu, sn, o);
+            if (lane >= o) { sf += t1; sr += t2; sn += t3; }
         }
-        if (lane == 31) { s_w[0][wid] = sf; s_w[1][wid] = sr; }
+        if (lane == 31) { s_w[0][wid] = sf; s_w[1][wid] = sr; s_w[2][wid] = sn; }
         __syncthreads();
-        int offf = s_base[0], offr = s_base[1];
-        for (int w = 0; w < wid; ++w) { offf += s_w[0][w]; offr += s_w[1][w]; }
+        int offf = s_base[0], offr = s_base[1], offn = s_base[2];
+        for (int w = 0; w < wid; ++w) { offf += s_w[0][w]; offr += s_w[1][w]; offn += s_w[2][w]; }
         if (flag) {
             int run = offr + sr - 1, slot0 = offf + sf - nfun;
-            s_runs[3 * run] = a; s_runs[3 * run + 1] = nsh; s_runs[3 * run + 2] = slot0;
+            s_runs[4 * run] = a; s_runs[4 * run + 1] = nsh; s_runs[4 * run + 2] = slot0; s_runs[4 * run + 3] = offn + sn - nreal;
+            if (nfun > nreal) atomicMin(&s_zero, slot0 + nreal);
         }
         __syncthreads();
-        if (tid == 127) { s_base[0] = offf + sf; s_base[1] = offr + sr; }
+        if (tid == 127) { s_base[0] = offf + sf; s_base[1] = offr + sr; s_base[2] = offn + sn; }
         __syncthreads();
     }
     const int nruns = s_base[1];
     // slot -> internal function index; pad slots point at a valid function (their Phi is zero)
+    int *nlist = fidx + td.nact;   // N column -> K slot
     for (int rn = 0; rn < nruns; ++rn) {
-        int a = s_runs[3 * rn], nsh = s_runs[3 * rn + 1], slot0 = s_runs[3 * rn + 2];
+        int a = s_runs[4 * rn], nsh = s_runs[4 * rn + 1], slot0 = s_runs[4 * rn + 2], col0 = s_runs[4 * rn + 3];
         int f0 = B.atom_func_off[a];
         int s_last = B.atom_shell_off[a] + nsh - 1, ll = B.sh_l[s_last];
         int nfun = B.sh_foff[s_last] - f0 + (ll + 1) * (ll + 2) / 2, nslot = (nfun + al) & ~al;
         for (int c = tid; c < nslot; c += 128) fidx[slot0 + c] = f0 + (c < nfun ? c : 0);
+        for (int c = tid; c < nfun; c += 128) nlist[col0 + c] = slot0 + c;
     }
     for (int c = td.nraw + tid; c < td.nact; c += 128) fidx[c] = 0;
+    for (int c = td.nreal + tid; c < td.nn; c += 128) nlist[c] = s_zero;   // nn > nreal implies that a padding slot exists
     // atom table for the GIAO taps of k_jtensor (see TileAtom)
     if (atab_pool) {
         TileAtom *atab = atab_pool + td.atab_off;
         const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
         for (int rn = tid; rn < nruns; rn += 128) {
-            const int a = s_runs[3 * rn];
-            const int slot_end = (rn + 1 < nruns) ? s_runs[3 * rn + 5] : td.nraw;
+            const int a = s_runs[4 * rn];
+            const int slot_end = (rn + 1 < nruns) ? s_runs[4 * rn + 6] : td.nraw;
             double nx = cx, ny = cy, nz = cz;
-            if (rn + 1 < nruns) { const int b = s_runs[3 * rn + 3]; nx = B.atom_xyz[3 * b]; ny = B.atom_xyz[3 * b + 1]; nz = B.atom_xyz[3 * b + 2]; }
+            if (rn + 1 < nruns) { const int b = s_runs[4 * rn + 4]; nx = B.atom_xyz[3 * b]; ny = B.atom_xyz[3 * b + 1]; nz = B.atom_xyz[3 * b + 2]; }
             TileAtom ta;
             ta.dx = B.atom_xyz[3 * a] - nx; ta.dy = B.atom_xyz[3 * a + 1] - ny; ta.dz = B.atom_xyz[3 * a + 2] - nz;
             ta.kend4 = slot_end / 4; ta.atom = a;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
     const bool tm = B.turbomole != 0;
 
     for (int rn = 0; rn < nruns; ++rn) {
-        const int a = s_runs[3 * rn], nsh = s_runs[3 * rn + 1], slot0 = s_runs[3 * rn + 2];
+        const int a = s_runs[4 * rn], nsh = s_runs[4 * rn + 1], slot0 = s_runs[4 * rn + 2];
         const double rx = x - B.atom_xyz[3 * a], ry = y - B.atom_xyz[3 * a + 1], rz = z - B.atom_xyz[3 * a + 2];
         const double r2 = rx * rx + ry * ry + rz * rz;
         const double dist = sqrt(r2);                                  // filter_screened, basis.f90:127
@@ -392,7 +398,7 @@ void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const doub
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s) {
     if (ntiles <= 0) return;
-    size_t smem = (size_t)3 * B.natoms * sizeof(int);
+    size_t smem = (size_t)4 * B.natoms * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
     k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
 }

@@ -43,11 +43,12 @@ struct DevBasis {
 
 struct TileDesc {
     int pt0, npts;      // range in the sorted point list
-    int nact;           // active slots, padded to a multiple of 8 (0: nothing within screening range)
-    int nraw;           // unpadded active function count
+    int nact;           // K slots: atom runs (each aligned to slot_align) padded to a multiple of 8 (0: nothing within screening range)
+    int nraw;           // K slots before the final padding
+    int nn, nreal;      // N columns: the nreal active functions padded to a multiple of 8 (no per-atom padding on this side)
     int geo, nruns;     // index into the TileGeo array; number of active atoms (slot runs)
     long long panel_off;  // doubles, into the panel pool: 4 planes x nact x LDP
-    long long fidx_off;   // ints, into the index pool
+    long long fidx_off;   // ints, into the index pool: nact slot -> function indices, then nn column -> K-slot indices
     long long atab_off;   // TileAtom entries, into the atom-table pool (nruns entries, atom order = slot order)
 };
 
@@ -58,7 +59,7 @@ struct __align__(32) TileAtom { double dx, dy, dz; int kend4, atom; };
 
 struct TileGeo { double lox, loy, loz, hix, hiy, hiz, rho, pad_; };   // axis-aligned bounding box of the tile's points (+ radius about its centre)
 struct TileSeg { int pt0, npts; };                         // a tile = npts <= MT consecutive points of the sorted list
-struct TileInfo { float rho, gmax; int imax, nraw, natom, pad_; };   // radius, largest consecutive gap (and where), active slots (atom runs aligned), active atoms
+struct TileInfo { float rho, gmax; int imax, nraw, natom, nreal; };   // radius, largest consecutive gap (and where), active slots (atom runs aligned), active atoms, active functions
 
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
 void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s);
