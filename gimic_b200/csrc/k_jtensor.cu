@@ -201,6 +201,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
         const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
         double curx = 0, cury = 0, curz = 0;
         int ia = 0;
+        int eslot[2][2];                                            // epilogue: K slot of this thread's 4 nu columns
         if (GIAO) {
             // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
             const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
@@ -236,6 +237,11 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                     ia = 0;
                     curx = atd[0]; cury = atd[1]; curz = atd[2];
                 }
+                // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) eslot[h][j] = nlist[min(vc * NV + h * 8 + 2 * t + j, nn - 1)];
             }
             const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
             const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
@@ -289,7 +295,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         if (h == 1 && !h1) continue;
-                        const int slot = nlist[vc * NV + h * 8 + 2 * t + j];   // K slot (= panel row) of this nu column
+                        const int slot = eslot[h][j];                         // K slot (= panel row) of this nu column
                         const double *pe = panel + (long)slot * LDP;
                         double Rx = 0, Ry = 0, Rz = 0;
                         if (GIAO) { const int f = fidx[slot]; Rx = a.fR[f]; Ry = a.fR[a.nbf + f]; Rz = a.fR[2 * a.nbf + f]; }
