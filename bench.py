@@ -157,7 +157,7 @@ def main():
            "nbf": args.natoms * 36, "grid": [args.grid] * 3, "points_per_step_per_gpu": args.grid ** 3 // NSLAB,
            "spincase": "total (closed shell)", "giao": True, "screening_thrs": 1e-8,
            "densities": "seeded random symmetric D, " + ("general" if args.general_p else "antisymmetric") + " P_x,P_y,P_z",
-           "cache": "inputs larger than L2 (contraction operand 7*nbf^2*8 B = %.1f GB, panels streamed)" % (7 * (args.natoms * 36) ** 2 * 8 / 1e9),
+           "cache": "inputs larger than L2 (contraction operand 4*nbf^2*8 B = %.1f GB, panels streamed)" % (4 * (args.natoms * 36) ** 2 * 8 / 1e9),
            "parallelism": f"grid slabs over {world} GPU(s), no data-path collective"}
 
     # ------------------------------------------------------------------ reference arm (CPU) -------
@@ -257,10 +257,10 @@ def main():
         peak, peak_src = fp64_peak()
         t_contract = tot["ms_contract"] * 1e-3
         achieved = tot["executed_flops"] / t_contract / 1e12 if t_contract > 0 else None
-        roof = {"bound": "tensor", "kernel": "k_jtensor<GIAO> (FP64 DMMA contraction + fused tensor epilogue)",
+        roof = {"bound": "tensor", "kernel": "k_jtensor<GIAO> (FP64 DMMA contraction of Phi with [D|Px|Py|Pz], GIAO terms by atom-boundary taps of the D accumulator, fused tensor epilogue)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": ncu_traffic(nbf), "peak_source": peak_src,
-                "flops": "EXECUTED DMMA flops 2*128*7*nact^2 per tile (screened-function skipping on; exact zeros in the reference)",
+                "flops": "EXECUTED FP64 flops per tile: DMMA 2*128*4*nact*nn + GIAO-tap DFMA 2*128*3*nn*natoms_active (screened-function skipping on; exact zeros in the reference)",
                 "avg_launch_ms": tot["ms_contract"] / max(tot["contract_launches"], 1), "launches_timed": tot["contract_launches"],
                 "share_of_step": tot["ms_contract"] / tot["ms_total"] if tot["ms_total"] else None,
                 "dense_equivalent_tflops": tot["dense_flops"] / (tot["ms_total"] * 1e-3) / 1e12,
