@@ -328,6 +328,7 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.nruns = c->h_info[t].natom;
         td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 7) / 8 * 8;
         td.nreal = c->h_info[t].nreal; td.nn = (td.nreal + 7) / 8 * 8;
+        if (td.nact > 65536) return fail(GIMIC_B200_EINVAL, "more than 65536 active basis-function slots in one tile of points (k_jtensor's K-step mask)");
         size_t d = (size_t)4 * td.nact * LDP;
         if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff); off = 0; foff = 0; aoff = 0; }
         td.panel_off = (long long)off; td.fidx_off = (long long)foff; td.atab_off = (long long)aoff;

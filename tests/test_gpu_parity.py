@@ -412,6 +412,29 @@ def test_binary_xdens_cache_gives_identical_tensors(gb, cases, tmp_path, opensh)
         gb.Gimic(cases["benzene_mol"], tmp_path / "XDENS.bin", screening_thrs=1e-8)   # nbf 252 vs a cache for 168
 
 
+def test_more_active_atoms_than_the_shared_memory_table(gb):
+    """k_jtensor stages the GIAO tap weights of up to 1024 active atoms per tile in shared memory and reads them from global
+    memory beyond that: 1100 one-function atoms with screening off (every atom active in every tile), plus a p shell on a few"""
+    rng = np.random.default_rng(31)
+    nat = 1100
+    coords = rng.uniform(-6, 6, size=(nat, 3))
+    nctr = np.ones(nat, np.int32); nctr[:5] = 2
+    ls, npf, xp, cc = [], [], [], []
+    for a in range(nat):
+        ls.append(0); npf.append(1); xp.append(0.4 + 0.001 * a); cc.append(1.0)
+        if a < 5:
+            ls.append(1); npf.append(1); xp.append(0.7); cc.append(1.0)
+    sh = dict(coords=coords, nctr_per_atom=nctr, ctr_l=np.array(ls, np.int32), ctr_npf=np.array(npf, np.int32), xp=np.array(xp), cc=np.array(cc))
+    nbf = nat + 15
+    flat = fixtures.dens_to_colmajor(fixtures.synthetic_density(nbf, seed=8, general_p=True) * 0.05)
+    g = gb.Gimic.from_arrays(dens_alpha=flat, screening=False, **sh)
+    o = O.Oracle.from_arrays(dens_a=flat, screening_thrs=-1.0, **sh)
+    r = rng.uniform(-5, 5, size=(150, 3))
+    assert_close(g.jtensors(r), o.ctensor(r), "1100 active atoms per tile")
+    assert g.stats()["n_tiles"] >= 1
+    g.close()
+
+
 def test_general_contraction_mol_file(gb, tmp_path):
     """INTGRL blocks with ncf > 1 (general contractions are split into segmented ones, intgrl.f90:172-216) and
     primitive lines that wrap over several records (list-directed reads)"""
