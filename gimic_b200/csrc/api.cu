@@ -375,7 +375,6 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
         a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = perm; a.tens = d_tens; a.edens = d_edens;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
-        { static const int dbg = [] { const char *e = std::getenv("GIMIC_B200_DBG"); return e ? std::atoi(e) : 0; }(); a.dbg = dbg; }
         launch_jtensor(a, c->opts.giao != 0, c->nsm, st);
         CUDA_TRY(cudaGetLastError());
         c->stats.launches += 2;

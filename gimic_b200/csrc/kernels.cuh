@@ -82,7 +82,6 @@ struct JtensorArgs {
     const double *rsx, *rsy, *rsz; const int *perm;
     double *tens; double *edens;                            // outputs in user point order (edens may be null)
     int paramag, diamag;
-    int dbg;                                                // timing experiments only (GIMIC_B200_DBG): 1 = taps without DFMAs, 2 = no taps
 };
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
 size_t jtensor_smem_bytes();
