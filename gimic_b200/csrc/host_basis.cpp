@@ -422,6 +422,68 @@ void density_sph_to_cart(const HostBasis &b, const double *dsph, double *dcart) 
     }
 }
 
+// ---- Fortran Ew.d formatting ---------------------------------------------------------------------
+namespace {
+// One value, right-justified in w characters: 0.ddddddE+ee (gfortran: no 'E' when the exponent needs three digits).
+void put_e(double x, int w, int d, char *dst) {
+    char tmp[64], body[64];
+    int len;
+    if (x == 0.0) {
+        len = std::snprintf(body, sizeof body, "0.%0*dE+00", d, 0);
+    } else if (!std::isfinite(x)) {
+        len = std::snprintf(body, sizeof body, "%s", std::isnan(x) ? "NaN" : (x < 0 ? "-Infinity" : "Infinity"));
+    } else {
+        auto res = std::to_chars(tmp, tmp + sizeof tmp - 1, std::fabs(x), std::chars_format::scientific, d - 1);   // d.ddddde+ee, correctly rounded
+        *res.ptr = 0;
+        const char *ep = std::strchr(tmp, 'e');
+        int e = std::atoi(ep + 1) + 1;
+        char *o = body;
+        if (x < 0) *o++ = '-';
+        *o++ = '0'; *o++ = '.';
+        for (const char *q = tmp; q < ep; ++q) if (*q != '.') *o++ = *q;
+        const int ae = e < 0 ? -e : e;
+        if (ae < 100) o += std::snprintf(o, 8, "E%c%02d", e < 0 ? '-' : '+', ae);
+        else o += std::snprintf(o, 8, "%c%03d", e < 0 ? '-' : '+', ae);
+        len = (int)(o - body);
+    }
+    if (len > w) { std::memset(dst, '*', (size_t)w); return; }   // field overflow: asterisks like Fortran
+    std::memset(dst, ' ', (size_t)(w - len));
+    std::memcpy(dst + (w - len), body, (size_t)len);
+}
+}  // namespace
+
+long format_fortran_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap) {
+    if (n <= 0) return 0;
+    if (per_line <= 0) per_line = 1;
+    const long first = first_count > 0 ? std::min<long>(first_count, n) : std::min<long>(per_line, n);
+    const long plen = prefix ? (long)std::strlen(prefix) : 0;
+    auto line_of = [&](long l) { return l < first ? 0L : 1 + (l - first) / per_line; };
+    const long nlines = line_of(n - 1) + 1;
+    const long last_count = nlines == 1 ? n : (n - first) - (nlines - 2) * (long)per_line;
+    const bool last_complete = nlines == 1 ? (n == (first_count > 0 ? first_count : per_line)) : last_count == per_line;
+    const long total = n * w + nlines * plen + (nlines - 1) + (last_complete ? 1 : 0);
+    if (total > cap) return -1;
+    unsigned nthr = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (n < 4096) nthr = 1;
+    auto work = [&](long lo, long hi) {
+        for (long l = lo; l < hi; ++l) {
+            const long ln = line_of(l);
+            char *p = out + l * w + (ln + 1) * plen + ln;
+            const bool starts = (l == 0) || (l == first) || (l > first && (l - first) % per_line == 0);
+            if (starts && plen) std::memcpy(p - plen, prefix, (size_t)plen);
+            put_e(v[l], w, d, p);
+            const bool ends = (l + 1 == first) || (l + 1 > first && (l + 1 - first) % per_line == 0);
+            if (ends && (l + 1 < n || last_complete)) p[w] = '\n';
+        }
+    };
+    std::vector<std::thread> th;
+    const long chunk = (n + nthr - 1) / nthr;
+    for (unsigned t = 1; t < nthr; ++t) { long lo = t * chunk, hi = std::min(n, lo + chunk); if (lo < hi) th.emplace_back(work, lo, hi); }
+    work(0, std::min(n, chunk));
+    for (auto &x : th) x.join();
+    return total;
+}
+
 // ---- quadrature nodes ---------------------------------------------------------------------------
 namespace {
 // P_n(x) and derivatives by the three-term recurrence (gaussint.f90:144-222)

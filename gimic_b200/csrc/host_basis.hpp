@@ -67,6 +67,11 @@ void c2s_rows(int l, bool turbomole, std::vector<double> &po);
 // vectors at every point; applying it to the densities once is the same bilinear form).  Both column-major.
 void density_sph_to_cart(const HostBasis &b, const double *dsph, double *dcart);
 
+// Bulk number formatting for the output files (vtkplot.f90 writes every value with a Fortran Ew.d edit descriptor; at 256^3
+// points that is 5e7 values).  Lines hold `per_line` values (the first line `first_count` if > 0), each line starts with
+// `prefix` and complete lines end with '\n'.  Threaded; returns the number of bytes written, or -1 if `cap` is too small.
+long format_fortran_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
+
 // Gauss-Legendre / Lobatto nodes in the piecewise-block layout of setup_gauss_data
 // (src/libgimic/gaussint.f90:267-319).  quadrature: 0 = gauss, 1 = lobatto.
 int gauss_blocks(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);

@@ -62,9 +62,10 @@ def _dist():
 
 
 class Driver:
-    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None):
+    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False):
         self.workdir = workdir or os.path.dirname(os.path.abspath(inpfile))
         self.inp = _inp.parse_file(inpfile)
+        self.vtk_appended = bool(vtk_appended)   # extra: .vti files with raw appended Float64 data instead of ASCII e14.6
         self.dist, self.rank, self.world = _dist()
         self.out = out if out is not None else sys.stdout
         I = self.inp
@@ -166,13 +167,13 @@ class Driver:
                                        (grid.mode == "bond" or grid.gtype == "even"))
             if grid.is_3d():
                 if I.get("Essential.acid"):
-                    writers.write_vti_scalar(os.path.join(wd, "acid.vti"), grid, f["acid"])
+                    writers.write_vti_scalar(os.path.join(wd, "acid.vti"), grid, f["acid"], self.vtk_appended)
                 if I.get("Essential.jmod"):
-                    writers.write_vti_scalar(os.path.join(wd, f"jmod{tag}.vti"), grid, f["jmod"])
+                    writers.write_vti_scalar(os.path.join(wd, f"jmod{tag}.vti"), grid, f["jmod"], self.vtk_appended)
             if I.get("Essential.prop"):
                 self.run_property(tens)
             if grid.mode in ("std", "base", "bond") and grid.gtype == "even":
-                writers.write_vti_vector(os.path.join(wd, f"jvec{tag}.vti"), grid, jv)
+                writers.write_vti_vector(os.path.join(wd, f"jvec{tag}.vti"), grid, jv, self.vtk_appended)
             elif (grid.mode in ("std", "base") and grid.gauss) or grid.mode == "file":
                 ele = os.path.join(wd, "grid.1.ele")
                 if os.path.exists(ele):
@@ -321,7 +322,7 @@ class Driver:
         if self.rank != 0:
             return
         if grid.mode != "file" and grid.gtype == "even" and grid.npts[0] > 1 and grid.npts[1] > 1:
-            writers.write_vti_scalar(os.path.join(self.workdir, f"{calc}.vti"), grid, f[calc])
+            writers.write_vti_scalar(os.path.join(self.workdir, f"{calc}.vti"), grid, f[calc], self.vtk_appended)
         else:
             np.savetxt(os.path.join(self.workdir, f"{calc}.txt"), np.column_stack([r, f[calc]]), fmt="%20.12e")
 
@@ -377,6 +378,8 @@ def main(argv=None):
                     help="one gimic.inp, or several (a current-profile scan): they share one device context, integrals are "
                          "batched into one tensor pass, and each report is written to <input stem>.out")
     ap.add_argument("--workdir", default=None)
+    ap.add_argument("--vtk", default="ascii", choices=["ascii", "appended"],
+                    help="ascii: the reference's .vti files (e14.6); appended: same files with raw Float64 blocks (extra, not a reference format)")
     a = ap.parse_args(argv)
     if len(a.infile) > 1:
         run_scan(a.infile)
@@ -389,5 +392,5 @@ def main(argv=None):
         device = int(os.environ["LOCAL_RANK"])
         torch.cuda.set_device(device)
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
-    Driver(a.infile, a.workdir, device=device).run()
+    Driver(a.infile, a.workdir, device=device, vtk_appended=(a.vtk == "appended")).run()
     return 0

@@ -8,7 +8,7 @@ AU2A = float(np.float32(0.52917726))     # globals.f90:51 is a single-precision 
 
 
 def fortran_e(x, w, d):
-    """Fortran Ew.d: 0.dddddE+ee"""
+    """Fortran Ew.d: 0.dddddE+ee (gfortran drops the 'E' when the exponent needs three digits; asterisks on overflow)"""
     x = float(x)
     if x == 0.0:
         s = "0." + "0" * d + "E+00"
@@ -16,8 +16,26 @@ def fortran_e(x, w, d):
         m, e = f"{abs(x):.{d - 1}E}".split("E")
         digits = m.replace(".", "")
         e = int(e) + 1
-        s = ("-" if x < 0 else "") + "0." + digits + f"E{e:+03d}"
-    return s.rjust(w)
+        s = ("-" if x < 0 else "") + "0." + digits + (f"E{e:+03d}" if abs(e) < 100 else f"{e:+04d}")
+    return "*" * w if len(s) > w else s.rjust(w)
+
+
+def format_e(values, w, d, per_line, first=0, prefix=""):
+    """Many values with Ew.d in one native, threaded call (gimic_b200_format_e): `per_line` values per line (`first` on the
+    first line if > 0), every line starting with `prefix`, complete lines ending in a newline.  Returns bytes."""
+    import ctypes as C
+    from . import _lib
+    v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    n = v.size
+    if n == 0:
+        return b""
+    nlines = n // max(per_line, 1) + 2
+    cap = n * w + nlines * (len(prefix) + 1) + 16
+    buf = np.empty(cap, dtype=np.uint8)
+    got = _lib.lib().gimic_b200_format_e(n, v.ctypes.data_as(_lib.dp), w, d, per_line, first, prefix.encode(), C.c_void_p(buf.ctypes.data), cap)
+    if got < 0:
+        raise _lib.GimicB200Error(got, "format_e failed")
+    return buf[:got].tobytes()
 
 
 def _ld_real(x):
@@ -39,6 +57,16 @@ def _ld_real(x):
 
 def _ld_int(i):
     return f"{int(i):12d}"
+
+
+class _Text:
+    """text-mode write() on a binary file (the bulk number blocks are written as bytes)"""
+
+    def __init__(self, fb):
+        self.fb = fb
+
+    def write(self, s):
+        self.fb.write(s.encode("ascii"))
 
 
 def _vti_header(f, npts, qmin, step, name, ncomp):
@@ -63,44 +91,75 @@ def _vti_geometry(grid):
     return qmin, step
 
 
-def write_vti_scalar(path, grid, values):
-    """write_vtk_imagedata, vtkplot.f90:14-86: values[i + p1*(j + p2*k)], e14.6, line break when mod(l,4)==0"""
+def _cell_average_norm(v, p1, p2, p3):
+    """|J| averaged over the corners of each cell (vtkplot.f90:132-226); None for grids without cells"""
+    sl = [slice(0, -1), slice(1, None)]
+    if p1 > 1 and p2 > 1 and p3 > 1:
+        avg = sum(v[a, b, c] for a in sl for b in sl for c in sl) / 8.0
+    elif p1 > 1 and p2 > 1 and p3 == 1:
+        avg = sum(v[0:1, b, c] for b in sl for c in sl) / 4.0
+    elif p1 > 1 and p2 == 1 and p3 > 1:
+        avg = sum(v[a, 0:1, c] for a in sl for c in sl) / 4.0
+    elif p1 == 1 and p2 > 1 and p3 > 1:
+        avg = sum(v[a, b, 0:1] for a in sl for b in sl) / 4.0
+    else:
+        return None
+    return np.sqrt((avg ** 2).sum(-1)).ravel()
+
+
+def _vti_appended(path, grid, name, ncomp, data, cell=None):
+    """EXTRA (not a reference format): the same ImageData file with raw appended Float64 blocks instead of ASCII numbers --
+    8 bytes per value instead of 14 characters, no formatting cost; ParaView/VTK read both."""
     qmin, step = _vti_geometry(grid)
+    npts = grid.npts
+    ext = " ".join(str(v) for v in (0, npts[0] - 1, 0, npts[1] - 1, 0, npts[2] - 1))
+    blocks = [np.ascontiguousarray(data, dtype="<f8").ravel()]
+    head = ['<?xml version="1.0"?>', '<VTKFile type="ImageData" version="0.1" byte_order="LittleEndian" header_type="UInt64">',
+            f'  <ImageData WholeExtent="{ext}" Origin="{qmin[0]!r} {qmin[1]!r} {qmin[2]!r}" Spacing="{step[0]!r} {step[1]!r} {step[2]!r}">',
+            f'    <Piece Extent="{ext}">', f'      <PointData {"Vectors" if ncomp == 3 else "Scalars"}="{name}">',
+            f'        <DataArray Name="{name}" type="Float64" NumberOfComponents="{ncomp}" format="appended" offset="0"/>',
+            '      </PointData>']
+    if cell is not None:
+        off = 8 + blocks[0].nbytes
+        blocks.append(np.ascontiguousarray(cell, dtype="<f8").ravel())
+        head += ['      <CellData Scalars="cell_norm">',
+                 f'        <DataArray Name="cell_norm" type="Float64" NumberOfComponents="1" format="appended" offset="{off}"/>', '      </CellData>']
+    head += ['    </Piece>', '  </ImageData>', '  <AppendedData encoding="raw">']
+    with open(path, "wb") as fb:
+        fb.write(("\n".join(head) + "\n_").encode("ascii"))
+        for b in blocks:
+            fb.write(np.uint64(b.nbytes).tobytes()); fb.write(b.tobytes())
+        fb.write(b"\n  </AppendedData>\n</VTKFile>\n")
+
+
+def write_vti_scalar(path, grid, values, appended=False):
+    """write_vtk_imagedata, vtkplot.f90:14-86: values[i + p1*(j + p2*k)], e14.6, line break when mod(l,4)==0"""
     v = np.asarray(values, dtype=np.float64).ravel()
-    with open(path, "w") as f:
+    if appended:
+        return _vti_appended(path, grid, "scalars", 1, v)
+    qmin, step = _vti_geometry(grid)
+    with open(path, "wb") as fb:
+        f = _Text(fb)
         _vti_header(f, grid.npts, qmin, step, "scalars", 1)
-        out = []
-        for l, x in enumerate(v):
-            out.append(fortran_e(x, 14, 6))
-            if l % 4 == 0:
-                out.append("\n")
-        f.write("".join(out))
+        fb.write(format_e(v, 14, 6, 4, first=1))              # a line break after value l when mod(l,4)==0 (0-based)
         f.write("\n    </DataArray>\n    </PointData>\n    </Piece>\n    </ImageData>\n </VTKFile>\n")
 
 
-def write_vti_vector(path, grid, vec):
+def write_vti_vector(path, grid, vec, appended=False):
     """write_vtk_vector_imagedata, vtkplot.f90:88-234: 3e14.6 per point + CellData of cell-averaged |J|"""
-    qmin, step = _vti_geometry(grid)
     p1, p2, p3 = grid.npts
     v = np.asarray(vec, dtype=np.float64).reshape(p3, p2, p1, 3)
-    with open(path, "w") as f:
+    nrm = _cell_average_norm(v, p1, p2, p3)
+    if appended:
+        return _vti_appended(path, grid, "vectors", 3, v, nrm)
+    qmin, step = _vti_geometry(grid)
+    with open(path, "wb") as fb:
+        f = _Text(fb)
         _vti_header(f, grid.npts, qmin, step, "vectors", 3)
-        f.write("".join(fortran_e(a, 14, 6) + fortran_e(b, 14, 6) + fortran_e(c, 14, 6) + "\n" for a, b, c in v.reshape(-1, 3)))
+        fb.write(format_e(v, 14, 6, 3))
         f.write("\n    </DataArray>\n    </PointData>\n    <CellData Scalars=\"foo\">\n")
-        sl = [slice(0, -1), slice(1, None)]
-        if p1 > 1 and p2 > 1 and p3 > 1:
-            avg = sum(v[a, b, c] for a in sl for b in sl for c in sl) / 8.0
-        elif p1 > 1 and p2 > 1 and p3 == 1:
-            avg = sum(v[0:1, b, c] for b in sl for c in sl) / 4.0
-        elif p1 > 1 and p2 == 1 and p3 > 1:
-            avg = sum(v[a, 0:1, c] for a in sl for c in sl) / 4.0
-        elif p1 == 1 and p2 > 1 and p3 > 1:
-            avg = sum(v[a, b, 0:1] for a in sl for b in sl) / 4.0
-        else:
-            avg = None
-        if avg is not None:
-            nrm = np.sqrt((avg ** 2).sum(-1)).ravel()
-            f.write("".join(fortran_e(x, 14, 6) + "\n" for x in nrm))
+        if nrm is not None:
+            fb.write(format_e(nrm, 14, 6, 1))
         f.write("    </CellData>\n    </Piece>\n    </ImageData>\n </VTKFile>\n")
 
 
@@ -116,14 +175,15 @@ def _vtu_write(path, points, name, ncomp, data, cells):
     pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
     v = np.asarray(data, dtype=np.float64).reshape(pts.shape[0], ncomp)
     nc = cells.shape[0]
-    with open(path, "w") as f:
+    with open(path, "wb") as fb:
+        f = _Text(fb)
         f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n  <UnstructuredGrid>\n')
         f.write(f'    <Piece NumberOfPoints="{pts.shape[0]:10d}" NumberOfCells="{nc:10d}">\n      <Points>\n')
         f.write('        <DataArray type="Float32" NumberOfComponents="3" Format="ascii">\n')
-        f.write("".join("        " + "".join(fortran_e(x, 20, 10) for x in p) + "\n" for p in pts))
+        fb.write(format_e(pts, 20, 10, 3, prefix="        "))
         f.write('        </DataArray>\n      </Points>\n      <PointData Scalars="scalars">\n')
         f.write(f'        <DataArray Name="{name}" type="Float64" NumberOfComponents="{ncomp}" Format="ascii">\n')
-        f.write("".join("        " + "".join(fortran_e(x, 20, 10) for x in p) + "\n" for p in v))
+        fb.write(format_e(v, 20, 10, ncomp, prefix="        "))
         f.write('        </DataArray>\n      </PointData>\n      <Cells>\n        <DataArray type="Int32" Name="connectivity" Format="ascii">\n')
         f.write("".join("        " + "".join(f"{int(i) - 1:10d}" for i in c) + "\n" for c in cells))
         f.write('        </DataArray>\n        <DataArray type="Int32" Name="offsets" Format="ascii">\n        ')

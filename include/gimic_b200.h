@@ -178,6 +178,12 @@ int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrat
  * (spherical count when the file is over spherical components).  Host only. */
 int gimic_b200_convert_xdens(const char *xdens_text, int nbf, int nmat, const char *xdens_binary);
 
+/* Bulk formatting of n doubles with the Fortran edit descriptor Ew.d (vtkplot.f90 writes e14.6 / e20.10 for every value; at
+ * 256^3 points text formatting, not the GPU, is the wall-clock bottleneck).  Lines hold per_line values (the first line
+ * first_count values if first_count > 0), start with `prefix` (may be NULL) and end with a newline when complete.  Threaded
+ * over the host cores.  Returns the number of bytes written to out (capacity cap), or a negative GIMIC_B200_E* code. */
+long gimic_b200_format_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
+
 /* Cartesian -> spherical projection of cao2sao.f90:163-231 for angular momentum l (0..5), as used when opts.spherical is
  * set: po[(m + l) * ncart + c], m = -l..l, c in the standard (turbomole_order = 0) or Turbomole cartesian component order;
  * integer-valued rows, bug-compatible with the reference (see host_basis.cpp); host only. */

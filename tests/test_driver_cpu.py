@@ -144,3 +144,44 @@ def test_vti_writers_roundtrip(tmp_path):
     assert txt.count("\n") == 6 + g.n + 4 + (4 * 2 * 1) + 4          # header, vectors, CellData of (p1-1)(p2-1)(p3-1) cells, footer
     head = open(os.path.join(GOLD, "..", "golden", "open_shell_MOL")).readline()
     assert head.startswith("INTGRL")
+
+
+def test_native_bulk_formatter_equals_the_python_edit_descriptor():
+    """gimic_b200_format_e (threaded, std::to_chars) == fortran_e value by value: line grouping of the vti scalar block
+    (break after value l when l % 4 == 0), 3 per line, prefixed vtu rows; zeros, three-digit exponents, rounding carries"""
+    from gimic_b200.writers import fortran_e, format_e
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.normal(size=20000) * 10.0 ** rng.integers(-30, 30, size=20000),
+                        [0.0, -0.0, 1e-100, -3.5e120, 1.0, -1.0, 9.9999995e-5, 0.99999995, 123456.5, 0.1234565, 0.1234575]])
+    for w, d, per_line, first, prefix in [(14, 6, 4, 1, ""), (14, 6, 3, 0, ""), (20, 10, 3, 0, "        "), (14, 6, 1, 0, ""), (20, 10, 1, 0, "  ")]:
+        got = format_e(v, w, d, per_line, first, prefix).decode()
+        lines, line = [], []
+        for x in v:
+            line.append(fortran_e(x, w, d))
+            if len(line) == ((first or per_line) if not lines else per_line):
+                lines.append(prefix + "".join(line) + "\n"); line = []
+        assert got == "".join(lines) + (prefix + "".join(line) if line else ""), (w, d, per_line, first)
+    assert format_e([], 14, 6, 3) == b"" and fortran_e(1e-101, 14, 6) == "  0.100000-100" and fortran_e(1e200, 8, 6) == "*" * 8
+
+
+def test_vti_appended_extra_holds_the_same_numbers(tmp_path):
+    """--vtk appended (an extra, not a reference format): raw Float64 blocks at the offsets the header names"""
+    import re
+    from gimic_b200 import grids, writers
+    g = grids.std_grid([-1, -1, -1], [1, 0, 0], [0, 1, 0], [2, 2, 2], "even", spacing=[0.5, 1.0, 2.0])
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=(g.n, 3)); s = rng.normal(size=g.n)
+    writers.write_vti_vector(tmp_path / "jvec.vti", g, v, appended=True)
+    writers.write_vti_scalar(tmp_path / "jmod.vti", g, s, appended=True)
+    for name, arrs in (("jvec.vti", [v.ravel(), None]), ("jmod.vti", [s])):
+        raw = open(tmp_path / name, "rb").read()
+        head, data = raw.split(b'<AppendedData encoding="raw">\n_', 1)
+        offs = [int(x) for x in re.findall(rb'offset="(\d+)"', head)]
+        assert len(offs) == len(arrs) and b'header_type="UInt64"' in head
+        for off, ref in zip(offs, arrs):
+            nbytes = int(np.frombuffer(data[off:off + 8], np.uint64)[0])
+            got = np.frombuffer(data[off + 8:off + 8 + nbytes], "<f8")
+            if ref is not None:
+                assert np.array_equal(got, ref)
+            else:
+                assert got.size == 4 * 2 * 1 and (got >= 0).all()          # cell-averaged |J|
