@@ -435,6 +435,52 @@ def test_more_active_atoms_than_the_shared_memory_table(gb):
     g.close()
 
 
+@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106])
+def test_random_molecules_vs_oracle(gb, seed):
+    """randomised inputs: 2..40 atoms in a box of random size, every atom with its own random shell set (l = 0..4, 1..4
+    primitives, exponents from tight to diffuse so the screening radii differ widely), random component order, open or closed
+    shell, random option switches; points inside and far outside the molecule (tiles with no, few and all atoms active)"""
+    rng = np.random.default_rng(seed)
+    nat = int(rng.integers(2, 41))
+    box = rng.uniform(2.0, 25.0)
+    coords = rng.uniform(-box, box, size=(nat, 3)) + rng.uniform(-50, 50, size=3) * (seed % 2)   # odd seeds: far from the origin
+    nctr, ls, npf, xp, cc = [], [], [], [], []
+    for a in range(nat):
+        k = int(rng.integers(1, 6)); nctr.append(k)
+        for _ in range(k):
+            l = int(rng.integers(0, 5)); n = int(rng.integers(1, 5))
+            ls.append(l); npf.append(n)
+            xp += list(10.0 ** rng.uniform(-1.3, 2.0, size=n)); cc += list(rng.uniform(0.1, 1.0, size=n))
+    sh = dict(coords=coords, nctr_per_atom=np.array(nctr, np.int32), ctr_l=np.array(ls, np.int32), ctr_npf=np.array(npf, np.int32),
+              xp=np.array(xp), cc=np.array(cc))
+    nbf = int(sum((l + 1) * (l + 2) // 2 for l in ls))
+    uhf = bool(rng.integers(0, 2)); tm = bool(rng.integers(0, 2))
+    kw = dict(giao=bool(rng.integers(0, 4)), diamag=bool(rng.integers(0, 4)), paramag=bool(rng.integers(0, 4)))
+    thr = float(10.0 ** rng.uniform(-10, -5))
+    da = fixtures.dens_to_colmajor(fixtures.synthetic_density(nbf, seed=seed, general_p=bool(rng.integers(0, 2))))
+    db = fixtures.dens_to_colmajor(fixtures.synthetic_density(nbf, seed=seed + 1000, general_p=True)) if uhf else None
+    g = gb.Gimic.from_arrays(dens_alpha=da, dens_beta=db, turbomole_order=tm, screening_thrs=thr, **kw, **sh)
+    o = O.Oracle.from_arrays(dens_a=da, dens_b=db, turbomole_order=tm, screening_thrs=thr, **kw, **sh)
+    ctr = coords.mean(0)
+    r = np.vstack([ctr + rng.uniform(-box - 3, box + 3, size=(400, 3)), ctr + rng.uniform(-box - 40, box + 40, size=(150, 3)),
+                   coords[rng.integers(0, nat, size=50)] + rng.normal(scale=0.05, size=(50, 3))])
+    for sc in (("alpha", "beta", "total", "spindens") if uhf else ("total",)):
+        res = g.fields(r, np.array([0.3, -0.2, 0.9]), sc, tens=True, edens=True)
+        to, eo = o.ctensor(r, sc, want_edens=True)
+        what = f"seed {seed} {sc} nat={nat} nbf={nbf} uhf={uhf} tm={tm} {kw} thr={thr:.1e}"
+        # Random (unphysical) densities make single tensor components cancel to 1e-4 of the point's scale, and total/spindens
+        # are sums of alpha and beta parts of either sign: the 1e-10 bound is taken at the scale of the quantities that are
+        # summed (the largest component of the point, alpha and beta separately), where FP64 noise limits the oracle as well.
+        scale = np.abs(to).max(axis=1, keepdims=True)
+        if uhf:
+            scale = np.maximum(scale, np.maximum(np.abs(o.ctensor(r, "alpha")), np.abs(o.ctensor(r, "beta"))).max(axis=1, keepdims=True))
+        err = np.abs(res["tens"] - to) / (RTOL * np.maximum(np.abs(to), 1e-3 * scale) + ATOL)
+        assert err.max() <= 1.0, f"{what}: {err.max():.3g}"
+        if not uhf:
+            assert_close(res["edens"], eo, what + " edens")
+    g.close()
+
+
 def test_general_contraction_mol_file(gb, tmp_path):
     """INTGRL blocks with ncf > 1 (general contractions are split into segmented ones, intgrl.f90:172-216) and
     primitive lines that wrap over several records (list-directed reads)"""
