@@ -52,6 +52,26 @@ module b200_module
             import; type(c_ptr), value :: h; type(b200_grid) :: g; real(c_double) :: b(3), out7(7)
             integer(c_int), value :: spincase, what, jlo, jhi
         end function
+        ! the same sums for ngrids grids in one tensor pass (current-profile scans): b(3,ngrids), out7(7,ngrids)
+        integer(c_int) function gimic_b200_integrate_batch(h, ngrids, grids, b, spincase, what, out7) bind(c)
+            import; type(c_ptr), value :: h; integer(c_int), value :: ngrids, spincase, what
+            type(b200_grid) :: grids(*); real(c_double) :: b(3,*), out7(7,*)
+        end function
+        ! get_property (jfield.f90:584-929): part(5, nseg, natoms+1) partial sums per point block; seg_end = cumulative nelpts
+        integer(c_int) function gimic_b200_property(h, n, r, w, tens, natoms, coords, nseg, seg_end, part, flags) bind(c)
+            import; type(c_ptr), value :: h; integer(c_long), value :: n; integer(c_int), value :: natoms, nseg, flags
+            real(c_double) :: r(3,*), w(*), tens(9,*), coords(3,*), part(5,nseg,*); integer(c_long) :: seg_end(*)
+        end function
+        ! per-point integrands for one nucleus (centre3) or the magnetizability (centre3 = c_null_ptr): out4(4, n)
+        integer(c_int) function gimic_b200_property_integrand(h, n, r, tens, centre3, out4, flags) bind(c)
+            import; type(c_ptr), value :: h, centre3; integer(c_long), value :: n; integer(c_int), value :: flags
+            real(c_double) :: r(3,*), tens(9,*), out4(4,*)
+        end function
+        ! n values with the edit descriptor Ew.d into a character buffer (vtkplot.f90 writers); returns the bytes written
+        integer(c_long) function gimic_b200_format_e(n, v, w, d, per_line, first_count, prefix, out, cap) bind(c)
+            import; integer(c_long), value :: n, cap; integer(c_int), value :: w, d, per_line, first_count
+            real(c_double) :: v(*); character(kind=c_char) :: prefix(*), out(*)
+        end function
         function gimic_b200_last_error() bind(c) result(msg)
             import; type(c_ptr) :: msg
         end function
@@ -70,14 +90,15 @@ contains
     end function
 
     ! replaces new_basis + new_dens + read_dens in driver (gimic.F90:144-158)
-    subroutine b200_init(molfile, densfile, is_uhf, use_giao, use_diamag, use_paramag, use_screening, screen_thrs)
+    subroutine b200_init(molfile, densfile, is_uhf, use_giao, use_diamag, use_paramag, use_screening, screen_thrs, use_spherical)
         character(*), intent(in) :: molfile, densfile
-        logical, intent(in) :: is_uhf, use_giao, use_diamag, use_paramag, use_screening
+        logical, intent(in) :: is_uhf, use_giao, use_diamag, use_paramag, use_screening, use_spherical
         real(c_double), intent(in) :: screen_thrs
         type(b200_opts) :: o
         call gimic_b200_default_opts(o)
         o%uhf = merge(1, 0, is_uhf); o%giao = merge(1, 0, use_giao); o%diamag = merge(1, 0, use_diamag)
         o%paramag = merge(1, 0, use_paramag); o%screening = merge(1, 0, use_screening); o%screening_thrs = screen_thrs
+        o%spherical = merge(1, 0, use_spherical)
         if (gimic_b200_create(b200_handle, trim(molfile)//c_null_char, trim(densfile)//c_null_char, o) /= 0) then
             stop 'gimic_b200_create failed'
         end if
