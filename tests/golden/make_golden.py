@@ -144,6 +144,11 @@ def main():
             g["magnet"] = [float(v) for v in m[0]]
         grids[name] = g
         shutil.copyfile(os.path.join(t, "benzene", name, "gimic.inp"), os.path.join(OUT, "inputs", f"benzene_{name}.inp"))
+    # inputs of the remaining benzene tests (no stdout geometry block is parsed for them)
+    for name, fname in (("diamag-off", "gimic.inp"), ("giao-test", "gimic.inp"), ("paramag-off", "gimic.inp"),
+                        ("skip-jmod-integration", "gimic.inp"), ("vectors", "vectors.inp"), ("magnetizability", "gimic.inp")):
+        shutil.copyfile(os.path.join(t, "benzene", name, fname), os.path.join(OUT, "inputs", f"benzene_{name}.inp"))
+    shutil.copyfile(os.path.join(t, "benzene", "magnetizability", "coord.au"), os.path.join(OUT, "benzene_coord.au"))
     json.dump(grids, open(os.path.join(OUT, "benzene_grids.json"), "w"), indent=1)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):

@@ -197,8 +197,8 @@ BENZENE_INPUTS = sorted(f[:-4] for f in os.listdir(INPUTS) if f.startswith("benz
 
 @pytest.mark.parametrize("inp_name", BENZENE_INPUTS)
 def test_every_benzene_reference_input_runs_and_matches_the_oracle(tmp_path, cases, inp_name):
-    """All 13 test/benzene/* inputs (2d/3d grids, bond grids even/gauss/lobatto, the magnet / radius / rotation / spacing
-    keywords) through the driver.  The reference tree lacks the XDENS of these tests, so the densities are synthetic (nbf = 252
+    """All 19 test/benzene/* inputs (2d/3d/vectors grids, bond grids even/gauss/lobatto, the magnet / radius / rotation / spacing
+    keywords, diamag-off / paramag-off / giao-test / skip-jmod-integration, magnetizability with prop=on) through the driver.  The reference tree lacks the XDENS of these tests, so the densities are synthetic (nbf = 252
     on the real benzene MOL); the driver's numbers are compared with the oracle evaluated on the oracle's own grid for the same
     input: integrals at the printed 6 decimals, jvec files at their 6 printed digits."""
     from make_golden import read_vti
@@ -212,13 +212,30 @@ def test_every_benzene_reference_input_runs_and_matches_the_oracle(tmp_path, cas
     fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))
     shutil.copy(os.path.join(INPUTS, inp_name + ".inp"), d / "gimic.inp")
     I = _inp_mod.parse_file(str(d / "gimic.inp"))
+    import oracle_lib as O
+    _, coords = read_mol_geometry(str(d / "MOL"))
+    if I.grid_arg == "file":      # test/benzene/magnetizability: the NumGrid blobs are not in the reference tree -> a small stand-in
+        rng = np.random.default_rng(5)
+        counts = rng.integers(60, 120, size=coords.shape[0])
+        pts = np.vstack([coords[a] + rng.normal(scale=1.5, size=(c, 3)) for a, c in enumerate(counts)])
+        np.savetxt(d / "gridfile.grd", pts, fmt="%.10f"); np.savetxt(d / "grid_w.grd", rng.uniform(0, 0.1, size=pts.shape[0]), fmt="%.12e")
+        shutil.copy(os.path.join(GOLD, "benzene_coord.au"), d / "coord.au")
+        np.savetxt(d / "nelpts.info", np.column_stack([np.arange(1, len(counts) + 1), counts]), fmt="%d")
     out = io.StringIO()
     drv = Driver(str(d / "gimic.inp"), out=out)
     drv.run()
-    import oracle_lib as O
-    o = O.Oracle.from_files(str(d / "MOL"), str(xd), screening_thrs=I.get("Advanced.screening_thrs"))
+    o = O.Oracle.from_files(str(d / "MOL"), str(xd), screening_thrs=I.get("Advanced.screening_thrs"), giao=I.get("Advanced.GIAO"),
+                            diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"))
     assert o.nbf == 252
-    _, coords = read_mol_geometry(str(d / "MOL"))
+    if I.grid_arg == "file":
+        r2 = np.loadtxt(d / "gridfile.grd"); w2 = np.loadtxt(d / "grid_w.grd"); c2 = np.loadtxt(d / "coord.au")
+        assert np.allclose(c2, coords, atol=1e-6)          # the reference's coord.au is the MOL geometry
+        tot, _ = O.property(r2, w2, o.ctensor(r2), c2, counts)
+        m = re.findall(r"shielding constant    =\s+([-\d.]+)", out.getvalue())
+        assert len(m) == coords.shape[0] and np.allclose([float(x) for x in m], tot[:-1, 0:3].sum(1) / 3.0, atol=1.1e-6)
+        chi = re.search(r"isotropic magnetizability chi =\s+([-\d.]+)", out.getvalue())
+        assert abs(float(chi.group(1)) - tot[-1, 0:3].sum() / 3.0) < 1.1e-6
+        return
     og = _oracle_grid(I, coords)
     bb = og.magnet(I.get("magnet_axis"), I.get("magnet"))
     assert np.allclose(drv.magnet, bb, atol=1e-14)
