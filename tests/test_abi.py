@@ -143,3 +143,38 @@ def test_product_does_not_touch_the_oracle():
                     if re.search(r"oracle_lib|libgimic_oracle|gimic_oracle|\boracle/", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_links(L, tmp_path):
+    """include/gimic_b200.h compiles as C99 (no C++/torch types in the boundary) and a C caller of the legacy symbols
+    (what GimicInterface.cpp / gimic.pyx bind, gimic_interface.h:9-18) links against libgimic_b200.so; the host-only
+    entry points run without a GPU"""
+    import subprocess
+    from gimic_b200 import _lib
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "gimic_b200.h"
+int main(void) {
+    double a = 0.0, b = 2.0, pts[18], wgts[18];
+    int npts = 18, order = 9;
+    void (*legacy[])(void) = {(void (*)(void))gimic_init, (void (*)(void))gimic_finalize, (void (*)(void))gimic_set_uhf,
+        (void (*)(void))gimic_set_magnet, (void (*)(void))gimic_set_spin, (void (*)(void))gimic_set_screening,
+        (void (*)(void))gimic_calc_jtensor, (void (*)(void))gimic_calc_jvector, (void (*)(void))gimic_calc_modj};
+    gimic_b200_opts o;
+    gimic_b200_default_opts(&o);
+    mkgausspoints(&a, &b, &npts, &order, pts, wgts);
+    double rows[5 * 6];
+    if (gimic_b200_c2s_rows(2, 0, rows)) return 2;
+    printf("%d %d %.15f %.15f %g %s\n", (int)(sizeof legacy / sizeof legacy[0]), o.giao, pts[0], wgts[17], rows[2 * 6 + 0], gimic_b200_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libgimic_b200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    po, wo = O.gauss_points(0.0, 2.0, 18, 9)
+    assert out[0] == "9" and out[1] == "1" and abs(float(out[2]) - po[0]) < 1e-14 and abs(float(out[3]) - wo[17]) < 1e-14
+    assert float(out[4]) == -1.0            # d shell, m = 0 row: 2zz - xx - yy -> coefficient of xx
