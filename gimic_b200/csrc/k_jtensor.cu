@@ -31,6 +31,10 @@
 // in registers for the whole tile and need only a 4-lane shuffle reduction at the end.
 // mma.sync.m16n8k4.f64 lowers to 2 DMMA.8x8x4 on sm_100a (there is no FP64 tcgen05 kind).
 #include "kernels.cuh"
+#ifndef KS_UNROLL
+#define KS_UNROLL 8
+#endif
+constexpr int KSU = KS_UNROLL;   // unroll factor of the K-step loop (measured on the 1.2 M-point chunk: 2 -> 76.4 ms, 4 -> 74.4 ms, 8 -> 73.8 ms)
 
 namespace gb {
 
@@ -250,7 +254,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
             mbar_wait(bar_full + 8 * s, ph);
-#pragma unroll 4
+#pragma unroll KSU
             for (int ks = 0; ks < nks; ++ks) {
                 // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
                 const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
