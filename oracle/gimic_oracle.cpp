@@ -14,7 +14,11 @@
 //   test/open-shell/3d/reference/*.vti                (6 digits)
 //   test/open-shell/integration/reference/stdout      (6 decimals)
 // divj/edens have no reference implementation at this commit: parity unpinned
-// for those two quantities.
+// for those two quantities.  spherical=on (cao2sao.f90) is
+// restated statement by statement, but the reference has no golden for it (its
+// own comments call the scheme buggy): parity unpinned for that switch as well;
+// the spherical branch is tied to the golden-pinned cartesian branch by
+// tests/test_oracle_golden.py::test_spherical_oracle_equals_cartesian_oracle_with_folded_density.
 //
 // Every function cites the reference file:line it follows (paths relative to
 // the reference root).
