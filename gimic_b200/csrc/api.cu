@@ -56,6 +56,8 @@ struct gimic_b200_ctx {
     int *d_f2user = nullptr;
     double *d_dens[2] = {nullptr, nullptr};   // dens_t%da / %db in the XDENS layout
     double *d_op[4] = {nullptr, nullptr, nullptr, nullptr};   // contraction operands per spin case
+    double *d_opj[4] = {nullptr, nullptr, nullptr, nullptr};  // J = T.B path: one pair-plane (D, P.B) per spin case, for the field in opj_B
+    double opj_B[4][3] = {};
     int nq = gb::NQ, ldb = 0; long long plane_stride = 0;
     double bbox_lo[3] = {0, 0, 0}; double inv_cell = 1.0;
     size_t pool_max_bytes = (size_t)8 << 30;
@@ -77,6 +79,7 @@ struct gimic_b200_ctx {
         for (void *p : owned) cudaFree(p);
         for (int i = 0; i < 2; ++i) if (d_dens[i]) cudaFree(d_dens[i]);
         for (int i = 0; i < 4; ++i) if (d_op[i]) cudaFree(d_op[i]);
+        for (int i = 0; i < 4; ++i) if (d_opj[i]) cudaFree(d_opj[i]);
         for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &segs, &tiles, &panel, &fidx, &atab, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
         if (h_info) cudaFreeHost(h_info);
         if (h_segs) cudaFreeHost(h_segs);
@@ -213,6 +216,33 @@ int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
     return 0;
 }
 
+// Operand of the J = T.B path: the tensor is only ever contracted with B, so P_x, P_y, P_z enter as the single matrix
+// sum_b B_b P_b (jfield.f90:167-184 applied before instead of after the contraction).  Rebuilt when B changes.
+int get_operand_j(gimic_b200_ctx *c, int spincase, const double *B3, const double **op) {
+    const bool uhf = c->opts.uhf != 0;
+    if (!uhf) {
+        if (spincase == GIMIC_B200_BETA) return fail(GIMIC_B200_ESPIN, "ctensor(): beta current requested, but not open-shell system!");
+        if (spincase == GIMIC_B200_SPINDENS) return fail(GIMIC_B200_ESPIN, "ctensor(): spindens requested, but not open-shell system!");
+        spincase = GIMIC_B200_ALPHA;
+    }
+    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
+    const bool same = c->d_opj[spincase] && c->opj_B[spincase][0] == B3[0] && c->opj_B[spincase][1] == B3[1] && c->opj_B[spincase][2] == B3[2];
+    if (!same) {
+        const int nbf = c->hb.nbf;
+        if (!c->d_opj[spincase]) CUDA_TRY(cudaMalloc((void **)&c->d_opj[spincase], (size_t)c->plane_stride * sizeof(double)));
+        const double *A = c->d_dens[0], *Bm = nullptr; double sg = 0.0;
+        if (spincase == GIMIC_B200_BETA) A = c->d_dens[1];
+        if (spincase == GIMIC_B200_TOTAL) { Bm = c->d_dens[1]; sg = 1.0; }
+        if (spincase == GIMIC_B200_SPINDENS) { Bm = c->d_dens[1]; sg = -1.0; }
+        gb::launch_build_operand_j(c->d_opj[spincase], nbf, c->ldb, A, Bm, sg, c->d_f2user, B3, c->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 3; ++k) c->opj_B[spincase][k] = B3[k];
+    }
+    *op = c->d_opj[spincase];
+    return 0;
+}
+
 int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b, bool dens_on_device) {
     gb::finalize_basis(c->hb, c->opts.screening != 0, c->opts.screening_thrs);
     if (int rc = build_device_basis(c)) return rc;
@@ -246,12 +276,15 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
 
 // ---- the batched tensor pipeline ------------------------------------------------------------------
 // d_r: device, 3 x n (AoS).  d_tens: device 9 x n.  d_edens: device n or null.
-int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, double *d_tens, double *d_edens) {
+// jB3 / d_jvec non-null: the J = T.B path (3 x n output, operands (D, P.B)); d_tens is then unused.
+int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, double *d_tens, double *d_edens,
+                const double *jB3 = nullptr, double *d_jvec = nullptr) {
     using namespace gb;
     if (n <= 0) return 0;
     if (n > 2000000000L) return fail(GIMIC_B200_EINVAL, "more than 2e9 points in one call");
     const double *op = nullptr;
-    if (int rc = get_operand(c, spincase, &op)) return rc;
+    const bool jpath = d_jvec != nullptr;
+    if (int rc = jpath ? get_operand_j(c, spincase, jB3, &op) : get_operand(c, spincase, &op)) return rc;
     cudaStream_t st = c->stream;
     int ntiles = (int)((n + MT - 1) / MT);
     const bool prof = c->profiling;
@@ -336,8 +369,8 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         td.panel_off = (long long)off; td.fidx_off = (long long)foff; td.atab_off = (long long)aoff;
         off += d; foff += td.nact + td.nn; aoff += td.nruns;
         sum_nact += td.nact;
-        flops += 2.0 * MT * c->nq * (double)td.nact * td.nn;   // DMMA: K runs over the nact slots, N over the nn columns (multiples of 8)
-        if (giao) flops += 2.0 * MT * 3.0 * (double)td.nn * td.nruns;   // GIAO taps: 3 DFMA per accumulator element per active atom
+        flops += 2.0 * MT * (jpath ? 2 : c->nq) * (double)td.nact * td.nn;   // DMMA: K runs over the nact slots, N over the nn columns (multiples of 8)
+        if (giao) flops += 2.0 * MT * (jpath ? 1.0 : 3.0) * (double)td.nn * td.nruns;   // GIAO taps: 3 (J path: 1) DFMA per accumulator element per active atom
     }
     fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff);
     batch_start.push_back(ntiles);
@@ -376,6 +409,7 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>(); a.atab_pool = c->atab.as<TileAtom>(); a.geo = c->geo.as<TileGeo>();
         a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
         a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = perm; a.tens = d_tens; a.edens = d_edens;
+        a.jvec = d_jvec; for (int k = 0; k < 3; ++k) a.B[k] = jpath ? jB3[k] : 0.0;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
         launch_jtensor(a, c->opts.giao != 0, c->nsm, st);
         CUDA_TRY(cudaGetLastError());
@@ -519,8 +553,11 @@ int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const d
     cudaEventRecord(c->ev_call[0], st);
     const double *d_r = nullptr;
     if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    // Only J (and |J|, rho) wanted: contract with B before instead of after the GEMM -- 2 operand planes instead of 4 and one
+    // tap weight per row instead of three (compute_jvectors, jfield.f90:167-184, folded into the contraction).
+    const bool jpath = !tens && !acid && !divj && (jvec || jmod);
     double *d_tens = tens;
-    if (!dev || !tens) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
+    if (!jpath && (!dev || !tens)) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
     // scalar/vector field outputs on the device
     const size_t nf = (size_t)n;
     double *d_jvec = jvec, *d_jmod = jmod, *d_acid = acid, *d_edens = edens, *d_divj = divj;
@@ -530,9 +567,17 @@ int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const d
         d_jvec = jvec ? f : nullptr; d_jmod = jmod ? f + 3 * nf : nullptr; d_acid = acid ? f + 4 * nf : nullptr;
         d_edens = edens ? f + 5 * nf : nullptr; d_divj = divj ? f + 6 * nf : nullptr;
     }
-    if (int rc = run_tensors(c, n, d_r, spincase, d_tens, d_edens)) return rc;
+    if (jpath) {
+        if (!d_jvec) {   // |J| alone: J goes to scratch
+            if (c->jv6.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (jvec)");
+            d_jvec = c->jv6.as<double>();
+        }
+        if (int rc = run_tensors(c, n, d_r, spincase, nullptr, d_edens, B3, d_jvec)) return rc;
+        if (d_jmod) { gb::launch_jmod(n, d_r, d_jvec, B3, d_jmod, st); c->stats.launches += 1; }
+        if (!jvec) d_jvec = nullptr;
+    } else if (int rc = run_tensors(c, n, d_r, spincase, d_tens, d_edens)) return rc;
     if (c->profiling) cudaEventRecord(c->ev[0], st);
-    if (d_jvec || d_jmod || d_acid) {
+    if (!jpath && (d_jvec || d_jmod || d_acid)) {
         const double zero3[3] = {0, 0, 0};
         gb::launch_fields(n, d_r, d_tens, B3 ? B3 : zero3, d_jvec, d_jmod, d_acid, st);
         c->stats.launches += 1;

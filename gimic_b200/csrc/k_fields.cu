@@ -58,6 +58,25 @@ void launch_fields(long n, const double *r, const double *tens, const double *B3
     k_fields<<<(unsigned)((n + FB - 1) / FB), FB, 0, s>>>(n, r, tens, B3[0], B3[1], B3[2], jvec, jmod, acid);
 }
 
+// signed |J| from J alone (jfield.f90:446-489), for the J = T.B path that never forms the tensor
+__global__ void k_jmod(long n, const double *__restrict__ r, const double *__restrict__ jvec, double bx, double by, double bz,
+                       double *__restrict__ jmod) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double vx = jvec[3 * i], vy = jvec[3 * i + 1], vz = jvec[3 * i + 2];
+    double cx = r[3 * i], cy = r[3 * i + 1], cz = r[3 * i + 2];
+    double jm = sqrt(vx * vx + vy * vy + vz * vz);
+    const double d = bx * cx + by * cy + bz * cz;
+    cx -= d * bx; cy -= d * by; cz -= d * bz;
+    const double nx = by * cz - bz * cy, ny = bz * cx - bx * cz, nz = bx * cy - by * cx;   // cross_product(mag, coord)
+    if (nx * vx + ny * vy + nz * vz < 0.0) jm = -1.0 * jm;
+    jmod[i] = jm;
+}
+void launch_jmod(long n, const double *r, const double *jvec, const double *B3, double *jmod, cudaStream_t s) {
+    if (n <= 0) return;
+    k_jmod<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, r, jvec, B3[0], B3[1], B3[2], jmod);
+}
+
 // divj by central differences: r6 holds the 6 shifted copies (+x,-x,+y,-y,+z,-z) of every point
 __global__ void k_shift_points(long n, const double *__restrict__ r, double h, double *__restrict__ r6) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;

@@ -31,6 +31,7 @@
 // in registers for the whole tile and need only a 4-lane shuffle reduction at the end.
 // mma.sync.m16n8k4.f64 lowers to 2 DMMA.8x8x4 on sm_100a (there is no FP64 tcgen05 kind).
 #include "kernels.cuh"
+#include <type_traits>
 #ifndef KS_UNROLL
 #define KS_UNROLL 8
 #endif
@@ -85,9 +86,10 @@ constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 
 constexpr int ATAB_MAX = 1024;      // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
 constexpr int KMASK_WORDS = 512;    // atom-end bits for up to 16384 K steps = 65536 slots
 
-struct Smem {
+template <int NPP_>
+struct SmemT {
     static constexpr int A_DOUBLES = BK * LDP;
-    static constexpr int NPP = (NQ + 1) / 2;                 // pair-planes: (q0,q1) (q2,q3) (q4,q5) (q6,-)
+    static constexpr int NPP = NPP_;                         // pair-planes: tensor path (D,Px) (Py,Pz); J path (D, P.B)
     static constexpr int PP_DOUBLES = BK * LDB2;             // one pair-plane of a stage: [k][16 nu x 2 + pad]
     static constexpr int B_DOUBLES = NPP * PP_DOUBLES;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
@@ -97,6 +99,8 @@ struct Smem {
     static constexpr size_t BAR_OFF = KMASK_OFF + (size_t)KMASK_WORDS * 4;
     static constexpr size_t BYTES = BAR_OFF + 2 * STAGES * 8 + 16;
 };
+using Smem = SmemT<(NQ + 1) / 2>;   // tensor path
+using SmemJ = SmemT<1>;             // J = T.B path
 
 // Tile bookkeeping shared by both roles: every thread of the CTA calls this once per tile (two CTA barriers).
 __device__ __forceinline__ int next_tile(const JtensorArgs &a, int *s_tile) {
@@ -106,9 +110,8 @@ __device__ __forceinline__ int next_tile(const JtensorArgs &a, int *s_tile) {
     return *s_tile;
 }
 
-template <bool GIAO>
+template <class SM>
 __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_base, uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
-    using SM = Smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t git = 0;
     for (;;) {
@@ -376,15 +379,222 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
     }
 }
 
+template <bool GIAO>
+__device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const double *s_stage, double *s_rows, double *s_atab, uint32_t *s_kmask,
+                                              uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
+    using SM = SmemJ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = warp * 16;
+    uint32_t git = 0;
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        const int rowA = row0 + g, rowB = row0 + g + 8;
+        const bool vA = rowA < td.npts, vB = rowB < td.npts;
+        if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
+            if (t == 0) {
+                if (vA) { long o = a.perm[td.pt0 + rowA]; for (int i = 0; i < 3; ++i) a.jvec[3 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
+                if (vB) { long o = a.perm[td.pt0 + rowB]; for (int i = 0; i < 3; ++i) a.jvec[3 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
+            }
+            continue;
+        }
+        const int nact = td.nact, nn = td.nn;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
+        const uint32_t NIT = (uint32_t)nkc * nvc;
+        const double *panel = a.panel_pool + td.panel_off;
+        const long plane = (long)nact * LDP;
+        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
+        {
+        // ===================================== consumer warps =====================================
+        // Row table: lane t=0 of a quad owns row A, lane t=1 row B.  [0..2] running sums T_m = sum_b Tp(m,b) B_b, [3..5] V_d,
+        // [6] rho; [13..15] the point's absolute coordinates (as r enters jtensor.F90:112 and bfeval.f90:168-189).
+        double *rowA_s = s_rows + rowA * ROWLD, *rowB_s = s_rows + rowB * ROWLD;
+        if (t < 2) {
+            double *rs = t ? rowB_s : rowA_s;
+            const long p = td.pt0 + ((t ? vB : vA) ? (t ? rowB : rowA) : 0);
+#pragma unroll
+            for (int i = 0; i < 13; ++i) rs[i] = 0.0;
+            rs[13] = a.rsx[p]; rs[14] = a.rsy[p]; rs[15] = a.rsz[p];
+        }
+        if (GIAO && threadIdx.x == 0) {   // tile centre, same expression as k_basis; read in the epilogue (after the bar.sync below)
+            const TileGeo tg = a.geo[td.geo];
+            s_rows[MT * ROWLD] = 0.5 * (tg.lox + tg.hix); s_rows[MT * ROWLD + 1] = 0.5 * (tg.loy + tg.hiy); s_rows[MT * ROWLD + 2] = 0.5 * (tg.loz + tg.hiz);
+        }
+        __syncwarp();
+        double acc[2][2][4];                                        // planes D and P.B
+        double zac[2][4];                                           // S = (B x r) . Z (GIAO taps with per-row weights)
+        // w = B x r of this thread's two rows: B.(r x Y) = Y.(B x r)
+        double wAx = 0, wAy = 0, wAz = 0, wBx = 0, wBy = 0, wBz = 0;
+        if (GIAO) {
+            const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+            const double ax = rowA_s[13], ay = rowA_s[14], az = rowA_s[15], cx = rowB_s[13], cy = rowB_s[14], cz = rowB_s[15];
+            wAx = by * az - bz * ay; wAy = bz * ax - bx * az; wAz = bx * ay - by * ax;
+            wBx = by * cz - bz * cy; wBy = bz * cx - bx * cz; wBz = bx * cy - by * cx;
+        }
+        const int nruns = td.nruns;
+        const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
+        double curx = 0, cury = 0, curz = 0;
+        int ia = 0;
+        int eslot[2][2];                                            // epilogue: K slot of this thread's 4 nu columns
+        if (GIAO) {
+            // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
+            const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
+            const int ctid = threadIdx.x, nwords = (nact / 4 + 31) / 32;
+            for (int w = ctid; w < nwords; w += NCONSUMER_WARPS * 32) s_kmask[w] = 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+            for (int r = ctid; r < nruns; r += NCONSUMER_WARPS * 32) {
+                const double2 t0 = __ldg(atab + 2 * r), t1 = __ldg(atab + 2 * r + 1);
+                if (r < ATAB_MAX) { s_atab[3 * r] = t0.x; s_atab[3 * r + 1] = t0.y; s_atab[3 * r + 2] = t1.x; }
+                const int e = __double2loint(t1.y) - 1;
+                atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+            if (nruns > ATAB_MAX) { atd = reinterpret_cast<const double *>(atab); astr = 4; }
+        }
+        int kc = 0, vc = 0;
+        for (uint32_t it = 0; it < NIT; ++it) {
+            const uint32_t gi = git + it, s = gi % STAGES, ph = (gi / STAGES) & 1;
+            if (kc == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
+                if (GIAO) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) zac[h][i] = 0.0;
+                    ia = 0;
+                    curx = atd[0]; cury = atd[1]; curz = atd[2];
+                }
+                // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) eslot[h][j] = nlist[min(vc * NV + h * 8 + 2 * t + j, nn - 1)];
+            }
+            const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
+            const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
+            const int nks = min(BK, nact - kc * BK) / 4;
+            const bool h1 = vc * NV + 8 < nn;                       // second n8 tile of this chunk holds real columns
+            const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
+            const double *sB = sA + SM::A_DOUBLES;
+            mbar_wait(bar_full + 8 * s, ph);
+#pragma unroll KSU
+            for (int ks = 0; ks < nks; ++ks) {
+                // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
+                const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
+                const double a0 = pa[0], a1 = pa[8];
+                const double2 *pb = reinterpret_cast<const double2 *>(sB + (ks * 4 + t) * LDB2) + g;   // one LDS.128 = both planes of a pair
+#pragma unroll
+                for (int pp = 0; pp < SM::NPP; ++pp)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !h1) continue;
+                        const double2 b = pb[pp * (SM::PP_DOUBLES / 2) + h * 8];
+                        mma_16x8x4_f64(acc[0][h], a0, a1, b.x);
+                        mma_16x8x4_f64(acc[1][h], a0, a1, b.y);
+                    }
+                if (GIAO && ((m8 >> ks) & 1u)) {
+                    // last K step of an atom: S += C_A * ((B x r) . (R_A - R_next)), one weight per row (see the header)
+                    const double oA = wAx * curx + wAy * cury + wAz * curz, oB = wBx * curx + wBy * cury + wBz * curz;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        zac[h][0] = fma(oA, acc[0][h][0], zac[h][0]); zac[h][1] = fma(oA, acc[0][h][1], zac[h][1]);
+                        zac[h][2] = fma(oB, acc[0][h][2], zac[h][2]); zac[h][3] = fma(oB, acc[0][h][3], zac[h][3]);
+                    }
+                    ia = min(ia + 1, nruns - 1);
+                    const double *nx = atd + astr * ia;
+                    curx = nx[0]; cury = nx[1]; curz = nx[2];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
+            if (++kc == nkc) {
+                // ---- fused epilogue for nu chunk vc ---------------------------------------------
+                double eA[7], eB[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) { eA[i] = 0.0; eB[i] = 0.0; }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (h == 1 && !h1) continue;
+                        const int slot = eslot[h][j];                         // K slot (= panel row) of this nu column
+                        const double *pe = panel + (long)slot * LDP;
+                        double Rx = 0, Ry = 0, Rz = 0;
+                        if (GIAO) { const int f = fidx[slot]; Rx = a.fR[f]; Ry = a.fR[a.nbf + f]; Rz = a.fR[2 * a.nbf + f]; }
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int row = rr ? rowB : rowA;
+                            double *e = rr ? eB : eA;
+                            const int ci = 2 * rr + j;
+                            const double e0 = pe[row], e1 = pe[plane + row], e2 = pe[2 * plane + row], e3 = pe[3 * plane + row];
+                            const double x0 = acc[0][h][ci];
+                            const double t0 = x0 * e0;
+                            e[6] += t0;
+                            double z = acc[1][h][ci];
+                            if (GIAO) {
+                                e[3] += Rx * t0; e[4] += Ry * t0; e[5] += Rz * t0;
+                                const double cenx = s_rows[MT * ROWLD], ceny = s_rows[MT * ROWLD + 1], cenz = s_rows[MT * ROWLD + 2];
+                                const double wx = rr ? wBx : wAx, wy = rr ? wBy : wAy, wz = rr ? wBz : wAz;
+                                z += (wx * (Rx - cenx) + wy * (Ry - ceny) + wz * (Rz - cenz)) * x0 - zac[h][ci];   // (B x r) . Y
+                            }
+                            e[0] += z * e1; e[1] += z * e2; e[2] += z * e3;
+                        }
+                    }
+                // reduce over the 4 lanes of the quad (they hold different nu) and add into the row table
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    eA[i] += __shfl_xor_sync(0xffffffffu, eA[i], 1); eA[i] += __shfl_xor_sync(0xffffffffu, eA[i], 2);
+                    eB[i] += __shfl_xor_sync(0xffffffffu, eB[i], 1); eB[i] += __shfl_xor_sync(0xffffffffu, eB[i], 2);
+                }
+                if (t < 2) {
+                    double *rs = t ? rowB_s : rowA_s;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) rs[i] += t ? eB[i] : eA[i];
+                }
+                kc = 0; ++vc;
+            }
+        }
+
+        // ---- finalise and store ---------------------------------------------------------------------
+        if (t < 2) {
+            const bool v = t ? vB : vA;
+            if (v) {
+                const double *e = t ? rowB_s : rowA_s;
+                const double px = e[13], py = e[14], pz = e[15];
+                const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+                // J_m = sum_b ct(m,b) B_b:  1/2 [T_m + (V x B)_m]  +  1/2 rho (B x r)_m   (jtensor.F90:209-235 contracted with B)
+                double jx = e[0] + (e[4] * bz - e[5] * by), jy = e[1] + (e[5] * bx - e[3] * bz), jz = e[2] + (e[3] * by - e[4] * bx);
+                jx = a.paramag ? 0.5 * jx : 0.0; jy = a.paramag ? 0.5 * jy : 0.0; jz = a.paramag ? 0.5 * jz : 0.0;
+                const double rho = e[6];
+                if (a.diamag) {
+                    jx += 0.5 * rho * (by * pz - bz * py); jy += 0.5 * rho * (bz * px - bx * pz); jz += 0.5 * rho * (bx * py - by * px);
+                }
+                const long o = a.perm[td.pt0 + (t ? rowB : rowA)];
+                a.jvec[3 * o] = jx; a.jvec[3 * o + 1] = jy; a.jvec[3 * o + 2] = jz;
+                if (a.edens) a.edens[o] = rho;
+            }
+        }
+        }
+        git += NIT;
+    }
+}
+
 // Pipeline: warps 8-11 are producers.  Per stage they (1) wait for the slot to be released by the 8 consumer warps
 // (empty barrier), (2) issue ONE bulk-TMA copy of the contiguous Phi panel rows [kc*BK, +kcnt) x 132 doubles
 // (expect_tx on the full barrier) and (3) gather the density elements B_q[fidx[k]][fidx[nu]] of all NQ planes with
 // 8-byte cp.async, whose completion arrives on the same full barrier.  Consumer warps only wait(full) -> LDS + DMMA ->
 // arrive(empty); nobody executes a CTA-wide barrier inside a tile.  The two roles are separate code paths so that
 // setmaxnreg can give the consumers 232 registers (ptxas budgets each path by the setmaxnreg that dominates it).
-template <bool GIAO>
+template <bool GIAO, bool JVEC>
 __global__ void __launch_bounds__(NTHREADS, 1) k_jtensor(JtensorArgs a) {
-    using SM = Smem;
+    using SM = typename std::conditional<JVEC, SmemJ, Smem>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_stage = reinterpret_cast<double *>(smem_raw);
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -397,24 +607,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_jtensor(JtensorArgs a) {
     __syncthreads();
     if ((threadIdx.x >> 5) >= NCONSUMER_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
-        producer_role<GIAO>(a, s_base, bar_full, bar_empty, s_tile);
+        producer_role<SM>(a, s_base, bar_full, bar_empty, s_tile);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-        consumer_role<GIAO>(a, s_stage, reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF),
-                            reinterpret_cast<uint32_t *>(smem_raw + SM::KMASK_OFF), bar_full, bar_empty, s_tile);
+        double *rows = reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), *atab = reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF);
+        uint32_t *kmask = reinterpret_cast<uint32_t *>(smem_raw + SM::KMASK_OFF);
+        if (JVEC) consumer_role_j<GIAO>(a, s_stage, rows, atab, kmask, bar_full, bar_empty, s_tile);
+        else consumer_role<GIAO>(a, s_stage, rows, atab, kmask, bar_full, bar_empty, s_tile);
     }
 }
 
 size_t jtensor_smem_bytes() { return Smem::BYTES; }
 
+template <bool GIAO, bool JVEC>
+static void launch_one(const JtensorArgs &a, int grid, cudaStream_t s) {
+    constexpr size_t bytes = JVEC ? SmemJ::BYTES : Smem::BYTES;
+    // per-device function attribute (a process may hold contexts on several GPUs): cheap enough to set on every launch
+    cudaFuncSetAttribute(k_jtensor<GIAO, JVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_jtensor<GIAO, JVEC><<<grid, NTHREADS, bytes, s>>>(a);
+}
+
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;
-    // per-device function attribute (a process may hold contexts on several GPUs): cheap enough to set on every launch
-    if (giao) cudaFuncSetAttribute(k_jtensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::BYTES);
-    else cudaFuncSetAttribute(k_jtensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::BYTES);
-    int grid = a.ntiles < nsm ? a.ntiles : nsm;
-    if (giao) k_jtensor<true><<<grid, NTHREADS, Smem::BYTES, s>>>(a);
-    else k_jtensor<false><<<grid, NTHREADS, Smem::BYTES, s>>>(a);
+    const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+    const bool jv = a.jvec != nullptr;   // J = T.B path: operands are ONE pair-plane (D, sum_b B_b P_b)
+    if (giao) { if (jv) launch_one<true, true>(a, grid, s); else launch_one<true, false>(a, grid, s); }
+    else { if (jv) launch_one<false, true>(a, grid, s); else launch_one<false, false>(a, grid, s); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,6 +655,27 @@ __global__ void k_build_operand(double *__restrict__ out, int nbf, int ldb, long
     }
     for (int pp = 0; pp < 2; ++pp) *reinterpret_cast<double2 *>(out + pp * plane_stride + dst) = make_double2(v[2 * pp], v[2 * pp + 1]);
 }
+// J = T.B path: ONE pair-plane (D, B_x P_x + B_y P_y + B_z P_z): the tensor is only ever contracted with this field direction.
+__global__ void k_build_operand_j(double *__restrict__ out, int nbf, int ldb, const double *__restrict__ srcA, const double *__restrict__ srcB,
+                                  double signB, const int *__restrict__ f2user, double bx, double by, double bz) {
+    const int nu = blockIdx.x * blockDim.x + threadIdx.x, mu = blockIdx.y;
+    if (nu >= nbf) return;
+    const long un = f2user[nu], um = f2user[mu];
+    const long src = um + (long)nbf * un, nn = (long)nbf * nbf;
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[q] = srcA[q * nn + src];
+        if (srcB) v[q] += signB * srcB[q * nn + src];
+    }
+    *reinterpret_cast<double2 *>(out + 2 * ((long)mu * ldb + nu)) = make_double2(v[0], bx * v[1] + by * v[2] + bz * v[3]);
+}
+void launch_build_operand_j(double *out, int nbf, int ldb, const double *srcA, const double *srcB, double signB, const int *f2user,
+                            const double *B3, cudaStream_t s) {
+    dim3 grid((nbf + 127) / 128, nbf);
+    k_build_operand_j<<<grid, 128, 0, s>>>(out, nbf, ldb, srcA, srcB, signB, f2user, B3[0], B3[1], B3[2]);
+}
+
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
                           const int *f2user, cudaStream_t s) {
     dim3 grid((nbf + 127) / 128, nbf);

@@ -81,6 +81,7 @@ struct JtensorArgs {
     const double *fR; int nbf;
     const double *rsx, *rsy, *rsz; const int *perm;
     double *tens; double *edens;                            // outputs in user point order (edens may be null)
+    double *jvec; double B[3];                              // J = T.B path (jvec != null): 3 x n output instead of tens, field direction
     int paramag, diamag;
 };
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
@@ -89,6 +90,9 @@ size_t jtensor_smem_bytes();
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
                           const int *f2user, cudaStream_t s);
 
+void launch_build_operand_j(double *out, int nbf, int ldb, const double *srcA, const double *srcB, double signB, const int *f2user,
+                            const double *B3, cudaStream_t s);
+void launch_jmod(long n, const double *r, const double *jvec, const double *B3 /*host*/, double *jmod, cudaStream_t s);
 void launch_fields(long n, const double *r, const double *tens, const double *B3 /*host values*/, double *jvec, double *jmod, double *acid, cudaStream_t s);
 void launch_divj(long n, const double *jv6 /* [6][n][3] shifted jvecs */, double h, double *divj, cudaStream_t s);
 void launch_shift_points(long n, const double *r, double h, double *r6, cudaStream_t s);

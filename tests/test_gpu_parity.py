@@ -478,7 +478,67 @@ def test_random_molecules_vs_oracle(gb, seed):
         assert err.max() <= 1.0, f"{what}: {err.max():.3g}"
         if not uhf:
             assert_close(res["edens"], eo, what + " edens")
+        Bf = np.array([0.3, -0.2, 0.9])
+        jerr = np.abs(g.fields(r, Bf, sc, jvec=True)["jvec"] - O.jvectors(to, Bf)) / (RTOL * np.maximum(np.abs(O.jvectors(to, Bf)), 1e-3 * scale) + ATOL)
+        assert jerr.max() <= 1.0, f"{what} J path: {jerr.max():.3g}"
     g.close()
+
+
+def _jscale_close(j, jref, tref, what):
+    """J = T.B compared at the scale of the tensor components that are summed (1e-10 of the point's largest |T B| term)"""
+    scale = np.abs(tref).max(axis=1, keepdims=True)
+    err = np.abs(j - jref) / (RTOL * np.maximum(np.abs(jref), 1e-3 * scale) + ATOL)
+    assert err.max() <= 1.0, f"{what}: {err.max():.3g}"
+
+
+def test_jvec_only_path_vs_oracle(gb, cases, c4h4, opensh):
+    """fields(jvec/jmod without tens/acid) takes the J = T.B kernel (operands (D, sum_b B_b P_b), one tap weight per row):
+    same J, signed |J| and rho as contracting the oracle's tensor with B afterwards (compute_jvectors, jfield.f90:167-184)"""
+    rng = np.random.default_rng(12)
+    r = np.vstack([rng.uniform(-5, 5, size=(700, 3)), rng.uniform(-30, 30, size=(100, 3))])
+    for B in (np.array([0.0, 0.0, 1.0]), np.array([0.3, -0.5, 0.8]), np.array([-1.0, 0.0, 0.0])):
+        g, o = c4h4
+        tref, eref = o.ctensor(r, "total", want_edens=True)
+        f = g.fields(r, B, "total", jvec=True, jmod=True, edens=True)
+        jref = O.jvectors(tref, B)
+        _jscale_close(f["jvec"], jref, tref, f"c4h4 J path B={B}")
+        assert_close(f["edens"], eref, "J path edens")
+        jm = O.jmod_signed(r, jref, B)
+        big = np.abs(jm) > 1e-9 * np.abs(jm).max()                      # the sign of a vanishing |J| is noise
+        assert np.allclose(f["jmod"][big], jm[big], rtol=1e-9, atol=1e-12)
+        only = g.fields(r, B, "total", jmod=True)                        # |J| alone (J to scratch)
+        assert np.array_equal(only["jmod"], f["jmod"]) and set(only) == {"jmod"}
+        full = g.fields(r, B, "total", tens=True, jvec=True)             # tensor path for comparison
+        _jscale_close(f["jvec"], full["jvec"], tref, "J path vs tensor path")
+    g, o = opensh
+    B = np.array([0.2, 0.1, -0.97])
+    for sc in ("alpha", "beta", "total", "spindens"):
+        tref = o.ctensor(r, sc)
+        scale_t = np.maximum(np.abs(o.ctensor(r, "alpha")), np.abs(o.ctensor(r, "beta")))
+        _jscale_close(g.fields(r, B, sc, jvec=True)["jvec"], O.jvectors(tref, B), np.maximum(np.abs(tref), scale_t), f"open shell {sc}")
+    for kw in (dict(giao=False), dict(diamag=False), dict(paramag=False), dict(screening=False)):
+        m, x = cases["c4h4"]["mol"], cases["c4h4"]["xdens"]
+        g2 = gb.Gimic(m, x, screening_thrs=1e-8, **kw)
+        o2 = O.Oracle.from_files(m, x, screening_thrs=1e-8, **kw)
+        tref = o2.ctensor(r[:300], "total")
+        _jscale_close(g2.fields(r[:300], B, "total", jvec=True)["jvec"], O.jvectors(tref, B), np.maximum(np.abs(tref), 1e-6), f"J path {kw}")
+        g2.close()
+
+
+def test_jvec_only_path_far_from_origin_and_large(gb):
+    """J path on the synthetic ring (atoms 120 bohr from the origin: the per-row tap weights are built from position
+    differences) and on a 42-centre flake (tiles with hundreds of active functions)"""
+    rng = np.random.default_rng(3)
+    B = np.array([0.1, 0.2, 0.97])
+    for geometry, natoms, npts in (("ring", 30, 400), ("flake", 42, 300)):
+        sh, dens, nbf = fixtures.synthetic_case(natoms, geometry, seed=77, general_p=True)
+        flat = fixtures.dens_to_colmajor(dens)
+        g = gb.Gimic.from_arrays(dens_alpha=flat, **sh); o = O.Oracle.from_arrays(dens_a=flat, **sh)
+        ctr = sh["coords"][rng.integers(0, natoms, size=npts)]
+        r = ctr + rng.normal(scale=2.5, size=(npts, 3))
+        tref = o.ctensor(r)
+        _jscale_close(g.fields(r, B, "total", jvec=True)["jvec"], O.jvectors(tref, B), tref, f"{geometry} J path")
+        g.close()
 
 
 def test_general_contraction_mol_file(gb, tmp_path):
