@@ -86,11 +86,13 @@ constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 
 constexpr int ATAB_MAX = 1024;      // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
 constexpr int KMASK_WORDS = 512;    // atom-end bits for up to 16384 K steps = 65536 slots
 
-template <int NPP_>
+template <int NPP_, int NV_, int LDB_>
 struct SmemT {
     static constexpr int A_DOUBLES = BK * LDP;
     static constexpr int NPP = NPP_;                         // pair-planes: tensor path (D,Px) (Py,Pz); J path (D, P.B)
-    static constexpr int PP_DOUBLES = BK * LDB2;             // one pair-plane of a stage: [k][16 nu x 2 + pad]
+    static constexpr int NVC = NV_;                          // nu columns per accumulator chunk
+    static constexpr int LDB = LDB_;                         // smem row stride (doubles) of a pair-plane B tile: NVC x 2 + 4 pad
+    static constexpr int PP_DOUBLES = BK * LDB;              // one pair-plane of a stage: [k][NVC nu x 2 + pad]
     static constexpr int B_DOUBLES = NPP * PP_DOUBLES;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
     static constexpr size_t ROW_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;        // per-row epilogue sums + point coordinates
@@ -99,8 +101,9 @@ struct SmemT {
     static constexpr size_t BAR_OFF = KMASK_OFF + (size_t)KMASK_WORDS * 4;
     static constexpr size_t BYTES = BAR_OFF + 2 * STAGES * 8 + 16;
 };
-using Smem = SmemT<(NQ + 1) / 2>;   // tensor path
-using SmemJ = SmemT<1>;             // J = T.B path
+constexpr int NVJ = 32, LDB2J = 68;                // J path: 4 n8 tiles per chunk; 68 doubles = 34 16-byte units = 2 (mod 8) -> conflict-free LDS.128
+using Smem = SmemT<(NQ + 1) / 2, NV, LDB2>;        // tensor path
+using SmemJ = SmemT<1, NVJ, LDB2J>;                // J = T.B path: same 16 KB of B per stage, twice the columns per A fragment
 
 // Tile bookkeeping shared by both roles: every thread of the CTA calls this once per tile (two CTA barriers).
 __device__ __forceinline__ int next_tile(const JtensorArgs &a, int *s_tile) {
@@ -120,14 +123,15 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
         const TileDesc td = a.tiles[tile];
         if (td.nact == 0) continue;
         const int nact = td.nact, nn = td.nn;
-        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + SM::NVC - 1) / SM::NVC;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
         const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
         {
         // ===================================== producer warps =====================================
         const int pw = warp - NCONSUMER_WARPS;
-        const int ldn = lane & 15, ldk0 = (lane >> 4) + 2 * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0+8, ...
+        constexpr int LPW = 32 / SM::NVC > 0 ? 32 / SM::NVC : 1;    // k rows covered by one warp per pass (2 for 16 columns, 1 for 32)
+        const int ldn = lane % SM::NVC, ldk0 = lane / SM::NVC + LPW * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0 + LPW*4, ...
         int kc = 0, vc = 0;
         long nu = fidx[nlist[min(ldn, nn - 1)]];
         for (uint32_t itl = 0; itl < NIT; ++itl) {
@@ -139,19 +143,19 @@ __device__ __forceinline__ void producer_role(const JtensorArgs &a, uint32_t s_b
                 mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kcnt * LDP * 8));
                 tma_bulk_g2s(sA, panel + (long)kc * BK * LDP, (uint32_t)(kcnt * LDP * 8), bar_full + 8 * s);
             }
-            const bool nu_ok = vc * NV + ldn < nn;
+            const bool nu_ok = vc * SM::NVC + ldn < nn;
             const double *srcB = a.Bop + 2 * nu;
             const uint32_t dstB = sB + (uint32_t)(ldn * 16);
 #pragma unroll 4
-            for (int k = ldk0; k < (nu_ok ? kcnt : 0); k += 2 * NPRODUCER_WARPS) {
+            for (int k = ldk0; k < (nu_ok ? kcnt : 0); k += LPW * NPRODUCER_WARPS) {
                 const long mu = fidx[kc * BK + k];
                 const double *src = srcB + 2 * mu * a.ldb;
-                const uint32_t dst = dstB + (uint32_t)(k * LDB2 * 8);
+                const uint32_t dst = dstB + (uint32_t)(k * SM::LDB * 8);
 #pragma unroll
                 for (int pp = 0; pp < SM::NPP; ++pp) cp_async_16(dst + (uint32_t)(pp * SM::PP_DOUBLES * 8), src + pp * a.plane_stride);
             }
             cp_async_arrive_noinc(bar_full + 8 * s);
-            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[nlist[min(vc * NV + ldn, nn - 1)]]; }
+            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) nu = fidx[nlist[min(vc * SM::NVC + ldn, nn - 1)]]; }
         }
         }
         git += NIT;
@@ -401,7 +405,7 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
             continue;
         }
         const int nact = td.nact, nn = td.nn;
-        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NVJ - 1) / NVJ;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
         const long plane = (long)nact * LDP;
@@ -423,8 +427,9 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
             s_rows[MT * ROWLD] = 0.5 * (tg.lox + tg.hix); s_rows[MT * ROWLD + 1] = 0.5 * (tg.loy + tg.hiy); s_rows[MT * ROWLD + 2] = 0.5 * (tg.loz + tg.hiz);
         }
         __syncwarp();
-        double acc[2][2][4];                                        // planes D and P.B
-        double zac[2][4];                                           // S = (B x r) . Z (GIAO taps with per-row weights)
+        constexpr int NH = NVJ / 8;                                 // n8 tiles per chunk
+        double acc[2][NH][4];                                       // planes D and P.B
+        double zac[NH][4];                                          // S = (B x r) . Z (GIAO taps with per-row weights)
         // w = B x r of this thread's two rows: B.(r x Y) = Y.(B x r)
         double wAx = 0, wAy = 0, wAz = 0, wBx = 0, wBy = 0, wBz = 0;
         if (GIAO) {
@@ -437,7 +442,7 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
         const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
         double curx = 0, cury = 0, curz = 0;
         int ia = 0;
-        int eslot[2][2];                                            // epilogue: K slot of this thread's 4 nu columns
+        int eslot[NVJ / 8][2];                                      // epilogue: K slot of this thread's nu columns
         if (GIAO) {
             // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
             const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
@@ -460,12 +465,12 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < NH; ++h)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
                 if (GIAO) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < NH; ++h)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) zac[h][i] = 0.0;
                     ia = 0;
@@ -473,37 +478,51 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
                 }
                 // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < NH; ++h)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) eslot[h][j] = nlist[min(vc * NV + h * 8 + 2 * t + j, nn - 1)];
+                    for (int j = 0; j < 2; ++j) eslot[h][j] = nlist[min(vc * NVJ + h * 8 + 2 * t + j, nn - 1)];
             }
             const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
             const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
             const int nks = min(BK, nact - kc * BK) / 4;
-            const bool h1 = vc * NV + 8 < nn;                       // second n8 tile of this chunk holds real columns
+            const int nh = min(NH, (nn - vc * NVJ) / 8);            // n8 tiles of this chunk that hold real columns (nn is a multiple of 8)
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
             mbar_wait(bar_full + 8 * s, ph);
+            // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b = B[k t][n g] (one LDS.128 = both planes).
+            // Software-pipelined by hand: the fragments of step ks+1 are loaded before the MMAs of step ks (the tap branch between
+            // the steps keeps the compiler from doing it; ncu showed every DMMA waiting on its own LDS, 29 % short-scoreboard stalls)
+            const double *pa0 = sA + t * LDP + row0 + g;
+            const double2 *pb0 = reinterpret_cast<const double2 *>(sB + t * LDB2J) + g;
+            double a0 = pa0[0], a1 = pa0[8];
+            double2 bf[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) bf[h] = pb0[h * 8];
 #pragma unroll KSU
             for (int ks = 0; ks < nks; ++ks) {
-                // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
-                const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
-                const double a0 = pa[0], a1 = pa[8];
-                const double2 *pb = reinterpret_cast<const double2 *>(sB + (ks * 4 + t) * LDB2) + g;   // one LDS.128 = both planes of a pair
+                double na0 = 0, na1 = 0;
+                double2 nb[NH];
+                if (ks + 1 < nks) {
+                    const double *pa = pa0 + (ks + 1) * 4 * LDP;
+                    na0 = pa[0]; na1 = pa[8];
+                    const double2 *pb = pb0 + (ks + 1) * 4 * (LDB2J / 2);
 #pragma unroll
-                for (int pp = 0; pp < SM::NPP; ++pp)
+                    for (int h = 0; h < NH; ++h) nb[h] = pb[h * 8];
+                }
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && !h1) continue;
-                        const double2 b = pb[pp * (SM::PP_DOUBLES / 2) + h * 8];
-                        mma_16x8x4_f64(acc[0][h], a0, a1, b.x);
-                        mma_16x8x4_f64(acc[1][h], a0, a1, b.y);
-                    }
+                for (int h = 0; h < NH; ++h) {
+                    if (h >= nh) continue;
+                    mma_16x8x4_f64(acc[0][h], a0, a1, bf[h].x);
+                    mma_16x8x4_f64(acc[1][h], a0, a1, bf[h].y);
+                }
+                a0 = na0; a1 = na1;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) bf[h] = nb[h];
                 if (GIAO && ((m8 >> ks) & 1u)) {
                     // last K step of an atom: S += C_A * ((B x r) . (R_A - R_next)), one weight per row (see the header)
                     const double oA = wAx * curx + wAy * cury + wAz * curz, oB = wBx * curx + wBy * cury + wBz * curz;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < NH; ++h) {
                         zac[h][0] = fma(oA, acc[0][h][0], zac[h][0]); zac[h][1] = fma(oA, acc[0][h][1], zac[h][1]);
                         zac[h][2] = fma(oB, acc[0][h][2], zac[h][2]); zac[h][3] = fma(oB, acc[0][h][3], zac[h][3]);
                     }
@@ -520,10 +539,10 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
 #pragma unroll
                 for (int i = 0; i < 7; ++i) { eA[i] = 0.0; eB[i] = 0.0; }
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < NH; ++h)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        if (h == 1 && !h1) continue;
+                        if (h >= nh) continue;
                         const int slot = eslot[h][j];                         // K slot (= panel row) of this nu column
                         const double *pe = panel + (long)slot * LDP;
                         double Rx = 0, Ry = 0, Rz = 0;
