@@ -152,13 +152,22 @@ class Driver:
             if self.rank == 0:
                 cache["total"] = cache["alpha"] + cache["beta"]
                 cache["spindens"] = cache["alpha"] - cache["beta"]
+        want_jmod = bool(I.get("Essential.jmod")) and grid.is_3d()
+        want_acid = bool(I.get("Essential.acid")) and grid.is_3d()
+        # Only J (and |J|) is written when neither ACID nor the property quadrature is asked for: the library then contracts
+        # with B inside the GEMM (2 operand planes instead of 4) and never forms the tensors (closed shell, single rank).
+        j_only = (not self.uhf) and self.world == 1 and not want_acid and not I.get("Essential.prop")
         for sc, tag in cases:
-            tens = cache[sc] if self.uhf and (self.rank == 0) else (None if self.uhf else self._tensors(sc))
-            if self.rank != 0:
-                continue
-            r = grid.points()
-            f = self.g.fields_from_tensors(r, tens, self.magnet, jvec=True, jmod=bool(I.get("Essential.jmod")) and grid.is_3d(),
-                                           acid=bool(I.get("Essential.acid")) and grid.is_3d())
+            if j_only:
+                r = grid.points()
+                tens = None
+                f = self.g.fields(r, self.magnet, sc, jvec=True, jmod=want_jmod)
+            else:
+                tens = cache[sc] if self.uhf and (self.rank == 0) else (None if self.uhf else self._tensors(sc))
+                if self.rank != 0:
+                    continue
+                r = grid.points()
+                f = self.g.fields_from_tensors(r, tens, self.magnet, jvec=True, jmod=want_jmod, acid=want_acid)
             self.out.write(" magnetic field\n " + "".join(writers._ld_real(b) for b in self.magnet) + "\n \n")
             jv = f["jvec"]
             regular = grid.mode in ("std", "base", "bond")

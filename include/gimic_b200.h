@@ -108,6 +108,9 @@ int gimic_b200_calc_jtensors(gimic_b200_handle h, long n, const double *r, int s
  *   acid  = get_acid(T)               (acid.f90:9-45, with the reference's 0.3333333)
  *   edens = Phi^T D Phi ("diapam", jtensor.F90:168)        -- no reference run mode at this commit
  *   divj  = div(T.B) by central differences of step divj_h  -- no reference run mode at this commit */
+/* When only jvec and/or jmod (and edens) are requested (tens, acid, divj NULL) the tensor is never formed: the contraction
+ * runs with the operand pair (D, sum_b B_b P_b) -- compute_jvectors (jfield.f90:167-184) applied before instead of after
+ * the GEMM -- which halves the tensor-core work.  Same J within the 1e-10 / 1e-12 tolerance. */
 int gimic_b200_calc_fields(gimic_b200_handle h, long n, const double *r, const double *B3, int spincase,
                            double *tens, double *jvec, double *jmod, double *acid, double *edens, double *divj,
                            double divj_h, int flags);
