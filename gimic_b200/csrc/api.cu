@@ -644,6 +644,23 @@ int gimic_b200_fields_from_tensors(gimic_b200_handle c, long n, const double *r,
     return 0;
 }
 
+int gimic_b200_jmod_from_jvec(gimic_b200_handle c, long n, const double *r, const double *jvec, const double *B3, double *jmod, int flags) {
+    if (!c || !r || !jvec || !B3 || !jmod) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (n <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    const double *d_r, *d_j;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    if (int rc = stage_in(c, c->tens_tmp, jvec, (size_t)3 * n, flags, &d_j)) return rc;
+    double *d_m = jmod;
+    if (!dev) { if (c->f_tmp.ensure((size_t)n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (jmod)"); d_m = c->f_tmp.as<double>(); }
+    gb::launch_jmod(n, d_r, d_j, B3, d_m, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) CUDA_TRY(cudaMemcpyAsync(jmod, d_m, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g, long lo, long hi, int spincase, double *tens, int flags) {
     if (!c || !g || !tens) return fail(GIMIC_B200_EINVAL, "null argument");
     const long ntot = (long)g->npts[0] * g->npts[1] * g->npts[2];

@@ -156,12 +156,25 @@ class Driver:
         want_acid = bool(I.get("Essential.acid")) and grid.is_3d()
         # Only J (and |J|) is written when neither ACID nor the property quadrature is asked for: the library then contracts
         # with B inside the GEMM (2 operand planes instead of 4) and never forms the tensors (closed shell, single rank).
-        j_only = (not self.uhf) and self.world == 1 and not want_acid and not I.get("Essential.prop")
+        j_only = self.world == 1 and not want_acid and not I.get("Essential.prop")
+        jcache = {}
+        if j_only and self.uhf:
+            # J is linear in the densities like the tensor: alpha and beta once, total / spindens by combination
+            r = grid.points()
+            jcache["alpha"] = self.g.fields(r, self.magnet, "alpha", jvec=True)["jvec"]
+            jcache["beta"] = self.g.fields(r, self.magnet, "beta", jvec=True)["jvec"]
+            jcache["total"] = jcache["alpha"] + jcache["beta"]
+            jcache["spindens"] = jcache["alpha"] - jcache["beta"]
         for sc, tag in cases:
             if j_only:
                 r = grid.points()
                 tens = None
-                f = self.g.fields(r, self.magnet, sc, jvec=True, jmod=want_jmod)
+                if self.uhf:
+                    f = {"jvec": jcache[sc]}
+                    if want_jmod:
+                        f["jmod"] = self.g.jmod_from_jvec(r, jcache[sc], self.magnet)
+                else:
+                    f = self.g.fields(r, self.magnet, sc, jvec=True, jmod=want_jmod)
             else:
                 tens = cache[sc] if self.uhf and (self.rank == 0) else (None if self.uhf else self._tensors(sc))
                 if self.rank != 0:

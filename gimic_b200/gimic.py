@@ -232,6 +232,14 @@ class Gimic:
                                                     _dptr(B), *args, 0))
         return res
 
+    def jmod_from_jvec(self, r, jvec, B):
+        """signed |J| (jfield.f90:446-489) of given J vectors"""
+        r = _host(r).reshape(-1, 3); jvec = _host(jvec).reshape(-1, 3)
+        out = np.empty(r.shape[0])
+        _lib.check(_lib.lib().gimic_b200_jmod_from_jvec(self._h, r.shape[0], C.c_void_p(r.ctypes.data), C.c_void_p(jvec.ctypes.data),
+                                                        _dptr(_host(B, (3,))), C.c_void_p(out.ctypes.data), 0))
+        return out
+
     def jtensors_grid(self, grid, lo=0, hi=None, spincase="total", out=None):
         """Tensors on the flat index range [lo, hi) of a regular grid; points are generated on the device."""
         L = _lib.lib()

@@ -124,6 +124,9 @@ int gimic_b200_calc_basis(gimic_b200_handle h, long n, const double *r, double *
 int gimic_b200_fields_from_tensors(gimic_b200_handle h, long n, const double *r, const double *tens,
                                    const double *B3, double *jvec, double *jmod, double *acid, int flags);
 
+/* Signed modulus from J alone (jfield.f90:446-489), e.g. for J vectors combined by linearity (total = alpha + beta). */
+int gimic_b200_jmod_from_jvec(gimic_b200_handle h, long n, const double *r, const double *jvec, const double *B3, double *jmod, int flags);
+
 /* Regular grid (grid_t of src/fgimic/grid.f90:19-32 reduced to what gridpoint/get_weight need):
  * r(i,j,k) = origin + pts[0][i] basv(:,1) + pts[1][j] basv(:,2) + pts[2][k] basv(:,3)  (grid.f90:498-511) */
 typedef struct {

@@ -25,6 +25,13 @@ def assert_close(a, ref, what=""):
     assert e <= 1.0, f"{what}: max |a-ref| / (1e-10|ref| + 1e-12) = {e:.3g}"
 
 
+def _jscale_close(j, jref, tref, what):
+    """J = T.B compared at the scale of the tensor components that are summed (1e-10 of the point's largest |T B| term)"""
+    scale = np.abs(tref).max(axis=1, keepdims=True)
+    err = np.abs(j - jref) / (RTOL * np.maximum(np.abs(jref), 1e-3 * scale) + ATOL)
+    assert err.max() <= 1.0, f"{what}: {err.max():.3g}"
+
+
 @pytest.fixture(scope="module")
 def gb():
     import gimic_b200
@@ -150,6 +157,29 @@ def test_edge_cases(c4h4):
     assert_close(g.jtensors(on_atom), o.ctensor(on_atom), "on nuclei")
     plane = r.copy(); plane[:, 2] = 0.0                                      # molecular plane: exact zeros of odd-z functions
     assert_close(g.jtensors(plane), o.ctensor(plane), "nuclear plane")
+
+
+def test_edge_cases_j_path(gb, c4h4):
+    """the same edge cases through the J = T.B kernel (fields with jvec only): empty, single, ragged, screened, on nuclei"""
+    import torch
+    g, o = c4h4
+    B = np.array([0.1, -0.3, 0.95])
+    J = lambda x: g.fields(x, B, "total", jvec=True)["jvec"]
+    Jo = lambda x: O.jvectors(o.ctensor(x), B)
+    assert J(np.zeros((0, 3))).shape == (0, 3)
+    r1 = np.array([[0.3, -0.2, 0.7]])
+    assert_close(J(r1), Jo(r1), "single point")
+    rng = np.random.default_rng(5)
+    r = rng.uniform(-6, 6, size=(129, 3))
+    far = np.array([[200.0, 0, 0], [0, -300.0, 5.0], [1e4, 1e4, 1e4]])
+    assert (J(far) == 0).all()
+    mix = np.vstack([far, r[:5], far, r, o.atom_coords()])
+    tref = o.ctensor(mix)
+    _jscale_close(J(mix), O.jvectors(tref, B), tref, "mixed tile")
+    a = J(mix); p = rng.permutation(mix.shape[0])
+    assert np.array_equal(J(mix[p]), a[p])                                   # fixed reduction order: bit-reproducible
+    f = g.fields(mix, B, "total", jvec=True, jmod=True)
+    assert np.array_equal(g.jmod_from_jvec(mix, f["jvec"], B), f["jmod"])
 
 
 def test_point_order_invariance(c4h4):
@@ -483,13 +513,6 @@ def test_random_molecules_vs_oracle(gb, seed):
         jerr = np.abs(g.fields(r, Bf, sc, jvec=True)["jvec"] - O.jvectors(to, Bf)) / (RTOL * np.maximum(np.abs(O.jvectors(to, Bf)), 1e-2 * scale) + ATOL)
         assert jerr.max() <= 1.0, f"{what} J path: {jerr.max():.3g}"
     g.close()
-
-
-def _jscale_close(j, jref, tref, what):
-    """J = T.B compared at the scale of the tensor components that are summed (1e-10 of the point's largest |T B| term)"""
-    scale = np.abs(tref).max(axis=1, keepdims=True)
-    err = np.abs(j - jref) / (RTOL * np.maximum(np.abs(jref), 1e-3 * scale) + ATOL)
-    assert err.max() <= 1.0, f"{what}: {err.max():.3g}"
 
 
 def test_jvec_only_path_vs_oracle(gb, cases, c4h4, opensh):
