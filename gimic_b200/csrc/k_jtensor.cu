@@ -82,7 +82,8 @@ constexpr int ROWLD = 17;   // doubles per row-table entry: 13 sums + 3 coordina
 constexpr int NCONSUMER_WARPS = 8;
 constexpr int NPRODUCER_WARPS = 4;   // one warpgroup, so that setmaxnreg can hand its registers to the consumers
 constexpr int NTHREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
-constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 = 64512 <= 65536
+constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 = 64512 < 65536.  Do NOT use the whole file: with
+                                                          // 240/32 (= 65536) setmaxnreg.inc never succeeds and the kernel hangs (measured)
 constexpr int ATAB_MAX = 1024;      // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
 constexpr int KMASK_WORDS = 512;    // atom-end bits for up to 16384 K steps = 65536 slots
 
