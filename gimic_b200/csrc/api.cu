@@ -905,6 +905,13 @@ long gimic_b200_format_e(long n, const double *v, int w, int d, int per_line, in
     return rc;
 }
 
+long gimic_b200_format_f(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap) {
+    if (n < 0 || (n > 0 && (!v || !out)) || w <= 0 || w > 40 || d < 0 || d > 30) { fail(GIMIC_B200_EINVAL, "bad argument"); return GIMIC_B200_EINVAL; }
+    long rc = gb::format_fortran(n, v, 'F', w, d, per_line, first_count, prefix, out, cap);
+    if (rc < 0) { fail(GIMIC_B200_EINVAL, "output buffer too small"); return GIMIC_B200_EINVAL; }
+    return rc;
+}
+
 int gimic_b200_c2s_rows(int l, int turbomole_order, double *po) {
     if (!po || l < 0 || l > gb::MAX_L) return fail(GIMIC_B200_EINVAL, "bad argument");
     std::vector<double> rows;

@@ -452,7 +452,29 @@ void put_e(double x, int w, int d, char *dst) {
 }
 }  // namespace
 
+namespace {
+// One value with the fixed-point descriptor Fw.d, right-justified (asterisks on overflow like Fortran)
+void put_f(double x, int w, int d, char *dst) {
+    char body[400];
+    int len;
+    if (!std::isfinite(x)) len = std::snprintf(body, sizeof body, "%s", std::isnan(x) ? "NaN" : (x < 0 ? "-Infinity" : "Infinity"));
+    else {
+        auto res = std::to_chars(body, body + sizeof body - 1, x, std::chars_format::fixed, d);   // correctly rounded, like printf %.*f
+        len = (int)(res.ptr - body);
+    }
+    if (len > w) { std::memset(dst, '*', (size_t)w); return; }
+    std::memset(dst, ' ', (size_t)(w - len));
+    std::memcpy(dst + (w - len), body, (size_t)len);
+}
+}  // namespace
+
+long format_fortran(long n, const double *v, char kind, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
+
 long format_fortran_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap) {
+    return format_fortran(n, v, 'E', w, d, per_line, first_count, prefix, out, cap);
+}
+
+long format_fortran(long n, const double *v, char kind, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap) {
     if (n <= 0) return 0;
     if (per_line <= 0) per_line = 1;
     const long first = first_count > 0 ? std::min<long>(first_count, n) : std::min<long>(per_line, n);
@@ -471,7 +493,7 @@ long format_fortran_e(long n, const double *v, int w, int d, int per_line, int f
             char *p = out + l * w + (ln + 1) * plen + ln;
             const bool starts = (l == 0) || (l == first) || (l > first && (l - first) % per_line == 0);
             if (starts && plen) std::memcpy(p - plen, prefix, (size_t)plen);
-            put_e(v[l], w, d, p);
+            if (kind == 'F') put_f(v[l], w, d, p); else put_e(v[l], w, d, p);
             const bool ends = (l + 1 == first) || (l + 1 > first && (l + 1 - first) % per_line == 0);
             if (ends && (l + 1 < n || last_complete)) p[w] = '\n';
         }

@@ -71,6 +71,8 @@ void density_sph_to_cart(const HostBasis &b, const double *dsph, double *dcart);
 // points that is 5e7 values).  Lines hold `per_line` values (the first line `first_count` if > 0), each line starts with
 // `prefix` and complete lines end with '\n'.  Threaded; returns the number of bytes written, or -1 if `cap` is too small.
 long format_fortran_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
+// same with kind = 'E' (Ew.d) or 'F' (Fw.d)
+long format_fortran(long n, const double *v, char kind, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
 
 // Gauss-Legendre / Lobatto nodes in the piecewise-block layout of setup_gauss_data
 // (src/libgimic/gaussint.f90:267-319).  quadrature: 0 = gauss, 1 = lobatto.

@@ -20,9 +20,7 @@ def fortran_e(x, w, d):
     return "*" * w if len(s) > w else s.rjust(w)
 
 
-def format_e(values, w, d, per_line, first=0, prefix=""):
-    """Many values with Ew.d in one native, threaded call (gimic_b200_format_e): `per_line` values per line (`first` on the
-    first line if > 0), every line starting with `prefix`, complete lines ending in a newline.  Returns bytes."""
+def _format(kind, values, w, d, per_line, first=0, prefix=""):
     import ctypes as C
     from . import _lib
     v = np.ascontiguousarray(values, dtype=np.float64).ravel()
@@ -32,10 +30,22 @@ def format_e(values, w, d, per_line, first=0, prefix=""):
     nlines = n // max(per_line, 1) + 2
     cap = n * w + nlines * (len(prefix) + 1) + 16
     buf = np.empty(cap, dtype=np.uint8)
-    got = _lib.lib().gimic_b200_format_e(n, v.ctypes.data_as(_lib.dp), w, d, per_line, first, prefix.encode(), C.c_void_p(buf.ctypes.data), cap)
+    fn = _lib.lib().gimic_b200_format_e if kind == "E" else _lib.lib().gimic_b200_format_f
+    got = fn(n, v.ctypes.data_as(_lib.dp), w, d, per_line, first, prefix.encode(), C.c_void_p(buf.ctypes.data), cap)
     if got < 0:
-        raise _lib.GimicB200Error(got, "format_e failed")
+        raise _lib.GimicB200Error(got, "number formatting failed")
     return buf[:got].tobytes()
+
+
+def format_e(values, w, d, per_line, first=0, prefix=""):
+    """Many values with Ew.d in one native, threaded call (gimic_b200_format_e): `per_line` values per line (`first` on the
+    first line if > 0), every line starting with `prefix`, complete lines ending in a newline.  Returns bytes."""
+    return _format("E", values, w, d, per_line, first, prefix)
+
+
+def format_f(values, w, d, per_line, first=0, prefix=""):
+    """Same for the fixed-point descriptor Fw.d (gimic_b200_format_f)."""
+    return _format("F", values, w, d, per_line, first, prefix)
 
 
 def _ld_real(x):
@@ -212,11 +222,19 @@ def write_jmod_txt(path, grid, vec, regular=True):
     r = grid.points() * AU2A
     jm = np.sqrt((v ** 2).sum(1))
     p1 = grid.npts[0]
-    with open(path, "w") as f:
-        for n in range(v.shape[0]):
-            f.write("".join(f"{x:11.7f}" for x in (*r[n], jm[n])) + "\n")
-            if regular and (n + 1) % p1 == 0:
-                f.write("\n")
+    n = v.shape[0]
+    rows = np.frombuffer(format_f(np.column_stack([r, jm]), 11, 7, 4), dtype=np.uint8).reshape(n, 45)   # 4 x f11.7 + newline
+    with open(path, "wb") as f:
+        if regular and n % p1 == 0:
+            blocks = np.concatenate([rows.reshape(n // p1, p1 * 45), np.full((n // p1, 1), 10, np.uint8)], axis=1)   # blank line per i-row
+            f.write(blocks.tobytes())
+        elif regular:
+            for k in range(0, n, p1):
+                f.write(rows[k:k + p1].tobytes())
+                if k + p1 <= n:
+                    f.write(b"\n")
+        else:
+            f.write(rows.tobytes())
 
 
 def write_mol_xyz(path, symbols, coords):

@@ -189,6 +189,8 @@ int gimic_b200_convert_xdens(const char *xdens_text, int nbf, int nmat, const ch
  * first_count values if first_count > 0), start with `prefix` (may be NULL) and end with a newline when complete.  Threaded
  * over the host cores.  Returns the number of bytes written to out (capacity cap), or a negative GIMIC_B200_E* code. */
 long gimic_b200_format_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
+/* Same for the fixed-point descriptor Fw.d (jmod.txt: '(6f11.7)', jfield.f90:540). */
+long gimic_b200_format_f(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap);
 
 /* Cartesian -> spherical projection of cao2sao.f90:163-231 for angular momentum l (0..5), as used when opts.spherical is
  * set: po[(m + l) * ncart + c], m = -l..l, c in the standard (turbomole_order = 0) or Turbomole cartesian component order;

@@ -185,3 +185,25 @@ def test_vti_appended_extra_holds_the_same_numbers(tmp_path):
                 assert np.array_equal(got, ref)
             else:
                 assert got.size == 4 * 2 * 1 and (got >= 0).all()          # cell-averaged |J|
+
+
+def test_native_f_format_and_jmod_txt_writer(tmp_path):
+    """gimic_b200_format_f == '%w.df' (Fortran Fw.d) incl. asterisks on overflow; jmod.txt ('(6f11.7)' rows, a blank line after
+    each i-row on regular grids, jfield.f90:356-376,540) is byte-identical to a per-row reference implementation"""
+    from gimic_b200 import grids, writers
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.normal(size=3000) * 10.0 ** rng.integers(-9, 3, size=3000),
+                        [0.0, 0.5, -0.5, 1e-8, -1e-8, 123.45678949999, 999.99999995, -999.99999995, 99999.9999999]])
+    got = writers.format_f(v, 11, 7, 1).decode().split("\n")[:-1]
+    assert got == [("%11.7f" % x) if len("%11.7f" % x) <= 11 else "*" * 11 for x in v]
+    g = grids.std_grid([-1, -1, 0], [1, 0, 0], [0, 1, 0], [2, 2, 0], "gauss", grid_points=[9, 9, 0], gauss_order=9)
+    vec = rng.normal(size=(g.n, 3)) * 1e-2
+    r = g.points() * writers.AU2A; jm = np.sqrt((vec ** 2).sum(1))
+    for regular in (True, False):
+        writers.write_jmod_txt(tmp_path / "jmod.txt", g, vec, regular=regular)
+        ref = ""
+        for n in range(g.n):
+            ref += "".join(f"{x:11.7f}" for x in (*r[n], jm[n])) + "\n"
+            if regular and (n + 1) % g.npts[0] == 0:
+                ref += "\n"
+        assert open(tmp_path / "jmod.txt").read() == ref
