@@ -72,6 +72,15 @@ module b200_module
             import; integer(c_long), value :: n, cap; integer(c_int), value :: w, d, per_line, first_count
             real(c_double) :: v(*); character(kind=c_char) :: prefix(*), out(*)
         end function
+        integer(c_long) function gimic_b200_format_f(n, v, w, d, per_line, first_count, prefix, out, cap) bind(c)
+            import; integer(c_long), value :: n, cap; integer(c_int), value :: w, d, per_line, first_count
+            real(c_double) :: v(*); character(kind=c_char) :: prefix(*), out(*)
+        end function
+        ! signed |J| of given J vectors (jmod2_vtkplot, jfield.f90:446-489)
+        integer(c_int) function gimic_b200_jmod_from_jvec(h, n, r, jvec, b, jmod, flags) bind(c)
+            import; type(c_ptr), value :: h; integer(c_long), value :: n; integer(c_int), value :: flags
+            real(c_double) :: r(3,*), jvec(3,*), b(3), jmod(*)
+        end function
         function gimic_b200_last_error() bind(c) result(msg)
             import; type(c_ptr) :: msg
         end function
