@@ -185,8 +185,9 @@ int init_device(gimic_b200_ctx *c) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->ev_call) CUDA_TRY(cudaEventCreate(&e));
-    // panel pool: one batch per ~pool of Phi/dPhi panels; fewer, larger k_jtensor launches have fewer tails (+1% at 24 GB vs 8 GB)
-    c->pool_max_bytes = std::min<size_t>((size_t)24 << 30, std::max<size_t>((size_t)2 << 30, prop.totalGlobalMem / 8));
+    // panel pool: one batch (one k_basis + one k_jtensor launch) per ~pool of Phi/dPhi panels.  8 GB is the configuration of the
+    // committed ncu captures and launch lists; GIMIC_B200_POOL_MB=24576 (one launch per 2M-point step) measured +1 %.
+    c->pool_max_bytes = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, prop.totalGlobalMem / 8));
     if (const char *mb = std::getenv("GIMIC_B200_POOL_MB")) { long v = std::atol(mb); if (v > 0) c->pool_max_bytes = (size_t)v << 20; }
     return 0;
 }
