@@ -195,7 +195,7 @@ class Driver:
             if I.get("Essential.prop"):
                 self.run_property(tens)
             if grid.mode in ("std", "base", "bond") and grid.gtype == "even":
-                writers.write_vti_vector(os.path.join(wd, f"jvec{tag}.vti"), grid, jv, self.vtk_appended)
+                writers.write_vti_vector(os.path.join(wd, f"jvec{tag}.vti"), grid, writers.radius_masked_vectors(grid, jv), self.vtk_appended)
             elif (grid.mode in ("std", "base") and grid.gauss) or grid.mode == "file":
                 ele = os.path.join(wd, "grid.1.ele")
                 if os.path.exists(ele):

@@ -173,6 +173,18 @@ def write_vti_vector(path, grid, vec, appended=False):
         f.write("    </CellData>\n    </Piece>\n    </ImageData>\n </VTKFile>\n")
 
 
+def radius_masked_vectors(grid, vec):
+    """cdens visualisation with the `radius` keyword (jfield.f90:310-346): on 2-D bond grids the vectors written to jvec.vti are
+    zeroed where |coord*AU2A - center| > radius.  The reference compares Angstrom coordinates with the bohr centre and radius
+    (unit slip); replicated as is.  Returns vec itself when the rule does not apply."""
+    if grid.mode != "bond" or grid.is_3d() or not (grid.radius > 0.1) or grid.radius >= 1.0e10:
+        return vec
+    coord = grid.points() * AU2A
+    out = np.array(vec, dtype=np.float64, copy=True).reshape(-1, 3)
+    out[np.sqrt(((coord - grid.center()) ** 2).sum(1)) > grid.radius] = 0.0
+    return out
+
+
 def read_ele(path):
     """TetGen .ele: first line 'ncells 4 0', then 'idx n1 n2 n3 n4' (jfield.f90:421-431)"""
     with open(path) as f:

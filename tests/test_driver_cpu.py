@@ -207,3 +207,20 @@ def test_native_f_format_and_jmod_txt_writer(tmp_path):
             if regular and (n + 1) % g.npts[0] == 0:
                 ref += "\n"
         assert open(tmp_path / "jmod.txt").read() == ref
+
+
+def test_radius_keyword_masks_vectors_of_2d_bond_grids_like_the_reference():
+    """jfield.f90:310-346: 2-D bond grid + radius keyword -> vectors beyond the radius are zeroed in jvec.vti, with the reference's
+    Angstrom-vs-bohr comparison; no-op for the default radius (1e10), 3-D grids and base grids"""
+    from gimic_b200 import grids, writers
+    c1, c2, fix = np.array([0.0, 0.0, 0.0]), np.array([2.6, 0.0, 0.0]), np.array([1.3, 2.2, 0.0])
+    g = grids.bond_grid(c1, c2, fix, 1.3, [-3.0, 3.0], [-3.0, 3.0], "even", spacing=[0.5, 0.5, 0.5], radius=1.5)
+    v = np.ones((g.n, 3))
+    m = writers.radius_masked_vectors(g, v)
+    far = np.sqrt(((g.points() * writers.AU2A - g.center()) ** 2).sum(1)) > 1.5
+    assert far.any() and (~far).any() and (m[far] == 0).all() and (m[~far] == 1).all() and (v == 1).all()
+    g0 = grids.bond_grid(c1, c2, fix, 1.3, [-3.0, 3.0], [-3.0, 3.0], "even", spacing=[0.5, 0.5, 0.5])
+    assert writers.radius_masked_vectors(g0, v) is v
+    gb = grids.std_grid([-1, -1, -1], [1, 0, 0], [0, 1, 0], [2, 2, 2], "even", spacing=[0.5, 0.5, 0.5])
+    vb = np.ones((gb.n, 3))
+    assert writers.radius_masked_vectors(gb, vb) is vb
