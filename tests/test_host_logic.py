@@ -89,3 +89,27 @@ def test_integral_allreduce_world2_gloo(cases):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert np.allclose(res[:3], ref, rtol=1e-11, atol=1e-13)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference algorithm on the host CPU, oracle port): one JSON line with the keys the driver
+    reads; tiny workload so that it runs in seconds.  The CUDA arm refuses to run without a GPU (no CPU fallback)."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                                   "--natoms", "6", "--grid", "16", "--cpu-points", "32"], text=True)
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "points/s" and d["dtype"] == "f64" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["value"] > 0 and "workload" in d["config"] and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import torch
+    if not torch.cuda.is_available():
+        p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--natoms", "6", "--grid", "16"], capture_output=True, text=True)
+        assert p.returncode != 0 and "no CPU path" in p.stdout
