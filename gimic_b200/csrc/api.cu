@@ -913,6 +913,17 @@ long gimic_b200_format_f(long n, const double *v, int w, int d, int per_line, in
     return rc;
 }
 
+int gimic_b200_mol_geometry(const char *mol, int max_atoms, double *xyz, char *symbols2) {
+    if (!mol) return fail(GIMIC_B200_EINVAL, "null argument");
+    gb::HostBasis hb; std::string err;
+    if (!gb::parse_mol(mol, hb, err)) return fail(GIMIC_B200_EIO, err);
+    for (int a = 0; a < hb.natoms && a < max_atoms; ++a) {
+        if (xyz) for (int k = 0; k < 3; ++k) xyz[3 * a + k] = hb.xyz[3 * a + k];
+        if (symbols2) { symbols2[2 * a] = hb.symbol[a].size() > 0 ? hb.symbol[a][0] : ' '; symbols2[2 * a + 1] = hb.symbol[a].size() > 1 ? hb.symbol[a][1] : ' '; }
+    }
+    return hb.natoms;
+}
+
 int gimic_b200_c2s_rows(int l, int turbomole_order, double *po) {
     if (!po || l < 0 || l > gb::MAX_L) return fail(GIMIC_B200_EINVAL, "bad argument");
     std::vector<double> rows;

@@ -51,6 +51,20 @@ def read_mol_geometry(mol):
     return syms, np.array(xyz)
 
 
+def mol_geometry(mol):
+    """(symbols, coords) from the library's own MOL reader (gimic_b200_mol_geometry; host only, no device context)"""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    n = L.gimic_b200_mol_geometry(os.fsencode(mol), 0, None, None)
+    if n < 0:
+        raise RuntimeError(L.gimic_b200_last_error().decode())
+    xyz = np.zeros((n, 3)); sym = C.create_string_buffer(2 * n)
+    L.gimic_b200_mol_geometry(os.fsencode(mol), n, xyz.ctypes.data_as(C.POINTER(C.c_double)), sym)
+    raw = sym.raw[: 2 * n].decode()
+    return [raw[2 * a: 2 * a + 2] for a in range(n)], xyz
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -62,9 +76,11 @@ def _dist():
 
 
 class Driver:
-    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False):
+    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False, dryrun=False):
         self.workdir = workdir or os.path.dirname(os.path.abspath(inpfile))
         self.inp = _inp.parse_file(inpfile)
+        if dryrun:                               # the -y switch overrides the keyword (src/gimic.in:139-140)
+            self.inp.values[""]["dryrun"] = True
         self.vtk_appended = bool(vtk_appended)   # extra: .vti files with raw appended Float64 data instead of ASCII e14.6
         self.dist, self.rank, self.world = _dist()
         self.out = out if out is not None else sys.stdout
@@ -76,13 +92,19 @@ class Driver:
                             bool(I.get("Advanced.GIAO")), bool(I.get("Advanced.diamag")), bool(I.get("Advanced.paramag")),
                             bool(I.get("Advanced.screening")), float(I.get("Advanced.screening_thrs")),
                             bool(I.get("Advanced.spherical")))
-        self.g = gimic if gimic is not None else Gimic(
-            path(I.get("basis")), path(I.get("xdens")), uhf=self.uhf, giao=I.get("Advanced.GIAO"),
-            diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"),
-            screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device,
-            spherical=bool(I.get("Advanced.spherical")))
-        self.xyz = self.g.atom_coords()
-        self.symbols = self._symbols(path(I.get("basis")))
+        if I.get("dryrun") and gimic is None:
+            # driver (gimic.F90:142-159): a dry run builds the basis but neither the c2s operator nor the densities;
+            # here that means no device context at all, only the MOL geometry (parsed by the library's own reader)
+            self.g = None
+            self.symbols, self.xyz = mol_geometry(path(I.get("basis")))
+        else:
+            self.g = gimic if gimic is not None else Gimic(
+                path(I.get("basis")), path(I.get("xdens")), uhf=self.uhf, giao=I.get("Advanced.GIAO"),
+                diamag=I.get("Advanced.diamag"), paramag=I.get("Advanced.paramag"),
+                screening=I.get("Advanced.screening"), screening_thrs=I.get("Advanced.screening_thrs"), device=device,
+                spherical=bool(I.get("Advanced.spherical")))
+            self.xyz = self.g.atom_coords()
+            self.symbols = self._symbols(path(I.get("basis")))
         self.grid = grids.from_input(I, self.xyz, self.workdir)
         self.magnet = grids.get_magnet(self.grid, I.get("magnet_axis"), I.get("magnet"))
 
@@ -104,10 +126,18 @@ class Driver:
         self.say()
         self.say("INFO: " + ("Open-shell calculation" if self.uhf else "Closed-shell calculation"))
         self.say()
-        if I.get("dryrun"):
-            self.say("*** Dry run, not calculating ...")
-            return
         calc = I.get("calc")
+        if I.get("dryrun"):
+            # gimic.F90:174-185,196-204,222-230: the note, then the run mode's banner, then return before any arithmetic
+            self.say("*** Dry run, not calculating ...")
+            self.say()
+            if calc == "cdens":
+                self.say("Calculating current density")
+                self.say("*****************************************")
+            elif calc == "integral":
+                self.say("Integrating current density")
+                self.say("*****************************************")
+            return
         if calc == "cdens":
             self.run_cdens()
         elif calc == "integral":
@@ -361,7 +391,7 @@ def run_scan(infiles, device=-1, outs=None):
             out = outs[k]
         else:
             out = open(os.path.splitext(f)[0] + ".out", "w"); opened.append(out)
-        share = next((d.g for d in drivers if d.context_key == _context_key_of(f)), None)
+        share = next((d.g for d in drivers if d.g is not None and d.context_key == _context_key_of(f)), None)
         drivers.append(Driver(f, out=out, device=device, gimic=share))
     batch = [d for d in drivers if d.inp.get("calc") == "integral" and not d.inp.get("dryrun") and d.world == 1]
     pre = {id(d): {} for d in batch}
@@ -402,11 +432,16 @@ def main(argv=None):
     ap.add_argument("--workdir", default=None)
     ap.add_argument("--vtk", default="ascii", choices=["ascii", "appended"],
                     help="ascii: the reference's .vti files (e14.6); appended: same files with raw Float64 blocks (extra, not a reference format)")
+    ap.add_argument("-y", "--dryrun", action="store_true",
+                    help="lay out the grid and write mol.xyz / grid.xyz without calculating anything (src/gimic.in:53-54); needs no GPU")
     a = ap.parse_args(argv)
     if len(a.infile) > 1:
         run_scan(a.infile)
         return 0
     a.infile = a.infile[0]
+    if a.dryrun:
+        Driver(a.infile, a.workdir, dryrun=True).run()
+        return 0
     device = -1
     if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch

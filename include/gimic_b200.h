@@ -178,6 +178,11 @@ int gimic_b200_property_integrand(gimic_b200_handle h, long n, const double *r, 
  * (gaussint.f90:267-319); host only. */
 int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrature, double *pts, double *wgts);
 
+/* Geometry of an INTGRL/MOL file without creating a context (host only; e.g. for a dry run that only lays out the grid):
+ * returns the number of atoms (or a negative GIMIC_B200_E* code) and fills up to max_atoms entries of xyz (3 per atom, bohr)
+ * and symbols2 (the two-character element field of intgrl.f90:111, not NUL-terminated); either may be NULL. */
+int gimic_b200_mol_geometry(const char *mol, int max_atoms, double *xyz, char *symbols2);
+
 /* XDENS text (dens.f90:129-135: one real per line, 4 or 8 matrices of nbf x nbf) -> binary cache that gimic_b200_create
  * recognises by its "GB2XDENS" magic (int64 nbf, int64 nmat, raw doubles in file order).  Values are stored exactly as the
  * text reader parses them, before UHF halving / Turbomole reordering.  nbf = the dimension of the matrices in the file

@@ -76,6 +76,11 @@ module b200_module
             import; integer(c_long), value :: n, cap; integer(c_int), value :: w, d, per_line, first_count
             real(c_double) :: v(*); character(kind=c_char) :: prefix(*), out(*)
         end function
+        ! geometry of a MOL file without a context (dry run, gimic.F90:142-204): returns natoms; symbols2 = 2 characters per atom
+        integer(c_int) function gimic_b200_mol_geometry(mol, max_atoms, xyz, symbols2) bind(c)
+            import; integer(c_int), value :: max_atoms
+            character(kind=c_char) :: mol(*), symbols2(*); real(c_double) :: xyz(3,*)
+        end function
         ! signed |J| of given J vectors (jmod2_vtkplot, jfield.f90:446-489)
         integer(c_int) function gimic_b200_jmod_from_jvec(h, n, r, jvec, b, jmod, flags) bind(c)
             import; type(c_ptr), value :: h; integer(c_long), value :: n; integer(c_int), value :: flags

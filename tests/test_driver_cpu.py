@@ -224,3 +224,32 @@ def test_radius_keyword_masks_vectors_of_2d_bond_grids_like_the_reference():
     gb = grids.std_grid([-1, -1, -1], [1, 0, 0], [0, 1, 0], [2, 2, 2], "even", spacing=[0.5, 0.5, 0.5])
     vb = np.ones((gb.n, 3))
     assert writers.radius_masked_vectors(gb, vb) is vb
+
+
+def test_dry_run_needs_no_device(tmp_path):
+    """-y / dryrun=on (gimic.F90:150-204, src/gimic.in:53-54,139-140): basis geometry and grid only, no densities and
+    here no device context; mol.xyz and grid.xyz are written, the run mode's banner is printed, nothing is calculated.
+    Runs in this GPU-less container: proof that the dry run does not reach a compute entry point."""
+    import shutil
+    from gimic_b200 import driver
+    shutil.copy(os.path.join(GOLD, "benzene_MOL"), tmp_path / "MOL")      # no XDENS on purpose
+    shutil.copy(os.path.join(INPUTS, "benzene_integration-gauss.inp"), tmp_path / "gimic.inp")
+    out = io.StringIO()
+    d = driver.Driver(str(tmp_path / "gimic.inp"), out=out, dryrun=True)
+    assert d.g is None
+    d.run()
+    text = out.getvalue()
+    assert "Dry run, not calculating" in text and "Integrating current density" in text and "Magnetic field <x,y,z>" in text
+    assert "Induced current" not in text
+    syms, coords = driver.read_mol_geometry(str(tmp_path / "MOL"))
+    assert [s.strip() for s in d.symbols] == [s.strip() for s in syms] and np.allclose(d.xyz, coords, rtol=0, atol=0)
+    assert (tmp_path / "mol.xyz").exists() and (tmp_path / "grid.xyz").exists()
+    assert int(open(tmp_path / "mol.xyz").readline()) == len(syms)
+    # the command-line switch
+    os.remove(tmp_path / "mol.xyz")
+    assert driver.main([str(tmp_path / "gimic.inp"), "--dryrun"]) == 0 and (tmp_path / "mol.xyz").exists()
+    # without the switch the same input needs the device context and fails loudly here (no CPU fallback)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            driver.Driver(str(tmp_path / "gimic.inp"), out=io.StringIO())
