@@ -125,7 +125,7 @@ def _vti_appended(path, grid, name, ncomp, data, cell=None):
     ext = " ".join(str(v) for v in (0, npts[0] - 1, 0, npts[1] - 1, 0, npts[2] - 1))
     blocks = [np.ascontiguousarray(data, dtype="<f8").ravel()]
     head = ['<?xml version="1.0"?>', '<VTKFile type="ImageData" version="0.1" byte_order="LittleEndian" header_type="UInt64">',
-            f'  <ImageData WholeExtent="{ext}" Origin="{qmin[0]!r} {qmin[1]!r} {qmin[2]!r}" Spacing="{step[0]!r} {step[1]!r} {step[2]!r}">',
+            f'  <ImageData WholeExtent="{ext}" Origin="{float(qmin[0])!r} {float(qmin[1])!r} {float(qmin[2])!r}" Spacing="{float(step[0])!r} {float(step[1])!r} {float(step[2])!r}">',
             f'    <Piece Extent="{ext}">', f'      <PointData {"Vectors" if ncomp == 3 else "Scalars"}="{name}">',
             f'        <DataArray Name="{name}" type="Float64" NumberOfComponents="{ncomp}" format="appended" offset="0"/>',
             '      </PointData>']

@@ -178,6 +178,9 @@ def test_vti_appended_extra_holds_the_same_numbers(tmp_path):
         head, data = raw.split(b'<AppendedData encoding="raw">\n_', 1)
         offs = [int(x) for x in re.findall(rb'offset="(\d+)"', head)]
         assert len(offs) == len(arrs) and b'header_type="UInt64"' in head
+        geo = re.search(rb'Origin="([^"]*)" Spacing="([^"]*)"', head)        # plain numbers a VTK reader can parse
+        assert [float(x) for x in geo.group(1).split()] == [-1.0, -1.0, -1.0]
+        assert [float(x) for x in geo.group(2).split()] == [0.5, 1.0, 2.0]
         for off, ref in zip(offs, arrs):
             nbytes = int(np.frombuffer(data[off:off + 8], np.uint64)[0])
             got = np.frombuffer(data[off + 8:off + 8 + nbytes], "<f8")
