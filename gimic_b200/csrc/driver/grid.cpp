@@ -203,7 +203,7 @@ Vec3 get_magnet(const GridSpec &g, const std::string &magnet_axis, const Vec3 &m
         if (axis[0] == '-') { d = -1.0; axis = axis.substr(1); }
         const char a = axis.empty() ? '\0' : axis[0];
         if (a == 'i' || a == 'j' || a == 'k') { const int v = a - 'i'; for (int c = 0; c < 3; ++c) mag[c] = g.basv[v][c] * d; }
-        else if (a == 'x' || a == 'y' || a == 'z') { mag[a - 'x'] = 1.0 * d; }
+        else if (a == 'x' || a == 'y' || a == 'z') { for (int c = 0; c < 3; ++c) mag[c] = (c == a - 'x' ? 1.0 : 0.0) * d; }   // (/D0,D0,D1/)*dir, magnet.f90:38-43
         else if (a == 'X') { ortho = true; for (int c = 0; c < 3; ++c) mag[c] = g.ortho[c] * d; }
         else throw DriverError("Invalid axis specifier: " + axis);
     } else {

@@ -1,0 +1,47 @@
+// gimic-b200: command-line program over the native driver (the counterpart of `gimic [-y] gimic.inp`, src/gimic.in:25-159).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/gimic_b200_driver.h"
+
+static void usage(FILE *f) {
+    std::fputs("usage: gimic-b200 [-y|--dryrun] [--workdir DIR] [--vtk ascii|appended] [--device N] [gimic.inp ...]\n"
+               "  one input: files are written to its directory (or --workdir), the report to stdout\n"
+               "  several inputs (a current-profile scan): one device context, integrals batched into one tensor pass,\n"
+               "  each report written to <input stem>.out\n", f);
+}
+
+int main(int argc, char **argv) {
+    std::vector<const char *> files;
+    const char *workdir = nullptr;
+    int flags = 0, device = -1;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto value = [&](const char *opt) -> const char * {
+            if (i + 1 >= argc) { std::fprintf(stderr, "gimic-b200: %s needs a value\n", opt); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--help") { usage(stdout); return 0; }
+        else if (a == "-y" || a == "--dryrun") flags |= GIMIC_B200_RUN_DRYRUN;
+        else if (a == "--workdir") workdir = value("--workdir");
+        else if (a == "--device") device = std::atoi(value("--device"));
+        else if (a == "--vtk") {
+            const std::string v = value("--vtk");
+            if (v == "appended") flags |= GIMIC_B200_RUN_VTK_APPENDED;
+            else if (v != "ascii") { std::fprintf(stderr, "gimic-b200: --vtk must be ascii or appended\n"); return 2; }
+        } else if (a == "--version") { std::printf("%s\n", gimic_b200_version()); return 0; }
+        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "gimic-b200: unknown option %s\n", a.c_str()); usage(stderr); return 2; }
+        else files.push_back(argv[i]);
+    }
+    if (files.empty()) files.push_back("gimic.inp");
+    const int rc = files.size() == 1 ? gimic_b200_run_input(files[0], workdir, device, flags, nullptr)
+                                     : gimic_b200_run_scan((int)files.size(), files.data(), device, flags);
+    if (rc != 0) {
+        std::fprintf(stderr, "gimic-b200: %s\n", gimic_b200_driver_last_error());
+        return 1;
+    }
+    return 0;
+}

@@ -109,6 +109,7 @@ extern const double AU2A;                                     // real(4) literal
 std::string fortran_e(double x, int w, int d);
 std::string ld_real(double x);                                // gfortran list-directed real(8)
 std::string ld_int(long i);
+std::string py_repr(double x);                             // shortest round-trip decimal, laid out like Python's repr(float)
 std::string format_block(char kind, const double *v, long n, int w, int d, int per_line, int first = 0, const std::string &prefix = "");
 void write_vti_scalar(const std::string &path, const GridSpec &g, const std::vector<double> &values, bool appended);
 void write_vti_vector(const std::string &path, const GridSpec &g, const std::vector<double> &vec, bool appended);
@@ -138,6 +139,9 @@ struct RunOptions {
 int run_input(const std::string &inpfile, const RunOptions &opt, FILE *out);
 // many inputs sharing contexts, integrals batched per context (jobscripts/src/current-profile-*): reports go to <stem>.out
 int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt);
+// writers alone: lay `data` out on the grid of a gimic.inp (kind: vti_scalar | vti_vector | jmod_txt | vtu_vector | vtu_scalar)
+int write_field(const std::string &inpfile, const std::string &workdir, const std::string &kind, const double *data, long n, const std::string &name,
+                bool appended);
 const std::string &last_error_message();
 
 }  // namespace gbd

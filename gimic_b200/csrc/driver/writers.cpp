@@ -82,17 +82,6 @@ std::vector<double> cell_average_norm(const std::vector<double> &vec, int p1, in
     return out;
 }
 
-std::string repr(double x) {                                   // shortest round-trip decimal, like Python's repr
-    char buf[40];
-    for (int prec = 1; prec <= 17; ++prec) {
-        snprintf(buf, sizeof buf, "%.*g", prec, x);
-        if (std::strtod(buf, nullptr) == x) break;
-    }
-    std::string s = buf;
-    if (s.find_first_of(".eEni") == std::string::npos) s += ".0";
-    return s;
-}
-
 // EXTRA (not a reference format): the same ImageData file with raw appended Float64 blocks instead of ASCII numbers
 void vti_appended(const std::string &path, const GridSpec &g, const char *name, int ncomp, const std::vector<double> &data,
                   const std::vector<double> *cell) {
@@ -100,8 +89,8 @@ void vti_appended(const std::string &path, const GridSpec &g, const char *name, 
     vti_geometry(g, qmin, step);
     std::string ext = fmt("0 %d 0 %d 0 %d", g.npts[0] - 1, g.npts[1] - 1, g.npts[2] - 1);
     std::string head = "<?xml version=\"1.0\"?>\n<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
-    head += "  <ImageData WholeExtent=\"" + ext + "\" Origin=\"" + repr(qmin[0]) + " " + repr(qmin[1]) + " " + repr(qmin[2]) + "\" Spacing=\"" +
-            repr(step[0]) + " " + repr(step[1]) + " " + repr(step[2]) + "\">\n";
+    head += "  <ImageData WholeExtent=\"" + ext + "\" Origin=\"" + py_repr(qmin[0]) + " " + py_repr(qmin[1]) + " " + py_repr(qmin[2]) + "\" Spacing=\"" +
+            py_repr(step[0]) + " " + py_repr(step[1]) + " " + py_repr(step[2]) + "\">\n";
     head += "    <Piece Extent=\"" + ext + "\">\n";
     head += std::string("      <PointData ") + (ncomp == 3 ? "Vectors" : "Scalars") + "=\"" + name + "\">\n";
     head += fmt("        <DataArray Name=\"%s\" type=\"Float64\" NumberOfComponents=\"%d\" format=\"appended\" offset=\"0\"/>\n", name, ncomp);
@@ -122,6 +111,28 @@ void vti_appended(const std::string &path, const GridSpec &g, const char *name, 
 }
 
 }  // namespace
+
+// Shortest round-trip decimal with Python's repr() layout: fixed notation for 1e-4 <= |x| < 1e16, else d.ddde+XX
+std::string py_repr(double x) {
+    if (x != x) return "nan";
+    if (std::isinf(x)) return x < 0 ? "-inf" : "inf";
+    if (x == 0.0) return std::signbit(x) ? "-0.0" : "0.0";
+    char buf[48];
+    int prec = 1;
+    for (; prec <= 17; ++prec) {
+        snprintf(buf, sizeof buf, "%.*e", prec - 1, x);
+        if (std::strtod(buf, nullptr) == x) break;
+    }
+    std::string m(buf);
+    const size_t epos = m.find('e');
+    const int e = std::atoi(m.c_str() + epos + 1);
+    if (e >= -4 && e < 16) {
+        const int dec = std::max(prec - 1 - e, 1);           // digits after the point; at least ".0"
+        snprintf(buf, sizeof buf, "%.*f", dec, x);
+        return buf;
+    }
+    return m.substr(0, epos) + fmt("e%+03d", e);
+}
 
 // Fortran Ew.d: 0.dddddE+ee (gfortran drops the 'E' when the exponent needs three digits; asterisks on overflow)
 std::string fortran_e(double x, int w, int d) {
@@ -145,6 +156,10 @@ std::string fortran_e(double x, int w, int d) {
 std::string ld_real(double x) {
     const double ax = std::fabs(x);
     char buf[64];
+    // e.g. the z spacing of a tilted 2-D grid: vtkplot.f90:33-38 divides a non-zero extent by npts-1 = 0; gfortran prints
+    // non-finite values right-justified in the same 25-column field
+    if (x != x) return rjust("NaN", 26);
+    if (std::isinf(x)) return rjust(x < 0 ? "-Infinity" : "Infinity", 26);
     if (ax != 0.0 && !(0.1 <= ax && ax < 1e16)) {
         snprintf(buf, sizeof buf, "%.16E", ax);
         std::string m(buf);

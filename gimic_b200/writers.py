@@ -52,6 +52,10 @@ def _ld_real(x):
     """gfortran list-directed real(8): 17 significant digits, F form for 1e-1 <= |x| < 1e16"""
     x = float(x)
     ax = abs(x)
+    if x != x or ax == float("inf"):
+        # e.g. the z spacing of a tilted 2-D grid: vtkplot.f90:33-38 divides a non-zero extent by npts-1 = 0; gfortran prints
+        # non-finite values right-justified in the same 25-column field
+        return ("NaN" if x != x else ("-Infinity" if x < 0 else "Infinity")).rjust(26)
     if ax != 0.0 and not (0.1 <= ax < 1e16):
         m, e = f"{ax:.16E}".split("E")
         s = ("-" if x < 0 else "") + m + f"E{int(e):+04d}"
@@ -97,7 +101,7 @@ def _vti_geometry(grid):
     step = qmax - qmin                                          # vtkplot.f90:33-38
     for i in range(3):
         if step[i] > 1e-8:
-            step[i] = step[i] / (npts[i] - 1)
+            step[i] = step[i] / (npts[i] - 1) if npts[i] > 1 else float("inf")     # IEEE x/0 like the Fortran
     return qmin, step
 
 

@@ -1,0 +1,54 @@
+/* gimic_b200_driver.h -- C ABI of the native run-mode driver (libgimic_b200_driver.so, host-only C++17).
+ *
+ * What it replaces: the reference's executable pair -- the `gimic` front end (src/gimic.in:25-159: parse gimic.inp with
+ * getkw, validate with check_top/check_grid :161-283, hand the keywords to gimic.bin) and `program gimic`
+ * (src/fgimic/gimic.F90:7-58 main, :60-261 initialize / driver / run_cdens / run_integral), together with the grid set-up
+ * (grid.f90, magnet.f90), the writers (vtkplot.f90, jfield.f90:250-443) and the report formats (integral.f90:167-183,
+ * 306-322,502-510; jfield.f90:584-929).  Same gimic.inp, same files in the work directory (mol.xyz, grid.xyz, jvec*.vti,
+ * jmod*.vti, jmod*.txt, acid.vti, jvec.vtu, sigma*.vtu, intchi*.vtu), same stdout report.
+ *
+ * The driver is a CLIENT of include/gimic_b200.h: every number on the hot path comes out of libgimic_b200.so (CUDA, no CPU
+ * fallback); this layer does input, geometry, orchestration and text.  `gimic-b200` (gimic_b200/gimic-b200) is the
+ * command-line program over these entry points.
+ *
+ * All functions return 0 or a negative GIMIC_B200_E* code (include/gimic_b200.h); the message is available from
+ * gimic_b200_driver_last_error() (thread-local).
+ */
+#ifndef GIMIC_B200_DRIVER_H
+#define GIMIC_B200_DRIVER_H
+
+#include "gimic_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    GIMIC_B200_RUN_DRYRUN = 1,        /* -y / dryrun=on (src/gimic.in:53-54,139-140; gimic.F90:174-185): lay out the grid, write
+                                         mol.xyz / grid.xyz, print the banners, calculate nothing; needs no GPU */
+    GIMIC_B200_RUN_VTK_APPENDED = 2   /* extra: .vti files with raw appended Float64 blocks instead of ASCII e14.6 */
+};
+
+/* One gimic.inp: `gimic gimic.inp > report` (src/gimic.in:116-159 + program gimic).  workdir NULL: the directory of the
+ * input file (basis / xdens / grid files are resolved against it, outputs are written into it).  device: CUDA ordinal or -1.
+ * report_path NULL: the report goes to stdout. */
+int gimic_b200_run_input(const char *inpfile, const char *workdir, int device, int flags, const char *report_path);
+
+/* A current-profile scan (jobscripts/src/current-profile-local-submit: `gimic gimic.N.inp > gimic.N.out` for every slice):
+ * inputs that agree on basis, densities and Advanced settings share ONE device context, and all their plane integrals go
+ * through ONE tensor pass per spin case (gimic_b200_integrate_batch).  Each report is written to <input stem>.out. */
+int gimic_b200_run_scan(int n, const char *const *inpfiles, int device, int flags);
+
+/* Writers alone (vtkplot.f90:14-391, jfield.f90:356-376,531-541): lay `data` out on the grid that gimic.inp describes and
+ * write it as `filename` in the work directory.  kind: "vti_scalar" (n = npoints), "vti_vector" (3 x npoints, with the
+ * CellData block and the radius mask of 2-D bond grids), "jmod_txt" (3 x npoints), "vtu_vector" / "vtu_scalar" (needs
+ * grid.1.ele).  For a caller that computed a field through the batched C ABI itself (e.g. the reference's Fortran loops). */
+int gimic_b200_write_field(const char *inpfile, const char *workdir, const char *kind, const double *data, long n,
+                           const char *filename, int flags);
+
+const char *gimic_b200_driver_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIMIC_B200_DRIVER_H */

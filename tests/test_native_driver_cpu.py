@@ -1,0 +1,220 @@
+"""CPU-side checks of the native (C++) run-mode driver, libgimic_b200_driver.so + the gimic-b200 program
+(include/gimic_b200_driver.h): the compiled counterpart of `gimic gimic.inp` (src/gimic.in:25-159 + src/fgimic/gimic.F90).
+Input parsing, grid geometry, field direction, report text and every file format must equal the Python driver above the same
+C ABI (which the other tests pin against the oracle and the reference's goldens) byte for byte; what needs the GPU is in
+tests/test_native_driver_gpu.py."""
+import ctypes as C
+import filecmp
+import io
+import os
+import re
+import shutil
+import subprocess
+import numpy as np
+import pytest
+
+import fixtures
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = fixtures.GOLD
+INPUTS = os.path.join(GOLD, "inputs")
+EXE = os.path.join(ROOT, "gimic_b200", "gimic-b200")
+DRV_SO = os.path.join(ROOT, "gimic_b200", "libgimic_b200_driver.so")
+ALL_INPUTS = sorted(f[:-4] for f in os.listdir(INPUTS))
+
+
+@pytest.fixture(scope="module")
+def D():
+    import __graft_entry__ as ge
+    from gimic_b200 import _lib
+    if not (os.path.exists(_lib.SO_PATH) and os.path.exists(DRV_SO) and os.path.exists(EXE)):
+        ge.build()
+    _lib.lib()                                   # libgimic_b200.so first (RTLD_GLOBAL), the driver links against it
+    L = C.CDLL(DRV_SO)
+    L.gimic_b200_run_input.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+    L.gimic_b200_run_scan.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int]
+    L.gimic_b200_write_field.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_long, C.c_char_p, C.c_int]
+    L.gimic_b200_driver_last_error.restype = C.c_char_p
+    return L
+
+
+def _mol_for(name):
+    return "c4h4_MOL" if name.startswith("c4h4") else "open_shell_MOL" if name.startswith("open") else "benzene_MOL"
+
+
+def _workdir(base, name, text=None):
+    d = base / name
+    d.mkdir(parents=True)
+    shutil.copy(os.path.join(GOLD, _mol_for(name)), d / "MOL")
+    if text is None:
+        shutil.copy(os.path.join(INPUTS, name + ".inp"), d / "gimic.inp")
+    else:
+        (d / "gimic.inp").write_text(text)
+    if "read-grid" in name or "magnetizability" in name:
+        np.savetxt(d / "gridfile.grd", fixtures.golden_npz("c4h4_readgrid.npz")["grid"][:64], fmt="%.6f")
+    return d
+
+
+def test_driver_header_symbols_exported(D):
+    hdr = open(os.path.join(ROOT, "include", "gimic_b200_driver.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(gimic_b200_\w+)\s*\(", hdr))
+    assert names == {"gimic_b200_run_input", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_driver_last_error"}
+    for n in names:
+        assert hasattr(D, n), n
+
+
+@pytest.mark.parametrize("name", ALL_INPUTS)
+def test_native_dry_run_equals_python_driver(D, tmp_path, name):
+    """-y on every reference input (19 benzene, 2 c4h4, 2 open-shell): report text, mol.xyz and grid.xyz byte-identical to the
+    Python driver -- covers the gimic.inp reader, std / bond / file grids, even / gauss / lobatto axes, rotation, radius and
+    get_magnet.  No XDENS in the directory, no GPU in this container: the dry run reaches no compute entry point."""
+    from gimic_b200 import driver
+    dn, dp = _workdir(tmp_path / "nat", name), _workdir(tmp_path / "py", name)
+    p = subprocess.run([EXE, "-y", str(dn / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    out = io.StringIO()
+    driver.Driver(str(dp / "gimic.inp"), out=out, dryrun=True).run()
+    assert p.stdout == out.getvalue()
+    assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
+    for f in os.listdir(dn):
+        assert filecmp.cmp(dn / f, dp / f, shallow=False), f
+    # the library entry point with a report file gives the same text
+    rep = tmp_path / "report.txt"
+    assert D.gimic_b200_run_input(os.fsencode(dn / "gimic.inp"), None, -1, 1, os.fsencode(rep)) == 0
+    assert rep.read_text() == out.getvalue()
+
+
+def _py_grid(d):
+    from gimic_b200 import inp as _inp, grids, driver
+    I = _inp.parse_file(str(d / "gimic.inp"))
+    _, xyz = driver.mol_geometry(str(d / "MOL"))
+    return grids.from_input(I, xyz, str(d))
+
+
+def _write(D, d, kind, data, fname, flags=0):
+    v = np.ascontiguousarray(data, dtype=np.float64).ravel()
+    rc = D.gimic_b200_write_field(os.fsencode(d / "gimic.inp"), None, kind.encode(), v.ctypes.data_as(C.POINTER(C.c_double)), v.size,
+                                  fname.encode(), flags)
+    assert rc == 0, D.gimic_b200_driver_last_error().decode()
+
+
+@pytest.mark.parametrize("name", ["benzene_3d", "benzene_2d", "benzene_keyword-radius", "benzene_keyword-rotation", "open-shell_3d"])
+def test_native_vti_writers_equal_python_writers(D, tmp_path, name):
+    """write_vtk_imagedata / write_vtk_vector_imagedata (vtkplot.f90:14-234) incl. the CellData block of cell-averaged |J|, the
+    radius mask of 2-D bond grids (jfield.f90:310-346) and the appended-binary extra: native bytes == Python writer bytes"""
+    from gimic_b200 import writers
+    text = open(os.path.join(INPUTS, name + ".inp")).read()
+    if name == "benzene_keyword-radius":        # make it the 2-D even bond grid the mask applies to
+        text = text.replace("calc=integral", "calc=cdens").replace("type=gauss", "type=even")
+        text = re.sub(r"gauss_order\s*=\s*\d+", "", text)
+    d = _workdir(tmp_path, name, text)
+    g = _py_grid(d)
+    rng = np.random.default_rng(11)
+    vec = rng.normal(size=(g.n, 3)) * 10.0 ** rng.integers(-12, 3, size=(g.n, 1))
+    vec[::17] = 0.0
+    sca = rng.normal(size=g.n) * 10.0 ** rng.integers(-120, 3, size=g.n)     # three-digit exponents drop the 'E'
+    for appended in (False, True):
+        tag = "a" if appended else ""
+        writers.write_vti_vector(str(d / f"py_vec{tag}.vti"), g, writers.radius_masked_vectors(g, vec), appended)
+        writers.write_vti_scalar(str(d / f"py_sca{tag}.vti"), g, sca, appended)
+        _write(D, d, "vti_vector", vec, f"nat_vec{tag}.vti", 2 if appended else 0)
+        _write(D, d, "vti_scalar", sca, f"nat_sca{tag}.vti", 2 if appended else 0)
+        assert filecmp.cmp(d / f"py_vec{tag}.vti", d / f"nat_vec{tag}.vti", shallow=False), (name, appended)
+        assert filecmp.cmp(d / f"py_sca{tag}.vti", d / f"nat_sca{tag}.vti", shallow=False), (name, appended)
+    if name == "benzene_keyword-radius":
+        masked = writers.radius_masked_vectors(g, vec)
+        assert masked is not vec and (np.abs(masked).sum(1) == 0).sum() > (np.abs(vec).sum(1) == 0).sum()    # the mask did bite
+
+
+def test_native_jmod_txt_and_vtu_writers_equal_python_writers(D, tmp_path):
+    """jmod.txt ('(6f11.7)' rows with a blank line per i-row on bond grids, jfield.f90:356-376,531-541) and the UnstructuredGrid
+    writers (vtkplot.f90:241-391) on a Grid(file) input with a TetGen .ele file"""
+    from gimic_b200 import writers
+    rng = np.random.default_rng(12)
+    d = _workdir(tmp_path, "benzene_integration-gauss", open(os.path.join(INPUTS, "benzene_integration-gauss.inp")).read().replace("calc=integral", "calc=cdens"))
+    g = _py_grid(d)
+    vec = rng.normal(size=(g.n, 3))
+    writers.write_jmod_txt(str(d / "py_jmod.txt"), g, vec, regular=True)
+    _write(D, d, "jmod_txt", vec, "nat_jmod.txt")
+    assert filecmp.cmp(d / "py_jmod.txt", d / "nat_jmod.txt", shallow=False)
+    d2 = _workdir(tmp_path, "c4h4_read-grid")
+    with open(d2 / "grid.1.ele", "w") as f:
+        f.write("3  4  0\n    1    14  17  4  7\n    2     10     8   12   45\n    3     5     6     7     8\n")
+    g2 = _py_grid(d2)
+    assert g2.n == 64
+    vec2 = rng.normal(size=(g2.n, 3)) * 1e-3
+    cells = writers.read_ele(str(d2 / "grid.1.ele"))
+    writers.write_vtu_vector(str(d2 / "py.vtu"), g2.points(), vec2, cells)
+    writers.write_vtu_scalar(str(d2 / "pys.vtu"), g2.points(), vec2[:, 0], cells)
+    _write(D, d2, "vtu_vector", vec2, "nat.vtu")
+    _write(D, d2, "vtu_scalar", vec2[:, 0], "nats.vtu")
+    assert filecmp.cmp(d2 / "py.vtu", d2 / "nat.vtu", shallow=False) and filecmp.cmp(d2 / "pys.vtu", d2 / "nats.vtu", shallow=False)
+    # wrong length and unknown kind are errors with a message, not crashes
+    v = np.zeros(5)
+    rc = D.gimic_b200_write_field(os.fsencode(d2 / "gimic.inp"), None, b"vtu_vector", v.ctypes.data_as(C.POINTER(C.c_double)), 5, b"x.vtu", 0)
+    assert rc < 0 and b"expected 192 values" in D.gimic_b200_driver_last_error()
+    rc = D.gimic_b200_write_field(os.fsencode(d2 / "gimic.inp"), None, b"nonsense", v.ctypes.data_as(C.POINTER(C.c_double)), 64, b"x", 0)
+    assert rc < 0 and b"unknown kind" in D.gimic_b200_driver_last_error()
+
+
+BAD_INPUTS = [
+    ("calc=cdens\nmagnet=[0,0,1]\n", "no Grid section"),
+    ("calc=nonsense\nmagnet=[0,0,1]\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n}\n", "unknown option calc"),
+    ("calc=cdens\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n}\n", "Direction of magnetic field"),
+    ("calc=cdens\nmagnet=[0,0,1]\nmagnet_axis=z\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n}\n", "Both magnet vector and axis"),
+    ("calc=cdens\nmagnet=[0,0,1]\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n}\n", "Required option 'jvec'"),
+    ("calc=cdens\nmagnet=[0,0,1]\nGrid(bond){\n type=even\n bond=[1,2]\n fixpoint=3\n distance=1.0\n spacing=[1,1,1]\n}\n", "width and height"),
+    ("calc=cdens\nmagnet=[0,0,1]\nfrobnicate=3\nGrid(file){\n file=gridfile.grd\n}\n", "unknown keyword 'frobnicate'"),
+    ("calc=cdens\nmagnet=[0,0,1]\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n", "unbalanced"),
+    ("calc=cdens\nmagnet=[0,0,0]\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n}\n", "Magnetic field is zero"),
+    ("calc=cdens\nmagnet=[0,0,1]\nGrid(bond){\n type=even\n bond=[1,99]\n fixpoint=3\n distance=1.0\n height=[-1,1]\n width=[-1,1]\n spacing=[1,1,1]\n}\n", "out of range"),
+]
+
+
+@pytest.mark.parametrize("text,needle", BAD_INPUTS)
+def test_native_rejects_bad_input_like_the_front_end(D, tmp_path, text, needle):
+    """check_top / check_grid (src/gimic.in:161-283) and the grid set-up errors: a negative code and the front end's message;
+    the Python reader raises on the same inputs"""
+    from gimic_b200 import inp as _inp, grids, driver
+    d = _workdir(tmp_path, "benzene_bad", 'basis="MOL"\n' + text)
+    rc = D.gimic_b200_run_input(os.fsencode(d / "gimic.inp"), None, -1, 1, os.fsencode(tmp_path / "rep"))
+    assert rc < 0
+    assert needle in D.gimic_b200_driver_last_error().decode()
+    with pytest.raises(Exception):
+        I = _inp.parse_file(str(d / "gimic.inp"))
+        _, xyz = driver.mol_geometry(str(d / "MOL"))
+        grids.get_magnet(grids.from_input(I, xyz, str(d)), I.get("magnet_axis"), I.get("magnet"))
+    p = subprocess.run([EXE, "-y", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and needle in p.stderr
+
+
+def test_native_driver_has_no_cpu_fallback(D, tmp_path):
+    """without -y the run needs the device context: in a GPU-less container it fails loudly (nothing is computed on the host)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    d = _workdir(tmp_path, "c4h4_integration")
+    fixtures.write_xdens(str(d / "XDENS"), fixtures.golden_npz("c4h4_xdens.npz")["xdens"])
+    p = subprocess.run([EXE, str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 1 and "Induced current" not in p.stdout
+    assert "CUDA" in p.stderr or "cuda" in p.stderr
+    rc = D.gimic_b200_run_input(os.fsencode(d / "gimic.inp"), None, -1, 0, os.fsencode(tmp_path / "rep"))
+    assert rc == -3                                           # GIMIC_B200_ECUDA
+    missing = subprocess.run([EXE, str(tmp_path / "nothing.inp")], capture_output=True, text=True, timeout=60)
+    assert missing.returncode == 1 and "cannot open input file" in missing.stderr
+
+
+def test_python_repr_layout_of_the_appended_header_numbers(D, tmp_path):
+    """the appended-VTK extra prints Origin / Spacing like Python's repr(float): fixed notation for 1e-4 <= |x| < 1e16"""
+    from gimic_b200 import writers
+    text = ("basis=MOL\ncalc=cdens\nmagnet=[0,0,1]\nGrid(std){\n type=even\n origin=[-100000.0, 1.0e-5, 0.30000000000000004]\n ivec=[1,0,0]\n jvec=[0,1,0]\n"
+            " lengths=[2.0e5, 1.0e-4, 3.0]\n grid_points=[3,3,3]\n}\n")
+    d = _workdir(tmp_path, "benzene_repr", text)
+    g = _py_grid(d)
+    v = np.arange(g.n, dtype=np.float64)
+    writers.write_vti_scalar(str(d / "py.vti"), g, v, True)
+    _write(D, d, "vti_scalar", v, "nat.vti", 2)
+    assert filecmp.cmp(d / "py.vti", d / "nat.vti", shallow=False)
+    head = open(d / "nat.vti", "rb").read(400).decode("latin1")
+    assert 'Origin="-100000.0 1e-05 0.30000000000000004"' in head and 'Spacing="100000.0 5e-05 1.5"' in head

@@ -1,0 +1,163 @@
+"""The native (C++) driver on the GPU: `gimic-b200 gimic.inp` must write the same report and the same files as the Python driver
+above the same C ABI -- which tests/test_gpu_driver.py pins against the reference's goldens and the oracle.  Runs last among the
+GPU tests (file name order)."""
+import filecmp
+import io
+import os
+import re
+import shutil
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+import fixtures
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = fixtures.GOLD
+INPUTS = os.path.join(GOLD, "inputs")
+EXE = os.path.join(ROOT, "gimic_b200", "gimic-b200")
+sys.path.insert(0, GOLD)
+NUM = re.compile(r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eEdD]?[-+]\d+)?")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(EXE):
+        import __graft_entry__ as ge
+        ge.build()
+
+
+def _same_text(a, b, what):
+    """byte-identical; should the two runs ever differ in a last printed digit, the non-numeric text must still be identical
+    and the numbers equal at print precision"""
+    if a == b:
+        return
+    ta, tb = NUM.split(a), NUM.split(b)
+    assert ta == tb, f"{what}: layout differs"
+    na = np.array([float(x.replace("D", "E").replace("d", "e")) for x in NUM.findall(a)])
+    nb = np.array([float(x.replace("D", "E").replace("d", "e")) for x in NUM.findall(b)])
+    assert np.allclose(na, nb, rtol=2e-6, atol=1e-12 * max(1.0, np.abs(nb).max())), what
+
+
+def _pair(tmp_path, name, mol, xdens, extra=None):
+    dirs = []
+    for k in ("nat", "py"):
+        d = tmp_path / k / name
+        d.mkdir(parents=True)
+        shutil.copy(mol, d / "MOL"); shutil.copy(xdens, d / "XDENS")
+        shutil.copy(os.path.join(INPUTS, name + ".inp"), d / "gimic.inp")
+        if extra:
+            extra(d)
+        dirs.append(d)
+    return dirs
+
+
+def _run_both(dn, dp, args=()):
+    from gimic_b200.driver import Driver
+    p = subprocess.run([EXE, *args, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    out = io.StringIO()
+    Driver(str(dp / "gimic.inp"), out=out, vtk_appended=("appended" in args)).run()
+    _same_text(p.stdout, out.getvalue(), "report")
+    assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
+    for f in sorted(os.listdir(dn)):
+        if not filecmp.cmp(dn / f, dp / f, shallow=False):
+            _same_text(open(dn / f, errors="replace").read(), open(dp / f, errors="replace").read(), f)
+    return p.stdout
+
+
+def test_native_c4h4_read_grid_and_integration(tmp_path, cases):
+    """the two c4h4 reference cases: jvec.vtu on the 4110-point file grid (golden: 10 digits) and the bond-plane integral"""
+    from make_golden import read_vtu_vectors
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+
+    def extra(d):
+        np.savetxt(d / "gridfile.grd", gold["grid"], fmt="%.6f")
+        with open(d / "grid.1.ele", "w") as f:
+            f.write("3  4  0\n    1    1475  1730  1474  1717\n    2     100     8   112   245\n    3     5     6     7     8\n")
+    dn, dp = _pair(tmp_path, "c4h4_read-grid", cases["c4h4"]["mol"], cases["c4h4"]["xdens"], extra)
+    _run_both(dn, dp)
+    _, vec = read_vtu_vectors(str(dn / "jvec.vtu"))
+    ref = gold["jvec"]
+    assert np.abs(vec - ref).max() < 1e-9 * np.abs(ref).max() + 1e-14          # the reference's own golden, straight from the C++ driver
+    dn, dp = _pair(tmp_path, "c4h4_integration", cases["c4h4"]["mol"], cases["c4h4"]["xdens"])
+    text = _run_both(dn, dp)
+    want = next(b for b in fixtures.golden_json("c4h4_integration.json")["blocks"] if b["section"] == "current" and b["spin"] == "total")
+    m = re.search(r"Induced current \(au\)\s+:\s*([-\d.]+)", text)
+    assert m is not None and abs(float(m.group(1)) - want["au"]) < 1.01e-6       # the reference's printed value, from the C++ driver
+
+
+def test_native_open_shell_cases(tmp_path, cases):
+    """UHF: the 33^3 cdens run (8 .vti files through the J path, alpha/beta combined by linearity) and the four-spin-case integral"""
+    for name in ("open-shell_3d", "open-shell_integration"):
+        dn, dp = _pair(tmp_path, name, cases["open_shell"]["mol"], cases["open_shell"]["xdens"])
+        text = _run_both(dn, dp)
+        assert "Open-shell calculation" in text
+    assert os.path.exists(tmp_path / "nat" / "open-shell_3d" / "jvecspindens.vti")
+
+
+@pytest.mark.parametrize("inp_name", sorted(f[:-4] for f in os.listdir(INPUTS) if f.startswith("benzene_")))
+def test_native_every_benzene_input(tmp_path, cases, inp_name):
+    """all 19 test/benzene inputs (synthetic densities, nbf = 252): native == Python driver, incl. the ACID / tensor path, jmod.txt on
+    Gauss grids, rotation / radius / spacing keywords and the property report of the magnetizability input"""
+    xd = tmp_path / "XDENS"
+    fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))
+
+    def extra(d):
+        if inp_name != "benzene_magnetizability":
+            return
+        from gimic_b200.driver import read_mol_geometry
+        _, coords = read_mol_geometry(str(d / "MOL"))
+        rng = np.random.default_rng(5)
+        counts = rng.integers(60, 120, size=coords.shape[0])
+        pts = np.vstack([coords[a] + rng.normal(scale=1.5, size=(c, 3)) for a, c in enumerate(counts)])
+        np.savetxt(d / "gridfile.grd", pts, fmt="%.10f"); np.savetxt(d / "grid_w.grd", rng.uniform(0, 0.1, size=pts.shape[0]), fmt="%.12e")
+        shutil.copy(os.path.join(GOLD, "benzene_coord.au"), d / "coord.au")
+        np.savetxt(d / "nelpts.info", np.column_stack([np.arange(1, len(counts) + 1), counts]), fmt="%d")
+        with open(d / "grid.1.ele", "w") as f:
+            f.write("2  4  0\n    1    1  2  3  4\n    2     5     6     7     8\n")
+    dn, dp = _pair(tmp_path, inp_name, cases["benzene_mol"], xd, extra)
+    text = _run_both(dn, dp)
+    if inp_name == "benzene_magnetizability":
+        assert "isotropic magnetizability chi" in text and os.path.exists(dn / "intchi.vtu") and os.path.exists(dn / "sigma_zz12.vtu")
+
+
+def test_native_appended_vtk_and_scalar_modes(tmp_path, cases):
+    """--vtk appended, calc=edens and calc=divj"""
+    dn, dp = _pair(tmp_path, "open-shell_3d", cases["open_shell"]["mol"], cases["open_shell"]["xdens"])
+    _run_both(dn, dp, ("--vtk", "appended"))
+    for calc in ("edens", "divj"):
+        def extra(d, calc=calc):
+            txt = open(d / "gimic.inp").read().replace("calc=integral", "calc=" + calc)
+            txt = re.sub(r"Grid\(bond\) \{.*?\n\}", "Grid(base) {\n type=even\n origin=[-4.0,-3.0,-1.0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n"
+                         " lengths=[3.0,3.0,1.0]\n spacing=[0.5,0.5,0.5]\n}", txt, flags=re.S)
+            open(d / "gimic.inp", "w").write(txt)
+        dn, dp = _pair(tmp_path / calc, "c4h4_integration", cases["c4h4"]["mol"], cases["c4h4"]["xdens"], extra)
+        _run_both(dn, dp)
+        assert os.path.exists(dn / f"{calc}.vti")
+
+
+def test_native_scan_equals_python_scan(tmp_path, cases):
+    """a current-profile scan: `gimic-b200 gimic.0.inp ... gimic.5.inp` (one context, one batched tensor pass) writes the same
+    gimic.N.out reports as the Python scan and as separate native runs"""
+    from gimic_b200.driver import run_scan
+    dn, dp = _pair(tmp_path, "c4h4_integration", cases["c4h4"]["mol"], cases["c4h4"]["xdens"])
+    base = open(dn / "gimic.inp").read()
+    edges = np.linspace(-1.25614, 6.0, 7)
+    names = {"nat": [], "py": []}
+    for k in range(6):
+        txt = base.replace("width=[-1.25614, 6.0]", f"width=[{edges[k]:.6f}, {edges[k + 1]:.6f}]").replace("grid_points=[30, 30, 0]", "grid_points=[30, 9, 0]")
+        for key, d in (("nat", dn), ("py", dp)):
+            (d / f"gimic.{k}.inp").write_text(txt)
+            names[key].append(str(d / f"gimic.{k}.inp"))
+    p = subprocess.run([EXE, *names["nat"]], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    run_scan(names["py"])
+    for k in range(6):
+        a = open(dn / f"gimic.{k}.out").read()
+        _same_text(a, open(dp / f"gimic.{k}.out").read(), f"gimic.{k}.out")
+        single = subprocess.run([EXE, names["nat"][k]], capture_output=True, text=True, timeout=600)
+        assert single.returncode == 0, single.stderr
+        _same_text(a, single.stdout, f"separate run {k}")
