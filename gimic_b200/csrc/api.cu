@@ -315,10 +315,12 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
             if (c->h_info) cudaFreeHost(c->h_info);
             if (c->h_segs) cudaFreeHost(c->h_segs);
             if (c->h_tiles) cudaFreeHost(c->h_tiles);
-            c->h_info_cap = (size_t)ntiles + ntiles / 4 + 64;
-            CUDA_TRY(cudaMallocHost((void **)&c->h_info, c->h_info_cap * sizeof(TileInfo)));
-            CUDA_TRY(cudaMallocHost((void **)&c->h_segs, c->h_info_cap * sizeof(TileSeg)));
-            CUDA_TRY(cudaMallocHost((void **)&c->h_tiles, c->h_info_cap * sizeof(TileDesc)));
+            c->h_info = nullptr; c->h_segs = nullptr; c->h_tiles = nullptr; c->h_info_cap = 0;   // a failed allocation below must not leave stale pointers
+            const size_t cap = (size_t)ntiles + ntiles / 4 + 64;
+            CUDA_TRY(cudaMallocHost((void **)&c->h_info, cap * sizeof(TileInfo)));
+            CUDA_TRY(cudaMallocHost((void **)&c->h_segs, cap * sizeof(TileSeg)));
+            CUDA_TRY(cudaMallocHost((void **)&c->h_tiles, cap * sizeof(TileDesc)));
+            c->h_info_cap = cap;
         }
         if (c->geo.ensure((size_t)ntiles * sizeof(TileGeo)) || c->nraw.ensure((size_t)ntiles * sizeof(TileInfo)) ||
             c->segs.ensure((size_t)ntiles * sizeof(TileSeg)) || c->tiles.ensure((size_t)ntiles * sizeof(TileDesc)))
@@ -842,7 +844,7 @@ int gimic_b200_calc_basis(gimic_b200_handle c, long n, const double *r, double *
 
 int gimic_b200_property(gimic_b200_handle c, long n, const double *r, const double *w, const double *tens, int natoms,
                         const double *coords, int nseg, const long *seg_end, double *part, int flags) {
-    if (!c || !r || !w || !tens || !coords || !seg_end || !part || natoms < 0 || nseg <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
+    if (!c || !r || !w || !tens || !coords || !seg_end || !part || natoms < 0 || nseg <= 0 || n < 0) return fail(GIMIC_B200_EINVAL, "bad argument");
     if (seg_end[nseg - 1] != n) return fail(GIMIC_B200_EINVAL, "segment ends must be cumulative and finish at n");
     for (int i = 1; i < nseg; ++i) if (seg_end[i] < seg_end[i - 1]) return fail(GIMIC_B200_EINVAL, "segment ends must be non-decreasing");
     CUDA_TRY(cudaSetDevice(c->device));
