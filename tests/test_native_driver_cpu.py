@@ -218,3 +218,45 @@ def test_python_repr_layout_of_the_appended_header_numbers(D, tmp_path):
     assert filecmp.cmp(d / "py.vti", d / "nat.vti", shallow=False)
     head = open(d / "nat.vti", "rb").read(400).decode("latin1")
     assert 'Origin="-100000.0 1e-05 0.30000000000000004"' in head and 'Spacing="100000.0 5e-05 1.5"' in head
+
+
+SYNTAX_VARIANTS = {
+    "baseline": lambda t: t,
+    "crlf_free_spacing": lambda t: t.replace("=", "  =  ").replace("Grid(bond) {", "Grid ( bond )\n{"),
+    "continuation": lambda t: t.replace("grid_points=[30, 30, 0]", "grid_points=[30, |\n      30, |   \n\n 0]"),
+    "quotes_and_case": lambda t: t.replace("type=gauss", "type='gauss'").replace("acid=on", "acid=TRUE").replace("openshell=false", "openshell=No"),
+    "fortran_exponents": lambda t: t.replace("distance=1.32", "distance=0.132D+01").replace("height=[-5.0, 5.0]", "height=[-0.5d1 5.e0]"),
+    "comment_chars_in_strings": lambda t: t.replace('title=""', 'title="ring # 1 {test}"'),
+    "one_line_sections": lambda t: t.replace("Essential {\n    acid=on\n}", "Essential { acid=on jmod=off }"),
+    "gimlet_section_ignored": lambda t: t + "\nGimlet {\n  foo=1\n  bar=[1,2]\n}\n",
+    "trailing_garbage": lambda t: t + "\n}\n",                                   # unbalanced: both must refuse
+    "scalar_for_array": lambda t: t.replace("bond=[1,2]", "bond=1"),            # both accept a bare scalar for an array keyword? they must agree
+    "array_for_scalar": lambda t: t.replace("fixpoint=4", "fixpoint=[4,5]"),   # both must refuse
+    "bad_bool": lambda t: t.replace("acid=on", "acid=maybe"),
+    "bad_number": lambda t: t.replace("distance=1.32", "distance=1.3.2"),
+    "unknown_section": lambda t: t + "\nNonsense {\n a=1\n}\n",
+}
+
+
+@pytest.mark.parametrize("variant", sorted(SYNTAX_VARIANTS))
+def test_gimic_inp_surface_syntax_agrees_with_the_python_reader(D, tmp_path, variant):
+    """doc/input.rst:4-19 surface syntax (free spacing, '|' continuation, quotes, Fortran d-exponents, '#' inside strings, one-line
+    sections, the ignored Gimlet section) and its error cases: the native reader accepts exactly what the Python reader accepts and
+    then produces the identical dry-run report and grid.xyz"""
+    from gimic_b200 import driver
+    text = SYNTAX_VARIANTS[variant](open(os.path.join(INPUTS, "benzene_integration-gauss.inp")).read())
+    dn, dp = _workdir(tmp_path / "nat", "benzene_v", text), _workdir(tmp_path / "py", "benzene_v", text)
+    p = subprocess.run([EXE, "-y", str(dn / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    out = io.StringIO()
+    try:
+        driver.Driver(str(dp / "gimic.inp"), out=out, dryrun=True).run()
+        py_ok = True
+    except Exception:
+        py_ok = False
+    assert (p.returncode == 0) == py_ok, (variant, p.stderr)
+    if py_ok:
+        assert p.stdout == out.getvalue()
+        assert filecmp.cmp(dn / "grid.xyz", dp / "grid.xyz", shallow=False)
+    expect_ok = variant not in ("trailing_garbage", "array_for_scalar", "bad_bool", "bad_number", "unknown_section")
+    if variant != "scalar_for_array":
+        assert py_ok == expect_ok, variant
