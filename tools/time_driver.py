@@ -13,3 +13,17 @@ for case, inp in (("open_shell", "open-shell_3d"), ("c4h4", "c4h4_integration"),
         drv.run(); t2 = time.perf_counter()
         print(f"{inp:26s} rep {rep}: setup (parse MOL/XDENS, upload) {t1 - t0:6.3f} s, run (compute + write files) {t2 - t1:6.3f} s")
         drv.g.close()
+
+if "--native" in sys.argv:
+    # the gimic-b200 program: whole-process wall clock (CUDA context creation + MOL/XDENS parse + compute + files), the number to put
+    # beside the reference's `gimic gimic.inp` timings (c4h4/integration 2.13 s, open-shell/integration 10.04 s in its golden stdout)
+    import subprocess
+    exe = os.path.join(ROOT, "gimic_b200", "gimic-b200")
+    for case, inp in (("open_shell", "open-shell_3d"), ("c4h4", "c4h4_integration"), ("open_shell", "open-shell_integration")):
+        d = cases[case]["dir"]
+        shutil.copy(os.path.join(fixtures.GOLD, "inputs", inp + ".inp"), os.path.join(d, "gimic.inp"))
+        for rep in range(2):
+            t0 = time.perf_counter()
+            p = subprocess.run([exe, os.path.join(d, "gimic.inp")], capture_output=True, text=True)
+            t1 = time.perf_counter()
+            print(f"{inp:26s} rep {rep}: gimic-b200 process wall clock {t1 - t0:6.3f} s (rc {p.returncode}, {len(p.stdout)} bytes of report)")
