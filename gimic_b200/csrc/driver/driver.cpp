@@ -428,7 +428,7 @@ int guarded(F &&body) {
         body();
         return 0;
     } catch (const InputError &e) {
-        return fail(GIMIC_B200_EINVAL, e.what());
+        return fail(std::string(e.what()).find("cannot open") == 0 ? GIMIC_B200_EIO : GIMIC_B200_EINVAL, e.what());
     } catch (const DriverError &e) {
         // errors that come out of the library keep its message; classify by what the library reported last
         const std::string lib = gimic_b200_last_error();

@@ -260,3 +260,27 @@ def test_gimic_inp_surface_syntax_agrees_with_the_python_reader(D, tmp_path, var
     expect_ok = variant not in ("trailing_garbage", "array_for_scalar", "bad_bool", "bad_number", "unknown_section")
     if variant != "scalar_for_array":
         assert py_ok == expect_ok, variant
+
+
+def test_driver_header_is_c99_and_a_c_caller_links(D, tmp_path):
+    """include/gimic_b200_driver.h from plain C: a dry run through gimic_b200_run_input and the error path"""
+    d = _workdir(tmp_path, "benzene_2d")
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "gimic_b200_driver.h"
+int main(int argc, char **argv) {
+    int rc = gimic_b200_run_input(argv[1], NULL, -1, GIMIC_B200_RUN_DRYRUN, argv[2]);
+    int bad = gimic_b200_run_input("/nonexistent/gimic.inp", NULL, -1, GIMIC_B200_RUN_DRYRUN, NULL);
+    printf("%d %d %s\n", rc, bad, gimic_b200_driver_last_error());
+    (void)argc;
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.join(ROOT, "gimic_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libgimic_b200_driver.so", "-l:libgimic_b200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe), str(d / "gimic.inp"), str(tmp_path / "rep.txt")], text=True)
+    assert out.startswith("0 -2 cannot open input file"), out       # GIMIC_B200_EIO
+    assert "Dry run, not calculating" in (tmp_path / "rep.txt").read_text() and (d / "grid.xyz").exists()
