@@ -86,6 +86,17 @@ module b200_module
             import; type(c_ptr), value :: h; integer(c_long), value :: n; integer(c_int), value :: flags
             real(c_double) :: r(3,*), jvec(3,*), b(3), jmod(*)
         end function
+        ! ---- include/gimic_b200_driver.h (libgimic_b200_driver.so): run modes and writers ------------------------------
+        ! `gimic gimic.inp` as one call (src/gimic.in:116-159 + program gimic); flags: 1 dry run, 2 appended-binary .vti
+        integer(c_int) function gimic_b200_run_input(inpfile, workdir, device, flags, report_path) bind(c)
+            import; character(c_char) :: inpfile(*), workdir(*), report_path(*); integer(c_int), value :: device, flags
+        end function
+        ! writers of vtkplot.f90:14-391 / jfield.f90:531-541 on the grid that gimic.inp describes; kind = 'vti_scalar',
+        ! 'vti_vector', 'jmod_txt', 'vtu_vector', 'vtu_scalar' (NUL-terminated)
+        integer(c_int) function gimic_b200_write_field(inpfile, workdir, kind, data, n, fname, flags) bind(c)
+            import; character(c_char) :: inpfile(*), workdir(*), kind(*), fname(*); real(c_double) :: data(*)
+            integer(c_long), value :: n; integer(c_int), value :: flags
+        end function
         function gimic_b200_last_error() bind(c) result(msg)
             import; type(c_ptr) :: msg
         end function
