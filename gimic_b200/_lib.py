@@ -17,7 +17,7 @@ ip = C.POINTER(C.c_int)
 LEGACY_SYMBOLS = ["gimic_init", "gimic_finalize", "gimic_set_uhf", "gimic_set_magnet", "gimic_set_spin",
                   "gimic_set_screening", "gimic_calc_jtensor", "gimic_calc_jvector", "gimic_calc_modj",
                   "gimic_get_gauss_points", "mkgausspoints"]
-API_SYMBOLS = ["gimic_b200_default_opts", "gimic_b200_create", "gimic_b200_create_from_arrays", "gimic_b200_destroy",
+API_SYMBOLS = ["gimic_b200_default_opts", "gimic_b200_create", "gimic_b200_create_from_arrays", "gimic_b200_destroy", "gimic_b200_device_count",
                "gimic_b200_nbf", "gimic_b200_natoms", "gimic_b200_atom_coords", "gimic_b200_is_uhf",
                "gimic_b200_calc_jtensors", "gimic_b200_calc_basis", "gimic_b200_calc_fields", "gimic_b200_fields_from_tensors", "gimic_b200_jmod_from_jvec",
                "gimic_b200_calc_jtensors_grid", "gimic_b200_integrate", "gimic_b200_integrate_batch", "gimic_b200_property", "gimic_b200_property_integrand", "gimic_b200_gauss_points",

@@ -532,6 +532,11 @@ int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double
 }
 
 int gimic_b200_destroy(gimic_b200_handle h) { delete h; return 0; }
+int gimic_b200_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GIMIC_B200_ECUDA, "no CUDA device available: gimic-b200 has no CPU path"); }
+    return ndev;
+}
 int gimic_b200_nbf(gimic_b200_handle h) { return h ? (h->hb.spherical ? h->hb.nbf_sph : h->hb.nbf) : fail(GIMIC_B200_EINVAL, "null handle"); }
 int gimic_b200_natoms(gimic_b200_handle h) { return h ? h->hb.natoms : fail(GIMIC_B200_EINVAL, "null handle"); }
 int gimic_b200_is_uhf(gimic_b200_handle h) { return h ? h->opts.uhf : fail(GIMIC_B200_EINVAL, "null handle"); }

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <sys/stat.h>
 
 #include "../../../include/gimic_b200_driver.h"
@@ -67,7 +68,8 @@ class Run {
     RunOptions opt;
     Printer out;
     bool uhf = false;
-    std::shared_ptr<Context> ctx;
+    std::shared_ptr<Context> ctx;                   // primary context (devices[0])
+    std::vector<std::shared_ptr<Context>> peers;    // contexts on the other listed devices (multi-device run)
     std::string context_key;
     std::vector<std::string> symbols;
     std::vector<double> xyz;
@@ -96,16 +98,34 @@ class Run {
         for (int a = 0; a < natoms; ++a) symbols.push_back(sym.substr(2 * (size_t)a, 2));
         if (!inp.flag("dryrun")) {
             ctx = find_shared(context_key);
+            gimic_b200_opts go;
+            gimic_b200_default_opts(&go);
+            go.uhf = uhf; go.giao = inp.flag("Advanced.GIAO"); go.diamag = inp.flag("Advanced.diamag");
+            go.paramag = inp.flag("Advanced.paramag"); go.screening = inp.flag("Advanced.screening");
+            go.screening_thrs = inp.real("Advanced.screening_thrs"); go.device = o.devices.empty() ? o.device : o.devices[0];
+            go.spherical = inp.flag("Advanced.spherical");
             if (!ctx) {
-                gimic_b200_opts go;
-                gimic_b200_default_opts(&go);
-                go.uhf = uhf; go.giao = inp.flag("Advanced.GIAO"); go.diamag = inp.flag("Advanced.diamag");
-                go.paramag = inp.flag("Advanced.paramag"); go.screening = inp.flag("Advanced.screening");
-                go.screening_thrs = inp.real("Advanced.screening_thrs"); go.device = o.device;
-                go.spherical = inp.flag("Advanced.spherical");
                 ctx = std::make_shared<Context>();
                 ctx->key = context_key;
-                check(gimic_b200_create(&ctx->h, mol.c_str(), xdens.c_str(), &go));
+                if (o.devices.size() > 1) {
+                    // one context per listed GPU, created concurrently (each reads MOL / XDENS itself: use the binary XDENS cache
+                    // for large cases); densities are replicated, nothing is exchanged between devices afterwards
+                    peers.resize(o.devices.size() - 1);
+                    std::vector<std::string> errs(o.devices.size());
+                    std::vector<std::thread> th;
+                    for (size_t d = 0; d < o.devices.size(); ++d)
+                        th.emplace_back([&, d] {
+                            gimic_b200_opts gd = go;
+                            gd.device = o.devices[d];
+                            auto c = d == 0 ? ctx : (peers[d - 1] = std::make_shared<Context>());
+                            c->key = context_key;
+                            if (gimic_b200_create(&c->h, mol.c_str(), xdens.c_str(), &gd) < 0) errs[d] = gimic_b200_last_error();
+                        });
+                    for (auto &t : th) t.join();
+                    for (const auto &e : errs) if (!e.empty()) throw DriverError(e);
+                } else {
+                    check(gimic_b200_create(&ctx->h, mol.c_str(), xdens.c_str(), &go));
+                }
             }
             check(gimic_b200_atom_coords(ctx->h, xyz.data()));
         }
@@ -147,17 +167,48 @@ class Run {
     }
 
   private:
+    // Runs fn(handle, device index, lo, hi) for one contiguous slab of range(n) per device, each on its own host thread (the C ABI is thread-safe
+    // per handle, errors are thread-local).  Slabs are the block partition of schedule() (parallel.F90:66-84); outputs go to
+    // disjoint parts of caller-owned host arrays, so the devices exchange nothing.
+    template <class Fn>
+    void over_devices(long n, Fn fn) const {
+        const size_t nd = 1 + peers.size();
+        if (nd == 1) { check(fn(ctx->h, (size_t)0, 0L, n)); return; }
+        std::vector<std::string> errs(nd);
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < nd; ++d) {
+            const long base = n / (long)nd, rem = n % (long)nd;
+            const long lo = (long)d * base + std::min<long>((long)d, rem), hi = lo + base + ((long)d < rem ? 1 : 0);
+            if (hi <= lo) continue;
+            gimic_b200_handle h = d == 0 ? ctx->h : peers[d - 1]->h;
+            th.emplace_back([&errs, fn, h, lo, hi, d] { if (fn(h, d, lo, hi) < 0) errs[d] = gimic_b200_last_error(); });
+        }
+        for (auto &t : th) t.join();
+        for (const auto &e : errs) if (!e.empty()) throw DriverError(e);
+    }
+
     // calc_jtensors (jfield.f90:62-138) on the whole grid
     std::vector<double> tensors(int spincase) const {
         const long n = grid.n();
         std::vector<double> t((size_t)n * 9);
+        double *tp = t.data();
         if (grid.is_file()) {
-            check(gimic_b200_calc_jtensors(ctx->h, n, grid.xdata.data(), spincase, t.data(), 0));
+            const double *xp = grid.xdata.data();
+            over_devices(n, [=](gimic_b200_handle h, size_t, long lo, long hi) { return gimic_b200_calc_jtensors(h, hi - lo, xp + 3 * lo, spincase, tp + 9 * lo, 0); });
         } else {
             const gimic_b200_grid g = grid.cstruct();
-            check(gimic_b200_calc_jtensors_grid(ctx->h, &g, 0, n, spincase, t.data(), 0));
+            over_devices(n, [=](gimic_b200_handle h, size_t, long lo, long hi) { return gimic_b200_calc_jtensors_grid(h, &g, lo, hi, spincase, tp + 9 * lo, 0); });
         }
         return t;
+    }
+
+    // J (and signed |J|, rho, div J) straight from the contraction, point slabs over the devices
+    void point_fields(const std::vector<double> &r, int spincase, double *jvec, double *jmod, double *edens, double *divj) const {
+        const double *rp = r.data(), *B = magnet.data();
+        over_devices((long)r.size() / 3, [=](gimic_b200_handle h, size_t, long lo, long hi) {
+            return gimic_b200_calc_fields(h, hi - lo, rp + 3 * lo, B, spincase, nullptr, jvec ? jvec + 3 * lo : nullptr, jmod ? jmod + lo : nullptr, nullptr,
+                                          edens ? edens + lo : nullptr, divj ? divj + lo : nullptr, 1e-3, 0);
+        });
     }
 
     static std::vector<double> combine(const std::vector<double> &a, const std::vector<double> &b, double sign) {
@@ -187,8 +238,7 @@ class Run {
             for (int sc : {GIMIC_B200_ALPHA, GIMIC_B200_BETA}) {
                 if (j_only) {
                     cache[sc].assign((size_t)n * 3, 0.0);
-                    check(gimic_b200_calc_fields(ctx->h, n, r.data(), magnet.data(), sc, nullptr, cache[sc].data(), nullptr, nullptr, nullptr,
-                                                 nullptr, 1e-3, 0));
+                    point_fields(r, sc, cache[sc].data(), nullptr, nullptr, nullptr);
                 } else {
                     cache[sc] = tensors(sc);
                 }
@@ -207,8 +257,7 @@ class Run {
                     if (want_jmod) check(gimic_b200_jmod_from_jvec(ctx->h, n, r.data(), jv.data(), magnet.data(), jmod.data(), 0));
                 } else {
                     jv.assign((size_t)n * 3, 0.0);
-                    check(gimic_b200_calc_fields(ctx->h, n, r.data(), magnet.data(), sc, nullptr, jv.data(), want_jmod ? jmod.data() : nullptr,
-                                                 nullptr, nullptr, nullptr, 1e-3, 0));
+                    point_fields(r, sc, jv.data(), want_jmod ? jmod.data() : nullptr, nullptr, nullptr);
                 }
             } else {
                 tens = uhf ? cache[sc] : tensors(sc);
@@ -352,8 +401,18 @@ class Run {
         } else {
             const gimic_b200_grid g = grid.cstruct();
             for (int sc : cases) {
-                Sums s{};
-                check(gimic_b200_integrate(ctx->h, &g, magnet.data(), sc, sc == GIMIC_B200_TOTAL ? what : (what & 3), 0, grid.npts[1], s.data()));
+                // rows j split over the devices like schedule() (parallel.F90:66-84); the <= 7 partial sums are added on the host
+                // in device order (the collect_sum of integral.f90:157-161), so the result does not depend on thread timing
+                const size_t nd = 1 + peers.size();
+                std::vector<Sums> part(nd, Sums{});
+                const int w = sc == GIMIC_B200_TOTAL ? what : (what & 3);
+                const double *B = magnet.data();
+                Sums *pp = part.data();
+                over_devices((long)grid.npts[1], [=](gimic_b200_handle h, size_t d, long lo, long hi) {
+                    return gimic_b200_integrate(h, &g, B, sc, w, (int)lo, (int)hi, pp[d].data());
+                });
+                Sums s = part[0];
+                for (size_t d = 1; d < nd; ++d) for (int k = 0; k < 7; ++k) s[(size_t)k] += part[d][(size_t)k];
                 results[sc] = s;
             }
         }
@@ -410,8 +469,7 @@ class Run {
         const long n = grid.n();
         std::vector<double> v((size_t)n, 0.0);
         const bool ed = calc == "edens";
-        check(gimic_b200_calc_fields(ctx->h, n, r.data(), magnet.data(), GIMIC_B200_TOTAL, nullptr, nullptr, nullptr, nullptr, ed ? v.data() : nullptr,
-                                     ed ? nullptr : v.data(), 1e-3, 0));
+        point_fields(r, GIMIC_B200_TOTAL, nullptr, nullptr, ed ? v.data() : nullptr, ed ? nullptr : v.data());
         if (!grid.is_file() && grid.gtype == "even" && grid.npts[0] > 1 && grid.npts[1] > 1)
             write_vti_scalar(join_path(workdir, calc + ".vti"), grid, v, opt.vtk_appended);
         else
@@ -504,6 +562,7 @@ int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt) {
             files.f.push_back(o);
             RunOptions ro = opt;
             ro.workdir.clear();                                   // every input runs in its own directory
+            if (!ro.devices.empty()) { ro.device = ro.devices[0]; ro.devices.clear(); }   // a scan batches all planes on one device
             auto finder = [&](const std::string &key) {
                 for (const auto &r : runs) if (r->ctx && r->context_key == key) return r->ctx;
                 return std::shared_ptr<Context>();
@@ -594,6 +653,30 @@ int gimic_b200_run_input(const char *inpfile, const char *workdir, int device, i
     o.dryrun = (flags & GIMIC_B200_RUN_DRYRUN) != 0;
     o.vtk_appended = (flags & GIMIC_B200_RUN_VTK_APPENDED) != 0;
     o.device = device;
+    if (workdir) o.workdir = workdir;
+    FILE *out = stdout;
+    if (report_path) {
+        out = std::fopen(report_path, "w");
+        if (!out) { gbd::g_error = std::string("cannot write ") + report_path; return GIMIC_B200_EIO; }
+    }
+    const int rc = gbd::run_input(inpfile, o, out);
+    if (report_path) std::fclose(out); else std::fflush(out);
+    return rc;
+}
+
+int gimic_b200_run_input_multi(const char *inpfile, const char *workdir, int ndevices, const int *devices, int flags, const char *report_path) {
+    if (!inpfile || ndevices < 0 || (ndevices > 0 && !devices)) { gbd::g_error = "bad argument"; return GIMIC_B200_EINVAL; }
+    gbd::RunOptions o;
+    o.dryrun = (flags & GIMIC_B200_RUN_DRYRUN) != 0;
+    o.vtk_appended = (flags & GIMIC_B200_RUN_VTK_APPENDED) != 0;
+    if (ndevices == 0) {                                          // all GPUs of the node
+        const int nd = gimic_b200_device_count();
+        if (nd < 0) { gbd::g_error = gimic_b200_last_error(); return nd; }
+        for (int d = 0; d < nd; ++d) o.devices.push_back(d);
+    } else {
+        o.devices.assign(devices, devices + ndevices);
+    }
+    if (!o.devices.empty()) o.device = o.devices[0];
     if (workdir) o.workdir = workdir;
     FILE *out = stdout;
     if (report_path) {

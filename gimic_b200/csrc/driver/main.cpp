@@ -8,7 +8,8 @@
 #include "../../../include/gimic_b200_driver.h"
 
 static void usage(FILE *f) {
-    std::fputs("usage: gimic-b200 [-y|--dryrun] [--workdir DIR] [--vtk ascii|appended] [--device N] [gimic.inp ...]\n"
+    std::fputs("usage: gimic-b200 [-y|--dryrun] [--workdir DIR] [--vtk ascii|appended] [--device N | --devices all|0,1,..] [gimic.inp ...]\n"
+               "  --devices: one process, one context + host thread per listed GPU (point slabs / plane rows split, nothing exchanged)\n"
                "  one input: files are written to its directory (or --workdir), the report to stdout\n"
                "  several inputs (a current-profile scan): one device context, integrals batched into one tensor pass,\n"
                "  each report written to <input stem>.out\n", f);
@@ -18,6 +19,8 @@ int main(int argc, char **argv) {
     std::vector<const char *> files;
     const char *workdir = nullptr;
     int flags = 0, device = -1;
+    bool multi = false;
+    std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto value = [&](const char *opt) -> const char * {
@@ -28,6 +31,21 @@ int main(int argc, char **argv) {
         else if (a == "-y" || a == "--dryrun") flags |= GIMIC_B200_RUN_DRYRUN;
         else if (a == "--workdir") workdir = value("--workdir");
         else if (a == "--device") device = std::atoi(value("--device"));
+        else if (a == "--devices") {
+            const std::string v = value("--devices");
+            multi = true;
+            if (v != "all") {
+                size_t pos = 0;
+                while (pos <= v.size()) {
+                    const size_t comma = v.find(',', pos);
+                    const std::string tok = v.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+                    if (tok.empty() || tok.find_first_not_of("0123456789") != std::string::npos) { std::fprintf(stderr, "gimic-b200: bad device list '%s'\n", v.c_str()); return 2; }
+                    devices.push_back(std::atoi(tok.c_str()));
+                    if (comma == std::string::npos) break;
+                    pos = comma + 1;
+                }
+            }
+        }
         else if (a == "--vtk") {
             const std::string v = value("--vtk");
             if (v == "appended") flags |= GIMIC_B200_RUN_VTK_APPENDED;
@@ -37,8 +55,10 @@ int main(int argc, char **argv) {
         else files.push_back(argv[i]);
     }
     if (files.empty()) files.push_back("gimic.inp");
-    const int rc = files.size() == 1 ? gimic_b200_run_input(files[0], workdir, device, flags, nullptr)
-                                     : gimic_b200_run_scan((int)files.size(), files.data(), device, flags);
+    int rc;
+    if (files.size() > 1) rc = gimic_b200_run_scan((int)files.size(), files.data(), !devices.empty() ? devices[0] : device, flags);
+    else if (multi && !(flags & GIMIC_B200_RUN_DRYRUN)) rc = gimic_b200_run_input_multi(files[0], workdir, (int)devices.size(), devices.data(), flags, nullptr);
+    else rc = gimic_b200_run_input(files[0], workdir, device, flags, nullptr);
     if (rc != 0) {
         std::fprintf(stderr, "gimic-b200: %s\n", gimic_b200_driver_last_error());
         return 1;

@@ -132,6 +132,8 @@ struct RunOptions {
     bool dryrun = false;         // -y
     bool vtk_appended = false;   // --vtk appended (extra)
     int device = -1;
+    std::vector<int> devices;    // more than one entry: single-process multi-device run (one context per listed GPU, one host
+                                 // thread each); point slabs / plane rows are split like schedule() of parallel.F90:66-84
     std::string workdir;         // default: the directory of the input file
 };
 

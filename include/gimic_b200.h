@@ -94,6 +94,9 @@ int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double
                                   int dens_flags, const gimic_b200_opts *opts);
 int gimic_b200_destroy(gimic_b200_handle h);
 
+/* Number of CUDA devices visible to the process (for callers that place one context per GPU), or GIMIC_B200_ECUDA. */
+int gimic_b200_device_count(void);
+
 int gimic_b200_nbf(gimic_b200_handle h);
 int gimic_b200_natoms(gimic_b200_handle h);
 int gimic_b200_atom_coords(gimic_b200_handle h, double *xyz /* 3 x natoms */);

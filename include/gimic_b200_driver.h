@@ -34,6 +34,14 @@ enum {
  * report_path NULL: the report goes to stdout. */
 int gimic_b200_run_input(const char *inpfile, const char *workdir, int device, int flags, const char *report_path);
 
+/* The same run on several GPUs of one node from ONE process: a context per listed device (densities replicated), one host
+ * thread each; cdens splits the flat point index into contiguous slabs, integral mode splits the plane rows j -- the block
+ * partition of schedule() (src/fgimic/parallel.F90:66-84) -- and the <= 7 partial sums are added on the host in device order.
+ * Nothing is exchanged between the devices.  ndevices == 0: every GPU of the node.  (The torchrun entry `python -m gimic_b200`
+ * is the one-process-per-GPU form of the same partition, with an NCCL all-reduce for the integrals.) */
+int gimic_b200_run_input_multi(const char *inpfile, const char *workdir, int ndevices, const int *devices, int flags,
+                               const char *report_path);
+
 /* A current-profile scan (jobscripts/src/current-profile-local-submit: `gimic gimic.N.inp > gimic.N.out` for every slice):
  * inputs that agree on basis, densities and Advanced settings share ONE device context, and all their plane integrals go
  * through ONE tensor pass per spin case (gimic_b200_integrate_batch).  Each report is written to <input stem>.out. */

@@ -59,7 +59,7 @@ def test_driver_header_symbols_exported(D):
     hdr = open(os.path.join(ROOT, "include", "gimic_b200_driver.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b(gimic_b200_\w+)\s*\(", hdr))
-    assert names == {"gimic_b200_run_input", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_driver_last_error"}
+    assert names == {"gimic_b200_run_input", "gimic_b200_run_input_multi", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_driver_last_error"}
     for n in names:
         assert hasattr(D, n), n
 
@@ -284,3 +284,21 @@ int main(int argc, char **argv) {
     out = subprocess.check_output([str(exe), str(d / "gimic.inp"), str(tmp_path / "rep.txt")], text=True)
     assert out.startswith("0 -2 cannot open input file"), out       # GIMIC_B200_EIO
     assert "Dry run, not calculating" in (tmp_path / "rep.txt").read_text() and (d / "grid.xyz").exists()
+
+
+def test_multi_device_switch_without_gpus(D, tmp_path):
+    """--devices (one process, one context per GPU): the dry run ignores it, a real run without GPUs fails loudly, a malformed list
+    is a usage error"""
+    import torch
+    d = _workdir(tmp_path, "c4h4_integration")
+    p = subprocess.run([EXE, "-y", "--devices", "all", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and "Dry run, not calculating" in p.stdout
+    bad = subprocess.run([EXE, "--devices", "0,x", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 2 and "bad device list" in bad.stderr
+    if not torch.cuda.is_available():
+        fixtures.write_xdens(str(d / "XDENS"), fixtures.golden_npz("c4h4_xdens.npz")["xdens"])
+        for devs in ("all", "0,1"):
+            q = subprocess.run([EXE, "--devices", devs, str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
+            assert q.returncode == 1 and ("CUDA" in q.stderr or "cuda" in q.stderr) and "Induced current" not in q.stdout
+        D.gimic_b200_run_input_multi.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_char_p]
+        assert D.gimic_b200_run_input_multi(os.fsencode(d / "gimic.inp"), None, 0, None, 0, os.fsencode(tmp_path / "rep")) == -3

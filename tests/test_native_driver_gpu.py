@@ -35,7 +35,7 @@ def _same_text(a, b, what):
     if a == b:
         return
     ta, tb = NUM.split(a), NUM.split(b)
-    assert ta == tb, f"{what}: layout differs"
+    assert [x.split() for x in ta] == [x.split() for x in tb], f"{what}: layout differs"      # blanks move with a number's sign
     na = np.array([float(x.replace("D", "E").replace("d", "e")) for x in NUM.findall(a)])
     nb = np.array([float(x.replace("D", "E").replace("d", "e")) for x in NUM.findall(b)])
     assert np.allclose(na, nb, rtol=2e-6, atol=1e-12 * max(1.0, np.abs(nb).max())), what
@@ -161,3 +161,24 @@ def test_native_scan_equals_python_scan(tmp_path, cases):
         single = subprocess.run([EXE, names["nat"][k]], capture_output=True, text=True, timeout=600)
         assert single.returncode == 0, single.stderr
         _same_text(a, single.stdout, f"separate run {k}")
+
+
+@pytest.mark.parametrize("name,case", [("c4h4_integration", "c4h4"), ("open-shell_3d", "open_shell"), ("c4h4_read-grid", "c4h4")])
+def test_native_multi_device_partition_equals_single_device(tmp_path, cases, name, case):
+    """--devices 0,0: two contexts (here on the same GPU), point slabs / plane rows split between them -- the single-process form of
+    schedule() (parallel.F90:66-84).  Same report and files as the single-device run at print precision (tiles differ, so the
+    summation order inside a point may)."""
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+
+    def extra(d):
+        if name == "c4h4_read-grid":
+            np.savetxt(d / "gridfile.grd", gold["grid"], fmt="%.6f")
+    dn, dp = _pair(tmp_path, name, cases[case]["mol"], cases[case]["xdens"], extra)
+    one = subprocess.run([EXE, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=600)
+    two = subprocess.run([EXE, "--devices", "0,0", str(dp / "gimic.inp")], capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0 and two.returncode == 0, (one.stderr, two.stderr)
+    _same_text(one.stdout, two.stdout, "report")
+    assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
+    for f in sorted(os.listdir(dn)):
+        if not filecmp.cmp(dn / f, dp / f, shallow=False):
+            _same_text(open(dn / f, errors="replace").read(), open(dp / f, errors="replace").read(), f)
