@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -484,16 +486,18 @@ void gimic_b200_default_opts(gimic_b200_opts *o) {
 int gimic_b200_create(gimic_b200_handle *h, const char *mol, const char *xdens, const gimic_b200_opts *opts) {
     if (!h || !mol || !xdens) return fail(GIMIC_B200_EINVAL, "null argument");
     *h = nullptr;
-    gimic_b200_ctx *c = new gimic_b200_ctx();
+    try {
+    std::unique_ptr<gimic_b200_ctx> holder(new gimic_b200_ctx());
+    gimic_b200_ctx *c = holder.get();
     if (opts) c->opts = *opts; else gimic_b200_default_opts(&c->opts);
     c->mol_path = mol; c->xdens_path = xdens;
     std::string err;
-    if (!gb::parse_mol(mol, c->hb, err)) { delete c; return fail(GIMIC_B200_EIO, err); }
+    if (!gb::parse_mol(mol, c->hb, err)) return fail(GIMIC_B200_EIO, err);
     c->hb.spherical = c->opts.spherical != 0;
     // spherical=on: XDENS is over the 2l+1 components per shell (get_ncgto, intgrl.f90:134-138)
     const int nbf = c->hb.spherical ? c->hb.nbf_sph : c->hb.nbf, nmat = c->opts.uhf ? 8 : 4;
     std::vector<double> dens;
-    if (!gb::read_xdens(xdens, nbf, nmat, dens, err)) { delete c; return fail(GIMIC_B200_EIO, err); }
+    if (!gb::read_xdens(xdens, nbf, nmat, dens, err)) return fail(GIMIC_B200_EIO, err);
     const size_t nn = (size_t)nbf * nbf;
     if (c->opts.uhf)   // "scaling perturbed densities by 0.5", dens.f90:94-98
         for (int sp = 0; sp < 2; ++sp) for (int b = 1; b < 4; ++b) { double *m = &dens[(sp * 4 + b) * nn]; for (size_t i = 0; i < nn; ++i) m[i] /= 2.0; }
@@ -509,9 +513,11 @@ int gimic_b200_create(gimic_b200_handle *h, const char *mol, const char *xdens, 
     }
     int rc = init_device(c);
     if (!rc) rc = finish_create(c, dens.data(), c->opts.uhf ? dens.data() + 4 * nn : nullptr, false);
-    if (rc) { delete c; return rc; }
-    *h = c;
+    if (rc) return rc;
+    *h = holder.release();
     return 0;
+    } catch (const std::bad_alloc &) { return fail(GIMIC_B200_ENOMEM, "out of host memory"); }
+      catch (const std::exception &e) { return fail(GIMIC_B200_EINVAL, e.what()); }
 }
 
 int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double *coords, const int *nctr_per_atom, const int *ctr_l,
@@ -519,16 +525,20 @@ int gimic_b200_create_from_arrays(gimic_b200_handle *h, int natoms, const double
                                   const double *dens_beta, int dens_flags, const gimic_b200_opts *opts) {
     if (!h || !coords || !nctr_per_atom || !ctr_l || !ctr_npf || !xp || !cc || !dens_alpha) return fail(GIMIC_B200_EINVAL, "null argument");
     *h = nullptr;
-    gimic_b200_ctx *c = new gimic_b200_ctx();
+    try {
+    std::unique_ptr<gimic_b200_ctx> holder(new gimic_b200_ctx());
+    gimic_b200_ctx *c = holder.get();
     if (opts) c->opts = *opts; else gimic_b200_default_opts(&c->opts);
     std::string err;
-    if (!gb::basis_from_arrays(natoms, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, turbomole_order, c->hb, err)) { delete c; return fail(GIMIC_B200_EINVAL, err); }
+    if (!gb::basis_from_arrays(natoms, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, turbomole_order, c->hb, err)) return fail(GIMIC_B200_EINVAL, err);
     c->hb.spherical = c->opts.spherical != 0;
     int rc = init_device(c);
     if (!rc) rc = finish_create(c, dens_alpha, dens_beta, (dens_flags & GIMIC_B200_DEVICE_PTR) != 0);
-    if (rc) { delete c; return rc; }
-    *h = c;
+    if (rc) return rc;
+    *h = holder.release();
     return 0;
+    } catch (const std::bad_alloc &) { return fail(GIMIC_B200_ENOMEM, "out of host memory"); }
+      catch (const std::exception &e) { return fail(GIMIC_B200_EINVAL, e.what()); }
 }
 
 int gimic_b200_destroy(gimic_b200_handle h) { delete h; return 0; }
@@ -900,10 +910,13 @@ int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrat
 
 int gimic_b200_convert_xdens(const char *xdens_text, int nbf, int nmat, const char *xdens_binary) {
     if (!xdens_text || !xdens_binary || nbf <= 0 || (nmat != 4 && nmat != 8)) return fail(GIMIC_B200_EINVAL, "bad argument");
+    try {
     std::vector<double> v; std::string err;
     if (!gb::read_xdens(xdens_text, nbf, nmat, v, err)) return fail(GIMIC_B200_EIO, err);
     if (!gb::write_xdens_binary(xdens_binary, nbf, nmat, v.data(), err)) return fail(GIMIC_B200_EIO, err);
     return 0;
+    } catch (const std::bad_alloc &) { return fail(GIMIC_B200_ENOMEM, "out of host memory"); }
+      catch (const std::exception &e) { return fail(GIMIC_B200_EINVAL, e.what()); }
 }
 
 long gimic_b200_format_e(long n, const double *v, int w, int d, int per_line, int first_count, const char *prefix, char *out, long cap) {
@@ -922,6 +935,7 @@ long gimic_b200_format_f(long n, const double *v, int w, int d, int per_line, in
 
 int gimic_b200_mol_geometry(const char *mol, int max_atoms, double *xyz, char *symbols2) {
     if (!mol) return fail(GIMIC_B200_EINVAL, "null argument");
+    try {
     gb::HostBasis hb; std::string err;
     if (!gb::parse_mol(mol, hb, err)) return fail(GIMIC_B200_EIO, err);
     for (int a = 0; a < hb.natoms && a < max_atoms; ++a) {
@@ -929,6 +943,8 @@ int gimic_b200_mol_geometry(const char *mol, int max_atoms, double *xyz, char *s
         if (symbols2) { symbols2[2 * a] = hb.symbol[a].size() > 0 ? hb.symbol[a][0] : ' '; symbols2[2 * a + 1] = hb.symbol[a].size() > 1 ? hb.symbol[a][1] : ' '; }
     }
     return hb.natoms;
+    } catch (const std::bad_alloc &) { return fail(GIMIC_B200_ENOMEM, "out of host memory"); }
+      catch (const std::exception &e) { return fail(GIMIC_B200_EINVAL, e.what()); }
 }
 
 int gimic_b200_c2s_rows(int l, int turbomole_order, double *po) {

@@ -54,6 +54,7 @@ void make_axes(GridSpec &g, const Vec3 &step, const AxisOpts &o) {
         return;
     }
     if (o.gtype != "gauss" && o.gtype != "lobatto") throw DriverError("Unknown grid type: " + o.gtype);
+    if (o.gauss_order < 1) throw DriverError("gauss_order must be positive");
     long npts[3];                                             // setup_gauss_grid, grid.f90:291-349
     for (int d = 0; d < 3; ++d) {
         if (o.has_grid_points) npts[d] = o.grid_points[d];

@@ -112,7 +112,7 @@ bool parse_mol(const std::string &path, HostBasis &b, std::string &err) {
     r.line(s);
     if (!read_items(r, 1, t)) { err = "MOL file truncated (natoms)"; return false; }
     b.natoms = std::atoi(t[0].c_str());
-    if (b.natoms <= 0) { err = "MOL: bad atom count"; return false; }
+    if (b.natoms <= 0 || b.natoms > 10000000) { err = "MOL: bad atom count"; return false; }
     r.line(s);
     b.atom_shell_off.assign(1, 0);
     b.atom_func_off.assign(1, 0);
@@ -122,10 +122,14 @@ bool parse_mol(const std::string &path, HostBasis &b, std::string &err) {
         if (t.size() < 3) { err = "MOL: malformed atom header"; return false; }
         int nsh = std::atoi(t[2].c_str());
         if (nsh - 1 > MAX_L) { err = "Largest allowed l-quantum number in basis exceeded"; return false; }
+        if (nsh < 0) { err = "MOL: malformed atom header (shell count)"; return false; }
         if ((int)t.size() < 3 + nsh) { err = "MOL: malformed atom header (block counts)"; return false; }
         b.charge.push_back(to_double(t[0]));
         std::vector<int> nblk(nsh);
-        for (int i = 0; i < nsh; ++i) nblk[i] = std::atoi(t[3 + i].c_str());
+        for (int i = 0; i < nsh; ++i) {
+            nblk[i] = std::atoi(t[3 + i].c_str());
+            if (nblk[i] < 0 || nblk[i] > MAX_SHELLS_PER_ATOM) { err = "MOL: malformed atom header (block counts)"; return false; }   // posvec(99), basis.f90:118-136
+        }
         if (!r.line(s)) { err = "MOL file truncated (atom position)"; return false; }
         if (s.size() < 4) s.resize(4, ' ');
         b.symbol.push_back(s.substr(0, 2));
@@ -136,7 +140,7 @@ bool parse_mol(const std::string &path, HostBasis &b, std::string &err) {
             for (int blk = 0; blk < nblk[l]; ++blk) {
                 if (!read_items(r, 2, t)) { err = "MOL file truncated (block header)"; return false; }
                 int npf = std::atoi(t[0].c_str()), ncf = std::atoi(t[1].c_str());
-                if (npf <= 0 || ncf <= 0) { err = "MOL: bad contraction block"; return false; }
+                if (npf <= 0 || ncf <= 0 || npf > 10000 || ncf > 10000) { err = "MOL: bad contraction block"; return false; }
                 std::vector<double> xp(npf);
                 std::vector<std::vector<double>> co(ncf, std::vector<double>(npf));
                 for (int p = 0; p < npf; ++p) {

@@ -73,6 +73,8 @@ def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order
         return pts, wgt
     if gtype not in ("gauss", "lobatto"):
         raise ValueError("Unknown grid type: " + gtype)
+    if gauss_order < 1:
+        raise ValueError("gauss_order must be positive")
     npts = [0, 0, 0]                                     # setup_gauss_grid, grid.f90:291-349
     for d in range(3):
         if grid_points is not None:

@@ -168,6 +168,7 @@ BAD_INPUTS = [
     ("calc=cdens\nmagnet=[0,0,1]\nfrobnicate=3\nGrid(file){\n file=gridfile.grd\n}\n", "unknown keyword 'frobnicate'"),
     ("calc=cdens\nmagnet=[0,0,1]\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n", "unbalanced"),
     ("calc=cdens\nmagnet=[0,0,0]\nGrid(std){\n type=even\n origin=[0,0,0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n lengths=[1,1,1]\n spacing=[1,1,1]\n}\n", "Magnetic field is zero"),
+    ("calc=integral\nmagnet_axis=X\nGrid(bond){\n type=gauss\n gauss_order=0\n bond=[1,2]\n fixpoint=3\n distance=1.0\n height=[-1,1]\n width=[-1,1]\n grid_points=[9,9,0]\n}\n", "gauss_order must be positive"),
     ("calc=cdens\nmagnet=[0,0,1]\nGrid(bond){\n type=even\n bond=[1,99]\n fixpoint=3\n distance=1.0\n height=[-1,1]\n width=[-1,1]\n spacing=[1,1,1]\n}\n", "out of range"),
 ]
 
@@ -302,3 +303,24 @@ def test_multi_device_switch_without_gpus(D, tmp_path):
             assert q.returncode == 1 and ("CUDA" in q.stderr or "cuda" in q.stderr) and "Induced current" not in q.stdout
         D.gimic_b200_run_input_multi.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_char_p]
         assert D.gimic_b200_run_input_multi(os.fsencode(d / "gimic.inp"), None, 0, None, 0, os.fsencode(tmp_path / "rep")) == -3
+
+
+@pytest.mark.parametrize("mutation,needle", [
+    (lambda m: m.replace("\n      2  1\n", "\n   99999999999     2  1\n", 1), "bad contraction block"),       # found by fuzzing: used to allocate 16 GB
+    (lambda m: m.replace(" 6.0    1 4  5  3  2  1", " 6.0    1 -4  5  3  2  1", 1), "shell count"),
+    (lambda m: m.replace(" 6.0    1 4  5  3  2  1", " 6.0    1 4  5  3  2  100", 1), "block counts"),
+    (lambda m: m[: len(m) // 3], "truncated"),
+    (lambda m: "", "INTGRL"),
+])
+def test_malformed_mol_files_are_errors_not_crashes(D, tmp_path, mutation, needle):
+    """MOL reader (intgrl.f90:20-264) on damaged files: a message and a negative code within a second, no crash, no huge allocation"""
+    import time
+    mol = open(os.path.join(GOLD, "c4h4_MOL")).read()
+    bad = mutation(mol)
+    assert bad != mol
+    d = _workdir(tmp_path, "c4h4_integration")
+    (d / "MOL").write_text(bad)
+    t0 = time.perf_counter()
+    p = subprocess.run([EXE, "-y", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and needle in p.stderr, p.stderr
+    assert time.perf_counter() - t0 < 5.0
