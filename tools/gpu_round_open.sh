@@ -24,6 +24,7 @@ echo "== configs[3] (nbf=1512, ACID + jmod): tensor pass + HBM-bound field pass;
 timeout 600 python tools/bench_fields.py 128 > $OUT/${TAG}_bench_fields_config4.json 2>&1
 timeout 600 python tools/driver_e2e.py > $OUT/${TAG}_driver_e2e_config4.json 2>&1
 timeout 600 python tools/time_driver.py --native > $OUT/${TAG}_driver_small_cases.txt 2>&1
+timeout 300 python tools/legacy_latency.py > $OUT/${TAG}_legacy_latency.json 2>&1
 timeout 600 python tools/full_grid.py > $OUT/${TAG}_full_grid_256.json 2>&1
 
 echo "== ncu: launch list of the bench command, then ONE full capture of the contraction kernel"
