@@ -1,0 +1,278 @@
+"""End-to-end runs of the host-side layers above the C ABI in a container WITHOUT a GPU: the native C++ driver (gimic-b200) and the
+Python driver are pointed at a TEST DOUBLE of libgimic_b200.so (tests/mock_backend/mock_api.cpp, compiled into a temporary
+directory, never in-tree) whose compute entry points are answered by the CPU oracle.
+
+Checked here: (1) gimic-b200 writes byte-identical reports and files to the Python driver for every run mode (cdens closed / open
+shell, ACID, property, integrals, edens / divj, scan, appended VTK); (2) the single-process multi-device partition (two host
+threads, two contexts) reproduces the single-device run; (3) native driver + oracle backend reproduce the reference's own golden
+outputs (c4h4 jvec.vtu at 10 digits, the integration stdout windows, the eight open-shell .vti files).
+This says nothing about the CUDA kernels: tests/test_gpu_*.py hold those to the oracle on a B200."""
+import filecmp
+import io
+import os
+import re
+import shutil
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = fixtures.GOLD
+INPUTS = os.path.join(GOLD, "inputs")
+EXE = os.path.join(ROOT, "gimic_b200", "gimic-b200")
+sys.path.insert(0, GOLD)
+
+
+@pytest.fixture(scope="module")
+def mock_dir(tmp_path_factory):
+    import __graft_entry__ as ge
+    from gimic_b200 import _lib
+    if not (os.path.exists(_lib.SO_PATH) and os.path.exists(EXE)):
+        ge.build()
+    oracle_lib.lib()                                            # builds oracle/libgimic_oracle.so if needed
+    d = tmp_path_factory.mktemp("mock_backend")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", str(d / "libgimic_b200.so"),
+                           os.path.join(ROOT, "tests", "mock_backend", "mock_api.cpp"), os.path.join(ROOT, "gimic_b200", "csrc", "host_basis.cpp"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-l:libgimic_oracle.so", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    return d
+
+
+def _env(mock_dir):
+    e = dict(os.environ)
+    e["LD_LIBRARY_PATH"] = str(mock_dir) + os.pathsep + e.get("LD_LIBRARY_PATH", "")     # searched before the program's RUNPATH ($ORIGIN)
+    e["OMP_NUM_THREADS"] = "2"
+    return e
+
+
+def _native(mock_dir, args, timeout=900):
+    p = subprocess.run([EXE, *[str(a) for a in args]], capture_output=True, text=True, timeout=timeout, env=_env(mock_dir))
+    assert p.returncode == 0, p.stderr
+    return p.stdout
+
+
+PY_RUNNER = r'''
+import io, os, sys
+sys.path.insert(0, {root!r})
+from gimic_b200 import _lib
+_lib.SO_PATH = {so!r}                      # the test double instead of the CUDA library
+assert "TEST DOUBLE" in _lib.lib().gimic_b200_version().decode()
+from gimic_b200 import driver
+args = sys.argv[1:]
+appended = "--appended" in args
+files = [a for a in args if not a.startswith("--")]
+if len(files) > 1:
+    driver.run_scan(files)
+else:
+    out = io.StringIO()
+    driver.Driver(files[0], out=out, vtk_appended=appended).run()
+    sys.stdout.write(out.getvalue())
+'''
+
+
+def _python(mock_dir, args, timeout=900):
+    """the Python driver in a fresh interpreter bound to the test double (this process keeps the real library)"""
+    code = PY_RUNNER.format(root=ROOT, so=str(mock_dir / "libgimic_b200.so"))
+    p = subprocess.run([sys.executable, "-c", code, *[str(a) for a in args]], capture_output=True, text=True, timeout=timeout, env=_env(mock_dir))
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def _pair(tmp_path, name, mol, xdens, edit=None, extra=None):
+    dirs = []
+    for k in ("nat", "py"):
+        d = tmp_path / k / name
+        d.mkdir(parents=True)
+        shutil.copy(mol, d / "MOL"); shutil.copy(xdens, d / "XDENS")
+        txt = open(os.path.join(INPUTS, name + ".inp")).read()
+        (d / "gimic.inp").write_text(edit(txt) if edit else txt)
+        if extra:
+            extra(d)
+        dirs.append(d)
+    return dirs
+
+
+def _same_dirs(dn, dp):
+    assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
+    for f in sorted(os.listdir(dn)):
+        assert filecmp.cmp(dn / f, dp / f, shallow=False), f
+
+
+def _window(text, anchor, n=10):
+    lines = text.split("\n")
+    i = next(k for k, l in enumerate(lines) if l.startswith(anchor))
+    return [float(t) for l in lines[i:i + n] for t in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", l)]
+
+
+def _small(txt):
+    """shrink the quadrature so that the CPU oracle answers in seconds"""
+    return txt.replace("grid_points=[30, 30, 0]", "grid_points=[9, 9, 0]")
+
+
+def test_c4h4_read_grid_native_vs_python_and_golden(mock_dir, tmp_path, cases):
+    """test/c4h4/read-grid through gimic-b200: jvec.vtu equals the Python driver's bytes and the reference's golden at its 10 digits"""
+    from make_golden import read_vtu_vectors
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+
+    def extra(d):
+        np.savetxt(d / "gridfile.grd", gold["grid"], fmt="%.6f")
+        with open(d / "grid.1.ele", "w") as f:
+            f.write("3  4  0\n    1    1475  1730  1474  1717\n    2     100     8   112   245\n    3     5     6     7     8\n")
+    dn, dp = _pair(tmp_path, "c4h4_read-grid", cases["c4h4"]["mol"], cases["c4h4"]["xdens"], extra=extra)
+    a = _native(mock_dir, [dn / "gimic.inp"])
+    b = _python(mock_dir, [dp / "gimic.inp"])
+    assert a == b and "Closed-shell calculation" in a
+    _same_dirs(dn, dp)
+    pts, vec = read_vtu_vectors(str(dn / "jvec.vtu"))
+    ref = gold["jvec"]
+    assert pts.shape == vec.shape == (4110, 3) and np.allclose(pts, gold["grid"], atol=1e-9)
+    big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    assert (np.abs(vec - ref)[big] / np.abs(ref)[big]).max() < 4e-9
+    assert np.abs(vec - ref).max() < 1e-9 * np.abs(ref).max() + 1e-14
+
+
+@pytest.mark.parametrize("case,name,gold_json", [("c4h4", "c4h4_integration", "c4h4_integration.json"),
+                                                  ("open_shell", "open-shell_integration", "open_shell_integration.json")])
+def test_integration_reports_native_vs_python_and_golden(mock_dir, tmp_path, cases, case, name, gold_json):
+    """test/c4h4/integration and test/open-shell/integration (36 x 36 Gauss plane, all spin cases): the gimic-b200 report is the
+    Python driver's, and its numbers are the ones the reference printed"""
+    dn, dp = _pair(tmp_path, name, cases[case]["mol"], cases[case]["xdens"])
+    a = _native(mock_dir, [dn / "gimic.inp"])
+    b = _python(mock_dir, [dp / "gimic.inp"])
+    assert a == b
+    _same_dirs(dn, dp)
+    gold = fixtures.golden_json(gold_json)
+    cur = [blk for blk in gold["blocks"] if blk["section"] == "current"]
+    found = [float(x) for x in re.findall(r"Induced current \(au\)\s+:\s*([-\d.]+)", a)]
+    assert len(found) == len(cur) and np.allclose(found, [blk["au"] for blk in cur], rtol=0, atol=1.01e-6)
+    tail = a[a.index("*** Integrating current"):]                      # the window the reference's runtest compares
+    pos = [float(x) for x in re.findall(r"Positive contribution:\s*([-\d.]+)", tail)]
+    neg = [float(x) for x in re.findall(r"Negative contribution:\s*([-\d.]+)", tail)]
+    assert np.allclose(pos, [blk["pos"] for blk in cur], rtol=0, atol=1.01e-6) and np.allclose(neg, [blk["neg"] for blk in cur], rtol=0, atol=1.01e-6)
+
+
+def test_open_shell_3d_native_vs_python_and_golden(mock_dir, tmp_path, cases):
+    """test/open-shell/3d: eight .vti files (UHF, J path, alpha/beta combined by linearity) on a 17^3 subgrid of the reference's 33^3
+    grid (every second point, so the CPU oracle finishes in seconds): native == Python bytes, values == the reference's golden"""
+    from make_golden import read_vti
+    txt = open(os.path.join(INPUTS, "open-shell_3d.inp")).read()
+    assert "spacing=[0.5, 0.5, 0.5]" in txt
+    edit = lambda t: t.replace("spacing=[0.5, 0.5, 0.5]", "spacing=[1.0, 1.0, 1.0]")
+    dn, dp = _pair(tmp_path, "open-shell_3d", cases["open_shell"]["mol"], cases["open_shell"]["xdens"], edit=edit)
+    a = _native(mock_dir, [dn / "gimic.inp"])
+    b = _python(mock_dir, [dp / "gimic.inp"])
+    assert a == b and "Open-shell calculation" in a
+    _same_dirs(dn, dp)
+    assert all(os.path.exists(dn / f"jvec{t}.vti") and os.path.exists(dn / f"jmod{t}.vti") for t in ("", "alpha", "beta", "spindens"))
+    if True:
+        gold = fixtures.golden_npz("open_shell_3d.npz")
+        idx = gold["index"]
+        i, j, k = idx % 33, (idx // 33) % 33, idx // (33 * 33)
+        on = (i % 2 == 0) & (j % 2 == 0) & (k % 2 == 0)                  # golden sample points that lie on the 17^3 subgrid
+        sub = (i[on] // 2) + 17 * ((j[on] // 2) + 17 * (k[on] // 2))
+        assert on.sum() > 50
+        for tag in ("", "alpha", "beta", "spindens"):
+            jv = read_vti(str(dn / f"jvec{tag}.vti"))
+            gj = gold["jvec" + tag][on]
+            assert (np.abs(jv[sub] - gj) <= 2e-6 * np.abs(gj) + 1e-9 * np.abs(gj).max()).all(), tag
+
+
+def test_benzene_modes_native_vs_python(mock_dir, tmp_path, cases):
+    """benzene inputs with synthetic densities (nbf = 252) on shrunken grids: the ACID / tensor path (3d), a Gauss bond grid in cdens
+    mode (jmod.txt), the radius / rotation keywords, and the magnetizability input with prop=on (report + integrand plots)"""
+    from gimic_b200.driver import read_mol_geometry
+    xd = tmp_path / "XDENS"
+    fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))
+    shrink3 = lambda t: re.sub(r"grid_points=\[\s*\d+\s*,\s*\d+\s*,\s*\d+\s*\]", "grid_points=[6,5,4]", t)
+    shrink2 = lambda t: re.sub(r"grid_points=\[\s*\d+\s*,\s*\d+\s*,\s*0\s*\]", "grid_points=[9, 9, 0]", t)
+
+    def prop_files(d):
+        _, coords = read_mol_geometry(str(d / "MOL"))
+        rng = np.random.default_rng(5)
+        counts = rng.integers(6, 12, size=coords.shape[0])
+        pts = np.vstack([coords[a] + rng.normal(scale=1.5, size=(c, 3)) for a, c in enumerate(counts)])
+        np.savetxt(d / "gridfile.grd", pts, fmt="%.10f"); np.savetxt(d / "grid_w.grd", rng.uniform(0, 0.1, size=pts.shape[0]), fmt="%.12e")
+        shutil.copy(os.path.join(GOLD, "benzene_coord.au"), d / "coord.au")
+        np.savetxt(d / "nelpts.info", np.column_stack([np.arange(1, len(counts) + 1), counts]), fmt="%d")
+        with open(d / "grid.1.ele", "w") as f:
+            f.write("2  4  0\n    1    1  2  3  4\n    2     5     6     7     8\n")
+    for name, edit, extra in (("benzene_3d", shrink3, None), ("benzene_int-cdens", shrink2, None), ("benzene_keyword-radius", shrink2, None),
+                              ("benzene_keyword-rotation", shrink2, None), ("benzene_integration-lobatto", shrink2, None),
+                              ("benzene_magnetizability", None, prop_files)):
+        dn, dp = _pair(tmp_path, name, cases["benzene_mol"], xd, edit=edit, extra=extra)
+        a = _native(mock_dir, [dn / "gimic.inp"])
+        b = _python(mock_dir, [dp / "gimic.inp"])
+        assert a == b, name
+        _same_dirs(dn, dp)
+        if name == "benzene_3d":
+            assert os.path.exists(dn / "acid.vti") and os.path.exists(dn / "jmod.vti") and os.path.exists(dn / "jvec.vti")
+        if name == "benzene_magnetizability":
+            assert "isotropic magnetizability chi" in a and os.path.exists(dn / "intchi.vtu") and os.path.exists(dn / "sigma_zz12.vtu")
+
+
+def test_scalar_modes_appended_vtk_and_scan_native_vs_python(mock_dir, tmp_path, cases):
+    mol, xd = cases["c4h4"]["mol"], cases["c4h4"]["xdens"]
+    for calc in ("edens", "divj"):
+        def edit(txt, calc=calc):
+            txt = txt.replace("calc=integral", "calc=" + calc)
+            return re.sub(r"Grid\(bond\) \{.*?\n\}", "Grid(base) {\n type=even\n origin=[-4.0,-3.0,-1.0]\n ivec=[1,0,0]\n jvec=[0,1,0]\n"
+                          " lengths=[3.0,3.0,1.0]\n spacing=[0.5,0.5,0.5]\n}", txt, flags=re.S)
+        dn, dp = _pair(tmp_path / calc, "c4h4_integration", mol, xd, edit=edit)
+        assert _native(mock_dir, [dn / "gimic.inp"]) == _python(mock_dir, [dp / "gimic.inp"])
+        _same_dirs(dn, dp)
+        assert os.path.exists(dn / f"{calc}.vti")
+    # --vtk appended on a small open-shell cdens grid
+    edit = lambda t: t.replace("spacing=[0.5, 0.5, 0.5]", "spacing=[4.0, 4.0, 8.0]")
+    dn, dp = _pair(tmp_path / "app", "open-shell_3d", cases["open_shell"]["mol"], cases["open_shell"]["xdens"], edit=edit)
+    assert _native(mock_dir, ["--vtk", "appended", dn / "gimic.inp"]) == _python(mock_dir, ["--appended", dp / "gimic.inp"])
+    _same_dirs(dn, dp)
+    # scan: six slices of the c4h4 plane, one context, batched integrals; reports in gimic.N.out
+    dn, dp = _pair(tmp_path / "scan", "c4h4_integration", mol, xd)
+    base = open(dn / "gimic.inp").read()
+    edges = np.linspace(-1.25614, 6.0, 7)
+    names = {"nat": [], "py": []}
+    for k in range(6):
+        txt = base.replace("width=[-1.25614, 6.0]", f"width=[{edges[k]:.6f}, {edges[k + 1]:.6f}]").replace("grid_points=[30, 30, 0]", "grid_points=[9, 9, 0]")
+        assert txt != base
+        for key, d in (("nat", dn), ("py", dp)):
+            (d / f"gimic.{k}.inp").write_text(txt)
+            names[key].append(d / f"gimic.{k}.inp")
+    _native(mock_dir, names["nat"])
+    _python(mock_dir, names["py"])
+    for k in range(6):
+        a = open(dn / f"gimic.{k}.out").read()
+        assert a == open(dp / f"gimic.{k}.out").read(), k
+        assert a == _native(mock_dir, [names["nat"][k]]), k             # what a separate run prints
+        assert "Induced current (au)" in a
+
+
+@pytest.mark.parametrize("case,name,edit", [("c4h4", "c4h4_integration", None), ("open_shell", "open-shell_3d", "shrink"), ("c4h4", "c4h4_read-grid", None)])
+def test_multi_device_partition_equals_single_device(mock_dir, tmp_path, cases, case, name, edit):
+    """--devices 0,1 / all (the test double reports two devices): one context and one host thread per device, point slabs / plane
+    rows split like schedule() (parallel.F90:66-84).  The oracle evaluates every point independently, so files must be byte-identical
+    to the single-device run; integrals agree to the last printed digit (partial sums are added in device order)."""
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+    ed = (lambda t: t.replace("spacing=[0.5, 0.5, 0.5]", "spacing=[2.0, 2.0, 4.0]")) if edit else None
+
+    def extra(d):
+        if name == "c4h4_read-grid":
+            np.savetxt(d / "gridfile.grd", gold["grid"][:501], fmt="%.6f")
+    dn, dp = _pair(tmp_path, name, cases[case]["mol"], cases[case]["xdens"], edit=ed, extra=extra)
+    one = _native(mock_dir, [dn / "gimic.inp"])
+    two = _native(mock_dir, ["--devices", "0,1", dp / "gimic.inp"])
+    if name == "c4h4_integration":
+        na = np.array([float(x) for x in re.findall(r"[-+]?\d+\.\d+", one)]); nb = np.array([float(x) for x in re.findall(r"[-+]?\d+\.\d+", two)])
+        assert re.sub(r"[-+]?\d+\.\d+", "#", one) == re.sub(r"[-+]?\d+\.\d+", "#", two) and np.allclose(na, nb, rtol=0, atol=1.01e-6)
+    else:
+        assert one == two
+    _same_dirs(dn, dp)
+    d3 = tmp_path / "all"
+    shutil.copytree(dp, d3)
+    for f in os.listdir(d3):
+        if f not in ("MOL", "XDENS", "gimic.inp", "gridfile.grd"):
+            os.remove(d3 / f)
+    assert _native(mock_dir, ["--devices", "all", d3 / "gimic.inp"]) == two
+    _same_dirs(dp, d3)
