@@ -156,7 +156,8 @@ class Driver:
         if self.world == 1:
             return part
         import torch
-        dev = torch.device("cuda", torch.cuda.current_device())
+        # NCCL moves device tensors; any other backend (gloo in the CPU tests) moves host tensors
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else torch.device("cpu")
         sizes = [slab(n, r, self.world) for r in range(self.world)]
         mx = max(b - a for a, b in sizes)
         buf = torch.zeros((mx, 9), dtype=torch.float64, device=dev)

@@ -5,7 +5,8 @@ directory, never in-tree) whose compute entry points are answered by the CPU ora
 Checked here: (1) gimic-b200 writes byte-identical reports and files to the Python driver for every run mode (cdens closed / open
 shell, ACID, property, integrals, edens / divj, scan, appended VTK); (2) the single-process multi-device partition (two host
 threads, two contexts) reproduces the single-device run; (3) native driver + oracle backend reproduce the reference's own golden
-outputs (c4h4 jvec.vtu at 10 digits, the integration stdout windows, the eight open-shell .vti files).
+outputs (c4h4 jvec.vtu at 10 digits, the integration stdout windows, the eight open-shell .vti files); (4) the Python driver under
+torch.distributed with two ranks over gloo (slab gather for cdens, all-reduce for integrals) writes what a single process writes.
 This says nothing about the CUDA kernels: tests/test_gpu_*.py hold those to the oracle on a B200."""
 import filecmp
 import io
@@ -276,3 +277,52 @@ def test_multi_device_partition_equals_single_device(mock_dir, tmp_path, cases, 
             os.remove(d3 / f)
     assert _native(mock_dir, ["--devices", "all", d3 / "gimic.inp"]) == two
     _same_dirs(dp, d3)
+
+
+def _dist_worker(rank, world, port, so, inpfile, outfile):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), OMP_NUM_THREADS="2")
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from gimic_b200 import _lib
+    _lib.SO_PATH = so                                           # the test double
+    from gimic_b200 import driver
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = io.StringIO()
+    driver.Driver(inpfile, out=out).run()
+    if rank == 0:
+        open(outfile, "w").write(out.getvalue())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,name,edit", [("open_shell", "open-shell_3d", lambda t: t.replace("spacing=[0.5, 0.5, 0.5]", "spacing=[2.0, 2.0, 4.0]")),
+                                            ("c4h4", "c4h4_integration", None), ("c4h4", "c4h4_read-grid", None)])
+def test_python_driver_world2_gloo_equals_single_process(mock_dir, tmp_path, cases, case, name, edit):
+    """`torchrun -m gimic_b200 gimic.inp` semantics with two ranks over gloo (CPU): cdens splits the flat point index into slabs and
+    gathers the tensors on rank 0 (jfield.f90:90-137), integral mode splits the plane rows and all-reduces the <= 7 sums
+    (parallel.F90:66-84).  Rank 0 must write what a single process writes."""
+    import torch.multiprocessing as mp
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+
+    def extra(d):
+        if name == "c4h4_read-grid":
+            np.savetxt(d / "gridfile.grd", gold["grid"][:301], fmt="%.6f")
+    d1, d2 = _pair(tmp_path, name, cases[case]["mol"], cases[case]["xdens"], edit=edit, extra=extra)
+    single = _python(mock_dir, [d1 / "gimic.inp"])
+    ctx = mp.get_context("spawn")
+    port = 29500 + (os.getpid() * 7 + len(name)) % 2000
+    rep = tmp_path / "rank0.out"
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, str(mock_dir / "libgimic_b200.so"), str(d2 / "gimic.inp"), str(rep))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    dist_out = rep.read_text()
+    if name == "c4h4_integration":
+        num = r"[-+]?\d+\.\d+"
+        assert re.sub(num, "#", single) == re.sub(num, "#", dist_out)
+        assert np.allclose([float(x) for x in re.findall(num, single)], [float(x) for x in re.findall(num, dist_out)], rtol=0, atol=1.01e-6)
+    else:
+        assert single == dist_out
+    _same_dirs(d1, d2)
