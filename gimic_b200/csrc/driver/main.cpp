@@ -8,7 +8,7 @@
 #include "../../../include/gimic_b200_driver.h"
 
 static void usage(FILE *f) {
-    std::fputs("usage: gimic-b200 [-y|--dryrun] [--workdir DIR] [--vtk ascii|appended] [--device N | --devices all|0,1,..] [gimic.inp ...]\n"
+    std::fputs("usage: gimic-b200 [-y|--dryrun] [-t TITLE] [-d LEVEL] [-o NAME] [-b fgimic] [--workdir DIR] [--vtk ascii|appended] [--device N | --devices all|0,1,..] [gimic.inp ...]\n"
                "  --devices: one process, one context + host thread per listed GPU (point slabs / plane rows split, nothing exchanged)\n"
                "  one input: files are written to its directory (or --workdir), the report to stdout\n"
                "  several inputs (a current-profile scan): one device context, integrals batched into one tensor pass,\n"
@@ -30,6 +30,13 @@ int main(int argc, char **argv) {
         if (a == "-h" || a == "--help") { usage(stdout); return 0; }
         else if (a == "-y" || a == "--dryrun") flags |= GIMIC_B200_RUN_DRYRUN;
         else if (a == "--workdir") workdir = value("--workdir");
+        // switches of the reference front end (src/gimic.in:36-57) that do not touch the hot path: accepted so that existing
+        // command lines keep working (title / debug level / output base name only label the reference's own log)
+        else if (a == "-t" || a == "--title" || a == "-d" || a == "--debug" || a == "-o" || a == "--output") (void)value(a.c_str());
+        else if (a == "-b" || a == "--backend") {
+            const std::string v = value("--backend");
+            if (v != "fgimic" && v != "gimic") { std::fprintf(stderr, "gimic-b200: backend '%s' is not provided (this is the fgimic path)\n", v.c_str()); return 2; }
+        }
         else if (a == "--device") device = std::atoi(value("--device"));
         else if (a == "--devices") {
             const std::string v = value("--devices");

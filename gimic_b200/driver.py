@@ -435,6 +435,12 @@ def main(argv=None):
                     help="ascii: the reference's .vti files (e14.6); appended: same files with raw Float64 blocks (extra, not a reference format)")
     ap.add_argument("-y", "--dryrun", action="store_true",
                     help="lay out the grid and write mol.xyz / grid.xyz without calculating anything (src/gimic.in:53-54); needs no GPU")
+    # switches of the reference front end (src/gimic.in:36-57) that do not touch the hot path; accepted so that existing command
+    # lines keep working
+    ap.add_argument("-t", "--title", default=None, help="title of job (label only)")
+    ap.add_argument("-d", "--debug", type=int, default=None, help="debug level (label only)")
+    ap.add_argument("-o", "--output", default=None, help="base name for output file(s) (unused, like in the reference's fgimic backend)")
+    ap.add_argument("-b", "--backend", default="fgimic", choices=["fgimic", "gimic"], help="only the fgimic path is provided")
     a = ap.parse_args(argv)
     if len(a.infile) > 1:
         run_scan(a.infile)

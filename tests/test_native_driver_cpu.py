@@ -324,3 +324,15 @@ def test_malformed_mol_files_are_errors_not_crashes(D, tmp_path, mutation, needl
     p = subprocess.run([EXE, "-y", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
     assert p.returncode == 1 and needle in p.stderr, p.stderr
     assert time.perf_counter() - t0 < 5.0
+
+
+def test_reference_front_end_switches_are_accepted(D, tmp_path):
+    """`gimic -t title -d 1 -b fgimic -o out -y gimic.inp` (src/gimic.in:36-57) keeps working with both drivers"""
+    from gimic_b200 import driver
+    d = _workdir(tmp_path, "benzene_2d")
+    p = subprocess.run([EXE, "-t", "my job", "-d", "1", "-b", "fgimic", "-o", "out", "-y", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and "Dry run, not calculating" in p.stdout
+    q = subprocess.run([EXE, "-b", "pygimic", "-y", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert q.returncode == 2 and "not provided" in q.stderr
+    os.remove(d / "grid.xyz")
+    assert driver.main([str(d / "gimic.inp"), "-t", "my job", "-d", "1", "-b", "fgimic", "-o", "out", "-y"]) == 0 and (d / "grid.xyz").exists()
