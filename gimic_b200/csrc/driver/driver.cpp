@@ -2,6 +2,7 @@
 // run_integral), jvector_plots (src/fgimic/jfield.f90:250-443), the report printing of src/fgimic/integral.f90:167-183,
 // 306-322,502-510 and of get_property (jfield.f90:584-929).  All arithmetic on the path happens behind the C ABI
 // (include/gimic_b200.h); this file only orchestrates calls and lays out text.
+#include <cctype>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -83,6 +84,7 @@ class Run {
         workdir = o.workdir.empty() ? dirname_of(inpfile) : o.workdir;
         inp = parse_file(inpfile);
         if (o.dryrun) inp.force_flag("dryrun", true);                 // the -y switch overrides the keyword (src/gimic.in:139-140)
+        if (!o.title.empty()) inp.force_str("title", o.title);
         uhf = inp.flag("openshell");
         const std::string mol = path(inp.str("basis")), xdens = path(inp.str("xdens"));
         context_key = real_path(mol) + "\n" + real_path(xdens) +
@@ -147,6 +149,19 @@ class Run {
     }
 
     void run(const std::map<int, Sums> *pre = nullptr) {
+        // initialize(), gimic.F90:107-131 (the fdate() line is left out: reports stay reproducible)
+        std::string title = inp.str("title");
+        while (!title.empty() && std::isspace((unsigned char)title.front())) title.erase(title.begin());
+        while (!title.empty() && std::isspace((unsigned char)title.back())) title.pop_back();
+        out.say(" TITLE: " + title);
+        out.say();
+        if (!inp.flag("Advanced.GIAO")) { out.say("INFO: GIAOs not used!"); out.say(); }
+        if (!inp.flag("Advanced.diamag")) { out.say("INFO: Diamagnetic contributions not calculated!"); out.say(); }
+        if (!inp.flag("Advanced.paramag")) { out.say("INFO: Paramagnetic contributions not calculated!"); out.say(); }
+        if (!inp.flag("Advanced.diamag") && !inp.flag("Advanced.paramag")) {
+            out.say("    ...this does not make sense..."); out.say();
+            throw DriverError("neither diamagnetic nor paramagnetic contributions requested: nothing to calculate (gimic.F90:124-130)");
+        }
         write_mol_xyz(join_path(workdir, "mol.xyz"), symbols, xyz);
         write_grid_xyz(join_path(workdir, "grid.xyz"), grid, symbols, xyz);
         field_line();
@@ -647,44 +662,43 @@ int write_field(const std::string &inpfile, const std::string &workdir_in, const
 // ------------------------------------------------------------------------------------------------------- C ABI
 extern "C" {
 
+int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts);
+
 int gimic_b200_run_input(const char *inpfile, const char *workdir, int device, int flags, const char *report_path) {
-    if (!inpfile) { gbd::g_error = "null argument"; return GIMIC_B200_EINVAL; }
-    gbd::RunOptions o;
-    o.dryrun = (flags & GIMIC_B200_RUN_DRYRUN) != 0;
-    o.vtk_appended = (flags & GIMIC_B200_RUN_VTK_APPENDED) != 0;
-    o.device = device;
-    if (workdir) o.workdir = workdir;
-    FILE *out = stdout;
-    if (report_path) {
-        out = std::fopen(report_path, "w");
-        if (!out) { gbd::g_error = std::string("cannot write ") + report_path; return GIMIC_B200_EIO; }
-    }
-    const int rc = gbd::run_input(inpfile, o, out);
-    if (report_path) std::fclose(out); else std::fflush(out);
-    return rc;
+    gimic_b200_run_opts o;
+    std::memset(&o, 0, sizeof o);
+    o.flags = flags; o.device = device; o.workdir = workdir; o.report_path = report_path;
+    return gimic_b200_run(inpfile, &o);
 }
 
-int gimic_b200_run_input_multi(const char *inpfile, const char *workdir, int ndevices, const int *devices, int flags, const char *report_path) {
-    if (!inpfile || ndevices < 0 || (ndevices > 0 && !devices)) { gbd::g_error = "bad argument"; return GIMIC_B200_EINVAL; }
+int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts) {
+    if (!inpfile) { gbd::g_error = "null argument"; return GIMIC_B200_EINVAL; }
+    gimic_b200_run_opts d;
+    std::memset(&d, 0, sizeof d);
+    d.device = -1;
+    if (opts) d = *opts;
+    if (d.ndevices > 0 && !d.devices) { gbd::g_error = "bad argument: ndevices > 0 without a device list"; return GIMIC_B200_EINVAL; }
     gbd::RunOptions o;
-    o.dryrun = (flags & GIMIC_B200_RUN_DRYRUN) != 0;
-    o.vtk_appended = (flags & GIMIC_B200_RUN_VTK_APPENDED) != 0;
-    if (ndevices == 0) {                                          // all GPUs of the node
+    o.dryrun = (d.flags & GIMIC_B200_RUN_DRYRUN) != 0;
+    o.vtk_appended = (d.flags & GIMIC_B200_RUN_VTK_APPENDED) != 0;
+    o.device = d.device;
+    if (d.ndevices < 0 && !o.dryrun) {                            // every GPU of the node
         const int nd = gimic_b200_device_count();
         if (nd < 0) { gbd::g_error = gimic_b200_last_error(); return nd; }
-        for (int d = 0; d < nd; ++d) o.devices.push_back(d);
-    } else {
-        o.devices.assign(devices, devices + ndevices);
+        for (int k = 0; k < nd; ++k) o.devices.push_back(k);
+    } else if (d.ndevices > 0) {
+        o.devices.assign(d.devices, d.devices + d.ndevices);
     }
     if (!o.devices.empty()) o.device = o.devices[0];
-    if (workdir) o.workdir = workdir;
+    if (d.title) o.title = d.title;
+    if (d.workdir) o.workdir = d.workdir;
     FILE *out = stdout;
-    if (report_path) {
-        out = std::fopen(report_path, "w");
-        if (!out) { gbd::g_error = std::string("cannot write ") + report_path; return GIMIC_B200_EIO; }
+    if (d.report_path) {
+        out = std::fopen(d.report_path, "w");
+        if (!out) { gbd::g_error = std::string("cannot write ") + d.report_path; return GIMIC_B200_EIO; }
     }
     const int rc = gbd::run_input(inpfile, o, out);
-    if (report_path) std::fclose(out); else std::fflush(out);
+    if (d.report_path) std::fclose(out); else std::fflush(out);
     return rc;
 }
 

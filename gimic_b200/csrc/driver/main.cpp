@@ -17,7 +17,7 @@ static void usage(FILE *f) {
 
 int main(int argc, char **argv) {
     std::vector<const char *> files;
-    const char *workdir = nullptr;
+    const char *workdir = nullptr, *title = nullptr;
     int flags = 0, device = -1;
     bool multi = false;
     std::vector<int> devices;
@@ -32,7 +32,8 @@ int main(int argc, char **argv) {
         else if (a == "--workdir") workdir = value("--workdir");
         // switches of the reference front end (src/gimic.in:36-57) that do not touch the hot path: accepted so that existing
         // command lines keep working (title / debug level / output base name only label the reference's own log)
-        else if (a == "-t" || a == "--title" || a == "-d" || a == "--debug" || a == "-o" || a == "--output") (void)value(a.c_str());
+        else if (a == "-t" || a == "--title") title = value("--title");
+        else if (a == "-d" || a == "--debug" || a == "-o" || a == "--output") (void)value(a.c_str());
         else if (a == "-b" || a == "--backend") {
             const std::string v = value("--backend");
             if (v != "fgimic" && v != "gimic") { std::fprintf(stderr, "gimic-b200: backend '%s' is not provided (this is the fgimic path)\n", v.c_str()); return 2; }
@@ -64,8 +65,13 @@ int main(int argc, char **argv) {
     if (files.empty()) files.push_back("gimic.inp");
     int rc;
     if (files.size() > 1) rc = gimic_b200_run_scan((int)files.size(), files.data(), !devices.empty() ? devices[0] : device, flags);
-    else if (multi && !(flags & GIMIC_B200_RUN_DRYRUN)) rc = gimic_b200_run_input_multi(files[0], workdir, (int)devices.size(), devices.data(), flags, nullptr);
-    else rc = gimic_b200_run_input(files[0], workdir, device, flags, nullptr);
+    else {
+        gimic_b200_run_opts o;
+        std::memset(&o, 0, sizeof o);
+        o.flags = flags; o.device = device; o.workdir = workdir; o.title = title;
+        if (multi) { o.ndevices = devices.empty() ? -1 : (int)devices.size(); o.devices = devices.data(); }
+        rc = gimic_b200_run(files[0], &o);
+    }
     if (rc != 0) {
         std::fprintf(stderr, "gimic-b200: %s\n", gimic_b200_driver_last_error());
         return 1;

@@ -130,6 +130,7 @@ std::string dirname_of(const std::string &path);
 
 struct RunOptions {
     bool dryrun = false;         // -y
+    std::string title;           // -t: overrides the `title` keyword when non-empty (src/gimic.in:135-136)
     bool vtk_appended = false;   // --vtk appended (extra)
     int device = -1;
     std::vector<int> devices;    // more than one entry: single-process multi-device run (one context per listed GPU, one host

@@ -76,11 +76,13 @@ def _dist():
 
 
 class Driver:
-    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False, dryrun=False):
+    def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False, dryrun=False, title=None):
         self.workdir = workdir or os.path.dirname(os.path.abspath(inpfile))
         self.inp = _inp.parse_file(inpfile)
         if dryrun:                               # the -y switch overrides the keyword (src/gimic.in:139-140)
             self.inp.values[""]["dryrun"] = True
+        if title:                                # -t (src/gimic.in:135-136)
+            self.inp.values[""]["title"] = str(title)
         self.vtk_appended = bool(vtk_appended)   # extra: .vti files with raw appended Float64 data instead of ASCII e14.6
         self.dist, self.rank, self.world = _dist()
         self.out = out if out is not None else sys.stdout
@@ -119,6 +121,18 @@ class Driver:
     # -------------------------------------------------------------------------------------------------
     def run(self, integral_results=None):
         I = self.inp
+        # initialize(), gimic.F90:107-131 (the fdate() line is left out: reports stay reproducible)
+        self.say(" TITLE: " + str(I.get("title")).strip())
+        self.say()
+        if not I.get("Advanced.GIAO"):
+            self.say("INFO: GIAOs not used!"); self.say()
+        if not I.get("Advanced.diamag"):
+            self.say("INFO: Diamagnetic contributions not calculated!"); self.say()
+        if not I.get("Advanced.paramag"):
+            self.say("INFO: Paramagnetic contributions not calculated!"); self.say()
+        if not I.get("Advanced.diamag") and not I.get("Advanced.paramag"):
+            self.say("    ...this does not make sense..."); self.say()
+            raise ValueError("neither diamagnetic nor paramagnetic contributions requested: nothing to calculate (gimic.F90:124-130)")
         if self.rank == 0:
             writers.write_mol_xyz(os.path.join(self.workdir, "mol.xyz"), self.symbols, self.xyz)
             writers.write_grid_xyz(os.path.join(self.workdir, "grid.xyz"), self.grid, self.symbols, self.xyz)
@@ -447,7 +461,7 @@ def main(argv=None):
         return 0
     a.infile = a.infile[0]
     if a.dryrun:
-        Driver(a.infile, a.workdir, dryrun=True).run()
+        Driver(a.infile, a.workdir, dryrun=True, title=a.title).run()
         return 0
     device = -1
     if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
@@ -456,5 +470,5 @@ def main(argv=None):
         device = int(os.environ["LOCAL_RANK"])
         torch.cuda.set_device(device)
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
-    Driver(a.infile, a.workdir, device=device, vtk_appended=(a.vtk == "appended")).run()
+    Driver(a.infile, a.workdir, device=device, vtk_appended=(a.vtk == "appended"), title=a.title).run()
     return 0

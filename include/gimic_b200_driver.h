@@ -34,13 +34,23 @@ enum {
  * report_path NULL: the report goes to stdout. */
 int gimic_b200_run_input(const char *inpfile, const char *workdir, int device, int flags, const char *report_path);
 
-/* The same run on several GPUs of one node from ONE process: a context per listed device (densities replicated), one host
- * thread each; cdens splits the flat point index into contiguous slabs, integral mode splits the plane rows j -- the block
- * partition of schedule() (src/fgimic/parallel.F90:66-84) -- and the <= 7 partial sums are added on the host in device order.
- * Nothing is exchanged between the devices.  ndevices == 0: every GPU of the node.  (The torchrun entry `python -m gimic_b200`
- * is the one-process-per-GPU form of the same partition, with an NCCL all-reduce for the integrals.) */
-int gimic_b200_run_input_multi(const char *inpfile, const char *workdir, int ndevices, const int *devices, int flags,
-                               const char *report_path);
+/* The general form.  Zero-initialise the struct, then set what is needed (device = -1 selects the current device).
+ *   ndevices > 0 (list in `devices`) or ndevices < 0 (every GPU of the node): the run uses several GPUs from ONE process -- a
+ *   context per device (densities replicated), one host thread each; cdens splits the flat point index into contiguous slabs,
+ *   integral mode splits the plane rows j -- the block partition of schedule() (src/fgimic/parallel.F90:66-84) -- and the <= 7
+ *   partial sums are added on the host in device order.  Nothing is exchanged between the devices.  (The torchrun entry
+ *   `python -m gimic_b200` is the one-process-per-GPU form of the same partition, with an NCCL all-reduce for the integrals.)
+ *   title: the -t switch of the front end (src/gimic.in:135-136), overrides the `title` keyword. */
+typedef struct {
+    int flags;                /* GIMIC_B200_RUN_* */
+    int device;               /* CUDA ordinal for a single-device run, -1 = current device */
+    int ndevices;             /* 0: single device; > 0: `devices` lists the GPUs; < 0: all GPUs of the node */
+    const int *devices;
+    const char *workdir;      /* NULL: the directory of the input file */
+    const char *title;        /* NULL: the `title` keyword */
+    const char *report_path;  /* NULL: the report goes to stdout */
+} gimic_b200_run_opts;
+int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts);
 
 /* A current-profile scan (jobscripts/src/current-profile-local-submit: `gimic gimic.N.inp > gimic.N.out` for every slice):
  * inputs that agree on basis, densities and Advanced settings share ONE device context, and all their plane integrals go

@@ -28,6 +28,10 @@ module b200_module
 
     type(c_ptr), save :: b200_handle = c_null_ptr
 
+    type, bind(c) :: b200_run_opts
+        integer(c_int) :: flags, device, ndevices
+        type(c_ptr) :: devices, workdir, title, report_path      ! c_null_ptr = default
+    end type
     interface
         subroutine gimic_b200_default_opts(opts) bind(c)
             import; type(b200_opts) :: opts
@@ -90,6 +94,10 @@ module b200_module
         ! `gimic gimic.inp` as one call (src/gimic.in:116-159 + program gimic); flags: 1 dry run, 2 appended-binary .vti
         integer(c_int) function gimic_b200_run_input(inpfile, workdir, device, flags, report_path) bind(c)
             import; character(c_char) :: inpfile(*), workdir(*), report_path(*); integer(c_int), value :: device, flags
+        end function
+        ! general form: type(b200_run_opts) mirrors gimic_b200_run_opts (flags, device, ndevices, devices, workdir, title, report_path)
+        integer(c_int) function gimic_b200_run(inpfile, opts) bind(c)
+            import; character(c_char) :: inpfile(*); type(b200_run_opts) :: opts
         end function
         ! writers of vtkplot.f90:14-391 / jfield.f90:531-541 on the grid that gimic.inp describes; kind = 'vti_scalar',
         ! 'vti_vector', 'jmod_txt', 'vtu_vector', 'vtu_scalar' (NUL-terminated)

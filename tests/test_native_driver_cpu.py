@@ -59,7 +59,7 @@ def test_driver_header_symbols_exported(D):
     hdr = open(os.path.join(ROOT, "include", "gimic_b200_driver.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b(gimic_b200_\w+)\s*\(", hdr))
-    assert names == {"gimic_b200_run_input", "gimic_b200_run_input_multi", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_driver_last_error"}
+    assert names == {"gimic_b200_run_input", "gimic_b200_run", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_driver_last_error"}
     for n in names:
         assert hasattr(D, n), n
 
@@ -301,8 +301,14 @@ def test_multi_device_switch_without_gpus(D, tmp_path):
         for devs in ("all", "0,1"):
             q = subprocess.run([EXE, "--devices", devs, str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
             assert q.returncode == 1 and ("CUDA" in q.stderr or "cuda" in q.stderr) and "Induced current" not in q.stdout
-        D.gimic_b200_run_input_multi.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_char_p]
-        assert D.gimic_b200_run_input_multi(os.fsencode(d / "gimic.inp"), None, 0, None, 0, os.fsencode(tmp_path / "rep")) == -3
+        class RunOpts(C.Structure):
+            _fields_ = [("flags", C.c_int), ("device", C.c_int), ("ndevices", C.c_int), ("devices", C.POINTER(C.c_int)), ("workdir", C.c_char_p),
+                        ("title", C.c_char_p), ("report_path", C.c_char_p)]
+        D.gimic_b200_run.argtypes = [C.c_char_p, C.POINTER(RunOpts)]
+        o = RunOpts(flags=0, device=-1, ndevices=-1, report_path=os.fsencode(tmp_path / "rep"))
+        assert D.gimic_b200_run(os.fsencode(d / "gimic.inp"), C.byref(o)) == -3          # GIMIC_B200_ECUDA
+        o = RunOpts(flags=1, device=-1, ndevices=-1, title=b"via the struct", report_path=os.fsencode(tmp_path / "rep"))
+        assert D.gimic_b200_run(os.fsencode(d / "gimic.inp"), C.byref(o)) == 0 and "TITLE: via the struct" in (tmp_path / "rep").read_text()
 
 
 @pytest.mark.parametrize("mutation,needle", [
