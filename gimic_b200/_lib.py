@@ -21,7 +21,7 @@ API_SYMBOLS = ["gimic_b200_default_opts", "gimic_b200_create", "gimic_b200_creat
                "gimic_b200_nbf", "gimic_b200_natoms", "gimic_b200_atom_coords", "gimic_b200_is_uhf",
                "gimic_b200_calc_jtensors", "gimic_b200_calc_basis", "gimic_b200_calc_fields", "gimic_b200_fields_from_tensors", "gimic_b200_jmod_from_jvec",
                "gimic_b200_calc_jtensors_grid", "gimic_b200_integrate", "gimic_b200_integrate_batch", "gimic_b200_property", "gimic_b200_property_integrand", "gimic_b200_gauss_points",
-               "gimic_b200_mol_geometry", "gimic_b200_c2s_rows", "gimic_b200_convert_xdens", "gimic_b200_format_e", "gimic_b200_format_f",
+               "gimic_b200_mol_geometry", "gimic_b200_mol_summary", "gimic_b200_c2s_rows", "gimic_b200_convert_xdens", "gimic_b200_format_e", "gimic_b200_format_f",
                "gimic_b200_get_stats", "gimic_b200_set_profiling", "gimic_b200_last_error", "gimic_b200_version"]
 
 ALPHA, BETA, TOTAL, SPINDENS = 0, 1, 2, 3
@@ -85,6 +85,7 @@ def lib():
     L.gimic_b200_gauss_points.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp]
     L.gimic_b200_c2s_rows.argtypes = [C.c_int, C.c_int, dp]
     L.gimic_b200_mol_geometry.argtypes = [C.c_char_p, C.c_int, dp, C.c_char_p]
+    L.gimic_b200_mol_summary.argtypes = [C.c_char_p, ip]
     L.gimic_b200_format_e.restype = C.c_long
     L.gimic_b200_format_e.argtypes = [C.c_long, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_long]
     L.gimic_b200_format_f.restype = C.c_long

@@ -76,6 +76,7 @@ class Run {
     std::vector<double> xyz;
     GridSpec grid;
     Vec3 magnet{{0, 0, 0}};
+    int summary[4] = {0, 0, 0, 0};                  // natoms, primitive GTOs, contracted GTOs, TURBOMOLE flag (gimic_b200_mol_summary)
     std::map<int, Sums> results;
 
     // `find_shared`: returns an existing context for a key (scan mode) or nullptr
@@ -98,6 +99,7 @@ class Run {
         std::string sym((size_t)natoms * 2, ' ');
         check(gimic_b200_mol_geometry(mol.c_str(), natoms, xyz.data(), &sym[0]));
         for (int a = 0; a < natoms; ++a) symbols.push_back(sym.substr(2 * (size_t)a, 2));
+        check(gimic_b200_mol_summary(mol.c_str(), summary));
         if (!inp.flag("dryrun")) {
             ctx = find_shared(context_key);
             gimic_b200_opts go;
@@ -153,7 +155,7 @@ class Run {
         std::string title = inp.str("title");
         while (!title.empty() && std::isspace((unsigned char)title.front())) title.erase(title.begin());
         while (!title.empty() && std::isspace((unsigned char)title.back())) title.pop_back();
-        out.say(" TITLE: " + title);
+        out.say(title.empty() ? std::string(" TITLE:") : " TITLE: " + title);      // msg_out trims trailing blanks
         out.say();
         if (!inp.flag("Advanced.GIAO")) { out.say("INFO: GIAOs not used!"); out.say(); }
         if (!inp.flag("Advanced.diamag")) { out.say("INFO: Diamagnetic contributions not calculated!"); out.say(); }
@@ -162,8 +164,27 @@ class Run {
             out.say("    ...this does not make sense..."); out.say();
             throw DriverError("neither diamagnetic nor paramagnetic contributions requested: nothing to calculate (gimic.F90:124-130)");
         }
+        // driver(), gimic.F90:141-165: what new_basis (intgrl.f90:48-60, basis.f90:44-80), read_dens (dens.f90:94-103), new_grid and
+        // plot_grid_xyz (grid.f90:608-609) print on the way
+        if (summary[3]) { out.say("INFO: Detected TURBOMOLE input"); out.say(); }
+        out.say(sfmt("Number of atoms =%4d", summary[0])); out.say();
+        out.say("Normalizing basis"); out.say();
+        out.say(sfmt("  Total number of primitive  GTO's %6d", summary[1]));
+        out.say(sfmt("  Total number of contracted GTO's %6d", summary[2])); out.say();
+        if (inp.flag("Advanced.screening") && inp.real("Advanced.screening_thrs") > 0.0) {
+            out.say("*** Calculating screening coefficients");
+            out.say("INFO: Screening threshold: " + fortran_e(inp.real("Advanced.screening_thrs"), 12, 4)); out.say();
+        } else {
+            out.say("INFO: Screening is not used");
+        }
+        if (!inp.flag("dryrun")) {
+            if (uhf) out.say("INFO: scaling perturbed densities by 0.d5");
+            if (summary[3]) out.say("INFO: Reordering densities [TURBOMOLE]");
+        }
+        for (const std::string &line : grid.log) out.raw(line + "\n");
         write_mol_xyz(join_path(workdir, "mol.xyz"), symbols, xyz);
         write_grid_xyz(join_path(workdir, "grid.xyz"), grid, symbols, xyz);
+        out.say("*** Grid plot in grid.xyz");
         field_line();
         out.say(std::string("INFO: ") + (uhf ? "Open-shell calculation" : "Closed-shell calculation"));
         out.say();

@@ -40,6 +40,17 @@ Vec3 matvec(const double R[3][3], const Vec3 &v) {
     return o;
 }
 
+std::string f3(const double *v, int w = 12, int d = 6) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "%*.*f%*.*f%*.*f", w, d, v[0], w, d, v[1], w, d, v[2]);
+    return buf;
+}
+std::string i3(long a, long b, long c) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%5ld%5ld%5ld", a, b, c);
+    return buf;
+}
+
 void make_axes(GridSpec &g, const Vec3 &step, const AxisOpts &o) {
     const Vec3 &l = g.lengths;
     if (o.gtype == "even") {                                  // setup_even_grid, grid.f90:351-373
@@ -56,14 +67,17 @@ void make_axes(GridSpec &g, const Vec3 &step, const AxisOpts &o) {
     if (o.gtype != "gauss" && o.gtype != "lobatto") throw DriverError("Unknown grid type: " + o.gtype);
     if (o.gauss_order < 1) throw DriverError("gauss_order must be positive");
     long npts[3];                                             // setup_gauss_grid, grid.f90:291-349
+    bool fixed = false;
+    g.log.push_back(" INFO: Integration grid selected.");
     for (int d = 0; d < 3; ++d) {
         if (o.has_grid_points) npts[d] = o.grid_points[d];
         else if (std::fabs(o.spacing[d]) < 1e-10 || o.spacing[d] < 0.0) npts[d] = 0;
         else npts[d] = (long)nint(l[d] / o.spacing[d]);
         if (!(npts[d] > 1)) npts[d] = 0;
         long rem = npts[d] % o.gauss_order;
-        if (rem != 0) npts[d] = npts[d] - rem + o.gauss_order;
+        if (rem != 0) { npts[d] = npts[d] - rem + o.gauss_order; fixed = true; }
     }
+    if (fixed) g.log.push_back(" INFO: Adjusted number of grid points for quadrature: " + i3(npts[0], npts[1], npts[2]));
     for (int d = 0; d < 3; ++d) {
         const long n = npts[d] > 0 ? npts[d] : 1;
         g.pts[d].assign(n, 0.0); g.wgt[d].assign(n, 0.0);
@@ -86,6 +100,20 @@ GridSpec finish(const Vec3 &origin_in, const Vec3 b_in[3], const Vec3 &lengths, 
             if (n > 0.0) for (int c = 0; c < 3; ++c) g.basv[v][c] = g.basv[v][c] / n;
         }
     };
+    if (mode == "bond") {                                     // the block setup_bond_grid prints, grid.f90:258-275 (before any rotation)
+        g.log.push_back("");
+        g.log.push_back(" Integration grid data");
+        g.log.push_back(" " + std::string(48, '-'));
+        g.log.push_back(" center " + f3(center_bond ? center_bond->data() : origin_in.data()));
+        g.log.push_back(" origin " + f3(origin_in.data()));
+        g.log.push_back(" basv1  " + f3(g.basv[0]));
+        g.log.push_back(" basv2  " + f3(g.basv[1]));
+        g.log.push_back(" basv3  " + f3(g.basv[2]));
+        g.log.push_back(" lenghts" + f3(lengths.data()));
+        g.log.push_back(" magnet " + f3(ortho.data()));
+        g.log.push_back("");
+    }
+    g.log.push_back(" Grid mode = " + mode);
     normalise();
     if (std::fabs(dot(g.basv[0], g.basv[1])) > 1e-10) {      // ortho_coordsys, grid.f90:400-428
         Vec3 t = cross(Vec3{{g.basv[0][0], g.basv[0][1], g.basv[0][2]}}, Vec3{{g.basv[2][0], g.basv[2][1], g.basv[2][2]}});
@@ -106,9 +134,16 @@ GridSpec finish(const Vec3 &origin_in, const Vec3 b_in[3], const Vec3 &lengths, 
         }
         Vec3 r = matvec(R, sub(g.origin, ref));
         for (int c = 0; c < 3; ++c) g.origin[c] = r[c] + ref[c];
+        const double rad[3] = {o.rotation[0] / 180.0 * PII, o.rotation[1] / 180.0 * PII, o.rotation[2] / 180.0 * PII};
+        g.log.push_back(" INFO: Rotation is: " + f3(rad, 9, 5));
     }
     make_axes(g, step, o);
     for (int d = 0; d < 3; ++d) g.npts[d] = (int)g.pts[d].size();
+    char buf[96];
+    g.log.push_back("   Number of grid points <v1,v2>:" + i3(g.npts[0], g.npts[1], g.npts[2]));
+    snprintf(buf, sizeof buf, "   Total number of grid points  :%10ld", g.n());
+    g.log.push_back(buf);
+    g.log.push_back("");
     return g;
 }
 
@@ -189,6 +224,10 @@ GridSpec file_grid(std::vector<double> xyz) {
     g.xdata = std::move(xyz);
     for (int d = 0; d < 3; ++d) { g.pts[d].assign(1, 0.0); g.wgt[d].assign(1, 1.0); }
     g.npts[0] = (int)(g.xdata.size() / 3); g.npts[1] = g.npts[2] = 1;
+    char buf[96];
+    snprintf(buf, sizeof buf, "   Total number of grid points  :%10ld", g.n());   // extgrid, grid.f90:572-575
+    g.log.push_back(buf);
+    g.log.push_back("");
     return g;
 }
 

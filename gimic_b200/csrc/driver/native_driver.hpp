@@ -77,6 +77,7 @@ struct GridSpec {
     bool has_center_bond = false;
     Vec3 center_bond{{0, 0, 0}};
     std::vector<double> xdata;        // file grids: explicit points, 3 per point
+    std::vector<std::string> log;     // what new_grid prints while it sets the grid up (grid.f90:87,131-137,259-275,301,328-332,710-711)
 
     long n() const { return (long)npts[0] * npts[1] * npts[2]; }
     bool is_file() const { return mode == "file"; }

@@ -65,6 +65,17 @@ def mol_geometry(mol):
     return [raw[2 * a: 2 * a + 2] for a in range(n)], xyz
 
 
+def mol_summary(mol):
+    """(natoms, primitive GTOs, contracted cartesian GTOs, is_turbomole) as new_basis prints them (gimic_b200_mol_summary)"""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    info = (C.c_int * 4)()
+    if L.gimic_b200_mol_summary(os.fsencode(mol), info) < 0:
+        raise RuntimeError(L.gimic_b200_last_error().decode())
+    return int(info[0]), int(info[1]), int(info[2]), bool(info[3])
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -107,6 +118,7 @@ class Driver:
                 spherical=bool(I.get("Advanced.spherical")))
             self.xyz = self.g.atom_coords()
             self.symbols = self._symbols(path(I.get("basis")))
+        self.summary = mol_summary(path(I.get("basis")))
         self.grid = grids.from_input(I, self.xyz, self.workdir)
         self.magnet = grids.get_magnet(self.grid, I.get("magnet_axis"), I.get("magnet"))
 
@@ -122,7 +134,7 @@ class Driver:
     def run(self, integral_results=None):
         I = self.inp
         # initialize(), gimic.F90:107-131 (the fdate() line is left out: reports stay reproducible)
-        self.say(" TITLE: " + str(I.get("title")).strip())
+        self.say((" TITLE: " + str(I.get("title")).strip()).rstrip())       # msg_out trims trailing blanks
         self.say()
         if not I.get("Advanced.GIAO"):
             self.say("INFO: GIAOs not used!"); self.say()
@@ -133,9 +145,31 @@ class Driver:
         if not I.get("Advanced.diamag") and not I.get("Advanced.paramag"):
             self.say("    ...this does not make sense..."); self.say()
             raise ValueError("neither diamagnetic nor paramagnetic contributions requested: nothing to calculate (gimic.F90:124-130)")
+        # driver(), gimic.F90:141-165: what new_basis (intgrl.f90:48-60, basis.f90:44-80), read_dens (dens.f90:94-103), new_grid and
+        # plot_grid_xyz (grid.f90:608-609) print on the way
+        natoms, ngto, ncgto, turbomole = self.summary
+        if turbomole:
+            self.say("INFO: Detected TURBOMOLE input"); self.say()
+        self.say(f"Number of atoms ={natoms:4d}"); self.say()
+        self.say("Normalizing basis"); self.say()
+        self.say(f"  Total number of primitive  GTO's {ngto:6d}")
+        self.say(f"  Total number of contracted GTO's {ncgto:6d}"); self.say()
+        if I.get("Advanced.screening") and float(I.get("Advanced.screening_thrs")) > 0.0:
+            self.say("*** Calculating screening coefficients")
+            self.say("INFO: Screening threshold: " + writers.fortran_e(float(I.get("Advanced.screening_thrs")), 12, 4)); self.say()
+        else:
+            self.say("INFO: Screening is not used")
+        if not I.get("dryrun"):
+            if self.uhf:
+                self.say("INFO: scaling perturbed densities by 0.d5")
+            if turbomole:
+                self.say("INFO: Reordering densities [TURBOMOLE]")
         if self.rank == 0:
+            for line in self.grid.log:
+                self.out.write(line + "\n")
             writers.write_mol_xyz(os.path.join(self.workdir, "mol.xyz"), self.symbols, self.xyz)
             writers.write_grid_xyz(os.path.join(self.workdir, "grid.xyz"), self.grid, self.symbols, self.xyz)
+        self.say("*** Grid plot in grid.xyz")
         self.say("   Magnetic field <x,y,z> =" + "".join(f"{b:10.5f}" for b in self.magnet))
         self.say()
         self.say("INFO: " + ("Open-shell calculation" if self.uhf else "Closed-shell calculation"))

@@ -31,6 +31,7 @@ class GridSpec(Grid):
         self.xdata = xdata            # file grids: explicit points (n, 3)
         if xdata is not None:
             self.npts = (int(xdata.shape[0]), 1, 1)
+        self.log = []                 # what new_grid prints while it sets the grid up (grid.f90:87,131-137,259-275,301,328-332,710-711)
 
     def points(self):
         if self.xdata is not None:
@@ -60,7 +61,11 @@ def _rotation_matrix(angle_deg):
     return Rx @ (Ry @ Rz)
 
 
-def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order=7):
+def _f3(v, w=12, d=6):
+    return "".join(f"{float(x):{w}.{d}f}" for x in v)
+
+
+def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order=7, log=None):
     pts, wgt = [], []
     if gtype == "even":                                  # setup_even_grid, grid.f90:351-373
         for d in range(3):
@@ -76,6 +81,9 @@ def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order
     if gauss_order < 1:
         raise ValueError("gauss_order must be positive")
     npts = [0, 0, 0]                                     # setup_gauss_grid, grid.f90:291-349
+    fixed = False
+    if log is not None:
+        log.append(" INFO: Integration grid selected.")
     for d in range(3):
         if grid_points is not None:
             npts[d] = int(grid_points[d])
@@ -88,6 +96,9 @@ def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order
         rem = npts[d] % gauss_order
         if rem != 0:
             npts[d] = npts[d] - rem + gauss_order
+            fixed = True
+    if fixed and log is not None:
+        log.append(" INFO: Adjusted number of grid points for quadrature: " + "".join(f"{n:5d}" for n in npts))
     for d in range(3):
         n = npts[d] if npts[d] > 0 else 1
         p, w = np.zeros(n), np.zeros(n)
@@ -99,6 +110,11 @@ def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order
 def _finish(origin, basv, lengths, mode, gtype, ortho, radius, step, grid_points, spacing, gauss_order, rotation,
             rotation_origin, out_len, down_len, center_bond=None):
     basv = np.array(basv, dtype=np.float64)
+    log = []
+    if mode == "bond":                                   # the block setup_bond_grid prints, grid.f90:258-275 (before any rotation)
+        log += ["", " Integration grid data", " " + "-" * 48, " center " + _f3(center_bond), " origin " + _f3(origin), " basv1  " + _f3(basv[0]),
+                " basv2  " + _f3(basv[1]), " basv3  " + _f3(basv[2]), " lenghts" + _f3(lengths), " magnet " + _f3(ortho), ""]
+    log.append(" Grid mode = " + mode)
     for v in range(3):                                   # normalise, grid.f90:278-288
         n = math.sqrt(float(np.dot(basv[v], basv[v])))
         if n > 0.0:
@@ -117,8 +133,12 @@ def _finish(origin, basv, lengths, mode, gtype, ortho, radius, step, grid_points
         R = _rotation_matrix(rotation)
         basv = np.array([R @ basv[v] for v in range(3)])
         origin = R @ (origin - ref) + ref
-    pts, wgt = _axes(lengths, gtype, step, grid_points, spacing, gauss_order)
-    return GridSpec(origin, basv, pts, wgt, radius, mode, gtype, ortho, lengths, center_bond)
+        log.append(" INFO: Rotation is: " + _f3([a / 180.0 * PII for a in rotation], 9, 5))
+    pts, wgt = _axes(lengths, gtype, step, grid_points, spacing, gauss_order, log)
+    g = GridSpec(origin, basv, pts, wgt, radius, mode, gtype, ortho, lengths, center_bond)
+    log += ["   Number of grid points <v1,v2>:" + "".join(f"{n:5d}" for n in g.npts), f"   Total number of grid points  :{g.n:10d}", ""]
+    g.log = log
+    return g
 
 
 def std_grid(origin, ivec, jvec, lengths, gtype="even", spacing=None, grid_points=None, gauss_order=7, rotation=None,
@@ -164,8 +184,10 @@ def bond_grid(c1, c2, fix, distance, height, width, gtype="even", spacing=None, 
 def file_grid(xyz):
     """extgrid, grid.f90:543-576: an explicit point list; basis vectors are zero (so get_magnet never flips B)"""
     xyz = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
-    return GridSpec(np.zeros(3), np.zeros((3, 3)), [np.zeros(1)] * 3, [np.ones(1)] * 3, -1.0, "file", "file", np.zeros(3),
-                    np.zeros(3), xdata=xyz)
+    g = GridSpec(np.zeros(3), np.zeros((3, 3)), [np.zeros(1)] * 3, [np.ones(1)] * 3, -1.0, "file", "file", np.zeros(3),
+                 np.zeros(3), xdata=xyz)
+    g.log = [f"   Total number of grid points  :{g.n:10d}", ""]      # extgrid, grid.f90:572-575
+    return g
 
 
 def get_magnet(grid, magnet_axis="", magnet=(0.0, 0.0, 0.0)):

@@ -342,3 +342,24 @@ def test_reference_front_end_switches_are_accepted(D, tmp_path):
     assert q.returncode == 2 and "not provided" in q.stderr
     os.remove(d / "grid.xyz")
     assert driver.main([str(d / "gimic.inp"), "-t", "my job", "-d", "1", "-b", "fgimic", "-o", "out", "-y"]) == 0 and (d / "grid.xyz").exists()
+
+
+@pytest.mark.parametrize("name,gold_json", [("c4h4_integration", "c4h4_integration.json"), ("open-shell_integration", "open_shell_integration.json")])
+def test_report_preamble_equals_the_reference_stdout(D, tmp_path, name, gold_json):
+    """What the reference prints before the results (test/*/integration/reference/stdout: TURBOMOLE note, atom and GTO counts, screening
+    threshold, the 'Integration grid data' block, grid mode, rotation, adjusted quadrature sizes, point counts, grid plot note, field
+    direction): the dry-run report carries the same lines, and the numbers of the grid block are the golden's"""
+    d = _workdir(tmp_path, name)
+    p = subprocess.run([EXE, "-y", str(d / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    out = p.stdout
+    geo = fixtures.golden_json(gold_json)["geometry"]
+    for key, label in (("center", " center "), ("origin", " origin "), ("basv1", " basv1  "), ("basv2", " basv2  "), ("basv3", " basv3  ")):
+        line = next(l for l in out.split("\n") if l.startswith(label))
+        assert np.allclose([float(x) for x in line[len(label):].split()], geo[key], rtol=0, atol=1.01e-6), (key, line)
+    for needle in (" Integration grid data", " Grid mode = bond", " INFO: Integration grid selected.",
+                   " INFO: Adjusted number of grid points for quadrature:    36   36    0", "   Number of grid points <v1,v2>:   36   36    1",
+                   "   Total number of grid points  :      1296", " *** Grid plot in grid.xyz", " Number of atoms =   8", " Normalizing basis",
+                   " *** Calculating screening coefficients", " INFO: Screening threshold:   0.1000E-07", "  TITLE:"):
+        assert needle + "\n" in out, needle
+    assert ("  Total number of contracted GTO's    168\n" in out) and (" INFO: Detected TURBOMOLE input\n" in out) == name.startswith("c4h4")
