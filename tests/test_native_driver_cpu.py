@@ -363,3 +363,20 @@ def test_report_preamble_equals_the_reference_stdout(D, tmp_path, name, gold_jso
                    " *** Calculating screening coefficients", " INFO: Screening threshold:   0.1000E-07", "  TITLE:"):
         assert needle + "\n" in out, needle
     assert ("  Total number of contracted GTO's    168\n" in out) and (" INFO: Detected TURBOMOLE input\n" in out) == name.startswith("c4h4")
+
+
+def test_python_repr_layout_on_random_magnitudes(D, tmp_path):
+    """py_repr (shortest round-trip digits, repr() layout) against Python itself for 60 random origins / spacings over 40 decades"""
+    from gimic_b200 import writers
+    rng = np.random.default_rng(3)
+    for it in range(60):
+        o = rng.normal(size=3) * 10.0 ** rng.integers(-20, 20, size=3)
+        l = np.abs(rng.normal(size=3)) * 10.0 ** rng.integers(-6, 17, size=3) + 1e-7
+        text = ("basis=MOL\ncalc=cdens\nmagnet=[0,0,1]\nGrid(std){\n type=even\n origin=[%r, %r, %r]\n ivec=[1,0,0]\n jvec=[0,1,0]\n"
+                " lengths=[%r, %r, %r]\n grid_points=[2,2,2]\n}\n" % (*map(float, o), *map(float, l)))
+        d = _workdir(tmp_path, f"benzene_r{it}", text)
+        g = _py_grid(d)
+        v = np.arange(8, dtype=np.float64)
+        writers.write_vti_scalar(str(d / "py.vti"), g, v, True)
+        _write(D, d, "vti_scalar", v, "nat.vti", 2)
+        assert filecmp.cmp(d / "py.vti", d / "nat.vti", shallow=False), (it, open(d / "py.vti", "rb").read(300), open(d / "nat.vti", "rb").read(300))
