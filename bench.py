@@ -219,7 +219,7 @@ def main():
 
     def run_steps(k, host):
         tot = {"ms_total": 0.0, "ms_contract": 0.0, "ms_basis": 0.0, "ms_sort": 0.0, "ms_tiles": 0.0, "launches": 0,
-               "contract_launches": 0, "executed_flops": 0.0, "dense_flops": 0.0, "sum_nact": 0.0, "n_tiles": 0}
+               "contract_launches": 0, "executed_flops": 0.0, "useful_flops": 0.0, "dense_flops": 0.0, "sum_nact": 0.0, "n_tiles": 0}
         for _ in range(k):
             if host:
                 g.jtensors(r_host.numpy(), "total", out=t_host.numpy())
@@ -261,6 +261,10 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": ncu_traffic(nbf), "peak_source": peak_src,
                 "flops": "EXECUTED FP64 flops per tile: DMMA 2*128*4*nact*nn + GIAO-tap DFMA 2*128*3*nn*natoms_active (screened-function skipping on; exact zeros in the reference)",
+                # the same flops without K/N padding and partial tiles (real points x active functions): what a perfect tiling would issue
+                "useful_tflops": (tot["useful_flops"] / t_contract / 1e12) if t_contract > 0 else None,
+                "useful_frac": (tot["useful_flops"] / t_contract / 1e12 / peak) if t_contract > 0 else None,
+                "executed_over_useful": (tot["executed_flops"] / tot["useful_flops"]) if tot["useful_flops"] else None,
                 "avg_launch_ms": tot["ms_contract"] / max(tot["contract_launches"], 1), "launches_timed": tot["contract_launches"],
                 "share_of_step": tot["ms_contract"] / tot["ms_total"] if tot["ms_total"] else None,
                 "dense_equivalent_tflops": tot["dense_flops"] / (tot["ms_total"] * 1e-3) / 1e12,

@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [("n_points", C.c_long), ("n_tiles", C.c_long), ("sum_nact", C.c_double), ("executed_flops", C.c_double),
                 ("dense_flops", C.c_double), ("ms_sort", C.c_float), ("ms_tiles", C.c_float), ("ms_basis", C.c_float),
                 ("ms_contract", C.c_float), ("ms_fields", C.c_float), ("ms_total", C.c_float), ("launches", C.c_long),
-                ("contract_launches", C.c_long)]
+                ("contract_launches", C.c_long), ("useful_flops", C.c_double)]
 
 
 class GimicB200Error(RuntimeError):

@@ -361,7 +361,7 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     size_t pool_doubles = std::max(max_tile, std::min(total, c->pool_max_bytes / 8));
     std::vector<int> batch_start(1, 0);
     size_t off = 0, foff = 0, fidx_max = 0, aoff = 0, atab_max = 0;
-    double sum_nact = 0, flops = 0;
+    double sum_nact = 0, flops = 0, useful = 0;
     const bool giao = c->opts.giao != 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc &td = c->h_tiles[t];
@@ -376,6 +376,8 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         sum_nact += td.nact;
         flops += 2.0 * MT * (jpath ? 2 : c->nq) * (double)td.nact * td.nn;   // DMMA: K runs over the nact slots, N over the nn columns (multiples of 8)
         if (giao) flops += 2.0 * MT * (jpath ? 1.0 : 3.0) * (double)td.nn * td.nruns;   // GIAO taps: 3 (J path: 1) DFMA per accumulator element per active atom
+        useful += 2.0 * td.npts * (jpath ? 2 : c->nq) * (double)td.nreal * td.nreal;
+        if (giao) useful += 2.0 * td.npts * (jpath ? 1.0 : 3.0) * (double)td.nreal * td.nruns;
     }
     fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff);
     batch_start.push_back(ntiles);
@@ -433,7 +435,7 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
             cudaEventElapsedTime(&m, c->evpool[3 * b + 1], c->evpool[3 * b + 2]); c->stats.ms_contract += m;
         }
     }
-    c->stats.n_points += n; c->stats.n_tiles += ntiles; c->stats.sum_nact += sum_nact; c->stats.executed_flops += flops;
+    c->stats.n_points += n; c->stats.n_tiles += ntiles; c->stats.sum_nact += sum_nact; c->stats.executed_flops += flops; c->stats.useful_flops += useful;
     const double nbf = c->hb.nbf;
     c->stats.dense_flops += (double)n * (c->opts.giao ? 14.0 * nbf * nbf + 56.0 * nbf : 8.0 * nbf * nbf + 20.0 * nbf);
     return 0;

@@ -214,12 +214,15 @@ typedef struct {
     long n_points;            /* points processed */
     long n_tiles;             /* point tiles */
     double sum_nact;          /* sum over tiles of the padded active-function count */
-    double executed_flops;    /* 2 * MT * NQ * nact^2 summed over tiles (DMMA flops actually issued) */
+    double executed_flops;    /* FP64 flops actually issued, summed over tiles: DMMA 2*128*planes*nact*nn (padded K slots x padded N columns,
+                                 all 128 rows of a tile) + GIAO-tap DFMA 2*128*(3|1)*nn*active_atoms */
     double dense_flops;       /* n_points * (14 nbf^2 + 56 nbf), the reference's algorithmic work */
     float ms_sort, ms_tiles, ms_basis, ms_contract, ms_fields;   /* CUDA-event times per stage (profiling on) */
     float ms_total;           /* CUDA-event time of the whole call on the library stream, copies included (calc_fields/calc_jtensors) */
     long launches;            /* kernel launches issued */
     long contract_launches;   /* launches of the contraction kernel (k_jtensor) among them */
+    double useful_flops;      /* the same count without padding: real points of each tile x its active functions on both sides
+                                 (2*npts*planes*nreal^2 + taps); executed - useful = work spent on K/N padding and partial tiles */
 } gimic_b200_stats;
 int gimic_b200_get_stats(gimic_b200_handle h, gimic_b200_stats *out);
 int gimic_b200_set_profiling(gimic_b200_handle h, int enable);  /* per-stage CUDA-event timing (adds syncs) */
