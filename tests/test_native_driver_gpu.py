@@ -77,7 +77,7 @@ def _pair(tmp_path, name, mol, xdens, extra=None):
 
 def _run_both(dn, dp, args=()):
     from gimic_b200.driver import Driver
-    p = subprocess.run([EXE, *args, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=600)
+    p = subprocess.run([EXE, *args, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stderr
     out = io.StringIO()
     Driver(str(dp / "gimic.inp"), out=out, vtk_appended=("appended" in args)).run()
@@ -173,13 +173,13 @@ def test_native_scan_equals_python_scan(tmp_path, cases):
         for key, d in (("nat", dn), ("py", dp)):
             (d / f"gimic.{k}.inp").write_text(txt)
             names[key].append(str(d / f"gimic.{k}.inp"))
-    p = subprocess.run([EXE, *names["nat"]], capture_output=True, text=True, timeout=600)
+    p = subprocess.run([EXE, *names["nat"]], capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stderr
     run_scan(names["py"])
     for k in range(6):
         a = open(dn / f"gimic.{k}.out").read()
         _same_text(a, open(dp / f"gimic.{k}.out").read(), f"gimic.{k}.out")
-        single = subprocess.run([EXE, names["nat"][k]], capture_output=True, text=True, timeout=600)
+        single = subprocess.run([EXE, names["nat"][k]], capture_output=True, text=True, timeout=240)
         assert single.returncode == 0, single.stderr
         _same_text(a, single.stdout, f"separate run {k}")
 
@@ -195,8 +195,8 @@ def test_native_multi_device_partition_equals_single_device(tmp_path, cases, nam
         if name == "c4h4_read-grid":
             np.savetxt(d / "gridfile.grd", gold["grid"], fmt="%.6f")
     dn, dp = _pair(tmp_path, name, cases[case]["mol"], cases[case]["xdens"], extra)
-    one = subprocess.run([EXE, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=600)
-    two = subprocess.run([EXE, "--devices", "0,0", str(dp / "gimic.inp")], capture_output=True, text=True, timeout=600)
+    one = subprocess.run([EXE, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=240)
+    two = subprocess.run([EXE, "--devices", "0,0", str(dp / "gimic.inp")], capture_output=True, text=True, timeout=240)
     assert one.returncode == 0 and two.returncode == 0, (one.stderr, two.stderr)
     _same_text(one.stdout, two.stdout, "report")
     assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
