@@ -949,12 +949,12 @@ int gimic_b200_mol_geometry(const char *mol, int max_atoms, double *xyz, char *s
       catch (const std::exception &e) { return fail(GIMIC_B200_EINVAL, e.what()); }
 }
 
-int gimic_b200_mol_summary(const char *mol, int *info4) {
-    if (!mol || !info4) return fail(GIMIC_B200_EINVAL, "null argument");
+int gimic_b200_mol_summary(const char *mol, int *info5) {
+    if (!mol || !info5) return fail(GIMIC_B200_EINVAL, "null argument");
     try {
     gb::HostBasis hb; std::string err;
     if (!gb::parse_mol(mol, hb, err)) return fail(GIMIC_B200_EIO, err);
-    info4[0] = hb.natoms; info4[1] = hb.ngto; info4[2] = hb.nbf; info4[3] = hb.turbomole ? 1 : 0;
+    info5[0] = hb.natoms; info5[1] = hb.ngto; info5[2] = hb.nbf; info5[3] = hb.turbomole ? 1 : 0; info5[4] = hb.nbf_sph;
     return 0;
     } catch (const std::bad_alloc &) { return fail(GIMIC_B200_ENOMEM, "out of host memory"); }
       catch (const std::exception &e) { return fail(GIMIC_B200_EINVAL, e.what()); }

@@ -76,7 +76,7 @@ class Run {
     std::vector<double> xyz;
     GridSpec grid;
     Vec3 magnet{{0, 0, 0}};
-    int summary[4] = {0, 0, 0, 0};                  // natoms, primitive GTOs, contracted GTOs, TURBOMOLE flag (gimic_b200_mol_summary)
+    int summary[5] = {0, 0, 0, 0, 0};               // natoms, primitive GTOs, contracted GTOs, TURBOMOLE flag, spherical count (gimic_b200_mol_summary)
     std::map<int, Sums> results;
 
     // `find_shared`: returns an existing context for a key (scan mode) or nullptr
@@ -649,6 +649,22 @@ int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt) {
     });
 }
 
+// XDENS text -> binary cache next to it (<xdens>.bin) for the basis / open-shell / spherical settings of a gimic.inp.  A 10^4-function
+// XDENS is 3.2 GB of text (4e8 list-directed reads in read_dens, dens.f90:129-135); the cache is read at disk speed.
+int cache_xdens(const std::string &inpfile, const std::string &workdir_in, std::string &written) {
+    return guarded([&] {
+        const std::string workdir = workdir_in.empty() ? dirname_of(inpfile) : workdir_in;
+        const Input inp = parse_file(inpfile);
+        auto resolve = [&](const std::string &n) { return (!n.empty() && n[0] == '/') ? n : join_path(workdir, n); };
+        const std::string mol = resolve(inp.str("basis")), xdens = resolve(inp.str("xdens"));
+        int info[5];
+        check(gimic_b200_mol_summary(mol.c_str(), info));
+        const int nbf = inp.flag("Advanced.spherical") ? info[4] : info[2];
+        written = xdens + ".bin";
+        check(gimic_b200_convert_xdens(xdens.c_str(), nbf, inp.flag("openshell") ? 8 : 4, written.c_str()));
+    });
+}
+
 // Write an array computed elsewhere (e.g. by the reference's Fortran loops calling the batched C ABI) on the grid of a gimic.inp
 int write_field(const std::string &inpfile, const std::string &workdir_in, const std::string &kind, const double *data, long n, const std::string &name,
                 bool appended) {
@@ -740,6 +756,14 @@ int gimic_b200_run_scan(int n, const char *const *inpfiles, int device, int flag
 int gimic_b200_write_field(const char *inpfile, const char *workdir, const char *kind, const double *data, long n, const char *filename, int flags) {
     if (!inpfile || !kind || !filename) { gbd::g_error = "null argument"; return GIMIC_B200_EINVAL; }
     return gbd::write_field(inpfile, workdir ? workdir : "", kind, data, n, filename, (flags & GIMIC_B200_RUN_VTK_APPENDED) != 0);
+}
+
+int gimic_b200_cache_xdens(const char *inpfile, const char *workdir, char *written, int cap) {
+    if (!inpfile) { gbd::g_error = "null argument"; return GIMIC_B200_EINVAL; }
+    std::string out;
+    const int rc = gbd::cache_xdens(inpfile, workdir ? workdir : "", out);
+    if (rc == 0 && written && cap > 0) std::snprintf(written, (size_t)cap, "%s", out.c_str());
+    return rc;
 }
 
 const char *gimic_b200_driver_last_error(void) { return gbd::g_error.c_str(); }

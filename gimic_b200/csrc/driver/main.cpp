@@ -10,6 +10,7 @@
 static void usage(FILE *f) {
     std::fputs("usage: gimic-b200 [-y|--dryrun] [-t TITLE] [-d LEVEL] [-o NAME] [-b fgimic] [--workdir DIR] [--vtk ascii|appended] [--device N | --devices all|0,1,..] [gimic.inp ...]\n"
                "  --devices: one process, one context + host thread per listed GPU (point slabs / plane rows split, nothing exchanged)\n"
+               "  --cache-xdens: only convert the text XDENS named in the input(s) to the binary cache <xdens>.bin (host only)\n"
                "  one input: files are written to its directory (or --workdir), the report to stdout\n"
                "  several inputs (a current-profile scan): one device context, integrals batched into one tensor pass,\n"
                "  each report written to <input stem>.out\n", f);
@@ -19,7 +20,7 @@ int main(int argc, char **argv) {
     std::vector<const char *> files;
     const char *workdir = nullptr, *title = nullptr;
     int flags = 0, device = -1;
-    bool multi = false;
+    bool multi = false, cache = false;
     std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -30,6 +31,7 @@ int main(int argc, char **argv) {
         if (a == "-h" || a == "--help") { usage(stdout); return 0; }
         else if (a == "-y" || a == "--dryrun") flags |= GIMIC_B200_RUN_DRYRUN;
         else if (a == "--workdir") workdir = value("--workdir");
+        else if (a == "--cache-xdens") cache = true;
         // switches of the reference front end (src/gimic.in:36-57) that do not touch the hot path: accepted so that existing
         // command lines keep working (title / debug level / output base name only label the reference's own log)
         else if (a == "-t" || a == "--title") title = value("--title");
@@ -63,6 +65,14 @@ int main(int argc, char **argv) {
         else files.push_back(argv[i]);
     }
     if (files.empty()) files.push_back("gimic.inp");
+    if (cache) {                                     // host only: XDENS text -> <xdens>.bin for every input given
+        for (const char *f : files) {
+            char path[4096];
+            if (gimic_b200_cache_xdens(f, workdir, path, (int)sizeof path) != 0) { std::fprintf(stderr, "gimic-b200: %s\n", gimic_b200_driver_last_error()); return 1; }
+            std::printf(" binary density cache written: %s (set xdens to it)\n", path);
+        }
+        return 0;
+    }
     int rc;
     if (files.size() > 1) rc = gimic_b200_run_scan((int)files.size(), files.data(), !devices.empty() ? devices[0] : device, flags);
     else {

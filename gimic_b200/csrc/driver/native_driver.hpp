@@ -146,6 +146,7 @@ int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt);
 // writers alone: lay `data` out on the grid of a gimic.inp (kind: vti_scalar | vti_vector | jmod_txt | vtu_vector | vtu_scalar)
 int write_field(const std::string &inpfile, const std::string &workdir, const std::string &kind, const double *data, long n, const std::string &name,
                 bool appended);
+int cache_xdens(const std::string &inpfile, const std::string &workdir, std::string &written);   // XDENS text -> <xdens>.bin
 const std::string &last_error_message();
 
 }  // namespace gbd

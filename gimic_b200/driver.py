@@ -66,11 +66,12 @@ def mol_geometry(mol):
 
 
 def mol_summary(mol):
-    """(natoms, primitive GTOs, contracted cartesian GTOs, is_turbomole) as new_basis prints them (gimic_b200_mol_summary)"""
+    """(natoms, primitive GTOs, contracted cartesian GTOs, is_turbomole) as new_basis prints them (gimic_b200_mol_summary; its fifth
+    entry, the spherical count, is only needed to size an XDENS over spherical components)"""
     import ctypes as C
     from . import _lib
     L = _lib.lib()
-    info = (C.c_int * 4)()
+    info = (C.c_int * 5)()
     if L.gimic_b200_mol_summary(os.fsencode(mol), info) < 0:
         raise RuntimeError(L.gimic_b200_last_error().decode())
     return int(info[0]), int(info[1]), int(info[2]), bool(info[3])

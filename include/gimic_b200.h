@@ -186,9 +186,10 @@ int gimic_b200_gauss_points(double a, double b, int npts, int order, int quadrat
  * and symbols2 (the two-character element field of intgrl.f90:111, not NUL-terminated); either may be NULL. */
 int gimic_b200_mol_geometry(const char *mol, int max_atoms, double *xyz, char *symbols2);
 
-/* What new_basis prints about a MOL file (basis.f90:44-62, intgrl.f90:48-60), host only: info4 = { number of atoms, total number of
- * primitive GTOs (sum of npf x components), number of contracted cartesian GTOs, 1 if the file says TURBOMOLE }. */
-int gimic_b200_mol_summary(const char *mol, int *info4);
+/* What new_basis prints about a MOL file (basis.f90:44-62, intgrl.f90:48-60), host only: info5 = { number of atoms, total number of
+ * primitive GTOs (sum of npf x components), number of contracted cartesian GTOs, 1 if the file says TURBOMOLE, number of
+ * contracted spherical GTOs (the dimension of the XDENS matrices when Advanced.spherical is on) }. */
+int gimic_b200_mol_summary(const char *mol, int *info5);
 
 /* XDENS text (dens.f90:129-135: one real per line, 4 or 8 matrices of nbf x nbf) -> binary cache that gimic_b200_create
  * recognises by its "GB2XDENS" magic (int64 nbf, int64 nmat, raw doubles in file order).  Values are stored exactly as the

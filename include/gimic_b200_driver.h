@@ -64,6 +64,12 @@ int gimic_b200_run_scan(int n, const char *const *inpfiles, int device, int flag
 int gimic_b200_write_field(const char *inpfile, const char *workdir, const char *kind, const double *data, long n,
                            const char *filename, int flags);
 
+/* Parse the text XDENS named in gimic.inp once (threaded) and write the binary cache <xdens>.bin beside it, sized from the input's
+ * basis / openshell / Advanced.spherical settings; point `xdens=` at the .bin afterwards (gimic_b200_create recognises it).  Replaces
+ * the 4 x nbf^2 (8 x for open shell) list-directed reads of read_dens (src/libgimic/dens.f90:56-135) on every later run.  Host only.
+ * `written` (may be NULL) receives the path of the cache file. */
+int gimic_b200_cache_xdens(const char *inpfile, const char *workdir, char *written, int cap);
+
 const char *gimic_b200_driver_last_error(void);
 
 #ifdef __cplusplus

@@ -59,7 +59,8 @@ def test_driver_header_symbols_exported(D):
     hdr = open(os.path.join(ROOT, "include", "gimic_b200_driver.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b(gimic_b200_\w+)\s*\(", hdr))
-    assert names == {"gimic_b200_run_input", "gimic_b200_run", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_driver_last_error"}
+    assert names == {"gimic_b200_run_input", "gimic_b200_run", "gimic_b200_run_scan", "gimic_b200_write_field", "gimic_b200_cache_xdens",
+                     "gimic_b200_driver_last_error"}
     for n in names:
         assert hasattr(D, n), n
 
@@ -380,3 +381,23 @@ def test_python_repr_layout_on_random_magnitudes(D, tmp_path):
         writers.write_vti_scalar(str(d / "py.vti"), g, v, True)
         _write(D, d, "vti_scalar", v, "nat.vti", 2)
         assert filecmp.cmp(d / "py.vti", d / "nat.vti", shallow=False), (it, open(d / "py.vti", "rb").read(300), open(d / "nat.vti", "rb").read(300))
+
+
+def test_cache_xdens_switch(D, tmp_path):
+    """gimic-b200 --cache-xdens gimic.inp: the text XDENS named in the input becomes <xdens>.bin (GB2XDENS magic, sizes from the MOL file and
+    the openshell keyword, values bit for bit what the text parser reads); host only"""
+    d = _workdir(tmp_path, "open-shell_integration")
+    vals = fixtures.golden_npz("open_shell_xdens.npz")["xdens"]
+    fixtures.write_xdens(str(d / "XDENS"), vals)
+    p = subprocess.run([EXE, "--cache-xdens", str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "XDENS.bin" in p.stdout, p.stderr
+    raw = open(d / "XDENS.bin", "rb").read()
+    assert raw[:8] == b"GB2XDENS"
+    nbf, nmat = np.frombuffer(raw[8:24], dtype=np.int64)
+    assert (nbf, nmat) == (168, 8)
+    got = np.frombuffer(raw[24:], dtype=np.float64)
+    want = np.array([float("%.14E" % v) for v in vals])
+    assert got.shape == want.shape and np.array_equal(got, want)
+    (d / "XDENS").write_text("1.0\n")
+    q = subprocess.run([EXE, "--cache-xdens", str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
+    assert q.returncode == 1 and "too short" in q.stderr
