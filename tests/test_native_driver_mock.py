@@ -102,17 +102,6 @@ def _same_dirs(dn, dp):
         assert filecmp.cmp(dn / f, dp / f, shallow=False), f
 
 
-def _window(text, anchor, n=10):
-    lines = text.split("\n")
-    i = next(k for k, l in enumerate(lines) if l.startswith(anchor))
-    return [float(t) for l in lines[i:i + n] for t in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", l)]
-
-
-def _small(txt):
-    """shrink the quadrature so that the CPU oracle answers in seconds"""
-    return txt.replace("grid_points=[30, 30, 0]", "grid_points=[9, 9, 0]")
-
-
 def test_c4h4_read_grid_native_vs_python_and_golden(mock_dir, tmp_path, cases):
     """test/c4h4/read-grid through gimic-b200: jvec.vtu equals the Python driver's bytes and the reference's golden at its 10 digits"""
     from make_golden import read_vtu_vectors

@@ -1,7 +1,7 @@
 """Latency of the legacy one-point-per-call boundary (gimic_interface.h: gimic_calc_jtensor / gimic_calc_jvector), the way
 src/pygimic/field.py:82-93 and tools/PyGimicTest.py.in drive the reference, next to the same points through ONE batched call.
 The reference itself needs ~0.65 ms per tensor at nbf=168 on one core (1549 evals/s, test/open-shell/integration stdout)."""
-import ctypes as C, json, os, sys, tempfile, time
+import json, os, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
