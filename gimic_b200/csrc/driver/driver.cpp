@@ -8,8 +8,11 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <ctime>
 #include <memory>
 #include <thread>
+#include <sys/resource.h>
 #include <sys/stat.h>
 
 #include "../../../include/gimic_b200_driver.h"
@@ -78,10 +81,20 @@ class Run {
     Vec3 magnet{{0, 0, 0}};
     int summary[5] = {0, 0, 0, 0, 0};               // natoms, primitive GTOs, contracted GTOs, TURBOMOLE flag, spherical count (gimic_b200_mol_summary)
     std::map<int, Sums> results;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();   // stockas_klocka reports the times of the whole run
+    double cpu0[2] = {0, 0};
+
+    static void cpu_times(double *us) {
+        struct rusage ru;
+        getrusage(RUSAGE_SELF, &ru);
+        us[0] = (double)ru.ru_utime.tv_sec + 1e-6 * (double)ru.ru_utime.tv_usec;
+        us[1] = (double)ru.ru_stime.tv_sec + 1e-6 * (double)ru.ru_stime.tv_usec;
+    }
 
     // `find_shared`: returns an existing context for a key (scan mode) or nullptr
     template <class Finder>
     Run(const std::string &inpfile, const RunOptions &o, FILE *report, Finder find_shared) : opt(o), out{report} {
+        cpu_times(cpu0);
         workdir = o.workdir.empty() ? dirname_of(inpfile) : o.workdir;
         inp = parse_file(inpfile);
         if (o.dryrun) inp.force_flag("dryrun", true);                 // the -y switch overrides the keyword (src/gimic.in:139-140)
@@ -151,7 +164,34 @@ class Run {
     }
 
     void run(const std::map<int, Sums> *pre = nullptr) {
-        // initialize(), gimic.F90:107-131 (the fdate() line is left out: reports stay reproducible)
+        run_body(pre);
+        // finalize() + stockas_klocka (gimic.F90:43-52,134-138; grid.f90:453; basis.f90:348-349; timer.f90:13-43).  The jobscripts
+        // recognise a finished slice by the word "wall" in gimic.N.out (jobscripts/src/current-profile-local-submit:52).
+        double cpu[2];
+        cpu_times(cpu);
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        out.say("*** Deallocated grid data");
+        out.say("INFO: Deallocated basis set and atom data");
+        out.say();
+        out.say(std::string(70, '-'));
+        out.say(sfmt("   wall time:%9.2fsec", wall));
+        out.say(sfmt("        user:%9.2fsec", cpu[0] - cpu0[0]));
+        out.say(sfmt("         sys:%9.2fsec", cpu[1] - cpu0[1]));
+        out.say(std::string(70, '-'));
+        char date[64];
+        const std::time_t now = std::time(nullptr);
+        std::tm tmv;
+        localtime_r(&now, &tmv);
+        std::strftime(date, sizeof date, "%a %b %e %H:%M:%S %Y", &tmv);
+        out.say(date);
+        out.say("Hello World! (tm)");
+        out.say();
+        out.say("done.");
+        out.say();
+    }
+
+    void run_body(const std::map<int, Sums> *pre) {
+        // initialize(), gimic.F90:107-131 (its fdate() line is left out)
         std::string title = inp.str("title");
         while (!title.empty() && std::isspace((unsigned char)title.front())) title.erase(title.begin());
         while (!title.empty() && std::isspace((unsigned char)title.back())) title.pop_back();

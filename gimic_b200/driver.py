@@ -11,6 +11,7 @@ splits plane rows and all-reduces the partial sums.
 """
 import os
 import sys
+import time
 import numpy as np
 
 from . import inp as _inp
@@ -89,6 +90,7 @@ def _dist():
 
 class Driver:
     def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False, dryrun=False, title=None):
+        self._t0, self._cpu0 = time.perf_counter(), os.times()    # stockas_klocka reports the times of the whole run
         self.workdir = workdir or os.path.dirname(os.path.abspath(inpfile))
         self.inp = _inp.parse_file(inpfile)
         if dryrun:                               # the -y switch overrides the keyword (src/gimic.in:139-140)
@@ -133,8 +135,27 @@ class Driver:
 
     # -------------------------------------------------------------------------------------------------
     def run(self, integral_results=None):
+        self._run(integral_results)
+        # finalize() + stockas_klocka (gimic.F90:43-52,134-138; grid.f90:453; basis.f90:348-349; timer.f90:13-43).  The jobscripts
+        # recognise a finished slice by the word "wall" in gimic.N.out (jobscripts/src/current-profile-local-submit:52).
+        cpu = os.times()
+        self.say("*** Deallocated grid data")
+        self.say("INFO: Deallocated basis set and atom data")
+        self.say()
+        self.say("-" * 70)
+        self.say(f"   wall time:{time.perf_counter() - self._t0:9.2f}sec")
+        self.say(f"        user:{cpu.user - self._cpu0.user:9.2f}sec")
+        self.say(f"         sys:{cpu.system - self._cpu0.system:9.2f}sec")
+        self.say("-" * 70)
+        self.say(time.strftime("%a %b %e %H:%M:%S %Y"))
+        self.say("Hello World! (tm)")
+        self.say()
+        self.say("done.")
+        self.say()
+
+    def _run(self, integral_results=None):
         I = self.inp
-        # initialize(), gimic.F90:107-131 (the fdate() line is left out: reports stay reproducible)
+        # initialize(), gimic.F90:107-131 (its fdate() line is left out)
         self.say((" TITLE: " + str(I.get("title")).strip()).rstrip())       # msg_out trims trailing blanks
         self.say()
         if not I.get("Advanced.GIAO"):

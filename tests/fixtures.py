@@ -28,6 +28,20 @@ def materialize(tmp):
     return out
 
 
+_CLOCK = None
+
+
+def strip_clock(text):
+    """a report with the run-dependent part of its trailer (timer.f90:13-43: wall / user / sys times and the date) blanked, so that
+    two runs can be compared byte for byte"""
+    global _CLOCK
+    import re
+    if _CLOCK is None:
+        _CLOCK = (re.compile(r"^( {4}wall time:| {9}user:| {10}sys:).*$", re.M),
+                  re.compile(r"^( -{70}\n) \w{3} \w{3} [ \d]\d \d\d:\d\d:\d\d \d{4}$", re.M))
+    return _CLOCK[1].sub(r"\1 <date>", _CLOCK[0].sub(r"\1", text))
+
+
 def golden_npz(name):
     return np.load(os.path.join(GOLD, name))
 

@@ -81,11 +81,11 @@ def _run_both(dn, dp, args=()):
     assert p.returncode == 0, p.stderr
     out = io.StringIO()
     Driver(str(dp / "gimic.inp"), out=out, vtk_appended=("appended" in args)).run()
-    _same_text(p.stdout, out.getvalue(), "report")
+    _same_text(fixtures.strip_clock(p.stdout), fixtures.strip_clock(out.getvalue()), "report")
     assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
     for f in sorted(os.listdir(dn)):
         if not filecmp.cmp(dn / f, dp / f, shallow=False):
-            _same_text(open(dn / f, errors="replace").read(), open(dp / f, errors="replace").read(), f)
+            _same_text(fixtures.strip_clock(open(dn / f, errors="replace").read()), fixtures.strip_clock(open(dp / f, errors="replace").read()), f)
     return p.stdout
 
 
@@ -177,11 +177,11 @@ def test_native_scan_equals_python_scan(tmp_path, cases):
     assert p.returncode == 0, p.stderr
     run_scan(names["py"])
     for k in range(6):
-        a = open(dn / f"gimic.{k}.out").read()
-        _same_text(a, open(dp / f"gimic.{k}.out").read(), f"gimic.{k}.out")
+        a = fixtures.strip_clock(open(dn / f"gimic.{k}.out").read())
+        _same_text(a, fixtures.strip_clock(open(dp / f"gimic.{k}.out").read()), f"gimic.{k}.out")
         single = subprocess.run([EXE, names["nat"][k]], capture_output=True, text=True, timeout=240)
         assert single.returncode == 0, single.stderr
-        _same_text(a, single.stdout, f"separate run {k}")
+        _same_text(a, fixtures.strip_clock(single.stdout), f"separate run {k}")
 
 
 @pytest.mark.parametrize("name,case", [("c4h4_integration", "c4h4"), ("open-shell_3d", "open_shell"), ("c4h4_read-grid", "c4h4")])
@@ -198,7 +198,7 @@ def test_native_multi_device_partition_equals_single_device(tmp_path, cases, nam
     one = subprocess.run([EXE, str(dn / "gimic.inp")], capture_output=True, text=True, timeout=240)
     two = subprocess.run([EXE, "--devices", "0,0", str(dp / "gimic.inp")], capture_output=True, text=True, timeout=240)
     assert one.returncode == 0 and two.returncode == 0, (one.stderr, two.stderr)
-    _same_text(one.stdout, two.stdout, "report")
+    _same_text(fixtures.strip_clock(one.stdout), fixtures.strip_clock(two.stdout), "report")
     assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
     for f in sorted(os.listdir(dn)):
         if not filecmp.cmp(dn / f, dp / f, shallow=False):

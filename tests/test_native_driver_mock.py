@@ -52,7 +52,7 @@ def _env(mock_dir):
 def _native(mock_dir, args, timeout=900):
     p = subprocess.run([EXE, *[str(a) for a in args]], capture_output=True, text=True, timeout=timeout, env=_env(mock_dir))
     assert p.returncode == 0, p.stderr
-    return p.stdout
+    return fixtures.strip_clock(p.stdout)
 
 
 PY_RUNNER = r'''
@@ -79,7 +79,7 @@ def _python(mock_dir, args, timeout=900):
     code = PY_RUNNER.format(root=ROOT, so=str(mock_dir / "libgimic_b200.so"))
     p = subprocess.run([sys.executable, "-c", code, *[str(a) for a in args]], capture_output=True, text=True, timeout=timeout, env=_env(mock_dir))
     assert p.returncode == 0, p.stderr[-2000:]
-    return p.stdout
+    return fixtures.strip_clock(p.stdout)
 
 
 def _pair(tmp_path, name, mol, xdens, edit=None, extra=None):
@@ -99,7 +99,10 @@ def _pair(tmp_path, name, mol, xdens, edit=None, extra=None):
 def _same_dirs(dn, dp):
     assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
     for f in sorted(os.listdir(dn)):
-        assert filecmp.cmp(dn / f, dp / f, shallow=False), f
+        if f.endswith(".out"):             # scan reports carry wall-clock times
+            assert fixtures.strip_clock(open(dn / f).read()) == fixtures.strip_clock(open(dp / f).read()), f
+        else:
+            assert filecmp.cmp(dn / f, dp / f, shallow=False), f
 
 
 def test_c4h4_read_grid_native_vs_python_and_golden(mock_dir, tmp_path, cases):
@@ -233,8 +236,9 @@ def test_scalar_modes_appended_vtk_and_scan_native_vs_python(mock_dir, tmp_path,
     _native(mock_dir, names["nat"])
     _python(mock_dir, names["py"])
     for k in range(6):
-        a = open(dn / f"gimic.{k}.out").read()
-        assert a == open(dp / f"gimic.{k}.out").read(), k
+        a = fixtures.strip_clock(open(dn / f"gimic.{k}.out").read())
+        assert a == fixtures.strip_clock(open(dp / f"gimic.{k}.out").read()), k
+        assert "wall time:" in a                                        # what the jobscripts grep for in a finished slice
         assert a == _native(mock_dir, [names["nat"][k]]), k             # what a separate run prints
         assert "Induced current (au)" in a
 
@@ -307,7 +311,7 @@ def test_python_driver_world2_gloo_equals_single_process(mock_dir, tmp_path, cas
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
-    dist_out = rep.read_text()
+    dist_out = fixtures.strip_clock(rep.read_text())
     if name == "c4h4_integration":
         num = r"[-+]?\d+\.\d+"
         assert re.sub(num, "#", single) == re.sub(num, "#", dist_out)
