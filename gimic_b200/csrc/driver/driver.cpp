@@ -10,7 +10,9 @@
 #include <cstring>
 #include <chrono>
 #include <ctime>
+#include <fstream>
 #include <memory>
+#include <sstream>
 #include <thread>
 #include <sys/resource.h>
 #include <sys/stat.h>
@@ -685,6 +687,39 @@ int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt) {
         for (size_t i = 0; i < runs.size(); ++i) {
             runs[i]->run(pre[i].empty() ? nullptr : &pre[i]);
             std::fflush(runs[i]->out.f);
+        }
+        // current_profile.dat next to the first input: slice position (index x delta when the jobscripts' calculation.dat is there,
+        // jobscripts/src/current-profile-header:38, else the index), net / diatropic / paratropic current in nA/T -- what
+        // jobscripts/src/gradient.sh.in:38-47 assembles by grepping every gimic.N.out, here from the unrounded sums (8 decimals)
+        std::vector<const Run *> rows;
+        for (const auto &r : runs)
+            if (r->inp.str("calc") == "integral" && !r->inp.flag("dryrun") && r->results.count(GIMIC_B200_TOTAL)) rows.push_back(r.get());
+        if (rows.size() >= 2) {
+            bool has_delta = false;
+            double delta = 0.0;
+            {
+                std::ifstream cf(join_path(rows[0]->workdir, "calculation.dat"));
+                std::stringstream ss;
+                if (cf) ss << cf.rdbuf();
+                const std::string txt = ss.str();
+                const size_t p = txt.find("delta=");
+                if (p != std::string::npos) {
+                    std::string tok = txt.substr(p + 6, 40);
+                    for (char &ch : tok) if (ch == 'd' || ch == 'D') ch = 'e';
+                    char *end = nullptr;
+                    delta = std::strtod(tok.c_str(), &end);
+                    has_delta = end != tok.c_str();
+                }
+            }
+            const std::string ppath = join_path(rows[0]->workdir, "current_profile.dat");
+            FILE *pf = std::fopen(ppath.c_str(), "w");
+            if (!pf) throw DriverError("cannot write " + ppath);
+            for (size_t k = 0; k < rows.size(); ++k) {
+                const Sums &sm = rows[k]->results.at(GIMIC_B200_TOTAL);
+                if (has_delta) std::fprintf(pf, "%5.2f", (double)k * delta); else std::fprintf(pf, "%5zu", k);
+                std::fprintf(pf, "\t% .8f\t% .8f\t% .8f\n", au2si(sm[0]), au2si(sm[1]), au2si(sm[2]));
+            }
+            std::fclose(pf);
         }
     });
 }

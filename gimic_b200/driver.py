@@ -497,7 +497,36 @@ def run_scan(infiles, device=-1, outs=None):
         d.run(pre.get(id(d)))
     for o in opened:
         o.close()
+    write_current_profile(drivers)
     return drivers
+
+
+def _profile_delta(workdir):
+    """slice width from the jobscripts' calculation.dat ('delta=0.02 nsteps=400', jobscripts/src/current-profile-header:38), or None"""
+    import re
+    try:
+        m = re.search(r"delta=([-+.\deEdD]+)", open(os.path.join(workdir, "calculation.dat")).read())
+        return float(m.group(1).replace("d", "e").replace("D", "e")) if m else None
+    except (OSError, ValueError):
+        return None
+
+
+def write_current_profile(drivers):
+    """current_profile.dat next to the first input: slice position (index x delta when calculation.dat is there, else the index),
+    net / diatropic / paratropic current strength in nA/T -- what jobscripts/src/gradient.sh.in:38-47 assembles by grepping the
+    'Induced current' blocks of every gimic.N.out, here from the unrounded sums of the batched pass (8 decimals)."""
+    rows = [d for d in drivers if d.rank == 0 and d.inp.get("calc") == "integral" and not d.inp.get("dryrun") and getattr(d, "results", None)]
+    if len(rows) < 2:
+        return None
+    wd = rows[0].workdir
+    delta = _profile_delta(wd)
+    path = os.path.join(wd, "current_profile.dat")
+    with open(path, "w") as f:
+        for k, d in enumerate(rows):
+            tot, pos, neg = (au2si(v) for v in d.results["total"][0:3])
+            x = f"{k * delta:5.2f}" if delta is not None else f"{k:5d}"
+            f.write(f"{x}\t{tot: .8f}\t{pos: .8f}\t{neg: .8f}\n")
+    return path
 
 
 def _context_key_of(inpfile):

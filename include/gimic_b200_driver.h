@@ -54,7 +54,9 @@ int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts);
 
 /* A current-profile scan (jobscripts/src/current-profile-local-submit: `gimic gimic.N.inp > gimic.N.out` for every slice):
  * inputs that agree on basis, densities and Advanced settings share ONE device context, and all their plane integrals go
- * through ONE tensor pass per spin case (gimic_b200_integrate_batch).  Each report is written to <input stem>.out. */
+ * through ONE tensor pass per spin case (gimic_b200_integrate_batch).  Each report is written to <input stem>.out, and
+ * current_profile.dat (slice position, net / diatropic / paratropic current in nA/T; the table jobscripts/src/gradient.sh.in:38-47
+ * pastes together from the reports) next to the first input. */
 int gimic_b200_run_scan(int n, const char *const *inpfiles, int device, int flags);
 
 /* Writers alone (vtkplot.f90:14-391, jfield.f90:356-376,531-541): lay `data` out on the grid that gimic.inp describes and

@@ -233,8 +233,20 @@ def test_scalar_modes_appended_vtk_and_scan_native_vs_python(mock_dir, tmp_path,
         for key, d in (("nat", dn), ("py", dp)):
             (d / f"gimic.{k}.inp").write_text(txt)
             names[key].append(d / f"gimic.{k}.inp")
+    for d in (dn, dp):
+        (d / "calculation.dat").write_text("atom1=1\natom2=2\nin=0.0 out=7.0\ndelta=1.209357 nsteps=6\n")
     _native(mock_dir, names["nat"])
     _python(mock_dir, names["py"])
+    # current_profile.dat (what jobscripts/src/gradient.sh.in pastes together from the gimic.N.out files): same bytes from both drivers,
+    # and its columns are the numbers printed in the reports (there rounded to 6 decimals)
+    assert filecmp.cmp(dn / "current_profile.dat", dp / "current_profile.dat", shallow=False)
+    prof = np.loadtxt(dn / "current_profile.dat")
+    assert prof.shape == (6, 4) and np.allclose(prof[:, 0], np.round(np.arange(6) * 1.209357, 2))
+    for k in range(6):
+        rep = open(dn / f"gimic.{k}.out").read()
+        tail = rep[rep.index("*** Integrating current"):]
+        si = float(re.search(r"Induced current \(nA/T\)\s+:\s*([-\d.]+)", tail).group(1))
+        assert abs(prof[k, 1] - si) < 1.01e-6 and abs(prof[k, 1] - (prof[k, 2] + prof[k, 3])) < 1e-7
     for k in range(6):
         a = fixtures.strip_clock(open(dn / f"gimic.{k}.out").read())
         assert a == fixtures.strip_clock(open(dp / f"gimic.{k}.out").read()), k
