@@ -382,6 +382,10 @@ def test_python_repr_layout_on_random_magnitudes(D, tmp_path):
         writers.write_vti_scalar(str(d / "py.vti"), g, v, True)
         _write(D, d, "vti_scalar", v, "nat.vti", 2)
         assert filecmp.cmp(d / "py.vti", d / "nat.vti", shallow=False), (it, open(d / "py.vti", "rb").read(300), open(d / "nat.vti", "rb").read(300))
+        # the ASCII header prints the same numbers list-directed (gfortran layout, 17 significant digits): ld_real on both sides
+        writers.write_vti_scalar(str(d / "pya.vti"), g, v, False)
+        _write(D, d, "vti_scalar", v, "nata.vti", 0)
+        assert filecmp.cmp(d / "pya.vti", d / "nata.vti", shallow=False), (it, open(d / "pya.vti", "rb").read(400), open(d / "nata.vti", "rb").read(400))
 
 
 def test_cache_xdens_switch(D, tmp_path):
