@@ -53,8 +53,9 @@ void vti_header(OutFile &f, const GridSpec &g, const Vec3 &qmin, const Vec3 &ste
     for (int d = 0; d < 3; ++d) ext += ld_int(0) + ld_int(g.npts[d] - 1);
     f.w("<?xml version=\"1.0\"?>\n");
     f.w(" <VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\">\n");
-    f.w("   <ImageData WholeExtent=\"" + ext + " \" Origin=\"" + ld_real(qmin[0]) + ld_real(qmin[1]) + ld_real(qmin[2]) + "\" Spacing=\"" +
-        ld_real(step[0]) + ld_real(step[1]) + ld_real(step[2]) + "\">\n");
+    // gfortran separates a numeric list item from a following character item by one blank (test/*/reference/*.vti)
+    f.w("   <ImageData WholeExtent=\"" + ext + " \" Origin=\"" + ld_real(qmin[0]) + ld_real(qmin[1]) + ld_real(qmin[2]) + " \" Spacing=\"" +
+        ld_real(step[0]) + ld_real(step[1]) + ld_real(step[2]) + " \">\n");
     f.w("   <Piece Extent=\"" + ext + " \">\n");
     f.w("   <PointData Scalars=\"scalars\">\n");
     f.w(fmt("   <DataArray Name=\"%s\" type=\"Float64\" NumberOfComponents=\"%d\" Format=\"ascii\">\n", name, ncomp));
@@ -167,7 +168,7 @@ std::string ld_real(double x) {
         const int e = std::atoi(m.c_str() + epos + 1);
         return "  " + std::string(x < 0 ? "-" : "") + m.substr(0, epos) + fmt("E%+04d", e) + " ";
     }
-    int dec = 17;
+    int dec = ax == 0.0 ? 16 : 17;                 // gfortran prints zero as 0.0000000000000000 (test/benzene/2d/reference/jvec.vti)
     if (ax >= 1.0) {
         snprintf(buf, sizeof buf, "%.0f", std::floor(ax));
         dec = 17 - (int)std::strlen(buf);

@@ -62,6 +62,8 @@ def _ld_real(x):
         return "  " + s + " "
     nint = len(str(int(ax))) if ax >= 1.0 else 0
     dec = 17 - max(nint, 0) if ax >= 1.0 else 17
+    if ax == 0.0:
+        dec = 16                      # gfortran prints zero as 0.0000000000000000 (test/benzene/2d/reference/jvec.vti)
     s = f"{ax:.{dec}f}"
     if ax < 1.0:
         s = s  # 0.ddddddddddddddddd
@@ -87,8 +89,9 @@ def _vti_header(f, npts, qmin, step, name, ncomp):
     ext = "".join(_ld_int(v) for v in (0, npts[0] - 1, 0, npts[1] - 1, 0, npts[2] - 1))
     f.write('<?xml version="1.0"?>\n')
     f.write(' <VTKFile type="ImageData" version="0.1" byte_order="LittleEndian">\n')
-    f.write('   <ImageData WholeExtent="' + ext + ' " Origin="' + "".join(_ld_real(v) for v in qmin) + '" Spacing="'
-            + "".join(_ld_real(v) for v in step) + '">\n')
+    # gfortran separates a numeric list item from a following character item by one blank (test/*/reference/*.vti)
+    f.write('   <ImageData WholeExtent="' + ext + ' " Origin="' + "".join(_ld_real(v) for v in qmin) + ' " Spacing="'
+            + "".join(_ld_real(v) for v in step) + ' ">\n')
     f.write('   <Piece Extent="' + ext + ' ">\n')
     f.write('   <PointData Scalars="scalars">\n')
     f.write(f'   <DataArray Name="{name}" type="Float64" NumberOfComponents="{ncomp}" Format="ascii">\n')

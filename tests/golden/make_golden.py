@@ -96,6 +96,34 @@ def parse_integral_stdout(path):
     return dict(blocks=blocks, geometry=geo)
 
 
+_NUMLINE = re.compile(r"^\s*(?:[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[EeDd]?[-+]\d+)?\s*)+$")
+
+
+def file_frame(path, coord_chars=0):
+    """The non-numeric skeleton of an output file: text lines verbatim ("T:<line>"), lines that hold only numbers as "D:<tokens>:<length>",
+    run-length encoded.  coord_chars > 0: also a SHA-256 over the first coord_chars characters of every numeric line (the coordinate
+    columns of jmod.txt, which do not depend on the densities)."""
+    import hashlib
+    kinds, h = [], hashlib.sha256()
+    for line in open(path, encoding="utf-8", errors="replace").read().split("\n"):
+        if line.strip() and _NUMLINE.match(line):
+            kinds.append(f"D:{len(line.split())}:{len(line)}")
+            if coord_chars:
+                h.update(line[:coord_chars].encode() + b"\n")
+        else:
+            kinds.append("T:" + line)
+    rle = []
+    for k in kinds:
+        if rle and rle[-1][0] == k:
+            rle[-1][1] += 1
+        else:
+            rle.append([k, 1])
+    out = {"rle": rle}
+    if coord_chars:
+        out["coord_sha256"] = h.hexdigest()
+    return out
+
+
 def main():
     t = os.path.join(REF, "test")
     shutil.copyfile(os.path.join(t, "c4h4/MOL"), os.path.join(OUT, "c4h4_MOL"))
@@ -124,6 +152,23 @@ def main():
         assert jv.shape == (n, 3) and jm.shape == (n,), (jv.shape, jm.shape)
         d[f"jvec{tag}"] = jv[idx]; d[f"jmod{tag}"] = jm[idx]
     np.savez_compressed(os.path.join(OUT, "open_shell_3d.npz"), **d)
+    # skeletons of the reference's output files (every byte that is not a data value: XML boilerplate, list-directed header numbers,
+    # block sizes, tokens per line, line lengths); benzene files included -- their skeleton only depends on MOL + gimic.inp
+    frames = {}
+    for rel, cc in (("benzene/2d/reference/jvec.vti", 0), ("benzene/2d-keyword-magnet/reference/jvec.vti", 0), ("benzene/vectors/reference/jvec.vti", 0),
+                    ("benzene/3d/reference/jvec.vti", 0), ("benzene/3d/reference/jmod.vti", 0), ("benzene/3d/reference/acid.vti", 0),
+                    ("benzene/3d-keyword-magnet/reference/jvec.vti", 0), ("benzene/int-cdens/reference/jmod.txt", 33),
+                    ("open-shell/3d/reference/jvec.vti", 0), ("open-shell/3d/reference/jmodspindens.vti", 0)):
+        frames[rel] = file_frame(os.path.join(t, rel), cc)
+    # jvec.vtu: the Points block holds the grid coordinates (independent of the densities): hash its lines as well
+    import hashlib
+    vtu = os.path.join(t, "c4h4/read-grid/reference/jvec.vtu")
+    frames["c4h4/read-grid/reference/jvec.vtu"] = file_frame(vtu)
+    hp = hashlib.sha256()
+    for line in open(vtu).read().split("\n")[6:6 + 4110]:
+        hp.update(line.encode() + b"\n")
+    frames["c4h4/read-grid/reference/jvec.vtu"]["points_sha256"] = hp.hexdigest()
+    json.dump(frames, open(os.path.join(OUT, "file_frames.json"), "w"), indent=0)
     # grid geometry / point counts / field direction printed by the reference for the benzene keyword tests
     # (their XDENS is a stripped blob, but these lines only depend on MOL + gimic.inp)
     grids = {}

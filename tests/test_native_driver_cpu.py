@@ -406,3 +406,67 @@ def test_cache_xdens_switch(D, tmp_path):
     (d / "XDENS").write_text("1.0\n")
     q = subprocess.run([EXE, "--cache-xdens", str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
     assert q.returncode == 1 and "too short" in q.stderr
+
+
+FRAME_CASES = [("benzene/2d/reference/jvec.vti", "benzene_2d", "vti_vector"), ("benzene/2d-keyword-magnet/reference/jvec.vti", "benzene_2d-keyword-magnet", "vti_vector"),
+               ("benzene/vectors/reference/jvec.vti", "benzene_vectors", "vti_vector"), ("benzene/3d/reference/jvec.vti", "benzene_3d", "vti_vector"),
+               ("benzene/3d/reference/jmod.vti", "benzene_3d", "vti_scalar"), ("benzene/3d/reference/acid.vti", "benzene_3d", "vti_scalar"),
+               ("benzene/3d-keyword-magnet/reference/jvec.vti", "benzene_3d-keyword-magnet", "vti_vector"),
+               ("benzene/int-cdens/reference/jmod.txt", "benzene_int-cdens", "jmod_txt"),
+               ("open-shell/3d/reference/jvec.vti", "open-shell_3d", "vti_vector"), ("open-shell/3d/reference/jmodspindens.vti", "open-shell_3d", "vti_scalar")]
+
+
+@pytest.mark.parametrize("rel,name,kind", FRAME_CASES)
+def test_output_files_have_the_skeleton_of_the_reference_files(D, tmp_path, rel, name, kind):
+    """Every byte of the reference's own output files that is not a data value -- XML boilerplate, the list-directed WholeExtent / Origin /
+    Spacing numbers as gfortran printed them, block sizes, values per line, line lengths, the blank lines of jmod.txt and (for jmod.txt) the
+    coordinate columns themselves -- is reproduced by both writers.  The skeleton only depends on MOL + gimic.inp, so the benzene cases are
+    checkable although their densities are missing from the reference tree (tests/golden/file_frames.json, made by make_golden.py)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import file_frame
+    from gimic_b200 import writers
+    want = fixtures.golden_json("file_frames.json")[rel]
+    d = _workdir(tmp_path, name)
+    g = _py_grid(d)
+    ncomp = 1 if kind == "vti_scalar" else 3
+    v = np.zeros((g.n, ncomp)) if ncomp == 3 else np.zeros(g.n)
+    if kind == "vti_vector":
+        writers.write_vti_vector(str(d / "py.out"), g, v)
+    elif kind == "vti_scalar":
+        writers.write_vti_scalar(str(d / "py.out"), g, v)
+    else:
+        writers.write_jmod_txt(str(d / "py.out"), g, v, regular=True)
+    _write(D, d, kind, v, "nat.out")
+    assert filecmp.cmp(d / "py.out", d / "nat.out", shallow=False)
+    got = file_frame(str(d / "nat.out"), 33 if kind == "jmod_txt" else 0)
+    assert got["rle"] == want["rle"], [(a, b) for a, b in zip(got["rle"], want["rle"]) if a != b][:3]
+    if "coord_sha256" in want:
+        assert got["coord_sha256"] == want["coord_sha256"]
+
+
+def test_vtu_file_has_the_skeleton_of_the_reference_file(D, tmp_path):
+    """test/c4h4/read-grid/reference/jvec.vtu: boilerplate, NumberOfPoints / NumberOfCells field widths, the 3e20.10 Points block (hashed: the
+    coordinates come from gridfile.grd), connectivity / offsets / types / CellData line layouts for the reference's 23221 cells (stand-in
+    connectivity: the TetGen file is not shipped with the tests, its values do not change any line length)"""
+    import hashlib, sys
+    sys.path.insert(0, GOLD)
+    from make_golden import file_frame
+    from gimic_b200 import writers
+    want = fixtures.golden_json("file_frames.json")["c4h4/read-grid/reference/jvec.vtu"]
+    d = _workdir(tmp_path, "c4h4_read-grid")
+    np.savetxt(d / "gridfile.grd", fixtures.golden_npz("c4h4_readgrid.npz")["grid"], fmt="%.6f")
+    ncells = 23221
+    with open(d / "grid.1.ele", "w") as f:
+        f.write(f"{ncells}  4  0\n" + "".join(f"{c + 1:6d} {1 + c % 4000:6d} {2 + c % 4000:6d} {3 + c % 4000:6d} {4 + c % 4000:6d}\n" for c in range(ncells)))
+    g = _py_grid(d)
+    v = np.zeros((g.n, 3))
+    writers.write_vtu_vector(str(d / "py.vtu"), g.points(), v, writers.read_ele(str(d / "grid.1.ele")))
+    _write(D, d, "vtu_vector", v, "nat.vtu")
+    assert filecmp.cmp(d / "py.vtu", d / "nat.vtu", shallow=False)
+    got = file_frame(str(d / "nat.vtu"))
+    assert got["rle"] == want["rle"], [(a, b) for a, b in zip(got["rle"], want["rle"]) if a != b][:3]
+    h = hashlib.sha256()
+    for line in open(d / "nat.vtu").read().split("\n")[6:6 + 4110]:
+        h.update(line.encode() + b"\n")
+    assert h.hexdigest() == want["points_sha256"]
