@@ -81,6 +81,7 @@ class Run {
     std::vector<double> xyz;
     GridSpec grid;
     Vec3 magnet{{0, 0, 0}};
+    std::vector<std::string> magnet_log;            // what get_magnet prints every time it is called (magnet.f90:66-86)
     int summary[5] = {0, 0, 0, 0, 0};               // natoms, primitive GTOs, contracted GTOs, TURBOMOLE flag, spherical count (gimic_b200_mol_summary)
     std::map<int, Sums> results;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();   // stockas_klocka reports the times of the whole run
@@ -149,7 +150,7 @@ class Run {
             check(gimic_b200_atom_coords(ctx->h, xyz.data()));
         }
         grid = grid_from_input(inp, xyz, workdir);
-        magnet = get_magnet(grid, inp.str("magnet_axis"), inp.vec3("magnet"));
+        magnet = get_magnet(grid, inp.str("magnet_axis"), inp.vec3("magnet"), &magnet_log);
     }
 
     std::string path(const std::string &name) const { return (!name.empty() && name[0] == '/') ? name : join_path(workdir, name); }
@@ -160,9 +161,8 @@ class Run {
         what = 1 | (inp.flag("Essential.jmod") ? 2 : 0) | (inp.flag("Essential.acid") ? 4 : 0);
     }
 
-    void field_line() const {
-        out.say(sfmt("   Magnetic field <x,y,z> =%10.5f%10.5f%10.5f", magnet[0], magnet[1], magnet[2]));
-        out.say();
+    void field_line() const {                       // integrate_* call get_magnet again (integral.f90:85,225)
+        for (const std::string &line : magnet_log) out.raw(line + "\n");
     }
 
     void run(const std::map<int, Sums> *pre = nullptr) {
@@ -180,20 +180,26 @@ class Run {
         out.say(sfmt("        user:%9.2fsec", cpu[0] - cpu0[0]));
         out.say(sfmt("         sys:%9.2fsec", cpu[1] - cpu0[1]));
         out.say(std::string(70, '-'));
-        char date[64];
-        const std::time_t now = std::time(nullptr);
-        std::tm tmv;
-        localtime_r(&now, &tmv);
-        std::strftime(date, sizeof date, "%a %b %e %H:%M:%S %Y", &tmv);
-        out.say(date);
+        out.say(fdate());
         out.say("Hello World! (tm)");
         out.say();
         out.say("done.");
         out.say();
     }
 
+    static std::string fdate() {
+        char date[64];
+        const std::time_t now = std::time(nullptr);
+        std::tm tmv;
+        localtime_r(&now, &tmv);
+        std::strftime(date, sizeof date, "%a %b %e %H:%M:%S %Y", &tmv);
+        return date;
+    }
+
     void run_body(const std::map<int, Sums> *pre) {
-        // initialize(), gimic.F90:107-131 (its fdate() line is left out)
+        // initialize(), gimic.F90:107-131
+        out.say();
+        out.say(fdate());
         std::string title = inp.str("title");
         while (!title.empty() && std::isspace((unsigned char)title.front())) title.erase(title.begin());
         while (!title.empty() && std::isspace((unsigned char)title.back())) title.pop_back();

@@ -232,7 +232,7 @@ GridSpec file_grid(std::vector<double> xyz) {
 }
 
 // get_magnet + check_field, magnet.f90:11-86
-Vec3 get_magnet(const GridSpec &g, const std::string &magnet_axis, const Vec3 &magnet) {
+Vec3 get_magnet(const GridSpec &g, const std::string &magnet_axis, const Vec3 &magnet, std::vector<std::string> *log) {
     std::string axis = magnet_axis;
     while (!axis.empty() && std::isspace((unsigned char)axis.front())) axis.erase(axis.begin());
     while (!axis.empty() && std::isspace((unsigned char)axis.back())) axis.pop_back();
@@ -250,8 +250,20 @@ Vec3 get_magnet(const GridSpec &g, const std::string &magnet_axis, const Vec3 &m
         mag = magnet;
     }
     if (!any(mag)) throw DriverError("Magnetic field is zero, not wasting more CPU.");
-    if (!ortho && dot(g.basv[2], mag.data()) > 0.0)           // left handed coordinate system, reversing magnetic field
-        for (int c = 0; c < 3; ++c) mag[c] = -mag[c];
+    if (!ortho) {                                             // check_field, magnet.f90:66-86
+        const double x = dot(g.basv[2], mag.data());
+        if (x > 0.0) {
+            for (int c = 0; c < 3; ++c) mag[c] = -mag[c];
+            if (log) log->push_back(" INFO: Left handed coordinate system, reversing magnetic field");
+        }
+        if (log) {
+            if (std::fabs(x) - 1.0 > 1e-12 && std::fabs(x) > 1e-12) log->push_back(" WARNING: Magnetic field not orthogonal to grid");
+            char buf[96];
+            snprintf(buf, sizeof buf, "    Magnetic field <x,y,z> =%10.5f%10.5f%10.5f", mag[0], mag[1], mag[2]);
+            log->push_back(buf);
+            log->push_back("");
+        }
+    }
     return mag;
 }
 

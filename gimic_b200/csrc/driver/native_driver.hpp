@@ -101,7 +101,9 @@ GridSpec std_grid(const Vec3 &origin, const Vec3 &ivec, const Vec3 &jvec, const 
 GridSpec bond_grid(const Vec3 &c1, const Vec3 &c2, const Vec3 &fix, double distance, const std::array<double, 2> &height,
                    const std::array<double, 2> &width, const AxisOpts &o, bool has_radius, double radius, bool has_magnet, const Vec3 &magnet);
 GridSpec file_grid(std::vector<double> xyz);
-Vec3 get_magnet(const GridSpec &g, const std::string &magnet_axis, const Vec3 &magnet);
+// log (optional) receives what check_field prints (magnet.f90:66-86): nothing for the 'X' specifier, else the notes about a reversed /
+// non-orthogonal field and the 'Magnetic field <x,y,z>' line
+Vec3 get_magnet(const GridSpec &g, const std::string &magnet_axis, const Vec3 &magnet, std::vector<std::string> *log = nullptr);
 GridSpec grid_from_input(const Input &inp, const std::vector<double> &atom_coords, const std::string &workdir);
 std::vector<double> read_numbers(const std::string &path);   // whitespace-separated reals, '#' comments (np.loadtxt-like)
 

@@ -123,7 +123,8 @@ class Driver:
             self.symbols = self._symbols(path(I.get("basis")))
         self.summary = mol_summary(path(I.get("basis")))
         self.grid = grids.from_input(I, self.xyz, self.workdir)
-        self.magnet = grids.get_magnet(self.grid, I.get("magnet_axis"), I.get("magnet"))
+        self.magnet_log = []        # what get_magnet prints every time it is called (magnet.f90:66-86)
+        self.magnet = grids.get_magnet(self.grid, I.get("magnet_axis"), I.get("magnet"), self.magnet_log)
 
     @staticmethod
     def _symbols(mol):
@@ -155,7 +156,9 @@ class Driver:
 
     def _run(self, integral_results=None):
         I = self.inp
-        # initialize(), gimic.F90:107-131 (its fdate() line is left out)
+        # initialize(), gimic.F90:107-131
+        self.say()
+        self.say(time.strftime("%a %b %e %H:%M:%S %Y"))
         self.say((" TITLE: " + str(I.get("title")).strip()).rstrip())       # msg_out trims trailing blanks
         self.say()
         if not I.get("Advanced.GIAO"):
@@ -192,8 +195,7 @@ class Driver:
             writers.write_mol_xyz(os.path.join(self.workdir, "mol.xyz"), self.symbols, self.xyz)
             writers.write_grid_xyz(os.path.join(self.workdir, "grid.xyz"), self.grid, self.symbols, self.xyz)
         self.say("*** Grid plot in grid.xyz")
-        self.say("   Magnetic field <x,y,z> =" + "".join(f"{b:10.5f}" for b in self.magnet))
-        self.say()
+        self._field_lines()
         self.say("INFO: " + ("Open-shell calculation" if self.uhf else "Closed-shell calculation"))
         self.say()
         calc = I.get("calc")
@@ -232,6 +234,11 @@ class Driver:
         if self.rank != 0:
             return None
         return np.concatenate([gathered[r][: b - a].cpu().numpy() for r, (a, b) in enumerate(sizes)])
+
+    def _field_lines(self):
+        if self.rank == 0:
+            for line in self.magnet_log:
+                self.out.write(line + "\n")
 
     def _tensors(self, spincase):
         """calc_jtensors (jfield.f90:62-138): slab of the flat index per rank, gathered on rank 0"""
@@ -406,9 +413,7 @@ class Driver:
         self.results = res
         bar = "*" * 60
         bound = self.grid.radius
-        def field_line():
-            self.say("   Magnetic field <x,y,z> =" + "".join(f"{b:10.5f}" for b in self.magnet))
-            self.say()
+        field_line = self._field_lines            # integrate_* call get_magnet again (integral.f90:85,225)
         def block(lbl_au, lbl_si, x, p, n):
             self.say()
             self.say(bar)

@@ -190,8 +190,9 @@ def file_grid(xyz):
     return g
 
 
-def get_magnet(grid, magnet_axis="", magnet=(0.0, 0.0, 0.0)):
-    """get_magnet + check_field, magnet.f90:11-86"""
+def get_magnet(grid, magnet_axis="", magnet=(0.0, 0.0, 0.0), log=None):
+    """get_magnet + check_field, magnet.f90:11-86.  log (a list) receives what check_field prints: nothing for the 'X' (plane normal)
+    specifier, else the notes about a reversed / non-orthogonal field and the 'Magnetic field <x,y,z>' line"""
     axis = (magnet_axis or "").strip()
     ortho, d = False, 1.0
     if axis:
@@ -211,8 +212,17 @@ def get_magnet(grid, magnet_axis="", magnet=(0.0, 0.0, 0.0)):
     if not np.asarray(mag).any():
         raise ValueError("Magnetic field is zero, not wasting more CPU.")
     mag = np.array(mag, dtype=np.float64)
-    if not ortho and float(np.dot(grid.basv[2], mag)) > 0.0:   # left handed coordinate system, reversing magnetic field
-        mag = -mag
+    if not ortho:                                              # check_field, magnet.f90:66-86
+        x = float(np.dot(grid.basv[2], mag))
+        if x > 0.0:
+            mag = -mag
+            if log is not None:
+                log.append(" INFO: Left handed coordinate system, reversing magnetic field")
+        if log is not None:
+            if abs(x) - 1.0 > 1e-12 and abs(x) > 1e-12:
+                log.append(" WARNING: Magnetic field not orthogonal to grid")
+            log.append(" " + "   Magnetic field <x,y,z> =" + "".join(f"{b:10.5f}" for b in mag))
+            log.append("")
     return mag
 
 

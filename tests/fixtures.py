@@ -38,8 +38,8 @@ def strip_clock(text):
     import re
     if _CLOCK is None:
         _CLOCK = (re.compile(r"^( {4}wall time:| {9}user:| {10}sys:).*$", re.M),
-                  re.compile(r"^( -{70}\n) \w{3} \w{3} [ \d]\d \d\d:\d\d:\d\d \d{4}$", re.M))
-    return _CLOCK[1].sub(r"\1 <date>", _CLOCK[0].sub(r"\1", text))
+                  re.compile(r"^ \w{3} \w{3} [ \d]\d \d\d:\d\d:\d\d \d{4}$", re.M))
+    return _CLOCK[1].sub(" <date>", _CLOCK[0].sub(r"\1", text))
 
 
 def golden_npz(name):
