@@ -176,9 +176,9 @@ class Run {
         out.say("INFO: Deallocated basis set and atom data");
         out.say();
         out.say(std::string(70, '-'));
-        out.say(sfmt("   wall time:%9.2fsec", wall));
-        out.say(sfmt("        user:%9.2fsec", cpu[0] - cpu0[0]));
-        out.say(sfmt("         sys:%9.2fsec", cpu[1] - cpu0[1]));
+        out.say(sfmt("   wall time:%9.2fsec (%6.1f h )", wall, wall / 3600.0));
+        out.say(sfmt("        user:%9.2fsec (%6.1f h )", cpu[0] - cpu0[0], (cpu[0] - cpu0[0]) / 3600.0));
+        out.say(sfmt("         sys:%9.2fsec (%6.1f h )", cpu[1] - cpu0[1], (cpu[1] - cpu0[1]) / 3600.0));
         out.say(std::string(70, '-'));
         out.say(fdate());
         out.say("Hello World! (tm)");
@@ -351,7 +351,7 @@ class Run {
                 check(gimic_b200_fields_from_tensors(ctx->h, n, r.data(), tens.data(), magnet.data(), jv.data(), want_jmod ? jmod.data() : nullptr,
                                                      want_acid ? acid.data() : nullptr, 0));
             }
-            out.raw(" magnetic field\n " + ld_real(magnet[0]) + ld_real(magnet[1]) + ld_real(magnet[2]) + "\n \n");
+            out.raw(" magnetic field\n" + ld_real(magnet[0]) + ld_real(magnet[1]) + ld_real(magnet[2]) + "\n \n");
             const bool regular = grid.mode == "std" || grid.mode == "base" || grid.mode == "bond";
             if (grid.gauss && !grid.is_file())
                 write_jmod_txt(join_path(workdir, "jmod" + tag + ".txt"), grid, jv, regular && (grid.mode == "bond" || grid.gtype == "even"));
@@ -426,8 +426,9 @@ class Run {
                 write_vtu(join_path(workdir, names[(size_t)q]), grd, "scalars", 1, col, cells);
             }
         };
-        auto table = [&](const std::vector<std::array<double, 3>> &contrib) {
-            out.raw("  \n atom contributions, total, positive, negative\n");
+        // write(*,*) " " before the shielding tables, write(*,*) "" before the chi table (jfield.f90:762,890)
+        auto table = [&](const std::vector<std::array<double, 3>> &contrib, const char *lead) {
+            out.raw(std::string(lead) + "\n atom contributions, total, positive, negative\n");
             double cs[3] = {0, 0, 0};
             for (size_t l = 0; l < contrib.size(); ++l) {
                 out.pf("atom %5zu%14.6f%14.6f%14.6f\n", l + 1, contrib[l][0], contrib[l][1], contrib[l][2]);
@@ -439,14 +440,14 @@ class Run {
         out.pf(" npts%12ld\n", n);
         for (int k = 0; k < nat; ++k) {
             const Res &R = res[(size_t)k];
-            out.pf(" atom %11d\n in ppm\n", k + 1);
+            out.pf(" atom %12d\n in ppm\n", k + 1);
             const char *lbl[3] = {"sigma_xx ", "sigma_yy ", "sigma_zz "};
             for (int q = 0; q < 3; ++q) out.pf(" %10s  %14.6f\n", lbl[q], R.xyz[q]);
             out.pf("%30s  %14.6f\n", "shielding constant    = ", R.iso);
             out.pf("%30s  %14.6f\n", "positive contribution = ", R.pos);
             out.pf("%30s  %14.6f\n", "negative contribution = ", R.neg);
             out.pf("%30s  %14.6f\n", "sum = ", R.pos + R.neg);
-            table(R.atoms);
+            table(R.atoms, "  ");
             if (have_cells) {
                 const std::string id = std::to_string(k + 1);
                 const std::vector<std::string> names = {"sigma" + id + ".vtu", "sigma_xx" + id + ".vtu", "sigma_yy" + id + ".vtu", "sigma_zz" + id + ".vtu"};
@@ -459,9 +460,11 @@ class Run {
         const char *clbl[3] = {"chi_xx ", "chi_yy ", "chi_zz "};
         for (int q = 0; q < 3; ++q) out.pf(" %7s  %14.8f\n", clbl[q], X.xyz[q]);
         out.raw(" in au\n");
-        out.pf(" %30s  %14.6f\n", "isotropic magnetizability chi = ", X.iso);
-        out.pf(" %30s  %14.6f\n", "positive contribution         = ", X.pos);
-        out.pf(" %30s  %14.6f\n", "negative contribution         = ", X.neg);
+        // (X,A30,2X,F14.6) with 32-character labels, jfield.f90:876-878: the A30 edit descriptor keeps the leftmost 30 characters, so the
+        // reference prints these three lines without their '= ' (test/benzene/magnetizability/reference/stdout)
+        out.pf(" %30.30s  %14.6f\n", "isotropic magnetizability chi = ", X.iso);
+        out.pf(" %30.30s  %14.6f\n", "positive contribution         = ", X.pos);
+        out.pf(" %30.30s  %14.6f\n", "negative contribution         = ", X.neg);
         out.pf(" %30s  %14.6f\n \n", "sum ", X.pos + X.neg);
         const double fac = 7.89104e-29;                               // fac_au2simag, jfield.f90:606
         out.raw(" in SI units J/T^2 \n conversion factor: 7.89104*10^-29 J/T^2 \n \n");
@@ -469,7 +472,7 @@ class Run {
                                                        {"negative contribution     = ", X.neg}, {"sum ", X.pos + X.neg}};
         for (const auto &p : si) out.pf("%30s  %s\n", p.first, fortran_e(p.second * fac, 14, 6).c_str());
         out.raw(" ****************************************************\n");
-        table(X.atoms);
+        table(X.atoms, " ");
         if (have_cells) plot_integrands(nullptr, {"intchi.vtu", "intchi_xx.vtu", "intchi_yy.vtu", "intchi_zz.vtu"});
     }
 

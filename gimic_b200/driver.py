@@ -144,9 +144,9 @@ class Driver:
         self.say("INFO: Deallocated basis set and atom data")
         self.say()
         self.say("-" * 70)
-        self.say(f"   wall time:{time.perf_counter() - self._t0:9.2f}sec")
-        self.say(f"        user:{cpu.user - self._cpu0.user:9.2f}sec")
-        self.say(f"         sys:{cpu.system - self._cpu0.system:9.2f}sec")
+        for label, t in (("   wall time:", time.perf_counter() - self._t0), ("        user:", cpu.user - self._cpu0.user),
+                         ("         sys:", cpu.system - self._cpu0.system)):
+            self.say(f"{label}{t:9.2f}sec ({t / 3600.0:6.1f} h )")
         self.say("-" * 70)
         self.say(time.strftime("%a %b %e %H:%M:%S %Y"))
         self.say("Hello World! (tm)")
@@ -304,7 +304,7 @@ class Driver:
                     continue
                 r = grid.points()
                 f = self.g.fields_from_tensors(r, tens, self.magnet, jvec=True, jmod=want_jmod, acid=want_acid)
-            self.out.write(" magnetic field\n " + "".join(writers._ld_real(b) for b in self.magnet) + "\n \n")
+            self.out.write(" magnetic field\n" + "".join(writers._ld_real(b) for b in self.magnet) + "\n \n")   # print *, magnet
             jv = f["jvec"]
             regular = grid.mode in ("std", "base", "bond")
             if grid.gauss and grid.mode != "file":
@@ -351,8 +351,8 @@ class Driver:
             for col, name in zip((3, 0, 1, 2), names):
                 writers.write_vtu_scalar(os.path.join(wd, name), grd, f4[:, col], cells)
         w(f" npts{grd.shape[0]:12d}\n")
-        def table(contrib):
-            w("  \n atom contributions, total, positive, negative\n")
+        def table(contrib, lead="  "):       # write(*,*) " " before the shielding tables, write(*,*) "" before the chi table (jfield.f90:762,890)
+            w(lead + "\n atom contributions, total, positive, negative\n")
             for l, c in enumerate(contrib):
                 w(f"atom {l + 1:5d}{c[0]:14.6f}{c[1]:14.6f}{c[2]:14.6f}\n")
             cs = contrib.sum(0)
@@ -360,7 +360,7 @@ class Driver:
             w(" ****************************************************\n")
         for k in range(coord.shape[0]):
             sg = res["sigma"][k]
-            w(f" atom {k + 1:11d}\n in ppm\n")
+            w(f" atom {k + 1:12d}\n in ppm\n")
             for lbl, v in zip(("sigma_xx ", "sigma_yy ", "sigma_zz "), sg):
                 w(f" {lbl:>10s}  {v:14.6f}\n")
             w(f"{'shielding constant    = ':>30s}  {res['sigma_iso'][k]:14.6f}\n")
@@ -377,9 +377,11 @@ class Driver:
         for lbl, v in zip(("chi_xx ", "chi_yy ", "chi_zz "), res["chi"]):
             w(f" {lbl:>7s}  {v:14.8f}\n")
         w(" in au\n")
-        w(f" {'isotropic magnetizability chi = ':>30s}  {res['chi_iso']:14.6f}\n")
-        w(f" {'positive contribution         = ':>30s}  {res['chi_pos']:14.6f}\n")
-        w(f" {'negative contribution         = ':>30s}  {res['chi_neg']:14.6f}\n")
+        # (X,A30,2X,F14.6) with 32-character labels, jfield.f90:876-878: the A30 edit descriptor keeps the leftmost 30 characters, so the
+        # reference prints these three lines without their '= ' (test/benzene/magnetizability/reference/stdout)
+        w(f" {'isotropic magnetizability chi = '[:30]:>30s}  {res['chi_iso']:14.6f}\n")
+        w(f" {'positive contribution         = '[:30]:>30s}  {res['chi_pos']:14.6f}\n")
+        w(f" {'negative contribution         = '[:30]:>30s}  {res['chi_neg']:14.6f}\n")
         w(f" {'sum ':>30s}  {res['chi_pos'] + res['chi_neg']:14.6f}\n \n")
         fac = 7.89104e-29                                   # fac_au2simag, jfield.f90:606
         w(" in SI units J/T^2 \n conversion factor: 7.89104*10^-29 J/T^2 \n \n")
@@ -387,7 +389,7 @@ class Driver:
                        ("negative contribution     = ", res["chi_neg"]), ("sum ", res["chi_pos"] + res["chi_neg"])):
             w(f"{lbl:>30s}  {writers.fortran_e(v * fac, 14, 6)}\n")
         w(" ****************************************************\n")
-        table(res["chi_atoms"])
+        table(res["chi_atoms"], " ")
         if cells is not None:
             plot_integrands(None, ["intchi.vtu", "intchi_xx.vtu", "intchi_yy.vtu", "intchi_zz.vtu"])
 

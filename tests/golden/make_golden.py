@@ -144,7 +144,8 @@ def main():
 
     # the reports themselves from two lines above 'TITLE:' on (i.e. without the program banner), for line-by-line comparison
     for src, dst in (("c4h4/integration/reference/stdout", "c4h4_integration_stdout.txt"),
-                     ("open-shell/integration/reference/stdout", "open_shell_integration_stdout.txt")):
+                     ("open-shell/integration/reference/stdout", "open_shell_integration_stdout.txt"),
+                     ("benzene/magnetizability/reference/stdout", "benzene_magnetizability_stdout.txt")):
         lines = open(os.path.join(t, src), encoding="utf-8", errors="replace").read().split("\n")
         k = next(i for i, l in enumerate(lines) if l.strip().startswith("TITLE:"))
         open(os.path.join(OUT, dst), "w").write("\n".join(lines[k - 2:]))

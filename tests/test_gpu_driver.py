@@ -142,7 +142,7 @@ def test_property_mode_report(tmp_path, cases):
     m = re.findall(r"shielding constant    =\s+([-\d.]+)", got)
     assert len(m) == xyz.shape[0]
     assert np.allclose([float(x) for x in m], tot[:-1, 0:3].sum(1) / 3.0, atol=1.1e-6)
-    chi = re.search(r"isotropic magnetizability chi =\s+([-\d.]+)", got)
+    chi = re.search(r"isotropic magnetizability chi\s+([-\d.]+)", got)
     assert abs(float(chi.group(1)) - tot[-1, 0:3].sum() / 3.0) < 1.1e-6
     assert "atom contributions, total, positive, negative" in got and "in SI units J/T^2" in got
     # integrand plots sigma<k>.vtu, sigma_{xx,yy,zz}<k>.vtu, intchi*.vtu (jfield.f90:786-808, 915-918) vs the formula on oracle tensors
@@ -233,7 +233,7 @@ def test_every_benzene_reference_input_runs_and_matches_the_oracle(tmp_path, cas
         tot, _ = O.property(r2, w2, o.ctensor(r2), c2, counts)
         m = re.findall(r"shielding constant    =\s+([-\d.]+)", out.getvalue())
         assert len(m) == coords.shape[0] and np.allclose([float(x) for x in m], tot[:-1, 0:3].sum(1) / 3.0, atol=1.1e-6)
-        chi = re.search(r"isotropic magnetizability chi =\s+([-\d.]+)", out.getvalue())
+        chi = re.search(r"isotropic magnetizability chi\s+([-\d.]+)", out.getvalue())
         assert abs(float(chi.group(1)) - tot[-1, 0:3].sum() / 3.0) < 1.1e-6
         return
     og = _oracle_grid(I, coords)

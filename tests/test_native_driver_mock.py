@@ -362,3 +362,37 @@ def test_whole_report_equals_the_reference_stdout_line_by_line(mock_dir, tmp_pat
         for p, q in zip(num.findall(x), num.findall(y)):
             unit = 10.0 ** -len(q.split(".")[1]) if "." in q and "E" not in q.upper() else (0.0 if "." not in q else 1e-4 * abs(float(q)))
             assert abs(float(p) - float(q)) <= 1.01 * unit, (k, x, y)
+
+
+def test_property_report_has_the_layout_of_the_reference_stdout(mock_dir, tmp_path, cases):
+    """test/benzene/magnetizability/reference/stdout (cdens on a Grid(file) with prop=on: shieldings of 12 nuclei, magnetizability, per-atom
+    contribution tables, SI block).  Its XDENS and NumGrid files are missing from the reference tree, so the numbers here come from synthetic
+    densities on a stand-in point set -- but every format is fixed-width: the report must have the same lines in the same order, the same
+    text, and the same LENGTH line by line.  Not printed here: the 'Estimated CPU time for single core calculation' note of calc_jtensors."""
+    from gimic_b200.driver import read_mol_geometry
+    xd = tmp_path / "XDENS"
+    fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))
+
+    def prop_files(d):
+        _, coords = read_mol_geometry(str(d / "MOL"))
+        rng = np.random.default_rng(5)
+        counts = rng.integers(6, 12, size=coords.shape[0])
+        pts = np.vstack([coords[a] + rng.normal(scale=1.5, size=(c, 3)) for a, c in enumerate(counts)])
+        np.savetxt(d / "gridfile.grd", pts, fmt="%.10f"); np.savetxt(d / "grid_w.grd", rng.uniform(0, 0.1, size=pts.shape[0]), fmt="%.12e")
+        shutil.copy(os.path.join(GOLD, "benzene_coord.au"), d / "coord.au")
+        np.savetxt(d / "nelpts.info", np.column_stack([np.arange(1, len(counts) + 1), counts]), fmt="%d")
+    dn, _ = _pair(tmp_path, "benzene_magnetizability", cases["benzene_mol"], xd, extra=prop_files)
+    ours = _native(mock_dir, [dn / "gimic.inp"]).split("\n")
+    gold = fixtures.strip_clock(open(os.path.join(GOLD, "benzene_magnetizability_stdout.txt")).read()).split("\n")
+    k = next(i for i, l in enumerate(gold) if "Estimated CPU time" in l)
+    del gold[k:k + 2]
+    gold = [l for l in gold if l != "This is F-GIMIC."]
+    while gold and gold[-1] == "":
+        gold.pop()
+    while ours and ours[-1] == "":
+        ours.pop()
+    assert len(ours) == len(gold), (len(ours), len(gold))
+    num = re.compile(r"[-+]?\d+\.\d+(?:[EeDd][-+]?\d+)?|[-+]?\d+")
+    for k, (x, y) in enumerate(zip(ours, gold)):
+        assert num.sub("#", x).split() == num.sub("#", y).split(), (k, x, y)
+        assert len(x) == len(y), (k, x, y)
