@@ -521,7 +521,11 @@ class Run {
         auto one = [&](int sc, int off, const char *lbl_au, const char *lbl_si) {
             note_spin(sc);
             field_line();
-            if (bound < 1.0e10) out.say(" Integration bound set to radius " + py_repr(bound));
+            if (bound < 1.0e10) {                   // write(str_g, *) 'Integration bound set to radius ', bound (integral.f90:93,231); msg_out trims
+                std::string v = ld_real(bound);
+                while (!v.empty() && v.back() == ' ') v.pop_back();
+                out.say(" Integration bound set to radius " + v);
+            }
             const Sums &s = results.at(sc);
             block(lbl_au, lbl_si, s[off], s[off + 1], s[off + 2]);
         };
@@ -530,7 +534,7 @@ class Run {
             for (int sc : cases) one(sc, 3, "Induced mod current (au)   :", "Induced mod current (nA/T) :");
             out.say();
         } else {
-            out.raw("  Jmod integration skipped.\n");
+            out.raw(" Jmod integration skipped.\n");              // write(*,*) "...", gimic.F90:242
         }
         out.say("*** Integrating current");
         for (int sc : cases) one(sc, 0, "   Induced current (au)    :", "   Induced current (nA/T)  :");
@@ -545,6 +549,7 @@ class Run {
             out.say();
             out.say(bar);
             out.say();
+            out.say();                              // call nl after integrate_acid, gimic.F90:257
         }
     }
 

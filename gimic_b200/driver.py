@@ -433,17 +433,17 @@ class Driver:
                 self._note_spin(sc)
                 field_line()
                 if bound < 1.0e10:
-                    self.say(f" Integration bound set to radius {bound}")
+                    self.say(" Integration bound set to radius " + writers._ld_real(bound).rstrip())   # write(str_g, *) ..., bound (integral.f90:93,231)
                 block("Induced mod current (au)   :", "Induced mod current (nA/T) :", *res[sc][3:6])
             self.say()
         else:
-            self.out.write("  Jmod integration skipped.\n")
+            self.out.write(" Jmod integration skipped.\n")          # write(*,*) "...", gimic.F90:242
         self.say("*** Integrating current")
         for sc in cases:
             self._note_spin(sc)
             field_line()
             if bound < 1.0e10:
-                self.say(f" Integration bound set to radius {bound}")
+                self.say(" Integration bound set to radius " + writers._ld_real(bound).rstrip())   # write(str_g, *) ..., bound (integral.f90:93,231)
             block("   Induced current (au)    :", "   Induced current (nA/T)  :", *res[sc][0:3])
         self.say()
         if I.get("Essential.acid"):
@@ -456,6 +456,7 @@ class Driver:
             self.say()
             self.say(bar)
             self.say()
+            self.say()                          # call nl after integrate_acid, gimic.F90:257
 
     def run_scalar(self, calc):
         """edens / divj: whitelisted by the reference front-end (src/gimic.in:267) but not implemented at this commit.

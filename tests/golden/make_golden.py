@@ -143,12 +143,14 @@ def main():
               open(os.path.join(OUT, "open_shell_integration.json"), "w"), indent=1)
 
     # the reports themselves from two lines above 'TITLE:' on (i.e. without the program banner), for line-by-line comparison
-    for src, dst in (("c4h4/integration/reference/stdout", "c4h4_integration_stdout.txt"),
-                     ("open-shell/integration/reference/stdout", "open_shell_integration_stdout.txt"),
-                     ("benzene/magnetizability/reference/stdout", "benzene_magnetizability_stdout.txt")):
-        lines = open(os.path.join(t, src), encoding="utf-8", errors="replace").read().split("\n")
+    os.makedirs(os.path.join(OUT, "stdout"), exist_ok=True)
+    reports = [("c4h4/integration", "c4h4_integration"), ("open-shell/integration", "open-shell_integration")]
+    reports += [("benzene/" + n, "benzene_" + n) for n in sorted(os.listdir(os.path.join(t, "benzene")))
+                if os.path.exists(os.path.join(t, "benzene", n, "reference", "stdout"))]
+    for src, dst in reports:
+        lines = open(os.path.join(t, src, "reference", "stdout"), encoding="utf-8", errors="replace").read().split("\n")
         k = next(i for i, l in enumerate(lines) if l.strip().startswith("TITLE:"))
-        open(os.path.join(OUT, dst), "w").write("\n".join(lines[k - 2:]))
+        open(os.path.join(OUT, "stdout", dst + ".txt"), "w").write("\n".join(lines[k - 2:]))
 
     d = {}
     n = 33 ** 3
