@@ -322,8 +322,9 @@ void write_mol_xyz(const std::string &path, const std::vector<std::string> &symb
 void write_grid_xyz(const std::string &path, const GridSpec &g, const std::vector<std::string> &symbols, const std::vector<double> &coords) {
     const int p1 = g.npts[0], p2 = g.npts[1], p3 = g.npts[2];
     std::vector<Vec3> corners;
-    if (g.is_file()) {
-    } else if (p3 > 1) {
+    // file grids take the p3 == 1 branch like every grid with npts = (n, 1, 1): gridpoint(i,j,k) = xdata(:,i), so the four 'X' lines are the
+    // first and the last point twice, and the count line says natoms+5 although no 'Be' line follows (no case for 'file', grid.f90:660-667)
+    if (p3 > 1) {
         const int idx[8][3] = {{0, 0, 0}, {p1 - 1, 0, 0}, {0, p2 - 1, 0}, {0, 0, p3 - 1}, {p1 - 1, p2 - 1, 0}, {p1 - 1, 0, p3 - 1},
                                {0, p2 - 1, p3 - 1}, {p1 - 1, p2 - 1, p3 - 1}};
         for (auto &i : idx) corners.push_back(g.gridpoint(i[0], i[1], i[2]));

@@ -267,9 +267,9 @@ def write_mol_xyz(path, symbols, coords):
 def write_grid_xyz(path, grid, symbols, coords):
     """plot_grid_xyz, grid.f90:586-672: atoms + grid corners ('X') + field-direction marker ('Be')"""
     p1, p2, p3 = grid.npts
-    if grid.mode == "file":
-        corners = []
-    elif p3 > 1:
+    # file grids take the p3 == 1 branch like every grid with npts = (n, 1, 1): gridpoint(i,j,k) = xdata(:,i), so the four 'X' lines are the
+    # first and the last point twice, and the count line says natoms+5 although no 'Be' line follows (no case for 'file', grid.f90:660-667)
+    if p3 > 1:
         idx = [(0, 0, 0), (p1 - 1, 0, 0), (0, p2 - 1, 0), (0, 0, p3 - 1), (p1 - 1, p2 - 1, 0), (p1 - 1, 0, p3 - 1), (0, p2 - 1, p3 - 1),
                (p1 - 1, p2 - 1, p3 - 1)]
         corners = [grid.gridpoint(*i) for i in idx]
