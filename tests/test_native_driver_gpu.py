@@ -85,7 +85,8 @@ def _run_both(dn, dp, args=()):
     assert sorted(os.listdir(dn)) == sorted(os.listdir(dp))
     for f in sorted(os.listdir(dn)):
         if not filecmp.cmp(dn / f, dp / f, shallow=False):
-            _same_text(fixtures.strip_clock(open(dn / f, errors="replace").read()), fixtures.strip_clock(open(dp / f, errors="replace").read()), f)
+            _same_text(fixtures.strip_clock(open(dn / f, errors="replace").read()), fixtures.strip_clock(open(dp / f, errors="replace").read()), f,
+                       floor_rel=1e-9)
     return p.stdout
 
 
