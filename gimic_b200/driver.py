@@ -546,6 +546,37 @@ def _context_key_of(inpfile):
             bool(I.get("Advanced.screening")), float(I.get("Advanced.screening_thrs")), bool(I.get("Advanced.spherical")))
 
 
+def run_native(infiles, workdir=None, dryrun=False, vtk_appended=False, title=None, device=-1, devices=None, report=None):
+    """The same run through the compiled driver (include/gimic_b200_driver.h): gimic_b200_run for one input, gimic_b200_run_scan for several.
+    Returns 0; raises RuntimeError with the driver's message otherwise."""
+    import ctypes as C
+    from . import _lib
+    _lib.lib()                                                   # libgimic_b200.so first (RTLD_GLOBAL): the driver links against it
+    D = C.CDLL(os.path.join(os.path.dirname(_lib.SO_PATH), "libgimic_b200_driver.so"))
+    D.gimic_b200_driver_last_error.restype = C.c_char_p
+
+    class RunOpts(C.Structure):
+        _fields_ = [("flags", C.c_int), ("device", C.c_int), ("ndevices", C.c_int), ("devices", C.POINTER(C.c_int)), ("workdir", C.c_char_p),
+                    ("title", C.c_char_p), ("report_path", C.c_char_p)]
+    flags = (1 if dryrun else 0) | (2 if vtk_appended else 0)
+    infiles = [infiles] if isinstance(infiles, str) else list(infiles)
+    if len(infiles) > 1:
+        arr = (C.c_char_p * len(infiles))(*[os.fsencode(f) for f in infiles])
+        D.gimic_b200_run_scan.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int]
+        rc = D.gimic_b200_run_scan(len(infiles), arr, int(device), flags)
+    else:
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        o = RunOpts(flags=flags, device=int(device), ndevices=len(devices) if devices else 0, devices=devs,
+                    workdir=os.fsencode(workdir) if workdir else None, title=title.encode() if title else None,
+                    report_path=os.fsencode(report) if report else None)
+        D.gimic_b200_run.argtypes = [C.c_char_p, C.POINTER(RunOpts)]
+        sys.stdout.flush()
+        rc = D.gimic_b200_run(os.fsencode(infiles[0]), C.byref(o))
+    if rc != 0:
+        raise RuntimeError(f"gimic_b200 driver error {rc}: " + D.gimic_b200_driver_last_error().decode(errors="replace"))
+    return 0
+
+
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(prog="gimic_b200", description="GIMIC grid hot path on B200 (cdens / integral / edens / divj)")
@@ -563,7 +594,10 @@ def main(argv=None):
     ap.add_argument("-d", "--debug", type=int, default=None, help="debug level (label only)")
     ap.add_argument("-o", "--output", default=None, help="base name for output file(s) (unused, like in the reference's fgimic backend)")
     ap.add_argument("-b", "--backend", default="fgimic", choices=["fgimic", "gimic"], help="only the fgimic path is provided")
+    ap.add_argument("--native", action="store_true", help="hand the run to the compiled driver (libgimic_b200_driver.so, the code behind gimic-b200)")
     a = ap.parse_args(argv)
+    if a.native:
+        return run_native(a.infile, workdir=a.workdir, dryrun=a.dryrun, vtk_appended=(a.vtk == "appended"), title=a.title)
     if len(a.infile) > 1:
         run_scan(a.infile)
         return 0

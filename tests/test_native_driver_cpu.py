@@ -470,3 +470,16 @@ def test_vtu_file_has_the_skeleton_of_the_reference_file(D, tmp_path):
     for line in open(d / "nat.vtu").read().split("\n")[6:6 + 4110]:
         h.update(line.encode() + b"\n")
     assert h.hexdigest() == want["points_sha256"]
+
+
+def test_python_entry_can_hand_the_run_to_the_compiled_driver(D, tmp_path):
+    """python -m gimic_b200 --native: the same report file and grid.xyz as the Python driver (dry run here; no GPU needed)"""
+    from gimic_b200 import driver
+    d1, d2 = _workdir(tmp_path / "a", "benzene_keyword-rotation"), _workdir(tmp_path / "b", "benzene_keyword-rotation")
+    assert driver.run_native(str(d1 / "gimic.inp"), dryrun=True, title="handed over", report=str(tmp_path / "native.txt")) == 0
+    out = io.StringIO()
+    driver.Driver(str(d2 / "gimic.inp"), out=out, dryrun=True, title="handed over").run()
+    assert fixtures.strip_clock((tmp_path / "native.txt").read_text()) == fixtures.strip_clock(out.getvalue())
+    assert filecmp.cmp(d1 / "grid.xyz", d2 / "grid.xyz", shallow=False)
+    with pytest.raises(RuntimeError, match="cannot open input file"):
+        driver.run_native(str(tmp_path / "missing.inp"), dryrun=True)
