@@ -63,7 +63,25 @@ class Grid:
         return np.ascontiguousarray(np.transpose(r, (2, 1, 0, 3)).reshape(-1, 3))  # i fastest
 
 
-class Gimic:
+class NotAvailable(NotImplementedError):
+    """pygimic.gimic_exceptions.NotAvailable: what the generic connector raises for an operation a backend does not provide"""
+
+
+class GimicConnector:
+    """The backend interface pygimic programs against (src/pygimic/connector.pyx:9-17, connector.pxd:6-9): jvector(r), jtensor(r),
+    set_property(name, value).  `Gimic` below is the B200 backend of it."""
+
+    def jvector(self, r):
+        raise NotAvailable("jvector()")
+
+    def jtensor(self, r):
+        raise NotAvailable("jtensor()")
+
+    def set_property(self, prop, val):
+        pass
+
+
+class Gimic(GimicConnector):
     def __init__(self, mol=None, xdens=None, *, uhf=False, giao=True, diamag=True, paramag=True, screening=True,
                  screening_thrs=1e-6, device=-1, spherical=False, _handle=None):
         L = _lib.lib()

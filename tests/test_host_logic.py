@@ -113,3 +113,18 @@ def test_bench_reference_arm_json_contract():
     if not torch.cuda.is_available():
         p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--natoms", "6", "--grid", "16"], capture_output=True, text=True)
         assert p.returncode != 0 and "no CPU path" in p.stdout
+
+
+def test_gimic_is_a_backend_of_the_generic_connector():
+    """src/pygimic/connector.pyx: the generic backend interface (jvector / jtensor / set_property); Gimic implements it"""
+    import gimic_b200
+    c = gimic_b200.GimicConnector()
+    for call in (lambda: c.jvector((0, 0, 0)), lambda: c.jtensor((0, 0, 0))):
+        try:
+            call(); raise AssertionError("the generic connector must refuse")
+        except gimic_b200.NotAvailable:
+            pass
+    assert c.set_property("magnet", [0, 0, 1]) is None
+    assert issubclass(gimic_b200.Gimic, gimic_b200.GimicConnector)
+    for m in ("jvector", "jtensor", "set_property"):
+        assert getattr(gimic_b200.Gimic, m) is not getattr(gimic_b200.GimicConnector, m)
