@@ -178,3 +178,43 @@ int main(void) {
     po, wo = O.gauss_points(0.0, 2.0, 18, 9)
     assert out[0] == "9" and out[1] == "1" and abs(float(out[2]) - po[0]) < 1e-14 and abs(float(out[3]) - wo[17]) < 1e-14
     assert float(out[4]) == -1.0            # d shell, m = 0 row: 2zz - xx - yy -> coefficient of xx
+
+
+def test_cpp_wrapper_mirrors_gimicinterface(L, tmp_path, cases):
+    """include/GimicB200Interface.h: the method set of the reference's GimicInterface (GimicInterface.h:4-15) over the handle API; compiles as
+    strict C++11, links, and -- in a container without a GPU -- construction fails loudly with the library's message (no CPU fallback)"""
+    import subprocess
+    import torch
+    from gimic_b200 import _lib
+    src = tmp_path / "caller.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <exception>
+#include "GimicB200Interface.h"
+int main(int argc, char **argv) {
+    try {
+        GimicB200Interface g(argv[1], argv[2]);
+        const double b[3] = {0.0, 0.0, 1.0}, r[6] = {0.1, 0.2, 0.3, 1.0, -0.5, 0.25};
+        double jt[9], jv[3], jvs[6], mj;
+        g.set_magnet(b); g.set_spin("total");
+        g.calc_jtensor(r, jt); g.calc_jvector(r, jv); g.calc_modj(r, &mj); g.calc_jvectors(2, r, jvs);
+        double want = 0.0;
+        for (int m = 0; m < 3; ++m) want += (jt[m + 6] - jv[m]) * (jt[m + 6] - jv[m]) + (jvs[m] - jv[m]) * (jvs[m] - jv[m]);   // J = T.B, B = e_z
+        std::printf("ok nbf=%d natoms=%d consistent=%d modj=%.12e\n", g.nbf(), g.natoms(), want < 1e-18 * mj * mj || want < 1e-22, mj);   /* tensor path vs J path: 1e-10 relative / 1e-12 absolute per component */
+        try { g.set_spin("sideways"); } catch (const std::invalid_argument &e) { std::printf("spin refused\n"); }
+    } catch (const std::exception &e) {
+        std::printf("refused: %s\n", e.what());
+    }
+    (void)argc;
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libgimic_b200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe), cases["c4h4"]["mol"], cases["c4h4"]["xdens"]], text=True)
+    if torch.cuda.is_available():
+        assert out.startswith("ok nbf=168 natoms=8 consistent=1") and "spin refused" in out, out
+    else:
+        assert out.startswith("refused: gimic_b200: no CUDA device available"), out
