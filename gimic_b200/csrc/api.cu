@@ -196,6 +196,7 @@ int init_device(gimic_b200_ctx *c) {
 
 int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
     const bool uhf = c->opts.uhf != 0;
+    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
     if (!uhf) {
         if (spincase == GIMIC_B200_BETA) return fail(GIMIC_B200_ESPIN, "ctensor(): beta current requested, but not open-shell system!");
         if (spincase == GIMIC_B200_SPINDENS) return fail(GIMIC_B200_ESPIN, "ctensor(): spindens requested, but not open-shell system!");
@@ -223,6 +224,7 @@ int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
 // sum_b B_b P_b (jfield.f90:167-184 applied before instead of after the contraction).  Rebuilt when B changes.
 int get_operand_j(gimic_b200_ctx *c, int spincase, const double *B3, const double **op) {
     const bool uhf = c->opts.uhf != 0;
+    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
     if (!uhf) {
         if (spincase == GIMIC_B200_BETA) return fail(GIMIC_B200_ESPIN, "ctensor(): beta current requested, but not open-shell system!");
         if (spincase == GIMIC_B200_SPINDENS) return fail(GIMIC_B200_ESPIN, "ctensor(): spindens requested, but not open-shell system!");
