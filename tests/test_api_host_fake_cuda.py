@@ -37,3 +37,69 @@ def test_every_entry_point_runs_on_the_fake_cuda_runtime(tmp_path, cases):
     q = subprocess.run([str(exe), cases["c4h4"]["mol"], cases["c4h4"]["xdens"], cases["open_shell"]["mol"], cases["open_shell"]["xdens"]],
                        capture_output=True, text=True, timeout=300, env=dict(env, FAKE_CUDA_NO_DEVICE="1"))
     assert q.returncode == 3 and "create refused: no CUDA device available" in q.stdout
+
+
+WRAPPER_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import gimic_b200, fixtures
+from gimic_b200 import grids
+mol, xd, molu, xdu = sys.argv[1:5]
+g = gimic_b200.Gimic(mol, xd, screening_thrs=1e-8)
+assert (g.nbf, g.natoms, g.uhf) == (168, 8, False)
+r = np.random.default_rng(0).normal(size=(1000, 3))
+g.set_profiling(True)
+t = g.jtensors(r)
+st = g.stats()
+assert t.shape == (1000, 9) and st["n_points"] == 1000 and st["n_tiles"] >= 8 and "useful_flops" in st and st["launches"] > 0
+f = g.fields(r, [0, 0, 1.0], "total", tens=True, jvec=True, jmod=True, acid=True, edens=True, divj=True)
+assert {{k: v.shape for k, v in f.items()}} == dict(tens=(1000, 9), jvec=(1000, 3), jmod=(1000,), acid=(1000,), edens=(1000,), divj=(1000,))
+assert g.fields(r, [0, 0, 1.0], jvec=True, jmod=True)["jvec"].shape == (1000, 3)                     # J path
+assert g.fields_from_tensors(r, t, [0, 0, 1.0], jvec=True, jmod=True, acid=True)["acid"].shape == (1000,)
+bf, dr = g.basis(r[:5])
+assert bf.shape == (5, 168) and dr.shape == (5, 3, 168) and g.jmod_from_jvec(r, f["jvec"], [0, 0, 1.0]).shape == (1000,)
+xyz = g.atom_coords()
+gr = grids.bond_grid(xyz[0], xyz[1], xyz[2], 1.0, [-2.0, 2.0], [-1.0, 3.0], "gauss", grid_points=[9, 9, 0], gauss_order=9)
+assert g.integrate(gr, [0, 0, 1.0], "total", 7).shape == (7,) and g.integrate_batch([gr, gr, gr], [0, 0, 1.0]).shape == (3, 7)
+assert g.jtensors_grid(gr).shape == (81, 9) and g.jtensors_grid(gr, 10, 30).shape == (20, 9)
+res = g.property(r, np.full(1000, 0.01), t, xyz, [400, 600])
+assert res["sigma"].shape == (8, 3) and res["chi_atoms"].shape == (2, 3) and g.property_integrand(r, t, xyz[0]).shape == (1000, 4)
+assert g.jtensor(r[0]).shape == (9,) and len(g.jvector(r[0])) == 3
+for bad in ("beta", "spindens"):
+    try:
+        g.jtensors(r, bad); raise SystemExit("closed-shell context accepted " + bad)
+    except gimic_b200.GimicB200Error as e:
+        assert e.code == -4
+g.close()
+u = gimic_b200.Gimic(molu, xdu, uhf=True, screening_thrs=1e-8)
+for sc in ("alpha", "beta", "total", "spindens"):
+    assert u.jtensors(r[:300], sc).shape == (300, 9)
+sh, da, nbf = fixtures.synthetic_case(5, "flake", seed=5)
+a = gimic_b200.Gimic.from_arrays(dens_alpha=fixtures.dens_to_colmajor(da), dens_beta=fixtures.dens_to_colmajor(da[::-1].copy()), **sh)
+assert (a.nbf, a.natoms, a.uhf) == (nbf, 5, True) and a.jtensors(r[:200], "spindens").shape == (200, 9)
+a.close()
+assert "torch" not in sys.modules
+print("python wrapper ok")
+'''
+
+
+def test_python_wrapper_signatures_on_the_fake_cuda_runtime(tmp_path, cases):
+    """gimic_b200.Gimic (ctypes over include/gimic_b200.h) against the REAL libgimic_b200.so whose libcudart is replaced by the fake runtime:
+    every wrapper method is called once -- argument marshalling, the Stats / Opts / Grid struct layouts and the error codes must match the
+    library (results are zeros: kernels are no-ops).  Runs in a fresh interpreter that never imports torch, so that the fake runtime is the
+    only libcudart.so.12 in the process."""
+    import __graft_entry__ as ge
+    import sys
+    from gimic_b200 import _lib
+    if not os.path.exists(_lib.SO_PATH):
+        ge.build()
+    if not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("CUDA headers not installed")
+    fake = tmp_path / "fakecuda"
+    fake.mkdir()
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", str(fake / "libcudart.so.12"),
+                           os.path.join(ROOT, "tests", "fake_cudart", "fake_cudart.cpp")])
+    code = WRAPPER_SCRIPT.format(root=ROOT, tests=os.path.join(ROOT, "tests"))
+    p = subprocess.run([sys.executable, "-c", code, cases["c4h4"]["mol"], cases["c4h4"]["xdens"], cases["open_shell"]["mol"], cases["open_shell"]["xdens"]],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, LD_LIBRARY_PATH=str(fake)))
+    assert p.returncode == 0 and "python wrapper ok" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
