@@ -644,14 +644,9 @@ int run_input(const std::string &inpfile, const RunOptions &opt, FILE *out) {
 // slices, one process and one MOL/XDENS read each) as ONE context and ONE tensor pass per spin case: all inputs that share
 // basis, densities and Advanced settings are integrated by gimic_b200_integrate_batch.
 int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt) {
-    struct Closer { std::vector<FILE *> f; ~Closer() { for (FILE *p : f) if (p) std::fclose(p); } } files;
     return guarded([&] {
         std::vector<std::unique_ptr<Run>> runs;
         for (const std::string &f : inpfiles) {
-            const std::string rep = stem_of(f) + ".out";
-            FILE *o = std::fopen(rep.c_str(), "w");
-            if (!o) throw DriverError("cannot write " + rep);
-            files.f.push_back(o);
             RunOptions ro = opt;
             ro.workdir.clear();                                   // every input runs in its own directory
             if (!ro.devices.empty()) { ro.device = ro.devices[0]; ro.devices.clear(); }   // a scan batches all planes on one device
@@ -659,7 +654,8 @@ int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt) {
                 for (const auto &r : runs) if (r->ctx && r->context_key == key) return r->ctx;
                 return std::shared_ptr<Context>();
             };
-            runs.emplace_back(new Run(f, ro, o, finder));
+            // the report file is only open while it is written (a scan can have more slices than the process may hold open files)
+            runs.emplace_back(new Run(f, ro, nullptr, finder));
         }
         std::vector<std::map<int, Sums>> pre(runs.size());
         std::vector<Context *> order;                             // contexts in order of first appearance
@@ -699,8 +695,12 @@ int run_scan(const std::vector<std::string> &inpfiles, const RunOptions &opt) {
             }
         }
         for (size_t i = 0; i < runs.size(); ++i) {
+            const std::string rep = stem_of(inpfiles[i]) + ".out";
+            struct Report { FILE *f; ~Report() { if (f) std::fclose(f); } } report{std::fopen(rep.c_str(), "w")};
+            if (!report.f) throw DriverError("cannot write " + rep);
+            runs[i]->out.f = report.f;
             runs[i]->run(pre[i].empty() ? nullptr : &pre[i]);
-            std::fflush(runs[i]->out.f);
+            runs[i]->out.f = nullptr;
         }
         // current_profile.dat next to the first input: slice position (index x delta when the jobscripts' calculation.dat is there,
         // jobscripts/src/current-profile-header:38, else the index), net / diatropic / paratropic current in nA/T -- what

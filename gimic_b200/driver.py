@@ -479,12 +479,11 @@ def run_scan(infiles, device=-1, outs=None):
     share basis, densities and Advanced settings are integrated by gimic_b200_integrate_batch.  Reports go to
     <input stem>.out next to each input (or to the streams in `outs`).  Inputs with calc != integral run one by one on the
     shared context.  Returns the drivers (results in .results)."""
-    drivers, opened = [], []
+    import io
+    drivers = []
     for k, f in enumerate(infiles):
-        if outs is not None:
-            out = outs[k]
-        else:
-            out = open(os.path.splitext(f)[0] + ".out", "w"); opened.append(out)
+        # a report file is only open while it is written (a scan can have more slices than the process may hold open files)
+        out = outs[k] if outs is not None else io.StringIO()
         share = next((d.g for d in drivers if d.g is not None and d.context_key == _context_key_of(f)), None)
         drivers.append(Driver(f, out=out, device=device, gimic=share))
     batch = [d for d in drivers if d.inp.get("calc") == "integral" and not d.inp.get("dryrun") and d.world == 1]
@@ -501,10 +500,14 @@ def run_scan(infiles, device=-1, outs=None):
             sums = ds[0].g.integrate_batch([d.grid for d in ds], np.array([d.magnet for d in ds]), sc, what)
             for d, row in zip(ds, sums):
                 pre[id(d)][sc] = row
-    for d in drivers:
-        d.run(pre.get(id(d)))
-    for o in opened:
-        o.close()
+    for d, f in zip(drivers, infiles):
+        if outs is None:
+            with open(os.path.splitext(f)[0] + ".out", "w") as fh:
+                d.out = fh
+                d.run(pre.get(id(d)))
+            d.out = None
+        else:
+            d.run(pre.get(id(d)))
     write_current_profile(drivers)
     return drivers
 
