@@ -1,0 +1,28 @@
+"""The measurement / profiling scripts under tools/ only run on a GPU box; here they must at least parse, and every file they name must exist."""
+import ast
+import os
+import re
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOLS = os.path.join(ROOT, "tools")
+
+
+@pytest.mark.parametrize("name", sorted(f for f in os.listdir(TOOLS) if f.endswith(".py")))
+def test_python_tools_parse(name):
+    ast.parse(open(os.path.join(TOOLS, name)).read(), filename=name)
+
+
+@pytest.mark.parametrize("name", sorted(f for f in os.listdir(TOOLS) if f.endswith(".sh")))
+def test_shell_tools_parse_and_reference_existing_files(name):
+    path = os.path.join(TOOLS, name)
+    subprocess.check_call(["bash", "-n", path])
+    text = open(path).read()
+    for rel in set(re.findall(r"\b(tools/[\w./-]+\.(?:py|sh)|tests/[\w./-]+\.(?:py|cpp)|bench\.py)\b", text)):
+        assert os.path.exists(os.path.join(ROOT, rel)), f"{name} names {rel}, which does not exist"
+
+
+def test_bench_and_entry_parse():
+    for f in ("bench.py", "__graft_entry__.py"):
+        ast.parse(open(os.path.join(ROOT, f)).read(), filename=f)
