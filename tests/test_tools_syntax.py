@@ -26,3 +26,15 @@ def test_shell_tools_parse_and_reference_existing_files(name):
 def test_bench_and_entry_parse():
     for f in ("bench.py", "__graft_entry__.py"):
         ast.parse(open(os.path.join(ROOT, f)).read(), filename=f)
+
+
+def test_ncu_launch_list_summary_reads_the_committed_capture():
+    """tools/ncu_summary.py launches on profiles/r01_launches_tap.csv (the committed ncu launch list of bench.py): the contraction kernel's
+    share of a step is what DESIGN.md quotes"""
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(TOOLS, "ncu_summary.py"), "launches", os.path.join(ROOT, "profiles", "r01_launches_tap.csv")],
+                                  text=True)
+    first = out.split("\n")[0]
+    assert "k_jtensor" in first
+    share = float(re.search(r"share=\s*([\d.]+)%", first).group(1))
+    assert 90.0 < share < 97.0
