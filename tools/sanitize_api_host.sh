@@ -32,6 +32,8 @@ import fixtures
 fixtures.materialize('$TMP')
 "
 "$OUT/api-harness-asan" "$TMP/c4h4/MOL" "$TMP/c4h4/XDENS" "$TMP/open_shell/MOL" "$TMP/open_shell/XDENS"
+# once more with a 1 MB panel pool: hundreds of batches per call (the emulated tile counts make the batch / offset bookkeeping non-trivial)
+GIMIC_B200_POOL_MB=1 "$OUT/api-harness-asan" "$TMP/c4h4/MOL" "$TMP/c4h4/XDENS" "$TMP/open_shell/MOL" "$TMP/open_shell/XDENS"
 # the driver's run modes on the real C ABI host code (the sanitizer-built program is passed for both slots of the runner)
 LD_LIBRARY_PATH= "$PY" -c "
 import os, subprocess, sys
