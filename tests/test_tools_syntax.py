@@ -38,3 +38,22 @@ def test_ncu_launch_list_summary_reads_the_committed_capture():
     assert "k_jtensor" in first
     share = float(re.search(r"share=\s*([\d.]+)%", first).group(1))
     assert 90.0 < share < 97.0
+
+
+@pytest.mark.skipif(subprocess.call("command -v cuobjdump >/dev/null 2>&1", shell=True) != 0, reason="cuobjdump not on PATH")
+def test_static_sass_record_of_the_built_library():
+    """tools/sass_static.py on the library as built: the contraction kernel is FP64 tensor-core code (DMMA) fed by bulk-TMA copies
+    (UBLKCP), mbarriers (SYNCS) and cp.async gathers (LDGSTS), re-partitions registers (USETMAXREG) and does not spill"""
+    import sys
+    so = os.path.join(ROOT, "gimic_b200", "libgimic_b200.so")
+    if not os.path.exists(so):
+        import __graft_entry__ as ge
+        ge.build()
+    out = subprocess.check_output([sys.executable, os.path.join(TOOLS, "sass_static.py")], text=True)
+    blocks = {m.group(1): m.group(2) for m in re.finditer(r"^(gb::[^\n]+)\n((?:    .*\n)+)", out, flags=re.M)}
+    for variant in ("gb::k_jtensor<true, false>", "gb::k_jtensor<true, true>", "gb::k_jtensor<false, false>", "gb::k_jtensor<false, true>"):
+        b = blocks[variant]
+        for op in ("DMMA", "UBLKCP", "SYNCS", "LDGSTS", "USETMAXREG"):
+            assert re.search(rf"\b{op} [1-9]", b), (variant, op)
+        assert "0 bytes spill stores, 0 bytes spill loads" in b and not re.search(r"\bSTL [1-9]", b), variant
+    assert "gb::k_basis" in blocks and "gb::k_fields" in blocks
