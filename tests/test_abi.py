@@ -218,3 +218,26 @@ int main(int argc, char **argv) {
         assert out.startswith("ok nbf=168 natoms=8 consistent=1") and "spin refused" in out, out
     else:
         assert out.startswith("refused: gimic_b200: no CUDA device available"), out
+
+
+def test_product_is_independent_of_the_oracle(L):
+    """oracle/ is test infrastructure: no product source names it (neither an import, an include, a path nor a link line), the
+    built libraries and the program have no dependency on libgimic_oracle.so, and importing the package does not load it"""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "gimic_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) and f != "Makefile":
+                continue
+            text = open(os.path.join(d, f), errors="replace").read()
+            assert not re.search(r"oracle[_/.](?:lib|gimic|_ref)|libgimic_oracle|import\s+oracle|from\s+oracle|\.\./oracle|oracle/", text), os.path.join(d, f)
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        assert "oracle/" not in open(os.path.join(ROOT, "include", h), errors="replace").read(), h
+    for name in ("libgimic_b200.so", "libgimic_b200_driver.so", "gimic-b200"):
+        dyn = subprocess.check_output(["readelf", "-d", os.path.join(pkg, name)], text=True)
+        assert "oracle" not in dyn, name
+    code = ("import sys; sys.path.insert(0, %r); import gimic_b200, gimic_b200.driver, gimic_b200.gimic; "
+            "maps = open('/proc/self/maps').read(); assert 'libgimic_oracle' not in maps; "
+            "assert not [m for m in sys.modules if 'oracle' in m], [m for m in sys.modules if 'oracle' in m]") % ROOT
+    subprocess.check_call([sys.executable, "-c", code])
