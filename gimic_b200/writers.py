@@ -10,7 +10,9 @@ AU2A = float(np.float32(0.52917726))     # globals.f90:51 is a single-precision 
 def fortran_e(x, w, d):
     """Fortran Ew.d: 0.dddddE+ee (gfortran drops the 'E' when the exponent needs three digits; asterisks on overflow)"""
     x = float(x)
-    if x == 0.0:
+    if x != x or x in (float("inf"), -float("inf")):          # gfortran: NaN / Infinity / -Infinity, right-justified
+        s = "NaN" if x != x else ("-Infinity" if x < 0 else "Infinity")
+    elif x == 0.0:
         s = "0." + "0" * d + "E+00"
     else:
         m, e = f"{abs(x):.{d - 1}E}".split("E")

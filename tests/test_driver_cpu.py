@@ -162,6 +162,12 @@ def test_native_bulk_formatter_equals_the_python_edit_descriptor():
                 lines.append(prefix + "".join(line) + "\n"); line = []
         assert got == "".join(lines) + (prefix + "".join(line) if line else ""), (w, d, per_line, first)
     assert format_e([], 14, 6, 3) == b"" and fortran_e(1e-101, 14, 6) == "  0.100000-100" and fortran_e(1e200, 8, 6) == "*" * 8
+    # non-finite values and the ends of the double range: both formatters print them like gfortran and agree with each other
+    odd = [float("nan"), float("inf"), -float("inf"), 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, -1.7976931348623157e308, 4.9e-310]
+    for w, d in ((14, 6), (24, 16)):
+        assert format_e(odd, w, d, 1).decode().split("\n")[:-1] == [fortran_e(x, w, d) for x in odd]
+    assert fortran_e(float("nan"), 14, 6) == " " * 11 + "NaN" and fortran_e(-float("inf"), 14, 6) == "     -Infinity"
+    assert fortran_e(5e-324, 14, 6) == "  0.494066-323"
 
 
 def test_vti_appended_extra_holds_the_same_numbers(tmp_path):
@@ -257,3 +263,25 @@ def test_dry_run_needs_no_device(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             driver.Driver(str(tmp_path / "gimic.inp"), out=io.StringIO())
+
+
+def test_native_formatters_on_arbitrary_doubles():
+    """property test (hypothesis): for any double, any reasonable Ew.d / Fw.d, gimic_b200_format_e / _f print what the
+    per-value Python edit descriptors print (correct rounding of the exact binary value, exponent carries, three-digit
+    exponents, asterisks on overflow, non-finite values)"""
+    from hypothesis import given, settings, strategies as st
+    from gimic_b200.writers import fortran_e, format_e, format_f
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.floats(allow_nan=True, allow_infinity=True, width=64), min_size=1, max_size=40),
+           st.integers(min_value=1, max_value=17), st.integers(min_value=0, max_value=9), st.integers(min_value=1, max_value=5))
+    def check(vals, d, extra, per_line):
+        w = d + 7 + extra
+        got = format_e(vals, w, d, per_line).decode()
+        toks = [got_line[i:i + w] for got_line in got.split("\n") for i in range(0, len(got_line), w)]
+        assert toks == [fortran_e(x, w, d) for x in vals]
+        finite = [x for x in vals if x == x and abs(x) < 1e15]
+        if finite:
+            gf = format_f(finite, w, d, 1).decode().split("\n")[:-1]
+            assert gf == [("%*.*f" % (w, d, x)) if len("%*.*f" % (w, d, x)) <= w else "*" * w for x in finite]
+    check()
