@@ -138,8 +138,10 @@ std::string py_repr(double x) {
 // Fortran Ew.d: 0.dddddE+ee (gfortran drops the 'E' when the exponent needs three digits; asterisks on overflow)
 std::string fortran_e(double x, int w, int d) {
     std::string s;
-    if (x == 0.0) {
-        s = "0." + std::string(d, '0') + "E+00";
+    if (!std::isfinite(x)) {
+        s = std::isnan(x) ? "NaN" : (x < 0 ? "-Infinity" : "Infinity");
+    } else if (x == 0.0) {
+        s = std::string(std::signbit(x) ? "-" : "") + "0." + std::string(d, '0') + "E+00";      // gfortran keeps the sign of a negative zero
     } else {
         char buf[64];
         snprintf(buf, sizeof buf, "%.*E", d - 1, std::fabs(x));

@@ -433,7 +433,7 @@ void put_e(double x, int w, int d, char *dst) {
     char tmp[64], body[64];
     int len;
     if (x == 0.0) {
-        len = std::snprintf(body, sizeof body, "0.%0*dE+00", d, 0);
+        len = std::snprintf(body, sizeof body, "%s0.%0*dE+00", std::signbit(x) ? "-" : "", d, 0);   // gfortran keeps the sign of a negative zero
     } else if (!std::isfinite(x)) {
         len = std::snprintf(body, sizeof body, "%s", std::isnan(x) ? "NaN" : (x < 0 ? "-Infinity" : "Infinity"));
     } else {

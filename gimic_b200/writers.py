@@ -13,7 +13,7 @@ def fortran_e(x, w, d):
     if x != x or x in (float("inf"), -float("inf")):          # gfortran: NaN / Infinity / -Infinity, right-justified
         s = "NaN" if x != x else ("-Infinity" if x < 0 else "Infinity")
     elif x == 0.0:
-        s = "0." + "0" * d + "E+00"
+        s = ("-" if str(x)[0] == "-" else "") + "0." + "0" * d + "E+00"      # gfortran keeps the sign of a negative zero
     else:
         m, e = f"{abs(x):.{d - 1}E}".split("E")
         digits = m.replace(".", "")

@@ -168,6 +168,7 @@ def test_native_bulk_formatter_equals_the_python_edit_descriptor():
         assert format_e(odd, w, d, 1).decode().split("\n")[:-1] == [fortran_e(x, w, d) for x in odd]
     assert fortran_e(float("nan"), 14, 6) == " " * 11 + "NaN" and fortran_e(-float("inf"), 14, 6) == "     -Infinity"
     assert fortran_e(5e-324, 14, 6) == "  0.494066-323"
+    assert fortran_e(-0.0, 14, 6) == " -0.000000E+00" and format_e([-0.0, 0.0], 14, 6, 2) == b" -0.000000E+00  0.000000E+00\n"
 
 
 def test_vti_appended_extra_holds_the_same_numbers(tmp_path):
