@@ -308,8 +308,13 @@ void write_jmod_txt(const std::string &path, const GridSpec &g, const std::vecto
 }
 
 namespace {
+// F16.10; a coordinate that is not finite (grid_points = 1 along a non-zero length: step = l/0, grid.f90:157) prints like gfortran
+std::string f16(double x) {
+    if (std::isfinite(x)) return fmt("%16.10f", x);
+    return rjust(std::isnan(x) ? "NaN" : (x < 0 ? "-Infinity" : "Infinity"), 16);
+}
 std::string xyz_line(const std::string &sym, const double *c) {
-    return sym + fmt("%16.10f%16.10f%16.10f\n", c[0] * AU2A, c[1] * AU2A, c[2] * AU2A);
+    return sym + f16(c[0] * AU2A) + f16(c[1] * AU2A) + f16(c[2] * AU2A) + "\n";
 }
 }  // namespace
 

@@ -7,6 +7,16 @@ import numpy as np
 AU2A = float(np.float32(0.52917726))     # globals.f90:51 is a single-precision literal
 
 
+def _f16(x):
+    """F16.10; a coordinate that is not finite (grid_points = 1 along a non-zero length: step = l/0, grid.f90:157) prints like gfortran"""
+    x = float(x)
+    if x != x:
+        return "NaN".rjust(16)
+    if x in (float("inf"), -float("inf")):
+        return ("-Infinity" if x < 0 else "Infinity").rjust(16)
+    return f"{x:16.10f}"
+
+
 def fortran_e(x, w, d):
     """Fortran Ew.d: 0.dddddE+ee (gfortran drops the 'E' when the exponent needs three digits; asterisks on overflow)"""
     x = float(x)
@@ -263,7 +273,7 @@ def write_mol_xyz(path, symbols, coords):
     with open(path, "w") as f:
         f.write(f"{len(symbols):12d}\n\n")
         for s, c in zip(symbols, coords):
-            f.write(f"{s}" + "".join(f"{x * AU2A:16.10f}" for x in c) + "\n")
+            f.write(f"{s}" + "".join(_f16(x * AU2A) for x in c) + "\n")
 
 
 def write_grid_xyz(path, grid, symbols, coords):
@@ -285,8 +295,8 @@ def write_grid_xyz(path, grid, symbols, coords):
     with open(path, "w") as f:
         f.write(f"{len(symbols) + len(corners) + 1:12d}\n\n")
         for s, c in zip(symbols, coords):
-            f.write(f"{s}" + "".join(f"{x * AU2A:16.10f}" for x in c) + "\n")
+            f.write(f"{s}" + "".join(_f16(x * AU2A) for x in c) + "\n")
         for c in corners:
-            f.write("X " + "".join(f"{x * AU2A:16.10f}" for x in c) + "\n")
+            f.write("X " + "".join(_f16(x * AU2A) for x in c) + "\n")
         if marker is not None:
-            f.write("Be " + "".join(f"{x * AU2A:16.10f}" for x in marker) + "\n")
+            f.write("Be " + "".join(_f16(x * AU2A) for x in marker) + "\n")

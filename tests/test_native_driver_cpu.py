@@ -483,3 +483,21 @@ def test_python_entry_can_hand_the_run_to_the_compiled_driver(D, tmp_path):
     assert filecmp.cmp(d1 / "grid.xyz", d2 / "grid.xyz", shallow=False)
     with pytest.raises(RuntimeError, match="cannot open input file"):
         driver.run_native(str(tmp_path / "missing.inp"), dryrun=True)
+
+
+def test_one_grid_point_along_an_axis_gives_nan_coordinates_like_the_reference(D, tmp_path):
+    """grid_points = 1 along an axis: the reference divides the length by npts - 1 = 0 (grid.f90:157) and carries on with NaN / Inf
+    coordinates; both drivers do the same and print them the way gfortran does ('NaN', never printf's '-nan')"""
+    from gimic_b200 import driver
+    text = ('calc=cdens\ntitle=""\nbasis="MOL"\nxdens="XDENS"\ndebug=1\nopenshell=false\nmagnet=[0.0, 0.0, 1.0]\n'
+            "Grid(base) {\n type=even\n origin=[-4.0, -4.0, -3.0]\n ivec=[1, 0, 0]\n jvec=[0, 1, 0]\n lengths=[4.5, 8.0, 0]\n grid_points=[3, 20, 1]\n}\n")
+    dn, dp = _workdir(tmp_path / "nat", "benzene_nan", text), _workdir(tmp_path / "py", "benzene_nan", text)
+    p = subprocess.run([EXE, "-y", str(dn / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    out = io.StringIO()
+    with np.errstate(all="ignore"):
+        driver.Driver(str(dp / "gimic.inp"), out=out, dryrun=True).run()
+    assert fixtures.strip_clock(p.stdout) == fixtures.strip_clock(out.getvalue())
+    assert filecmp.cmp(dn / "grid.xyz", dp / "grid.xyz", shallow=False)
+    xyz = open(dn / "grid.xyz").read()
+    assert "             NaN" in xyz and "nan" not in xyz
