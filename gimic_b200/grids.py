@@ -14,9 +14,25 @@ from .gengauss import gausspoints
 PII = 3.141592653589793  # globals.f90:41
 
 
+
+def _dot3(a, b):
+    """a.b summed left to right in plain doubles -- the same operation order as the native driver (csrc/driver/grid.cpp), so that
+    both drivers take the same side of knife-edge tests like check_field's x > 0 (numpy's BLAS may fuse or reorder)"""
+    return float(a[0]) * float(b[0]) + float(a[1]) * float(b[1]) + float(a[2]) * float(b[2])
+
+
+def _matvec3(R, v):
+    return np.array([0.0 + float(R[i][0]) * float(v[0]) + float(R[i][1]) * float(v[1]) + float(R[i][2]) * float(v[2]) for i in range(3)])
+
+
+def _matmul3(A, B):
+    return np.array([[0.0 + float(A[i][0]) * float(B[0][j]) + float(A[i][1]) * float(B[1][j]) + float(A[i][2]) * float(B[2][j])
+                      for j in range(3)] for i in range(3)])
+
+
 def _unit(v):
     v = np.asarray(v, dtype=np.float64)
-    return v / math.sqrt(float(np.dot(v, v)))
+    return v / math.sqrt(_dot3(v, v))
 
 
 class GridSpec(Grid):
@@ -58,7 +74,7 @@ def _rotation_matrix(angle_deg):
     Rz = np.array([[math.cos(rz), math.sin(rz), 0.0], [-math.sin(rz), math.cos(rz), 0.0], [0.0, 0.0, 1.0]])
     Ry = np.array([[math.cos(ry), 0.0, -math.sin(ry)], [0.0, 1.0, 0.0], [math.sin(ry), 0.0, math.cos(ry)]])
     Rx = np.array([[1.0, 0.0, 0.0], [0.0, math.cos(rx), math.sin(rx)], [0.0, -math.sin(rx), math.cos(rx)]])
-    return Rx @ (Ry @ Rz)
+    return _matmul3(Rx, _matmul3(Ry, Rz))
 
 
 def _f3(v, w=12, d=6):
@@ -116,14 +132,14 @@ def _finish(origin, basv, lengths, mode, gtype, ortho, radius, step, grid_points
                 " basv2  " + _f3(basv[1]), " basv3  " + _f3(basv[2]), " lenghts" + _f3(lengths), " magnet " + _f3(ortho), ""]
     log.append(" Grid mode = " + mode)
     for v in range(3):                                   # normalise, grid.f90:278-288
-        n = math.sqrt(float(np.dot(basv[v], basv[v])))
+        n = math.sqrt(_dot3(basv[v], basv[v]))
         if n > 0.0:
             basv[v] = basv[v] / n
-    if abs(float(np.dot(basv[0], basv[1]))) > 1e-10:     # ortho_coordsys, grid.f90:400-428
+    if abs(_dot3(basv[0], basv[1])) > 1e-10:     # ortho_coordsys, grid.f90:400-428
         t = np.cross(basv[0], basv[2])
-        basv[1] = t / math.sqrt(float(np.dot(t, t)))
+        basv[1] = t / math.sqrt(_dot3(t, t))
         for v in range(3):
-            n = math.sqrt(float(np.dot(basv[v], basv[v])))
+            n = math.sqrt(_dot3(basv[v], basv[v]))
             if n > 0.0:
                 basv[v] = basv[v] / n
     origin = np.array(origin, dtype=np.float64)
@@ -131,8 +147,8 @@ def _finish(origin, basv, lengths, mode, gtype, ortho, radius, step, grid_points
         ref = np.array(rotation_origin, dtype=np.float64) if rotation_origin is not None else \
             origin + out_len * basv[1] + down_len * basv[0]
         R = _rotation_matrix(rotation)
-        basv = np.array([R @ basv[v] for v in range(3)])
-        origin = R @ (origin - ref) + ref
+        basv = np.array([_matvec3(R, basv[v]) for v in range(3)])
+        origin = _matvec3(R, origin - ref) + ref
         log.append(" INFO: Rotation is: " + _f3([a / 180.0 * PII for a in rotation], 9, 5))
     pts, wgt = _axes(lengths, gtype, step, grid_points, spacing, gauss_order, log)
     g = GridSpec(origin, basv, pts, wgt, radius, mode, gtype, ortho, lengths, center_bond)
@@ -213,7 +229,7 @@ def get_magnet(grid, magnet_axis="", magnet=(0.0, 0.0, 0.0), log=None):
         raise ValueError("Magnetic field is zero, not wasting more CPU.")
     mag = np.array(mag, dtype=np.float64)
     if not ortho:                                              # check_field, magnet.f90:66-86
-        x = float(np.dot(grid.basv[2], mag))
+        x = _dot3(grid.basv[2], mag)
         if x > 0.0:
             mag = -mag
             if log is not None:
