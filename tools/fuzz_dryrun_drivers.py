@@ -16,6 +16,7 @@ import fixtures
 from gimic_b200 import driver
 EXE = os.path.join(ROOT, "gimic_b200", "gimic-b200"); GOLD = fixtures.GOLD
 rng = None
+NATOMS, MAXPTS = 12, 40          # benzene; points per axis (the complete-run variant of this fuzz uses smaller grids)
 def num(x): return f"{x:.6g}"
 def gen():
     calc = rng.choice(["integral","cdens"])
@@ -28,10 +29,10 @@ def gen():
     if bond:
         g.append("Grid(bond) {"); g.append(f" type={typ}")
         if rng.random()<0.7:
-            a,b = rng.choice(np.arange(1,13),2,replace=False); g.append(f" bond=[{a},{b}]")
+            a,b = rng.choice(np.arange(1,NATOMS+1),2,replace=False); g.append(f" bond=[{a},{b}]")
         else:
             g.append(" coord1=[%s]"%", ".join(num(v) for v in rng.normal(size=3)*2)); g.append(" coord2=[%s]"%", ".join(num(v) for v in rng.normal(size=3)*2+1))
-        if rng.random()<0.7: g.append(f" fixpoint={rng.integers(1,13)}")
+        if rng.random()<0.7: g.append(f" fixpoint={rng.integers(1,NATOMS+1)}")
         else: g.append(" fixcoord=[%s]"%", ".join(num(v) for v in rng.normal(size=3)*3))
         g.append(f" distance={num(rng.uniform(0.1,2.5))}")
         g.append(f" height=[{num(-rng.uniform(0.5,6))}, {num(rng.uniform(0.5,6))}]"); g.append(f" width=[{num(-rng.uniform(0.5,6))}, {num(rng.uniform(0.5,6))}]")
@@ -47,8 +48,8 @@ def gen():
         g.append(" lengths=[%s]"%", ".join(num(v) for v in L))
     if typ!="even": g.append(f" gauss_order={rng.integers(2,12)}")
     if rng.random()<0.6 or typ!="even":
-        n3 = rng.integers(0,12) if not bond else 0
-        g.append(f" grid_points=[{rng.integers(1,40)}, {rng.integers(1,40)}, {n3}]")
+        n3 = rng.integers(0,min(12,MAXPTS)) if not bond else 0
+        g.append(f" grid_points=[{rng.integers(1,MAXPTS)}, {rng.integers(1,MAXPTS)}, {n3}]")
     else:
         g.append(" spacing=[%s]"%", ".join(num(v) for v in rng.uniform(0.1,2,size=3)))
     if rng.random()<0.4:
