@@ -36,6 +36,16 @@ struct Context {
 
 const char *SPIN_LABEL[4] = {"alpha", "beta", "total", "spin"};
 
+// printf writes a NaN as "nan" or "-nan"; gfortran's F and E edits write "NaN" (and never a sign).  Same width, so columns stay put.
+void gfortran_nan(char *s) {
+    for (char *p = s; (p = std::strstr(p, "nan")) != nullptr; p += 3) {
+        const bool word = (p > s && std::isalpha((unsigned char)p[-1])) || std::isalpha((unsigned char)p[3]);
+        if (word) continue;
+        p[0] = 'N'; p[2] = 'N';
+        if (p > s && p[-1] == '-') p[-1] = ' ';
+    }
+}
+
 struct Printer {
     FILE *f;
     void raw(const std::string &s) const { std::fwrite(s.data(), 1, s.size(), f); }
@@ -46,6 +56,7 @@ struct Printer {
         va_start(ap, fmtstr);
         vsnprintf(buf, sizeof buf, fmtstr, ap);
         va_end(ap);
+        gfortran_nan(buf);
         raw(buf);
     }
 };
@@ -57,6 +68,7 @@ std::string sfmt(const char *fmtstr, ...) {
     va_start(ap, fmtstr);
     vsnprintf(buf, sizeof buf, fmtstr, ap);
     va_end(ap);
+    gfortran_nan(buf);
     return buf;
 }
 

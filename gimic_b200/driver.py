@@ -10,6 +10,7 @@ gathers the tensors on rank 0 (which writes the files, like the reference's MPI 
 splits plane rows and all-reduces the partial sums.
 """
 import os
+import re
 import sys
 import time
 import numpy as np
@@ -88,6 +89,21 @@ def _dist():
     return None, 0, 1
 
 
+
+class _GfortranNaN:
+    """report sink: Python formats a NaN as 'nan'; gfortran's F and E edits (and the native driver) write 'NaN'"""
+    _pat = re.compile(r"(?<![A-Za-z])nan(?![A-Za-z])")
+
+    def __init__(self, out):
+        self._out = out
+
+    def write(self, s):
+        return self._out.write(self._pat.sub("NaN", s) if "nan" in s else s)
+
+    def __getattr__(self, name):
+        return getattr(self._out, name)
+
+
 class Driver:
     def __init__(self, inpfile, workdir=None, out=None, device=-1, gimic=None, vtk_appended=False, dryrun=False, title=None):
         self._t0, self._cpu0 = time.perf_counter(), os.times()    # stockas_klocka reports the times of the whole run
@@ -99,7 +115,7 @@ class Driver:
             self.inp.values[""]["title"] = str(title)
         self.vtk_appended = bool(vtk_appended)   # extra: .vti files with raw appended Float64 data instead of ASCII e14.6
         self.dist, self.rank, self.world = _dist()
-        self.out = out if out is not None else sys.stdout
+        self.out = _GfortranNaN(out if out is not None else sys.stdout)
         I = self.inp
         self.uhf = bool(I.get("openshell"))
         path = lambda n: n if os.path.isabs(n) else os.path.join(self.workdir, n)

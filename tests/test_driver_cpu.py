@@ -286,3 +286,15 @@ def test_native_formatters_on_arbitrary_doubles():
             gf = format_f(finite, w, d, 1).decode().split("\n")[:-1]
             assert gf == [("%*.*f" % (w, d, x)) if len("%*.*f" % (w, d, x)) <= w else "*" * w for x in finite]
     check()
+
+
+def test_report_sink_prints_nan_like_gfortran():
+    """a NaN in a report line (e.g. an integral over a grid with one point on an axis, where the reference's step is l/0) reads 'NaN' as
+    gfortran's F edit writes it, at the same width; words containing 'nan' are left alone"""
+    import io
+    from gimic_b200.driver import _GfortranNaN
+    buf = io.StringIO()
+    out = _GfortranNaN(buf)
+    out.write(f" Induced current (au)    :{float('nan'):14.6f}\n resonance nanoring\n")
+    assert buf.getvalue() == " Induced current (au)    :           NaN\n resonance nanoring\n"
+    assert out.getvalue() == buf.getvalue()                      # everything else is the wrapped stream's
