@@ -19,7 +19,7 @@ rng = None
 NATOMS, MAXPTS = 12, 40          # benzene; points per axis (the complete-run variant of this fuzz uses smaller grids)
 def num(x): return f"{x:.6g}"
 def gen():
-    calc = rng.choice(["integral","cdens"])
+    calc = rng.choice(["integral","cdens","integral","cdens","edens","divj"])
     typ = rng.choice(["gauss","even","lobatto"]) if calc=="integral" else rng.choice(["even","gauss"])
     lines = [f"calc={calc}", 'title=""','basis="MOL"','xdens="XDENS"',"debug=1","openshell=false"]
     if rng.random()<0.5: lines.append("magnet_axis="+rng.choice(["X","Y","Z","-x","i","j","k","-k","T"]))
@@ -56,7 +56,9 @@ def gen():
         g.append(" rotation=[%s]"%", ".join(num(v) for v in rng.uniform(-90,90,size=3)))
         if rng.random()<0.5: g.append(" rotation_origin=[%s]"%", ".join(num(v) for v in rng.normal(size=3)))
     g.append("}")
-    adv = ["Advanced {"," lip_order=5"," spherical=off"," diamag=on"," paramag=on"," GIAO=on"," screening=on"," screening_thrs=1.d-8","}"]
+    onoff = lambda: rng.choice(["on", "on", "off"])
+    adv = ["Advanced {"," lip_order=5"," spherical=off",f" diamag={onoff()}",f" paramag={onoff()}",f" GIAO={onoff()}",f" screening={onoff()}",
+           " screening_thrs=" + rng.choice(["1.d-8", "1e-6", "0.5D-10", "1.0E-12"]),"}"]
     ess = ["Essential {", f" acid={rng.choice(['on','off'])}", f" jmod={rng.choice(['on','off'])}", "}"]
     return "\n".join(lines+g+adv+ess)+"\n"
 
