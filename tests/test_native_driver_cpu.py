@@ -505,8 +505,8 @@ def test_one_grid_point_along_an_axis_gives_nan_coordinates_like_the_reference(D
 
 def test_randomized_grid_inputs_agree_between_the_drivers(D, tmp_path):
     """tools/fuzz_dryrun_drivers.py, two fixed seeds x 40 random gimic.inp files over the grid / magnet keywords: same accept / refuse
-    decision, same dry-run report, same grid.xyz byte for byte (seed 1 used to hit a field lying in the grid plane, where check_field's
-    x > 0 was decided by the summation order)"""
+    decision, same dry-run report, same grid.xyz byte for byte; plus the input on which this comparison once failed: a field along a rotated
+    in-plane basis vector (magnet_axis=i), where check_field's x > 0 (magnet.f90:75) is decided by the last bit of the summation"""
     import importlib.util
     spec = importlib.util.spec_from_file_location("fuzz_dryrun_drivers", os.path.join(ROOT, "tools", "fuzz_dryrun_drivers.py"))
     fz = importlib.util.module_from_spec(spec)
@@ -514,3 +514,13 @@ def test_randomized_grid_inputs_agree_between_the_drivers(D, tmp_path):
     with np.errstate(all="ignore"):
         assert fz.run(1, 40, tmp_path / "a") == 0
         assert fz.run(11, 40, tmp_path / "b") == 0
+    text = ('calc=integral\ntitle=""\nbasis="MOL"\nxdens="XDENS"\ndebug=1\nopenshell=false\nmagnet_axis=i\nGrid(bond) {\n type=even\n bond=[5,11]\n'
+            " fixpoint=10\n distance=2.48005\n height=[-4.49534, 5.27421]\n width=[-0.772161, 4.24791]\n grid_points=[9, 21, 0]\n"
+            " rotation=[2.42421, -43.0696, -19.5473]\n}\n")
+    from gimic_b200 import driver
+    dn, dp = _workdir(tmp_path / "nat", "benzene_inplane", text), _workdir(tmp_path / "py", "benzene_inplane", text)
+    p = subprocess.run([EXE, "-y", str(dn / "gimic.inp")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    out = io.StringIO()
+    driver.Driver(str(dp / "gimic.inp"), out=out, dryrun=True).run()
+    assert fixtures.strip_clock(p.stdout) == fixtures.strip_clock(out.getvalue())
