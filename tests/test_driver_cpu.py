@@ -298,3 +298,48 @@ def test_report_sink_prints_nan_like_gfortran():
     out.write(f" Induced current (au)    :{float('nan'):14.6f}\n resonance nanoring\n")
     assert buf.getvalue() == " Induced current (au)    :           NaN\n resonance nanoring\n"
     assert out.getvalue() == buf.getvalue()                      # everything else is the wrapped stream's
+
+
+def test_random_grids_equal_the_oracle_grids():
+    """200 random std / bond grids (even, gauss, lobatto; grid_points or spacing; rotation, rotation_origin, radius): the product's
+    grid code gives the oracle's points (1e-11 bohr), weights and fields for magnet_axis = X, k, -k, z, -x, y.  Not compared: magnet_axis
+    = i / j on such grids -- check_field (magnet.f90:75) then tests the sign of a dot product of two orthogonal vectors, i.e. of
+    rounding noise, in the reference as well; the two drivers agree with each other there (same summation order), the oracle need not."""
+    import warnings
+    from gimic_b200 import grids
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(1); N = 200; bad = 0
+    for k in range(N):
+        typ=str(rng.choice(["even","gauss","lobatto"])); order=int(rng.integers(2,12))
+        kw={}
+        if typ!="even" or rng.random()<0.5: kw["grid_points"]=[int(rng.integers(2,25)),int(rng.integers(2,25)),0]
+        else: kw["spacing"]=list(rng.uniform(0.2,1.5,size=3))
+        if rng.random()<0.5:
+            kw["rotation"]=list(rng.uniform(-90,90,size=3))
+            if rng.random()<0.5: kw["rotation_origin"]=list(rng.normal(size=3))
+        try:
+            if rng.random()<0.5:
+                c1,c2,fix=rng.normal(size=3)*2,rng.normal(size=3)*2+1,rng.normal(size=3)*3
+                d=float(rng.uniform(0.1,2)); h=[-float(rng.uniform(0.5,5)),float(rng.uniform(0.5,5))]; w=[-float(rng.uniform(0.5,5)),float(rng.uniform(0.5,5))]
+                rad=float(rng.uniform(1,4)) if rng.random()<0.3 else None
+                g=grids.bond_grid(c1,c2,fix,d,h,w,gtype=typ,gauss_order=order,radius=rad,**kw)
+                o=O.grid_bond(c1,c2,fix,d,height=h,width=w,radius=rad,type=typ,gauss_order=order,**kw)
+            else:
+                org=rng.uniform(-5,0,size=3); i=rng.normal(size=3); j=np.cross(i,rng.normal(size=3)); L=rng.uniform(1,8,size=3)
+                if "grid_points" in kw: kw["grid_points"][2]=int(rng.integers(0,8))
+                if "grid_points" in kw and kw["grid_points"][2]==1: kw["grid_points"][2]=2
+                g=grids.std_grid(org,i,j,L,gtype=typ,gauss_order=order,**kw)
+                o=O.grid_std(org,i,j,L,type=typ,gauss_order=order,**kw)
+        except Exception as e:
+            print("EXC",k,repr(e)[:200]); bad+=1; continue
+        ok = list(g.npts)==list(o.npts)
+        if ok:
+            pg,po=g.points(),o.points()
+            ok = np.allclose(pg,po,rtol=0,atol=1e-11)
+            for d in range(3):
+                pw=o.axis(d); ok = ok and np.allclose(g.wgt[d],pw[1],rtol=1e-12,atol=1e-14)
+            for ax in ("X","k","-k","z","-x","y"):
+                ok = ok and np.allclose(grids.get_magnet(g,ax,None),o.magnet(ax),atol=1e-12)
+        if not ok: bad+=1; print("MISMATCH",k,typ,kw,list(g.npts),list(o.npts))
+    assert bad == 0
+
