@@ -300,14 +300,13 @@ def test_report_sink_prints_nan_like_gfortran():
     assert out.getvalue() == buf.getvalue()                      # everything else is the wrapped stream's
 
 
+@pytest.mark.filterwarnings("ignore")
 def test_random_grids_equal_the_oracle_grids():
     """200 random std / bond grids (even, gauss, lobatto; grid_points or spacing; rotation, rotation_origin, radius): the product's
     grid code gives the oracle's points (1e-11 bohr), weights and fields for magnet_axis = X, k, -k, z, -x, y.  Not compared: magnet_axis
     = i / j on such grids -- check_field (magnet.f90:75) then tests the sign of a dot product of two orthogonal vectors, i.e. of
     rounding noise, in the reference as well; the two drivers agree with each other there (same summation order), the oracle need not."""
-    import warnings
     from gimic_b200 import grids
-    warnings.simplefilter("ignore")
     rng = np.random.default_rng(1); N = 200; bad = 0
     for k in range(N):
         typ=str(rng.choice(["even","gauss","lobatto"])); order=int(rng.integers(2,12))
