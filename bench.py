@@ -203,7 +203,7 @@ def main():
 
     sh, dens, nbf, origin, basv, pts = build_workload(args.natoms, args.grid, args.geometry, args.general_p)
     flat = synthetic.dens_to_colmajor(dens)
-    g = gimic_b200.Gimic.from_arrays(dens_alpha=flat, device=local_rank, **sh)
+    g = gimic_b200.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, device=local_rank, **sh)
     del flat
     r_np = slab_points(origin, basv, pts, rank % NSLAB)
     n = r_np.shape[0]

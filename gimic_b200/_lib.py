@@ -20,7 +20,7 @@ LEGACY_SYMBOLS = ["gimic_init", "gimic_finalize", "gimic_set_uhf", "gimic_set_ma
 API_SYMBOLS = ["gimic_b200_default_opts", "gimic_b200_create", "gimic_b200_create_from_arrays", "gimic_b200_destroy", "gimic_b200_device_count",
                "gimic_b200_nbf", "gimic_b200_natoms", "gimic_b200_atom_coords", "gimic_b200_is_uhf",
                "gimic_b200_calc_jtensors", "gimic_b200_calc_basis", "gimic_b200_calc_fields", "gimic_b200_fields_from_tensors", "gimic_b200_jmod_from_jvec",
-               "gimic_b200_calc_jtensors_grid", "gimic_b200_integrate", "gimic_b200_integrate_batch", "gimic_b200_property", "gimic_b200_property_integrand", "gimic_b200_gauss_points",
+               "gimic_b200_calc_jtensors_grid", "gimic_b200_partition_points", "gimic_b200_partition_grid", "gimic_b200_partition_calc", "gimic_b200_partition_info", "gimic_b200_integrate", "gimic_b200_integrate_batch", "gimic_b200_property", "gimic_b200_property_integrand", "gimic_b200_gauss_points",
                "gimic_b200_mol_geometry", "gimic_b200_mol_summary", "gimic_b200_c2s_rows", "gimic_b200_convert_xdens", "gimic_b200_format_e", "gimic_b200_format_f",
                "gimic_b200_get_stats", "gimic_b200_set_profiling", "gimic_b200_last_error", "gimic_b200_version"]
 
@@ -78,6 +78,11 @@ def lib():
     L.gimic_b200_fields_from_tensors.argtypes = [vp, C.c_long, vp, vp, dp, vp, vp, vp, C.c_int]
     L.gimic_b200_jmod_from_jvec.argtypes = [vp, C.c_long, vp, vp, dp, vp, C.c_int]
     L.gimic_b200_calc_jtensors_grid.argtypes = [vp, C.POINTER(GridStruct), C.c_long, C.c_long, C.c_int, vp, C.c_int]
+    lp = C.POINTER(C.c_long)
+    L.gimic_b200_partition_points.argtypes = [vp, C.c_long, vp, C.c_int, C.c_int, C.c_int, lp]
+    L.gimic_b200_partition_grid.argtypes = [vp, C.POINTER(GridStruct), C.c_int, C.c_int, lp]
+    L.gimic_b200_partition_calc.argtypes = [vp, dp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.gimic_b200_partition_info.argtypes = [vp, lp]
     L.gimic_b200_integrate.argtypes = [vp, C.POINTER(GridStruct), dp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.gimic_b200_integrate_batch.argtypes = [vp, C.c_int, C.POINTER(GridStruct), dp, C.c_int, C.c_int, dp]
     L.gimic_b200_property.argtypes = [vp, C.c_long, vp, vp, vp, C.c_int, dp, C.c_int, C.POINTER(C.c_long), dp, C.c_int]

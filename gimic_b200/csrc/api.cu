@@ -48,15 +48,24 @@ struct Buf {
 
 }  // namespace
 
+struct Plan {                        // one sorted, tiled point set (and this rank's share of it) -- see build_plan()
+    bool valid = false;
+    long n = 0;                      // points of the whole set
+    int rank = 0, nranks = 1;
+    gb::PlanSummary sum{};           // host copy
+    long count() const { return valid ? (long)(sum.pt_hi - sum.pt_lo) : 0; }
+    int ntiles() const { return valid ? sum.thi - sum.tlo : 0; }
+};
+
 struct gimic_b200_ctx {
     int device = 0, nsm = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     gimic_b200_opts opts{};
     gb::HostBasis hb;
     gb::DevBasis db{};
     std::vector<void *> owned;
     int *d_f2user = nullptr;
-    double *d_dens[2] = {nullptr, nullptr};   // dens_t%da / %db in the XDENS layout
+    double *d_dens[2] = {nullptr, nullptr};   // dens_t%da / %db in the XDENS layout (released once every operand set that needs them is built)
     double *d_op[4] = {nullptr, nullptr, nullptr, nullptr};   // contraction operands per spin case
     double *d_opj[4] = {nullptr, nullptr, nullptr, nullptr};  // J = T.B path: one pair-plane (D, P.B) per spin case, for the field in opj_B
     double opj_B[4][3] = {};
@@ -64,14 +73,15 @@ struct gimic_b200_ctx {
     double bbox_lo[3] = {0, 0, 0}; double inv_cell = 1.0;
     size_t pool_max_bytes = (size_t)8 << 30;
     // workspaces
-    Buf keys0, keys1, vals0, vals1, sorttmp, rs, geo, nraw, segs, tiles, panel, fidx, atab, misc, r_in, tens_tmp, f_tmp, shift, jv6, gridbuf, quad;
-    gb::TileInfo *h_info = nullptr; size_t h_info_cap = 0;
-    gb::TileSeg *h_segs = nullptr;
+    Buf keys0, keys1, vals0, vals1, sorttmp, rs, panel, fidx, atab, misc, r_in, r_in2, tens_tmp, tens_tmp2, f_tmp, f_tmp2, shift, jv6, gridbuf, quad;
+    Buf p_seg, p_geo, p_info, p_cnt, p_off, geo, desc, cum, pkeys0, pkeys1, pord0, pord1, tiles, d_summary;   // tile plan (k_prepare.cu)
+    gb::PlanSummary *h_summary = nullptr;   // pinned
+    Plan plan;
     double split_radius = 2.5;   // bohr: tiles wider than this are cut at their largest consecutive gap if that shrinks them
-    gb::TileDesc *h_tiles = nullptr;
     bool profiling = false;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_call[2] = {};
+    cudaEvent_t ev_chunk[4] = {};      // [0,1] results of buffer 0/1 ready (compute stream), [2,3] buffer 0/1 drained (copy stream)
     std::vector<cudaEvent_t> evpool;   // per-batch (basis, contract) stamps, resolved at the end of a call
     gimic_b200_stats stats{};
     std::string mol_path, xdens_path;   // for the legacy set_uhf-after-init path
@@ -82,14 +92,16 @@ struct gimic_b200_ctx {
         for (int i = 0; i < 2; ++i) if (d_dens[i]) cudaFree(d_dens[i]);
         for (int i = 0; i < 4; ++i) if (d_op[i]) cudaFree(d_op[i]);
         for (int i = 0; i < 4; ++i) if (d_opj[i]) cudaFree(d_opj[i]);
-        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &geo, &nraw, &segs, &tiles, &panel, &fidx, &atab, &misc, &r_in, &tens_tmp, &f_tmp, &shift, &jv6, &gridbuf, &quad}) b->release();
-        if (h_info) cudaFreeHost(h_info);
-        if (h_segs) cudaFreeHost(h_segs);
-        if (h_tiles) cudaFreeHost(h_tiles);
+        for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &panel, &fidx, &atab, &misc, &r_in, &r_in2, &tens_tmp, &tens_tmp2, &f_tmp, &f_tmp2,
+                       &shift, &jv6, &gridbuf, &quad, &p_seg, &p_geo, &p_info, &p_cnt, &p_off, &geo, &desc, &cum, &pkeys0, &pkeys1, &pord0, &pord1,
+                       &tiles, &d_summary}) b->release();
+        if (h_summary) cudaFreeHost(h_summary);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : evpool) cudaEventDestroy(e);
         for (auto &e : ev_call) if (e) cudaEventDestroy(e);
+        for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -185,8 +197,11 @@ int init_device(gimic_b200_ctx *c) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
     c->nsm = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->ev_call) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : c->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_summary, sizeof(gb::PlanSummary)));
     // panel pool: one batch (one k_basis + one k_jtensor launch) per ~pool of Phi/dPhi panels.  8 GB is the configuration of the
     // committed ncu captures and launch lists; GIMIC_B200_POOL_MB=24576 (one launch per 2M-point step) measured +1 %.
     c->pool_max_bytes = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, prop.totalGlobalMem / 8));
@@ -194,26 +209,28 @@ int init_device(gimic_b200_ctx *c) {
     return 0;
 }
 
-int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
-    const bool uhf = c->opts.uhf != 0;
+int check_spincase(gimic_b200_ctx *c, int &spincase) {
     if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
-    if (!uhf) {
+    if (!c->opts.uhf) {
         if (spincase == GIMIC_B200_BETA) return fail(GIMIC_B200_ESPIN, "ctensor(): beta current requested, but not open-shell system!");
         if (spincase == GIMIC_B200_SPINDENS) return fail(GIMIC_B200_ESPIN, "ctensor(): spindens requested, but not open-shell system!");
         spincase = GIMIC_B200_ALPHA;
     }
-    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
+    return 0;
+}
+
+// Contraction operands of a spin case.  alpha (and beta) are built from the densities at creation; total / spin density of an
+// open-shell context are alpha +- beta (jtensor.F90:86-88, 97-99: linear in D and P), built on first use.
+int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
+    if (int rc = check_spincase(c, spincase)) return rc;
     if (!c->d_op[spincase]) {
-        const int nbf = c->hb.nbf;
+        if (spincase != GIMIC_B200_TOTAL && spincase != GIMIC_B200_SPINDENS) return fail(GIMIC_B200_EINVAL, "operands of this spin case were not built");
+        const size_t count = (size_t)((c->nq + 1) / 2) * c->plane_stride;
         void *p = nullptr;
-        CUDA_TRY(cudaMalloc(&p, (size_t)((c->nq + 1) / 2) * c->plane_stride * sizeof(double)));
-        const double *A = c->d_dens[0], *Bm = nullptr; double sg = 0.0;
-        if (spincase == GIMIC_B200_BETA) A = c->d_dens[1];
-        if (spincase == GIMIC_B200_TOTAL) { Bm = c->d_dens[1]; sg = 1.0; }       // T_alpha + T_beta (jtensor.F90:86-88), by linearity in D, P
-        if (spincase == GIMIC_B200_SPINDENS) { Bm = c->d_dens[1]; sg = -1.0; }   // T_alpha - T_beta (jtensor.F90:97-99)
-        gb::launch_build_operand((double *)p, nbf, c->ldb, c->plane_stride, A, Bm, sg, c->d_f2user, c->stream);
+        CUDA_TRY(cudaMalloc(&p, count * sizeof(double)));
+        gb::launch_operand_combine((double *)p, c->d_op[GIMIC_B200_ALPHA], c->d_op[GIMIC_B200_BETA], spincase == GIMIC_B200_TOTAL ? 1.0 : -1.0,
+                                   (long)count, c->stream);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->d_op[spincase] = (double *)p;
     }
     *op = c->d_op[spincase];
@@ -223,25 +240,14 @@ int get_operand(gimic_b200_ctx *c, int spincase, const double **op) {
 // Operand of the J = T.B path: the tensor is only ever contracted with B, so P_x, P_y, P_z enter as the single matrix
 // sum_b B_b P_b (jfield.f90:167-184 applied before instead of after the contraction).  Rebuilt when B changes.
 int get_operand_j(gimic_b200_ctx *c, int spincase, const double *B3, const double **op) {
-    const bool uhf = c->opts.uhf != 0;
-    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
-    if (!uhf) {
-        if (spincase == GIMIC_B200_BETA) return fail(GIMIC_B200_ESPIN, "ctensor(): beta current requested, but not open-shell system!");
-        if (spincase == GIMIC_B200_SPINDENS) return fail(GIMIC_B200_ESPIN, "ctensor(): spindens requested, but not open-shell system!");
-        spincase = GIMIC_B200_ALPHA;
-    }
-    if (spincase < 0 || spincase > 3) return fail(GIMIC_B200_EINVAL, "invalid spin case");
+    if (int rc = check_spincase(c, spincase)) return rc;
     const bool same = c->d_opj[spincase] && c->opj_B[spincase][0] == B3[0] && c->opj_B[spincase][1] == B3[1] && c->opj_B[spincase][2] == B3[2];
     if (!same) {
-        const int nbf = c->hb.nbf;
+        const double *full = nullptr;
+        if (int rc = get_operand(c, spincase, &full)) return rc;
         if (!c->d_opj[spincase]) CUDA_TRY(cudaMalloc((void **)&c->d_opj[spincase], (size_t)c->plane_stride * sizeof(double)));
-        const double *A = c->d_dens[0], *Bm = nullptr; double sg = 0.0;
-        if (spincase == GIMIC_B200_BETA) A = c->d_dens[1];
-        if (spincase == GIMIC_B200_TOTAL) { Bm = c->d_dens[1]; sg = 1.0; }
-        if (spincase == GIMIC_B200_SPINDENS) { Bm = c->d_dens[1]; sg = -1.0; }
-        gb::launch_build_operand_j(c->d_opj[spincase], nbf, c->ldb, A, Bm, sg, c->d_f2user, B3, c->stream);
+        gb::launch_operand_j(c->d_opj[spincase], full, c->plane_stride, B3, c->stream);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
         for (int k = 0; k < 3; ++k) c->opj_B[spincase][k] = B3[k];
     }
     *op = c->d_opj[spincase];
@@ -250,6 +256,10 @@ int get_operand_j(gimic_b200_ctx *c, int spincase, const double *B3, const doubl
 
 int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b, bool dens_on_device) {
     gb::finalize_basis(c->hb, c->opts.screening != 0, c->opts.screening_thrs);
+    // With screening off every tile has all nbf functions active: k_jtensor's K-step mask covers 65536 slots per tile.
+    if (!c->opts.screening && c->hb.nbf + 3 * c->hb.natoms > 65536)
+        return fail(GIMIC_B200_EINVAL, "more than 65536 basis-function slots with Advanced.screening off: a tile of points cannot hold all functions; "
+                                       "switch screening on (exact: screened functions are zeros in the reference too)");
     if (int rc = build_device_basis(c)) return rc;
     const size_t nn = (size_t)c->hb.nbf * c->hb.nbf;
     std::vector<double> cart[2];
@@ -270,32 +280,44 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
     c->nq = gb::NQ;
     c->ldb = c->hb.nbf;
     c->plane_stride = 2LL * c->hb.nbf * c->ldb;          // doubles per pair-plane [nbf][ldb][2]
+    // The densities are only needed to build the alpha / beta operand planes (internal function order, pair-planes); the raw
+    // XDENS-layout copy is released right away (3.2 GB per spin at nbf = 10^4).
     for (int sp = 0; sp < (c->opts.uhf ? 2 : 1); ++sp) {
         const double *src = sp ? dens_b : dens_a;
         if (!src) return fail(GIMIC_B200_EINVAL, sp ? "open-shell context needs beta densities" : "densities missing");
-        CUDA_TRY(cudaMalloc((void **)&c->d_dens[sp], 4 * nn * sizeof(double)));
-        CUDA_TRY(cudaMemcpy(c->d_dens[sp], src, 4 * nn * sizeof(double), dens_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        const double *d_src = src;
+        if (!dens_on_device) {
+            CUDA_TRY(cudaMalloc((void **)&c->d_dens[sp], 4 * nn * sizeof(double)));
+            CUDA_TRY(cudaMemcpy(c->d_dens[sp], src, 4 * nn * sizeof(double), cudaMemcpyHostToDevice));
+            d_src = c->d_dens[sp];
+        }
+        void *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, (size_t)((c->nq + 1) / 2) * c->plane_stride * sizeof(double)));
+        c->d_op[sp ? GIMIC_B200_BETA : GIMIC_B200_ALPHA] = (double *)p;
+        gb::launch_build_operand((double *)p, c->hb.nbf, c->ldb, c->plane_stride, d_src, nullptr, 0.0, c->d_f2user, c->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->d_dens[sp]) { cudaFree(c->d_dens[sp]); c->d_dens[sp] = nullptr; }
     }
     return 0;
 }
 
 // ---- the batched tensor pipeline ------------------------------------------------------------------
-// d_r: device, 3 x n (AoS).  d_tens: device 9 x n.  d_edens: device n or null.
-// jB3 / d_jvec non-null: the J = T.B path (3 x n output, operands (D, P.B)); d_tens is then unused.
-int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, double *d_tens, double *d_edens,
-                const double *jB3 = nullptr, double *d_jvec = nullptr) {
+// build_plan: Hilbert sort of the points, tiles (with gap splitting), per-tile active-set sizes, this rank's equal-cost share
+// of the tile list, panel-pool batches and the processing order -- all on the device; the host reads one PlanSummary.
+// d_r: device, 3 x n (AoS).
+int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nranks) {
     using namespace gb;
-    if (n <= 0) return 0;
+    c->plan.valid = false;
+    if (n <= 0) return fail(GIMIC_B200_EINVAL, "no points");
     if (n > 2000000000L) return fail(GIMIC_B200_EINVAL, "more than 2e9 points in one call");
-    const double *op = nullptr;
-    const bool jpath = d_jvec != nullptr;
-    if (int rc = jpath ? get_operand_j(c, spincase, jB3, &op) : get_operand(c, spincase, &op)) return rc;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(GIMIC_B200_EINVAL, "rank / nranks out of range");
     cudaStream_t st = c->stream;
-    int ntiles = (int)((n + MT - 1) / MT);
     const bool prof = c->profiling;
+    const long nrun0 = (n + MT - 1) / MT;
 
     if (c->keys0.ensure(n * 8) || c->keys1.ensure(n * 8) || c->vals0.ensure(n * 4) || c->vals1.ensure(n * 4) ||
-        c->rs.ensure((size_t)3 * n * 8) || c->misc.ensure(256))
+        c->rs.ensure((size_t)3 * n * 8) || c->misc.ensure(256) || c->d_summary.ensure(sizeof(PlanSummary)))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed");
     size_t tb = sort_temp_bytes(n);
     if (c->sorttmp.ensure(tb)) return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (sort)");
@@ -309,107 +331,95 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     if (prof) cudaEventRecord(c->ev[1], st);
     c->stats.launches += 4;
 
-    // Tiles: runs of MT consecutive points along the Hilbert curve.  A run that straddles a re-entry of the
-    // curve (thin / planar point sets, cluster boundaries) is cut at its largest consecutive gap; a few rounds.
-    std::vector<TileSeg> segs(ntiles);
-    for (int t = 0; t < ntiles; ++t) segs[t] = TileSeg{t * MT, (int)std::min<long>(MT, n - (long)t * MT)};
-    for (int round = 0; round < 8; ++round) {
-        ntiles = (int)segs.size();
-        if ((size_t)ntiles > c->h_info_cap) {
-            if (c->h_info) cudaFreeHost(c->h_info);
-            if (c->h_segs) cudaFreeHost(c->h_segs);
-            if (c->h_tiles) cudaFreeHost(c->h_tiles);
-            c->h_info = nullptr; c->h_segs = nullptr; c->h_tiles = nullptr; c->h_info_cap = 0;   // a failed allocation below must not leave stale pointers
-            const size_t cap = (size_t)ntiles + ntiles / 4 + 64;
-            CUDA_TRY(cudaMallocHost((void **)&c->h_info, cap * sizeof(TileInfo)));
-            CUDA_TRY(cudaMallocHost((void **)&c->h_segs, cap * sizeof(TileSeg)));
-            CUDA_TRY(cudaMallocHost((void **)&c->h_tiles, cap * sizeof(TileDesc)));
-            c->h_info_cap = cap;
-        }
-        if (c->geo.ensure((size_t)ntiles * sizeof(TileGeo)) || c->nraw.ensure((size_t)ntiles * sizeof(TileInfo)) ||
-            c->segs.ensure((size_t)ntiles * sizeof(TileSeg)) || c->tiles.ensure((size_t)ntiles * sizeof(TileDesc)))
+    // Gap splitting rarely adds more than a few per cent of tiles; if a thin point set needs more, the summary says so and
+    // the plan is rebuilt with room for every possible piece.
+    const long long pool_doubles = (long long)(c->pool_max_bytes / 8);
+    long cap = nrun0 + nrun0 / 2 + 1024;
+    PlanSummary &S = c->plan.sum;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        cap = std::min<long>(cap, nrun0 * MAXSUB);
+        if (c->p_seg.ensure((size_t)nrun0 * MAXSUB * sizeof(TileSeg)) || c->p_geo.ensure((size_t)nrun0 * MAXSUB * sizeof(TileGeo)) ||
+            c->p_info.ensure((size_t)nrun0 * MAXSUB * sizeof(TileInfo)) || c->p_cnt.ensure((size_t)nrun0 * 4) || c->p_off.ensure((size_t)(nrun0 + 1) * 4) ||
+            c->geo.ensure((size_t)cap * sizeof(TileGeo)) || c->desc.ensure((size_t)cap * sizeof(TileDesc)) || c->cum.ensure((size_t)(cap + 1) * sizeof(TileCum)) ||
+            c->pkeys0.ensure((size_t)cap * 8) || c->pkeys1.ensure((size_t)cap * 8) || c->pord0.ensure((size_t)cap * 4) || c->pord1.ensure((size_t)cap * 4) ||
+            c->tiles.ensure((size_t)cap * sizeof(TileDesc)))
             return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tiles)");
-        std::copy(segs.begin(), segs.end(), c->h_segs);
-        CUDA_TRY(cudaMemcpyAsync(c->segs.p, c->h_segs, (size_t)ntiles * sizeof(TileSeg), cudaMemcpyHostToDevice, st));
-        launch_tile_count(c->db, rsx, rsy, rsz, c->segs.as<TileSeg>(), ntiles, c->geo.as<TileGeo>(), c->nraw.as<TileInfo>(), st);
+        PlanBuffers pb;
+        pb.slot_seg = c->p_seg.as<TileSeg>(); pb.slot_geo = c->p_geo.as<TileGeo>(); pb.slot_info = c->p_info.as<TileInfo>();
+        pb.cnt = c->p_cnt.as<int>(); pb.off = c->p_off.as<int>(); pb.geo = c->geo.as<TileGeo>(); pb.desc = c->desc.as<TileDesc>();
+        pb.cum = c->cum.as<TileCum>(); pb.keys0 = c->pkeys0.as<unsigned long long>(); pb.keys1 = c->pkeys1.as<unsigned long long>();
+        pb.ord0 = c->pord0.as<int>(); pb.ord1 = c->pord1.as<int>(); pb.tiles = c->tiles.as<TileDesc>();
+        pb.summary = c->d_summary.as<PlanSummary>(); pb.cap = (int)cap;
+        launch_plan_tiles(c->db, rsx, rsy, rsz, n, c->split_radius, rank, nranks, pool_doubles, pb, st);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(c->h_info, c->nraw.p, (size_t)ntiles * sizeof(TileInfo), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        c->stats.launches += 1;
-        std::vector<TileSeg> next;
-        next.reserve(segs.size() + 16);
-        bool any = false;
-        for (int t = 0; t < ntiles; ++t) {
-            const TileInfo &ti = c->h_info[t];
-            const TileSeg &sg = segs[t];
-            if (round < 7 && sg.npts >= 16 && ti.nraw > 0 && ti.rho > c->split_radius && ti.gmax > 0.5f * ti.rho) {
-                next.push_back(TileSeg{sg.pt0, ti.imax + 1});
-                next.push_back(TileSeg{sg.pt0 + ti.imax + 1, sg.npts - ti.imax - 1});
-                any = true;
-            } else next.push_back(sg);
+        c->stats.launches += 6;
+        CUDA_TRY(cudaMemcpyAsync(c->h_summary, pb.summary, sizeof(PlanSummary), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));          // the ONE host round trip of a plan
+        S = *c->h_summary;
+        if (!S.overflow) {
+            if (S.nbatch > MAX_BATCH) return fail(GIMIC_B200_EINVAL, "point set needs more than 4096 panel-pool batches: pass fewer points per call or raise GIMIC_B200_POOL_MB");
+            const int nt = S.thi - S.tlo;
+            if (nt > 0) {
+                const size_t sb = plan_sort_temp_bytes(nt);
+                if (c->sorttmp.ensure(sb)) return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tile sort)");
+                launch_plan_order(pb, S.tlo, nt, c->sorttmp.p, sb, st);
+                CUDA_TRY(cudaGetLastError());
+                c->stats.launches += 2;
+            }
+            break;
         }
-        if (!any) break;
-        segs.swap(next);
+        if (attempt == 1) return fail(GIMIC_B200_EINVAL, "tile plan overflow");
+        cap = nrun0 * MAXSUB;
     }
     if (prof) cudaEventRecord(c->ev[2], st);
+    c->plan.valid = true; c->plan.n = n; c->plan.rank = rank; c->plan.nranks = nranks;
+    if (prof) {
+        CUDA_TRY(cudaEventSynchronize(c->ev[2]));
+        float m = 0;
+        cudaEventElapsedTime(&m, c->ev[0], c->ev[1]); c->stats.ms_sort += m;
+        cudaEventElapsedTime(&m, c->ev[1], c->ev[2]); c->stats.ms_tiles += m;
+    }
+    return 0;
+}
 
-    // host: tile descriptors, split into batches that fit the panel pool
-    size_t max_tile = 0, total = 0;
-    for (int t = 0; t < ntiles; ++t) {
-        int nact = (c->h_info[t].nraw + 7) / 8 * 8;
-        size_t d = (size_t)4 * nact * LDP;
-        max_tile = std::max(max_tile, d); total += d;
-    }
-    size_t pool_doubles = std::max(max_tile, std::min(total, c->pool_max_bytes / 8));
-    std::vector<int> batch_start(1, 0);
-    size_t off = 0, foff = 0, fidx_max = 0, aoff = 0, atab_max = 0;
-    double sum_nact = 0, flops = 0, useful = 0;
-    const bool giao = c->opts.giao != 0;
-    for (int t = 0; t < ntiles; ++t) {
-        TileDesc &td = c->h_tiles[t];
-        td.pt0 = segs[t].pt0; td.npts = segs[t].npts; td.geo = t; td.nruns = c->h_info[t].natom;
-        td.nraw = c->h_info[t].nraw; td.nact = (td.nraw + 7) / 8 * 8;
-        td.nreal = c->h_info[t].nreal; td.nn = (td.nreal + 7) / 8 * 8;
-        if (td.nact > 65536) return fail(GIMIC_B200_EINVAL, "more than 65536 active basis-function slots in one tile of points (k_jtensor's K-step mask)");
-        size_t d = (size_t)4 * td.nact * LDP;
-        if (off + d > pool_doubles) { batch_start.push_back(t); fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff); off = 0; foff = 0; aoff = 0; }
-        td.panel_off = (long long)off; td.fidx_off = (long long)foff; td.atab_off = (long long)aoff;
-        off += d; foff += td.nact + td.nn; aoff += td.nruns;
-        sum_nact += td.nact;
-        flops += 2.0 * MT * (jpath ? 2 : c->nq) * (double)td.nact * td.nn;   // DMMA: K runs over the nact slots, N over the nn columns (multiples of 8)
-        if (giao) flops += 2.0 * MT * (jpath ? 1.0 : 3.0) * (double)td.nn * td.nruns;   // GIAO taps: 3 (J path: 1) DFMA per accumulator element per active atom
-        useful += 2.0 * td.npts * (jpath ? 2 : c->nq) * (double)td.nreal * td.nreal;
-        if (giao) useful += 2.0 * td.npts * (jpath ? 1.0 : 3.0) * (double)td.nreal * td.nruns;
-    }
-    fidx_max = std::max(fidx_max, foff); atab_max = std::max(atab_max, aoff);
-    batch_start.push_back(ntiles);
-    // inside a batch the contraction kernel pulls tiles from an atomic counter: longest first (cost ~ nact^2)
-    static const int sched = [] { const char *e = std::getenv("GIMIC_B200_SCHED"); return e ? std::atoi(e) : 0; }();
-    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
-        TileDesc *t0 = c->h_tiles + batch_start[b], *t1 = c->h_tiles + batch_start[b + 1];
-        if (sched == 0) {          // longest first
-            std::stable_sort(t0, t1, [](const TileDesc &x, const TileDesc &y) { return x.nact > y.nact; });
-        } else if (sched == 2) {   // Hilbert order, except that the heaviest 1/8 of the tiles go first (tail protection)
-            std::vector<int> v; for (TileDesc *t = t0; t < t1; ++t) v.push_back(t->nact);
-            if (!v.empty()) {
-                std::nth_element(v.begin(), v.begin() + v.size() / 8, v.end(), std::greater<int>());
-                const int cut = v[v.size() / 8];
-                std::stable_partition(t0, t1, [cut](const TileDesc &x) { return x.nact > cut; });
-            }
-        }                          // sched == 1: plain Hilbert order
-    }
-    if (c->panel.ensure(std::max<size_t>(pool_doubles, 2) * 8) || c->fidx.ensure(std::max<size_t>(fidx_max, 1) * 4) ||
-        c->atab.ensure(std::max<size_t>(atab_max, 1) * sizeof(TileAtom)))
+// What one pass over the planned tiles writes (device pointers; any may be null).  jpath: contract with B before the GEMM
+// (operands (D, P.B), jvec / jmod / edens only).
+struct Outputs {
+    double *tens = nullptr, *jvec = nullptr, *jmod = nullptr, *acid = nullptr, *edens = nullptr;
+    const double *B3 = nullptr;       // host, needed for jvec / jmod
+    bool jpath = false;
+};
+
+// exec_plan: basis panels + contraction for the planned tiles, batch by batch.  compact == false: results go to the caller's
+// point order (row perm[p] of the outputs, which hold plan.n rows); compact == true: row p - pt_lo (plan.count() rows).
+int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact) {
+    using namespace gb;
+    const Plan &P = c->plan;
+    if (!P.valid) return fail(GIMIC_B200_EINVAL, "no tile plan: call gimic_b200_partition_points / _grid first");
+    const double *op = nullptr;
+    if (int rc = o.jpath ? get_operand_j(c, spincase, o.B3, &op) : get_operand(c, spincase, &op)) return rc;
+    if ((o.jvec || o.jmod) && !o.B3) return fail(GIMIC_B200_EINVAL, "jvec / jmod need the magnetic field direction");
+    const PlanSummary &S = P.sum;
+    const int nt = S.thi - S.tlo;
+    if (nt <= 0) return 0;
+    cudaStream_t st = c->stream;
+    const bool prof = c->profiling, giao = c->opts.giao != 0;
+    const long n = P.n;
+    const double *rsx = c->rs.as<double>(), *rsy = rsx + n, *rsz = rsy + n;
+    const long long pool_cap = (long long)(c->pool_max_bytes / 8);
+    const size_t pool_doubles = (size_t)std::max<long long>(2, std::min<long long>(S.panel_range, pool_cap + S.max_tile_panel));
+    // index / atom-table pools by their bound relative to the panel pool: a tile holds 4*LDP panel doubles per K slot, at most
+    // 2 index ints per slot (slot -> function, column -> slot) and at most one atom run per slot
+    const size_t slots = pool_doubles / (4 * LDP) + 16;
+    if (c->panel.ensure(pool_doubles * 8) || c->fidx.ensure(2 * slots * 4) || c->atab.ensure(slots * sizeof(TileAtom)))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
-    CUDA_TRY(cudaMemcpyAsync(c->tiles.p, c->h_tiles, (size_t)ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
-
-    const size_t nbatch = batch_start.size() - 1;
-    if (prof) while (c->evpool.size() < 3 * nbatch) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); c->evpool.push_back(e); }
-    for (size_t b = 0; b < nbatch; ++b) {
-        const int t0 = batch_start[b], nb = batch_start[b + 1] - t0;
+    const int nbatch = S.nbatch;
+    if (prof) while (c->evpool.size() < 3 * (size_t)nbatch) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); c->evpool.push_back(e); }
+    for (int b = 0; b < nbatch; ++b) {
+        const int t0 = S.batch_start[b] - S.tlo, nb = S.batch_start[b + 1] - S.batch_start[b];
         if (nb <= 0) continue;
         if (prof) cudaEventRecord(c->evpool[3 * b], st);
-        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(),
+        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, S.max_nruns, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(),
                      giao ? c->atab.as<TileAtom>() : nullptr, st);
         if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
@@ -417,10 +427,11 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
         a.tiles = c->tiles.as<TileDesc>() + t0; a.ntiles = nb; a.counter = c->misc.as<int>();
         a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>(); a.atab_pool = c->atab.as<TileAtom>(); a.geo = c->geo.as<TileGeo>();
         a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
-        a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = perm; a.tens = d_tens; a.edens = d_edens;
-        a.jvec = d_jvec; for (int k = 0; k < 3; ++k) a.B[k] = jpath ? jB3[k] : 0.0;
+        a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = compact ? nullptr : c->vals1.as<int>(); a.out_base = compact ? S.pt_lo : 0;
+        a.tens = o.tens; a.edens = o.edens; a.jvec = o.jvec; a.jmod = o.jmod; a.acid = o.acid; a.jpath = o.jpath ? 1 : 0;
+        for (int k = 0; k < 3; ++k) a.B[k] = o.B3 ? o.B3[k] : 0.0;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
-        launch_jtensor(a, c->opts.giao != 0, c->nsm, st);
+        launch_jtensor(a, giao, c->nsm, st);
         CUDA_TRY(cudaGetLastError());
         c->stats.launches += 2;
         c->stats.contract_launches += 1;
@@ -429,18 +440,30 @@ int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, doub
     if (prof) {
         CUDA_TRY(cudaStreamSynchronize(st));
         float m = 0;
-        cudaEventElapsedTime(&m, c->ev[0], c->ev[1]); c->stats.ms_sort += m;
-        cudaEventElapsedTime(&m, c->ev[1], c->ev[2]); c->stats.ms_tiles += m;
-        for (size_t b = 0; b < nbatch; ++b) {
-            if (batch_start[b + 1] - batch_start[b] <= 0) continue;
+        for (int b = 0; b < nbatch; ++b) {
+            if (S.batch_start[b + 1] - S.batch_start[b] <= 0) continue;
             cudaEventElapsedTime(&m, c->evpool[3 * b], c->evpool[3 * b + 1]); c->stats.ms_basis += m;
             cudaEventElapsedTime(&m, c->evpool[3 * b + 1], c->evpool[3 * b + 2]); c->stats.ms_contract += m;
         }
     }
-    c->stats.n_points += n; c->stats.n_tiles += ntiles; c->stats.sum_nact += sum_nact; c->stats.executed_flops += flops; c->stats.useful_flops += useful;
+    const double tapw = giao ? (o.jpath ? 1.0 : 3.0) : 0.0, planes = o.jpath ? 2.0 : 4.0;
+    c->stats.n_points += P.count(); c->stats.n_tiles += nt; c->stats.sum_nact += S.sum_nact;
+    c->stats.executed_flops += (o.jpath ? S.flops2 : S.flops4) + tapw * S.taps;
+    c->stats.useful_flops += planes * S.useful_mm + tapw * S.useful_taps;
     const double nbf = c->hb.nbf;
-    c->stats.dense_flops += (double)n * (c->opts.giao ? 14.0 * nbf * nbf + 56.0 * nbf : 8.0 * nbf * nbf + 20.0 * nbf);
+    c->stats.dense_flops += (double)P.count() * (c->opts.giao ? 14.0 * nbf * nbf + 56.0 * nbf : 8.0 * nbf * nbf + 20.0 * nbf);
     return 0;
+}
+
+// one plan over all n points on this device, results in the caller's point order
+int run_tensors(gimic_b200_ctx *c, long n, const double *d_r, int spincase, const Outputs &o) {
+    if (n <= 0) return 0;
+    int sc = spincase;
+    if (int rc = check_spincase(c, sc)) return rc;       // before any work is queued
+    if (int rc = build_plan(c, n, d_r, 0, 1)) return rc;
+    const int rc = exec_plan(c, spincase, o, false);
+    c->plan.valid = false;                               // the workspaces are reused by the next call
+    return rc;
 }
 
 void reset_stats(gimic_b200_ctx *c) { c->stats = gimic_b200_stats{}; }
@@ -562,6 +585,49 @@ int gimic_b200_atom_coords(gimic_b200_handle h, double *xyz) {
 int gimic_b200_set_profiling(gimic_b200_handle h, int enable) { if (!h) return fail(GIMIC_B200_EINVAL, "null handle"); h->profiling = enable != 0; return 0; }
 int gimic_b200_get_stats(gimic_b200_handle h, gimic_b200_stats *out) { if (!h || !out) return fail(GIMIC_B200_EINVAL, "null argument"); *out = h->stats; return 0; }
 
+}  // extern "C" (reopened below)
+
+namespace {
+// One pass over `n` device-resident points: tensors and/or derived fields, all outputs device pointers in the caller's order.
+// divj (no reference semantics at this commit): central differences of J = T.B at r +- h e_a, 6n more points on the J path.
+int fields_on_device(gimic_b200_ctx *c, long n, const double *d_r, const double *B3, int spincase, double *d_tens, double *d_jvec,
+                     double *d_jmod, double *d_acid, double *d_edens, double *d_divj, double divj_h) {
+    cudaStream_t st = c->stream;
+    // Only J (and |J|, rho) wanted: contract with B before instead of after the GEMM -- 2 operand planes instead of 4 and one
+    // tap weight per row instead of three (compute_jvectors, jfield.f90:167-184, folded into the contraction).
+    Outputs o;
+    o.jpath = !d_tens && !d_acid && (d_jvec || d_jmod);
+    o.tens = d_tens; o.jvec = d_jvec; o.jmod = d_jmod; o.acid = d_acid; o.edens = d_edens; o.B3 = B3;
+    if (d_tens || d_jvec || d_jmod || d_acid || d_edens) {
+        if (!o.jpath && !d_tens && !d_acid && !d_jvec && !d_jmod) {       // edens alone: the cheapest pass that forms rho
+            static const double z3[3] = {0, 0, 0};
+            o.jpath = true; if (!o.B3) o.B3 = z3;
+        }
+        if (int rc = run_tensors(c, n, d_r, spincase, o)) return rc;
+    }
+    if (d_divj) {
+        const double hstep = divj_h > 0 ? divj_h : 1e-3;
+        if (c->shift.ensure((size_t)18 * n * 8) || c->jv6.ensure((size_t)18 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (divj)");
+        double *r6 = c->shift.as<double>(), *v6 = c->jv6.as<double>();
+        gb::launch_shift_points(n, d_r, hstep, r6, st);
+        gimic_b200_stats keep = c->stats;
+        Outputs o6; o6.jpath = true; o6.jvec = v6; o6.B3 = B3;
+        if (int rc = run_tensors(c, 6 * n, r6, spincase, o6)) return rc;
+        keep.launches = c->stats.launches; c->stats = keep;   // statistics describe the primary pass only
+        gb::launch_divj(n, v6, hstep, d_divj, st);
+        c->stats.launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Host buffers: the points are processed in chunks of the caller's order so that the device->host copy of chunk k (copy
+// stream, pinned or pageable destination) overlaps the contraction of chunk k+1; two sets of device staging buffers.
+constexpr long CHUNK_POINTS = 1L << 21;
+}  // namespace
+
+extern "C" {
+
 int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const double *B3, int spincase, double *tens, double *jvec,
                            double *jmod, double *acid, double *edens, double *divj, double divj_h, int flags) {
     if (!c || (n > 0 && !r)) return fail(GIMIC_B200_EINVAL, "null argument");
@@ -570,65 +636,47 @@ int gimic_b200_calc_fields(gimic_b200_handle c, long n, const double *r, const d
     CUDA_TRY(cudaSetDevice(c->device));
     reset_stats(c);
     if (n == 0) return 0;
+    { int sc = spincase; if (int rc = check_spincase(c, sc)) return rc; }
     const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->stream, cs = c->copy_stream;
     cudaEventRecord(c->ev_call[0], st);
-    const double *d_r = nullptr;
-    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
-    // Only J (and |J|, rho) wanted: contract with B before instead of after the GEMM -- 2 operand planes instead of 4 and one
-    // tap weight per row instead of three (compute_jvectors, jfield.f90:167-184, folded into the contraction).
-    const bool jpath = !tens && !acid && !divj && (jvec || jmod);
-    double *d_tens = tens;
-    if (!jpath && (!dev || !tens)) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
-    // scalar/vector field outputs on the device
-    const size_t nf = (size_t)n;
-    double *d_jvec = jvec, *d_jmod = jmod, *d_acid = acid, *d_edens = edens, *d_divj = divj;
-    if (!dev) {
-        if (c->f_tmp.ensure(nf * 8 * 7)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (fields)");
-        double *f = c->f_tmp.as<double>();
-        d_jvec = jvec ? f : nullptr; d_jmod = jmod ? f + 3 * nf : nullptr; d_acid = acid ? f + 4 * nf : nullptr;
-        d_edens = edens ? f + 5 * nf : nullptr; d_divj = divj ? f + 6 * nf : nullptr;
-    }
-    if (jpath) {
-        if (!d_jvec) {   // |J| alone: J goes to scratch
-            if (c->jv6.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (jvec)");
-            d_jvec = c->jv6.as<double>();
+    if (dev) {
+        if (int rc = fields_on_device(c, n, r, B3, spincase, tens, jvec, jmod, acid, edens, divj, divj_h)) return rc;
+    } else {
+        const long chunk = std::min<long>(n, CHUNK_POINTS);
+        const size_t nf = (size_t)chunk;
+        Buf *rin[2] = {&c->r_in, &c->r_in2}, *tt[2] = {&c->tens_tmp, &c->tens_tmp2}, *ft[2] = {&c->f_tmp, &c->f_tmp2};
+        const int nbuf = n > chunk ? 2 : 1;
+        for (int k = 0; k < nbuf; ++k)
+            if (rin[k]->ensure(nf * 24) || (tens && tt[k]->ensure(nf * 72)) || ft[k]->ensure(nf * 8 * 7)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (staging)");
+        int it = 0;
+        for (long lo = 0; lo < n; lo += chunk, ++it) {
+            const long m = std::min<long>(chunk, n - lo);
+            const int k = it & 1;
+            if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[2 + k], 0));     // buffer k drained by the copy stream
+            double *d_r = rin[k]->as<double>();
+            CUDA_TRY(cudaMemcpyAsync(d_r, r + 3 * lo, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+            double *f = ft[k]->as<double>();
+            double *d_tens = tens ? tt[k]->as<double>() : nullptr;
+            double *d_jvec = jvec ? f : nullptr, *d_jmod = jmod ? f + 3 * nf : nullptr, *d_acid = acid ? f + 4 * nf : nullptr,
+                   *d_edens = edens ? f + 5 * nf : nullptr, *d_divj = divj ? f + 6 * nf : nullptr;
+            if (int rc = fields_on_device(c, m, d_r, B3, spincase, d_tens, d_jvec, d_jmod, d_acid, d_edens, d_divj, divj_h)) return rc;
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[k], st));
+            CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_chunk[k], 0));
+            if (tens) CUDA_TRY(cudaMemcpyAsync(tens + 9 * lo, d_tens, (size_t)m * 72, cudaMemcpyDeviceToHost, cs));
+            if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec + 3 * lo, d_jvec, (size_t)m * 24, cudaMemcpyDeviceToHost, cs));
+            if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod + lo, d_jmod, (size_t)m * 8, cudaMemcpyDeviceToHost, cs));
+            if (acid) CUDA_TRY(cudaMemcpyAsync(acid + lo, d_acid, (size_t)m * 8, cudaMemcpyDeviceToHost, cs));
+            if (edens) CUDA_TRY(cudaMemcpyAsync(edens + lo, d_edens, (size_t)m * 8, cudaMemcpyDeviceToHost, cs));
+            if (divj) CUDA_TRY(cudaMemcpyAsync(divj + lo, d_divj, (size_t)m * 8, cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[2 + k], cs));
         }
-        if (int rc = run_tensors(c, n, d_r, spincase, nullptr, d_edens, B3, d_jvec)) return rc;
-        if (d_jmod) { gb::launch_jmod(n, d_r, d_jvec, B3, d_jmod, st); c->stats.launches += 1; }
-        if (!jvec) d_jvec = nullptr;
-    } else if (int rc = run_tensors(c, n, d_r, spincase, d_tens, d_edens)) return rc;
-    if (c->profiling) cudaEventRecord(c->ev[0], st);
-    if (!jpath && (d_jvec || d_jmod || d_acid)) {
-        const double zero3[3] = {0, 0, 0};
-        gb::launch_fields(n, d_r, d_tens, B3 ? B3 : zero3, d_jvec, d_jmod, d_acid, st);
-        c->stats.launches += 1;
-    }
-    if (c->profiling) { cudaEventRecord(c->ev[1], st); cudaEventSynchronize(c->ev[1]); float m = 0; cudaEventElapsedTime(&m, c->ev[0], c->ev[1]); c->stats.ms_fields += m; }
-    if (d_divj) {
-        // div J by central differences of J = T.B at r +- h e_a: 6 more tensor passes (no reference semantics at this commit)
-        const double hstep = divj_h > 0 ? divj_h : 1e-3;
-        if (c->shift.ensure((size_t)18 * n * 8) || c->jv6.ensure((size_t)(54 + 18) * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (divj)");
-        double *r6 = c->shift.as<double>(), *t6 = c->jv6.as<double>(), *v6 = t6 + (size_t)54 * n;
-        gb::launch_shift_points(n, d_r, hstep, r6, st);
-        gimic_b200_stats keep = c->stats;
-        if (int rc = run_tensors(c, 6 * n, r6, spincase, t6, nullptr)) return rc;
-        keep.launches = c->stats.launches; c->stats = keep;   // statistics describe the primary pass only
-        gb::launch_fields(6 * n, r6, t6, B3, v6, nullptr, nullptr, st);
-        gb::launch_divj(n, v6, hstep, d_divj, st);
-        c->stats.launches += 3;
-    }
-    CUDA_TRY(cudaGetLastError());
-    if (!dev) {
-        if (tens) CUDA_TRY(cudaMemcpyAsync(tens, d_tens, (size_t)9 * n * 8, cudaMemcpyDeviceToHost, st));
-        if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec, d_jvec, nf * 24, cudaMemcpyDeviceToHost, st));
-        if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod, d_jmod, nf * 8, cudaMemcpyDeviceToHost, st));
-        if (acid) CUDA_TRY(cudaMemcpyAsync(acid, d_acid, nf * 8, cudaMemcpyDeviceToHost, st));
-        if (edens) CUDA_TRY(cudaMemcpyAsync(edens, d_edens, nf * 8, cudaMemcpyDeviceToHost, st));
-        if (divj) CUDA_TRY(cudaMemcpyAsync(divj, d_divj, nf * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[2], 0));
+        if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[3], 0));
     }
     cudaEventRecord(c->ev_call[1], st);
     CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(cs));
     cudaEventElapsedTime(&c->stats.ms_total, c->ev_call[0], c->ev_call[1]);
     return 0;
 }
@@ -691,20 +739,135 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g,
     if (n == 0) return 0;
     CUDA_TRY(cudaSetDevice(c->device));
     reset_stats(c);
+    { int sc = spincase; if (int rc = check_spincase(c, sc)) return rc; }
     const double *ob, *p0, *p1, *p2, *w0;
     if (int rc = grid_upload(c, g, &ob, &p0, &p1, &p2, &w0)) return rc;
-    cudaEventRecord(c->ev_call[0], c->stream);
-    if (c->r_in.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid points)");
-    gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], lo, hi, c->r_in.as<double>(), c->stream);
-    c->stats.launches += 1;
+    cudaStream_t st = c->stream, cs = c->copy_stream;
+    cudaEventRecord(c->ev_call[0], st);
     const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
-    double *d_tens = tens;
-    if (!dev) { if (c->tens_tmp.ensure((size_t)9 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (tensors)"); d_tens = c->tens_tmp.as<double>(); }
-    if (int rc = run_tensors(c, n, c->r_in.as<double>(), spincase, d_tens, nullptr)) return rc;
-    if (!dev) CUDA_TRY(cudaMemcpyAsync(tens, d_tens, (size_t)9 * n * 8, cudaMemcpyDeviceToHost, c->stream));
-    cudaEventRecord(c->ev_call[1], c->stream);
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (dev) {
+        if (c->r_in.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid points)");
+        gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], lo, hi, c->r_in.as<double>(), st);
+        c->stats.launches += 1;
+        Outputs o; o.tens = tens;
+        if (int rc = run_tensors(c, n, c->r_in.as<double>(), spincase, o)) return rc;
+    } else {
+        // host output: chunks of the flat index range, the copy of chunk k overlaps the contraction of chunk k+1 (see calc_fields)
+        const long chunk = std::min<long>(n, CHUNK_POINTS);
+        Buf *rin[2] = {&c->r_in, &c->r_in2}, *tt[2] = {&c->tens_tmp, &c->tens_tmp2};
+        const int nbuf = n > chunk ? 2 : 1;
+        for (int k = 0; k < nbuf; ++k)
+            if (rin[k]->ensure((size_t)chunk * 24) || tt[k]->ensure((size_t)chunk * 72)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (staging)");
+        int it = 0;
+        for (long a = lo; a < hi; a += chunk, ++it) {
+            const long m = std::min<long>(chunk, hi - a);
+            const int k = it & 1;
+            if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[2 + k], 0));
+            gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], a, a + m, rin[k]->as<double>(), st);
+            c->stats.launches += 1;
+            Outputs o; o.tens = tt[k]->as<double>();
+            if (int rc = run_tensors(c, m, rin[k]->as<double>(), spincase, o)) return rc;
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[k], st));
+            CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_chunk[k], 0));
+            CUDA_TRY(cudaMemcpyAsync(tens + 9 * (a - lo), o.tens, (size_t)m * 72, cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaEventRecord(c->ev_chunk[2 + k], cs));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[2], 0));
+        if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[3], 0));
+    }
+    cudaEventRecord(c->ev_call[1], st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(cs));
     cudaEventElapsedTime(&c->stats.ms_total, c->ev_call[0], c->ev_call[1]);
+    return 0;
+}
+
+// ---- cost-balanced partition (multi-GPU) -----------------------------------------------------------------------------------
+// The reference splits the flat point index into equal-count contiguous slabs (schedule(), src/fgimic/parallel.F90:66-84, used
+// by jfield.f90:90-104).  The cost of a point is ~ (active functions)^2, which on a planar molecule differs 5x between slabs
+// near and far from the plane.  Here every rank sorts and tiles the WHOLE point set (identical on all ranks: same input, same
+// deterministic kernels, integer costs), and rank r takes the run of Hilbert-ordered tiles whose cumulative cost lies in
+// [r, r+1) x total / nranks.  The tiles -- hence every result bit -- are the same as in a single-rank run.
+int gimic_b200_partition_points(gimic_b200_handle c, long n, const double *r, int flags, int rank, int nranks, long *count) {
+    if (!c || (n > 0 && !r) || !count) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (n <= 0) return fail(GIMIC_B200_EINVAL, "no points");
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    const double *d_r = nullptr;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
+    if (int rc = build_plan(c, n, d_r, rank, nranks)) return rc;
+    *count = c->plan.count();
+    return 0;
+}
+
+int gimic_b200_partition_grid(gimic_b200_handle c, const gimic_b200_grid *g, int rank, int nranks, long *count) {
+    if (!c || !g || !count) return fail(GIMIC_B200_EINVAL, "null argument");
+    const long n = (long)g->npts[0] * g->npts[1] * g->npts[2];
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    const double *ob, *p0, *p1, *p2, *w0;
+    if (int rc = grid_upload(c, g, &ob, &p0, &p1, &p2, &w0)) return rc;
+    if (c->r_in.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid points)");
+    gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], 0, n, c->r_in.as<double>(), c->stream);
+    c->stats.launches += 1;
+    if (int rc = build_plan(c, n, c->r_in.as<double>(), rank, nranks)) return rc;
+    *count = c->plan.count();
+    return 0;
+}
+
+int gimic_b200_partition_info(gimic_b200_handle c, long *info8) {
+    if (!c || !info8) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (!c->plan.valid) return fail(GIMIC_B200_EINVAL, "no partition: call gimic_b200_partition_points / _grid first");
+    const gb::PlanSummary &S = c->plan.sum;
+    info8[0] = c->plan.n; info8[1] = c->plan.count(); info8[2] = S.ntiles; info8[3] = S.thi - S.tlo;
+    info8[4] = S.cost_total; info8[5] = S.cost_range; info8[6] = S.nbatch; info8[7] = S.tlo;
+    return 0;
+}
+
+int gimic_b200_partition_calc(gimic_b200_handle c, const double *B3, int spincase, long *index, double *tens, double *jvec, double *jmod,
+                              double *acid, double *edens, int flags) {
+    if (!c) return fail(GIMIC_B200_EINVAL, "null handle");
+    if (!c->plan.valid) return fail(GIMIC_B200_EINVAL, "no partition: call gimic_b200_partition_points / _grid first");
+    if ((jvec || jmod) && !B3) return fail(GIMIC_B200_EINVAL, "jvec/jmod need the magnetic field direction");
+    CUDA_TRY(cudaSetDevice(c->device));
+    { int sc = spincase; if (int rc = check_spincase(c, sc)) return rc; }
+    const long m = c->plan.count();
+    { const gimic_b200_stats keep = c->stats; reset_stats(c);      // sort / tile times of the partition call stay part of the picture
+      c->stats.ms_sort = keep.ms_sort; c->stats.ms_tiles = keep.ms_tiles; c->stats.launches = keep.launches; }
+    if (m == 0) return 0;
+    const bool dev = (flags & GIMIC_B200_DEVICE_PTR) != 0;
+    cudaStream_t st = c->stream;
+    cudaEventRecord(c->ev_call[0], st);
+    const size_t nf = (size_t)m;
+    Outputs o;
+    o.jpath = !tens && !acid && (jvec || jmod || edens);
+    static const double z3[3] = {0, 0, 0};
+    o.B3 = B3 ? B3 : z3;
+    long *d_index = index;
+    if (dev) { o.tens = tens; o.jvec = jvec; o.jmod = jmod; o.acid = acid; o.edens = edens; }
+    else {
+        if ((tens && c->tens_tmp.ensure(nf * 72)) || c->f_tmp.ensure(nf * 8 * 7)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (partition outputs)");
+        double *f = c->f_tmp.as<double>();
+        o.tens = tens ? c->tens_tmp.as<double>() : nullptr;
+        o.jvec = jvec ? f : nullptr; o.jmod = jmod ? f + 3 * nf : nullptr; o.acid = acid ? f + 4 * nf : nullptr; o.edens = edens ? f + 5 * nf : nullptr;
+        d_index = index ? reinterpret_cast<long *>(f + 6 * nf) : nullptr;
+    }
+    if (o.tens || o.jvec || o.jmod || o.acid || o.edens)
+        if (int rc = exec_plan(c, spincase, o, true)) return rc;
+    if (index) { gb::launch_perm_index(c->vals1.as<int>() + c->plan.sum.pt_lo, m, d_index, st); c->stats.launches += 1; }
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) {
+        if (tens) CUDA_TRY(cudaMemcpyAsync(tens, o.tens, nf * 72, cudaMemcpyDeviceToHost, st));
+        if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec, o.jvec, nf * 24, cudaMemcpyDeviceToHost, st));
+        if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod, o.jmod, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (acid) CUDA_TRY(cudaMemcpyAsync(acid, o.acid, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (edens) CUDA_TRY(cudaMemcpyAsync(edens, o.edens, nf * 8, cudaMemcpyDeviceToHost, st));
+        if (index) CUDA_TRY(cudaMemcpyAsync(index, d_index, nf * 8, cudaMemcpyDeviceToHost, st));
+    }
+    cudaEventRecord(c->ev_call[1], st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev_call[0], c->ev_call[1]);
+    c->stats.ms_total = ms;
     return 0;
 }
 
@@ -766,7 +929,7 @@ int integrate_many(gimic_b200_ctx *c, int ng, const gimic_b200_grid *grids, cons
             c->stats.launches += 1;
         }
     }
-    if (int rc = run_tensors(c, (long)n, d_r, spincase, c->tens_tmp.as<double>(), nullptr)) return rc;
+    { Outputs o; o.tens = c->tens_tmp.as<double>(); if (int rc = run_tensors(c, (long)n, d_r, spincase, o)) return rc; }
     for (int g = 0; g < ng; ++g) {
         const gimic_b200_grid &G = grids[g];
         const int p1 = G.npts[0], p2 = G.npts[1], nrows = (int)(rowoff[g + 1] - rowoff[g]);

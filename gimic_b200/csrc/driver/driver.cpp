@@ -283,6 +283,38 @@ class Run {
         for (const auto &e : errs) if (!e.empty()) throw DriverError(e);
     }
 
+    // Several devices: every device tiles the whole point set and evaluates its equal-COST share of the tiles (gimic_b200_partition_*;
+    // the equal-count slabs of schedule() leave the devices far from the molecule idle on a planar system); the rows come back with
+    // their point indices and are scattered into the caller's arrays -- disjoint index sets, so the host threads exchange nothing.
+    void partitioned(const double *rp, long n, const gimic_b200_grid *g, int spincase, double *tens, double *jvec, double *jmod, double *edens) const {
+        const size_t nd = 1 + peers.size();
+        const double *B = magnet.data();
+        std::vector<std::string> errs(nd);
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < nd; ++d) {
+            gimic_b200_handle h = d == 0 ? ctx->h : peers[d - 1]->h;
+            th.emplace_back([=, &errs] {
+                long cnt = 0;
+                const int rc = g ? gimic_b200_partition_grid(h, g, (int)d, (int)nd, &cnt) : gimic_b200_partition_points(h, n, rp, 0, (int)d, (int)nd, &cnt);
+                if (rc < 0) { errs[d] = gimic_b200_last_error(); return; }
+                if (cnt == 0) return;
+                std::vector<long> idx((size_t)cnt);
+                std::vector<double> t(tens ? (size_t)cnt * 9 : 0), v(jvec ? (size_t)cnt * 3 : 0), m(jmod ? (size_t)cnt : 0), e(edens ? (size_t)cnt : 0);
+                if (gimic_b200_partition_calc(h, B, spincase, idx.data(), tens ? t.data() : nullptr, jvec ? v.data() : nullptr, jmod ? m.data() : nullptr,
+                                              nullptr, edens ? e.data() : nullptr, 0) < 0) { errs[d] = gimic_b200_last_error(); return; }
+                for (long i = 0; i < cnt; ++i) {
+                    const size_t o = (size_t)idx[(size_t)i];
+                    if (tens) for (int k = 0; k < 9; ++k) tens[9 * o + k] = t[(size_t)i * 9 + k];
+                    if (jvec) for (int k = 0; k < 3; ++k) jvec[3 * o + k] = v[(size_t)i * 3 + k];
+                    if (jmod) jmod[o] = m[(size_t)i];
+                    if (edens) edens[o] = e[(size_t)i];
+                }
+            });
+        }
+        for (auto &t : th) t.join();
+        for (const auto &e : errs) if (!e.empty()) throw DriverError(e);
+    }
+
     // calc_jtensors (jfield.f90:62-138) on the whole grid
     std::vector<double> tensors(int spincase) const {
         const long n = grid.n();
@@ -290,17 +322,20 @@ class Run {
         double *tp = t.data();
         if (grid.is_file()) {
             const double *xp = grid.xdata.data();
-            over_devices(n, [=](gimic_b200_handle h, size_t, long lo, long hi) { return gimic_b200_calc_jtensors(h, hi - lo, xp + 3 * lo, spincase, tp + 9 * lo, 0); });
+            if (peers.empty()) check(gimic_b200_calc_jtensors(ctx->h, n, xp, spincase, tp, 0));
+            else partitioned(xp, n, nullptr, spincase, tp, nullptr, nullptr, nullptr);
         } else {
             const gimic_b200_grid g = grid.cstruct();
-            over_devices(n, [=](gimic_b200_handle h, size_t, long lo, long hi) { return gimic_b200_calc_jtensors_grid(h, &g, lo, hi, spincase, tp + 9 * lo, 0); });
+            if (peers.empty()) check(gimic_b200_calc_jtensors_grid(ctx->h, &g, 0, n, spincase, tp, 0));
+            else partitioned(nullptr, n, &g, spincase, tp, nullptr, nullptr, nullptr);
         }
         return t;
     }
 
-    // J (and signed |J|, rho, div J) straight from the contraction, point slabs over the devices
+    // J (and signed |J|, rho, div J) straight from the contraction; div J (central differences, 6 more passes) keeps the slab split
     void point_fields(const std::vector<double> &r, int spincase, double *jvec, double *jmod, double *edens, double *divj) const {
         const double *rp = r.data(), *B = magnet.data();
+        if (!peers.empty() && !divj) { partitioned(rp, (long)r.size() / 3, nullptr, spincase, nullptr, jvec, jmod, edens); return; }
         over_devices((long)r.size() / 3, [=](gimic_b200_handle h, size_t, long lo, long hi) {
             return gimic_b200_calc_fields(h, hi - lo, rp + 3 * lo, B, spincase, nullptr, jvec ? jvec + 3 * lo : nullptr, jmod ? jmod + lo : nullptr, nullptr,
                                           edens ? edens + lo : nullptr, divj ? divj + lo : nullptr, 1e-3, 0);

@@ -22,7 +22,7 @@ Vec3 cross(const Vec3 &a, const Vec3 &b) { return Vec3{{a[1] * b[2] - a[2] * b[1
 Vec3 unit(const Vec3 &v) { double n = std::sqrt(dot(v.data(), v.data())); return Vec3{{v[0] / n, v[1] / n, v[2] / n}}; }
 Vec3 sub(const Vec3 &a, const Vec3 &b) { return Vec3{{a[0] - b[0], a[1] - b[1], a[2] - b[2]}}; }
 bool any(const Vec3 &v) { return v[0] != 0.0 || v[1] != 0.0 || v[2] != 0.0; }
-double nint(double x) { return std::floor(x + 0.5); }
+double nint(double x) { return std::round(x); }   // Fortran NINT: halves away from zero (also for negative arguments)
 
 // R = R_x . R_y . R_z with the sign conventions of grid.f90:716-757
 void rotation_matrix(const Vec3 &deg, double R[3][3]) {

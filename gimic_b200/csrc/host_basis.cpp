@@ -279,7 +279,7 @@ bool read_xdens(const std::string &path, int nbf, int nmat, std::vector<double> 
     if (hgot == sizeof head && std::memcmp(head, XD_MAGIC, 8) == 0) {
         long long hn, hm;
         std::memcpy(&hn, head + 8, 8); std::memcpy(&hm, head + 16, 8);
-        if (hn != nbf || hm < nmat) { std::fclose(f); err = "binary XDENS cache is for nbf=" + std::to_string(hn) + ", " + std::to_string(hm) + " matrices; expected nbf=" + std::to_string(nbf) + ", " + std::to_string(nmat); return false; }
+        if (hn != nbf || hm != nmat) { std::fclose(f); err = "binary XDENS cache is for nbf=" + std::to_string(hn) + ", " + std::to_string(hm) + " matrices; expected nbf=" + std::to_string(nbf) + ", " + std::to_string(nmat); return false; }
         out.resize(want);
         size_t got = std::fread(out.data(), sizeof(double), want, f);
         std::fclose(f);
@@ -310,6 +310,14 @@ bool read_xdens(const std::string &path, int nbf, int nmat, std::vector<double> 
     }
     for (unsigned t = 0; t < nthr; ++t) off[t + 1] = off[t] + cnt[t];
     if (off[nthr] < want) { err = "XDENS too short: expected " + std::to_string(want) + " values, found " + std::to_string(off[nthr]); return false; }
+    // The reference reads one value per record (read(iunit,*) array(i), dens.f90:129-135) and stops after nmat*nbf*nbf of them; a
+    // file with MORE numbers is one written for another basis size or an 8-matrix open-shell file opened as closed shell (or the
+    // other way round) -- the most common user error.  Refuse it instead of silently loading the first `want` tokens.
+    if (off[nthr] > want) {
+        err = "XDENS holds " + std::to_string(off[nthr]) + " values, expected " + std::to_string(nmat) + " matrices of " + std::to_string(nbf) + " x " +
+              std::to_string(nbf) + " = " + std::to_string(want) + (off[nthr] == 2 * want && nmat == 4 ? " (an open-shell file with 8 matrices? set uhf)" : " (density for another basis set?)");
+        return false;
+    }
     out.resize(want);
     std::vector<int> bad(nthr, 0);
     auto work = [&](unsigned t) {

@@ -106,6 +106,31 @@ constexpr int NVJ = 32, LDB2J = 68;                // J path: 4 n8 tiles per chu
 using Smem = SmemT<(NQ + 1) / 2, NV, LDB2>;        // tensor path
 using SmemJ = SmemT<1, NVJ, LDB2J>;                // J = T.B path: same 16 KB of B per stage, twice the columns per A fragment
 
+// ---- output helpers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long out_row(const JtensorArgs &a, long p) { return a.perm ? (long)a.perm[p] : p - a.out_base; }
+__device__ __forceinline__ void store_zero(const JtensorArgs &a, long o) {
+    if (a.tens) for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = 0.0;
+    if (a.jvec) for (int i = 0; i < 3; ++i) a.jvec[3 * o + i] = 0.0;
+    if (a.jmod) a.jmod[o] = 0.0;
+    if (a.acid) a.acid[o] = 0.0;
+    if (a.edens) a.edens[o] = 0.0;
+}
+// signed |J| (jmod2_vtkplot, jfield.f90:446-489): the sign of (B x (r - (B.r) B)) . J; same statements as k_fields / k_jmod
+__device__ __forceinline__ double signed_modulus(double vx, double vy, double vz, double cx, double cy, double cz, double bx, double by, double bz) {
+    double jm = sqrt(vx * vx + vy * vy + vz * vz);
+    const double d = bx * cx + by * cy + bz * cz;
+    cx -= d * bx; cy -= d * by; cz -= d * bz;
+    const double nx = by * cz - bz * cy, ny = bz * cx - bx * cz, nz = bx * cy - by * cx;   // cross_product(mag, coord)
+    if (nx * vx + ny * vy + nz * vz < 0.0) jm = -1.0 * jm;
+    return jm;
+}
+// get_acid (acid.f90:9-45) with the reference's DP33 = 0.3333333 (globals.f90:62)
+__device__ __forceinline__ double acid_of(const double (&t)[9]) {
+    const double xxmyy = (t[0] - t[4]) * (t[0] - t[4]), yymzz = (t[4] - t[8]) * (t[4] - t[8]), zzmxx = (t[8] - t[0]) * (t[8] - t[0]);
+    const double xypyx = (t[3] + t[1]) * (t[3] + t[1]), xzpzx = (t[6] + t[2]) * (t[6] + t[2]), yzpzy = (t[7] + t[5]) * (t[7] + t[5]);
+    return 0.3333333 * (xxmyy + yymzz + zzmxx) + 0.5 * (xypyx + xzpzx + yzpzy);
+}
+
 // Tile bookkeeping shared by both roles: every thread of the CTA calls this once per tile (two CTA barriers).
 __device__ __forceinline__ int next_tile(const JtensorArgs &a, int *s_tile) {
     __syncthreads();                                  // everybody is done with the previous tile (and with *s_tile)
@@ -178,10 +203,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
         const int rowA = row0 + g, rowB = row0 + g + 8;
         const bool vA = rowA < td.npts, vB = rowB < td.npts;
         if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
-            if (t == 0) {
-                if (vA) { long o = a.perm[td.pt0 + rowA]; for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
-                if (vB) { long o = a.perm[td.pt0 + rowB]; for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
-            }
+            if (t < 2 && (t ? vB : vA)) store_zero(a, out_row(a, td.pt0 + (t ? rowB : rowA)));
             continue;
         }
         const int nact = td.nact, nn = td.nn;
@@ -373,10 +395,21 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                 ct[0 + 3 * 1] += d3; ct[0 + 3 * 2] -= d2;                                // jtensor.F90:230-235
                 ct[1 + 3 * 0] -= d3; ct[1 + 3 * 2] += d1;
                 ct[2 + 3 * 0] += d2; ct[2 + 3 * 1] -= d1;
-                const long o = a.perm[td.pt0 + (t ? rowB : rowA)];
+                const long o = out_row(a, td.pt0 + (t ? rowB : rowA));
+                if (a.tens) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = ct[i];
+                    for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = ct[i];
+                }
                 if (a.edens) a.edens[o] = rho;
+                // derived fields straight from the registers (what the separate k_fields pass computes from the stored tensor)
+                if (a.jvec || a.jmod) {
+                    const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+                    const double vx = ct[0] * bx + ct[3] * by + ct[6] * bz, vy = ct[1] * bx + ct[4] * by + ct[7] * bz,
+                                 vz = ct[2] * bx + ct[5] * by + ct[8] * bz;                      // matmul(reshape(tens,(3,3)), b), jfield.f90:167-184
+                    if (a.jvec) { a.jvec[3 * o] = vx; a.jvec[3 * o + 1] = vy; a.jvec[3 * o + 2] = vz; }
+                    if (a.jmod) a.jmod[o] = signed_modulus(vx, vy, vz, px, py, pz, bx, by, bz);
+                }
+                if (a.acid) a.acid[o] = acid_of(ct);
             }
         }
         }
@@ -399,10 +432,7 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
         const int rowA = row0 + g, rowB = row0 + g + 8;
         const bool vA = rowA < td.npts, vB = rowB < td.npts;
         if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
-            if (t == 0) {
-                if (vA) { long o = a.perm[td.pt0 + rowA]; for (int i = 0; i < 3; ++i) a.jvec[3 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
-                if (vB) { long o = a.perm[td.pt0 + rowB]; for (int i = 0; i < 3; ++i) a.jvec[3 * o + i] = 0.0; if (a.edens) a.edens[o] = 0.0; }
-            }
+            if (t < 2 && (t ? vB : vA)) store_zero(a, out_row(a, td.pt0 + (t ? rowB : rowA)));
             continue;
         }
         const int nact = td.nact, nn = td.nn;
@@ -596,8 +626,9 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
                 if (a.diamag) {
                     jx += 0.5 * rho * (by * pz - bz * py); jy += 0.5 * rho * (bz * px - bx * pz); jz += 0.5 * rho * (bx * py - by * px);
                 }
-                const long o = a.perm[td.pt0 + (t ? rowB : rowA)];
-                a.jvec[3 * o] = jx; a.jvec[3 * o + 1] = jy; a.jvec[3 * o + 2] = jz;
+                const long o = out_row(a, td.pt0 + (t ? rowB : rowA));
+                if (a.jvec) { a.jvec[3 * o] = jx; a.jvec[3 * o + 1] = jy; a.jvec[3 * o + 2] = jz; }
+                if (a.jmod) a.jmod[o] = signed_modulus(jx, jy, jz, px, py, pz, bx, by, bz);
                 if (a.edens) a.edens[o] = rho;
             }
         }
@@ -650,7 +681,7 @@ static void launch_one(const JtensorArgs &a, int grid, cudaStream_t s) {
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;
     const int grid = a.ntiles < nsm ? a.ntiles : nsm;
-    const bool jv = a.jvec != nullptr;   // J = T.B path: operands are ONE pair-plane (D, sum_b B_b P_b)
+    const bool jv = a.jpath != 0;        // J = T.B path: operands are ONE pair-plane (D, sum_b B_b P_b)
     if (giao) { if (jv) launch_one<true, true>(a, grid, s); else launch_one<true, false>(a, grid, s); }
     else { if (jv) launch_one<false, true>(a, grid, s); else launch_one<false, false>(a, grid, s); }
 }
@@ -662,43 +693,47 @@ void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
 // src is the dens.f90 layout: element (a,b) at a + nbf*b.
 __global__ void k_build_operand(double *__restrict__ out, int nbf, int ldb, long long plane_stride, const double *__restrict__ srcA,
                                 const double *__restrict__ srcB, double signB, const int *__restrict__ f2user) {
-    const int nu = blockIdx.x * blockDim.x + threadIdx.x, mu = blockIdx.y;
+    const int nu = blockIdx.x * blockDim.x + threadIdx.x;
     if (nu >= nbf) return;
-    const long un = f2user[nu], um = f2user[mu];
-    const long src = um + (long)nbf * un, nn = (long)nbf * nbf;
-    const long dst = 2 * ((long)mu * ldb + nu);
-    double v[4];
+    const long un = f2user[nu], nn = (long)nbf * nbf;
+    for (int mu = blockIdx.y; mu < nbf; mu += gridDim.y) {   // gridDim.y is capped at 65535: rows beyond that by stride
+        const long um = f2user[mu];
+        const long src = um + (long)nbf * un;
+        const long dst = 2 * ((long)mu * ldb + nu);
+        double v[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        v[q] = srcA[q * nn + src];
-        if (srcB) v[q] += signB * srcB[q * nn + src];
+        for (int q = 0; q < 4; ++q) {
+            v[q] = srcA[q * nn + src];
+            if (srcB) v[q] += signB * srcB[q * nn + src];
+        }
+        for (int pp = 0; pp < 2; ++pp) *reinterpret_cast<double2 *>(out + pp * plane_stride + dst) = make_double2(v[2 * pp], v[2 * pp + 1]);
     }
-    for (int pp = 0; pp < 2; ++pp) *reinterpret_cast<double2 *>(out + pp * plane_stride + dst) = make_double2(v[2 * pp], v[2 * pp + 1]);
 }
 // J = T.B path: ONE pair-plane (D, B_x P_x + B_y P_y + B_z P_z): the tensor is only ever contracted with this field direction.
-__global__ void k_build_operand_j(double *__restrict__ out, int nbf, int ldb, const double *__restrict__ srcA, const double *__restrict__ srcB,
-                                  double signB, const int *__restrict__ f2user, double bx, double by, double bz) {
-    const int nu = blockIdx.x * blockDim.x + threadIdx.x, mu = blockIdx.y;
-    if (nu >= nbf) return;
-    const long un = f2user[nu], um = f2user[mu];
-    const long src = um + (long)nbf * un, nn = (long)nbf * nbf;
-    double v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        v[q] = srcA[q * nn + src];
-        if (srcB) v[q] += signB * srcB[q * nn + src];
+// Built from the tensor-path operand planes (same internal order, elementwise), so the raw densities need not stay resident.
+__global__ void k_operand_j(double2 *__restrict__ out, const double2 *__restrict__ p0, const double2 *__restrict__ p1, long count,
+                            double bx, double by, double bz) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+        const double2 a = p0[i], b = p1[i];                     // (D, Px), (Py, Pz)
+        out[i] = make_double2(a.x, bx * a.y + by * b.x + bz * b.y);
     }
-    *reinterpret_cast<double2 *>(out + 2 * ((long)mu * ldb + nu)) = make_double2(v[0], bx * v[1] + by * v[2] + bz * v[3]);
 }
-void launch_build_operand_j(double *out, int nbf, int ldb, const double *srcA, const double *srcB, double signB, const int *f2user,
-                            const double *B3, cudaStream_t s) {
-    dim3 grid((nbf + 127) / 128, nbf);
-    k_build_operand_j<<<grid, 128, 0, s>>>(out, nbf, ldb, srcA, srcB, signB, f2user, B3[0], B3[1], B3[2]);
+void launch_operand_j(double *out, const double *op, long long plane_stride, const double *B3, cudaStream_t s) {
+    const long count = plane_stride / 2;
+    k_operand_j<<<148 * 8, 256, 0, s>>>(reinterpret_cast<double2 *>(out), reinterpret_cast<const double2 *>(op),
+                                        reinterpret_cast<const double2 *>(op + plane_stride), count, B3[0], B3[1], B3[2]);
+}
+// total / spin-density operands of an open-shell context: alpha +- beta (jtensor.F90:86-88, 97-99; linear in D, P)
+__global__ void k_operand_combine(double *__restrict__ out, const double *__restrict__ a, const double *__restrict__ b, double sg, long count) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) out[i] = a[i] + sg * b[i];
+}
+void launch_operand_combine(double *out, const double *a, const double *b, double sg, long count, cudaStream_t s) {
+    k_operand_combine<<<148 * 8, 256, 0, s>>>(out, a, b, sg, count);
 }
 
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
                           const int *f2user, cudaStream_t s) {
-    dim3 grid((nbf + 127) / 128, nbf);
+    dim3 grid((nbf + 127) / 128, nbf < 65535 ? nbf : 65535);
     k_build_operand<<<grid, 128, 0, s>>>(out, nbf, ldb, plane_stride, srcA, srcB, signB, f2user);
 }
 

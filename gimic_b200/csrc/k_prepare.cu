@@ -101,92 +101,328 @@ void launch_grid_points(const double *ob, const double *p0, const double *p1, co
 
 // ---------------------------------------------------------------------------------------------
 // Screening of one atom against a tile: a shell can only be non-zero at some point p of the tile if |p - R| <= thr.
-// Cheap reject by the distance to the tile's bounding box, then the exact minimum distance over the tile's points
-// (staged in shared memory), so the active set is the exact union over the 128 points at shell granularity.  Shells are
-// sorted by descending thr inside each atom, so the active set of an atom is a prefix.  k_tile_count and k_basis call this
-// with identical inputs (same arithmetic => same counts); the per-point test sqrt(r2) <= thr is applied again in k_basis.
-__device__ __forceinline__ void atom_active(const DevBasis &B, int a, const TileGeo &tg, const double *sx, const double *sy,
-                                            const double *sz, int npts, int &nsh, int &nfun) {
-    nsh = 0; nfun = 0;
+// Cheap reject by the distance to the tile's bounding box (one atom per lane), then, one atom per warp, the exact minimum
+// distance over the tile's points (staged in shared memory), so the active set is the exact union over the tile's points at
+// shell granularity.  Shells are sorted by descending thr inside each atom, so the active set of an atom is a prefix.
+// k_tile_split and k_basis call these with identical inputs; every product below is written with explicit intrinsics so that
+// both kernels compute bit-identical distances (no context-dependent FMA contraction) => identical counts.  The per-point
+// test sqrt(r2) <= thr is applied again in k_basis (filter_screened, basis.f90:118-136).
+__device__ __forceinline__ bool atom_box_pass(const DevBasis &B, int a, const TileGeo &tg) {
     const double x = B.atom_xyz[3 * a], y = B.atom_xyz[3 * a + 1], z = B.atom_xyz[3 * a + 2];
     const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
                  dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
-    const double mx = B.atom_maxthr[a];
-    if (sqrt(dx * dx + dy * dy + dz * dz) - 1e-9 > mx) return;
+    return !(sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)))) - 1e-9 > B.atom_maxthr[a]);
+}
+// all 32 lanes, same atom: number of active functions (0: none) and shells of atom a for the points sx/sy/sz[0, np)
+__device__ __forceinline__ int atom_prefix_warp(const DevBasis &B, int a, const double *sx, const double *sy, const double *sz,
+                                                int np, int &nsh) {
+    nsh = 0;
+    const int lane = threadIdx.x & 31;
+    const double x = B.atom_xyz[3 * a], y = B.atom_xyz[3 * a + 1], z = B.atom_xyz[3 * a + 2];
     double d2 = 1e300;
-    for (int p = 0; p < npts; ++p) {
+    for (int p = lane; p < np; p += 32) {
         const double ex = sx[p] - x, ey = sy[p] - y, ez = sz[p] - z;
-        d2 = fmin(d2, ex * ex + ey * ey + ez * ez);
+        d2 = fmin(d2, __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
     }
-    const double lim = sqrt(d2) - 1e-9;
-    if (lim > mx) return;
-    int s1 = B.atom_shell_off[a + 1];
-    for (int s = B.atom_shell_off[a]; s < s1; ++s) {
-        if (B.sh_thr[s] >= lim) { int l = B.sh_l[s]; nfun += (l + 1) * (l + 2) / 2; ++nsh; }
-        else break;
-    }
-}
-
-template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce_128(T v, Op op, T *s4) {   // 128 threads; result broadcast to all
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s4[threadIdx.x >> 5] = v;
-    __syncthreads();
-    return op(op(s4[0], s4[1]), op(s4[2], s4[3]));
+    for (int o = 16; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    const double lim = sqrt(d2) - 1e-9;
+    if (lim > B.atom_maxthr[a]) return 0;
+    const int s0 = B.atom_shell_off[a], s1 = B.atom_shell_off[a + 1];
+    int cnt = 0;
+    for (int base = s0; base < s1; base += 32) {
+        const int s = base + lane;
+        const unsigned bal = __ballot_sync(0xffffffffu, s < s1 && B.sh_thr[s] >= lim);
+        if (bal == 0xffffffffu) { cnt += 32; continue; }
+        cnt += __ffs(~bal) - 1;      // shells are sorted by descending radius: the active ones are a prefix
+        break;
+    }
+    if (cnt == 0) return 0;
+    nsh = cnt;
+    return (cnt == s1 - s0 ? B.atom_func_off[a + 1] : B.sh_foff[s0 + cnt]) - B.atom_func_off[a];
 }
 
-__global__ void __launch_bounds__(128) k_tile_count(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
-                                                    const double *__restrict__ rsz, const TileSeg *__restrict__ segs,
-                                                    TileGeo *__restrict__ geo, TileInfo *__restrict__ info) {
-    __shared__ double s4[4];
-    __shared__ int i4[4];
-    __shared__ unsigned long long u4[4];
+// ---- k_tile_split -----------------------------------------------------------------------------------------------------------
+// One CTA (128 threads) per run of MT consecutive sorted points.  Depth-first, left piece first: evaluate a piece [a, b) of the
+// run (bounding box, radius, largest consecutive gap, active slots / atoms / functions); a piece wider than split_radius whose
+// largest gap exceeds half its radius is cut there (thin / planar point sets, cluster boundaries: a Hilbert run that leaves and
+// re-enters the point cloud would otherwise drag in the active sets of both ends), everything else is emitted in order.
+__device__ __forceinline__ void block_min6(double (&v)[6], double (*s_red)[6]) {   // 128 threads; result broadcast
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] = fmin(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s_red[threadIdx.x >> 5][i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = fmin(fmin(s_red[0][i], s_red[1][i]), fmin(s_red[2][i], s_red[3][i]));
+}
+
+__global__ void __launch_bounds__(128) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
+                                                    const double *__restrict__ rsz, long n, double split_radius,
+                                                    TileSeg *__restrict__ slot_seg, TileGeo *__restrict__ slot_geo,
+                                                    TileInfo *__restrict__ slot_info, int *__restrict__ cnt_out) {
     __shared__ double sx[MT], sy[MT], sz[MT];
-    const TileSeg sg = segs[blockIdx.x];
-    const bool valid = threadIdx.x < sg.npts;
-    const long pt = sg.pt0 + (valid ? threadIdx.x : 0);
-    const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
-    sx[threadIdx.x] = x; sy[threadIdx.x] = y; sz[threadIdx.x] = z;
-    auto fmn = [](double a, double b) { return fmin(a, b); };
-    auto fmx = [](double a, double b) { return fmax(a, b); };
-    TileGeo tg;
-    tg.lox = block_reduce_128(x, fmn, s4); tg.hix = block_reduce_128(x, fmx, s4);
-    tg.loy = block_reduce_128(y, fmn, s4); tg.hiy = block_reduce_128(y, fmx, s4);
-    tg.loz = block_reduce_128(z, fmn, s4); tg.hiz = block_reduce_128(z, fmx, s4);
-    const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
-    const double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
-    const double rho = block_reduce_128(d, fmx, s4);
-    tg.rho = rho; tg.pad_ = 0.0;
-    // largest gap between consecutive points of the sorted run (where a curve jump would be cut)
-    unsigned long long gi = 0;
-    if ((int)threadIdx.x + 1 < sg.npts) {
-        const double ex = rsx[pt + 1] - x, ey = rsy[pt + 1] - y, ez = rsz[pt + 1] - z;
-        gi = ((unsigned long long)__float_as_uint((float)sqrt(ex * ex + ey * ey + ez * ez)) << 32) | threadIdx.x;
-    }
-    auto umx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
-    gi = block_reduce_128(gi, umx, u4);
-    int cnt = 0, nat = 0, nre = 0;
+    __shared__ double s_red[4][6];
+    __shared__ unsigned long long s_u[4];
+    __shared__ int s_cnt[3];
+    __shared__ int s_stack[MAXSUB + SPLIT_DEPTH + 2][3];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long run = blockIdx.x;
+    const long pt0 = run * MT;
+    const int np = (int)((n - pt0) < MT ? (n - pt0) : MT);
+    { const long p = pt0 + (tid < np ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
+    int sp = 0, emitted = 0;               // identical in every thread (all decisions below are made on broadcast values)
+    if (tid == 0) { s_stack[0][0] = 0; s_stack[0][1] = np; s_stack[0][2] = 0; }
+    sp = 1;
     __syncthreads();
     const int al = B.slot_align - 1;
-    for (int a = threadIdx.x; a < B.natoms; a += 128) {
-        int nsh, nfun; atom_active(B, a, tg, sx, sy, sz, sg.npts, nsh, nfun);
-        cnt += (nfun + al) & ~al; nat += nfun > 0; nre += nfun;
+    while (sp > 0) {
+        --sp;
+        const int a = s_stack[sp][0], b = s_stack[sp][1], depth = s_stack[sp][2];
+        const bool in = tid >= a && tid < b;
+        const double x = sx[tid], y = sy[tid], z = sz[tid];
+        double v[6] = {in ? x : 1e300, in ? y : 1e300, in ? z : 1e300, in ? -x : 1e300, in ? -y : 1e300, in ? -z : 1e300};
+        block_min6(v, s_red);
+        TileGeo tg;
+        tg.lox = v[0]; tg.loy = v[1]; tg.loz = v[2]; tg.hix = -v[3]; tg.hiy = -v[4]; tg.hiz = -v[5];
+        const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
+        // radius about the centre and the largest gap between consecutive points, packed as (float bits << 32 | index): one max-reduction
+        unsigned long long key = 0;
+        if (in) {
+            const double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
+            key = (unsigned long long)__float_as_uint((float)d) << 32;     // non-negative floats order like their bit patterns
+        }
+        unsigned long long gap = 0;
+        if (tid >= a && tid + 1 < b) {
+            const double ex = sx[tid + 1] - x, ey = sy[tid + 1] - y, ez = sz[tid + 1] - z;
+            gap = ((unsigned long long)__float_as_uint((float)sqrt(ex * ex + ey * ey + ez * ez)) << 32) | (unsigned)(tid - a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o), g2 = __shfl_xor_sync(0xffffffffu, gap, o);
+            key = key > k2 ? key : k2; gap = gap > g2 ? gap : g2;
+        }
+        if (tid < 3) s_cnt[tid] = 0;
+        __syncthreads();
+        if (lane == 0) { s_u[wid] = key; }
+        __syncthreads();
+        key = s_u[0]; for (int w = 1; w < 4; ++w) key = key > s_u[w] ? key : s_u[w];
+        __syncthreads();
+        if (lane == 0) { s_u[wid] = gap; }
+        __syncthreads();
+        gap = s_u[0]; for (int w = 1; w < 4; ++w) gap = gap > s_u[w] ? gap : s_u[w];
+        const float rho = __uint_as_float((unsigned)(key >> 32)), gmax = __uint_as_float((unsigned)(gap >> 32));
+        const int imax = (int)(gap & 0xffffffffu);
+        tg.rho = (double)rho; tg.pad_ = 0.0;
+        // active slots (atom runs aligned), atoms, functions
+        for (int base = wid * 32; base < B.natoms; base += 128) {
+            const int at = base + lane;
+            unsigned bal = __ballot_sync(0xffffffffu, at < B.natoms && atom_box_pass(B, at, tg));
+            while (bal) {
+                const int aa = base + __ffs(bal) - 1;
+                bal &= bal - 1;
+                int nsh;
+                const int nfun = atom_prefix_warp(B, aa, sx + a, sy + a, sz + a, b - a, nsh);
+                if (lane == 0 && nfun > 0) { atomicAdd(&s_cnt[0], (nfun + al) & ~al); atomicAdd(&s_cnt[1], 1); atomicAdd(&s_cnt[2], nfun); }
+            }
+        }
+        __syncthreads();
+        const int nraw = s_cnt[0], natom = s_cnt[1], nreal = s_cnt[2];
+        const int npts = b - a;
+        const bool split = depth < SPLIT_DEPTH && npts >= 16 && nraw > 0 && rho > (float)split_radius && gmax > 0.5f * rho &&
+                           emitted + sp + 2 <= MAXSUB;
+        if (split) {
+            if (tid == 0) {
+                s_stack[sp][0] = a + imax + 1; s_stack[sp][1] = b; s_stack[sp][2] = depth + 1;          // right piece: later
+                s_stack[sp + 1][0] = a; s_stack[sp + 1][1] = a + imax + 1; s_stack[sp + 1][2] = depth + 1;   // left piece: next
+            }
+            sp += 2;
+        } else {
+            if (tid == 0) {
+                const long o = run * MAXSUB + emitted;
+                slot_seg[o] = TileSeg{(int)(pt0 + a), npts};
+                slot_geo[o] = tg;
+                slot_info[o] = TileInfo{rho, gmax, imax, nraw, natom, nreal};
+            }
+            ++emitted;
+        }
+        __syncthreads();
     }
-    auto iadd = [](int a, int b) { return a + b; };
-    cnt = block_reduce_128(cnt, iadd, i4);
-    nat = block_reduce_128(nat, iadd, i4);
-    nre = block_reduce_128(nre, iadd, i4);
-    if (threadIdx.x == 0) {
-        geo[blockIdx.x] = tg;
-        info[blockIdx.x] = TileInfo{(float)rho, __uint_as_float((unsigned)(gi >> 32)), (int)(gi & 0xffffffffu), cnt, nat, nre};
+    if (tid == 0) cnt_out[run] = emitted;
+}
+
+// Exclusive prefix sums by ONE CTA of 1024 threads (the arrays are a few MB at most and sit in L2; a call over 2^31 points has
+// 16 M runs: ~10 ms next to hours of contraction).  The element count may live on the device (n_dev).  out[n] = total.
+template <typename T, typename Add>
+__device__ __forceinline__ void block_scan_exclusive(const T *in, T *out, int n, T zero, Add add, T *s_part /*[1024]*/) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int chunk = (n + nt - 1) / nt;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    T acc = zero;
+    for (int i = lo; i < hi; ++i) acc = add(acc, in[i]);
+    s_part[tid] = acc;
+    __syncthreads();
+    for (int o = 1; o < nt; o <<= 1) {       // Hillis-Steele over the per-thread sums
+        T v = zero;
+        if (tid >= o) v = s_part[tid - o];
+        __syncthreads();
+        if (tid >= o) s_part[tid] = add(v, s_part[tid]);
+        __syncthreads();
+    }
+    T run = tid ? s_part[tid - 1] : zero;
+    for (int i = lo; i < hi; ++i) { const T v = in[i]; out[i] = run; run = add(run, v); }
+    if (tid == nt - 1) out[n] = s_part[nt - 1];
+}
+__global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cnt, int *off, int n, PlanSummary *sum, int cap) {
+    __shared__ int s_part[1024];
+    block_scan_exclusive<int>(cnt, off, n, 0, [](int a, int b) { return a + b; }, s_part);
+    __syncthreads();
+    if (threadIdx.x == 0) { sum->ntiles = off[n] < cap ? off[n] : cap; sum->overflow = off[n] > cap; }
+}
+__global__ void __launch_bounds__(1024) k_scan_cum(TileCum *cum, const PlanSummary *sum) {
+    __shared__ TileCum s_part[1024];
+    block_scan_exclusive<TileCum>(cum, cum, sum->ntiles, TileCum{0, 0, 0, 0},
+                                  [](TileCum a, TileCum b) { return TileCum{a.cost + b.cost, a.panel + b.panel, a.fidx + b.fidx, a.atab + b.atab}; }, s_part);
+}
+
+// compact tiles in Hilbert order + their sizes; one thread per initial run
+__global__ void k_tile_emit(const TileSeg *__restrict__ slot_seg, const TileGeo *__restrict__ slot_geo, const TileInfo *__restrict__ slot_info,
+                            const int *__restrict__ cnt, const int *__restrict__ off, long nrun0, int cap, TileGeo *__restrict__ geo,
+                            TileDesc *__restrict__ desc, TileCum *__restrict__ cum) {
+    const long run = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (run >= nrun0) return;
+    const int c = cnt[run], o = off[run];
+    for (int j = 0; j < c && o + j < cap; ++j) {
+        const int t = o + j;
+        const TileSeg sg = slot_seg[run * MAXSUB + j];
+        const TileInfo ti = slot_info[run * MAXSUB + j];
+        geo[t] = slot_geo[run * MAXSUB + j];
+        TileDesc td;
+        td.pt0 = sg.pt0; td.npts = sg.npts; td.nraw = ti.nraw; td.nact = (ti.nraw + 7) / 8 * 8;
+        td.nreal = ti.nreal; td.nn = (ti.nreal + 7) / 8 * 8; td.geo = t; td.nruns = ti.natom;
+        td.panel_off = 0; td.fidx_off = 0; td.atab_off = 0;
+        desc[t] = td;
+        TileCum tc;
+        // scheduling cost ~ MMA k-steps x columns (4 planes) + GIAO taps + a constant per tile (staging, epilogue tail); integers,
+        // so every rank computes the same prefix sums and hence the same partition
+        tc.cost = 4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + (td.nact ? 4096 : 64);
+        tc.panel = 4LL * td.nact * LDP; tc.fidx = td.nact + td.nn; tc.atab = td.nruns;
+        cum[t] = tc;
     }
 }
-void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
-                       TileGeo *geo, TileInfo *info, cudaStream_t s) {
-    if (ntiles <= 0) return;
-    k_tile_count<<<ntiles, 128, 0, s>>>(B, rsx, rsy, rsz, segs, geo, info);
+
+// this rank's share: tiles whose exclusive cost prefix falls into [rank, rank + 1) x total / nranks; panel-pool batches of that range
+__global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, int rank, int nranks,
+                                                    long long pool_doubles, PlanSummary *sum) {
+    const int ntiles = sum->ntiles;
+    __shared__ int s_lo, s_hi;
+    if (threadIdx.x == 0) {
+        const long long total = cum[ntiles].cost;
+        auto first_at_least = [&](long long target) {     // first t with cum[t].cost * nranks >= target (cum is non-decreasing)
+            int lo = 0, hi = ntiles;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cum[mid].cost * nranks >= target) hi = mid; else lo = mid + 1; }
+            return lo;
+        };
+        const int tlo = rank == 0 ? 0 : first_at_least((long long)rank * total), thi = rank + 1 >= nranks ? ntiles : first_at_least((long long)(rank + 1) * total);
+        s_lo = tlo; s_hi = thi;
+        sum->tlo = tlo; sum->thi = thi;
+        sum->cost_total = total; sum->cost_range = cum[thi].cost - cum[tlo].cost;
+        sum->panel_range = cum[thi].panel - cum[tlo].panel;
+        sum->pt_lo = tlo < thi ? desc[tlo].pt0 : 0;
+        sum->pt_hi = tlo < thi ? (long long)desc[thi - 1].pt0 + desc[thi - 1].npts : 0;
+        const long long nb = tlo < thi ? (cum[thi - 1].panel - cum[tlo].panel) / pool_doubles + 1 : 0;
+        sum->nbatch = (int)(nb < MAX_BATCH ? nb : MAX_BATCH + 1);      // MAX_BATCH + 1: too many, the host refuses
+        sum->max_nruns = 0; sum->max_tile_panel = 0;
+        sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
+        if (nb <= MAX_BATCH) sum->batch_start[nb] = thi;
+    }
+    __syncthreads();
+    const int tlo = s_lo, thi = s_hi;
+    const long long base = cum[tlo].panel;
+    for (int t = tlo + threadIdx.x + blockIdx.x * blockDim.x; t < thi; t += blockDim.x * gridDim.x) {
+        const long long b = (cum[t].panel - base) / pool_doubles;
+        if (b < MAX_BATCH && (t == tlo || (cum[t - 1].panel - base) / pool_doubles != b)) sum->batch_start[b] = t;
+    }
+}
+
+// offsets inside the batch, scheduling keys (batch, longest first) and the statistics of the range
+__global__ void __launch_bounds__(256) k_plan_finalize(TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, long long pool_doubles,
+                                                       PlanSummary *sum, unsigned long long *__restrict__ keys, int *__restrict__ ord) {
+    const int tlo = sum->tlo, thi = sum->thi;
+    const int t = tlo + blockIdx.x * blockDim.x + threadIdx.x;
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    int mr = 0; long long mp = 0;
+    if (t < thi && sum->nbatch <= MAX_BATCH) {
+        const long long b = (cum[t].panel - cum[tlo].panel) / pool_doubles;
+        const int t0 = sum->batch_start[b];
+        TileDesc td = desc[t];
+        td.panel_off = cum[t].panel - cum[t0].panel; td.fidx_off = cum[t].fidx - cum[t0].fidx; td.atab_off = cum[t].atab - cum[t0].atab;
+        desc[t] = td;
+        const long long c = cum[t + 1].cost - cum[t].cost;
+        const unsigned c32 = (unsigned)(c > 0xffffffffLL ? 0xffffffffLL : c);
+        keys[t - tlo] = ((unsigned long long)b << 32) | (0xffffffffu - c32);
+        ord[t - tlo] = t;
+        st[0] = td.nact; st[1] = 2.0 * MT * 4.0 * td.nact * td.nn; st[2] = 2.0 * MT * 2.0 * td.nact * td.nn;
+        st[3] = 2.0 * MT * (double)td.nn * td.nruns;                       // per tap weight (x3 tensor path, x1 J path)
+        st[4] = 2.0 * td.npts * (double)td.nreal * td.nreal;               // per plane
+        st[5] = 2.0 * td.npts * (double)td.nreal * td.nruns;
+        mr = td.nruns; mp = cum[t + 1].panel - cum[t].panel;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) st[i] += __shfl_xor_sync(0xffffffffu, st[i], o);
+        mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+        const long long m2 = __shfl_xor_sync(0xffffffffu, mp, o); mp = mp > m2 ? mp : m2;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sum->sum_nact, st[0]); atomicAdd(&sum->flops4, st[1]); atomicAdd(&sum->flops2, st[2]); atomicAdd(&sum->taps, st[3]);
+        atomicAdd(&sum->useful_mm, st[4]); atomicAdd(&sum->useful_taps, st[5]);
+        atomicMax(&sum->max_nruns, mr); atomicMax(reinterpret_cast<unsigned long long *>(&sum->max_tile_panel), (unsigned long long)mp);
+    }
+}
+
+__global__ void k_tile_gather(const TileDesc *__restrict__ desc, const int *__restrict__ ord, int nt, TileDesc *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt) out[i] = desc[ord[i]];
+}
+__global__ void k_perm_index(const int *__restrict__ perm, long n, long *__restrict__ index) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) index[i] = perm[i];
+}
+
+// Everything between the sorted points and the tile list, queued on one stream without a host round trip:
+// split -> scan -> emit -> scan -> range/batches -> offsets/keys.  The host then reads PlanSummary once.
+void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, double split_radius,
+                       int rank, int nranks, long long pool_doubles, const PlanBuffers &pb, cudaStream_t s) {
+    const long nrun0 = (n + MT - 1) / MT;
+    if (nrun0 <= 0) return;
+    k_tile_split<<<(unsigned)nrun0, 128, 0, s>>>(B, rsx, rsy, rsz, n, split_radius, pb.slot_seg, pb.slot_geo, pb.slot_info, pb.cnt);
+    k_scan_counts<<<1, 1024, 0, s>>>(pb.cnt, pb.off, (int)nrun0, pb.summary, pb.cap);
+    k_tile_emit<<<(unsigned)((nrun0 + 127) / 128), 128, 0, s>>>(pb.slot_seg, pb.slot_geo, pb.slot_info, pb.cnt, pb.off, nrun0, pb.cap, pb.geo, pb.desc, pb.cum);
+    k_scan_cum<<<1, 1024, 0, s>>>(pb.cum, pb.summary);
+    k_plan_range<<<64, 256, 0, s>>>(pb.desc, pb.cum, rank, nranks, pool_doubles, pb.summary);
+    k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0);
+}
+size_t plan_sort_temp_bytes(int nt) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (const int *)nullptr, (int *)nullptr, nt);
+    return bytes;
+}
+// processing order of this rank's nt tiles: batch by batch, longest first inside a batch (the contraction kernel pulls tiles from an atomic counter)
+void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, void *sorttmp, size_t sorttmp_bytes, cudaStream_t s) {
+    if (nt <= 0) return;
+    (void)tlo;
+    cub::DeviceRadixSort::SortPairs(sorttmp, sorttmp_bytes, pb.keys0, pb.keys1, pb.ord0, pb.ord1, nt, 0, 64, s);
+    k_tile_gather<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(pb.desc, pb.ord1, nt, pb.tiles);
+}
+void launch_perm_index(const int *perm, long n, long *index, cudaStream_t s) {
+    if (n <= 0) return;
+    k_perm_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(perm, n, index);
 }
 
 // position in the Turbomole component order (gtodefs.f90:109-123) of the c-th component in the standard order (:86-106)
@@ -237,7 +473,8 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
                                                const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                const double *__restrict__ rsz, double *__restrict__ panel_pool,
                                                int *__restrict__ fidx_pool, TileAtom *__restrict__ atab_pool) {
-    extern __shared__ int s_runs[];   // 4 ints per active atom: atom, shells, first K slot, first N column
+    extern __shared__ int s_dyn[];    // [natoms] packed (shells << 20 | functions) of every atom, then 4 ints per active atom (run)
+    int *s_atom = s_dyn, *s_runs = s_dyn + B.natoms;   // run: atom, shells, first K slot, first N column
     __shared__ int s_w[3][4];
     __shared__ int s_base[3];
     __shared__ int s_zero;            // a K slot whose panel rows are zero (padding), for the N-side padding columns
@@ -252,11 +489,25 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
     __shared__ double sx[MT], sy[MT], sz[MT];
     { const long p = td.pt0 + (tid < td.npts ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
     if (tid == 0) { s_base[0] = 0; s_base[1] = 0; s_base[2] = 0; s_zero = td.nraw < td.nact ? td.nraw : 0x7fffffff; }
+    for (int a = tid; a < B.natoms; a += 128) s_atom[a] = 0;
+    __syncthreads();
+    // phase A1: active prefix of every atom (same arithmetic as k_tile_split => the counts the descriptors were sized with)
+    for (int base = wid * 32; base < B.natoms; base += 128) {
+        const int at = base + lane;
+        unsigned bal = __ballot_sync(0xffffffffu, at < B.natoms && atom_box_pass(B, at, tg));
+        while (bal) {
+            const int aa = base + __ffs(bal) - 1;
+            bal &= bal - 1;
+            int nsh;
+            const int nfun = atom_prefix_warp(B, aa, sx, sy, sz, td.npts, nsh);
+            if (lane == 0 && nfun > 0) s_atom[aa] = (nsh << 20) | nfun;
+        }
+    }
     __syncthreads();
     const int al = B.slot_align - 1;
     for (int a0 = 0; a0 < B.natoms; a0 += 128) {
         int a = a0 + tid, nsh = 0, nreal = 0;
-        if (a < B.natoms) atom_active(B, a, tg, sx, sy, sz, td.npts, nsh, nreal);
+        if (a < B.natoms) { const int pk = s_atom[a]; nsh = pk >> 20; nreal = pk & 0xfffff; }
         const int nfun = (nreal + al) & ~al;         // slots of the atom's run (functions + alignment padding)
         int flag = nfun > 0, sf = nfun, sr = flag, sn = nreal;   // inclusive warp scans
 #pragma unroll
@@ -395,10 +646,10 @@ void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const doub
     k_basis_dense<<<(unsigned)n, 128, 0, s>>>(B, f2user, n, r, bf, dr);
 }
 
-void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
+void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s) {
     if (ntiles <= 0) return;
-    size_t smem = (size_t)4 * B.natoms * sizeof(int);
+    size_t smem = ((size_t)B.natoms + (size_t)4 * (max_nruns > 0 ? max_nruns : 1)) * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
     k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
 }

@@ -61,14 +61,46 @@ struct TileGeo { double lox, loy, loz, hix, hiy, hiz, rho, pad_; };   // axis-al
 struct TileSeg { int pt0, npts; };                         // a tile = npts <= MT consecutive points of the sorted list
 struct TileInfo { float rho, gmax; int imax, nraw, natom, nreal; };   // radius, largest consecutive gap (and where), active slots (atom runs aligned), active atoms, active functions
 
+// ---- device-side tile plan (k_prepare.cu): no host round trip between the sort and the first k_basis launch except ONE small
+// summary copy.  A run of MT consecutive Hilbert-sorted points that straddles a re-entry of the curve is cut at its largest
+// consecutive gap, recursively (depth <= SPLIT_DEPTH, at most MAXSUB pieces), inside one CTA (k_tile_split).
+constexpr int MAXSUB = 16;
+constexpr int SPLIT_DEPTH = 7;
+constexpr int MAX_BATCH = 4096;     // panel-pool batches one call may need
+struct TileCum { long long cost, panel, fidx, atab; };   // per tile: scheduling cost, panel doubles, index ints, atom-table entries (and their exclusive prefix sums)
+struct PlanSummary {                // device -> host, once per plan
+    int ntiles;                     // tiles of the whole point set (Hilbert order)
+    int tlo, thi;                   // the tile range this rank owns: equal shares of the cumulative cost
+    int nbatch, max_nruns, overflow;
+    long long pt_lo, pt_hi;         // sorted-point range of [tlo, thi)
+    long long panel_range;          // panel doubles of the range
+    long long max_tile_panel;
+    long long cost_total, cost_range;
+    double sum_nact, flops4, flops2, taps, useful_mm, useful_taps;   // statistics of the range (see gimic_b200_stats)
+    int batch_start[MAX_BATCH + 1]; // tile index (Hilbert order, absolute) where each batch begins; [nbatch] = thi
+};
+
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
 void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s);
 void launch_gather_points(const double *r, const int *perm, long n, double *rsx, double *rsy, double *rsz, cudaStream_t s);
 void launch_grid_points(const double *origin_basv /*12 doubles, device*/, const double *p0, const double *p1, const double *p2,
                         int n0, int n1, int n2, long lo, long hi, double *r, cudaStream_t s);
-void launch_tile_count(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, const TileSeg *segs, int ntiles,
-                       TileGeo *geo, TileInfo *info, cudaStream_t s);
-void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, const TileGeo *geo, const double *rsx, const double *rsy,
+struct PlanBuffers {                // device workspaces of one plan (all sized by the number of initial runs nrun0 = ceil(n / MT))
+    TileSeg *slot_seg; TileGeo *slot_geo; TileInfo *slot_info;   // [nrun0 * MAXSUB] pieces of every run, in order
+    int *cnt; int *off;                                          // [nrun0] pieces per run, [nrun0 + 1] their exclusive prefix sum
+    TileGeo *geo; TileDesc *desc;                                // [cap] compact tiles in Hilbert order
+    TileCum *cum;                                                // [cap + 1] sizes -> exclusive prefix sums (in place), [ntiles] = totals
+    unsigned long long *keys0, *keys1; int *ord0, *ord1;         // [cap] scheduling keys / tile order (CUB sort)
+    TileDesc *tiles;                                             // [cap] this rank's tiles in processing order (batch by batch, longest first)
+    PlanSummary *summary;                                        // device copy
+    int cap;
+};
+void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, double split_radius,
+                       int rank, int nranks, long long pool_doubles, const PlanBuffers &pb, cudaStream_t s);
+void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, void *sorttmp, size_t sorttmp_bytes, cudaStream_t s);
+size_t plan_sort_temp_bytes(int nt);
+void launch_perm_index(const int *perm, long n, long *index, cudaStream_t s);
+void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s);
 void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s);
 size_t sort_temp_bytes(long n);
@@ -79,9 +111,11 @@ struct JtensorArgs {
     const double *panel_pool; const int *fidx_pool; const TileAtom *atab_pool; const TileGeo *geo;
     const double *Bop; long long plane_stride; int ldb;     // pair-plane operands [2][nbf][ldb][2] = (D,Px), (Py,Pz); plane_stride in doubles
     const double *fR; int nbf;
-    const double *rsx, *rsy, *rsz; const int *perm;
-    double *tens; double *edens;                            // outputs in user point order (edens may be null)
-    double *jvec; double B[3];                              // J = T.B path (jvec != null): 3 x n output instead of tens, field direction
+    const double *rsx, *rsy, *rsz; const int *perm;         // perm == null: compact output, sorted point p goes to row p - out_base
+    long long out_base;
+    double *tens; double *edens;                            // outputs (any may be null): 9 x n tensors, n densities,
+    double *jvec, *jmod, *acid; double B[3];                // 3 x n J = T.B, n signed |J| (jfield.f90:446-489), n ACID (acid.f90:9-45); field direction
+    int jpath;                                              // J = T.B path: operands (D, P.B), the tensor is never formed (tens, acid unavailable)
     int paramag, diamag;
 };
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
@@ -90,8 +124,8 @@ size_t jtensor_smem_bytes();
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,
                           const int *f2user, cudaStream_t s);
 
-void launch_build_operand_j(double *out, int nbf, int ldb, const double *srcA, const double *srcB, double signB, const int *f2user,
-                            const double *B3, cudaStream_t s);
+void launch_operand_j(double *out, const double *op, long long plane_stride, const double *B3 /*host*/, cudaStream_t s);
+void launch_operand_combine(double *out, const double *a, const double *b, double sg, long count, cudaStream_t s);
 void launch_jmod(long n, const double *r, const double *jvec, const double *B3 /*host*/, double *jmod, cudaStream_t s);
 void launch_fields(long n, const double *r, const double *tens, const double *B3 /*host values*/, double *jvec, double *jmod, double *acid, cudaStream_t s);
 void launch_divj(long n, const double *jv6 /* [6][n][3] shifted jvecs */, double h, double *divj, cudaStream_t s);

@@ -256,25 +256,57 @@ class Driver:
             for line in self.magnet_log:
                 self.out.write(line + "\n")
 
+    def _gather_indexed(self, index, part, n):
+        """rows `part` of the points `index` (this rank's share of a cost-balanced partition) -> the full (n, width) array on rank 0"""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else torch.device("cpu")
+        part = np.ascontiguousarray(part, dtype=np.float64).reshape(index.shape[0], -1)
+        cnt = torch.tensor([index.shape[0]], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        self.dist.all_gather(counts, cnt)
+        counts = [int(c[0]) for c in counts]
+        mx = max(max(counts), 1)
+        buf = torch.zeros((mx, part.shape[1] + 1), dtype=torch.float64, device=dev)     # column 0: the point index (exact in a double below 2^53)
+        buf[: index.shape[0], 0] = torch.from_numpy(index.astype(np.float64)).to(dev)
+        buf[: index.shape[0], 1:] = torch.from_numpy(part).to(dev)
+        gathered = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
+        self.dist.gather(buf, gathered, dst=0)
+        if self.rank != 0:
+            return None
+        full = np.zeros((n, part.shape[1]))
+        for r, c in enumerate(counts):
+            rows = gathered[r][:c].cpu().numpy()
+            full[rows[:, 0].astype(np.int64)] = rows[:, 1:]
+        return full
+
+    def _partition(self):
+        """this rank's equal-COST share of the grid (gimic_b200_partition_*): replaces the equal-count slabs of schedule(), parallel.F90:66-84"""
+        grid = self.grid
+        self.g.partition(grid.points() if grid.mode == "file" else grid, self.rank, self.world)
+
     def _tensors(self, spincase):
-        """calc_jtensors (jfield.f90:62-138): slab of the flat index per rank, gathered on rank 0"""
+        """calc_jtensors (jfield.f90:62-138): one call on a single device; a cost-balanced share per rank, gathered on rank 0"""
         grid, n = self.grid, self.grid.n
-        lo, hi = slab(n, self.rank, self.world)
-        if grid.mode == "file":
-            part = self.g.jtensors(grid.points()[lo:hi], spincase)
-        else:
-            part = self.g.jtensors_grid(grid, lo, hi, spincase)
-        return self._gather_rows(part, n)
+        if self.world == 1:
+            return self.g.jtensors(grid.points(), spincase) if grid.mode == "file" else self.g.jtensors_grid(grid, 0, n, spincase)
+        self._partition()
+        res = self.g.partition_calc(None, spincase, tens=True)
+        return self._gather_indexed(res["index"], res["tens"], n)
 
     def _jvectors(self, spincase, want_jmod):
-        """J = T.B (and the signed modulus) straight from the contraction on this rank's slab of points, gathered on rank 0:
+        """J = T.B (and the signed modulus) straight from the contraction on this rank's share of the points, gathered on rank 0:
         3 (+1) doubles per point cross the wire instead of 9, and the contraction runs with 2 operand planes instead of 4"""
         n = self.grid.n
-        lo, hi = slab(n, self.rank, self.world)
-        f = self.g.fields(self.grid.points()[lo:hi], self.magnet, spincase, jvec=True, jmod=want_jmod)
-        jv = self._gather_rows(f["jvec"], n)
-        jm = self._gather_rows(f["jmod"].reshape(-1, 1), n) if want_jmod else None
-        return jv, (jm[:, 0] if jm is not None else None)
+        if self.world == 1:
+            f = self.g.fields(self.grid.points(), self.magnet, spincase, jvec=True, jmod=want_jmod)
+            return f["jvec"], (f["jmod"] if want_jmod else None)
+        self._partition()
+        res = self.g.partition_calc(self.magnet, spincase, jvec=True, jmod=want_jmod)
+        rows = np.concatenate([res["jvec"], res["jmod"].reshape(-1, 1)], axis=1) if want_jmod else res["jvec"]
+        full = self._gather_indexed(res["index"], rows, n)
+        if full is None:
+            return None, None
+        return np.ascontiguousarray(full[:, :3]), (np.ascontiguousarray(full[:, 3]) if want_jmod else None)
 
     def run_cdens(self):
         """run_cdens (gimic.F90:196-220) + jvector_plots (jfield.f90:250-443)"""

@@ -109,7 +109,7 @@ class Gimic(GimicConnector):
 
     @classmethod
     def from_arrays(cls, coords, nctr_per_atom, ctr_l, ctr_npf, xp, cc, dens_alpha, dens_beta=None, *,
-                    turbomole_order=False, giao=True, diamag=True, paramag=True, screening=True, screening_thrs=1e-8,
+                    turbomole_order=False, giao=True, diamag=True, paramag=True, screening=True, screening_thrs=1e-6,
                     device=-1, spherical=False):
         """dens_*: 4 matrices in the XDENS layout (flat, element (a,b) at a + nbf*b), numpy or CUDA torch tensor."""
         L = _lib.lib()
@@ -272,6 +272,59 @@ class Gimic(GimicConnector):
         _lib.check(L.gimic_b200_calc_jtensors_grid(self._h, C.byref(g), lo, hi, SPINCASES[spincase],
                                                    C.c_void_p(out.ctypes.data), 0))
         return out
+
+    # ---- cost-balanced multi-GPU partition (replaces schedule(), parallel.F90:66-84) ----------------------
+    def partition(self, points_or_grid, rank=0, nranks=1):
+        """Sort and tile the COMPLETE point set (a Grid, an (n, 3) numpy array or a CUDA torch tensor) and take this rank's equal-cost
+        share of the tiles.  Returns the number of points this rank owns; evaluate them with partition_calc()."""
+        L = _lib.lib()
+        cnt = C.c_long(0)
+        if isinstance(points_or_grid, Grid):
+            g = points_or_grid.struct()
+            _lib.check(L.gimic_b200_partition_grid(self._h, C.byref(g), int(rank), int(nranks), C.byref(cnt)))
+        elif _is_torch_cuda(points_or_grid):
+            r = points_or_grid
+            assert r.is_contiguous() and r.shape[-1] == 3
+            _lib.check(L.gimic_b200_partition_points(self._h, r.shape[0], C.c_void_p(r.data_ptr()), _lib.DEVICE_PTR, int(rank), int(nranks), C.byref(cnt)))
+        else:
+            r = _host(points_or_grid).reshape(-1, 3)
+            _lib.check(L.gimic_b200_partition_points(self._h, r.shape[0], C.c_void_p(r.ctypes.data), 0, int(rank), int(nranks), C.byref(cnt)))
+        self._part_count = int(cnt.value)
+        return self._part_count
+
+    def partition_info(self):
+        v = (C.c_long * 8)()
+        _lib.check(_lib.lib().gimic_b200_partition_info(self._h, v))
+        keys = ("points", "owned_points", "tiles", "owned_tiles", "cost_total", "cost_owned", "batches", "first_tile")
+        return dict(zip(keys, [int(x) for x in v]))
+
+    def partition_calc(self, B=None, spincase="total", tens=False, jvec=False, jmod=False, acid=False, edens=False, device=None):
+        """Evaluate the owned points of the last partition().  Returns a dict with `index` (caller point index / flat grid index of each
+        output row) and the requested arrays; numpy by default, CUDA torch tensors on `device` (no host copy) when given."""
+        L = _lib.lib()
+        m = self._part_count
+        Bp = None if B is None else _dptr(_host(B, (3,)))
+        res = {}
+        if device is not None:
+            import torch
+            def buf(flag, name, width, dtype=torch.float64):
+                if not flag:
+                    return None
+                res[name] = torch.empty((m, width) if width > 1 else (m,), dtype=dtype, device=device)
+                return C.c_void_p(res[name].data_ptr())
+            idx = buf(True, "index", 1, torch.int64)
+            flags = _lib.DEVICE_PTR
+        else:
+            def buf(flag, name, width, dtype=np.float64):
+                if not flag:
+                    return None
+                res[name] = np.empty((m, width) if width > 1 else (m,), dtype=dtype)
+                return C.c_void_p(res[name].ctypes.data)
+            idx = buf(True, "index", 1, np.int64)
+            flags = 0
+        args = [buf(tens, "tens", 9), buf(jvec, "jvec", 3), buf(jmod, "jmod", 1), buf(acid, "acid", 1), buf(edens, "edens", 1)]
+        _lib.check(L.gimic_b200_partition_calc(self._h, Bp, SPINCASES[spincase], idx, *args, flags))
+        return res
 
     def integrate(self, grid, B, spincase="total", what=3, jlo=0, jhi=None):
         """Partial quadrature sums over rows [jlo, jhi): [J, J+, J-, |J|, |J|+, |J|-, sum w*ACID]  (integral.f90)."""

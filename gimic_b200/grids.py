@@ -14,6 +14,10 @@ from .gengauss import gausspoints
 PII = 3.141592653589793  # globals.f90:41
 
 
+def _nint(x):
+    """Fortran NINT: nearest integer, halves away from zero (also for negative arguments)"""
+    return int(math.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)
+
 
 def _dot3(a, b):
     """a.b summed left to right in plain doubles -- the same operation order as the native driver (csrc/driver/grid.cpp), so that
@@ -88,7 +92,7 @@ def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order
             if d == 2 and (abs(lengths[2]) < 2.2250738585072014e-308 or abs(step[2]) < 2.2250738585072014e-308):
                 n = 1
             else:
-                n = int(math.floor(lengths[d] / step[d] + 0.5)) + 1      # nint
+                n = _nint(lengths[d] / step[d]) + 1
             pts.append(np.arange(n, dtype=np.float64) * step[d])
             wgt.append(np.ones(n))
         return pts, wgt
@@ -106,7 +110,7 @@ def _axes(lengths, gtype, step=None, grid_points=None, spacing=None, gauss_order
         elif abs(spacing[d]) < 1e-10 or spacing[d] < 0.0:
             npts[d] = 0
         else:
-            npts[d] = int(math.floor(lengths[d] / spacing[d] + 0.5))
+            npts[d] = _nint(lengths[d] / spacing[d])
         if not npts[d] > 1:
             npts[d] = 0
         rem = npts[d] % gauss_order

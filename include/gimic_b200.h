@@ -146,6 +146,21 @@ typedef struct {
 int gimic_b200_calc_jtensors_grid(gimic_b200_handle h, const gimic_b200_grid *g, long lo, long hi, int spincase,
                                   double *tens, int flags);
 
+/* Cost-balanced multi-GPU partition (replaces schedule(), src/fgimic/parallel.F90:66-84, which gives every rank an equal COUNT of
+ * consecutive flat indices, jfield.f90:90-104).  Every rank calls _partition_points / _partition_grid with the SAME complete point
+ * set and its own rank: the points are sorted along a Hilbert curve and tiled identically on every rank, and rank r is given the run
+ * of tiles whose cumulative cost (~ active functions^2, integers) lies in [r, r+1) x total / nranks.  *count = points this rank owns.
+ * _partition_calc then evaluates them: output row i belongs to caller point index[i] (flat grid index for _partition_grid); any output
+ * may be NULL; only jvec / jmod / edens requested => the tensor is never formed (see gimic_b200_calc_fields).  The plan stays valid for
+ * further _partition_calc calls (other spin cases, other fields) until the next compute call on the handle.  Tiles, and therefore every
+ * result bit, are those of a single-rank run.  index / outputs: host, or device with GIMIC_B200_DEVICE_PTR.
+ * _partition_info: { points, owned points, tiles, owned tiles, total cost, owned cost, panel batches, first owned tile }. */
+int gimic_b200_partition_points(gimic_b200_handle h, long n, const double *r, int flags, int rank, int nranks, long *count);
+int gimic_b200_partition_grid(gimic_b200_handle h, const gimic_b200_grid *g, int rank, int nranks, long *count);
+int gimic_b200_partition_calc(gimic_b200_handle h, const double *B3, int spincase, long *index, double *tens, double *jvec,
+                              double *jmod, double *acid, double *edens, int flags);
+int gimic_b200_partition_info(gimic_b200_handle h, long *info8);
+
 /* Plane/volume quadrature of integral.f90 over rows j in [jlo, jhi) of the grid (all i, all k):
  *   out[0..2] = sum, positive part, negative part of  w (n.T.B)        (integrate_current)
  *   out[3..5] = same for the signed modulus sgn(n.J)|J|               (integrate_modulus)

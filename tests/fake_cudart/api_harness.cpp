@@ -81,6 +81,30 @@ int main(int argc, char **argv) {
     for (int k = 0; k < 5; ++k) { Bs[3 * k + 2] = 1.0; gs[k].origin[0] += 0.3 * k; }
     EXPECT(gimic_b200_integrate_batch(h, 5, gs.data(), Bs.data(), GIMIC_B200_TOTAL, 3, outs.data()) == 0);
     EXPECT(gimic_b200_integrate_batch(h, 0, gs.data(), Bs.data(), GIMIC_B200_TOTAL, 3, outs.data()) == 0);
+    // ---- cost-balanced partition: every rank tiles the whole set; the shares are disjoint and cover it
+    {
+        long total = 0, info[8];
+        std::vector<long> idx(n);
+        EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), tens.data(), nullptr, nullptr, nullptr, nullptr, 0) == GIMIC_B200_EINVAL);   // no plan yet
+        long cost_sum = 0, tiles_sum = 0;
+        for (int rk = 0; rk < 3; ++rk) {
+            long cnt = -1;
+            EXPECT(gimic_b200_partition_points(h, n, r.data(), 0, rk, 3, &cnt) == 0 && cnt >= 0);
+            EXPECT(gimic_b200_partition_info(h, info) == 0 && info[0] == n && info[1] == cnt && info[3] <= info[2] && info[5] <= info[4]);
+            EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), tens.data(), jv.data(), jm.data(), ac.data(), ed.data(), 0) == 0);
+            EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), nullptr, jv.data(), jm.data(), nullptr, nullptr, 0) == 0);   // plan reused, J path
+            total += cnt; cost_sum += info[5]; tiles_sum += info[3];
+            // balanced to within one tile: no share is more than the mean + the largest tile cost (bounded here by the total / 2)
+            EXPECT(3 * info[5] <= info[4] + 3 * (info[4] / 2));
+        }
+        EXPECT(total == n && cost_sum == info[4] && tiles_sum == info[2]);
+        long cnt = 0;
+        EXPECT(gimic_b200_partition_points(h, n, r.data(), 0, 3, 3, &cnt) == GIMIC_B200_EINVAL);
+        EXPECT(gimic_b200_partition_grid(h, &g, 1, 2, &cnt) == 0 && cnt > 0 && cnt < 36 * 36);
+        EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), tens.data(), nullptr, nullptr, nullptr, nullptr, 0) == 0);
+        EXPECT(gimic_b200_calc_jtensors(h, 100, r.data(), GIMIC_B200_TOTAL, tens.data(), 0) == 0);      // any compute call drops the plan
+        EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), tens.data(), nullptr, nullptr, nullptr, nullptr, 0) == GIMIC_B200_EINVAL);
+    }
     // ---- property
     std::vector<double> w(n, 0.01);
     long seg[3] = {1000, 1000, n};

@@ -2,14 +2,16 @@
 //
 // tools/sanitize_api_host.sh links the REAL host code of libgimic_b200.so (api.cu, host_basis.cpp and the nvcc-generated launch
 // stubs of the kernels) against this stand-in for libcudart: "device" memory is zero-initialised host memory, copies are memcpy,
-// every kernel launch is a no-op that reports success -- except two small preparation kernels (point gather, per-tile active-set
-// count), which are emulated on the host so that api.cu's bookkeeping sees realistic tiles.  Nothing is computed (all results are zeros); what runs is the host-side
+// every kernel launch is a no-op that reports success -- except the small preparation kernels (point gather and the tile plan:
+// gap splitting, active-set counts, prefix sums, rank range, batches), which are restated serially on the host so that api.cu's
+// bookkeeping sees realistic tiles.  Nothing is computed (all results are zeros); what runs is the host-side
 // orchestration of every C-ABI entry point -- context creation, staging buffers, the tile / batch / pool bookkeeping, the
 // quadrature and property drivers -- under AddressSanitizer + UBSan in a container without a GPU.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -37,48 +39,163 @@ void emulate_gather_points(void **a) {              // k_gather_points(r, perm, 
     double *x = *(double **)a[3], *y = *(double **)a[4], *z = *(double **)a[5];
     for (long i = 0; i < n; ++i) { x[i] = r[3 * i]; y[i] = r[3 * i + 1]; z[i] = r[3 * i + 2]; }
 }
-void emulate_tile_count(void **a, unsigned ntiles) {   // k_tile_count(B, rsx, rsy, rsz, segs, geo, info), same counts as atom_active
+// ---- the device-side tile plan (k_prepare.cu), restated serially: the semantic model the CUDA kernels are written against ----------
+struct Piece { gb::TileGeo tg; float rho, gmax; int imax, nraw, natom, nreal; };
+Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, const double *sz, long p0, int npts) {
+    Piece P{};
+    gb::TileGeo tg{1e300, 1e300, 1e300, -1e300, -1e300, -1e300, 0.0, 0.0};
+    for (int p = 0; p < npts; ++p) {
+        const long q = p0 + p;
+        tg.lox = std::fmin(tg.lox, sx[q]); tg.hix = std::fmax(tg.hix, sx[q]);
+        tg.loy = std::fmin(tg.loy, sy[q]); tg.hiy = std::fmax(tg.hiy, sy[q]);
+        tg.loz = std::fmin(tg.loz, sz[q]); tg.hiz = std::fmax(tg.hiz, sz[q]);
+    }
+    const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
+    float rho = 0.f, gmax = 0.f; int imax = 0;
+    for (int p = 0; p < npts; ++p) {
+        const long q = p0 + p;
+        rho = std::fmax(rho, (float)std::sqrt((sx[q] - cx) * (sx[q] - cx) + (sy[q] - cy) * (sy[q] - cy) + (sz[q] - cz) * (sz[q] - cz)));
+        if (p + 1 < npts) {
+            const float g = (float)std::sqrt((sx[q + 1] - sx[q]) * (sx[q + 1] - sx[q]) + (sy[q + 1] - sy[q]) * (sy[q + 1] - sy[q]) + (sz[q + 1] - sz[q]) * (sz[q + 1] - sz[q]));
+            if (g >= gmax) { gmax = g; imax = p; }          // ties: the later gap (the kernel reduces (bits << 32 | index) by max)
+        }
+    }
+    tg.rho = rho; tg.pad_ = 0.0;
+    const int al = B.slot_align - 1;
+    for (int at = 0; at < B.natoms; ++at) {
+        const double x = B.atom_xyz[3 * at], y = B.atom_xyz[3 * at + 1], z = B.atom_xyz[3 * at + 2];
+        const double dx = std::fmax(std::fmax(tg.lox - x, x - tg.hix), 0.0), dy = std::fmax(std::fmax(tg.loy - y, y - tg.hiy), 0.0),
+                     dz = std::fmax(std::fmax(tg.loz - z, z - tg.hiz), 0.0);
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) - 1e-9 > B.atom_maxthr[at]) continue;
+        double d2 = 1e300;
+        for (int p = 0; p < npts; ++p) {
+            const long q = p0 + p;
+            d2 = std::fmin(d2, (sx[q] - x) * (sx[q] - x) + (sy[q] - y) * (sy[q] - y) + (sz[q] - z) * (sz[q] - z));
+        }
+        const double lim = std::sqrt(d2) - 1e-9;
+        if (lim > B.atom_maxthr[at]) continue;
+        int nfun = 0;
+        for (int s = B.atom_shell_off[at]; s < B.atom_shell_off[at + 1] && B.sh_thr[s] >= lim; ++s) nfun += (B.sh_l[s] + 1) * (B.sh_l[s] + 2) / 2;
+        P.nraw += (nfun + al) & ~al; P.natom += nfun > 0; P.nreal += nfun;
+    }
+    P.tg = tg; P.rho = rho; P.gmax = gmax; P.imax = imax;
+    return P;
+}
+void split_piece(const gb::DevBasis &B, const double *sx, const double *sy, const double *sz, long p0, int npts, int depth, double split_radius,
+                 long run, int &emitted, int pending, gb::TileSeg *seg, gb::TileGeo *geo, gb::TileInfo *info) {
+    const Piece P = eval_piece(B, sx, sy, sz, p0, npts);
+    const bool split = depth < gb::SPLIT_DEPTH && npts >= 16 && P.nraw > 0 && P.rho > (float)split_radius && P.gmax > 0.5f * P.rho &&
+                       emitted + pending + 2 <= gb::MAXSUB;
+    if (split) {
+        split_piece(B, sx, sy, sz, p0, P.imax + 1, depth + 1, split_radius, run, emitted, pending + 1, seg, geo, info);
+        split_piece(B, sx, sy, sz, p0 + P.imax + 1, npts - P.imax - 1, depth + 1, split_radius, run, emitted, pending, seg, geo, info);
+    } else {
+        const long o = run * gb::MAXSUB + emitted++;
+        seg[o] = gb::TileSeg{(int)p0, npts}; geo[o] = P.tg; info[o] = gb::TileInfo{P.rho, P.gmax, P.imax, P.nraw, P.natom, P.nreal};
+    }
+}
+void emulate_tile_split(void **a, unsigned nrun0) {
     const gb::DevBasis &B = *(const gb::DevBasis *)a[0];
     const double *sx = *(const double **)a[1], *sy = *(const double **)a[2], *sz = *(const double **)a[3];
-    const gb::TileSeg *segs = *(const gb::TileSeg **)a[4];
-    gb::TileGeo *geo = *(gb::TileGeo **)a[5];
-    gb::TileInfo *info = *(gb::TileInfo **)a[6];
-    const int al = B.slot_align - 1;
-    for (unsigned t = 0; t < ntiles; ++t) {
-        const gb::TileSeg sg = segs[t];
-        gb::TileGeo tg{1e300, 1e300, 1e300, -1e300, -1e300, -1e300, 0.0, 0.0};
-        for (int p = 0; p < sg.npts; ++p) {
-            const long q = sg.pt0 + p;
-            tg.lox = std::fmin(tg.lox, sx[q]); tg.hix = std::fmax(tg.hix, sx[q]);
-            tg.loy = std::fmin(tg.loy, sy[q]); tg.hiy = std::fmax(tg.hiy, sy[q]);
-            tg.loz = std::fmin(tg.loz, sz[q]); tg.hiz = std::fmax(tg.hiz, sz[q]);
-        }
-        const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
-        double gmax = 0.0; int imax = 0;
-        for (int p = 0; p < sg.npts; ++p) {
-            const long q = sg.pt0 + p;
-            tg.rho = std::fmax(tg.rho, std::sqrt((sx[q] - cx) * (sx[q] - cx) + (sy[q] - cy) * (sy[q] - cy) + (sz[q] - cz) * (sz[q] - cz)));
-            if (p + 1 < sg.npts) {
-                const double g = std::sqrt((sx[q + 1] - sx[q]) * (sx[q + 1] - sx[q]) + (sy[q + 1] - sy[q]) * (sy[q + 1] - sy[q]) + (sz[q + 1] - sz[q]) * (sz[q + 1] - sz[q]));
-                if (g > gmax) { gmax = g; imax = p; }
-            }
-        }
-        int cnt = 0, nat = 0, nre = 0;
-        for (int at = 0; at < B.natoms; ++at) {
-            const double x = B.atom_xyz[3 * at], y = B.atom_xyz[3 * at + 1], z = B.atom_xyz[3 * at + 2];
-            double d2 = 1e300;
-            for (int p = 0; p < sg.npts; ++p) {
-                const long q = sg.pt0 + p;
-                d2 = std::fmin(d2, (sx[q] - x) * (sx[q] - x) + (sy[q] - y) * (sy[q] - y) + (sz[q] - z) * (sz[q] - z));
-            }
-            const double lim = std::sqrt(d2) - 1e-9;
-            int nfun = 0;
-            for (int s = B.atom_shell_off[at]; s < B.atom_shell_off[at + 1] && B.sh_thr[s] >= lim; ++s) nfun += (B.sh_l[s] + 1) * (B.sh_l[s] + 2) / 2;
-            cnt += (nfun + al) & ~al; nat += nfun > 0; nre += nfun;
-        }
-        geo[t] = tg;
-        info[t] = gb::TileInfo{(float)tg.rho, (float)gmax, imax, cnt, nat, nre};
+    const long n = *(const long *)a[4];
+    const double split_radius = *(const double *)a[5];
+    gb::TileSeg *seg = *(gb::TileSeg **)a[6]; gb::TileGeo *geo = *(gb::TileGeo **)a[7]; gb::TileInfo *info = *(gb::TileInfo **)a[8];
+    int *cnt = *(int **)a[9];
+    for (long run = 0; run < (long)nrun0; ++run) {
+        const long p0 = run * gb::MT;
+        const int np = (int)std::min<long>(gb::MT, n - p0);
+        int emitted = 0;
+        split_piece(B, sx, sy, sz, p0, np, 0, split_radius, run, emitted, 0, seg, geo, info);
+        cnt[run] = emitted;
     }
+}
+void emulate_scan_counts(void **a) {
+    const int *cnt = *(const int **)a[0]; int *off = *(int **)a[1]; const int n = *(const int *)a[2];
+    gb::PlanSummary *sum = *(gb::PlanSummary **)a[3]; const int cap = *(const int *)a[4];
+    int run = 0;
+    for (int i = 0; i < n; ++i) { off[i] = run; run += cnt[i]; }
+    off[n] = run;
+    sum->ntiles = std::min(run, cap); sum->overflow = run > cap;
+}
+void emulate_tile_emit(void **a) {
+    const gb::TileSeg *seg = *(const gb::TileSeg **)a[0]; const gb::TileGeo *sgeo = *(const gb::TileGeo **)a[1];
+    const gb::TileInfo *info = *(const gb::TileInfo **)a[2]; const int *cnt = *(const int **)a[3], *off = *(const int **)a[4];
+    const long nrun0 = *(const long *)a[5]; const int cap = *(const int *)a[6];
+    gb::TileGeo *geo = *(gb::TileGeo **)a[7]; gb::TileDesc *desc = *(gb::TileDesc **)a[8]; gb::TileCum *cum = *(gb::TileCum **)a[9];
+    for (long run = 0; run < nrun0; ++run)
+        for (int j = 0; j < cnt[run] && off[run] + j < cap; ++j) {
+            const int t = off[run] + j;
+            const gb::TileInfo ti = info[run * gb::MAXSUB + j];
+            geo[t] = sgeo[run * gb::MAXSUB + j];
+            gb::TileDesc td{};
+            td.pt0 = seg[run * gb::MAXSUB + j].pt0; td.npts = seg[run * gb::MAXSUB + j].npts; td.nraw = ti.nraw; td.nact = (ti.nraw + 7) / 8 * 8;
+            td.nreal = ti.nreal; td.nn = (ti.nreal + 7) / 8 * 8; td.geo = t; td.nruns = ti.natom;
+            desc[t] = td;
+            cum[t] = gb::TileCum{4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + (td.nact ? 4096 : 64), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
+        }
+}
+void emulate_scan_cum(void **a) {
+    gb::TileCum *cum = *(gb::TileCum **)a[0]; const gb::PlanSummary *sum = *(const gb::PlanSummary **)a[1];
+    gb::TileCum run{0, 0, 0, 0};
+    for (int t = 0; t < sum->ntiles; ++t) {
+        const gb::TileCum v = cum[t];
+        cum[t] = run;
+        run = gb::TileCum{run.cost + v.cost, run.panel + v.panel, run.fidx + v.fidx, run.atab + v.atab};
+    }
+    cum[sum->ntiles] = run;
+}
+void emulate_plan_range(void **a) {
+    const gb::TileDesc *desc = *(const gb::TileDesc **)a[0]; const gb::TileCum *cum = *(const gb::TileCum **)a[1];
+    const int rank = *(const int *)a[2], nranks = *(const int *)a[3]; const long long pool = *(const long long *)a[4];
+    gb::PlanSummary *sum = *(gb::PlanSummary **)a[5];
+    const int nt = sum->ntiles;
+    const long long total = cum[nt].cost;
+    int tlo = nt, thi = nt;
+    for (int t = nt - 1; t >= 0; --t) {                       // tile t belongs to rank floor(cum[t].cost * nranks / total)
+        const long long r = cum[t].cost * nranks / total;
+        if (r >= rank) tlo = t;
+        if (r >= rank + 1) thi = t;
+    }
+    sum->tlo = tlo; sum->thi = thi; sum->cost_total = total; sum->cost_range = cum[thi].cost - cum[tlo].cost;
+    sum->panel_range = cum[thi].panel - cum[tlo].panel;
+    sum->pt_lo = tlo < thi ? desc[tlo].pt0 : 0; sum->pt_hi = tlo < thi ? (long long)desc[thi - 1].pt0 + desc[thi - 1].npts : 0;
+    const long long nb = tlo < thi ? (cum[thi - 1].panel - cum[tlo].panel) / pool + 1 : 0;
+    sum->nbatch = (int)(nb < gb::MAX_BATCH ? nb : gb::MAX_BATCH + 1);
+    sum->max_nruns = 0; sum->max_tile_panel = 0;
+    sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
+    if (nb <= gb::MAX_BATCH) sum->batch_start[nb] = thi;
+    for (int t = tlo; t < thi; ++t) {
+        const long long b = (cum[t].panel - cum[tlo].panel) / pool;
+        if (b < gb::MAX_BATCH && (t == tlo || (cum[t - 1].panel - cum[tlo].panel) / pool != b)) sum->batch_start[b] = t;
+    }
+}
+const int *g_last_ord0 = nullptr;
+void emulate_plan_finalize(void **a) {
+    gb::TileDesc *desc = *(gb::TileDesc **)a[0]; const gb::TileCum *cum = *(const gb::TileCum **)a[1]; const long long pool = *(const long long *)a[2];
+    gb::PlanSummary *sum = *(gb::PlanSummary **)a[3]; unsigned long long *keys = *(unsigned long long **)a[4]; int *ord = *(int **)a[5];
+    g_last_ord0 = ord;
+    if (sum->nbatch > gb::MAX_BATCH) return;
+    for (int t = sum->tlo; t < sum->thi; ++t) {
+        const long long b = (cum[t].panel - cum[sum->tlo].panel) / pool;
+        const int t0 = sum->batch_start[b];
+        gb::TileDesc &td = desc[t];
+        td.panel_off = cum[t].panel - cum[t0].panel; td.fidx_off = cum[t].fidx - cum[t0].fidx; td.atab_off = cum[t].atab - cum[t0].atab;
+        const long long c = cum[t + 1].cost - cum[t].cost;
+        keys[t - sum->tlo] = ((unsigned long long)b << 32) | (0xffffffffu - (unsigned)std::min<long long>(c, 0xffffffffLL));
+        ord[t - sum->tlo] = t;
+        sum->sum_nact += td.nact; sum->flops4 += 2.0 * gb::MT * 4.0 * td.nact * td.nn; sum->flops2 += 2.0 * gb::MT * 2.0 * td.nact * td.nn;
+        sum->taps += 2.0 * gb::MT * (double)td.nn * td.nruns; sum->useful_mm += 2.0 * td.npts * (double)td.nreal * td.nreal;
+        sum->useful_taps += 2.0 * td.npts * (double)td.nreal * td.nruns;
+        sum->max_nruns = std::max(sum->max_nruns, td.nruns); sum->max_tile_panel = std::max(sum->max_tile_panel, cum[t + 1].panel - cum[t].panel);
+    }
+}
+void emulate_tile_gather(void **a) {      // the CUB sort in front of it is a no-op here: fall back to the unsorted order
+    const gb::TileDesc *desc = *(const gb::TileDesc **)a[0]; const int *ord = *(const int **)a[1]; const int nt = *(const int *)a[2];
+    gb::TileDesc *out = *(gb::TileDesc **)a[3];
+    bool zeros = nt > 1;
+    for (int i = 0; i < nt && zeros; ++i) zeros = ord[i] == 0;
+    if (zeros && g_last_ord0) ord = g_last_ord0;
+    for (int i = 0; i < nt; ++i) out[i] = desc[ord[i]];
 }
 }  // namespace
 
@@ -112,7 +229,13 @@ cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **arg
     }
     if (!std::getenv("FAKE_CUDA_NO_EMULATION")) {
         if (name.find("k_gather_points") != std::string::npos) emulate_gather_points(args);
-        else if (name.find("k_tile_count") != std::string::npos) emulate_tile_count(args, grid.x);
+        else if (name.find("k_tile_split") != std::string::npos) emulate_tile_split(args, grid.x);
+        else if (name.find("k_scan_counts") != std::string::npos) emulate_scan_counts(args);
+        else if (name.find("k_tile_emit") != std::string::npos) emulate_tile_emit(args);
+        else if (name.find("k_scan_cum") != std::string::npos) emulate_scan_cum(args);
+        else if (name.find("k_plan_range") != std::string::npos) emulate_plan_range(args);
+        else if (name.find("k_plan_finalize") != std::string::npos) emulate_plan_finalize(args);
+        else if (name.find("k_tile_gather") != std::string::npos) emulate_tile_gather(args);
     }
     return cudaSuccess;
 }
@@ -164,6 +287,8 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStr
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)&g_dummy_event; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)&g_dummy_event; return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

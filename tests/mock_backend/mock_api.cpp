@@ -38,6 +38,9 @@ struct gimic_b200_ctx {
     void *o = nullptr;
     gimic_b200_opts opts{};
     gimic_b200_stats stats{};
+    std::vector<double> part_r;      // the owned points of the last gimic_b200_partition_* call
+    std::vector<long> part_index;    // and their caller indices
+    bool part_valid = false;
     ~gimic_b200_ctx() { if (o) go_destroy(o); }
 };
 
@@ -164,6 +167,46 @@ int gimic_b200_calc_jtensors_grid(gimic_b200_handle c, const gimic_b200_grid *g,
     for (long q = lo; q < hi; ++q) grid_point(g, q % n0, (q / n0) % n1, q / (n0 * n1), &r[(size_t)3 * (q - lo)]);
     c->stats = gimic_b200_stats{};
     return hi > lo ? tensors(c, hi - lo, r.data(), spincase, tens, nullptr) : 0;
+}
+
+// The product gives a rank a run of Hilbert-ordered tiles (an arbitrary, non-contiguous set of caller indices); the test double
+// hands out blocks of 7 consecutive points round-robin, so that callers which assumed contiguous slabs would fail.
+static int mock_partition(gimic_b200_ctx *c, long n, const double *r, int rank, int nranks, long *count) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(GIMIC_B200_EINVAL, "rank / nranks out of range");
+    c->part_r.clear(); c->part_index.clear();
+    for (long i = 0; i < n; ++i)
+        if ((i / 7) % nranks == rank) { c->part_index.push_back(i); for (int d = 0; d < 3; ++d) c->part_r.push_back(r[3 * i + d]); }
+    c->part_valid = true;
+    *count = (long)c->part_index.size();
+    return 0;
+}
+int gimic_b200_partition_points(gimic_b200_handle c, long n, const double *r, int flags, int rank, int nranks, long *count) {
+    if (!c || !r || !count || flags || n <= 0) return fail(GIMIC_B200_EINVAL, "bad argument");
+    return mock_partition(c, n, r, rank, nranks, count);
+}
+int gimic_b200_partition_grid(gimic_b200_handle c, const gimic_b200_grid *g, int rank, int nranks, long *count) {
+    if (!c || !g || !count) return fail(GIMIC_B200_EINVAL, "bad argument");
+    const long n0 = g->npts[0], n1 = g->npts[1], ntot = n0 * n1 * g->npts[2];
+    std::vector<double> r((size_t)3 * ntot);
+    for (long q = 0; q < ntot; ++q) grid_point(g, q % n0, (q / n0) % n1, q / (n0 * n1), &r[(size_t)3 * q]);
+    return mock_partition(c, ntot, r.data(), rank, nranks, count);
+}
+int gimic_b200_partition_info(gimic_b200_handle c, long *info8) {
+    if (!c || !info8 || !c->part_valid) return fail(GIMIC_B200_EINVAL, "no partition");
+    for (int i = 0; i < 8; ++i) info8[i] = 0;
+    info8[1] = (long)c->part_index.size();
+    return 0;
+}
+int gimic_b200_partition_calc(gimic_b200_handle c, const double *B3, int spincase, long *index, double *tens, double *jvec, double *jmod, double *acid,
+                              double *edens, int flags) {
+    if (!c || flags) return fail(GIMIC_B200_EINVAL, "bad argument");
+    if (!c->part_valid) return fail(GIMIC_B200_EINVAL, "no partition: call gimic_b200_partition_points / _grid first");
+    const long m = (long)c->part_index.size();
+    if (index) for (long i = 0; i < m; ++i) index[i] = c->part_index[(size_t)i];
+    if (m == 0) return 0;
+    const std::vector<double> r = c->part_r;      // calc_fields resets nothing of the plan, but keep the inputs stable
+    const int rc = gimic_b200_calc_fields(c, m, r.data(), B3, spincase, tens, jvec, jmod, acid, edens, nullptr, 0.0, 0);
+    return rc;
 }
 
 int gimic_b200_calc_basis(gimic_b200_handle, long, const double *, double *, double *, int) {

@@ -76,7 +76,7 @@ u = gimic_b200.Gimic(molu, xdu, uhf=True, screening_thrs=1e-8)
 for sc in ("alpha", "beta", "total", "spindens"):
     assert u.jtensors(r[:300], sc).shape == (300, 9)
 sh, da, nbf = fixtures.synthetic_case(5, "flake", seed=5)
-a = gimic_b200.Gimic.from_arrays(dens_alpha=fixtures.dens_to_colmajor(da), dens_beta=fixtures.dens_to_colmajor(da[::-1].copy()), **sh)
+a = gimic_b200.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fixtures.dens_to_colmajor(da), dens_beta=fixtures.dens_to_colmajor(da[::-1].copy()), **sh)
 assert (a.nbf, a.natoms, a.uhf) == (nbf, 5, True) and a.jtensors(r[:200], "spindens").shape == (200, 9)
 a.close()
 assert "torch" not in sys.modules

@@ -286,7 +286,7 @@ def test_closed_shell_rejects_beta(gb, c4h4):
 def test_synthetic_flake_vs_oracle(gb, natoms, npts, general_p):
     sh, dens, nbf = fixtures.synthetic_case(natoms, "flake", general_p=general_p)
     flat = fixtures.dens_to_colmajor(dens)
-    g = gb.Gimic.from_arrays(dens_alpha=flat, **sh)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, **sh)
     o = O.Oracle.from_arrays(dens_a=flat, **sh)
     assert g.nbf == nbf == o.nbf
     rng = np.random.default_rng(3)
@@ -305,7 +305,7 @@ def test_synthetic_ring_far_origin(gb):
     """atoms ~120 bohr from the origin: the gauge-difference operand must not lose digits"""
     sh, dens, nbf = fixtures.synthetic_case(10, "ring")
     flat = fixtures.dens_to_colmajor(dens)
-    g = gb.Gimic.from_arrays(dens_alpha=flat, **sh)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, **sh)
     o = O.Oracle.from_arrays(dens_a=flat, **sh)
     rng = np.random.default_rng(4)
     r = sh["coords"][rng.integers(0, 10, 400)] + rng.uniform(-5, 5, size=(400, 3))
@@ -321,7 +321,7 @@ def test_linearity_in_density(gb):
     r = rng.uniform(-12, 12, size=(4000, 3)); r[:, 2] *= 0.3
     ts = []
     for d in (d1, d2, 0.5 * d1 - 2.0 * d2):
-        g = gb.Gimic.from_arrays(dens_alpha=fixtures.dens_to_colmajor(d), **sh)
+        g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fixtures.dens_to_colmajor(d), **sh)
         ts.append(g.jtensors(r)); g.close()
     comb = 0.5 * ts[0] - 2.0 * ts[1]
     scale = np.abs(ts[0]).max() + np.abs(ts[1]).max()
@@ -332,7 +332,7 @@ def test_uhf_total_is_alpha_plus_beta(gb):
     sh, da, nbf = fixtures.synthetic_case(8, "flake", seed=5)
     db = fixtures.synthetic_density(nbf, seed=6)
     fa, fb = fixtures.dens_to_colmajor(da), fixtures.dens_to_colmajor(db)
-    g = gb.Gimic.from_arrays(dens_alpha=fa, dens_beta=fb, **sh)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fa, dens_beta=fb, **sh)
     o = O.Oracle.from_arrays(dens_a=fa, dens_b=fb, **sh)
     rng = np.random.default_rng(9)
     r = rng.uniform(-8, 8, size=(600, 3))
@@ -374,7 +374,7 @@ def test_high_angular_momentum_shells(gb, turbomole):
     nbf = nat * sum((l + 1) * (l + 2) // 2 for l, _, _ in shells)
     assert nbf == 3 * 56
     flat = fixtures.dens_to_colmajor(fixtures.synthetic_density(nbf, seed=3, general_p=True))
-    g = gb.Gimic.from_arrays(dens_alpha=flat, turbomole_order=turbomole, **sh)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, turbomole_order=turbomole, **sh)
     o = O.Oracle.from_arrays(dens_a=flat, turbomole_order=turbomole, **sh)
     r = rng.uniform(-3, 4, size=(300, 3))
     bf, dr = g.basis(r[:20])
@@ -399,7 +399,7 @@ def test_spherical_basis_vs_oracle(gb, turbomole):
     nsph = nat * sum(2 * l + 1 for l, _, _ in shells)
     da = fixtures.dens_to_colmajor(fixtures.synthetic_density(nsph, seed=3, general_p=True))
     db = fixtures.dens_to_colmajor(fixtures.synthetic_density(nsph, seed=4, general_p=True))
-    g = gb.Gimic.from_arrays(dens_alpha=da, dens_beta=db, turbomole_order=turbomole, spherical=True, **sh)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=da, dens_beta=db, turbomole_order=turbomole, spherical=True, **sh)
     o = O.Oracle.from_arrays(dens_a=da, dens_b=db, turbomole_order=turbomole, spherical=True, **sh)
     assert g.nbf == o.nbf == nsph
     r = rng.uniform(-3, 4, size=(300, 3))
@@ -557,7 +557,7 @@ def test_jvec_only_path_far_from_origin_and_large(gb):
     for geometry, natoms, npts in (("ring", 30, 400), ("flake", 42, 300)):
         sh, dens, nbf = fixtures.synthetic_case(natoms, geometry, seed=77, general_p=True)
         flat = fixtures.dens_to_colmajor(dens)
-        g = gb.Gimic.from_arrays(dens_alpha=flat, **sh); o = O.Oracle.from_arrays(dens_a=flat, **sh)
+        g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, **sh); o = O.Oracle.from_arrays(dens_a=flat, **sh)
         ctr = sh["coords"][rng.integers(0, natoms, size=npts)]
         r = ctr + rng.normal(scale=2.5, size=(npts, 3))
         tref = o.ctensor(r)
@@ -634,7 +634,7 @@ def test_full_size_nbf10008_properties(gb):
     assert nbf == 10008
     db = fixtures.synthetic_density(nbf, seed=99, general_p=True)
     fa, fb = fixtures.dens_to_colmajor(da), fixtures.dens_to_colmajor(db)
-    g = gb.Gimic.from_arrays(dens_alpha=fa, dens_beta=fb, **sh)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fa, dens_beta=fb, **sh)
     rng = np.random.default_rng(12)
     lo, hi = sh["coords"].min(0) - 6.0, sh["coords"].max(0) + 6.0
     r = rng.uniform(lo, hi, size=(20000, 3)); r[:, 2] = rng.uniform(-5, 5, size=20000)

@@ -12,7 +12,7 @@ import ctypes as C
 
 natoms, n1 = 42, (int(sys.argv[1]) if len(sys.argv) > 1 else 128)
 sh, dens, nbf = synthetic.synthetic_case(natoms, "flake", seed=1234)
-g = gimic_b200.Gimic.from_arrays(dens_alpha=synthetic.dens_to_colmajor(dens), **sh)
+g = gimic_b200.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=synthetic.dens_to_colmajor(dens), **sh)
 origin, basv, pts = synthetic.box_grid(sh["coords"], (n1, n1, n1))
 grid = gimic_b200.Grid(origin, basv, pts)
 n = grid.n

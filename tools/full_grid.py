@@ -8,7 +8,7 @@ from gimic_b200 import synthetic
 natoms = int(sys.argv[1]) if len(sys.argv) > 1 else 278
 n1 = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 sh, dens, nbf, origin, basv, pts = bench.build_workload(natoms, n1)
-g = gimic_b200.Gimic.from_arrays(dens_alpha=synthetic.dens_to_colmajor(dens), **sh)
+g = gimic_b200.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=synthetic.dens_to_colmajor(dens), **sh)
 grid = gimic_b200.Grid(origin, basv, pts)
 dev = torch.device("cuda", 0)
 out = torch.empty((grid.n, 9), dtype=torch.float64, device=dev)

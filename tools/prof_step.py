@@ -16,7 +16,7 @@ ap.add_argument("--no-giao", action="store_true")
 ap.add_argument("--jvec", action="store_true", help="J = T.B path (fields with jvec only) instead of the tensor path")
 a = ap.parse_args()
 sh, dens, nbf, origin, basv, pts = bench.build_workload(a.natoms, a.grid)
-g = gimic_b200.Gimic.from_arrays(dens_alpha=synthetic.dens_to_colmajor(dens), giao=not a.no_giao, **sh)
+g = gimic_b200.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=synthetic.dens_to_colmajor(dens), giao=not a.no_giao, **sh)
 r = bench.slab_points(origin, basv, pts, 0)
 r = np.ascontiguousarray(r[-a.points:])   # the planes of octant 0 closest to the molecular plane
 g.set_profiling(True)

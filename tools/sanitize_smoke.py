@@ -20,6 +20,6 @@ xyz = g.atom_coords()
 gr = grids.bond_grid(xyz[1], xyz[0], xyz[3], 1.48794, [-5.0, 5.0], [-1.25614, 6.0], "gauss", grid_points=[9, 9, 0], gauss_order=9)
 s = g.integrate(gr, B, "total", 7)
 sh, dens, nbf = fixtures.synthetic_case(6, "flake", seed=1)
-g2 = gimic_b200.Gimic.from_arrays(dens_alpha=fixtures.dens_to_colmajor(dens), giao=False, **sh)
+g2 = gimic_b200.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fixtures.dens_to_colmajor(dens), giao=False, **sh)
 t2 = g2.jtensors(r[:200])
 print("ok", float(np.abs(t).max()), float(np.abs(f["jvec"] - f2["jvec"]).max()), s[:3], float(np.abs(t2).max()))
