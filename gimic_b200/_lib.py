@@ -19,7 +19,7 @@ LEGACY_SYMBOLS = ["gimic_init", "gimic_finalize", "gimic_set_uhf", "gimic_set_ma
                   "gimic_get_gauss_points", "mkgausspoints"]
 API_SYMBOLS = ["gimic_b200_default_opts", "gimic_b200_create", "gimic_b200_create_from_arrays", "gimic_b200_destroy", "gimic_b200_device_count",
                "gimic_b200_nbf", "gimic_b200_natoms", "gimic_b200_atom_coords", "gimic_b200_is_uhf",
-               "gimic_b200_calc_jtensors", "gimic_b200_calc_basis", "gimic_b200_calc_fields", "gimic_b200_fields_from_tensors", "gimic_b200_jmod_from_jvec",
+               "gimic_b200_calc_jtensors", "gimic_b200_calc_basis", "gimic_b200_calc_basis_tiles", "gimic_b200_calc_fields", "gimic_b200_fields_from_tensors", "gimic_b200_jmod_from_jvec",
                "gimic_b200_calc_jtensors_grid", "gimic_b200_partition_points", "gimic_b200_partition_grid", "gimic_b200_partition_calc", "gimic_b200_partition_info", "gimic_b200_integrate", "gimic_b200_integrate_batch", "gimic_b200_property", "gimic_b200_property_integrand", "gimic_b200_gauss_points",
                "gimic_b200_mol_geometry", "gimic_b200_mol_summary", "gimic_b200_c2s_rows", "gimic_b200_convert_xdens", "gimic_b200_format_e", "gimic_b200_format_f",
                "gimic_b200_get_stats", "gimic_b200_set_profiling", "gimic_b200_last_error", "gimic_b200_version"]
@@ -43,7 +43,8 @@ class Stats(C.Structure):
     _fields_ = [("n_points", C.c_long), ("n_tiles", C.c_long), ("sum_nact", C.c_double), ("executed_flops", C.c_double),
                 ("dense_flops", C.c_double), ("ms_sort", C.c_float), ("ms_tiles", C.c_float), ("ms_basis", C.c_float),
                 ("ms_contract", C.c_float), ("ms_fields", C.c_float), ("ms_total", C.c_float), ("launches", C.c_long),
-                ("contract_launches", C.c_long), ("useful_flops", C.c_double)]
+                ("contract_launches", C.c_long), ("useful_flops", C.c_double), ("ms_plan", C.c_float), ("ms_span", C.c_float),
+                ("panel_bytes", C.c_double)]
 
 
 class GimicB200Error(RuntimeError):
@@ -74,6 +75,7 @@ def lib():
     L.gimic_b200_atom_coords.argtypes = [vp, dp]
     L.gimic_b200_calc_jtensors.argtypes = [vp, C.c_long, vp, C.c_int, vp, C.c_int]
     L.gimic_b200_calc_basis.argtypes = [vp, C.c_long, vp, vp, vp, C.c_int]
+    L.gimic_b200_calc_basis_tiles.argtypes = [vp, C.c_long, vp, vp, vp, ip]
     L.gimic_b200_calc_fields.argtypes = [vp, C.c_long, vp, dp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int]
     L.gimic_b200_fields_from_tensors.argtypes = [vp, C.c_long, vp, vp, dp, vp, vp, vp, C.c_int]
     L.gimic_b200_jmod_from_jvec.argtypes = [vp, C.c_long, vp, vp, dp, vp, C.c_int]

@@ -81,8 +81,10 @@ struct gimic_b200_ctx {
     bool profiling = false;
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_call[2] = {};
+    cudaEvent_t ev_plan[2] = {};       // span of the last gimic_b200_partition_* call
     cudaEvent_t ev_chunk[4] = {};      // [0,1] results of buffer 0/1 ready (compute stream), [2,3] buffer 0/1 drained (copy stream)
     std::vector<cudaEvent_t> evpool;   // per-batch (basis, contract) stamps, resolved at the end of a call
+    std::vector<cudaEvent_t> evbatch;  // per-batch "rows ready" events of the overlapped device->host drain
     gimic_b200_stats stats{};
     std::string mol_path, xdens_path;   // for the legacy set_uhf-after-init path
 
@@ -98,7 +100,9 @@ struct gimic_b200_ctx {
         if (h_summary) cudaFreeHost(h_summary);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : evpool) cudaEventDestroy(e);
+        for (auto &e : evbatch) cudaEventDestroy(e);
         for (auto &e : ev_call) if (e) cudaEventDestroy(e);
+        for (auto &e : ev_plan) if (e) cudaEventDestroy(e);
         for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -200,6 +204,7 @@ int init_device(gimic_b200_ctx *c) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->ev_call) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : c->ev_plan) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost((void **)&c->h_summary, sizeof(gb::PlanSummary)));
     // panel pool: one batch (one k_basis + one k_jtensor launch) per ~pool of Phi/dPhi panels.  8 GB is the configuration of the
@@ -392,7 +397,7 @@ struct Outputs {
 
 // exec_plan: basis panels + contraction for the planned tiles, batch by batch.  compact == false: results go to the caller's
 // point order (row perm[p] of the outputs, which hold plan.n rows); compact == true: row p - pt_lo (plan.count() rows).
-int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact) {
+int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, const std::function<int(int, long, long)> *after_batch = nullptr) {
     using namespace gb;
     const Plan &P = c->plan;
     if (!P.valid) return fail(GIMIC_B200_EINVAL, "no tile plan: call gimic_b200_partition_points / _grid first");
@@ -436,6 +441,8 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact) {
         c->stats.launches += 2;
         c->stats.contract_launches += 1;
         if (prof) cudaEventRecord(c->evpool[3 * b + 2], st);
+        // a batch is a contiguous run of Hilbert-ordered tiles = of compact output rows: the caller may start draining them
+        if (after_batch) if (int rc = (*after_batch)(b, (long)(S.batch_pt[b] - S.pt_lo), (long)(S.batch_pt[b + 1] - S.pt_lo))) return rc;
     }
     if (prof) {
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -448,6 +455,7 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact) {
     }
     const double tapw = giao ? (o.jpath ? 1.0 : 3.0) : 0.0, planes = o.jpath ? 2.0 : 4.0;
     c->stats.n_points += P.count(); c->stats.n_tiles += nt; c->stats.sum_nact += S.sum_nact;
+    c->stats.panel_bytes += 8.0 * (double)S.panel_range;
     c->stats.executed_flops += (o.jpath ? S.flops2 : S.flops4) + tapw * S.taps;
     c->stats.useful_flops += planes * S.useful_mm + tapw * S.useful_taps;
     const double nbf = c->hb.nbf;
@@ -703,14 +711,19 @@ int gimic_b200_fields_from_tensors(gimic_b200_handle c, long n, const double *r,
         double *f = c->f_tmp.as<double>();
         d_jvec = jvec ? f : nullptr; d_jmod = jmod ? f + 3 * nf : nullptr; d_acid = acid ? f + 4 * nf : nullptr;
     }
+    reset_stats(c);
+    cudaEventRecord(c->ev[0], st);
     gb::launch_fields(n, d_r, d_t, B3, d_jvec, d_jmod, d_acid, st);
+    cudaEventRecord(c->ev[1], st);
     CUDA_TRY(cudaGetLastError());
+    c->stats.launches = 1; c->stats.n_points = n;
     if (!dev) {
         if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec, d_jvec, nf * 24, cudaMemcpyDeviceToHost, st));
         if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod, d_jmod, nf * 8, cudaMemcpyDeviceToHost, st));
         if (acid) CUDA_TRY(cudaMemcpyAsync(acid, d_acid, nf * 8, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->stats.ms_fields, c->ev[0], c->ev[1]);      // the kernel alone (HBM roofline of the field pass)
     return 0;
 }
 
@@ -793,9 +806,11 @@ int gimic_b200_partition_points(gimic_b200_handle c, long n, const double *r, in
     if (n <= 0) return fail(GIMIC_B200_EINVAL, "no points");
     CUDA_TRY(cudaSetDevice(c->device));
     reset_stats(c);
+    cudaEventRecord(c->ev_plan[0], c->stream);
     const double *d_r = nullptr;
     if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, flags, &d_r)) return rc;
     if (int rc = build_plan(c, n, d_r, rank, nranks)) return rc;
+    cudaEventRecord(c->ev_plan[1], c->stream);
     *count = c->plan.count();
     return 0;
 }
@@ -806,11 +821,13 @@ int gimic_b200_partition_grid(gimic_b200_handle c, const gimic_b200_grid *g, int
     CUDA_TRY(cudaSetDevice(c->device));
     reset_stats(c);
     const double *ob, *p0, *p1, *p2, *w0;
+    cudaEventRecord(c->ev_plan[0], c->stream);
     if (int rc = grid_upload(c, g, &ob, &p0, &p1, &p2, &w0)) return rc;
     if (c->r_in.ensure((size_t)3 * n * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (grid points)");
     gb::launch_grid_points(ob, p0, p1, p2, g->npts[0], g->npts[1], g->npts[2], 0, n, c->r_in.as<double>(), c->stream);
     c->stats.launches += 1;
     if (int rc = build_plan(c, n, c->r_in.as<double>(), rank, nranks)) return rc;
+    cudaEventRecord(c->ev_plan[1], c->stream);
     *count = c->plan.count();
     return 0;
 }
@@ -852,22 +869,38 @@ int gimic_b200_partition_calc(gimic_b200_handle c, const double *B3, int spincas
         o.jvec = jvec ? f : nullptr; o.jmod = jmod ? f + 3 * nf : nullptr; o.acid = acid ? f + 4 * nf : nullptr; o.edens = edens ? f + 5 * nf : nullptr;
         d_index = index ? reinterpret_cast<long *>(f + 6 * nf) : nullptr;
     }
-    if (o.tens || o.jvec || o.jmod || o.acid || o.edens)
-        if (int rc = exec_plan(c, spincase, o, true)) return rc;
+    cudaStream_t cs = c->copy_stream;
     if (index) { gb::launch_perm_index(c->vals1.as<int>() + c->plan.sum.pt_lo, m, d_index, st); c->stats.launches += 1; }
+    // host outputs: the rows of a finished panel batch are copied out on the copy stream while the next batch is contracted
+    std::vector<cudaEvent_t> &evb = c->evbatch;
+    const std::function<int(int, long, long)> drain = [&](int b, long lo, long hi) -> int {
+        if (hi <= lo) return 0;
+        while (evb.size() <= (size_t)b) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evb.push_back(e); }
+        CUDA_TRY(cudaEventRecord(evb[b], st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, evb[b], 0));
+        const size_t k = (size_t)(hi - lo);
+        if (tens) CUDA_TRY(cudaMemcpyAsync(tens + 9 * lo, o.tens + 9 * lo, k * 72, cudaMemcpyDeviceToHost, cs));
+        if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec + 3 * lo, o.jvec + 3 * lo, k * 24, cudaMemcpyDeviceToHost, cs));
+        if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod + lo, o.jmod + lo, k * 8, cudaMemcpyDeviceToHost, cs));
+        if (acid) CUDA_TRY(cudaMemcpyAsync(acid + lo, o.acid + lo, k * 8, cudaMemcpyDeviceToHost, cs));
+        if (edens) CUDA_TRY(cudaMemcpyAsync(edens + lo, o.edens + lo, k * 8, cudaMemcpyDeviceToHost, cs));
+        return 0;
+    };
+    if (o.tens || o.jvec || o.jmod || o.acid || o.edens)
+        if (int rc = exec_plan(c, spincase, o, true, dev ? nullptr : &drain)) return rc;
     CUDA_TRY(cudaGetLastError());
     if (!dev) {
-        if (tens) CUDA_TRY(cudaMemcpyAsync(tens, o.tens, nf * 72, cudaMemcpyDeviceToHost, st));
-        if (jvec) CUDA_TRY(cudaMemcpyAsync(jvec, o.jvec, nf * 24, cudaMemcpyDeviceToHost, st));
-        if (jmod) CUDA_TRY(cudaMemcpyAsync(jmod, o.jmod, nf * 8, cudaMemcpyDeviceToHost, st));
-        if (acid) CUDA_TRY(cudaMemcpyAsync(acid, o.acid, nf * 8, cudaMemcpyDeviceToHost, st));
-        if (edens) CUDA_TRY(cudaMemcpyAsync(edens, o.edens, nf * 8, cudaMemcpyDeviceToHost, st));
         if (index) CUDA_TRY(cudaMemcpyAsync(index, d_index, nf * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(c->ev_chunk[2], cs));
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_chunk[2], 0));      // the call's end stamp covers the last copy
     }
     cudaEventRecord(c->ev_call[1], st);
     CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(cs));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev_call[0], c->ev_call[1]);
     c->stats.ms_total = ms;
+    cudaEventElapsedTime(&c->stats.ms_plan, c->ev_plan[0], c->ev_plan[1]);
+    cudaEventElapsedTime(&c->stats.ms_span, c->ev_plan[0], c->ev_call[1]);
     return 0;
 }
 
@@ -1021,6 +1054,42 @@ int gimic_b200_calc_basis(gimic_b200_handle c, long n, const double *r, double *
         if (dr) CUDA_TRY(cudaMemcpyAsync(dr, d_dr, (size_t)n * nb * 24, cudaMemcpyDeviceToHost, c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// The same vectors through the HOT-PATH kernels: Hilbert sort, tiles, k_basis panels (what the contraction consumes), scattered
+// back into the dense layout.  Exists so that tests can hold k_basis itself -- not only k_basis_dense -- to the oracle.
+int gimic_b200_calc_basis_tiles(gimic_b200_handle c, long n, const double *r, double *bf, double *dr, int *tile_info3) {
+    if (!c || (n > 0 && !r) || (!bf && !dr)) return fail(GIMIC_B200_EINVAL, "null argument");
+    if (n <= 0) return 0;
+    if (c->hb.spherical) return fail(GIMIC_B200_EINVAL, "calc_basis_tiles: cartesian contexts only (spherical=on folds the projection into the densities)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    reset_stats(c);
+    const size_t nb = (size_t)c->hb.nbf;
+    const double *d_r = nullptr;
+    if (int rc = stage_in(c, c->r_in, r, (size_t)3 * n, 0, &d_r)) return rc;
+    if (int rc = build_plan(c, n, d_r, 0, 1)) return rc;
+    c->plan.valid = false;
+    const gb::PlanSummary &S = c->plan.sum;
+    if (S.nbatch != 1) return fail(GIMIC_B200_EINVAL, "calc_basis_tiles: the panels of all points must fit one pool batch (pass fewer points)");
+    if (c->f_tmp.ensure((size_t)n * nb * 4 * 8)) return fail(GIMIC_B200_ENOMEM, "device allocation failed (basis vectors)");
+    double *d_bf = c->f_tmp.as<double>(), *d_dr = d_bf + (size_t)n * nb;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemsetAsync(d_bf, 0, (size_t)n * nb * 4 * 8, st));
+    const size_t pool_doubles = (size_t)std::max<long long>(2, S.panel_range), slots = pool_doubles / (4 * gb::LDP) + 16;
+    if (c->panel.ensure(pool_doubles * 8) || c->fidx.ensure(2 * slots * 4) || c->atab.ensure(slots * sizeof(gb::TileAtom)))
+        return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
+    const int nt = S.thi - S.tlo;
+    const double *rsx = c->rs.as<double>(), *rsy = rsx + n, *rsz = rsy + n;
+    gb::launch_basis(c->db, c->tiles.as<gb::TileDesc>(), nt, S.max_nruns, c->geo.as<gb::TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(),
+                     c->opts.giao ? c->atab.as<gb::TileAtom>() : nullptr, st);
+    gb::launch_panel_scatter(c->tiles.as<gb::TileDesc>(), nt, c->panel.as<double>(), c->fidx.as<int>(), c->vals1.as<int>(), c->d_f2user, (int)nb,
+                             bf ? d_bf : nullptr, dr ? d_dr : nullptr, st);
+    CUDA_TRY(cudaGetLastError());
+    if (bf) CUDA_TRY(cudaMemcpyAsync(bf, d_bf, (size_t)n * nb * 8, cudaMemcpyDeviceToHost, st));
+    if (dr) CUDA_TRY(cudaMemcpyAsync(dr, d_dr, (size_t)n * nb * 24, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (tile_info3) { tile_info3[0] = nt; tile_info3[1] = (int)(S.sum_nact / std::max(nt, 1)); tile_info3[2] = S.max_nruns; }
     return 0;
 }
 

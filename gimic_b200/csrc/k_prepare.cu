@@ -338,14 +338,14 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
         sum->nbatch = (int)(nb < MAX_BATCH ? nb : MAX_BATCH + 1);      // MAX_BATCH + 1: too many, the host refuses
         sum->max_nruns = 0; sum->max_tile_panel = 0;
         sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
-        if (nb <= MAX_BATCH) sum->batch_start[nb] = thi;
+        if (nb <= MAX_BATCH) { sum->batch_start[nb] = thi; sum->batch_pt[nb] = sum->pt_hi; }
     }
     __syncthreads();
     const int tlo = s_lo, thi = s_hi;
     const long long base = cum[tlo].panel;
     for (int t = tlo + threadIdx.x + blockIdx.x * blockDim.x; t < thi; t += blockDim.x * gridDim.x) {
         const long long b = (cum[t].panel - base) / pool_doubles;
-        if (b < MAX_BATCH && (t == tlo || (cum[t - 1].panel - base) / pool_doubles != b)) sum->batch_start[b] = t;
+        if (b < MAX_BATCH && (t == tlo || (cum[t - 1].panel - base) / pool_doubles != b)) { sum->batch_start[b] = t; sum->batch_pt[b] = desc[t].pt0; }
     }
 }
 
@@ -644,6 +644,30 @@ __global__ void k_basis_dense(DevBasis B, const int *__restrict__ f2user, long n
 void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s) {
     if (n <= 0) return;
     k_basis_dense<<<(unsigned)n, 128, 0, s>>>(B, f2user, n, r, bf, dr);
+}
+
+// Diagnostic: the panels k_basis wrote for the contraction, scattered into dense reference-order arrays bf[i][f], dr[i][m][f]
+// (zeros elsewhere) -- the very numbers k_jtensor's TMA copies and epilogue loads consume.  One CTA per tile.
+__global__ void k_panel_scatter(const TileDesc *__restrict__ tiles, const double *__restrict__ panel_pool, const int *__restrict__ fidx_pool,
+                                const int *__restrict__ perm, const int *__restrict__ f2user, int nbf, double *__restrict__ bf, double *__restrict__ dr) {
+    const TileDesc td = tiles[blockIdx.x];
+    if (td.nact == 0) return;
+    const double *panel = panel_pool + td.panel_off;
+    const int *fidx = fidx_pool + td.fidx_off, *nlist = fidx + td.nact;
+    const long plane = (long)td.nact * LDP;
+    for (int e = threadIdx.x; e < td.nreal * td.npts; e += blockDim.x) {
+        const int col = e / td.npts, row = e - col * td.npts;
+        const int slot = nlist[col];
+        const long f = f2user[fidx[slot]], i = perm[td.pt0 + row];
+        const double *p = panel + (long)slot * LDP + row;
+        if (bf) bf[i * nbf + f] = p[0];
+        if (dr) { dr[(i * 3 + 0) * nbf + f] = p[plane]; dr[(i * 3 + 1) * nbf + f] = p[2 * plane]; dr[(i * 3 + 2) * nbf + f] = p[3 * plane]; }
+    }
+}
+void launch_panel_scatter(const TileDesc *tiles, int ntiles, const double *panel_pool, const int *fidx_pool, const int *perm, const int *f2user,
+                          int nbf, double *bf, double *dr, cudaStream_t s) {
+    if (ntiles <= 0) return;
+    k_panel_scatter<<<ntiles, 256, 0, s>>>(tiles, panel_pool, fidx_pool, perm, f2user, nbf, bf, dr);
 }
 
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,

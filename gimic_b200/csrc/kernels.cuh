@@ -78,6 +78,7 @@ struct PlanSummary {                // device -> host, once per plan
     long long cost_total, cost_range;
     double sum_nact, flops4, flops2, taps, useful_mm, useful_taps;   // statistics of the range (see gimic_b200_stats)
     int batch_start[MAX_BATCH + 1]; // tile index (Hilbert order, absolute) where each batch begins; [nbatch] = thi
+    long long batch_pt[MAX_BATCH + 1];   // first sorted point of each batch; [nbatch] = pt_hi (a batch is a contiguous run of compact output rows)
 };
 
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
@@ -102,6 +103,8 @@ size_t plan_sort_temp_bytes(int nt);
 void launch_perm_index(const int *perm, long n, long *index, cudaStream_t s);
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
                   const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s);
+void launch_panel_scatter(const TileDesc *tiles, int ntiles, const double *panel_pool, const int *fidx_pool, const int *perm, const int *f2user,
+                          int nbf, double *bf, double *dr, cudaStream_t s);
 void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s);
 size_t sort_temp_bytes(long n);
 void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s);

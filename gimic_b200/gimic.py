@@ -196,6 +196,17 @@ class Gimic(GimicConnector):
                                                     C.c_void_p(dr.ctypes.data) if want_dr else None, 0))
         return (bf, dr) if want_dr else bf
 
+    def basis_tiles(self, r, want_dr=True):
+        """The same vectors as basis(), but evaluated by the hot-path kernels (sort, tiles, k_basis panels) -- diagnostic."""
+        r = _host(r).reshape(-1, 3)
+        n = r.shape[0]
+        bf = np.empty((n, self.nbf)); dr = np.empty((n, 3, self.nbf)) if want_dr else None
+        info = (C.c_int * 3)()
+        _lib.check(_lib.lib().gimic_b200_calc_basis_tiles(self._h, n, C.c_void_p(r.ctypes.data), C.c_void_p(bf.ctypes.data),
+                                                          C.c_void_p(dr.ctypes.data) if want_dr else None, info))
+        self.last_tile_info = tuple(info)
+        return (bf, dr) if want_dr else bf
+
     def jtensors(self, r, spincase="total", out=None):
         """tens[i, m + 3*b] for points r[i, :]  (calc_jtensors, jfield.f90:62-138)."""
         L = _lib.lib()

@@ -123,6 +123,11 @@ int gimic_b200_calc_fields(gimic_b200_handle h, long n, const double *r, const d
  * Either output may be NULL.  (The London/GIAO vectors db, d2 are products of these with r x R_A, bfeval.f90:168-293.) */
 int gimic_b200_calc_basis(gimic_b200_handle h, long n, const double *r, double *bf, double *dr, int flags);
 
+/* The same vectors evaluated by the HOT-PATH kernels (spatial sort, tiles, the k_basis panels the contraction consumes) and scattered
+ * back into the dense layout of gimic_b200_calc_basis: a diagnostic that lets tests hold the panel kernel itself to bfeval.f90.
+ * Host buffers, cartesian contexts; tile_info3 (may be NULL) = { tiles, mean padded active slots per tile, max active atoms of a tile }. */
+int gimic_b200_calc_basis_tiles(gimic_b200_handle h, long n, const double *r, double *bf, double *dr, int *tile_info3);
+
 /* Field arithmetic alone on existing tensors (the HBM-bound pass). */
 int gimic_b200_fields_from_tensors(gimic_b200_handle h, long n, const double *r, const double *tens,
                                    const double *B3, double *jvec, double *jmod, double *acid, int flags);
@@ -239,6 +244,9 @@ typedef struct {
     long contract_launches;   /* launches of the contraction kernel (k_jtensor) among them */
     double useful_flops;      /* the same count without padding: real points of each tile x its active functions on both sides
                                  (2*npts*planes*nreal^2 + taps); executed - useful = work spent on K/N padding and partial tiles */
+    float ms_plan;            /* gimic_b200_partition_*: CUDA-event time of the plan (point generation / upload, sort, tiles, partition) */
+    float ms_span;            /* from the start of the last gimic_b200_partition_* call to the end of gimic_b200_partition_calc */
+    double panel_bytes;       /* bytes of basis-function panels k_basis wrote (4 planes x padded K slots x 132 doubles per tile) */
 } gimic_b200_stats;
 int gimic_b200_get_stats(gimic_b200_handle h, gimic_b200_stats *out);
 int gimic_b200_set_profiling(gimic_b200_handle h, int enable);  /* per-stage CUDA-event timing (adds syncs) */

@@ -163,10 +163,10 @@ void emulate_plan_range(void **a) {
     sum->nbatch = (int)(nb < gb::MAX_BATCH ? nb : gb::MAX_BATCH + 1);
     sum->max_nruns = 0; sum->max_tile_panel = 0;
     sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
-    if (nb <= gb::MAX_BATCH) sum->batch_start[nb] = thi;
+    if (nb <= gb::MAX_BATCH) { sum->batch_start[nb] = thi; sum->batch_pt[nb] = sum->pt_hi; }
     for (int t = tlo; t < thi; ++t) {
         const long long b = (cum[t].panel - cum[tlo].panel) / pool;
-        if (b < gb::MAX_BATCH && (t == tlo || (cum[t - 1].panel - cum[tlo].panel) / pool != b)) sum->batch_start[b] = t;
+        if (b < gb::MAX_BATCH && (t == tlo || (cum[t - 1].panel - cum[tlo].panel) / pool != b)) { sum->batch_start[b] = t; sum->batch_pt[b] = desc[t].pt0; }
     }
 }
 const int *g_last_ord0 = nullptr;

@@ -51,4 +51,4 @@ def golden_json(name):
 
 
 from gimic_b200.synthetic import (C_TZVP, NFUNC_C, hex_flake, ring, synthetic_shells, synthetic_density,  # noqa: E402,F401
-                                  synthetic_case, dens_to_colmajor)
+                                  synthetic_case, dens_to_colmajor, box_grid)

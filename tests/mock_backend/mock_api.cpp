@@ -209,6 +209,9 @@ int gimic_b200_partition_calc(gimic_b200_handle c, const double *B3, int spincas
     return rc;
 }
 
+int gimic_b200_calc_basis_tiles(gimic_b200_handle, long, const double *, double *, double *, int *) {
+    return fail(GIMIC_B200_EINVAL, "test double: calc_basis_tiles is not provided");
+}
 int gimic_b200_calc_basis(gimic_b200_handle, long, const double *, double *, double *, int) {
     return fail(GIMIC_B200_EINVAL, "test double: calc_basis is not provided");
 }

@@ -656,3 +656,179 @@ def test_full_size_nbf10008_properties(gb):
     assert_close(ta[idx], o.ctensor(r[idx], "alpha"), "alpha vs oracle at nbf=10008")
     assert_close(tt[idx[:16]], o.ctensor(r[idx[:16]], "total"), "total vs oracle at nbf=10008")
     g.close()
+
+
+# ---- round 2: hot-path basis panels, device-side tile plan, cost-balanced partition, fused field outputs -----------------------
+def test_hot_path_basis_panels_vs_oracle(gb, c4h4, opensh):
+    """k_basis ITSELF (the panels k_jtensor's TMA copies and epilogue loads consume), not the diagnostic k_basis_dense:
+    Phi, dPhi/dr and the exact screening zeros per point, through sort -> tiles -> k_basis -> scatter (bfeval.f90:81-122,295-338)"""
+    for (g, o), seed in ((c4h4, 11), (opensh, 12)):       # Turbomole and standard component order
+        rng = np.random.default_rng(seed)
+        # a dense cluster (many points per tile), scattered points (many small active sets), atoms, a far point
+        r = np.vstack([rng.uniform(-1.5, 1.5, size=(300, 3)), rng.uniform(-9, 9, size=(200, 3)), o.atom_coords()[:3], [[40.0, 0, 0]]])
+        bf, dr = g.basis_tiles(r)
+        assert g.last_tile_info[0] >= 4
+        bfd, drd = g.basis(r)                                 # the dense diagnostic kernel: must agree bit for bit where both are non-zero
+        for i, p in enumerate(r):
+            obf, odr, _, _ = o.calc_basis(p)
+            assert_close(bf[i], obf, "bf (hot path)"); assert_close(dr[i], odr, "dr (hot path)")
+            assert ((bf[i] == 0) == (obf == 0)).all(), "screening pattern differs"
+        assert np.allclose(bf, bfd, rtol=1e-14, atol=0) and np.allclose(dr, drd, rtol=1e-14, atol=1e-300)
+        assert (bf[-1] == 0).all() and (dr[-1] == 0).all()
+
+
+def test_hot_path_basis_panels_synthetic_f_shells(gb):
+    sh, dens, nbf = fixtures.synthetic_case(14, "flake")
+    flat = fixtures.dens_to_colmajor(dens)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, **sh)
+    o = O.Oracle.from_arrays(dens_a=flat, **sh)
+    rng = np.random.default_rng(21)
+    r = rng.uniform(-9, 9, size=(400, 3)); r[:, 2] *= 0.4
+    bf, dr = g.basis_tiles(r)
+    for i in range(0, 400, 7):
+        obf, odr, _, _ = o.calc_basis(r[i])
+        assert_close(bf[i], obf, "bf"); assert_close(dr[i], odr, "dr")
+        assert ((bf[i] == 0) == (obf == 0)).all()
+    g.close()
+
+
+def _flake_grid(gb, sh, n):
+    origin, basv, pts = fixtures.box_grid(sh["coords"], (n, n, n), margin=6.0, zhalf=6.0)
+    return gb.Grid(origin, basv, pts)
+
+
+def test_partition_union_is_bitwise_the_single_rank_result(gb):
+    """every rank tiles the whole grid identically, so the union of the ranks' rows is the one-rank result bit for bit,
+    each point owned exactly once; the shares are balanced by cost, not by count (parallel.F90:66-84 splits by count)"""
+    sh, dens, nbf = fixtures.synthetic_case(30, "flake")
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fixtures.dens_to_colmajor(dens), **sh)
+    grid = _flake_grid(gb, sh, 40)
+    n = grid.n
+    full = g.jtensors_grid(grid, 0, n)
+    B = np.array([0.0, 0.0, 1.0])
+    for nranks in (1, 3, 8):
+        seen = np.zeros(n, dtype=np.int64)
+        got = np.full((n, 9), np.nan)
+        costs, counts, flops = [], [], []
+        for rk in range(nranks):
+            cnt = g.partition(grid, rk, nranks)
+            info = g.partition_info()
+            assert info["points"] == n and info["owned_points"] == cnt
+            res = g.partition_calc(B, "total", tens=True)
+            seen[res["index"]] += 1
+            got[res["index"]] = res["tens"]
+            costs.append(info["cost_owned"]); counts.append(cnt); flops.append(g.stats()["executed_flops"])
+            total_cost = info["cost_total"]
+        assert (seen == 1).all(), f"nranks={nranks}: points owned {seen.min()}..{seen.max()} times"
+        assert np.array_equal(got, full), f"nranks={nranks}: union differs from the single-rank tensors"
+        assert sum(costs) == total_cost
+        if nranks > 1:
+            mean = total_cost / nranks
+            assert max(costs) <= 1.05 * mean and min(costs) >= 0.95 * mean, costs
+            assert max(flops) <= 1.08 * np.mean(flops), flops            # the stats of the launched work, too
+            assert max(counts) > 1.15 * min(counts), counts              # equal cost is NOT equal count on a planar molecule
+    g.close()
+
+
+def test_partition_points_fields_and_plan_reuse(gb, c4h4, opensh):
+    g, o = c4h4
+    rng = np.random.default_rng(31)
+    r = rng.uniform(-6, 6, size=(5000, 3))
+    B = np.array([0.3, -0.2, 0.9]); B /= np.linalg.norm(B)
+    ref = g.fields(r, B, "total", tens=True, jvec=True, jmod=True, acid=True, edens=True)
+    parts = {k: np.full_like(v, np.nan) for k, v in ref.items()}
+    for rk in range(2):
+        g.partition(r, rk, 2)
+        a = g.partition_calc(B, "total", tens=True, jvec=True, jmod=True, acid=True, edens=True)
+        b = g.partition_calc(B, "total", jvec=True, jmod=True)          # the plan is reused; J path this time
+        for k in parts:
+            parts[k][a["index"]] = a[k]
+        jt = O.jvectors(a["tens"], B)
+        assert_close(a["jvec"], jt, "fused jvec vs its own tensor")
+        _jscale_close(b["jvec"], a["jvec"], a["tens"], "J path vs tensor path (partitioned)")
+        assert np.array_equal(a["index"], b["index"])
+    for k in parts:
+        assert np.array_equal(parts[k], ref[k]), k
+    # open shell: one plan, four spin cases
+    gu, ou = opensh
+    gu.partition(r[:1500], 0, 1)
+    for sc in ("alpha", "beta", "total", "spindens"):
+        res = gu.partition_calc(None, sc, tens=True)
+        assert_close(res["tens"], ou.ctensor(r[:1500][res["index"]], sc), f"partitioned open-shell {sc}")
+
+
+def test_partition_on_device_tensors(gb, c4h4):
+    import torch
+    g, o = c4h4
+    rng = np.random.default_rng(32)
+    r = rng.uniform(-5, 5, size=(3000, 3))
+    rd = torch.from_numpy(r).cuda()
+    cnt = g.partition(rd, 1, 3)
+    res = g.partition_calc(None, "total", tens=True, device=rd.device)
+    assert res["tens"].is_cuda and res["index"].shape[0] == cnt
+    idx = res["index"].cpu().numpy()
+    assert_close(res["tens"].cpu().numpy(), o.ctensor(r[idx]), "device-resident partition")
+
+
+def test_thin_point_sets_are_gap_split_on_the_device(gb, c4h4):
+    """planar and two-cluster point sets: a Hilbert run that leaves and re-enters the cloud is cut at its gaps (k_tile_split);
+    results = oracle, and the active sets stay small (no tile drags in both ends)"""
+    g, o = c4h4
+    rng = np.random.default_rng(33)
+    plane = np.zeros((4000, 3)); plane[:, 0] = rng.uniform(-8, 8, 4000); plane[:, 1] = rng.uniform(-8, 8, 4000); plane[:, 2] = 0.37
+    two = np.vstack([rng.normal(size=(700, 3)) * 0.3 + [0, 0, 0], rng.normal(size=(700, 3)) * 0.3 + [25.0, 0, 0]])
+    for name, r in (("plane", plane), ("two clusters", two), ("line", np.c_[np.linspace(-30, 30, 999), np.zeros(999), np.zeros(999)])):
+        t = g.jtensors(r)
+        assert_close(t, o.ctensor(r), name)
+        st = g.stats()
+        assert st["n_tiles"] >= -(-r.shape[0] // 128)
+    # the far cluster sees no basis function: with splitting no tile may carry the near cluster's active set over there
+    g.jtensors(two)
+    assert g.stats()["sum_nact"] / g.stats()["n_tiles"] <= g.nbf + 8
+
+
+def test_j_path_plain_tolerance_on_real_densities(c4h4, opensh, cases):
+    """J = T.B formed inside the contraction (operands (D, P.B)) at the plain 1e-10 / 1e-12 bound on the reference's own densities"""
+    gold = fixtures.golden_npz("c4h4_readgrid.npz")
+    g, o = c4h4
+    r, B = gold["grid"], gold["magnet"]
+    f = g.fields(r, B, "total", jvec=True, jmod=True, edens=True)
+    ref, ed = o.ctensor(r, "total", want_edens=True)
+    jv = O.jvectors(ref, B)
+    assert_close(f["jvec"], jv, "c4h4 J path"); assert_close(f["edens"], ed, "edens (J path)")
+    assert_close(np.abs(f["jmod"]), np.abs(O.jmod_signed(r, jv, B)), "|jmod| (J path)")
+    gu, ou = opensh
+    rng = np.random.default_rng(34)
+    ru = rng.uniform(-6, 6, size=(1500, 3))
+    Bu = np.array([1.0, 0.0, 0.0])
+    for sc in ("alpha", "beta", "total", "spindens"):
+        fu = gu.fields(ru, Bu, sc, jvec=True)
+        assert_close(fu["jvec"], O.jvectors(ou.ctensor(ru, sc), Bu), f"open-shell J path {sc}")
+
+
+def test_chunked_host_path_equals_one_call(gb, c4h4, monkeypatch):
+    """host buffers larger than one chunk are processed chunk by chunk with the copies overlapped: same numbers as device-resident"""
+    import torch
+    g, o = c4h4
+    rng = np.random.default_rng(35)
+    n = (1 << 21) + 70001                      # two chunks
+    r = np.empty((n, 3)); r[:] = rng.uniform(-7, 7, size=(n, 3))
+    th = g.jtensors(r)
+    pick = rng.choice(n, 400, replace=False)
+    assert_close(th[pick], o.ctensor(r[pick]), "chunked host path")
+    # both chunks filled, no row left untouched
+    td = g.jtensors(torch.from_numpy(r).cuda()).cpu().numpy()
+    assert np.abs(th - td).max() <= 1e-10 * np.abs(td).max()
+    assert not np.isnan(th).any()
+
+
+def test_nccl_integral_all_reduce_when_two_gpus(gb, cases, tmp_path):
+    """integral mode over torch.distributed/NCCL: plane rows split over 2 ranks, one all-reduce of the 7 partial sums
+    (integral.f90:157-161 has its collect_sum calls commented out) == the single-GPU sums == the c4h4 golden"""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (bench.py --gpus N records the same reduction in its stages.integral_nccl object)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", os.path.join(root, "tools", "dist_integral_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

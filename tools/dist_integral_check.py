@@ -39,5 +39,6 @@ if rank == 0:
     ok_gold = abs(res[0] - blk["au"]) < 1.01e-6 and abs(res[1] - blk["pos"]) < 1.01e-6 and abs(res[2] - blk["neg"]) < 1.01e-6
     print(json.dumps({"world": world, "sharded": res.tolist(), "single": full.tolist(), "match_single": bool(ok), "match_golden": bool(ok_gold)}))
     assert ok and ok_gold
+    print("OK")
 if world > 1:
     dist.destroy_process_group()
