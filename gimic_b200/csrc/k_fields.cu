@@ -10,18 +10,37 @@ namespace gb {
 
 constexpr int FB = 256;   // points per block in k_fields
 
-// Tensors are 9 doubles per point (AoS, the reference's tens(9,N)).  A block stages its 256x9
-// contiguous doubles through shared memory with fully coalesced loads, then each thread works on
-// one point (stride 9 is odd => conflict-free) and results go back out through smem, coalesced.
+// Tensors are 9 doubles per point (AoS, the reference's tens(9,N)).  A block stages its 256x9 contiguous doubles through shared
+// memory with 128-bit (double2) loads -- 72 B per point in, 24 + 8 + 8 B out, 24 B of coordinates for the signed modulus: the pass
+// is HBM-bound, so every byte moves once, fully coalesced, in 16-byte units where alignment allows (a block's tensor slab starts at
+// 256*9*8 B = a multiple of 16; the point count of the last block may be odd: scalar tail).  Each thread then works on one point
+// (stride 9 is odd => conflict-free) and the vectors go back out through shared memory, again as double2.
+// VEC = false: the same pass with 8-byte accesses, for caller pointers that are not 16-byte aligned (e.g. a view into a larger array).
+template <bool VEC>
 __global__ void __launch_bounds__(FB) k_fields(long n, const double *__restrict__ r, const double *__restrict__ tens, double bx,
                                                double by, double bz, double *__restrict__ jvec, double *__restrict__ jmod,
                                                double *__restrict__ acid) {
-    __shared__ double s_t[FB * 9];
-    __shared__ double s_r[FB * 3];
+    __shared__ __align__(16) double s_t[FB * 9];
+    __shared__ __align__(16) double s_r[FB * 3 + 1];
     const long base = (long)blockIdx.x * FB;
     const int cnt = (int)((n - base) < FB ? (n - base) : FB);
-    for (int i = threadIdx.x; i < cnt * 9; i += FB) s_t[i] = tens[base * 9 + i];
-    if (jmod) for (int i = threadIdx.x; i < cnt * 3; i += FB) s_r[i] = r[base * 3 + i];
+    if (!VEC) {
+        for (int i = threadIdx.x; i < cnt * 9; i += FB) s_t[i] = tens[base * 9 + i];
+        if (jmod) for (int i = threadIdx.x; i < cnt * 3; i += FB) s_r[i] = r[base * 3 + i];
+    } else {
+        const int nd = cnt * 9, n2 = nd >> 1;
+        const double2 *src = reinterpret_cast<const double2 *>(tens + base * 9);     // base*9*8 B is 16-byte aligned (FB*9 even)
+        double2 *dst = reinterpret_cast<double2 *>(s_t);
+        for (int i = threadIdx.x; i < n2; i += FB) dst[i] = __ldcs(src + i);          // streamed: read once
+        if ((nd & 1) && threadIdx.x == 0) s_t[nd - 1] = tens[base * 9 + nd - 1];
+    }
+    if (VEC && jmod) {
+        const int nd = cnt * 3, n2 = nd >> 1;
+        const double2 *src = reinterpret_cast<const double2 *>(r + base * 3);
+        double2 *dst = reinterpret_cast<double2 *>(s_r);
+        for (int i = threadIdx.x; i < n2; i += FB) dst[i] = __ldcs(src + i);
+        if ((nd & 1) && threadIdx.x == 0) s_r[nd - 1] = r[base * 3 + nd - 1];
+    }
     __syncthreads();
     double vx = 0, vy = 0, vz = 0, jm = 0, ac = 0;
     const int p = threadIdx.x;
@@ -44,18 +63,25 @@ __global__ void __launch_bounds__(FB) k_fields(long n, const double *__restrict_
             if (nx * vx + ny * vy + nz * vz < 0.0) jm = -1.0 * jm;
         }
     }
-    if (jmod && p < cnt) jmod[base + p] = jm;
-    if (acid && p < cnt) acid[base + p] = ac;
+    if (jmod && p < cnt) __stcs(jmod + base + p, jm);
+    if (acid && p < cnt) __stcs(acid + base + p, ac);
     if (jvec) {
         __syncthreads();
         if (p < cnt) { s_r[3 * p] = vx; s_r[3 * p + 1] = vy; s_r[3 * p + 2] = vz; }
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 3; i += FB) jvec[base * 3 + i] = s_r[i];
+        const int nd = cnt * 3, n2 = nd >> 1;
+        if (!VEC) { for (int i = threadIdx.x; i < nd; i += FB) jvec[base * 3 + i] = s_r[i]; return; }
+        double2 *dst = reinterpret_cast<double2 *>(jvec + base * 3);
+        const double2 *src = reinterpret_cast<const double2 *>(s_r);
+        for (int i = threadIdx.x; i < n2; i += FB) __stcs(dst + i, src[i]);
+        if ((nd & 1) && threadIdx.x == 0) jvec[base * 3 + nd - 1] = s_r[nd - 1];
     }
 }
 void launch_fields(long n, const double *r, const double *tens, const double *B3, double *jvec, double *jmod, double *acid, cudaStream_t s) {
     if (n <= 0) return;
-    k_fields<<<(unsigned)((n + FB - 1) / FB), FB, 0, s>>>(n, r, tens, B3[0], B3[1], B3[2], jvec, jmod, acid);
+    const bool vec = ((reinterpret_cast<uintptr_t>(tens) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(jvec)) & 15) == 0;
+    if (vec) k_fields<true><<<(unsigned)((n + FB - 1) / FB), FB, 0, s>>>(n, r, tens, B3[0], B3[1], B3[2], jvec, jmod, acid);
+    else k_fields<false><<<(unsigned)((n + FB - 1) / FB), FB, 0, s>>>(n, r, tens, B3[0], B3[1], B3[2], jvec, jmod, acid);
 }
 
 // signed |J| from J alone (jfield.f90:446-489), for the J = T.B path that never forms the tensor

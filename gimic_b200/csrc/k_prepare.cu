@@ -465,20 +465,25 @@ __device__ __forceinline__ void shell_to_panel(double rx, double ry, double rz, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_basis: one CTA (128 threads = 128 points) per tile.
-//  phase A: ordered compaction of the active atoms into (atom, nshell, slot0) runs + the slot->function index list
+// k_basis<NT>: NT threads = NT points; MT / NT CTAs per tile (NT = 128: one CTA per tile; NT = 32: four single-warp CTAs per tile,
+// small enough -- 96 registers x 32 threads, ~5 KB of shared memory -- to run NEXT TO the persistent contraction kernel on the same
+// SM, so that the panels of batch b+1 are written while batch b is contracted).
+//  phase A: ordered compaction of the active atoms into (atom, nshell, slot0) runs + the slot->function index list (written by part 0)
 //  phase B: every thread evaluates its point for all active shells and writes the 4 planes
 //           P0 = Phi, P1..3 = dPhi/dx,dy,dz at panel[(plane*nact + slot)*LDP + row]  (row-contiguous => coalesced)
-__global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 20) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
                                                const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                const double *__restrict__ rsz, double *__restrict__ panel_pool,
                                                int *__restrict__ fidx_pool, TileAtom *__restrict__ atab_pool) {
+    constexpr int Q = MT / NT;        // CTAs per tile
     extern __shared__ int s_dyn[];    // [natoms] packed (shells << 20 | functions) of every atom, then 4 ints per active atom (run)
     int *s_atom = s_dyn, *s_runs = s_dyn + B.natoms;   // run: atom, shells, first K slot, first N column
     __shared__ int s_w[3][4];
     __shared__ int s_base[3];
     __shared__ int s_zero;            // a K slot whose panel rows are zero (padding), for the N-side padding columns
-    const TileDesc td = tiles[blockIdx.x];
+    const TileDesc td = tiles[blockIdx.x / Q];
+    const int part = blockIdx.x % Q;
     if (td.nact == 0) return;
     const TileGeo tg = geo[td.geo];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -487,12 +492,12 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
     const long plane = (long)td.nact * LDP;
 
     __shared__ double sx[MT], sy[MT], sz[MT];
-    { const long p = td.pt0 + (tid < td.npts ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
+    for (int i = tid; i < MT; i += NT) { const long p = td.pt0 + (i < td.npts ? i : 0); sx[i] = rsx[p]; sy[i] = rsy[p]; sz[i] = rsz[p]; }
     if (tid == 0) { s_base[0] = 0; s_base[1] = 0; s_base[2] = 0; s_zero = td.nraw < td.nact ? td.nraw : 0x7fffffff; }
-    for (int a = tid; a < B.natoms; a += 128) s_atom[a] = 0;
+    for (int a = tid; a < B.natoms; a += NT) s_atom[a] = 0;
     __syncthreads();
     // phase A1: active prefix of every atom (same arithmetic as k_tile_split => the counts the descriptors were sized with)
-    for (int base = wid * 32; base < B.natoms; base += 128) {
+    for (int base = wid * 32; base < B.natoms; base += NT) {
         const int at = base + lane;
         unsigned bal = __ballot_sync(0xffffffffu, at < B.natoms && atom_box_pass(B, at, tg));
         while (bal) {
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
     }
     __syncthreads();
     const int al = B.slot_align - 1;
-    for (int a0 = 0; a0 < B.natoms; a0 += 128) {
+    for (int a0 = 0; a0 < B.natoms; a0 += NT) {
         int a = a0 + tid, nsh = 0, nreal = 0;
         if (a < B.natoms) { const int pk = s_atom[a]; nsh = pk >> 20; nreal = pk & 0xfffff; }
         const int nfun = (nreal + al) & ~al;         // slots of the atom's run (functions + alignment padding)
@@ -525,27 +530,27 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
             if (nfun > nreal) atomicMin(&s_zero, slot0 + nreal);
         }
         __syncthreads();
-        if (tid == 127) { s_base[0] = offf + sf; s_base[1] = offr + sr; s_base[2] = offn + sn; }
+        if (tid == NT - 1) { s_base[0] = offf + sf; s_base[1] = offr + sr; s_base[2] = offn + sn; }
         __syncthreads();
     }
     const int nruns = s_base[1];
     // slot -> internal function index; pad slots point at a valid function (their Phi is zero)
     int *nlist = fidx + td.nact;   // N column -> K slot
-    for (int rn = 0; rn < nruns; ++rn) {
+    for (int rn = 0; rn < nruns && part == 0; ++rn) {
         int a = s_runs[4 * rn], nsh = s_runs[4 * rn + 1], slot0 = s_runs[4 * rn + 2], col0 = s_runs[4 * rn + 3];
         int f0 = B.atom_func_off[a];
         int s_last = B.atom_shell_off[a] + nsh - 1, ll = B.sh_l[s_last];
         int nfun = B.sh_foff[s_last] - f0 + (ll + 1) * (ll + 2) / 2, nslot = (nfun + al) & ~al;
-        for (int c = tid; c < nslot; c += 128) fidx[slot0 + c] = f0 + (c < nfun ? c : 0);
-        for (int c = tid; c < nfun; c += 128) nlist[col0 + c] = slot0 + c;
+        for (int c = tid; c < nslot; c += NT) fidx[slot0 + c] = f0 + (c < nfun ? c : 0);
+        for (int c = tid; c < nfun; c += NT) nlist[col0 + c] = slot0 + c;
     }
-    for (int c = td.nraw + tid; c < td.nact; c += 128) fidx[c] = 0;
-    for (int c = td.nreal + tid; c < td.nn; c += 128) nlist[c] = s_zero;   // nn > nreal implies that a padding slot exists
+    for (int c = td.nraw + tid; c < td.nact && part == 0; c += NT) fidx[c] = 0;
+    for (int c = td.nreal + tid; c < td.nn && part == 0; c += NT) nlist[c] = s_zero;   // nn > nreal implies that a padding slot exists
     // atom table for the GIAO taps of k_jtensor (see TileAtom)
-    if (atab_pool) {
+    if (atab_pool && part == 0) {
         TileAtom *atab = atab_pool + td.atab_off;
         const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
-        for (int rn = tid; rn < nruns; rn += 128) {
+        for (int rn = tid; rn < nruns; rn += NT) {
             const int a = s_runs[4 * rn];
             const int slot_end = (rn + 1 < nruns) ? s_runs[4 * rn + 6] : td.nraw;
             double nx = cx, ny = cy, nz = cz;
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(128, 5) k_basis(DevBasis B, const TileDesc *__
         }
     }
 
-    const int row = tid;
+    const int row = part * NT + tid;
     const bool valid = row < td.npts;
     const long pt = td.pt0 + (valid ? row : 0);
     const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
@@ -671,11 +676,16 @@ void launch_panel_scatter(const TileDesc *tiles, int ntiles, const double *panel
 }
 
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
-                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s) {
+                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s, bool small_ctas) {
     if (ntiles <= 0) return;
     size_t smem = ((size_t)B.natoms + (size_t)4 * (max_nruns > 0 ? max_nruns : 1)) * sizeof(int);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
-    k_basis<<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
+    if (small_ctas) {      // single-warp CTAs that fit beside the contraction kernel (overlapped batches); the smem must stay small for that
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_basis<32><<<ntiles * (MT / 32), 32, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
+        return;
+    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+    k_basis<128><<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
 }
 
 }  // namespace gb

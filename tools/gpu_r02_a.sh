@@ -16,6 +16,13 @@ echo "== bench N=1 (headline: whole grid through the partition API)"
 timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; tail -c 1500 $OUT/${TAG}_bench_n1.json; tail -3 $OUT/${TAG}_bench_n1.err
 echo "== bench N=1 octant mode (round-1 workload, for comparison)"
 timeout 600 python bench.py --mode octant --steps 5 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_bench_n1_octant.json 2> $OUT/${TAG}_bench_n1_octant.err; tail -c 700 $OUT/${TAG}_bench_n1_octant.json
+echo "== A/B: tensor path with 16 consumer warps (GIMIC_B200_NCW=16): parity subset, then the octant step"
+( GIMIC_B200_NCW=16 timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "c4h4_read_grid or synthetic_flake or open_shell_spin or partition_union or far_origin or uhf_total or switches" ) > $OUT/${TAG}_pytest_ncw16.log 2>&1; tail -4 $OUT/${TAG}_pytest_ncw16.log
+GIMIC_B200_NCW=16 timeout 600 python bench.py --mode octant --steps 5 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_bench_n1_octant_ncw16.json 2> $OUT/${TAG}_bench_n1_octant_ncw16.err; tail -c 700 $OUT/${TAG}_bench_n1_octant_ncw16.json; tail -2 $OUT/${TAG}_bench_n1_octant_ncw16.err
+echo "== A/B: + panels of batch b+1 written beside the contraction of batch b (GIMIC_B200_OVERLAP=1)"
+( GIMIC_B200_NCW=16 GIMIC_B200_OVERLAP=1 timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "c4h4_read_grid or synthetic_flake or partition_union or hot_path" ) > $OUT/${TAG}_pytest_ncw16_ovl.log 2>&1; tail -4 $OUT/${TAG}_pytest_ncw16_ovl.log
+GIMIC_B200_NCW=16 GIMIC_B200_OVERLAP=1 timeout 600 python bench.py --mode octant --steps 5 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_bench_n1_octant_ncw16_ovl.json 2> $OUT/${TAG}_bench_n1_octant_ncw16_ovl.err; tail -c 700 $OUT/${TAG}_bench_n1_octant_ncw16_ovl.json; tail -2 $OUT/${TAG}_bench_n1_octant_ncw16_ovl.err
+GIMIC_B200_OVERLAP=1 timeout 600 python bench.py --mode octant --steps 5 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_bench_n1_octant_ncw8_ovl.json 2> /dev/null; tail -c 500 $OUT/${TAG}_bench_n1_octant_ncw8_ovl.json
 timeout 300 python tools/legacy_latency.py > $OUT/${TAG}_legacy_latency.json 2>&1; tail -c 400 $OUT/${TAG}_legacy_latency.json
 echo "== ncu launch list (octant step) + key counters of k_jtensor / k_basis / k_tile_split"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches.csv \
@@ -25,3 +32,6 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_secto
 timeout 600 ncu --metrics $M --clock-control none -k regex:'k_jtensor|k_basis|k_tile_split' -s 12 -c 6 --csv --log-file $OUT/${TAG}_ncu_key.csv \
     python bench.py --mode octant --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 tail -60 $OUT/${TAG}_ncu_key.csv | cut -c1-260
+GIMIC_B200_NCW=16 timeout 600 ncu --metrics $M --clock-control none -k regex:'k_jtensor' -s 3 -c 3 --csv --log-file $OUT/${TAG}_ncu_key_ncw16.csv \
+    python bench.py --mode octant --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
+tail -30 $OUT/${TAG}_ncu_key_ncw16.csv | cut -c1-260
