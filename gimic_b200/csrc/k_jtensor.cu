@@ -83,7 +83,10 @@ constexpr int ROWLD = 17;   // doubles per row-table entry: 13 sums + 3 coordina
 constexpr int NCONSUMER_WARPS = 8;
 constexpr int NPRODUCER_WARPS = 4;   // one warpgroup, so that setmaxnreg can hand its registers to the consumers
 constexpr int NTHREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
-constexpr int CONSUMER_REGS16 = 112;   // 16 consumer warps: (16*112 + 4*40) * 32 = 62464
+// 16 consumer warps.  setmaxnreg only REDISTRIBUTES the registers the CTA was launched with ((16 + 4) * 32 threads x 96 = 61440): a
+// request beyond that pool never completes and the kernel hangs (measured twice: 8 warps at 240/32 in round 1, 16 warps at 112/40 in
+// round 2).  (16*112 + 4*32) * 32 = 61440 exactly.
+constexpr int CONSUMER_REGS16 = 112, PRODUCER_REGS16 = 32;
 #ifndef DEFAULT_NCW
 #define DEFAULT_NCW 8
 #endif
@@ -136,6 +139,11 @@ __device__ __forceinline__ double acid_of(const double (&t)[9]) {
     const double xxmyy = (t[0] - t[4]) * (t[0] - t[4]), yymzz = (t[4] - t[8]) * (t[4] - t[8]), zzmxx = (t[8] - t[0]) * (t[8] - t[0]);
     const double xypyx = (t[3] + t[1]) * (t[3] + t[1]), xzpzx = (t[6] + t[2]) * (t[6] + t[2]), yzpzy = (t[7] + t[5]) * (t[7] + t[5]);
     return 0.3333333 * (xxmyy + yymzz + zzmxx) + 0.5 * (xypyx + xzpzx + yzpzy);
+}
+
+__device__ __forceinline__ void load_tap_weights(bool tab_sm, const double *s_atab, const double *gtab, int ia, double &x, double &y, double &z) {
+    if (tab_sm) { const double *p = s_atab + 3 * ia; x = p[0]; y = p[1]; z = p[2]; }          // [ATAB_MAX][3] in shared memory
+    else { const double *p = gtab + 4 * ia; x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2); }   // TileAtom = 4 doubles
 }
 
 // Tile bookkeeping shared by both roles: every thread of the CTA calls this once per tile (two CTA barriers).
@@ -239,7 +247,10 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
         double acc[NQ][2][4];
         double zac[3][2][4];                                        // Z_d (GIAO taps)
         const int nruns = td.nruns;
-        const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
+        // tap weights (dx,dy,dz) of run ia: shared memory (LDS; a generic pointer would cost a generic load per weight), or the
+        // global table when the tile has more active atoms than the shared copy holds
+        const bool tab_sm = nruns <= ATAB_MAX;
+        const double *gtab = reinterpret_cast<const double *>(a.atab_pool + td.atab_off);
         double curx = 0, cury = 0, curz = 0;
         int ia = 0;
         int eslot[2][2];                                            // epilogue: K slot of this thread's 4 nu columns
@@ -256,7 +267,6 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                 atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
-            if (nruns > ATAB_MAX) { atd = reinterpret_cast<const double *>(atab); astr = 4; }
         }
         int kc = 0, vc = 0;
         for (uint32_t it = 0; it < NIT; ++it) {
@@ -276,7 +286,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
 #pragma unroll
                             for (int i = 0; i < 4; ++i) zac[d][h][i] = 0.0;
                     ia = 0;
-                    curx = atd[0]; cury = atd[1]; curz = atd[2];
+                    load_tap_weights(tab_sm, s_atab, gtab, 0, curx, cury, curz);
                 }
                 // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
 #pragma unroll
@@ -318,8 +328,7 @@ __device__ __forceinline__ void consumer_role(const JtensorArgs &a, const double
                             zac[2][h][i] = fma(curz, cv, zac[2][h][i]);
                         }
                     ia = min(ia + 1, nruns - 1);
-                    const double *nx = atd + astr * ia;
-                    curx = nx[0]; cury = nx[1]; curz = nx[2];
+                    load_tap_weights(tab_sm, s_atab, gtab, ia, curx, cury, curz);
                 }
             }
             __syncwarp();
@@ -477,7 +486,10 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
             wBx = by * cz - bz * cy; wBy = bz * cx - bx * cz; wBz = bx * cy - by * cx;
         }
         const int nruns = td.nruns;
-        const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
+        // tap weights (dx,dy,dz) of run ia: shared memory (LDS; a generic pointer would cost a generic load per weight), or the
+        // global table when the tile has more active atoms than the shared copy holds
+        const bool tab_sm = nruns <= ATAB_MAX;
+        const double *gtab = reinterpret_cast<const double *>(a.atab_pool + td.atab_off);
         double curx = 0, cury = 0, curz = 0;
         int ia = 0;
         int eslot[NVJ / 8][2];                                      // epilogue: K slot of this thread's nu columns
@@ -494,7 +506,6 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
                 atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
-            if (nruns > ATAB_MAX) { atd = reinterpret_cast<const double *>(atab); astr = 4; }
         }
         int kc = 0, vc = 0;
         for (uint32_t it = 0; it < NIT; ++it) {
@@ -512,7 +523,7 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
 #pragma unroll
                         for (int i = 0; i < 4; ++i) zac[h][i] = 0.0;
                     ia = 0;
-                    curx = atd[0]; cury = atd[1]; curz = atd[2];
+                    load_tap_weights(tab_sm, s_atab, gtab, 0, curx, cury, curz);
                 }
                 // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
 #pragma unroll
@@ -565,8 +576,7 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
                         zac[h][2] = fma(oB, acc[0][h][2], zac[h][2]); zac[h][3] = fma(oB, acc[0][h][3], zac[h][3]);
                     }
                     ia = min(ia + 1, nruns - 1);
-                    const double *nx = atd + astr * ia;
-                    curx = nx[0]; cury = nx[1]; curz = nx[2];
+                    load_tap_weights(tab_sm, s_atab, gtab, ia, curx, cury, curz);
                 }
             }
             __syncwarp();
@@ -732,7 +742,10 @@ __device__ __forceinline__ void consumer_role16(const JtensorArgs &a, const doub
         double acc[NQ][4];
         double zac[3][4];                                           // Z_d (GIAO taps)
         const int nruns = td.nruns;
-        const double *atd = s_atab; int astr = 3;                  // tap weights (dx,dy,dz) of run ia at atd[astr*ia .. +2]
+        // tap weights (dx,dy,dz) of run ia: shared memory (LDS; a generic pointer would cost a generic load per weight), or the
+        // global table when the tile has more active atoms than the shared copy holds
+        const bool tab_sm = nruns <= ATAB_MAX;
+        const double *gtab = reinterpret_cast<const double *>(a.atab_pool + td.atab_off);
         double curx = 0, cury = 0, curz = 0;
         int ia = 0;
         int eslot[2];                                               // epilogue: K slot of this thread's 2 nu columns
@@ -749,7 +762,6 @@ __device__ __forceinline__ void consumer_role16(const JtensorArgs &a, const doub
                 atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NCW16 * 32) : "memory");
-            if (nruns > ATAB_MAX) { atd = reinterpret_cast<const double *>(atab); astr = 4; }
         }
         int kc = 0, vc = 0;
         for (uint32_t it = 0; it < NIT; ++it) {
@@ -766,7 +778,7 @@ __device__ __forceinline__ void consumer_role16(const JtensorArgs &a, const doub
 #pragma unroll
                         for (int i = 0; i < 4; ++i) zac[d][i] = 0.0;
                     ia = 0;
-                    curx = atd[0]; cury = atd[1]; curz = atd[2];
+                    load_tap_weights(tab_sm, s_atab, gtab, 0, curx, cury, curz);
                 }
                 // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
 #pragma unroll
@@ -800,8 +812,7 @@ __device__ __forceinline__ void consumer_role16(const JtensorArgs &a, const doub
                         zac[2][i] = fma(curz, cv, zac[2][i]);
                     }
                     ia = min(ia + 1, nruns - 1);
-                    const double *nx = atd + astr * ia;
-                    curx = nx[0]; cury = nx[1]; curz = nx[2];
+                    load_tap_weights(tab_sm, s_atab, gtab, ia, curx, cury, curz);
                 }
             }
             __syncwarp();
@@ -896,10 +907,11 @@ __global__ void __launch_bounds__((NCW + NPRODUCER_WARPS) * 32, 1) k_jtensor(Jte
     }
     __syncthreads();
     if ((threadIdx.x >> 5) >= NCW) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        if (NCW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS16));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
         producer_role<SM, NCW>(a, s_base, bar_full, bar_empty, s_tile);
     } else {
-        // (8*232 + 4*40) * 32 = 64512 and (16*112 + 4*40) * 32 = 62464 registers: below the 65536 of the file (see CONSUMER_REGS)
+        // (8*232 + 4*40) * 32 = 64512 = 384 x 168 and (16*112 + 4*32) * 32 = 61440 = 640 x 96: exactly the launch allocation
         if (NCW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS16));
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
         double *rows = reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), *atab = reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF);

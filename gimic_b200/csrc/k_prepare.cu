@@ -681,6 +681,8 @@ void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_
     size_t smem = ((size_t)B.natoms + (size_t)4 * (max_nruns > 0 ? max_nruns : 1)) * sizeof(int);
     if (small_ctas) {      // single-warp CTAs that fit beside the contraction kernel (overlapped batches); the smem must stay small for that
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // same shared-memory carve-out as the contraction kernel it is meant to run beside (an SM cannot hold CTAs of two configurations)
+        cudaFuncSetAttribute(k_basis<32>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         k_basis<32><<<ntiles * (MT / 32), 32, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
         return;
     }
