@@ -104,42 +104,60 @@ void launch_grid_points(const double *ob, const double *p0, const double *p1, co
 // Cheap reject by the distance to the tile's bounding box (one atom per lane), then, one atom per warp, the exact minimum
 // distance over the tile's points (staged in shared memory), so the active set is the exact union over the tile's points at
 // shell granularity.  Shells are sorted by descending thr inside each atom, so the active set of an atom is a prefix.
-// k_tile_split and k_basis call these with identical inputs; every product below is written with explicit intrinsics so that
+// k_tile_split and k_basis call this with identical inputs; every product below is written with explicit intrinsics so that
 // both kernels compute bit-identical distances (no context-dependent FMA contraction) => identical counts.  The per-point
 // test sqrt(r2) <= thr is applied again in k_basis (filter_screened, basis.f90:118-136).
-__device__ __forceinline__ bool atom_box_pass(const DevBasis &B, int a, const TileGeo &tg) {
-    const double x = B.atom_xyz[3 * a], y = B.atom_xyz[3 * a + 1], z = B.atom_xyz[3 * a + 2];
-    const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
-                 dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
-    return !(sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)))) - 1e-9 > B.atom_maxthr[a]);
-}
-// all 32 lanes, same atom: number of active functions (0: none) and shells of atom a for the points sx/sy/sz[0, np)
-__device__ __forceinline__ int atom_prefix_warp(const DevBasis &B, int a, const double *sx, const double *sy, const double *sz,
-                                                int np, int &nsh) {
-    nsh = 0;
+// for_active_atoms: warp-cooperative sweep over the 32 atoms [base, base + 32).  Lane i loads atom base+i (position, largest radius,
+// shell / function ranges) and tests its bounding box; the surviving atoms are then processed one at a time with their data broadcast
+// by shuffles, so that the only dependent global-memory round per candidate is the one that fetches the shell radii.
+// emit(atom, nsh, nfun) is called by all 32 lanes for every atom with nfun > 0.
+template <class Emit>
+__device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, const TileGeo &tg, const double *sx, const double *sy,
+                                                 const double *sz, int np, Emit emit) {
     const int lane = threadIdx.x & 31;
-    const double x = B.atom_xyz[3 * a], y = B.atom_xyz[3 * a + 1], z = B.atom_xyz[3 * a + 2];
-    double d2 = 1e300;
-    for (int p = lane; p < np; p += 32) {
-        const double ex = sx[p] - x, ey = sy[p] - y, ez = sz[p] - z;
-        d2 = fmin(d2, __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
+    const int at = base + lane;
+    double x = 0.0, y = 0.0, z = 0.0, mx = 0.0;
+    int s0 = 0, s1 = 0, f0 = 0, f1 = 0;
+    bool pass = false;
+    if (at < B.natoms) {
+        x = B.atom_xyz[3 * at]; y = B.atom_xyz[3 * at + 1]; z = B.atom_xyz[3 * at + 2];
+        mx = B.atom_maxthr[at];
+        s0 = B.atom_shell_off[at]; s1 = B.atom_shell_off[at + 1]; f0 = B.atom_func_off[at]; f1 = B.atom_func_off[at + 1];
+        const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
+                     dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
+        pass = !(sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)))) - 1e-9 > mx);
     }
+    unsigned bal = __ballot_sync(0xffffffffu, pass);
+    while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const double ax = __shfl_sync(0xffffffffu, x, src), ay = __shfl_sync(0xffffffffu, y, src), az = __shfl_sync(0xffffffffu, z, src);
+        const double amx = __shfl_sync(0xffffffffu, mx, src);
+        const int as0 = __shfl_sync(0xffffffffu, s0, src), as1 = __shfl_sync(0xffffffffu, s1, src);
+        const int af0 = __shfl_sync(0xffffffffu, f0, src), af1 = __shfl_sync(0xffffffffu, f1, src);
+        double d2 = 1e300;
+        for (int p = lane; p < np; p += 32) {
+            const double ex = sx[p] - ax, ey = sy[p] - ay, ez = sz[p] - az;
+            d2 = fmin(d2, __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-    const double lim = sqrt(d2) - 1e-9;
-    if (lim > B.atom_maxthr[a]) return 0;
-    const int s0 = B.atom_shell_off[a], s1 = B.atom_shell_off[a + 1];
-    int cnt = 0;
-    for (int base = s0; base < s1; base += 32) {
-        const int s = base + lane;
-        const unsigned bal = __ballot_sync(0xffffffffu, s < s1 && B.sh_thr[s] >= lim);
-        if (bal == 0xffffffffu) { cnt += 32; continue; }
-        cnt += __ffs(~bal) - 1;      // shells are sorted by descending radius: the active ones are a prefix
-        break;
+        for (int o = 16; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        const double lim = sqrt(d2) - 1e-9;
+        if (lim > amx) continue;
+        // shells are sorted by descending radius inside an atom: the active ones are a prefix
+        int cnt = 0, fend = af0;                  // active shells, function index after the last active shell
+        for (int sb = as0; sb < as1; sb += 32) {
+            const int s = sb + lane;
+            const bool in = s < as1;
+            const double thr = in ? B.sh_thr[s] : -1.0;
+            const int fnext = in ? (s + 1 < as1 ? B.sh_foff[s + 1] : af1) : af1;
+            const unsigned act = __ballot_sync(0xffffffffu, in && thr >= lim);
+            const int k = act == 0xffffffffu ? 32 : __ffs(~act) - 1;
+            if (k > 0) { cnt += k; fend = __shfl_sync(0xffffffffu, fnext, k - 1); }
+            if (k < 32) break;
+        }
+        if (cnt > 0) emit(base + src, cnt, fend - af0);
     }
-    if (cnt == 0) return 0;
-    nsh = cnt;
-    return (cnt == s1 - s0 ? B.atom_func_off[a + 1] : B.sh_foff[s0 + cnt]) - B.atom_func_off[a];
 }
 
 // ---- k_tile_split -----------------------------------------------------------------------------------------------------------
@@ -161,7 +179,7 @@ __device__ __forceinline__ void block_min6(double (&v)[6], double (*s_red)[6]) {
     for (int i = 0; i < 6; ++i) v[i] = fmin(fmin(s_red[0][i], s_red[1][i]), fmin(s_red[2][i], s_red[3][i]));
 }
 
-__global__ void __launch_bounds__(128) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
+__global__ void __launch_bounds__(128, 8) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                     const double *__restrict__ rsz, long n, double split_radius,
                                                     TileSeg *__restrict__ slot_seg, TileGeo *__restrict__ slot_geo,
                                                     TileInfo *__restrict__ slot_info, int *__restrict__ cnt_out) {
@@ -219,17 +237,10 @@ __global__ void __launch_bounds__(128) k_tile_split(DevBasis B, const double *__
         const int imax = (int)(gap & 0xffffffffu);
         tg.rho = (double)rho; tg.pad_ = 0.0;
         // active slots (atom runs aligned), atoms, functions
-        for (int base = wid * 32; base < B.natoms; base += 128) {
-            const int at = base + lane;
-            unsigned bal = __ballot_sync(0xffffffffu, at < B.natoms && atom_box_pass(B, at, tg));
-            while (bal) {
-                const int aa = base + __ffs(bal) - 1;
-                bal &= bal - 1;
-                int nsh;
-                const int nfun = atom_prefix_warp(B, aa, sx + a, sy + a, sz + a, b - a, nsh);
-                if (lane == 0 && nfun > 0) { atomicAdd(&s_cnt[0], (nfun + al) & ~al); atomicAdd(&s_cnt[1], 1); atomicAdd(&s_cnt[2], nfun); }
-            }
-        }
+        for (int base = wid * 32; base < B.natoms; base += 128)
+            for_active_atoms(B, base, tg, sx + a, sy + a, sz + a, b - a, [&](int, int, int nfun) {
+                if (lane == 0) { atomicAdd(&s_cnt[0], (nfun + al) & ~al); atomicAdd(&s_cnt[1], 1); atomicAdd(&s_cnt[2], nfun); }
+            });
         __syncthreads();
         const int nraw = s_cnt[0], natom = s_cnt[1], nreal = s_cnt[2];
         const int npts = b - a;
@@ -497,17 +508,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 20) k_basis(DevBasis B, co
     for (int a = tid; a < B.natoms; a += NT) s_atom[a] = 0;
     __syncthreads();
     // phase A1: active prefix of every atom (same arithmetic as k_tile_split => the counts the descriptors were sized with)
-    for (int base = wid * 32; base < B.natoms; base += NT) {
-        const int at = base + lane;
-        unsigned bal = __ballot_sync(0xffffffffu, at < B.natoms && atom_box_pass(B, at, tg));
-        while (bal) {
-            const int aa = base + __ffs(bal) - 1;
-            bal &= bal - 1;
-            int nsh;
-            const int nfun = atom_prefix_warp(B, aa, sx, sy, sz, td.npts, nsh);
-            if (lane == 0 && nfun > 0) s_atom[aa] = (nsh << 20) | nfun;
-        }
-    }
+    for (int base = wid * 32; base < B.natoms; base += NT)
+        for_active_atoms(B, base, tg, sx, sy, sz, td.npts, [&](int aa, int nsh, int nfun) { if (lane == 0) s_atom[aa] = (nsh << 20) | nfun; });
     __syncthreads();
     const int al = B.slot_align - 1;
     for (int a0 = 0; a0 < B.natoms; a0 += NT) {
