@@ -90,6 +90,9 @@ constexpr int CONSUMER_REGS16 = 112, PRODUCER_REGS16 = 32;
 #ifndef DEFAULT_NCW
 #define DEFAULT_NCW 8
 #endif
+#ifndef DEFAULT_EPI
+#define DEFAULT_EPI 0
+#endif
 constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 = 64512 < 65536.  Do NOT use the whole file: with
                                                           // 240/32 (= 65536) setmaxnreg.inc never succeeds and the kernel hangs (measured)
 constexpr int ATAB_MAX = 1024;      // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
@@ -887,6 +890,378 @@ __device__ __forceinline__ void consumer_role16(const JtensorArgs &a, const doub
     }
 }
 
+// ---- tensor path with an EPILOGUE WARPGROUP (default) -------------------------------------------------------------------------------
+// ncu source view of the kernel above (profiles/r02_ncu_jtensor_source_regions.txt): the consumer warps spend 85.6 % of their time in the
+// K loop, where the DMMA pipe is the limit, 10.4 % in the per-chunk epilogue (half of it waiting for the Phi / dPhi rows it loads from
+// global memory) and 4 % in the tile prologue -- and they do so all at the same time, so the DMMA pipe idles for those 14 %.
+// Here the epilogue is a role of its own.  16 warps: 8 consumers (K loop only), 4 producers, 4 epilogue warps (one thread per point).
+//   consumer, end of a nu chunk:  forms  x0 = X_0,  z_b = X_{1+b} + (r x Y)_b  for its 16 x 16 accumulator tile (the GIAO part needs the
+//            accumulators of the taps, so it stays here: 18 DFMA per element), writes the 4 values per (point, column) to a 64.5 KB
+//            exchange buffer in shared memory and goes on with the next chunk's K loop;
+//   epilogue warps:  row r reads the chunk's (x0, z_x, z_y, z_z) from the buffer and Phi, dPhi of the chunk's 16 columns from the panel
+//            (row-contiguous => one coalesced 256 B request per warp and plane, latency off the critical path), keeps the 13 sums of
+//            jtensor.F90:160-235 in registers for the whole tile, finalises and stores.
+// Two more mbarriers (buffer full / buffer free) couple the roles; the producers publish, per chunk, the panel row and the centre R of
+// each column (ring of 6 chunks) so that neither the consumers nor the epilogue warps chase  nlist -> fidx -> fR  through global memory.
+// Registers: (8 x 200 + 4 x 40 + 4 x 72) x 32 = 65536 = the 512 x 128 the CTA is launched with (setmaxnreg only redistributes that pool).
+constexpr int NEPI_WARPS = 4;
+constexpr int NTHREADS_E = (NCONSUMER_WARPS + NPRODUCER_WARPS + NEPI_WARPS) * 32;
+constexpr int CONSUMER_REGS_E = 200, PRODUCER_REGS_E = 40, EPI_REGS_E = 72;
+constexpr int XLD = 4 * MT + 4;        // doubles per column of the exchange buffer: [4 values][128 rows] + 4 pad (the 4 column pairs of a quad land 64 B apart)
+constexpr int CRING = 6;               // column tables in flight.  The table of chunk c is written with the chunk's first stage and read until the
+                                       // epilogue warps finish chunk c, i.e. before the consumers start the K loop of chunk c+2; the producers run at most
+                                       // STAGES stages ahead, so slot (c + CRING) % CRING is rewritten no earlier than stage (c+CRING)*nkc - STAGES >= (c+2)*nkc
+constexpr int ATAB_MAX_E = 128;        // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
+
+struct SmemE {
+    static constexpr int NPP = (NQ + 1) / 2, NVC = NV, LDB = LDB2;
+    static constexpr int A_DOUBLES = BK * LDP, PP_DOUBLES = BK * LDB, B_DOUBLES = NPP * PP_DOUBLES, STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+    static constexpr size_t X_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;                 // exchange buffer [NV][XLD]
+    static constexpr size_t COLR_OFF = X_OFF + (size_t)NV * XLD * 8;                    // [CRING][NV][4]: R_x, R_y, R_z of the column's centre
+    static constexpr size_t COLSLOT_OFF = COLR_OFF + (size_t)CRING * NV * 4 * 8;        // [CRING][NV]: panel row (K slot) of the column
+    static constexpr size_t ATAB_OFF = COLSLOT_OFF + (size_t)CRING * NV * 4;
+    static constexpr size_t KMASK_OFF = ATAB_OFF + (size_t)ATAB_MAX_E * 3 * 8;
+    static constexpr size_t BAR_OFF = KMASK_OFF + (size_t)KMASK_WORDS * 4;              // full[STAGES], empty[STAGES], xfull, xempty
+    static constexpr size_t BYTES = BAR_OFF + (2 * STAGES + 2) * 8 + 16;
+};
+static_assert(SmemE::BYTES <= 232448, "k_jtensor_e: shared memory over the 227 KB of a CTA");
+
+__device__ __forceinline__ void producer_role_e(const JtensorArgs &a, uint32_t s_base, uint32_t bar_full, uint32_t bar_empty, double *s_colR,
+                                                int *s_colSlot, int *s_tile) {
+    using SM = SmemE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t git = 0, gch = 0;           // stages / nu chunks issued so far (all tiles)
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        if (td.nact == 0) continue;
+        const int nact = td.nact, nn = td.nn;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
+        const uint32_t NIT = (uint32_t)nkc * nvc;
+        const double *panel = a.panel_pool + td.panel_off;
+        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
+        const int pw = warp - NCONSUMER_WARPS;
+        const int ldn = lane % NV, ldk0 = lane / NV + 2 * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0 + 8, ...
+        int kc = 0, vc = 0;
+        int slot = nlist[min(ldn, nn - 1)];
+        long nu = fidx[slot];
+        for (uint32_t itl = 0; itl < NIT; ++itl) {
+            const uint32_t gi = git + itl, s = gi % STAGES, ph = (gi / STAGES) & 1;
+            double Rx = 0, Ry = 0, Rz = 0;
+            const bool table = kc == 0 && pw == 0 && lane < NV;          // this lane publishes column ldn of chunk vc
+            if (table) { Rx = a.fR[nu]; Ry = a.fR[a.nbf + nu]; Rz = a.fR[2 * a.nbf + nu]; }   // in flight while the gathers are issued
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            const int kcnt = min(BK, nact - kc * BK);
+            const uint32_t sA = s_base + (uint32_t)(s * SM::STAGE_DOUBLES * 8), sB = sA + SM::A_DOUBLES * 8;
+            if (pw == 0 && lane == 0) {
+                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(kcnt * LDP * 8));
+                tma_bulk_g2s(sA, panel + (long)kc * BK * LDP, (uint32_t)(kcnt * LDP * 8), bar_full + 8 * s);
+            }
+            const bool nu_ok = vc * NV + ldn < nn;
+            const double *srcB = a.Bop + 2 * nu;
+            const uint32_t dstB = sB + (uint32_t)(ldn * 16);
+#pragma unroll 4
+            for (int k = ldk0; k < (nu_ok ? kcnt : 0); k += 2 * NPRODUCER_WARPS) {
+                const long mu = fidx[kc * BK + k];
+                const double *src = srcB + 2 * mu * a.ldb;
+                const uint32_t dst = dstB + (uint32_t)(k * SM::LDB * 8);
+#pragma unroll
+                for (int pp = 0; pp < SM::NPP; ++pp) cp_async_16(dst + (uint32_t)(pp * SM::PP_DOUBLES * 8), src + pp * a.plane_stride);
+            }
+            if (table) {
+                // visible to the consumers through this stage's full barrier (they read it at the END of the sweep) and, through the
+                // consumers' arrival on the exchange barrier, to the epilogue warps.  Ring of CRING chunks: the slot written now was
+                // last read two or more K sweeps ago.
+                const int ring = (int)((gch + vc) % CRING) * NV + ldn;
+                s_colSlot[ring] = slot;
+                double *cr = s_colR + 4 * ring;
+                cr[0] = Rx; cr[1] = Ry; cr[2] = Rz;
+                __threadfence_block();       // ordinary stores before the (asynchronous) arrival below
+            }
+            cp_async_arrive_noinc(bar_full + 8 * s);
+            if (++kc == nkc) { kc = 0; ++vc; if (vc < nvc) { slot = nlist[min(vc * NV + ldn, nn - 1)]; nu = fidx[slot]; } }
+        }
+        git += NIT; gch += nvc;
+    }
+}
+
+template <bool GIAO>
+__device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const double *s_stage, double *s_x, const double *s_colR, double *s_atab,
+                                                uint32_t *s_kmask, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_xfull, uint32_t bar_xempty,
+                                                int *s_tile) {
+    using SM = SmemE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = warp * 16;
+    uint32_t git = 0, gch = 0;
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        if (td.nact == 0) continue;                                   // the epilogue warps write the zeros
+        const int rowA = row0 + g, rowB = row0 + g + 8;
+        const int nact = td.nact, nn = td.nn;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;
+        const uint32_t NIT = (uint32_t)nkc * nvc;
+        // coordinates of this thread's two rows and the tile centre (GIAO: r x Y, and Y relative to the centre like the tap weights)
+        double rAx = 0, rAy = 0, rAz = 0, rBx = 0, rBy = 0, rBz = 0, cenx = 0, ceny = 0, cenz = 0;
+        if (GIAO) {
+            const long pA = td.pt0 + (rowA < td.npts ? rowA : 0), pB = td.pt0 + (rowB < td.npts ? rowB : 0);
+            rAx = a.rsx[pA]; rAy = a.rsy[pA]; rAz = a.rsz[pA]; rBx = a.rsx[pB]; rBy = a.rsy[pB]; rBz = a.rsz[pB];
+            const TileGeo tg = a.geo[td.geo];                          // same expression as k_basis
+            cenx = 0.5 * (tg.lox + tg.hix); ceny = 0.5 * (tg.loy + tg.hiy); cenz = 0.5 * (tg.loz + tg.hiz);
+        }
+        double acc[NQ][2][4];
+        double zac[3][2][4];                                        // Z_d (GIAO taps)
+        const int nruns = td.nruns;
+        const bool tab_sm = nruns <= ATAB_MAX_E;
+        const double *gtab = reinterpret_cast<const double *>(a.atab_pool + td.atab_off);
+        double curx = 0, cury = 0, curz = 0;
+        int ia = 0;
+        if (GIAO) {
+            // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
+            const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
+            const int ctid = threadIdx.x, nwords = (nact / 4 + 31) / 32;
+            for (int w = ctid; w < nwords; w += NCONSUMER_WARPS * 32) s_kmask[w] = 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+            for (int r = ctid; r < nruns; r += NCONSUMER_WARPS * 32) {
+                const double2 t0 = __ldg(atab + 2 * r), t1 = __ldg(atab + 2 * r + 1);
+                if (r < ATAB_MAX_E) { s_atab[3 * r] = t0.x; s_atab[3 * r + 1] = t0.y; s_atab[3 * r + 2] = t1.x; }
+                const int e = __double2loint(t1.y) - 1;
+                atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+        }
+        int kc = 0, vc = 0;
+        for (uint32_t it = 0; it < NIT; ++it) {
+            const uint32_t gi = git + it, s = gi % STAGES, ph = (gi / STAGES) & 1;
+            if (kc == 0) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
+                if (GIAO) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zac[d][h][i] = 0.0;
+                    ia = 0;
+                    load_tap_weights(tab_sm, s_atab, gtab, 0, curx, cury, curz);
+                }
+            }
+            const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
+            const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
+            const int nks = min(BK, nact - kc * BK) / 4;
+            const bool h1 = vc * NV + 8 < nn;                       // second n8 tile of this chunk holds real columns
+            const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
+            const double *sB = sA + SM::A_DOUBLES;
+            mbar_wait(bar_full + 8 * s, ph);
+#pragma unroll KSU
+            for (int ks = 0; ks < nks; ++ks) {
+                // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
+                const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
+                const double a0 = pa[0], a1 = pa[8];
+                const double2 *pb = reinterpret_cast<const double2 *>(sB + (ks * 4 + t) * LDB2) + g;   // one LDS.128 = both planes of a pair
+#pragma unroll
+                for (int pp = 0; pp < SM::NPP; ++pp)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !h1) continue;
+                        const double2 b = pb[pp * (SM::PP_DOUBLES / 2) + h * 8];
+                        mma_16x8x4_f64(acc[2 * pp][h], a0, a1, b.x);
+                        mma_16x8x4_f64(acc[2 * pp + 1][h], a0, a1, b.y);
+                    }
+                if (GIAO && ((m8 >> ks) & 1u)) {
+                    // last K step of an atom: Z_d += C_A * (R_A - R_next)_d  (see the header; C_A = acc[0] right now)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double cv = acc[0][h][i];
+                            zac[0][h][i] = fma(curx, cv, zac[0][h][i]);
+                            zac[1][h][i] = fma(cury, cv, zac[1][h][i]);
+                            zac[2][h][i] = fma(curz, cv, zac[2][h][i]);
+                        }
+                    ia = min(ia + 1, nruns - 1);
+                    load_tap_weights(tab_sm, s_atab, gtab, ia, curx, cury, curz);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
+            if (++kc == nkc) {
+                // ---- hand nu chunk vc to the epilogue warps: (x0, z_x, z_y, z_z) per (row, column) ----------------------------
+                const uint32_t c = gch + vc;
+                mbar_wait(bar_xempty, (c & 1) ^ 1);                  // the epilogue warps are done with the previous chunk
+                const double *colR = s_colR + (size_t)(c % CRING) * NV * 4;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !h1) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int col = h * 8 + 2 * t + j;
+                        double dRx = 0, dRy = 0, dRz = 0;
+                        if (GIAO) { const double2 r01 = *reinterpret_cast<const double2 *>(colR + 4 * col); dRx = r01.x - cenx; dRy = r01.y - ceny; dRz = colR[4 * col + 2] - cenz; }
+                        double *xc = s_x + (size_t)col * XLD;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int ci = 2 * rr + j, row = rr ? rowB : rowA;
+                            const double x0 = acc[0][h][ci];
+                            double zx = acc[1][h][ci], zy = acc[2][h][ci], zz = acc[3][h][ci];
+                            if (GIAO) {
+                                const double px = rr ? rBx : rAx, py = rr ? rBy : rAy, pz = rr ? rBz : rAz;
+                                const double yx = dRx * x0 - zac[0][h][ci], yy = dRy * x0 - zac[1][h][ci], yz = dRz * x0 - zac[2][h][ci];
+                                zx += py * yz - pz * yy;   // (r x Y')_x
+                                zy += pz * yx - px * yz;
+                                zz += px * yy - py * yx;
+                            }
+                            xc[row] = x0; xc[MT + row] = zx; xc[2 * MT + row] = zy; xc[3 * MT + row] = zz;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_xfull);
+                kc = 0; ++vc;
+            }
+        }
+        git += NIT; gch += nvc;
+    }
+}
+
+// one thread per point of the tile
+template <bool GIAO>
+__device__ __forceinline__ void epilogue_role_e(const JtensorArgs &a, const double *s_x, const double *s_colR, const int *s_colSlot,
+                                                uint32_t bar_xfull, uint32_t bar_xempty, int *s_tile) {
+    const int lane = threadIdx.x & 31;
+    const int row = threadIdx.x - (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
+    uint32_t gch = 0;
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        const bool valid = row < td.npts;
+        if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
+            if (valid) store_zero(a, out_row(a, td.pt0 + row));
+            continue;
+        }
+        const int nact = td.nact, nn = td.nn;
+        const int nvc = (nn + NV - 1) / NV;
+        const double *panel = a.panel_pool + td.panel_off + row;       // rows >= npts hold zeros (k_basis writes all MT rows)
+        const long plane = (long)nact * LDP;
+        const long p = td.pt0 + (valid ? row : 0);
+        const double px = a.rsx[p], py = a.rsy[p], pz = a.rsz[p];     // absolute coordinates (as r enters jtensor.F90:112 and bfeval.f90:168-189)
+        double e[13];                                                   // Tp(m,b) at [m+3b], V_d at [9+d], rho at [12]
+#pragma unroll
+        for (int i = 0; i < 13; ++i) e[i] = 0.0;
+        for (int vc = 0; vc < nvc; ++vc) {
+            const uint32_t c = gch + vc;
+            const int ncol = min(NV, nn - vc * NV);
+            const int *cslot = s_colSlot + (size_t)(c % CRING) * NV;
+            const double *colR = s_colR + (size_t)(c % CRING) * NV * 4;
+            mbar_wait(bar_xfull, c & 1);
+            for (int c0 = 0; c0 < ncol; c0 += 4) {                     // ncol is 8 or 16: four columns' panel rows in flight at a time
+                double ev[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double *pe = panel + (long)cslot[c0 + k] * LDP;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ev[k][q] = pe[q * plane];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double *xc = s_x + (size_t)(c0 + k) * XLD + row;
+                    const double x0 = xc[0], zx = xc[MT], zy = xc[2 * MT], zz = xc[3 * MT];
+                    const double t0 = x0 * ev[k][0];
+                    e[12] += t0;
+                    if (GIAO) { const double *cr = colR + 4 * (c0 + k); e[9] += cr[0] * t0; e[10] += cr[1] * t0; e[11] += cr[2] * t0; }
+                    e[0] += zx * ev[k][1]; e[1] += zx * ev[k][2]; e[2] += zx * ev[k][3];   // b = x: m = x,y,z
+                    e[3] += zy * ev[k][1]; e[4] += zy * ev[k][2]; e[5] += zy * ev[k][3];
+                    e[6] += zz * ev[k][1]; e[7] += zz * ev[k][2]; e[8] += zz * ev[k][3];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xempty);
+        }
+        gch += nvc;
+        // ---- finalise and store ---------------------------------------------------------------------
+        if (valid) {
+            double ct[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) ct[i] = e[i];
+            if (GIAO) {   // + sum_d eps(b,m,d) V_d  at ct[m + 3b]
+                ct[0 + 3 * 1] -= e[11]; ct[0 + 3 * 2] += e[10];
+                ct[1 + 3 * 0] += e[11]; ct[1 + 3 * 2] -= e[9];
+                ct[2 + 3 * 0] -= e[10]; ct[2 + 3 * 1] += e[9];
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) ct[i] = a.paramag ? 0.5 * ct[i] : 0.0;      // ZETA, jtensor.F90:209-223
+            const double rho = e[12];
+            const double d1 = a.diamag ? rho * (0.5 * px) : 0.0, d2 = a.diamag ? rho * (0.5 * py) : 0.0,
+                         d3 = a.diamag ? rho * (0.5 * pz) : 0.0;                     // dpd, jtensor.F90:187,225-228
+            ct[0 + 3 * 1] += d3; ct[0 + 3 * 2] -= d2;                                // jtensor.F90:230-235
+            ct[1 + 3 * 0] -= d3; ct[1 + 3 * 2] += d1;
+            ct[2 + 3 * 0] += d2; ct[2 + 3 * 1] -= d1;
+            const long o = out_row(a, td.pt0 + row);
+            if (a.tens) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = ct[i];
+            }
+            if (a.edens) a.edens[o] = rho;
+            // derived fields straight from the registers (what the separate k_fields pass computes from the stored tensor)
+            if (a.jvec || a.jmod) {
+                const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+                const double vx = ct[0] * bx + ct[3] * by + ct[6] * bz, vy = ct[1] * bx + ct[4] * by + ct[7] * bz,
+                             vz = ct[2] * bx + ct[5] * by + ct[8] * bz;                      // matmul(reshape(tens,(3,3)), b), jfield.f90:167-184
+                if (a.jvec) { a.jvec[3 * o] = vx; a.jvec[3 * o + 1] = vy; a.jvec[3 * o + 2] = vz; }
+                if (a.jmod) a.jmod[o] = signed_modulus(vx, vy, vz, px, py, pz, bx, by, bz);
+            }
+            if (a.acid) a.acid[o] = acid_of(ct);
+        }
+    }
+}
+
+template <bool GIAO>
+__global__ void __launch_bounds__(NTHREADS_E, 1) k_jtensor_e(JtensorArgs a) {
+    using SM = SmemE;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_stage = reinterpret_cast<double *>(smem_raw);
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bar_full = s_base + (uint32_t)SM::BAR_OFF, bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_xfull = bar_empty + STAGES * 8, bar_xempty = bar_xfull + 8;
+    int *s_tile = reinterpret_cast<int *>(smem_raw + SM::BAR_OFF + (2 * STAGES + 2) * 8);
+    double *s_x = reinterpret_cast<double *>(smem_raw + SM::X_OFF), *s_colR = reinterpret_cast<double *>(smem_raw + SM::COLR_OFF);
+    int *s_colSlot = reinterpret_cast<int *>(smem_raw + SM::COLSLOT_OFF);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, NPRODUCER_WARPS * 32 + 1); mbar_init(bar_empty + 8 * s, NCONSUMER_WARPS); }
+        mbar_init(bar_xfull, NCONSUMER_WARPS); mbar_init(bar_xempty, NEPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    if (warp >= NCONSUMER_WARPS + NPRODUCER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS_E));
+        epilogue_role_e<GIAO>(a, s_x, s_colR, s_colSlot, bar_xfull, bar_xempty, s_tile);
+    } else if (warp >= NCONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS_E));
+        producer_role_e(a, s_base, bar_full, bar_empty, s_colR, s_colSlot, s_tile);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS_E));
+        double *atab = reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF);
+        uint32_t *kmask = reinterpret_cast<uint32_t *>(smem_raw + SM::KMASK_OFF);
+        consumer_role_e<GIAO>(a, s_stage, s_x, s_colR, atab, kmask, bar_full, bar_empty, bar_xfull, bar_xempty, s_tile);
+    }
+}
+
+template <bool GIAO>
+static void launch_one_e(const JtensorArgs &a, int grid, cudaStream_t s) {
+    cudaFuncSetAttribute(k_jtensor_e<GIAO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemE::BYTES);
+    k_jtensor_e<GIAO><<<grid, NTHREADS_E, SmemE::BYTES, s>>>(a);
+}
+
 // Pipeline: warps 8-11 are producers.  Per stage they (1) wait for the slot to be released by the 8 consumer warps
 // (empty barrier), (2) issue ONE bulk-TMA copy of the contiguous Phi panel rows [kc*BK, +kcnt) x 132 doubles
 // (expect_tx on the full barrier) and (3) gather the density elements B_q[fidx[k]][fidx[nu]] of all NQ planes with
@@ -938,11 +1313,18 @@ static int tensor_path_consumer_warps() {
     return ncw;
 }
 
+// GIMIC_B200_EPI=0 selects the kernels without the epilogue warpgroup (A/B measurements)
+static bool tensor_path_epilogue_role() {
+    static const bool on = [] { const char *e = std::getenv("GIMIC_B200_EPI"); return e ? std::atoi(e) != 0 : DEFAULT_EPI != 0; }();
+    return on;
+}
+
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;
     const int grid = a.ntiles < nsm ? a.ntiles : nsm;
     const bool jv = a.jpath != 0;        // J = T.B path: operands are ONE pair-plane (D, sum_b B_b P_b)
     if (jv) { if (giao) launch_one<true, true, 8>(a, grid, s); else launch_one<false, true, 8>(a, grid, s); return; }
+    if (tensor_path_epilogue_role()) { if (giao) launch_one_e<true>(a, grid, s); else launch_one_e<false>(a, grid, s); return; }
     if (tensor_path_consumer_warps() == 16) { if (giao) launch_one<true, false, 16>(a, grid, s); else launch_one<false, false, 16>(a, grid, s); }
     else { if (giao) launch_one<true, false, 8>(a, grid, s); else launch_one<false, false, 8>(a, grid, s); }
 }
