@@ -91,7 +91,7 @@ constexpr int CONSUMER_REGS16 = 112, PRODUCER_REGS16 = 32;
 #define DEFAULT_NCW 8
 #endif
 #ifndef DEFAULT_EPI
-#define DEFAULT_EPI 0
+#define DEFAULT_EPI 1
 #endif
 constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // (8*232 + 4*40) * 32 = 64512 < 65536.  Do NOT use the whole file: with
                                                           // 240/32 (= 65536) setmaxnreg.inc never succeeds and the kernel hangs (measured)
@@ -143,6 +143,12 @@ __device__ __forceinline__ double acid_of(const double (&t)[9]) {
     const double xypyx = (t[3] + t[1]) * (t[3] + t[1]), xzpzx = (t[6] + t[2]) * (t[6] + t[2]), yzpzy = (t[7] + t[5]) * (t[7] + t[5]);
     return 0.3333333 * (xxmyy + yymzz + zzmxx) + 0.5 * (xypyx + xzpzx + yzpzy);
 }
+
+// Keep a loop-invariant value in a register: without this ptxas re-derives the lane id and every shared-memory address from the special
+// registers (S2R SR_TID.X, S2R/S2UR SR_CgaCtaId + LEA) at every pipeline stage -- three dependent ~40-cycle chains per stage that both
+// warps of a scheduler run at the same time (2.4 % of the consumer's samples in profiles/r02_ncu_jtensor_e_source_regions.txt).
+__device__ __forceinline__ void keep_in_register(uint32_t &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep_in_register(int &v) { asm volatile("" : "+r"(v)); }
 
 __device__ __forceinline__ void load_tap_weights(bool tab_sm, const double *s_atab, const double *gtab, int ia, double &x, double &y, double &z) {
     if (tab_sm) { const double *p = s_atab + 3 * ia; x = p[0]; y = p[1]; z = p[2]; }          // [ATAB_MAX][3] in shared memory
@@ -991,9 +997,10 @@ __device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const doub
                                                 uint32_t *s_kmask, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_xfull, uint32_t bar_xempty,
                                                 int *s_tile) {
     using SM = SmemE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31, row0 = (threadIdx.x >> 5) * 16;
+    keep_in_register(lane); keep_in_register(row0);
+    keep_in_register(bar_full); keep_in_register(bar_empty); keep_in_register(bar_xfull); keep_in_register(bar_xempty);
     const int g = lane >> 2, t = lane & 3;
-    const int row0 = warp * 16;
     uint32_t git = 0, gch = 0;
     for (;;) {
         const int tile = next_tile(a, s_tile);
