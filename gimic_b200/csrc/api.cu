@@ -76,7 +76,7 @@ struct gimic_b200_ctx {
     size_t pool_max_bytes = (size_t)8 << 30;
     // workspaces
     Buf keys0, keys1, vals0, vals1, sorttmp, rs, panel, fidx, atab, misc, r_in, r_in2, tens_tmp, tens_tmp2, f_tmp, f_tmp2, shift, jv6, gridbuf, quad;
-    Buf p_seg, p_geo, p_info, p_cnt, p_off, geo, desc, cum, pkeys0, pkeys1, pord0, pord1, tiles, d_summary;   // tile plan (k_prepare.cu)
+    Buf p_seg, p_geo, p_info, p_cnt, p_off, geo, desc, cum, pkeys0, pkeys1, pord0, pord1, tiles, d_summary, p_tops;   // tile plan (k_prepare.cu)
     gb::PlanSummary *h_summary = nullptr;   // pinned
     Plan plan;
     double split_radius = 2.5;   // bohr: tiles wider than this are cut at their largest consecutive gap if that shrinks them
@@ -98,7 +98,7 @@ struct gimic_b200_ctx {
         for (int i = 0; i < 4; ++i) if (d_opj[i]) cudaFree(d_opj[i]);
         for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &panel, &fidx, &atab, &misc, &r_in, &r_in2, &tens_tmp, &tens_tmp2, &f_tmp, &f_tmp2,
                        &shift, &jv6, &gridbuf, &quad, &p_seg, &p_geo, &p_info, &p_cnt, &p_off, &geo, &desc, &cum, &pkeys0, &pkeys1, &pord0, &pord1,
-                       &tiles, &d_summary}) b->release();
+                       &tiles, &d_summary, &p_tops}) b->release();
         if (h_summary) cudaFreeHost(h_summary);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : evpool) cudaEventDestroy(e);
@@ -365,7 +365,7 @@ int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nrank
             c->p_info.ensure((size_t)nrun0 * MAXSUB * sizeof(TileInfo)) || c->p_cnt.ensure((size_t)nrun0 * 4) || c->p_off.ensure((size_t)(nrun0 + 1) * 4) ||
             c->geo.ensure((size_t)cap * sizeof(TileGeo)) || c->desc.ensure((size_t)cap * sizeof(TileDesc)) || c->cum.ensure((size_t)(cap + 1) * sizeof(TileCum)) ||
             c->pkeys0.ensure((size_t)cap * 8) || c->pkeys1.ensure((size_t)cap * 8) || c->pord0.ensure((size_t)cap * 4) || c->pord1.ensure((size_t)cap * 4) ||
-            c->tiles.ensure((size_t)cap * sizeof(TileDesc)))
+            c->tiles.ensure((size_t)cap * sizeof(TileDesc)) || c->p_tops.ensure((size_t)(nrun0 * MAXSUB / 2048 + 4) * (sizeof(TileCum) + sizeof(int))))
             return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tiles)");
         PlanBuffers pb;
         pb.slot_seg = c->p_seg.as<TileSeg>(); pb.slot_geo = c->p_geo.as<TileGeo>(); pb.slot_info = c->p_info.as<TileInfo>();
@@ -373,9 +373,10 @@ int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nrank
         pb.cum = c->cum.as<TileCum>(); pb.keys0 = c->pkeys0.as<unsigned long long>(); pb.keys1 = c->pkeys1.as<unsigned long long>();
         pb.ord0 = c->pord0.as<int>(); pb.ord1 = c->pord1.as<int>(); pb.tiles = c->tiles.as<TileDesc>();
         pb.summary = c->d_summary.as<PlanSummary>(); pb.cap = (int)cap;
+        pb.tops_c = c->p_tops.as<TileCum>(); pb.tops_i = reinterpret_cast<int *>(pb.tops_c + (nrun0 * MAXSUB / 2048 + 4));
         launch_plan_tiles(c->db, rsx, rsy, rsz, n, c->split_radius, rank, nranks, pool_doubles, pb, st);
         CUDA_TRY(cudaGetLastError());
-        c->stats.launches += 6;
+        c->stats.launches += 10;
         CUDA_TRY(cudaMemcpyAsync(c->h_summary, pb.summary, sizeof(PlanSummary), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));          // the ONE host round trip of a plan
         S = *c->h_summary;

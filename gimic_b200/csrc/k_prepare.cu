@@ -57,13 +57,16 @@ void launch_morton_keys(const double *r, long n, const double *bbox_lo, double i
     k_morton_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, n, bbox_lo[0], bbox_lo[1], bbox_lo[2], inv_cell, keys, vals);
 }
 
+// Only the top 30 of the 48 key bits are sorted on (4 radix passes instead of 6): cells of (box / 1024) ~ 0.1 bohr along the curve; the
+// sort is stable, so points of one cell keep the caller's order -- they are closer together than any tile is wide.
+constexpr int SORT_BEGIN_BIT = 18;
 size_t sort_temp_bytes(long n) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, 0, 48);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, SORT_BEGIN_BIT, 48);
     return bytes;
 }
 void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s) {
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 48, s);
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, SORT_BEGIN_BIT, 48, s);
 }
 
 __global__ void k_gather_points(const double *__restrict__ r, const int *__restrict__ perm, long n, double *__restrict__ rsx,
@@ -266,10 +269,16 @@ __global__ void __launch_bounds__(128, 8) k_tile_split(DevBasis B, const double 
     if (tid == 0) cnt_out[run] = emitted;
 }
 
-// Exclusive prefix sums by ONE CTA of 1024 threads (the arrays are a few MB at most and sit in L2; a call over 2^31 points has
-// 16 M runs: ~10 ms next to hours of contraction).  The element count may live on the device (n_dev).  out[n] = total.
+// Exclusive prefix sums (out may alias in; out[n] = total): tiles of SCAN_TILE elements per CTA (k_scan_partial_*), one CTA over the
+// tile totals (k_scan_tops_*), offsets added back (k_scan_add_*).  The element count may live on the device (n_dev).  Round 2 first
+// used ONE CTA for the whole array: 0.88 ms per plan of the 256^3 grid (131 072 runs), a quarter of the replicated per-rank plan.
+constexpr int SCAN_TPB = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_TPB * SCAN_IPT;
+struct AddI { __device__ __forceinline__ int operator()(int a, int b) const { return a + b; } };
+struct AddC { __device__ __forceinline__ TileCum operator()(TileCum a, TileCum b) const { return TileCum{a.cost + b.cost, a.panel + b.panel, a.fidx + b.fidx, a.atab + b.atab}; } };
+
+// One CTA: exclusive scan of in[0, n) into out (may alias in); the total is left in s_part[blockDim.x - 1] and, if write_total, in out[n].
 template <typename T, typename Add>
-__device__ __forceinline__ void block_scan_exclusive(const T *in, T *out, int n, T zero, Add add, T *s_part /*[1024]*/) {
+__device__ __forceinline__ void block_scan_exclusive(const T *in, T *out, int n, T zero, Add add, T *s_part /*[blockDim.x]*/, bool write_total) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int chunk = (n + nt - 1) / nt;
     const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
@@ -286,18 +295,49 @@ __device__ __forceinline__ void block_scan_exclusive(const T *in, T *out, int n,
     }
     T run = tid ? s_part[tid - 1] : zero;
     for (int i = lo; i < hi; ++i) { const T v = in[i]; out[i] = run; run = add(run, v); }
-    if (tid == nt - 1) out[n] = s_part[nt - 1];
+    if (write_total && tid == nt - 1) out[n] = s_part[nt - 1];
 }
-__global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cnt, int *off, int n, PlanSummary *sum, int cap) {
+template <typename T, typename Add>
+__device__ __forceinline__ void scan_partial_body(const T *in, T *out, int n, T zero, Add add, T *tops, T *s_part) {
+    const int base = blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    const int m = min(SCAN_TILE, n - base);
+    block_scan_exclusive<T>(in + base, out + base, m, zero, add, s_part, false);
+    if (threadIdx.x == blockDim.x - 1) tops[blockIdx.x] = s_part[blockDim.x - 1];
+}
+template <typename T, typename Add>
+__device__ __forceinline__ void scan_add_body(T *out, int n, Add add, const T *tops_excl) {
+    const int base = blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    const int m = min(SCAN_TILE, n - base);
+    const T off = tops_excl[blockIdx.x];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) out[base + i] = add(off, out[base + i]);
+    if (base + m == n && threadIdx.x == 0) out[n] = tops_excl[(n + SCAN_TILE - 1) / SCAN_TILE];
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_partial_i(const int *in, int *out, int n, int *__restrict__ tops) {
+    __shared__ int s_part[SCAN_TPB];
+    scan_partial_body<int>(in, out, n, 0, AddI(), tops, s_part);
+}
+__global__ void __launch_bounds__(1024) k_scan_tops_i(int *tops, int n) {
     __shared__ int s_part[1024];
-    block_scan_exclusive<int>(cnt, off, n, 0, [](int a, int b) { return a + b; }, s_part);
-    __syncthreads();
-    if (threadIdx.x == 0) { sum->ntiles = off[n] < cap ? off[n] : cap; sum->overflow = off[n] > cap; }
+    const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    block_scan_exclusive<int>(tops, tops, nb, 0, AddI(), s_part, true);
 }
-__global__ void __launch_bounds__(1024) k_scan_cum(TileCum *cum, const PlanSummary *sum) {
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_add_i(int *out, int n, const int *__restrict__ tops, PlanSummary *sum, int cap) {
+    scan_add_body<int>(out, n, AddI(), tops);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const int tot = tops[(n + SCAN_TILE - 1) / SCAN_TILE]; sum->ntiles = tot < cap ? tot : cap; sum->overflow = tot > cap; }
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_partial_c(const TileCum *in, TileCum *out, const PlanSummary *sum, TileCum *__restrict__ tops) {
+    __shared__ TileCum s_part[SCAN_TPB];
+    scan_partial_body<TileCum>(in, out, sum->ntiles, TileCum{0, 0, 0, 0}, AddC(), tops, s_part);
+}
+__global__ void __launch_bounds__(1024) k_scan_tops_c(TileCum *tops, const PlanSummary *sum) {
     __shared__ TileCum s_part[1024];
-    block_scan_exclusive<TileCum>(cum, cum, sum->ntiles, TileCum{0, 0, 0, 0},
-                                  [](TileCum a, TileCum b) { return TileCum{a.cost + b.cost, a.panel + b.panel, a.fidx + b.fidx, a.atab + b.atab}; }, s_part);
+    const int nb = (sum->ntiles + SCAN_TILE - 1) / SCAN_TILE;
+    block_scan_exclusive<TileCum>(tops, tops, nb, TileCum{0, 0, 0, 0}, AddC(), s_part, true);
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_add_c(TileCum *out, const PlanSummary *sum, const TileCum *__restrict__ tops) {
+    scan_add_body<TileCum>(out, sum->ntiles, AddC(), tops);
 }
 
 // compact tiles in Hilbert order + their sizes; one thread per initial run
@@ -413,9 +453,14 @@ void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, 
     const long nrun0 = (n + MT - 1) / MT;
     if (nrun0 <= 0) return;
     k_tile_split<<<(unsigned)nrun0, 128, 0, s>>>(B, rsx, rsy, rsz, n, split_radius, pb.slot_seg, pb.slot_geo, pb.slot_info, pb.cnt);
-    k_scan_counts<<<1, 1024, 0, s>>>(pb.cnt, pb.off, (int)nrun0, pb.summary, pb.cap);
+    const int nb0 = (int)((nrun0 + SCAN_TILE - 1) / SCAN_TILE), nbc = (pb.cap + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_partial_i<<<nb0, SCAN_TPB, 0, s>>>(pb.cnt, pb.off, (int)nrun0, pb.tops_i);
+    k_scan_tops_i<<<1, 1024, 0, s>>>(pb.tops_i, (int)nrun0);
+    k_scan_add_i<<<nb0, SCAN_TPB, 0, s>>>(pb.off, (int)nrun0, pb.tops_i, pb.summary, pb.cap);
     k_tile_emit<<<(unsigned)((nrun0 + 127) / 128), 128, 0, s>>>(pb.slot_seg, pb.slot_geo, pb.slot_info, pb.cnt, pb.off, nrun0, pb.cap, pb.geo, pb.desc, pb.cum);
-    k_scan_cum<<<1, 1024, 0, s>>>(pb.cum, pb.summary);
+    k_scan_partial_c<<<nbc, SCAN_TPB, 0, s>>>(pb.cum, pb.cum, pb.summary, pb.tops_c);
+    k_scan_tops_c<<<1, 1024, 0, s>>>(pb.tops_c, pb.summary);
+    k_scan_add_c<<<nbc, SCAN_TPB, 0, s>>>(pb.cum, pb.summary, pb.tops_c);
     k_plan_range<<<64, 256, 0, s>>>(pb.desc, pb.cum, rank, nranks, pool_doubles, pb.summary);
     k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0);
 }

@@ -94,6 +94,7 @@ struct PlanBuffers {                // device workspaces of one plan (all sized 
     unsigned long long *keys0, *keys1; int *ord0, *ord1;         // [cap] scheduling keys / tile order (CUB sort)
     TileDesc *tiles;                                             // [cap] this rank's tiles in processing order (batch by batch, longest first)
     PlanSummary *summary;                                        // device copy
+    int *tops_i; TileCum *tops_c;                                // [cap / 2048 + 2] tile totals of the prefix sums
     int cap;
 };
 void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, double split_radius,

@@ -109,13 +109,18 @@ void emulate_tile_split(void **a, unsigned nrun0) {
         cnt[run] = emitted;
     }
 }
-void emulate_scan_counts(void **a) {
+// The prefix sums are three kernels each on the device (tile scans, scan of the tile totals, offsets added back).  Here the first one
+// produces the final result and the third only does what it does besides adding (the run -> tile count of the summary).
+void emulate_scan_partial_i(void **a) {
     const int *cnt = *(const int **)a[0]; int *off = *(int **)a[1]; const int n = *(const int *)a[2];
-    gb::PlanSummary *sum = *(gb::PlanSummary **)a[3]; const int cap = *(const int *)a[4];
     int run = 0;
-    for (int i = 0; i < n; ++i) { off[i] = run; run += cnt[i]; }
+    for (int i = 0; i < n; ++i) { const int v = cnt[i]; off[i] = run; run += v; }
     off[n] = run;
-    sum->ntiles = std::min(run, cap); sum->overflow = run > cap;
+}
+void emulate_scan_add_i(void **a) {
+    const int *off = *(const int **)a[0]; const int n = *(const int *)a[1];
+    gb::PlanSummary *sum = *(gb::PlanSummary **)a[3]; const int cap = *(const int *)a[4];
+    sum->ntiles = std::min(off[n], cap); sum->overflow = off[n] > cap;
 }
 void emulate_tile_emit(void **a) {
     const gb::TileSeg *seg = *(const gb::TileSeg **)a[0]; const gb::TileGeo *sgeo = *(const gb::TileGeo **)a[1];
@@ -134,8 +139,8 @@ void emulate_tile_emit(void **a) {
             cum[t] = gb::TileCum{4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + (td.nact ? 4096 : 64), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
         }
 }
-void emulate_scan_cum(void **a) {
-    gb::TileCum *cum = *(gb::TileCum **)a[0]; const gb::PlanSummary *sum = *(const gb::PlanSummary **)a[1];
+void emulate_scan_partial_c(void **a) {
+    gb::TileCum *cum = *(gb::TileCum **)a[1]; const gb::PlanSummary *sum = *(const gb::PlanSummary **)a[2];
     gb::TileCum run{0, 0, 0, 0};
     for (int t = 0; t < sum->ntiles; ++t) {
         const gb::TileCum v = cum[t];
@@ -230,9 +235,10 @@ cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **arg
     if (!std::getenv("FAKE_CUDA_NO_EMULATION")) {
         if (name.find("k_gather_points") != std::string::npos) emulate_gather_points(args);
         else if (name.find("k_tile_split") != std::string::npos) emulate_tile_split(args, grid.x);
-        else if (name.find("k_scan_counts") != std::string::npos) emulate_scan_counts(args);
+        else if (name.find("k_scan_partial_i") != std::string::npos) emulate_scan_partial_i(args);
+        else if (name.find("k_scan_add_i") != std::string::npos) emulate_scan_add_i(args);
         else if (name.find("k_tile_emit") != std::string::npos) emulate_tile_emit(args);
-        else if (name.find("k_scan_cum") != std::string::npos) emulate_scan_cum(args);
+        else if (name.find("k_scan_partial_c") != std::string::npos) emulate_scan_partial_c(args);
         else if (name.find("k_plan_range") != std::string::npos) emulate_plan_range(args);
         else if (name.find("k_plan_finalize") != std::string::npos) emulate_plan_finalize(args);
         else if (name.find("k_tile_gather") != std::string::npos) emulate_tile_gather(args);
