@@ -59,9 +59,7 @@ struct Plan {                        // one sorted, tiled point set (and this ra
 
 struct gimic_b200_ctx {
     int device = 0, nsm = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, basis_stream = nullptr;
-    bool overlap_basis = false;        // panels of batch b+1 written (single-warp CTAs, second stream) while batch b is contracted
-    cudaEvent_t ev_ovl[5] = {};        // [0,1] basis of buffer 0/1 done, [2,3] contraction of buffer 0/1 done, [4] plan ready
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     gimic_b200_opts opts{};
     gb::HostBasis hb;
     gb::DevBasis db{};
@@ -106,10 +104,8 @@ struct gimic_b200_ctx {
         for (auto &e : ev_call) if (e) cudaEventDestroy(e);
         for (auto &e : ev_plan) if (e) cudaEventDestroy(e);
         for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
-        for (auto &e : ev_ovl) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
-        if (basis_stream) cudaStreamDestroy(basis_stream);
     }
 };
 
@@ -210,9 +206,6 @@ int init_device(gimic_b200_ctx *c) {
     for (auto &e : c->ev_call) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->ev_plan) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->basis_stream, cudaStreamNonBlocking));
-    for (auto &e : c->ev_ovl) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    if (const char *ov = std::getenv("GIMIC_B200_OVERLAP")) c->overlap_basis = std::atoi(ov) != 0;
     CUDA_TRY(cudaMallocHost((void **)&c->h_summary, sizeof(gb::PlanSummary)));
     // panel pool: one batch (one k_basis + one k_jtensor launch) per ~pool of Phi/dPhi panels.  8 GB is the configuration of the
     // committed ncu captures and launch lists; GIMIC_B200_POOL_MB=24576 (one launch per 2M-point step) measured +1 %.
@@ -315,15 +308,11 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
 }
 
 // ---- the batched tensor pipeline ------------------------------------------------------------------
-// Panel doubles of one batch.  Overlapped mode keeps two batches in flight (one being written, one being contracted) and prefers
-// more, smaller batches: only the first batch's panels are written with nothing to hide behind.
+// Panel doubles of one batch: never smaller than the largest possible tile (every function active, every atom's run padded) -- consecutive
+// tiles then never skip a batch number, which the batch table of the plan relies on.
 long long plan_pool_doubles(const gimic_b200_ctx *c) {
-    const long long all = (long long)(c->pool_max_bytes / 8);
-    const long long want = c->overlap_basis ? std::min<long long>(all / 2, (long long)1 << 28) : all;      // <= 2 GB per batch when overlapped
-    // never smaller than the largest possible tile (every function active, every atom's run padded): consecutive tiles then never skip
-    // a batch number, which the batch table of the plan relies on
     const long long max_tile = 4LL * (((long long)c->hb.nbf + 3LL * c->hb.natoms + 7) / 8 * 8) * gb::LDP;
-    return std::max(want, max_tile);
+    return std::max((long long)(c->pool_max_bytes / 8), max_tile);
 }
 
 // build_plan: Hilbert sort of the points, tiles (with gap splitting), per-tile active-set sizes, this rank's equal-cost share
@@ -436,31 +425,20 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
     // 2 index ints per slot (slot -> function, column -> slot) and at most one atom run per slot
     const size_t slots = pool_doubles / (4 * LDP) + 16;
     const int nbatch = S.nbatch;
-    const bool ovl = c->overlap_basis && nbatch > 1;
-    const size_t nbuf = ovl ? 2 : 1;
-    if (c->panel.ensure(nbuf * pool_doubles * 8) || c->fidx.ensure(nbuf * 2 * slots * 4) || c->atab.ensure(nbuf * slots * sizeof(TileAtom)))
+    if (c->panel.ensure(pool_doubles * 8) || c->fidx.ensure(2 * slots * 4) || c->atab.ensure(slots * sizeof(TileAtom)))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (panel pool)");
-    cudaStream_t sb = ovl ? c->basis_stream : st;
-    if (ovl) { CUDA_TRY(cudaEventRecord(c->ev_ovl[4], st)); CUDA_TRY(cudaStreamWaitEvent(sb, c->ev_ovl[4], 0)); }
     if (prof) while (c->evpool.size() < 3 * (size_t)nbatch) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); c->evpool.push_back(e); }
     for (int b = 0; b < nbatch; ++b) {
         const int t0 = S.batch_start[b] - S.tlo, nb = S.batch_start[b + 1] - S.batch_start[b];
         if (nb <= 0) continue;
-        const int k = ovl ? (b & 1) : 0;
-        double *panel_b = c->panel.as<double>() + (size_t)k * pool_doubles;
-        int *fidx_b = c->fidx.as<int>() + (size_t)k * 2 * slots;
-        TileAtom *atab_b = c->atab.as<TileAtom>() + (size_t)k * slots;
-        if (ovl && b >= 2) CUDA_TRY(cudaStreamWaitEvent(sb, c->ev_ovl[2 + k], 0));      // the contraction that last read this buffer
-        if (prof) cudaEventRecord(c->evpool[3 * b], sb);
-        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, S.max_nruns, c->geo.as<TileGeo>(), rsx, rsy, rsz, panel_b, fidx_b,
-                     giao ? atab_b : nullptr, sb, ovl);
-        if (prof) cudaEventRecord(c->evpool[3 * b + 1], ovl ? sb : st);
-        if (ovl) { CUDA_TRY(cudaEventRecord(c->ev_ovl[k], sb)); CUDA_TRY(cudaStreamWaitEvent(st, c->ev_ovl[k], 0)); }
-        if (prof && ovl) cudaEventRecord(c->evpool[3 * b + 1], st);                      // contraction time: from here (its panels are ready)
+        if (prof) cudaEventRecord(c->evpool[3 * b], st);
+        launch_basis(c->db, c->tiles.as<TileDesc>() + t0, nb, S.max_nruns, c->geo.as<TileGeo>(), rsx, rsy, rsz, c->panel.as<double>(), c->fidx.as<int>(),
+                     giao ? c->atab.as<TileAtom>() : nullptr, st);
+        if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
         JtensorArgs a;
         a.tiles = c->tiles.as<TileDesc>() + t0; a.ntiles = nb; a.counter = c->misc.as<int>();
-        a.panel_pool = panel_b; a.fidx_pool = fidx_b; a.atab_pool = atab_b; a.geo = c->geo.as<TileGeo>();
+        a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>(); a.atab_pool = c->atab.as<TileAtom>(); a.geo = c->geo.as<TileGeo>();
         a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
         a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = compact ? nullptr : c->vals1.as<int>(); a.out_base = compact ? S.pt_lo : 0;
         a.tens = o.tens; a.edens = o.edens; a.jvec = o.jvec; a.jmod = o.jmod; a.acid = o.acid; a.jpath = o.jpath ? 1 : 0;
@@ -471,7 +449,6 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
         c->stats.launches += 2;
         c->stats.contract_launches += 1;
         if (prof) cudaEventRecord(c->evpool[3 * b + 2], st);
-        if (ovl) CUDA_TRY(cudaEventRecord(c->ev_ovl[2 + k], st));
         // a batch is a contiguous run of Hilbert-ordered tiles = of compact output rows: the caller may start draining them
         if (after_batch) if (int rc = (*after_batch)(b, (long)(S.batch_pt[b] - S.pt_lo), (long)(S.batch_pt[b + 1] - S.pt_lo))) return rc;
     }
@@ -480,7 +457,7 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
         float m = 0;
         for (int b = 0; b < nbatch; ++b) {
             if (S.batch_start[b + 1] - S.batch_start[b] <= 0) continue;
-            if (!ovl) { cudaEventElapsedTime(&m, c->evpool[3 * b], c->evpool[3 * b + 1]); c->stats.ms_basis += m; }
+            cudaEventElapsedTime(&m, c->evpool[3 * b], c->evpool[3 * b + 1]); c->stats.ms_basis += m;
             cudaEventElapsedTime(&m, c->evpool[3 * b + 1], c->evpool[3 * b + 2]); c->stats.ms_contract += m;
         }
     }

@@ -83,13 +83,10 @@ constexpr int ROWLD = 17;   // doubles per row-table entry: 13 sums + 3 coordina
 constexpr int NCONSUMER_WARPS = 8;
 constexpr int NPRODUCER_WARPS = 4;   // one warpgroup, so that setmaxnreg can hand its registers to the consumers
 constexpr int NTHREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
-// 16 consumer warps.  setmaxnreg only REDISTRIBUTES the registers the CTA was launched with ((16 + 4) * 32 threads x 96 = 61440): a
-// request beyond that pool never completes and the kernel hangs (measured twice: 8 warps at 240/32 in round 1, 16 warps at 112/40 in
-// round 2).  (16*112 + 4*32) * 32 = 61440 exactly.
-constexpr int CONSUMER_REGS16 = 112, PRODUCER_REGS16 = 32;
-#ifndef DEFAULT_NCW
-#define DEFAULT_NCW 8
-#endif
+// setmaxnreg only REDISTRIBUTES the registers the CTA was launched with: a request beyond that pool never completes and the kernel hangs
+// (measured twice: 8 consumer warps at 240/32 in round 1, a 16-consumer-warp variant at 112/40 in round 2 -- that variant, 16 x 8 column
+// tiles per warp at 112 registers, was measured 10 % slower, its epilogue spilling 444 B per thread, and removed:
+// profiles/r02_ab_ncw_overlap.json).
 #ifndef DEFAULT_EPI
 #define DEFAULT_EPI 1
 #endif
@@ -117,7 +114,6 @@ struct SmemT {
 constexpr int NVJ = 32, LDB2J = 68;                // J path: 4 n8 tiles per chunk; 68 doubles = 34 16-byte units = 2 (mod 8) -> conflict-free LDS.128
 using Smem = SmemT<(NQ + 1) / 2, NV, LDB2>;        // tensor path
 using SmemJ = SmemT<1, NVJ, LDB2J>;                // J = T.B path: same 16 KB of B per stage, twice the columns per A fragment
-using Smem16 = SmemT<(NQ + 1) / 2, NV, LDB2, 2>;    // tensor path with 16 consumer warps: two warps share a row block (one row table each)
 
 // ---- output helpers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ long out_row(const JtensorArgs &a, long p) { return a.perm ? (long)a.perm[p] : p - a.out_base; }
@@ -663,239 +659,6 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
     }
 }
 
-// ---- 16 consumer warps (tensor path) ------------------------------------------------------------------------------------------
-// Same pipeline, same shared-memory stages, but warp w owns rows 16 (w & 7).. and ONE n8 column tile (w >> 3) of the 16-wide nu chunk:
-// 16 + 12 fp64 accumulators per thread instead of 32 + 24, ~112 registers, FOUR warps per scheduler.  The other three warps'
-// DMMAs fill the issue slots while one warp taps the D accumulator at an atom boundary, crosses a stage boundary or waits for its
-// epilogue loads (with two warps per scheduler both reach those points together: ncu showed the FP64 datapath 84.5 % busy,
-// 77 % DMMA + 7 % DFMA).  The two warps of a row block keep separate row tables, added at the end of the tile.
-constexpr int NCW16 = 16;
-constexpr int TABLD = MT * ROWLD + 4;     // doubles per row table (+ tile centre)
-
-template <bool GIAO>
-__device__ __forceinline__ void epilogue_row16(const double (&x)[4][2], const double (&z)[3][2], const double *__restrict__ pe0,
-                                               const double *__restrict__ pe1, long plane, int row, double px, double py, double pz,
-                                               const double (&R)[2][3], double cenx, double ceny, double cenz, double *__restrict__ rs, int t) {
-    double e[13];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) e[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const double *pe = j ? pe1 : pe0;
-        const double e0 = pe[row], e1 = pe[plane + row], e2 = pe[2 * plane + row], e3 = pe[3 * plane + row];
-        const double x0 = x[0][j];
-        const double t0 = x0 * e0;
-        e[12] += t0;
-        double zx = x[1][j], zy = x[2][j], zz = x[3][j];
-        if (GIAO) {
-            e[9] += R[j][0] * t0; e[10] += R[j][1] * t0; e[11] += R[j][2] * t0;
-            const double yx = (R[j][0] - cenx) * x0 - z[0][j], yy = (R[j][1] - ceny) * x0 - z[1][j], yz = (R[j][2] - cenz) * x0 - z[2][j];
-            zx += py * yz - pz * yy;   // (r x Y')_x
-            zy += pz * yx - px * yz;
-            zz += px * yy - py * yx;
-        }
-        e[0] += zx * e1; e[1] += zx * e2; e[2] += zx * e3;   // b = x: m = x,y,z
-        e[3] += zy * e1; e[4] += zy * e2; e[5] += zy * e3;
-        e[6] += zz * e1; e[7] += zz * e2; e[8] += zz * e3;
-    }
-    // reduce over the 4 lanes of the quad (they hold different nu); lane t == 0 adds into the row table of this warp
-#pragma unroll
-    for (int i = 0; i < 13; ++i) { e[i] += __shfl_xor_sync(0xffffffffu, e[i], 1); e[i] += __shfl_xor_sync(0xffffffffu, e[i], 2); }
-    if (t == 0) {
-#pragma unroll
-        for (int i = 0; i < 13; ++i) rs[i] += e[i];
-    }
-}
-
-template <bool GIAO>
-__device__ __forceinline__ void consumer_role16(const JtensorArgs &a, const double *s_stage, double *s_rows, double *s_atab, uint32_t *s_kmask,
-                                                uint32_t bar_full, uint32_t bar_empty, int *s_tile) {
-    using SM = Smem16;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int rb = warp & 7, ch = warp >> 3;                 // row block, column half of the nu chunk
-    const int row0 = rb * 16;
-    double *tab = s_rows + ch * TABLD;                       // this warp's row table
-    uint32_t git = 0;
-    for (;;) {
-        const int tile = next_tile(a, s_tile);
-        if (tile >= a.ntiles) break;
-        const TileDesc td = a.tiles[tile];
-        const int rowA = row0 + g, rowB = row0 + g + 8;
-        const bool vA = rowA < td.npts, vB = rowB < td.npts;
-        if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
-            if (ch == 0 && t < 2 && (t ? vB : vA)) store_zero(a, out_row(a, td.pt0 + (t ? rowB : rowA)));
-            continue;
-        }
-        const int nact = td.nact, nn = td.nn;
-        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
-        const uint32_t NIT = (uint32_t)nkc * nvc;
-        const double *panel = a.panel_pool + td.panel_off;
-        const long plane = (long)nact * LDP;
-        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
-        // Row table of this warp: lane t=0 of a quad owns row A, lane t=1 row B.  [0..12] running sums Tp(m,b) at [m+3b], V_d at [9+d],
-        // rho at [12]; [13..15] the point's absolute coordinates (as r enters jtensor.F90:112 and bfeval.f90:168-189).
-        double *rowA_s = tab + rowA * ROWLD, *rowB_s = tab + rowB * ROWLD;
-        if (t < 2) {
-            double *rs = t ? rowB_s : rowA_s;
-            const long p = td.pt0 + ((t ? vB : vA) ? (t ? rowB : rowA) : 0);
-#pragma unroll
-            for (int i = 0; i < 13; ++i) rs[i] = 0.0;
-            rs[13] = a.rsx[p]; rs[14] = a.rsy[p]; rs[15] = a.rsz[p];
-        }
-        if (GIAO && threadIdx.x == 0) {   // tile centre, same expression as k_basis; read in the epilogue (after the bar.sync below)
-            const TileGeo tg = a.geo[td.geo];
-            s_rows[MT * ROWLD] = 0.5 * (tg.lox + tg.hix); s_rows[MT * ROWLD + 1] = 0.5 * (tg.loy + tg.hiy); s_rows[MT * ROWLD + 2] = 0.5 * (tg.loz + tg.hiz);
-        }
-        __syncwarp();
-        double acc[NQ][4];
-        double zac[3][4];                                           // Z_d (GIAO taps)
-        const int nruns = td.nruns;
-        // tap weights (dx,dy,dz) of run ia: shared memory (LDS; a generic pointer would cost a generic load per weight), or the
-        // global table when the tile has more active atoms than the shared copy holds
-        const bool tab_sm = nruns <= ATAB_MAX;
-        const double *gtab = reinterpret_cast<const double *>(a.atab_pool + td.atab_off);
-        double curx = 0, cury = 0, curz = 0;
-        int ia = 0;
-        int eslot[2];                                               // epilogue: K slot of this thread's 2 nu columns
-        if (GIAO) {
-            // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
-            const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
-            const int ctid = threadIdx.x, nwords = (nact / 4 + 31) / 32;
-            for (int w = ctid; w < nwords; w += NCW16 * 32) s_kmask[w] = 0u;
-            asm volatile("bar.sync 1, %0;" ::"n"(NCW16 * 32) : "memory");
-            for (int r = ctid; r < nruns; r += NCW16 * 32) {
-                const double2 t0 = __ldg(atab + 2 * r), t1 = __ldg(atab + 2 * r + 1);
-                if (r < ATAB_MAX) { s_atab[3 * r] = t0.x; s_atab[3 * r + 1] = t0.y; s_atab[3 * r + 2] = t1.x; }
-                const int e = __double2loint(t1.y) - 1;
-                atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NCW16 * 32) : "memory");
-        }
-        int kc = 0, vc = 0;
-        for (uint32_t it = 0; it < NIT; ++it) {
-            const uint32_t gi = git + it, s = gi % STAGES, ph = (gi / STAGES) & 1;
-            const bool live = ch == 0 || vc * NV + 8 < nn;          // this warp's n8 tile of the chunk holds real columns
-            if (kc == 0) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[q][i] = 0.0;
-                if (GIAO) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) zac[d][i] = 0.0;
-                    ia = 0;
-                    load_tap_weights(tab_sm, s_atab, gtab, 0, curx, cury, curz);
-                }
-                // K slots the epilogue of this chunk needs (loaded a whole K sweep early)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) eslot[j] = nlist[min(vc * NV + ch * 8 + 2 * t + j, nn - 1)];
-            }
-            const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
-            const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
-            const int nks = live ? min(BK, nact - kc * BK) / 4 : 0;
-            const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
-            const double *sB = sA + SM::A_DOUBLES;
-            mbar_wait(bar_full + 8 * s, ph);
-#pragma unroll KSU
-            for (int ks = 0; ks < nks; ++ks) {
-                // fragments (m16n8k4.f64): a0 = A[row g][k t], a1 = A[row g+8][k t]; b0 = B[k t][n g]
-                const double *pa = sA + (ks * 4 + t) * LDP + row0 + g;
-                const double a0 = pa[0], a1 = pa[8];
-                const double2 *pb = reinterpret_cast<const double2 *>(sB + (ks * 4 + t) * LDB2) + g + ch * 8;   // one LDS.128 = both planes of a pair
-#pragma unroll
-                for (int pp = 0; pp < SM::NPP; ++pp) {
-                    const double2 b = pb[pp * (SM::PP_DOUBLES / 2)];
-                    mma_16x8x4_f64(acc[2 * pp], a0, a1, b.x);
-                    mma_16x8x4_f64(acc[2 * pp + 1], a0, a1, b.y);
-                }
-                if (GIAO && ((m8 >> ks) & 1u)) {
-                    // last K step of an atom: Z_d += C_A * (R_A - R_next)_d  (see the header; C_A = acc[0] right now)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double cv = acc[0][i];
-                        zac[0][i] = fma(curx, cv, zac[0][i]);
-                        zac[1][i] = fma(cury, cv, zac[1][i]);
-                        zac[2][i] = fma(curz, cv, zac[2][i]);
-                    }
-                    ia = min(ia + 1, nruns - 1);
-                    load_tap_weights(tab_sm, s_atab, gtab, ia, curx, cury, curz);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
-            if (++kc == nkc) {
-                if (live) {
-                    // ---- fused epilogue for this warp's n8 tile of nu chunk vc: row A, then row B (13 sums live at a time) -----
-                    const double *pe0 = panel + (long)eslot[0] * LDP, *pe1 = panel + (long)eslot[1] * LDP;
-                    double R[2][3] = {{0, 0, 0}, {0, 0, 0}};
-                    if (GIAO) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) { const int f = fidx[eslot[j]]; R[j][0] = a.fR[f]; R[j][1] = a.fR[a.nbf + f]; R[j][2] = a.fR[2 * a.nbf + f]; }
-                    }
-                    const double cenx = s_rows[MT * ROWLD], ceny = s_rows[MT * ROWLD + 1], cenz = s_rows[MT * ROWLD + 2];
-                    {
-                        const double x[4][2] = {{acc[0][0], acc[0][1]}, {acc[1][0], acc[1][1]}, {acc[2][0], acc[2][1]}, {acc[3][0], acc[3][1]}};
-                        const double z[3][2] = {{zac[0][0], zac[0][1]}, {zac[1][0], zac[1][1]}, {zac[2][0], zac[2][1]}};
-                        epilogue_row16<GIAO>(x, z, pe0, pe1, plane, rowA, rowA_s[13], rowA_s[14], rowA_s[15], R, cenx, ceny, cenz, rowA_s, t);
-                    }
-                    {
-                        const double x[4][2] = {{acc[0][2], acc[0][3]}, {acc[1][2], acc[1][3]}, {acc[2][2], acc[2][3]}, {acc[3][2], acc[3][3]}};
-                        const double z[3][2] = {{zac[0][2], zac[0][3]}, {zac[1][2], zac[1][3]}, {zac[2][2], zac[2][3]}};
-                        epilogue_row16<GIAO>(x, z, pe0, pe1, plane, rowB, rowB_s[13], rowB_s[14], rowB_s[15], R, cenx, ceny, cenz, rowB_s, t);
-                    }
-                }
-                kc = 0; ++vc;
-            }
-        }
-        // ---- add the two column halves, finalise and store (the warp with ch == 0) ---------------------------------------------
-        asm volatile("bar.sync 2, %0;" ::"n"(NCW16 * 32) : "memory");
-        if (ch == 0 && t < 2) {
-            const bool v = t ? vB : vA;
-            if (v) {
-                const double *e0 = t ? rowB_s : rowA_s, *e1 = e0 + TABLD;
-                double e[13];
-#pragma unroll
-                for (int i = 0; i < 13; ++i) e[i] = e0[i] + e1[i];
-                const double px = e0[13], py = e0[14], pz = e0[15];
-                double ct[9];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) ct[i] = e[i];
-                if (GIAO) {   // + sum_d eps(b,m,d) V_d  at ct[m + 3b]
-                    ct[0 + 3 * 1] -= e[11]; ct[0 + 3 * 2] += e[10];
-                    ct[1 + 3 * 0] += e[11]; ct[1 + 3 * 2] -= e[9];
-                    ct[2 + 3 * 0] -= e[10]; ct[2 + 3 * 1] += e[9];
-                }
-#pragma unroll
-                for (int i = 0; i < 9; ++i) ct[i] = a.paramag ? 0.5 * ct[i] : 0.0;      // ZETA, jtensor.F90:209-223
-                const double rho = e[12];
-                const double d1 = a.diamag ? rho * (0.5 * px) : 0.0, d2 = a.diamag ? rho * (0.5 * py) : 0.0,
-                             d3 = a.diamag ? rho * (0.5 * pz) : 0.0;                     // dpd, jtensor.F90:187,225-228
-                ct[0 + 3 * 1] += d3; ct[0 + 3 * 2] -= d2;                                // jtensor.F90:230-235
-                ct[1 + 3 * 0] -= d3; ct[1 + 3 * 2] += d1;
-                ct[2 + 3 * 0] += d2; ct[2 + 3 * 1] -= d1;
-                const long o = out_row(a, td.pt0 + (t ? rowB : rowA));
-                if (a.tens) {
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = ct[i];
-                }
-                if (a.edens) a.edens[o] = rho;
-                if (a.jvec || a.jmod) {
-                    const double bx = a.B[0], by = a.B[1], bz = a.B[2];
-                    const double vx = ct[0] * bx + ct[3] * by + ct[6] * bz, vy = ct[1] * bx + ct[4] * by + ct[7] * bz,
-                                 vz = ct[2] * bx + ct[5] * by + ct[8] * bz;
-                    if (a.jvec) { a.jvec[3 * o] = vx; a.jvec[3 * o + 1] = vy; a.jvec[3 * o + 2] = vz; }
-                    if (a.jmod) a.jmod[o] = signed_modulus(vx, vy, vz, px, py, pz, bx, by, bz);
-                }
-                if (a.acid) a.acid[o] = acid_of(ct);
-            }
-        }
-        git += NIT;
-    }
-}
-
 // ---- tensor path with an EPILOGUE WARPGROUP (default) -------------------------------------------------------------------------------
 // ncu source view of the kernel above (profiles/r02_ncu_jtensor_source_regions.txt): the consumer warps spend 85.6 % of their time in the
 // K loop, where the DMMA pipe is the limit, 10.4 % in the per-chunk epilogue (half of it waiting for the Phi / dPhi rows it loads from
@@ -1277,7 +1040,7 @@ static void launch_one_e(const JtensorArgs &a, int grid, cudaStream_t s) {
 // setmaxnreg can give the consumers 232 registers (ptxas budgets each path by the setmaxnreg that dominates it).
 template <bool GIAO, bool JVEC, int NCW>
 __global__ void __launch_bounds__((NCW + NPRODUCER_WARPS) * 32, 1) k_jtensor(JtensorArgs a) {
-    using SM = typename std::conditional<JVEC, SmemJ, typename std::conditional<NCW == 16, Smem16, Smem>::type>::type;
+    using SM = typename std::conditional<JVEC, SmemJ, Smem>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_stage = reinterpret_cast<double *>(smem_raw);
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -1289,38 +1052,29 @@ __global__ void __launch_bounds__((NCW + NPRODUCER_WARPS) * 32, 1) k_jtensor(Jte
     }
     __syncthreads();
     if ((threadIdx.x >> 5) >= NCW) {
-        if (NCW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS16));
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
         producer_role<SM, NCW>(a, s_base, bar_full, bar_empty, s_tile);
     } else {
-        // (8*232 + 4*40) * 32 = 64512 = 384 x 168 and (16*112 + 4*32) * 32 = 61440 = 640 x 96: exactly the launch allocation
-        if (NCW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS16));
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
+        // (8*232 + 4*40) * 32 = 64512 = 384 x 168: exactly the launch allocation
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
         double *rows = reinterpret_cast<double *>(smem_raw + SM::ROW_OFF), *atab = reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF);
         uint32_t *kmask = reinterpret_cast<uint32_t *>(smem_raw + SM::KMASK_OFF);
         if (JVEC) consumer_role_j<GIAO>(a, s_stage, rows, atab, kmask, bar_full, bar_empty, s_tile);
-        else if (NCW == 16) consumer_role16<GIAO>(a, s_stage, rows, atab, kmask, bar_full, bar_empty, s_tile);
         else consumer_role<GIAO>(a, s_stage, rows, atab, kmask, bar_full, bar_empty, s_tile);
     }
 }
 
-size_t jtensor_smem_bytes() { return Smem16::BYTES; }
+size_t jtensor_smem_bytes() { return SmemE::BYTES; }
 
 template <bool GIAO, bool JVEC, int NCW>
 static void launch_one(const JtensorArgs &a, int grid, cudaStream_t s) {
-    constexpr size_t bytes = JVEC ? SmemJ::BYTES : (NCW == 16 ? Smem16::BYTES : Smem::BYTES);
+    constexpr size_t bytes = JVEC ? SmemJ::BYTES : Smem::BYTES;
     // per-device function attribute (a process may hold contexts on several GPUs): cheap enough to set on every launch
     cudaFuncSetAttribute(k_jtensor<GIAO, JVEC, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_jtensor<GIAO, JVEC, NCW><<<grid, (NCW + NPRODUCER_WARPS) * 32, bytes, s>>>(a);
 }
 
-// GIMIC_B200_NCW=8 selects the round-1 tensor-path mapping (8 consumer warps x 16x16 accumulator tiles) for A/B measurements
-static int tensor_path_consumer_warps() {
-    static const int ncw = [] { const char *e = std::getenv("GIMIC_B200_NCW"); const int v = e ? std::atoi(e) : DEFAULT_NCW; return v == 16 ? 16 : 8; }();
-    return ncw;
-}
-
-// GIMIC_B200_EPI=0 selects the kernels without the epilogue warpgroup (A/B measurements)
+// GIMIC_B200_EPI=0 selects the round-1 mapping of the tensor path (epilogue inside the consumer warps) for A/B measurements
 static bool tensor_path_epilogue_role() {
     static const bool on = [] { const char *e = std::getenv("GIMIC_B200_EPI"); return e ? std::atoi(e) != 0 : DEFAULT_EPI != 0; }();
     return on;
@@ -1332,8 +1086,7 @@ void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     const bool jv = a.jpath != 0;        // J = T.B path: operands are ONE pair-plane (D, sum_b B_b P_b)
     if (jv) { if (giao) launch_one<true, true, 8>(a, grid, s); else launch_one<false, true, 8>(a, grid, s); return; }
     if (tensor_path_epilogue_role()) { if (giao) launch_one_e<true>(a, grid, s); else launch_one_e<false>(a, grid, s); return; }
-    if (tensor_path_consumer_warps() == 16) { if (giao) launch_one<true, false, 16>(a, grid, s); else launch_one<false, false, 16>(a, grid, s); }
-    else { if (giao) launch_one<true, false, 8>(a, grid, s); else launch_one<false, false, 8>(a, grid, s); }
+    if (giao) launch_one<true, false, 8>(a, grid, s); else launch_one<false, false, 8>(a, grid, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -521,14 +521,13 @@ __device__ __forceinline__ void shell_to_panel(double rx, double ry, double rz, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_basis<NT>: NT threads = NT points; MT / NT CTAs per tile (NT = 128: one CTA per tile; NT = 32: four single-warp CTAs per tile,
-// small enough -- 96 registers x 32 threads, ~5 KB of shared memory -- to run NEXT TO the persistent contraction kernel on the same
-// SM, so that the panels of batch b+1 are written while batch b is contracted).
+// k_basis<NT>: NT threads = NT points, MT / NT CTAs per tile (NT = 128: one CTA per tile, the only instantiation.  A single-warp variant
+// that ran beside the contraction kernel on a second stream was measured 5 % SLOWER end to end and removed: profiles/r02_ab_ncw_overlap.json).
 //  phase A: ordered compaction of the active atoms into (atom, nshell, slot0) runs + the slot->function index list (written by part 0)
 //  phase B: every thread evaluates its point for all active shells and writes the 4 planes
 //           P0 = Phi, P1..3 = dPhi/dx,dy,dz at panel[(plane*nact + slot)*LDP + row]  (row-contiguous => coalesced)
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 20) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
+__global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__restrict__ tiles, const TileGeo *__restrict__ geo,
                                                const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                const double *__restrict__ rsz, double *__restrict__ panel_pool,
                                                int *__restrict__ fidx_pool, TileAtom *__restrict__ atab_pool) {
@@ -723,16 +722,9 @@ void launch_panel_scatter(const TileDesc *tiles, int ntiles, const double *panel
 }
 
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
-                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s, bool small_ctas) {
+                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s) {
     if (ntiles <= 0) return;
     size_t smem = ((size_t)B.natoms + (size_t)4 * (max_nruns > 0 ? max_nruns : 1)) * sizeof(int);
-    if (small_ctas) {      // single-warp CTAs that fit beside the contraction kernel (overlapped batches); the smem must stay small for that
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        // same shared-memory carve-out as the contraction kernel it is meant to run beside (an SM cannot hold CTAs of two configurations)
-        cudaFuncSetAttribute(k_basis<32>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        k_basis<32><<<ntiles * (MT / 32), 32, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
-        return;
-    }
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
     k_basis<128><<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
 }

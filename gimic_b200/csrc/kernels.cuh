@@ -103,7 +103,7 @@ void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, void *sorttmp, si
 size_t plan_sort_temp_bytes(int nt);
 void launch_perm_index(const int *perm, long n, long *index, cudaStream_t s);
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
-                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s, bool small_ctas = false);
+                  const double *rsz, double *panel_pool, int *fidx_pool, TileAtom *atab_pool, cudaStream_t s);
 void launch_panel_scatter(const TileDesc *tiles, int ntiles, const double *panel_pool, const int *fidx_pool, const int *perm, const int *f2user,
                           int nbf, double *bf, double *dr, cudaStream_t s);
 void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s);
