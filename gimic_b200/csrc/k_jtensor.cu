@@ -676,28 +676,34 @@ __device__ __forceinline__ void consumer_role_j(const JtensorArgs &a, const doub
 constexpr int NEPI_WARPS = 4;
 constexpr int NTHREADS_E = (NCONSUMER_WARPS + NPRODUCER_WARPS + NEPI_WARPS) * 32;
 constexpr int CONSUMER_REGS_E = 200, PRODUCER_REGS_E = 40, EPI_REGS_E = 72;
-constexpr int XLD = 4 * MT + 4;        // doubles per column of the exchange buffer: [4 values][128 rows] + 4 pad (the 4 column pairs of a quad land 64 B apart)
 constexpr int CRING = 6;               // column tables in flight.  The table of chunk c is written with the chunk's first stage and read until the
                                        // epilogue warps finish chunk c, i.e. before the consumers start the K loop of chunk c+2; the producers run at most
                                        // STAGES stages ahead, so slot (c + CRING) % CRING is rewritten no earlier than stage (c+CRING)*nkc - STAGES >= (c+2)*nkc
-constexpr int ATAB_MAX_E = 128;        // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
+constexpr int ATAB_MAX_E = 112;        // active atoms of a tile staged in shared memory (more: the taps read the table from global memory)
 
-struct SmemE {
-    static constexpr int NPP = (NQ + 1) / 2, NVC = NV, LDB = LDB2;
+template <int NPP_, int NV_, int LDB_, int NXV_>
+struct SmemET {
+    static constexpr int NPP = NPP_, NVC = NV_, LDB = LDB_;
+    static constexpr int NXV = NXV_;                         // values per (point, column) in the exchange buffer: 4 (x0, z_x, z_y, z_z) or 2 (x0, z)
+    static constexpr int XLD = NXV * MT + 4;                 // doubles per column: [NXV][128 rows] + 4 pad (the 4 column pairs of a quad land 64 B apart)
     static constexpr int A_DOUBLES = BK * LDP, PP_DOUBLES = BK * LDB, B_DOUBLES = NPP * PP_DOUBLES, STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
-    static constexpr size_t X_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;                 // exchange buffer [NV][XLD]
-    static constexpr size_t COLR_OFF = X_OFF + (size_t)NV * XLD * 8;                    // [CRING][NV][4]: R_x, R_y, R_z of the column's centre
-    static constexpr size_t COLSLOT_OFF = COLR_OFF + (size_t)CRING * NV * 4 * 8;        // [CRING][NV]: panel row (K slot) of the column
-    static constexpr size_t ATAB_OFF = COLSLOT_OFF + (size_t)CRING * NV * 4;
+    static constexpr size_t X_OFF = (size_t)STAGES * STAGE_DOUBLES * 8;                 // exchange buffer [NVC][XLD]
+    static constexpr size_t COLR_OFF = X_OFF + (size_t)NVC * XLD * 8;                   // [CRING][NVC][4]: R_x, R_y, R_z of the column's centre
+    static constexpr size_t COLSLOT_OFF = COLR_OFF + (size_t)CRING * NVC * 4 * 8;       // [CRING][NVC]: panel row (K slot) of the column
+    static constexpr size_t ATAB_OFF = COLSLOT_OFF + (size_t)CRING * NVC * 4;
     static constexpr size_t KMASK_OFF = ATAB_OFF + (size_t)ATAB_MAX_E * 3 * 8;
     static constexpr size_t BAR_OFF = KMASK_OFF + (size_t)KMASK_WORDS * 4;              // full[STAGES], empty[STAGES], xfull, xempty
     static constexpr size_t BYTES = BAR_OFF + (2 * STAGES + 2) * 8 + 16;
 };
-static_assert(SmemE::BYTES <= 232448, "k_jtensor_e: shared memory over the 227 KB of a CTA");
+using SmemE = SmemET<(NQ + 1) / 2, NV, LDB2, 4>;     // tensor path: 16 columns x 4 values
+using SmemEJ = SmemET<1, NVJ, LDB2J, 2>;             // J path: 32 columns x 2 values (the same 64.5 KB)
+static_assert(SmemE::BYTES <= 232448 && SmemEJ::BYTES <= 232448, "k_jtensor_e: shared memory over the 227 KB of a CTA");
 
+template <class SM>
 __device__ __forceinline__ void producer_role_e(const JtensorArgs &a, uint32_t s_base, uint32_t bar_full, uint32_t bar_empty, double *s_colR,
                                                 int *s_colSlot, int *s_tile) {
-    using SM = SmemE;
+    constexpr int NV = SM::NVC;                                    // columns per chunk (shadows the tensor path's constant)
+    constexpr int LPW = 32 / NV > 0 ? 32 / NV : 1;                // k rows covered by one warp per pass (2 for 16 columns, 1 for 32)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t git = 0, gch = 0;           // stages / nu chunks issued so far (all tiles)
     for (;;) {
@@ -711,7 +717,7 @@ __device__ __forceinline__ void producer_role_e(const JtensorArgs &a, uint32_t s
         const double *panel = a.panel_pool + td.panel_off;
         const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
         const int pw = warp - NCONSUMER_WARPS;
-        const int ldn = lane % NV, ldk0 = lane / NV + 2 * pw;    // this lane gathers nu slot ldn, k rows ldk0, ldk0 + 8, ...
+        const int ldn = lane % NV, ldk0 = lane / NV + LPW * pw;  // this lane gathers nu slot ldn, k rows ldk0, ldk0 + LPW*4, ...
         int kc = 0, vc = 0;
         int slot = nlist[min(ldn, nn - 1)];
         long nu = fidx[slot];
@@ -731,7 +737,7 @@ __device__ __forceinline__ void producer_role_e(const JtensorArgs &a, uint32_t s
             const double *srcB = a.Bop + 2 * nu;
             const uint32_t dstB = sB + (uint32_t)(ldn * 16);
 #pragma unroll 4
-            for (int k = ldk0; k < (nu_ok ? kcnt : 0); k += 2 * NPRODUCER_WARPS) {
+            for (int k = ldk0; k < (nu_ok ? kcnt : 0); k += LPW * NPRODUCER_WARPS) {
                 const long mu = fidx[kc * BK + k];
                 const double *src = srcB + 2 * mu * a.ldb;
                 const uint32_t dst = dstB + (uint32_t)(k * SM::LDB * 8);
@@ -876,7 +882,7 @@ __device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const doub
                         const int col = h * 8 + 2 * t + j;
                         double dRx = 0, dRy = 0, dRz = 0;
                         if (GIAO) { const double2 r01 = *reinterpret_cast<const double2 *>(colR + 4 * col); dRx = r01.x - cenx; dRy = r01.y - ceny; dRz = colR[4 * col + 2] - cenz; }
-                        double *xc = s_x + (size_t)col * XLD;
+                        double *xc = s_x + (size_t)col * SM::XLD;
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
                             const int ci = 2 * rr + j, row = rr ? rowB : rowA;
@@ -943,7 +949,7 @@ __device__ __forceinline__ void epilogue_role_e(const JtensorArgs &a, const doub
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const double *xc = s_x + (size_t)(c0 + k) * XLD + row;
+                    const double *xc = s_x + (size_t)(c0 + k) * SmemE::XLD + row;
                     const double x0 = xc[0], zx = xc[MT], zy = xc[2 * MT], zz = xc[3 * MT];
                     const double t0 = x0 * ev[k][0];
                     e[12] += t0;
@@ -994,9 +1000,234 @@ __device__ __forceinline__ void epilogue_role_e(const JtensorArgs &a, const doub
     }
 }
 
+// ---- J = T.B path with the epilogue warpgroup: operands (D, P.B), 32-column chunks, ONE tap weight per row, 2 values per (point, column) ----
 template <bool GIAO>
+__device__ __forceinline__ void consumer_role_ej(const JtensorArgs &a, const double *s_stage, double *s_x, const double *s_colR, double *s_atab,
+                                                 uint32_t *s_kmask, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_xfull, uint32_t bar_xempty,
+                                                 int *s_tile) {
+    using SM = SmemEJ;
+    int lane = threadIdx.x & 31, row0 = (threadIdx.x >> 5) * 16;
+    keep_in_register(lane); keep_in_register(row0);
+    keep_in_register(bar_full); keep_in_register(bar_empty); keep_in_register(bar_xfull); keep_in_register(bar_xempty);
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NH = NVJ / 8;                                 // n8 tiles per chunk
+    uint32_t git = 0, gch = 0;
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        if (td.nact == 0) continue;                                   // the epilogue warps write the zeros
+        const int rowA = row0 + g, rowB = row0 + g + 8;
+        const int nact = td.nact, nn = td.nn;
+        const int nkc = (nact + BK - 1) / BK, nvc = (nn + NVJ - 1) / NVJ;
+        const uint32_t NIT = (uint32_t)nkc * nvc;
+        // w = B x r of this thread's two rows: B.(r x Y) = Y.(B x r); tile centre (Y relative to the centre like the tap weights)
+        double wAx = 0, wAy = 0, wAz = 0, wBx = 0, wBy = 0, wBz = 0, cenx = 0, ceny = 0, cenz = 0;
+        if (GIAO) {
+            const long pA = td.pt0 + (rowA < td.npts ? rowA : 0), pB = td.pt0 + (rowB < td.npts ? rowB : 0);
+            const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+            const double ax = a.rsx[pA], ay = a.rsy[pA], az = a.rsz[pA], cx = a.rsx[pB], cy = a.rsy[pB], cz = a.rsz[pB];
+            wAx = by * az - bz * ay; wAy = bz * ax - bx * az; wAz = bx * ay - by * ax;
+            wBx = by * cz - bz * cy; wBy = bz * cx - bx * cz; wBz = bx * cy - by * cx;
+            const TileGeo tg = a.geo[td.geo];                          // same expression as k_basis
+            cenx = 0.5 * (tg.lox + tg.hix); ceny = 0.5 * (tg.loy + tg.hiy); cenz = 0.5 * (tg.loz + tg.hiz);
+        }
+        double acc[2][NH][4];                                       // planes D and P.B
+        double zac[NH][4];                                          // S = (B x r) . Z (GIAO taps with per-row weights)
+        const int nruns = td.nruns;
+        const bool tab_sm = nruns <= ATAB_MAX_E;
+        const double *gtab = reinterpret_cast<const double *>(a.atab_pool + td.atab_off);
+        double curx = 0, cury = 0, curz = 0;
+        int ia = 0;
+        if (GIAO) {
+            // stage the tile's atom table: weights to shared memory, atom ends as one bit per K step
+            const double2 *atab = reinterpret_cast<const double2 *>(a.atab_pool + td.atab_off);   // TileAtom = 2 x double2
+            const int ctid = threadIdx.x, nwords = (nact / 4 + 31) / 32;
+            for (int w = ctid; w < nwords; w += NCONSUMER_WARPS * 32) s_kmask[w] = 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+            for (int r = ctid; r < nruns; r += NCONSUMER_WARPS * 32) {
+                const double2 t0 = __ldg(atab + 2 * r), t1 = __ldg(atab + 2 * r + 1);
+                if (r < ATAB_MAX_E) { s_atab[3 * r] = t0.x; s_atab[3 * r + 1] = t0.y; s_atab[3 * r + 2] = t1.x; }
+                const int e = __double2loint(t1.y) - 1;
+                atomicOr(&s_kmask[e >> 5], 1u << (e & 31));
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+        }
+        int kc = 0, vc = 0;
+        for (uint32_t it = 0; it < NIT; ++it) {
+            const uint32_t gi = git + it, s = gi % STAGES, ph = (gi / STAGES) & 1;
+            if (kc == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[q][h][i] = 0.0;
+                if (GIAO) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) zac[h][i] = 0.0;
+                    ia = 0;
+                    load_tap_weights(tab_sm, s_atab, gtab, 0, curx, cury, curz);
+                }
+            }
+            const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
+            const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
+            const int nks = min(BK, nact - kc * BK) / 4;
+            const int nh = min(NH, (nn - vc * NVJ) / 8);            // n8 tiles of this chunk that hold real columns (nn is a multiple of 8)
+            const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
+            const double *sB = sA + SM::A_DOUBLES;
+            mbar_wait(bar_full + 8 * s, ph);
+            // fragments (m16n8k4.f64), software-pipelined by hand: the fragments of step ks+1 are loaded before the MMAs of step ks
+            const double *pa0 = sA + t * LDP + row0 + g;
+            const double2 *pb0 = reinterpret_cast<const double2 *>(sB + t * LDB2J) + g;
+            double a0 = pa0[0], a1 = pa0[8];
+            double2 bf[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) bf[h] = pb0[h * 8];
+#pragma unroll KSU
+            for (int ks = 0; ks < nks; ++ks) {
+                double na0 = 0, na1 = 0;
+                double2 nb[NH];
+                if (ks + 1 < nks) {
+                    const double *pa = pa0 + (ks + 1) * 4 * LDP;
+                    na0 = pa[0]; na1 = pa[8];
+                    const double2 *pb = pb0 + (ks + 1) * 4 * (LDB2J / 2);
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) nb[h] = pb[h * 8];
+                }
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    if (h >= nh) continue;
+                    mma_16x8x4_f64(acc[0][h], a0, a1, bf[h].x);
+                    mma_16x8x4_f64(acc[1][h], a0, a1, bf[h].y);
+                }
+                a0 = na0; a1 = na1;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) bf[h] = nb[h];
+                if (GIAO && ((m8 >> ks) & 1u)) {
+                    // last K step of an atom: S += C_A * ((B x r) . (R_A - R_next)), one weight per row (see the header)
+                    const double oA = wAx * curx + wAy * cury + wAz * curz, oB = wBx * curx + wBy * cury + wBz * curz;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        zac[h][0] = fma(oA, acc[0][h][0], zac[h][0]); zac[h][1] = fma(oA, acc[0][h][1], zac[h][1]);
+                        zac[h][2] = fma(oB, acc[0][h][2], zac[h][2]); zac[h][3] = fma(oB, acc[0][h][3], zac[h][3]);
+                    }
+                    ia = min(ia + 1, nruns - 1);
+                    load_tap_weights(tab_sm, s_atab, gtab, ia, curx, cury, curz);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // slot may be refilled
+            if (++kc == nkc) {
+                // ---- hand nu chunk vc to the epilogue warps: (x0, z) per (row, column), z = X_1 + (B x r) . Y ----------------------
+                const uint32_t c = gch + vc;
+                mbar_wait(bar_xempty, (c & 1) ^ 1);                  // the epilogue warps are done with the previous chunk
+                const double *colR = s_colR + (size_t)(c % CRING) * NVJ * 4;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    if (h >= nh) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int col = h * 8 + 2 * t + j;
+                        double dRx = 0, dRy = 0, dRz = 0;
+                        if (GIAO) { const double2 r01 = *reinterpret_cast<const double2 *>(colR + 4 * col); dRx = r01.x - cenx; dRy = r01.y - ceny; dRz = colR[4 * col + 2] - cenz; }
+                        double *xc = s_x + (size_t)col * SM::XLD;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int ci = 2 * rr + j, row = rr ? rowB : rowA;
+                            const double x0 = acc[0][h][ci];
+                            double z = acc[1][h][ci];
+                            if (GIAO) {
+                                const double wx = rr ? wBx : wAx, wy = rr ? wBy : wAy, wz = rr ? wBz : wAz;
+                                z += (wx * dRx + wy * dRy + wz * dRz) * x0 - zac[h][ci];   // (B x r) . Y
+                            }
+                            xc[row] = x0; xc[MT + row] = z;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_xfull);
+                kc = 0; ++vc;
+            }
+        }
+        git += NIT; gch += nvc;
+    }
+}
+
+template <bool GIAO>
+__device__ __forceinline__ void epilogue_role_ej(const JtensorArgs &a, const double *s_x, const double *s_colR, const int *s_colSlot,
+                                                 uint32_t bar_xfull, uint32_t bar_xempty, int *s_tile) {
+    const int lane = threadIdx.x & 31;
+    const int row = threadIdx.x - (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
+    uint32_t gch = 0;
+    for (;;) {
+        const int tile = next_tile(a, s_tile);
+        if (tile >= a.ntiles) break;
+        const TileDesc td = a.tiles[tile];
+        const bool valid = row < td.npts;
+        if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
+            if (valid) store_zero(a, out_row(a, td.pt0 + row));
+            continue;
+        }
+        const int nact = td.nact, nn = td.nn;
+        const int nvc = (nn + NVJ - 1) / NVJ;
+        const double *panel = a.panel_pool + td.panel_off + row;       // rows >= npts hold zeros (k_basis writes all MT rows)
+        const long plane = (long)nact * LDP;
+        const long p = td.pt0 + (valid ? row : 0);
+        const double px = a.rsx[p], py = a.rsy[p], pz = a.rsz[p];
+        double e[7];                                                    // T_m = sum_b Tp(m,b) B_b at [m], V_d at [3+d], rho at [6]
+#pragma unroll
+        for (int i = 0; i < 7; ++i) e[i] = 0.0;
+        for (int vc = 0; vc < nvc; ++vc) {
+            const uint32_t c = gch + vc;
+            const int ncol = min(NVJ, nn - vc * NVJ);
+            const int *cslot = s_colSlot + (size_t)(c % CRING) * NVJ;
+            const double *colR = s_colR + (size_t)(c % CRING) * NVJ * 4;
+            mbar_wait(bar_xfull, c & 1);
+            for (int c0 = 0; c0 < ncol; c0 += 4) {                     // ncol is a multiple of 8: four columns' panel rows in flight at a time
+                double ev[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double *pe = panel + (long)cslot[c0 + k] * LDP;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ev[k][q] = pe[q * plane];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double *xc = s_x + (size_t)(c0 + k) * SmemEJ::XLD + row;
+                    const double x0 = xc[0], z = xc[MT];
+                    const double t0 = x0 * ev[k][0];
+                    e[6] += t0;
+                    if (GIAO) { const double *cr = colR + 4 * (c0 + k); e[3] += cr[0] * t0; e[4] += cr[1] * t0; e[5] += cr[2] * t0; }
+                    e[0] += z * ev[k][1]; e[1] += z * ev[k][2]; e[2] += z * ev[k][3];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xempty);
+        }
+        gch += nvc;
+        if (valid) {
+            const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+            // J_m = sum_b ct(m,b) B_b:  1/2 [T_m + (V x B)_m]  +  1/2 rho (B x r)_m   (jtensor.F90:209-235 contracted with B)
+            double jx = e[0] + (e[4] * bz - e[5] * by), jy = e[1] + (e[5] * bx - e[3] * bz), jz = e[2] + (e[3] * by - e[4] * bx);
+            jx = a.paramag ? 0.5 * jx : 0.0; jy = a.paramag ? 0.5 * jy : 0.0; jz = a.paramag ? 0.5 * jz : 0.0;
+            const double rho = e[6];
+            if (a.diamag) {
+                jx += 0.5 * rho * (by * pz - bz * py); jy += 0.5 * rho * (bz * px - bx * pz); jz += 0.5 * rho * (bx * py - by * px);
+            }
+            const long o = out_row(a, td.pt0 + row);
+            if (a.jvec) { a.jvec[3 * o] = jx; a.jvec[3 * o + 1] = jy; a.jvec[3 * o + 2] = jz; }
+            if (a.jmod) a.jmod[o] = signed_modulus(jx, jy, jz, px, py, pz, bx, by, bz);
+            if (a.edens) a.edens[o] = rho;
+        }
+    }
+}
+
+template <bool GIAO, bool JVEC>
 __global__ void __launch_bounds__(NTHREADS_E, 1) k_jtensor_e(JtensorArgs a) {
-    using SM = SmemE;
+    using SM = typename std::conditional<JVEC, SmemEJ, SmemE>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_stage = reinterpret_cast<double *>(smem_raw);
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -1014,22 +1245,25 @@ __global__ void __launch_bounds__(NTHREADS_E, 1) k_jtensor_e(JtensorArgs a) {
     const int warp = threadIdx.x >> 5;
     if (warp >= NCONSUMER_WARPS + NPRODUCER_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EPI_REGS_E));
-        epilogue_role_e<GIAO>(a, s_x, s_colR, s_colSlot, bar_xfull, bar_xempty, s_tile);
+        if (JVEC) epilogue_role_ej<GIAO>(a, s_x, s_colR, s_colSlot, bar_xfull, bar_xempty, s_tile);
+        else epilogue_role_e<GIAO>(a, s_x, s_colR, s_colSlot, bar_xfull, bar_xempty, s_tile);
     } else if (warp >= NCONSUMER_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS_E));
-        producer_role_e(a, s_base, bar_full, bar_empty, s_colR, s_colSlot, s_tile);
+        producer_role_e<SM>(a, s_base, bar_full, bar_empty, s_colR, s_colSlot, s_tile);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS_E));
         double *atab = reinterpret_cast<double *>(smem_raw + SM::ATAB_OFF);
         uint32_t *kmask = reinterpret_cast<uint32_t *>(smem_raw + SM::KMASK_OFF);
-        consumer_role_e<GIAO>(a, s_stage, s_x, s_colR, atab, kmask, bar_full, bar_empty, bar_xfull, bar_xempty, s_tile);
+        if (JVEC) consumer_role_ej<GIAO>(a, s_stage, s_x, s_colR, atab, kmask, bar_full, bar_empty, bar_xfull, bar_xempty, s_tile);
+        else consumer_role_e<GIAO>(a, s_stage, s_x, s_colR, atab, kmask, bar_full, bar_empty, bar_xfull, bar_xempty, s_tile);
     }
 }
 
-template <bool GIAO>
+template <bool GIAO, bool JVEC>
 static void launch_one_e(const JtensorArgs &a, int grid, cudaStream_t s) {
-    cudaFuncSetAttribute(k_jtensor_e<GIAO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemE::BYTES);
-    k_jtensor_e<GIAO><<<grid, NTHREADS_E, SmemE::BYTES, s>>>(a);
+    constexpr size_t bytes = JVEC ? SmemEJ::BYTES : SmemE::BYTES;
+    cudaFuncSetAttribute(k_jtensor_e<GIAO, JVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_jtensor_e<GIAO, JVEC><<<grid, NTHREADS_E, bytes, s>>>(a);
 }
 
 // Pipeline: warps 8-11 are producers.  Per stage they (1) wait for the slot to be released by the 8 consumer warps
@@ -1064,7 +1298,7 @@ __global__ void __launch_bounds__((NCW + NPRODUCER_WARPS) * 32, 1) k_jtensor(Jte
     }
 }
 
-size_t jtensor_smem_bytes() { return SmemE::BYTES; }
+size_t jtensor_smem_bytes() { return SmemEJ::BYTES > SmemE::BYTES ? SmemEJ::BYTES : SmemE::BYTES; }
 
 template <bool GIAO, bool JVEC, int NCW>
 static void launch_one(const JtensorArgs &a, int grid, cudaStream_t s) {
@@ -1084,8 +1318,12 @@ void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;
     const int grid = a.ntiles < nsm ? a.ntiles : nsm;
     const bool jv = a.jpath != 0;        // J = T.B path: operands are ONE pair-plane (D, sum_b B_b P_b)
+    if (tensor_path_epilogue_role()) {
+        if (jv) { if (giao) launch_one_e<true, true>(a, grid, s); else launch_one_e<false, true>(a, grid, s); }
+        else { if (giao) launch_one_e<true, false>(a, grid, s); else launch_one_e<false, false>(a, grid, s); }
+        return;
+    }
     if (jv) { if (giao) launch_one<true, true, 8>(a, grid, s); else launch_one<false, true, 8>(a, grid, s); return; }
-    if (tensor_path_epilogue_role()) { if (giao) launch_one_e<true>(a, grid, s); else launch_one_e<false>(a, grid, s); return; }
     if (giao) launch_one<true, false, 8>(a, grid, s); else launch_one<false, false, 8>(a, grid, s);
 }
 

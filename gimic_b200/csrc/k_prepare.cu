@@ -358,9 +358,12 @@ __global__ void k_tile_emit(const TileSeg *__restrict__ slot_seg, const TileGeo 
         td.panel_off = 0; td.fidx_off = 0; td.atab_off = 0;
         desc[t] = td;
         TileCum tc;
-        // scheduling cost ~ MMA k-steps x columns (4 planes) + GIAO taps + a constant per tile (staging, epilogue tail); integers,
-        // so every rank computes the same prefix sums and hence the same partition
-        tc.cost = 4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + (td.nact ? 4096 : 64);
+        // scheduling cost in units of one DMMA column step: MMA k-steps x columns (4 planes) + GIAO taps + the tile's share of k_basis
+        // (4 planes x 132 doubles written per K slot at ~4.8 TB/s against 32 TF for the contraction: ~110 units per slot) + a constant
+        // per tile (descriptor, prologue, stores).  The last two were fitted on the 8-GPU run of the 256^3 grid, where ranks holding
+        // many cheap tiles far from the molecule ran 4 % longer than ranks of equal flops (profiles/r02_bench_n8_grid_h.json).
+        // Integers, so every rank computes the same prefix sums and hence the same partition.
+        tc.cost = 4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + 110LL * td.nact + (td.nact ? 8192 : 256);
         tc.panel = 4LL * td.nact * LDP; tc.fidx = td.nact + td.nn; tc.atab = td.nruns;
         cum[t] = tc;
     }

@@ -136,7 +136,7 @@ void emulate_tile_emit(void **a) {
             td.pt0 = seg[run * gb::MAXSUB + j].pt0; td.npts = seg[run * gb::MAXSUB + j].npts; td.nraw = ti.nraw; td.nact = (ti.nraw + 7) / 8 * 8;
             td.nreal = ti.nreal; td.nn = (ti.nreal + 7) / 8 * 8; td.geo = t; td.nruns = ti.natom;
             desc[t] = td;
-            cum[t] = gb::TileCum{4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + (td.nact ? 4096 : 64), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
+            cum[t] = gb::TileCum{4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + 110LL * td.nact + (td.nact ? 8192 : 256), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
         }
 }
 void emulate_scan_partial_c(void **a) {
