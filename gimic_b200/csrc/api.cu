@@ -75,6 +75,7 @@ struct gimic_b200_ctx {
     // workspaces
     Buf keys0, keys1, vals0, vals1, sorttmp, rs, panel, fidx, atab, misc, r_in, r_in2, tens_tmp, tens_tmp2, f_tmp, f_tmp2, shift, jv6, gridbuf, quad;
     Buf p_seg, p_geo, p_info, p_cnt, p_off, geo, desc, cum, pkeys0, pkeys1, pord0, pord1, tiles, d_summary, p_tops;   // tile plan (k_prepare.cu)
+    Buf items, part;                   // work items / partial row sums of sliced tiles (few tiles: see launch_tile_slices)
     gb::PlanSummary *h_summary = nullptr;   // pinned
     Plan plan;
     double split_radius = 2.5;   // bohr: tiles wider than this are cut at their largest consecutive gap if that shrinks them
@@ -96,7 +97,7 @@ struct gimic_b200_ctx {
         for (int i = 0; i < 4; ++i) if (d_opj[i]) cudaFree(d_opj[i]);
         for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &panel, &fidx, &atab, &misc, &r_in, &r_in2, &tens_tmp, &tens_tmp2, &f_tmp, &f_tmp2,
                        &shift, &jv6, &gridbuf, &quad, &p_seg, &p_geo, &p_info, &p_cnt, &p_off, &geo, &desc, &cum, &pkeys0, &pkeys1, &pord0, &pord1,
-                       &tiles, &d_summary, &p_tops}) b->release();
+                       &tiles, &d_summary, &p_tops, &items, &part}) b->release();
         if (h_summary) cudaFreeHost(h_summary);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : evpool) cudaEventDestroy(e);
@@ -161,6 +162,13 @@ int build_device_basis(gimic_b200_ctx *c) {
     if (int rc = upload(c, sh_po, &d.sh_prim_off)) return rc;
     if (int rc = upload(c, sh_foff, &d.sh_foff)) return rc;
     if (int rc = upload(c, sh_thr, &d.sh_thr)) return rc;
+    {
+        std::vector<double> t2(ns), m2(hb.natoms);
+        for (int i = 0; i < ns; ++i) t2[i] = (sh_thr[i] + 1e-9) * (sh_thr[i] + 1e-9);
+        for (int a = 0; a < hb.natoms; ++a) m2[a] = (maxthr[a] + 1e-9) * (maxthr[a] + 1e-9);
+        if (int rc = upload(c, t2, &d.sh_thr2e)) return rc;
+        if (int rc = upload(c, m2, &d.atom_maxthr2e)) return rc;
+    }
     if (int rc = upload(c, hb.alpha, &d.alpha)) return rc;
     if (int rc = upload(c, hb.ncc, &d.ncc)) return rc;
     if (int rc = upload(c, fR, &d.fR)) return rc;
@@ -436,8 +444,16 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
                      giao ? c->atab.as<TileAtom>() : nullptr, st);
         if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
+        // Few tiles in the batch (a plane of an integral, a handful of points): cut every tile into nsl column slices so that the work
+        // items fill the SMs; the slices' row sums are added by k_slice_reduce.  nsl depends only on the tile count and the device.
+        int nsl = 1;
+        if (nb * 2 <= c->nsm && jtensor_supports_slices()) nsl = std::min(16, c->nsm / nb);
+        if (nsl > 1 && (c->items.ensure((size_t)nb * nsl * sizeof(TileDesc)) || c->part.ensure((size_t)nb * nsl * MT * PART_LD * 8)))
+            return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tile slices)");
+        if (nsl > 1) { launch_tile_slices(c->tiles.as<TileDesc>() + t0, nb, nsl, c->items.as<TileDesc>(), st); c->stats.launches += 2; }
         JtensorArgs a;
-        a.tiles = c->tiles.as<TileDesc>() + t0; a.ntiles = nb; a.counter = c->misc.as<int>();
+        a.tiles = nsl > 1 ? c->items.as<TileDesc>() : c->tiles.as<TileDesc>() + t0; a.ntiles = nb * nsl; a.counter = c->misc.as<int>();
+        a.part = nsl > 1 ? c->part.as<double>() : nullptr;
         a.panel_pool = c->panel.as<double>(); a.fidx_pool = c->fidx.as<int>(); a.atab_pool = c->atab.as<TileAtom>(); a.geo = c->geo.as<TileGeo>();
         a.Bop = op; a.plane_stride = c->plane_stride; a.ldb = c->ldb; a.fR = c->db.fR; a.nbf = c->hb.nbf;
         a.rsx = rsx; a.rsy = rsy; a.rsz = rsz; a.perm = compact ? nullptr : c->vals1.as<int>(); a.out_base = compact ? S.pt_lo : 0;
@@ -445,6 +461,7 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
         for (int k = 0; k < 3; ++k) a.B[k] = o.B3 ? o.B3[k] : 0.0;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
         launch_jtensor(a, giao, c->nsm, st);
+        if (nsl > 1) launch_slice_reduce(a, c->tiles.as<TileDesc>() + t0, nb, nsl, giao, st);
         CUDA_TRY(cudaGetLastError());
         c->stats.launches += 2;
         c->stats.contract_launches += 1;

@@ -140,6 +140,56 @@ __device__ __forceinline__ double acid_of(const double (&t)[9]) {
     return 0.3333333 * (xxmyy + yymzz + zzmxx) + 0.5 * (xypyx + xzpzx + yzpzy);
 }
 
+// From the 13 row sums of a point (Tp(m,b) at [m+3b], V_d at [9+d], rho at [12]) to the tensor and the fields derived from it
+// (jtensor.F90:209-235; jfield.f90:167-184, 446-489; acid.f90).  Shared by the contraction's epilogue and k_slice_reduce.
+template <bool GIAO>
+__device__ __forceinline__ void finalise_store_tensor(const JtensorArgs &a, const double (&e)[13], double px, double py, double pz, long o) {
+    double ct[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ct[i] = e[i];
+    if (GIAO) {   // + sum_d eps(b,m,d) V_d  at ct[m + 3b]
+        ct[0 + 3 * 1] -= e[11]; ct[0 + 3 * 2] += e[10];
+        ct[1 + 3 * 0] += e[11]; ct[1 + 3 * 2] -= e[9];
+        ct[2 + 3 * 0] -= e[10]; ct[2 + 3 * 1] += e[9];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ct[i] = a.paramag ? 0.5 * ct[i] : 0.0;      // ZETA, jtensor.F90:209-223
+    const double rho = e[12];
+    const double d1 = a.diamag ? rho * (0.5 * px) : 0.0, d2 = a.diamag ? rho * (0.5 * py) : 0.0,
+                 d3 = a.diamag ? rho * (0.5 * pz) : 0.0;                     // dpd, jtensor.F90:187,225-228
+    ct[0 + 3 * 1] += d3; ct[0 + 3 * 2] -= d2;                                // jtensor.F90:230-235
+    ct[1 + 3 * 0] -= d3; ct[1 + 3 * 2] += d1;
+    ct[2 + 3 * 0] += d2; ct[2 + 3 * 1] -= d1;
+    if (a.tens) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = ct[i];
+    }
+    if (a.edens) a.edens[o] = rho;
+    // derived fields straight from the registers (what the separate k_fields pass computes from the stored tensor)
+    if (a.jvec || a.jmod) {
+        const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+        const double vx = ct[0] * bx + ct[3] * by + ct[6] * bz, vy = ct[1] * bx + ct[4] * by + ct[7] * bz,
+                     vz = ct[2] * bx + ct[5] * by + ct[8] * bz;                      // matmul(reshape(tens,(3,3)), b), jfield.f90:167-184
+        if (a.jvec) { a.jvec[3 * o] = vx; a.jvec[3 * o + 1] = vy; a.jvec[3 * o + 2] = vz; }
+        if (a.jmod) a.jmod[o] = signed_modulus(vx, vy, vz, px, py, pz, bx, by, bz);
+    }
+    if (a.acid) a.acid[o] = acid_of(ct);
+}
+// J path: T_m = sum_b Tp(m,b) B_b at [m], V_d at [3+d], rho at [6]
+__device__ __forceinline__ void finalise_store_j(const JtensorArgs &a, const double (&e)[13], double px, double py, double pz, long o) {
+    const double bx = a.B[0], by = a.B[1], bz = a.B[2];
+    // J_m = sum_b ct(m,b) B_b:  1/2 [T_m + (V x B)_m]  +  1/2 rho (B x r)_m   (jtensor.F90:209-235 contracted with B)
+    double jx = e[0] + (e[4] * bz - e[5] * by), jy = e[1] + (e[5] * bx - e[3] * bz), jz = e[2] + (e[3] * by - e[4] * bx);
+    jx = a.paramag ? 0.5 * jx : 0.0; jy = a.paramag ? 0.5 * jy : 0.0; jz = a.paramag ? 0.5 * jz : 0.0;
+    const double rho = e[6];
+    if (a.diamag) {
+        jx += 0.5 * rho * (by * pz - bz * py); jy += 0.5 * rho * (bz * px - bx * pz); jz += 0.5 * rho * (bx * py - by * px);
+    }
+    if (a.jvec) { a.jvec[3 * o] = jx; a.jvec[3 * o + 1] = jy; a.jvec[3 * o + 2] = jz; }
+    if (a.jmod) a.jmod[o] = signed_modulus(jx, jy, jz, px, py, pz, bx, by, bz);
+    if (a.edens) a.edens[o] = rho;
+}
+
 // Keep a loop-invariant value in a register: without this ptxas re-derives the lane id and every shared-memory address from the special
 // registers (S2R SR_TID.X, S2R/S2UR SR_CgaCtaId + LEA) at every pipeline stage -- three dependent ~40-cycle chains per stage that both
 // warps of a scheduler run at the same time (2.4 % of the consumer's samples in profiles/r02_ncu_jtensor_e_source_regions.txt).
@@ -710,12 +760,12 @@ __device__ __forceinline__ void producer_role_e(const JtensorArgs &a, uint32_t s
         const int tile = next_tile(a, s_tile);
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
-        if (td.nact == 0) continue;
-        const int nact = td.nact, nn = td.nn;
+        if (td.nact == 0 || td.col1 <= td.col0) continue;
+        const int nact = td.nact, nn = td.col1 - td.col0;                 // the columns of this work item (a whole tile or a slice of it)
         const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;   // nn is a multiple of 8: the last nu chunk may hold 8 columns
         const uint32_t NIT = (uint32_t)nkc * nvc;
         const double *panel = a.panel_pool + td.panel_off;
-        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact;
+        const int *fidx = a.fidx_pool + td.fidx_off, *nlist = fidx + nact + td.col0;
         const int pw = warp - NCONSUMER_WARPS;
         const int ldn = lane % NV, ldk0 = lane / NV + LPW * pw;  // this lane gathers nu slot ldn, k rows ldk0, ldk0 + LPW*4, ...
         int kc = 0, vc = 0;
@@ -775,9 +825,9 @@ __device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const doub
         const int tile = next_tile(a, s_tile);
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
-        if (td.nact == 0) continue;                                   // the epilogue warps write the zeros
+        if (td.nact == 0 || td.col1 <= td.col0) continue;            // the epilogue warps write the zeros; empty slices do nothing
         const int rowA = row0 + g, rowB = row0 + g + 8;
-        const int nact = td.nact, nn = td.nn;
+        const int nact = td.nact, nn = td.col1 - td.col0;
         const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;
         const uint32_t NIT = (uint32_t)nkc * nvc;
         // coordinates of this thread's two rows and the tile centre (GIAO: r x Y, and Y relative to the centre like the tap weights)
@@ -920,11 +970,12 @@ __device__ __forceinline__ void epilogue_role_e(const JtensorArgs &a, const doub
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
         const bool valid = row < td.npts;
+        if (td.col1 <= td.col0 && td.part >= 0) continue;            // empty slice
         if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
             if (valid) store_zero(a, out_row(a, td.pt0 + row));
             continue;
         }
-        const int nact = td.nact, nn = td.nn;
+        const int nact = td.nact, nn = td.col1 - td.col0;
         const int nvc = (nn + NV - 1) / NV;
         const double *panel = a.panel_pool + td.panel_off + row;       // rows >= npts hold zeros (k_basis writes all MT rows)
         const long plane = (long)nact * LDP;
@@ -963,39 +1014,13 @@ __device__ __forceinline__ void epilogue_role_e(const JtensorArgs &a, const doub
             if (lane == 0) mbar_arrive(bar_xempty);
         }
         gch += nvc;
-        // ---- finalise and store ---------------------------------------------------------------------
-        if (valid) {
-            double ct[9];
+        // ---- a slice hands its row sums to k_slice_reduce; a whole tile is finalised and stored here -------------------------------
+        if (td.part >= 0) {
+            double *pp = a.part + ((size_t)td.part * MT + row) * PART_LD;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) ct[i] = e[i];
-            if (GIAO) {   // + sum_d eps(b,m,d) V_d  at ct[m + 3b]
-                ct[0 + 3 * 1] -= e[11]; ct[0 + 3 * 2] += e[10];
-                ct[1 + 3 * 0] += e[11]; ct[1 + 3 * 2] -= e[9];
-                ct[2 + 3 * 0] -= e[10]; ct[2 + 3 * 1] += e[9];
-            }
-#pragma unroll
-            for (int i = 0; i < 9; ++i) ct[i] = a.paramag ? 0.5 * ct[i] : 0.0;      // ZETA, jtensor.F90:209-223
-            const double rho = e[12];
-            const double d1 = a.diamag ? rho * (0.5 * px) : 0.0, d2 = a.diamag ? rho * (0.5 * py) : 0.0,
-                         d3 = a.diamag ? rho * (0.5 * pz) : 0.0;                     // dpd, jtensor.F90:187,225-228
-            ct[0 + 3 * 1] += d3; ct[0 + 3 * 2] -= d2;                                // jtensor.F90:230-235
-            ct[1 + 3 * 0] -= d3; ct[1 + 3 * 2] += d1;
-            ct[2 + 3 * 0] += d2; ct[2 + 3 * 1] -= d1;
-            const long o = out_row(a, td.pt0 + row);
-            if (a.tens) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) a.tens[9 * o + i] = ct[i];
-            }
-            if (a.edens) a.edens[o] = rho;
-            // derived fields straight from the registers (what the separate k_fields pass computes from the stored tensor)
-            if (a.jvec || a.jmod) {
-                const double bx = a.B[0], by = a.B[1], bz = a.B[2];
-                const double vx = ct[0] * bx + ct[3] * by + ct[6] * bz, vy = ct[1] * bx + ct[4] * by + ct[7] * bz,
-                             vz = ct[2] * bx + ct[5] * by + ct[8] * bz;                      // matmul(reshape(tens,(3,3)), b), jfield.f90:167-184
-                if (a.jvec) { a.jvec[3 * o] = vx; a.jvec[3 * o + 1] = vy; a.jvec[3 * o + 2] = vz; }
-                if (a.jmod) a.jmod[o] = signed_modulus(vx, vy, vz, px, py, pz, bx, by, bz);
-            }
-            if (a.acid) a.acid[o] = acid_of(ct);
+            for (int i = 0; i < 13; ++i) pp[i] = e[i];
+        } else if (valid) {
+            finalise_store_tensor<GIAO>(a, e, px, py, pz, out_row(a, td.pt0 + row));
         }
     }
 }
@@ -1016,9 +1041,9 @@ __device__ __forceinline__ void consumer_role_ej(const JtensorArgs &a, const dou
         const int tile = next_tile(a, s_tile);
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
-        if (td.nact == 0) continue;                                   // the epilogue warps write the zeros
+        if (td.nact == 0 || td.col1 <= td.col0) continue;            // the epilogue warps write the zeros; empty slices do nothing
         const int rowA = row0 + g, rowB = row0 + g + 8;
-        const int nact = td.nact, nn = td.nn;
+        const int nact = td.nact, nn = td.col1 - td.col0;
         const int nkc = (nact + BK - 1) / BK, nvc = (nn + NVJ - 1) / NVJ;
         const uint32_t NIT = (uint32_t)nkc * nvc;
         // w = B x r of this thread's two rows: B.(r x Y) = Y.(B x r); tile centre (Y relative to the centre like the tap weights)
@@ -1167,19 +1192,20 @@ __device__ __forceinline__ void epilogue_role_ej(const JtensorArgs &a, const dou
         if (tile >= a.ntiles) break;
         const TileDesc td = a.tiles[tile];
         const bool valid = row < td.npts;
+        if (td.col1 <= td.col0 && td.part >= 0) continue;            // empty slice
         if (td.nact == 0) {   // nothing within screening range: the reference returns exact zeros
             if (valid) store_zero(a, out_row(a, td.pt0 + row));
             continue;
         }
-        const int nact = td.nact, nn = td.nn;
+        const int nact = td.nact, nn = td.col1 - td.col0;
         const int nvc = (nn + NVJ - 1) / NVJ;
         const double *panel = a.panel_pool + td.panel_off + row;       // rows >= npts hold zeros (k_basis writes all MT rows)
         const long plane = (long)nact * LDP;
         const long p = td.pt0 + (valid ? row : 0);
         const double px = a.rsx[p], py = a.rsy[p], pz = a.rsz[p];
-        double e[7];                                                    // T_m = sum_b Tp(m,b) B_b at [m], V_d at [3+d], rho at [6]
+        double e[13];                                                   // T_m = sum_b Tp(m,b) B_b at [m], V_d at [3+d], rho at [6] (7 used)
 #pragma unroll
-        for (int i = 0; i < 7; ++i) e[i] = 0.0;
+        for (int i = 0; i < 13; ++i) e[i] = 0.0;
         for (int vc = 0; vc < nvc; ++vc) {
             const uint32_t c = gch + vc;
             const int ncol = min(NVJ, nn - vc * NVJ);
@@ -1208,19 +1234,12 @@ __device__ __forceinline__ void epilogue_role_ej(const JtensorArgs &a, const dou
             if (lane == 0) mbar_arrive(bar_xempty);
         }
         gch += nvc;
-        if (valid) {
-            const double bx = a.B[0], by = a.B[1], bz = a.B[2];
-            // J_m = sum_b ct(m,b) B_b:  1/2 [T_m + (V x B)_m]  +  1/2 rho (B x r)_m   (jtensor.F90:209-235 contracted with B)
-            double jx = e[0] + (e[4] * bz - e[5] * by), jy = e[1] + (e[5] * bx - e[3] * bz), jz = e[2] + (e[3] * by - e[4] * bx);
-            jx = a.paramag ? 0.5 * jx : 0.0; jy = a.paramag ? 0.5 * jy : 0.0; jz = a.paramag ? 0.5 * jz : 0.0;
-            const double rho = e[6];
-            if (a.diamag) {
-                jx += 0.5 * rho * (by * pz - bz * py); jy += 0.5 * rho * (bz * px - bx * pz); jz += 0.5 * rho * (bx * py - by * px);
-            }
-            const long o = out_row(a, td.pt0 + row);
-            if (a.jvec) { a.jvec[3 * o] = jx; a.jvec[3 * o + 1] = jy; a.jvec[3 * o + 2] = jz; }
-            if (a.jmod) a.jmod[o] = signed_modulus(jx, jy, jz, px, py, pz, bx, by, bz);
-            if (a.edens) a.edens[o] = rho;
+        if (td.part >= 0) {
+            double *pp = a.part + ((size_t)td.part * MT + row) * PART_LD;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) pp[i] = e[i];
+        } else if (valid) {
+            finalise_store_j(a, e, px, py, pz, out_row(a, td.pt0 + row));
         }
     }
 }
@@ -1308,11 +1327,39 @@ static void launch_one(const JtensorArgs &a, int grid, cudaStream_t s) {
     k_jtensor<GIAO, JVEC, NCW><<<grid, (NCW + NPRODUCER_WARPS) * 32, bytes, s>>>(a);
 }
 
+// adds the row sums of a tile's slices in slice order (fixed => reproducible), finalises and stores.  One CTA (MT threads) per tile.
+template <bool GIAO>
+__global__ void __launch_bounds__(MT) k_slice_reduce(JtensorArgs a, const TileDesc *__restrict__ tiles, int S) {
+    const TileDesc td = tiles[blockIdx.x];
+    const int row = threadIdx.x;
+    if (td.nact == 0 || row >= td.npts) return;                       // empty tiles were zero-filled by their first item
+    const int w = ((td.nn + S - 1) / S + SLICE_COLS - 1) / SLICE_COLS * SLICE_COLS;
+    const int nsl = (td.nn + w - 1) / w;
+    const int ne = a.jpath ? 7 : 13;
+    double e[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) e[i] = 0.0;
+    for (int sl = 0; sl < nsl; ++sl) {
+        const double *pp = a.part + ((size_t)(blockIdx.x * S + sl) * MT + row) * PART_LD;
+        for (int i = 0; i < ne; ++i) e[i] += pp[i];
+    }
+    const long p = td.pt0 + row;
+    const double px = a.rsx[p], py = a.rsy[p], pz = a.rsz[p];
+    if (a.jpath) finalise_store_j(a, e, px, py, pz, out_row(a, p));
+    else finalise_store_tensor<GIAO>(a, e, px, py, pz, out_row(a, p));
+}
+void launch_slice_reduce(const JtensorArgs &a, const TileDesc *tiles, int nt, int S, bool giao, cudaStream_t s) {
+    if (nt <= 0) return;
+    if (giao) k_slice_reduce<true><<<nt, MT, 0, s>>>(a, tiles, S); else k_slice_reduce<false><<<nt, MT, 0, s>>>(a, tiles, S);
+}
+
 // GIMIC_B200_EPI=0 selects the round-1 mapping of the tensor path (epilogue inside the consumer warps) for A/B measurements
 static bool tensor_path_epilogue_role() {
     static const bool on = [] { const char *e = std::getenv("GIMIC_B200_EPI"); return e ? std::atoi(e) != 0 : DEFAULT_EPI != 0; }();
     return on;
 }
+
+bool jtensor_supports_slices() { return tensor_path_epilogue_role(); }
 
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s) {
     if (a.ntiles <= 0) return;

@@ -119,16 +119,19 @@ __device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, co
                                                  const double *sz, int np, Emit emit) {
     const int lane = threadIdx.x & 31;
     const int at = base + lane;
+    // All tile-level tests compare SQUARED distances with (radius + 1e-9)^2 (precomputed): a shell is kept if (thr + 1e-9)^2 >= d2, a
+    // superset of the per-point test sqrt(r2) <= thr of k_basis (the margin 2e-9 thr dwarfs the rounding of the squares).  The double
+    // sqrt these tests used to take was 35 % of k_tile_split's instructions (profiles/r02_ncu_tile_split.txt).
     double x = 0.0, y = 0.0, z = 0.0, mx = 0.0;
     int s0 = 0, s1 = 0, f0 = 0, f1 = 0;
     bool pass = false;
     if (at < B.natoms) {
         x = B.atom_xyz[3 * at]; y = B.atom_xyz[3 * at + 1]; z = B.atom_xyz[3 * at + 2];
-        mx = B.atom_maxthr[at];
+        mx = B.atom_maxthr2e[at];
         s0 = B.atom_shell_off[at]; s1 = B.atom_shell_off[at + 1]; f0 = B.atom_func_off[at]; f1 = B.atom_func_off[at + 1];
         const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
                      dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
-        pass = !(sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)))) - 1e-9 > mx);
+        pass = !(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx))) > mx);
     }
     unsigned bal = __ballot_sync(0xffffffffu, pass);
     while (bal) {
@@ -145,16 +148,15 @@ __device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, co
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-        const double lim = sqrt(d2) - 1e-9;
-        if (lim > amx) continue;
+        if (d2 > amx) continue;
         // shells are sorted by descending radius inside an atom: the active ones are a prefix
         int cnt = 0, fend = af0;                  // active shells, function index after the last active shell
         for (int sb = as0; sb < as1; sb += 32) {
             const int s = sb + lane;
             const bool in = s < as1;
-            const double thr = in ? B.sh_thr[s] : -1.0;
+            const double thr = in ? B.sh_thr2e[s] : -1.0;
             const int fnext = in ? (s + 1 < as1 ? B.sh_foff[s + 1] : af1) : af1;
-            const unsigned act = __ballot_sync(0xffffffffu, in && thr >= lim);
+            const unsigned act = __ballot_sync(0xffffffffu, in && thr >= d2);
             const int k = act == 0xffffffffu ? 32 : __ffs(~act) - 1;
             if (k > 0) { cnt += k; fend = __shfl_sync(0xffffffffu, fnext, k - 1); }
             if (k < 32) break;
@@ -212,15 +214,16 @@ __global__ void __launch_bounds__(128, 8) k_tile_split(DevBasis B, const double 
         tg.lox = v[0]; tg.loy = v[1]; tg.loz = v[2]; tg.hix = -v[3]; tg.hiy = -v[4]; tg.hiz = -v[5];
         const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
         // radius about the centre and the largest gap between consecutive points, packed as (float bits << 32 | index): one max-reduction
+        // (squared distances as floats: monotone, so the maxima are those of the distances; the two square roots are taken once, below)
         unsigned long long key = 0;
         if (in) {
-            const double d = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
+            const double d = (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz);
             key = (unsigned long long)__float_as_uint((float)d) << 32;     // non-negative floats order like their bit patterns
         }
         unsigned long long gap = 0;
         if (tid >= a && tid + 1 < b) {
             const double ex = sx[tid + 1] - x, ey = sy[tid + 1] - y, ez = sz[tid + 1] - z;
-            gap = ((unsigned long long)__float_as_uint((float)sqrt(ex * ex + ey * ey + ez * ez)) << 32) | (unsigned)(tid - a);
+            gap = ((unsigned long long)__float_as_uint((float)(ex * ex + ey * ey + ez * ez)) << 32) | (unsigned)(tid - a);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(128, 8) k_tile_split(DevBasis B, const double 
         if (lane == 0) { s_u[wid] = gap; }
         __syncthreads();
         gap = s_u[0]; for (int w = 1; w < 4; ++w) gap = gap > s_u[w] ? gap : s_u[w];
-        const float rho = __uint_as_float((unsigned)(key >> 32)), gmax = __uint_as_float((unsigned)(gap >> 32));
+        const float rho = sqrtf(__uint_as_float((unsigned)(key >> 32))), gmax = sqrtf(__uint_as_float((unsigned)(gap >> 32)));
         const int imax = (int)(gap & 0xffffffffu);
         tg.rho = (double)rho; tg.pad_ = 0.0;
         // active slots (atom runs aligned), atoms, functions
@@ -356,6 +359,7 @@ __global__ void k_tile_emit(const TileSeg *__restrict__ slot_seg, const TileGeo 
         td.pt0 = sg.pt0; td.npts = sg.npts; td.nraw = ti.nraw; td.nact = (ti.nraw + 7) / 8 * 8;
         td.nreal = ti.nreal; td.nn = (ti.nreal + 7) / 8 * 8; td.geo = t; td.nruns = ti.natom;
         td.panel_off = 0; td.fidx_off = 0; td.atab_off = 0;
+        td.col0 = 0; td.col1 = td.nn; td.part = -1; td.pad_ = 0;
         desc[t] = td;
         TileCum tc;
         // scheduling cost in units of one DMMA column step: MMA k-steps x columns (4 planes) + GIAO taps + the tile's share of k_basis
@@ -444,6 +448,23 @@ __global__ void k_tile_gather(const TileDesc *__restrict__ desc, const int *__re
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nt) out[i] = desc[ord[i]];
 }
+// work items of sliced tiles: item i*S + s contracts columns [s*w, min(nn, (s+1)*w)) of tile i, w = the tile's columns / S rounded up to
+// SLICE_COLS; slices past the last column are empty (col1 <= col0: every role skips them)
+__global__ void k_tile_slices(const TileDesc *__restrict__ tiles, int nt, int S, TileDesc *__restrict__ items) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nt * S) return;
+    const int i = j / S, s = j - i * S;
+    TileDesc td = tiles[i];
+    if (td.nact == 0) { if (s) { td.col0 = 0; td.col1 = 0; td.part = j; } items[j] = td; return; }     // slice 0 stores the zeros, the others do nothing
+    const int w = ((td.nn + S - 1) / S + SLICE_COLS - 1) / SLICE_COLS * SLICE_COLS;
+    td.col0 = min(s * w, td.nn); td.col1 = min(td.nn, td.col0 + w); td.part = j;
+    items[j] = td;
+}
+void launch_tile_slices(const TileDesc *tiles, int nt, int S, TileDesc *items, cudaStream_t s) {
+    if (nt <= 0) return;
+    k_tile_slices<<<(unsigned)((nt * S + 255) / 256), 256, 0, s>>>(tiles, nt, S, items);
+}
+
 __global__ void k_perm_index(const int *__restrict__ perm, long n, long *__restrict__ index) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) index[i] = perm[i];

@@ -35,6 +35,7 @@ struct DevBasis {
     const int *atom_func_off;     // [natoms+1] first internal function of the atom
     const int *sh_l, *sh_nprim, *sh_prim_off, *sh_foff;   // [nshell] internal order; sh_foff = first internal function
     const double *sh_thr;         // [nshell] screening radius (descending within an atom)
+    const double *sh_thr2e, *atom_maxthr2e;   // (radius + 1e-9)^2 per shell / of the atom's widest shell: the tile-level tests compare squared distances (no sqrt)
     const double *alpha, *ncc;    // primitives
     const double *fR;             // [3][nbf] centre coordinates of each internal function (SoA)
     int turbomole;                // component order (gtodefs.f90:109-123) instead of the standard one
@@ -50,6 +51,8 @@ struct TileDesc {
     long long panel_off;  // doubles, into the panel pool: 4 planes x nact x LDP
     long long fidx_off;   // ints, into the index pool: nact slot -> function indices, then nn column -> K-slot indices
     long long atab_off;   // TileAtom entries, into the atom-table pool (nruns entries, atom order = slot order)
+    int col0, col1;       // N columns this work item contracts: [0, nn) for a whole tile; a slice of it when few tiles share the GPU
+    int part, pad_;       // >= 0: the item is a slice -- its 13 row sums go to partial block `part` (k_slice_reduce adds the slices); -1: store results
 };
 
 // One active atom of a tile, in slot order.  kend4 = end of its slot run in units of 4 slots (one m16n8k4 K step).
@@ -120,9 +123,18 @@ struct JtensorArgs {
     double *tens; double *edens;                            // outputs (any may be null): 9 x n tensors, n densities,
     double *jvec, *jmod, *acid; double B[3];                // 3 x n J = T.B, n signed |J| (jfield.f90:446-489), n ACID (acid.f90:9-45); field direction
     int jpath;                                              // J = T.B path: operands (D, P.B), the tensor is never formed (tens, acid unavailable)
+    double *part;                                           // [items][MT][PART_LD] partial row sums of sliced tiles (see TileDesc::part)
     int paramag, diamag;
 };
 void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
+// Few tiles (a single plane of an integral, a handful of points): one tile per SM leaves most of the GPU idle and the call waits for one
+// tile's contraction (12.8 ms for a 36 x 36 plane at nbf = 10^4).  The tiles are then cut into S column slices, each a work item of
+// its own (same panels, same K sweep, a subset of the nu chunks); k_slice_reduce adds the slices' row sums in slice order and stores.
+constexpr int PART_LD = 13;          // doubles per row of a partial block
+constexpr int SLICE_COLS = 32;       // slice boundaries are multiples of this many columns (the widest nu chunk of the kernels)
+bool jtensor_supports_slices();      // the epilogue-warpgroup kernels do; the round-1 mapping (GIMIC_B200_EPI=0) does not
+void launch_tile_slices(const TileDesc *tiles, int nt, int S, TileDesc *items, cudaStream_t s);
+void launch_slice_reduce(const JtensorArgs &a, const TileDesc *tiles, int nt, int S, bool giao, cudaStream_t s);
 size_t jtensor_smem_bytes();
 
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,

@@ -54,28 +54,28 @@ Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, cons
     float rho = 0.f, gmax = 0.f; int imax = 0;
     for (int p = 0; p < npts; ++p) {
         const long q = p0 + p;
-        rho = std::fmax(rho, (float)std::sqrt((sx[q] - cx) * (sx[q] - cx) + (sy[q] - cy) * (sy[q] - cy) + (sz[q] - cz) * (sz[q] - cz)));
+        rho = std::fmax(rho, (float)((sx[q] - cx) * (sx[q] - cx) + (sy[q] - cy) * (sy[q] - cy) + (sz[q] - cz) * (sz[q] - cz)));      // squared, like the kernel
         if (p + 1 < npts) {
-            const float g = (float)std::sqrt((sx[q + 1] - sx[q]) * (sx[q + 1] - sx[q]) + (sy[q + 1] - sy[q]) * (sy[q + 1] - sy[q]) + (sz[q + 1] - sz[q]) * (sz[q + 1] - sz[q]));
+            const float g = (float)((sx[q + 1] - sx[q]) * (sx[q + 1] - sx[q]) + (sy[q + 1] - sy[q]) * (sy[q + 1] - sy[q]) + (sz[q + 1] - sz[q]) * (sz[q + 1] - sz[q]));
             if (g >= gmax) { gmax = g; imax = p; }          // ties: the later gap (the kernel reduces (bits << 32 | index) by max)
         }
     }
+    rho = std::sqrt(rho); gmax = std::sqrt(gmax);
     tg.rho = rho; tg.pad_ = 0.0;
     const int al = B.slot_align - 1;
     for (int at = 0; at < B.natoms; ++at) {
         const double x = B.atom_xyz[3 * at], y = B.atom_xyz[3 * at + 1], z = B.atom_xyz[3 * at + 2];
         const double dx = std::fmax(std::fmax(tg.lox - x, x - tg.hix), 0.0), dy = std::fmax(std::fmax(tg.loy - y, y - tg.hiy), 0.0),
                      dz = std::fmax(std::fmax(tg.loz - z, z - tg.hiz), 0.0);
-        if (std::sqrt(dx * dx + dy * dy + dz * dz) - 1e-9 > B.atom_maxthr[at]) continue;
+        if (dx * dx + dy * dy + dz * dz > B.atom_maxthr2e[at]) continue;
         double d2 = 1e300;
         for (int p = 0; p < npts; ++p) {
             const long q = p0 + p;
             d2 = std::fmin(d2, (sx[q] - x) * (sx[q] - x) + (sy[q] - y) * (sy[q] - y) + (sz[q] - z) * (sz[q] - z));
         }
-        const double lim = std::sqrt(d2) - 1e-9;
-        if (lim > B.atom_maxthr[at]) continue;
+        if (d2 > B.atom_maxthr2e[at]) continue;
         int nfun = 0;
-        for (int s = B.atom_shell_off[at]; s < B.atom_shell_off[at + 1] && B.sh_thr[s] >= lim; ++s) nfun += (B.sh_l[s] + 1) * (B.sh_l[s] + 2) / 2;
+        for (int s = B.atom_shell_off[at]; s < B.atom_shell_off[at + 1] && B.sh_thr2e[s] >= d2; ++s) nfun += (B.sh_l[s] + 1) * (B.sh_l[s] + 2) / 2;
         P.nraw += (nfun + al) & ~al; P.natom += nfun > 0; P.nreal += nfun;
     }
     P.tg = tg; P.rho = rho; P.gmax = gmax; P.imax = imax;
@@ -135,6 +135,7 @@ void emulate_tile_emit(void **a) {
             gb::TileDesc td{};
             td.pt0 = seg[run * gb::MAXSUB + j].pt0; td.npts = seg[run * gb::MAXSUB + j].npts; td.nraw = ti.nraw; td.nact = (ti.nraw + 7) / 8 * 8;
             td.nreal = ti.nreal; td.nn = (ti.nreal + 7) / 8 * 8; td.geo = t; td.nruns = ti.natom;
+            td.col0 = 0; td.col1 = td.nn; td.part = -1;
             desc[t] = td;
             cum[t] = gb::TileCum{4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + 110LL * td.nact + (td.nact ? 8192 : 256), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
         }
