@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgimic_b200.so")
+SO_PATH = os.environ.get("GIMIC_B200_LIB") or os.path.join(_HERE, "libgimic_b200.so")     # GIMIC_B200_LIB: an alternative build (A/B measurements)
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

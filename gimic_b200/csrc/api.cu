@@ -444,10 +444,12 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
                      giao ? c->atab.as<TileAtom>() : nullptr, st);
         if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
-        // Few tiles in the batch (a plane of an integral, a handful of points): cut every tile into nsl column slices so that the work
-        // items fill the SMs; the slices' row sums are added by k_slice_reduce.  nsl depends only on the tile count and the device.
+        // Few tiles in the whole point set (a plane of an integral, a handful of points): cut every tile into nsl column slices so that
+        // the work items fill the SMs; the slices' row sums are added by k_slice_reduce.  nsl depends only on the tile count of the
+        // WHOLE set (the same on every rank of a partition, so the ranks' results stay bit-identical to a single-rank run) and the device.
         int nsl = 1;
-        if (nb * 2 <= c->nsm && jtensor_supports_slices()) nsl = std::min(16, c->nsm / nb);
+        const char *slices_env = std::getenv("GIMIC_B200_SLICES");      // "0": never slice (tests compare the two paths)
+        if (S.ntiles * 2 <= c->nsm && jtensor_supports_slices() && !(slices_env && slices_env[0] == '0')) nsl = std::min(16, c->nsm / S.ntiles);
         if (nsl > 1 && (c->items.ensure((size_t)nb * nsl * sizeof(TileDesc)) || c->part.ensure((size_t)nb * nsl * MT * PART_LD * 8)))
             return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tile slices)");
         if (nsl > 1) { launch_tile_slices(c->tiles.as<TileDesc>() + t0, nb, nsl, c->items.as<TileDesc>(), st); c->stats.launches += 2; }

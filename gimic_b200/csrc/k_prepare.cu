@@ -184,33 +184,42 @@ __device__ __forceinline__ void block_min6(double (&v)[6], double (*s_red)[6]) {
     for (int i = 0; i < 6; ++i) v[i] = fmin(fmin(s_red[0][i], s_red[1][i]), fmin(s_red[2][i], s_red[3][i]));
 }
 
-__global__ void __launch_bounds__(128, 8) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
+struct PieceEval { TileGeo tg; float rho, gmax; int imax, nraw, natom, nreal; };
+// what a piece costs the contraction, in the units of k_tile_emit's cost: consumer warps whose 16 rows are past npts issue no MMAs, and
+// with at most 64 points every scheduler holds one live warp instead of two
+__host__ __device__ __forceinline__ long long piece_cost(int npts, int nraw, int nreal, int natom) {
+    const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
+    return (npts <= MT / 2 ? 2LL : 4LL) * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
+}
+__global__ void __launch_bounds__(128, 6) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                     const double *__restrict__ rsz, long n, double split_radius,
                                                     TileSeg *__restrict__ slot_seg, TileGeo *__restrict__ slot_geo,
                                                     TileInfo *__restrict__ slot_info, int *__restrict__ cnt_out) {
+    constexpr int NSTACK = MAXSUB + SPLIT_DEPTH + 2;
     __shared__ double sx[MT], sy[MT], sz[MT];
     __shared__ double s_red[4][6];
     __shared__ unsigned long long s_u[4];
     __shared__ int s_cnt[3];
-    __shared__ int s_stack[MAXSUB + SPLIT_DEPTH + 2][3];
+    __shared__ int s_stack[NSTACK][4];          // first point, end, depth, "already evaluated"
+    __shared__ PieceEval s_ev[NSTACK + 1];      // evaluated pieces on the stack; [NSTACK] = the piece in hand
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long run = blockIdx.x;
     const long pt0 = run * MT;
     const int np = (int)((n - pt0) < MT ? (n - pt0) : MT);
     { const long p = pt0 + (tid < np ? tid : 0); sx[tid] = rsx[p]; sy[tid] = rsy[p]; sz[tid] = rsz[p]; }
     int sp = 0, emitted = 0;               // identical in every thread (all decisions below are made on broadcast values)
-    if (tid == 0) { s_stack[0][0] = 0; s_stack[0][1] = np; s_stack[0][2] = 0; }
+    if (tid == 0) { s_stack[0][0] = 0; s_stack[0][1] = np; s_stack[0][2] = 0; s_stack[0][3] = 0; }
     sp = 1;
     __syncthreads();
     const int al = B.slot_align - 1;
-    while (sp > 0) {
-        --sp;
-        const int a = s_stack[sp][0], b = s_stack[sp][1], depth = s_stack[sp][2];
+    // box, radius, widest gap and active set of the points [a, b) of this run; every thread returns the same values
+    auto evaluate = [&](int a, int b, PieceEval *dst) {
+        PieceEval e;
         const bool in = tid >= a && tid < b;
         const double x = sx[tid], y = sy[tid], z = sz[tid];
         double v[6] = {in ? x : 1e300, in ? y : 1e300, in ? z : 1e300, in ? -x : 1e300, in ? -y : 1e300, in ? -z : 1e300};
         block_min6(v, s_red);
-        TileGeo tg;
+        TileGeo &tg = e.tg;
         tg.lox = v[0]; tg.loy = v[1]; tg.loz = v[2]; tg.hix = -v[3]; tg.hiy = -v[4]; tg.hiz = -v[5];
         const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
         // radius about the centre and the largest gap between consecutive points, packed as (float bits << 32 | index): one max-reduction
@@ -239,31 +248,52 @@ __global__ void __launch_bounds__(128, 8) k_tile_split(DevBasis B, const double 
         if (lane == 0) { s_u[wid] = gap; }
         __syncthreads();
         gap = s_u[0]; for (int w = 1; w < 4; ++w) gap = gap > s_u[w] ? gap : s_u[w];
-        const float rho = sqrtf(__uint_as_float((unsigned)(key >> 32))), gmax = sqrtf(__uint_as_float((unsigned)(gap >> 32)));
-        const int imax = (int)(gap & 0xffffffffu);
-        tg.rho = (double)rho; tg.pad_ = 0.0;
+        e.rho = sqrtf(__uint_as_float((unsigned)(key >> 32))); e.gmax = sqrtf(__uint_as_float((unsigned)(gap >> 32)));
+        e.imax = (int)(gap & 0xffffffffu);
+        tg.rho = (double)e.rho; tg.pad_ = 0.0;
         // active slots (atom runs aligned), atoms, functions
         for (int base = wid * 32; base < B.natoms; base += 128)
             for_active_atoms(B, base, tg, sx + a, sy + a, sz + a, b - a, [&](int, int, int nfun) {
                 if (lane == 0) { atomicAdd(&s_cnt[0], (nfun + al) & ~al); atomicAdd(&s_cnt[1], 1); atomicAdd(&s_cnt[2], nfun); }
             });
         __syncthreads();
-        const int nraw = s_cnt[0], natom = s_cnt[1], nreal = s_cnt[2];
+        e.nraw = s_cnt[0]; e.natom = s_cnt[1]; e.nreal = s_cnt[2];
+        if (tid == 0) *dst = e;
+        __syncthreads();                                   // s_cnt / s_u / s_red are reused by the next evaluation; *dst is visible
+        return piece_cost(b - a, e.nraw, e.nreal, e.natom);
+    };
+    while (sp > 0) {
+        --sp;
+        const int a = s_stack[sp][0], b = s_stack[sp][1], depth = s_stack[sp][2];
+        PieceEval *cur = &s_ev[NSTACK];
+        if (s_stack[sp][3]) { if (tid == 0) *cur = s_ev[sp]; __syncthreads(); } else evaluate(a, b, cur);
+        const float rho = cur->rho, gmax = cur->gmax;
+        const int imax = cur->imax, nraw = cur->nraw;
+        const long long cost = piece_cost(b - a, nraw, cur->nreal, cur->natom);
         const int npts = b - a;
-        const bool split = depth < SPLIT_DEPTH && npts >= 16 && nraw > 0 && rho > (float)split_radius && gmax > 0.5f * rho &&
-                           emitted + sp + 2 <= MAXSUB;
+        // A run of the sorted order that jumps (a curve piece that leaves a thin point set and comes back elsewhere) is cut at its
+        // widest gap -- if the two pieces together cost the contraction less than the whole: their active sets must shrink by more
+        // than the second pass over the (smaller) panels costs.  Round 2 first cut on the geometric test alone; plane grids then
+        // fell into up to MAXSUB partially filled tiles whose active sets were barely smaller than the run's.
+        bool split = depth < SPLIT_DEPTH && npts >= 16 && nraw > 0 && rho > (float)split_radius && gmax > 0.5f * rho &&
+                     emitted + sp + 2 <= MAXSUB;
+        const int m = a + imax + 1;
+        if (split) {         // the pieces are evaluated straight into the stack slots they would take (slot sp has been read above)
+            const long long cr = evaluate(m, b, &s_ev[sp]), cl = evaluate(a, m, &s_ev[sp + 1]);
+            split = 20 * (cl + cr) < 17 * cost;
+        }
         if (split) {
             if (tid == 0) {
-                s_stack[sp][0] = a + imax + 1; s_stack[sp][1] = b; s_stack[sp][2] = depth + 1;          // right piece: later
-                s_stack[sp + 1][0] = a; s_stack[sp + 1][1] = a + imax + 1; s_stack[sp + 1][2] = depth + 1;   // left piece: next
+                s_stack[sp][0] = m; s_stack[sp][1] = b; s_stack[sp][2] = depth + 1; s_stack[sp][3] = 1;                  // right piece: later
+                s_stack[sp + 1][0] = a; s_stack[sp + 1][1] = m; s_stack[sp + 1][2] = depth + 1; s_stack[sp + 1][3] = 1;   // left piece: next
             }
             sp += 2;
         } else {
             if (tid == 0) {
                 const long o = run * MAXSUB + emitted;
                 slot_seg[o] = TileSeg{(int)(pt0 + a), npts};
-                slot_geo[o] = tg;
-                slot_info[o] = TileInfo{rho, gmax, imax, nraw, natom, nreal};
+                slot_geo[o] = cur->tg;
+                slot_info[o] = TileInfo{rho, gmax, imax, nraw, cur->natom, cur->nreal};
             }
             ++emitted;
         }
@@ -367,7 +397,7 @@ __global__ void k_tile_emit(const TileSeg *__restrict__ slot_seg, const TileGeo 
         // per tile (descriptor, prologue, stores).  The last two were fitted on the 8-GPU run of the 256^3 grid, where ranks holding
         // many cheap tiles far from the molecule ran 4 % longer than ranks of equal flops (profiles/r02_bench_n8_grid_h.json).
         // Integers, so every rank computes the same prefix sums and hence the same partition.
-        tc.cost = 4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + 110LL * td.nact + (td.nact ? 8192 : 256);
+        tc.cost = piece_cost(td.npts, td.nraw, td.nreal, td.nruns);
         tc.panel = 4LL * td.nact * LDP; tc.fidx = td.nact + td.nn; tc.atab = td.nruns;
         cum[t] = tc;
     }

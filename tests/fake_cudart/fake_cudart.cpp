@@ -81,11 +81,20 @@ Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, cons
     P.tg = tg; P.rho = rho; P.gmax = gmax; P.imax = imax;
     return P;
 }
+long long piece_cost(int npts, int nraw, int nreal, int natom) {
+    const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
+    return (npts <= gb::MT / 2 ? 2LL : 4LL) * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
+}
 void split_piece(const gb::DevBasis &B, const double *sx, const double *sy, const double *sz, long p0, int npts, int depth, double split_radius,
                  long run, int &emitted, int pending, gb::TileSeg *seg, gb::TileGeo *geo, gb::TileInfo *info) {
     const Piece P = eval_piece(B, sx, sy, sz, p0, npts);
-    const bool split = depth < gb::SPLIT_DEPTH && npts >= 16 && P.nraw > 0 && P.rho > (float)split_radius && P.gmax > 0.5f * P.rho &&
-                       emitted + pending + 2 <= gb::MAXSUB;
+    bool split = depth < gb::SPLIT_DEPTH && npts >= 16 && P.nraw > 0 && P.rho > (float)split_radius && P.gmax > 0.5f * P.rho &&
+                 emitted + pending + 2 <= gb::MAXSUB;
+    if (split) {         // only if the two pieces cost the contraction less than the whole (k_tile_split)
+        const Piece L = eval_piece(B, sx, sy, sz, p0, P.imax + 1), R = eval_piece(B, sx, sy, sz, p0 + P.imax + 1, npts - P.imax - 1);
+        split = 20 * (piece_cost(P.imax + 1, L.nraw, L.nreal, L.natom) + piece_cost(npts - P.imax - 1, R.nraw, R.nreal, R.natom)) <
+                17 * piece_cost(npts, P.nraw, P.nreal, P.natom);
+    }
     if (split) {
         split_piece(B, sx, sy, sz, p0, P.imax + 1, depth + 1, split_radius, run, emitted, pending + 1, seg, geo, info);
         split_piece(B, sx, sy, sz, p0 + P.imax + 1, npts - P.imax - 1, depth + 1, split_radius, run, emitted, pending, seg, geo, info);
@@ -137,7 +146,7 @@ void emulate_tile_emit(void **a) {
             td.nreal = ti.nreal; td.nn = (ti.nreal + 7) / 8 * 8; td.geo = t; td.nruns = ti.natom;
             td.col0 = 0; td.col1 = td.nn; td.part = -1;
             desc[t] = td;
-            cum[t] = gb::TileCum{4LL * td.nact * td.nn + 3LL * td.nn * td.nruns + 110LL * td.nact + (td.nact ? 8192 : 256), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
+            cum[t] = gb::TileCum{piece_cost(td.npts, td.nraw, td.nreal, td.nruns), 4LL * td.nact * gb::LDP, td.nact + td.nn, td.nruns};
         }
 }
 void emulate_scan_partial_c(void **a) {

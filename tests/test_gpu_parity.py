@@ -835,3 +835,32 @@ def test_nccl_integral_all_reduce_when_two_gpus(gb, cases, tmp_path):
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29571", os.path.join(root, "tools", "dist_integral_check.py")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_column_sliced_tiles_equal_whole_tiles(gb, monkeypatch):
+    """few tiles (a plane, a handful of points): every tile is cut into column slices that run as separate work items and are added by
+    k_slice_reduce.  Same numbers as whole tiles (to rounding: the nu sums are split) and as the oracle; both paths (tensor, J)."""
+    sh, dens, nbf = fixtures.synthetic_case(14, "flake")
+    flat = fixtures.dens_to_colmajor(dens)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=flat, **sh)
+    o = O.Oracle.from_arrays(dens_a=flat, **sh)
+    rng = np.random.default_rng(41)
+    B = np.array([0.0, 0.6, 0.8])
+    for n in (1, 100, 1296, 5000):                 # 1 .. ~45 tiles: 16, 16, ~13 and ~3 slices per tile on 148 SMs
+        r = rng.uniform(-7, 7, size=(n, 3)); r[:, 2] *= 0.4
+        monkeypatch.setenv("GIMIC_B200_SLICES", "1")
+        a = g.fields(r, B, tens=True, jvec=True, jmod=True, acid=True, edens=True)
+        ja = g.fields(r, B, jvec=True, jmod=True)
+        la = g.stats()["launches"]
+        monkeypatch.setenv("GIMIC_B200_SLICES", "0")
+        b = g.fields(r, B, tens=True, jvec=True, jmod=True, acid=True, edens=True)
+        jb = g.fields(r, B, jvec=True, jmod=True)
+        lb = g.stats()["launches"]
+        assert la == lb + 2, "the sliced path was not taken"
+        ref, ed = o.ctensor(r, want_edens=True)
+        assert_close(a["tens"], ref, f"sliced tensors, n={n}"); assert_close(b["tens"], ref, f"whole tiles, n={n}")
+        assert_close(a["edens"], ed, "edens")
+        _jscale_close(a["jvec"], b["jvec"], ref, "sliced vs whole jvec"); _jscale_close(ja["jvec"], jb["jvec"], ref, "J path sliced vs whole")
+        _jscale_close(ja["jvec"], O.jvectors(ref, B), ref, "J path sliced vs oracle")
+        assert_close(a["acid"], O.acid_field(ref), "acid (sliced)")
+    g.close()
