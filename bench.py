@@ -200,10 +200,15 @@ def stage_records(g, grid, dev, t_dev_full, index_full, sh, B):
     for _ in range(5):
         t0 = time.perf_counter(); s7 = g.integrate(plane, B, "total", 3); ts.append(time.perf_counter() - t0)
     st = g.stats()
+    g.set_profiling(True)
+    g.integrate(plane, B, "total", 3)
+    sp = g.stats()
+    g.set_profiling(False)
     out["integral_36x36"] = {"what": "gimic_b200_integrate: one 36x36 Gauss-Legendre plane through the flake (current + modulus), nbf=10008",
                              "wall_us": min(ts) * 1e6, "points": 1296, "tiles": int(st["n_tiles"]), "mean_active_slots": st["sum_nact"] / max(st["n_tiles"], 1),
                              "executed_over_useful_flops": st["executed_flops"] / st["useful_flops"] if st["useful_flops"] else None,
-                             "sums": [float(v) for v in s7[:6]]}
+                             "stage_ms_profiled_call": {k: sp[k] for k in ("ms_total", "ms_sort", "ms_tiles", "ms_basis", "ms_contract")},
+                             "launches": int(sp["launches"]), "sums": [float(v) for v in s7[:6]]}
     return out
 
 

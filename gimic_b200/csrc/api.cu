@@ -336,7 +336,7 @@ int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nrank
     const bool prof = c->profiling;
     const long nrun0 = (n + MT - 1) / MT;
 
-    if (c->keys0.ensure(n * 8) || c->keys1.ensure(n * 8) || c->vals0.ensure(n * 4) || c->vals1.ensure(n * 4) ||
+    if (c->keys0.ensure(n * 4) || c->keys1.ensure(n * 4) || c->vals0.ensure(n * 4) || c->vals1.ensure(n * 4) ||
         c->rs.ensure((size_t)3 * n * 8) || c->misc.ensure(256) || c->d_summary.ensure(sizeof(PlanSummary)))
         return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed");
     size_t tb = sort_temp_bytes(n);
@@ -345,8 +345,8 @@ int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nrank
     int *perm = c->vals1.as<int>();
 
     if (prof) cudaEventRecord(c->ev[0], st);
-    launch_morton_keys(d_r, n, c->bbox_lo, c->inv_cell, c->keys0.as<uint64_t>(), c->vals0.as<int>(), st);
-    launch_sort_pairs(c->sorttmp.p, tb, c->keys0.as<uint64_t>(), c->keys1.as<uint64_t>(), c->vals0.as<int>(), perm, n, st);
+    launch_morton_keys(d_r, n, c->bbox_lo, c->inv_cell, c->keys0.as<uint32_t>(), c->vals0.as<int>(), st);
+    launch_sort_pairs(c->sorttmp.p, tb, c->keys0.as<uint32_t>(), c->keys1.as<uint32_t>(), c->vals0.as<int>(), perm, n, st);
     launch_gather_points(d_r, perm, n, rsx, rsy, rsz, st);
     if (prof) cudaEventRecord(c->ev[1], st);
     c->stats.launches += 4;

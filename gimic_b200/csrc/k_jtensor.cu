@@ -827,7 +827,6 @@ __device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const doub
         const TileDesc td = a.tiles[tile];
         if (td.nact == 0 || td.col1 <= td.col0) continue;            // the epilogue warps write the zeros; empty slices do nothing
         const int rowA = row0 + g, rowB = row0 + g + 8;
-        const bool live = row0 < td.npts;                            // a warp whose 16 rows are all past the tile's points issues no MMAs (partial tiles)
         const int nact = td.nact, nn = td.col1 - td.col0;
         const int nkc = (nact + BK - 1) / BK, nvc = (nn + NV - 1) / NV;
         const uint32_t NIT = (uint32_t)nkc * nvc;
@@ -883,7 +882,7 @@ __device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const doub
             }
             const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
             const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
-            const int nks = live ? min(BK, nact - kc * BK) / 4 : 0;
+            const int nks = min(BK, nact - kc * BK) / 4;
             const bool h1 = vc * NV + 8 < nn;                       // second n8 tile of this chunk holds real columns
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
@@ -927,7 +926,7 @@ __device__ __forceinline__ void consumer_role_e(const JtensorArgs &a, const doub
                 const double *colR = s_colR + (size_t)(c % CRING) * NV * 4;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if ((h == 1 && !h1) || !live) continue;
+                    if (h == 1 && !h1) continue;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const int col = h * 8 + 2 * t + j;
@@ -1044,7 +1043,6 @@ __device__ __forceinline__ void consumer_role_ej(const JtensorArgs &a, const dou
         const TileDesc td = a.tiles[tile];
         if (td.nact == 0 || td.col1 <= td.col0) continue;            // the epilogue warps write the zeros; empty slices do nothing
         const int rowA = row0 + g, rowB = row0 + g + 8;
-        const bool live = row0 < td.npts;                            // a warp whose 16 rows are all past the tile's points issues no MMAs (partial tiles)
         const int nact = td.nact, nn = td.col1 - td.col0;
         const int nkc = (nact + BK - 1) / BK, nvc = (nn + NVJ - 1) / NVJ;
         const uint32_t NIT = (uint32_t)nkc * nvc;
@@ -1101,8 +1099,8 @@ __device__ __forceinline__ void consumer_role_ej(const JtensorArgs &a, const dou
             }
             const int k4base = kc * (BK / 4);                                   // BK/4 = 8 K steps per stage: their bits share a word
             const uint32_t m8 = GIAO ? (s_kmask[k4base >> 5] >> (k4base & 31)) : 0u;
-            const int nks = live ? min(BK, nact - kc * BK) / 4 : 0;
-            const int nh = live ? min(NH, (nn - vc * NVJ) / 8) : 0; // n8 tiles of this chunk that hold real columns (nn is a multiple of 8)
+            const int nks = min(BK, nact - kc * BK) / 4;
+            const int nh = min(NH, (nn - vc * NVJ) / 8);            // n8 tiles of this chunk that hold real columns (nn is a multiple of 8)
             const double *sA = s_stage + (size_t)s * SM::STAGE_DOUBLES;
             const double *sB = sA + SM::A_DOUBLES;
             mbar_wait(bar_full + 8 * s, ph);

@@ -24,12 +24,13 @@ __device__ __forceinline__ uint64_t spread16(uint32_t v) {   // 16 bits -> every
     return x;
 }
 
-// 48-bit 3-D Hilbert index (16 bits per axis, Skilling's axes-to-transpose).  A Hilbert curve is
+constexpr int KEY_DROP_BITS = 18;
+// 48-bit 3-D Hilbert index (16 bits per axis, Skilling's axes-to-transpose), of which the key keeps the top 30 bits.  A Hilbert curve is
 // continuous, so any run of 128 consecutive sorted points is spatially compact; a Morton (Z) curve
 // jumps, and the few tiles straddling a jump get a huge bounding sphere => nact ~ nbf => one CTA
 // runs 100x longer than the rest (measured: SMs 5.7% active, profiles/r01_ncu_jtensor_a.txt).
 __global__ void k_morton_keys(const double *__restrict__ r, long n, double lox, double loy, double loz, double inv_cell,
-                              uint64_t *__restrict__ keys, int *__restrict__ vals) {
+                              uint32_t *__restrict__ keys, int *__restrict__ vals) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t X[3];
@@ -48,25 +49,25 @@ __global__ void k_morton_keys(const double *__restrict__ r, long n, double lox, 
     uint32_t t = 0;
     for (uint32_t Q = 1u << 15; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
     X[0] ^= t; X[1] ^= t; X[2] ^= t;
-    keys[i] = (spread16(X[0]) << 2) | (spread16(X[1]) << 1) | spread16(X[2]);
+    keys[i] = (uint32_t)(((spread16(X[0]) << 2) | (spread16(X[1]) << 1) | spread16(X[2])) >> KEY_DROP_BITS);
     vals[i] = (int)i;
 }
 
-void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s) {
+void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint32_t *keys, int *vals, cudaStream_t s) {
     if (n <= 0) return;
     k_morton_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, n, bbox_lo[0], bbox_lo[1], bbox_lo[2], inv_cell, keys, vals);
 }
 
-// Only the top 30 of the 48 key bits are sorted on (4 radix passes instead of 6): cells of (box / 1024) ~ 0.1 bohr along the curve; the
-// sort is stable, so points of one cell keep the caller's order -- they are closer together than any tile is wide.
-constexpr int SORT_BEGIN_BIT = 18;
+// Only the top 30 of the 48 index bits are kept (KEY_DROP_BITS = 18) and sorted on: 4 radix passes over 32-bit keys instead of 6 over
+// 64-bit ones.  Cells of (box / 1024) ~ 0.1 bohr along the curve; the sort is stable, so points of one cell keep the caller's order --
+// they are closer together than any tile is wide.
 size_t sort_temp_bytes(long n) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, SORT_BEGIN_BIT, 48);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int *)nullptr, (int *)nullptr, (int)n, 0, 48 - KEY_DROP_BITS);
     return bytes;
 }
-void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s) {
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, SORT_BEGIN_BIT, 48, s);
+void launch_sort_pairs(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const int *vin, int *vout, long n, cudaStream_t s) {
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 48 - KEY_DROP_BITS, s);
 }
 
 __global__ void k_gather_points(const double *__restrict__ r, const int *__restrict__ perm, long n, double *__restrict__ rsx,
@@ -185,11 +186,14 @@ __device__ __forceinline__ void block_min6(double (&v)[6], double (*s_red)[6]) {
 }
 
 struct PieceEval { TileGeo tg; float rho, gmax; int imax, nraw, natom, nreal; };
-// what a piece costs the contraction, in the units of k_tile_emit's cost: consumer warps whose 16 rows are past npts issue no MMAs, and
-// with at most 64 points every scheduler holds one live warp instead of two
+// what a piece costs the contraction (one DMMA column step = 1): MMA k-steps x columns (4 planes) + GIAO taps + the tile's share of
+// k_basis + a fixed part.  A tile costs the same whether its 128 rows are all points or not: letting the consumer warps without
+// valid rows skip their MMAs was measured (round 2, calls L/M) -- the extra branch cost the full-tile loop 4.5 % and a 36x36 plane
+// gained nothing.
 __host__ __device__ __forceinline__ long long piece_cost(int npts, int nraw, int nreal, int natom) {
     const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
-    return (npts <= MT / 2 ? 2LL : 4LL) * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
+    (void)npts;
+    return 4LL * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
 }
 __global__ void __launch_bounds__(128, 6) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                     const double *__restrict__ rsz, long n, double split_radius,

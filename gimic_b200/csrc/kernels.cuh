@@ -85,7 +85,7 @@ struct PlanSummary {                // device -> host, once per plan
 };
 
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
-void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint64_t *keys, int *vals, cudaStream_t s);
+void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint32_t *keys, int *vals, cudaStream_t s);
 void launch_gather_points(const double *r, const int *perm, long n, double *rsx, double *rsy, double *rsz, cudaStream_t s);
 void launch_grid_points(const double *origin_basv /*12 doubles, device*/, const double *p0, const double *p1, const double *p2,
                         int n0, int n1, int n2, long lo, long hi, double *r, cudaStream_t s);
@@ -111,7 +111,7 @@ void launch_panel_scatter(const TileDesc *tiles, int ntiles, const double *panel
                           int nbf, double *bf, double *dr, cudaStream_t s);
 void launch_basis_dense(const DevBasis &B, const int *f2user, long n, const double *r, double *bf, double *dr, cudaStream_t s);
 size_t sort_temp_bytes(long n);
-void launch_sort_pairs(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const int *vin, int *vout, long n, cudaStream_t s);
+void launch_sort_pairs(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const int *vin, int *vout, long n, cudaStream_t s);
 
 struct JtensorArgs {
     const TileDesc *tiles; int ntiles; int *counter;

@@ -83,7 +83,8 @@ Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, cons
 }
 long long piece_cost(int npts, int nraw, int nreal, int natom) {
     const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
-    return (npts <= gb::MT / 2 ? 2LL : 4LL) * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
+    (void)npts;
+    return 4LL * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
 }
 void split_piece(const gb::DevBasis &B, const double *sx, const double *sy, const double *sz, long p0, int npts, int depth, double split_radius,
                  long run, int &emitted, int pending, gb::TileSeg *seg, gb::TileGeo *geo, gb::TileInfo *info) {
