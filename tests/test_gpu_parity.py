@@ -502,9 +502,14 @@ def test_random_molecules_vs_oracle(gb, seed):
         # are sums of alpha and beta parts of either sign: the 1e-10 bound is taken at the scale of the quantities that are
         # summed (the largest component of the point, alpha and beta separately), where FP64 noise limits the oracle as well.
         scale = np.abs(to).max(axis=1, keepdims=True)
-        if uhf:
-            scale = np.maximum(scale, np.maximum(np.abs(o.ctensor(r, "alpha")), np.abs(o.ctensor(r, "beta"))).max(axis=1, keepdims=True))
-        err = np.abs(res["tens"] - to) / (RTOL * np.maximum(np.abs(to), 1e-3 * scale) + ATOL)
+        bound = RTOL * np.maximum(np.abs(to), 1e-3 * scale) + ATOL
+        if uhf and sc in ("total", "spindens"):
+            # T(alpha) +- T(beta): each part carries the 1e-10 bound at its own scale and the two add (one contraction with the
+            # operand D_alpha +- D_beta sums terms of the size of both), so the bound of the combination is the sum of the bounds
+            ta, tb = o.ctensor(r, "alpha"), o.ctensor(r, "beta")
+            sa, sb = np.abs(ta).max(axis=1, keepdims=True), np.abs(tb).max(axis=1, keepdims=True)
+            bound = RTOL * (np.maximum(np.abs(ta), 1e-3 * sa) + np.maximum(np.abs(tb), 1e-3 * sb)) + ATOL
+        err = np.abs(res["tens"] - to) / bound
         assert err.max() <= 1.0, f"{what}: {err.max():.3g}"
         if not uhf:
             assert_close(res["edens"], eo, what + " edens")
