@@ -444,15 +444,20 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
                      giao ? c->atab.as<TileAtom>() : nullptr, st);
         if (prof) cudaEventRecord(c->evpool[3 * b + 1], st);
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
-        // Few tiles in the whole point set (a plane of an integral, a handful of points): cut every tile into nsl column slices so that
-        // the work items fill the SMs; the slices' row sums are added by k_slice_reduce.  nsl depends only on the tile count of the
-        // WHOLE set (the same on every rank of a partition, so the ranks' results stay bit-identical to a single-rank run) and the device.
+        // Less than one tile per SM in the whole point set (a plane of an integral, a handful of points): cut the tiles into column
+        // slices so that the work items fill the SMs twice over, each of about the same cost (slice_width, kernels.cuh); the slices'
+        // row sums are added by k_slice_reduce.  Slot count and item cost depend only on the WHOLE set's tiles (the same on every
+        // rank of a partition, so the ranks' results stay bit-identical to a single-rank run) and on the device.
         int nsl = 1;
+        long long item_cost = 1;
         const char *slices_env = std::getenv("GIMIC_B200_SLICES");      // "0": never slice (tests compare the two paths)
-        if (S.ntiles * 2 <= c->nsm && jtensor_supports_slices() && !(slices_env && slices_env[0] == '0')) nsl = std::min(16, c->nsm / S.ntiles);
+        if (S.ntiles <= c->nsm && jtensor_supports_slices() && !(slices_env && slices_env[0] == '0')) {
+            nsl = 16;
+            item_cost = std::max<long long>(1, S.cost_total / (2LL * c->nsm));
+        }
         if (nsl > 1 && (c->items.ensure((size_t)nb * nsl * sizeof(TileDesc)) || c->part.ensure((size_t)nb * nsl * MT * PART_LD * 8)))
             return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tile slices)");
-        if (nsl > 1) { launch_tile_slices(c->tiles.as<TileDesc>() + t0, nb, nsl, c->items.as<TileDesc>(), st); c->stats.launches += 2; }
+        if (nsl > 1) { launch_tile_slices(c->tiles.as<TileDesc>() + t0, nb, nsl, item_cost, c->items.as<TileDesc>(), st); c->stats.launches += 2; }
         JtensorArgs a;
         a.tiles = nsl > 1 ? c->items.as<TileDesc>() : c->tiles.as<TileDesc>() + t0; a.ntiles = nb * nsl; a.counter = c->misc.as<int>();
         a.part = nsl > 1 ? c->part.as<double>() : nullptr;
@@ -463,7 +468,7 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
         for (int k = 0; k < 3; ++k) a.B[k] = o.B3 ? o.B3[k] : 0.0;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
         launch_jtensor(a, giao, c->nsm, st);
-        if (nsl > 1) launch_slice_reduce(a, c->tiles.as<TileDesc>() + t0, nb, nsl, giao, st);
+        if (nsl > 1) launch_slice_reduce(a, c->tiles.as<TileDesc>() + t0, nb, nsl, item_cost, giao, st);
         CUDA_TRY(cudaGetLastError());
         c->stats.launches += 2;
         c->stats.contract_launches += 1;

@@ -1329,11 +1329,11 @@ static void launch_one(const JtensorArgs &a, int grid, cudaStream_t s) {
 
 // adds the row sums of a tile's slices in slice order (fixed => reproducible), finalises and stores.  One CTA (MT threads) per tile.
 template <bool GIAO>
-__global__ void __launch_bounds__(MT) k_slice_reduce(JtensorArgs a, const TileDesc *__restrict__ tiles, int S) {
+__global__ void __launch_bounds__(MT) k_slice_reduce(JtensorArgs a, const TileDesc *__restrict__ tiles, int S, long long item_cost) {
     const TileDesc td = tiles[blockIdx.x];
     const int row = threadIdx.x;
     if (td.nact == 0 || row >= td.npts) return;                       // empty tiles were zero-filled by their first item
-    const int w = ((td.nn + S - 1) / S + SLICE_COLS - 1) / SLICE_COLS * SLICE_COLS;
+    const int w = slice_width(td, S, item_cost);
     const int nsl = (td.nn + w - 1) / w;
     const int ne = a.jpath ? 7 : 13;
     double e[13];
@@ -1348,9 +1348,9 @@ __global__ void __launch_bounds__(MT) k_slice_reduce(JtensorArgs a, const TileDe
     if (a.jpath) finalise_store_j(a, e, px, py, pz, out_row(a, p));
     else finalise_store_tensor<GIAO>(a, e, px, py, pz, out_row(a, p));
 }
-void launch_slice_reduce(const JtensorArgs &a, const TileDesc *tiles, int nt, int S, bool giao, cudaStream_t s) {
+void launch_slice_reduce(const JtensorArgs &a, const TileDesc *tiles, int nt, int S, long long item_cost, bool giao, cudaStream_t s) {
     if (nt <= 0) return;
-    if (giao) k_slice_reduce<true><<<nt, MT, 0, s>>>(a, tiles, S); else k_slice_reduce<false><<<nt, MT, 0, s>>>(a, tiles, S);
+    if (giao) k_slice_reduce<true><<<nt, MT, 0, s>>>(a, tiles, S, item_cost); else k_slice_reduce<false><<<nt, MT, 0, s>>>(a, tiles, S, item_cost);
 }
 
 // GIMIC_B200_EPI=0 selects the round-1 mapping of the tensor path (epilogue inside the consumer warps) for A/B measurements

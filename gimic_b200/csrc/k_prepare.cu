@@ -4,6 +4,7 @@
 // caos.f90:17-110 and basis.f90:118-136): one exp per primitive (the reference evaluates each four
 // times), integer powers by repeated multiplication, and the *same* screening test
 // sqrt(|r-R|^2) <= thr  so screened functions are exact zeros as in the reference.
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
@@ -115,40 +116,55 @@ void launch_grid_points(const double *ob, const double *p0, const double *p1, co
 // shell / function ranges) and tests its bounding box; the surviving atoms are then processed one at a time with their data broadcast
 // by shuffles, so that the only dependent global-memory round per candidate is the one that fetches the shell radii.
 // emit(atom, nsh, nfun) is called by all 32 lanes for every atom with nfun > 0.
+// The minimum distance is searched in SINGLE precision on coordinates relative to the tile centre (FP64 vector instructions issue
+// at a fraction of the FP32 rate and 64-bit shuffles are two instructions: the FP64 search was 45 % of k_tile_split's instructions,
+// profiles/r02_ncu_tile_split.txt) and turned into a rigorous LOWER bound of the exact squared distance:
+//   per component, fl32(x - c) - fl32(a - c) differs from x - a by at most 2^-23 (|x - c| + |a - c|), i.e. |delta| <= D :=
+//   2.5e-7 (2 rho + d) with d the distance found, so d2 - (2 d D + D^2) - 3e-7 d2 (FMA chain) never exceeds the exact value.
+// A lower bound only ever ADDS shells to the active set (by a relative margin of ~1e-6 in radius); the per-point test inside
+// k_basis is the exact one.
+struct TileFrame { double cx, cy, cz; float rho; };
+__device__ __forceinline__ TileFrame tile_frame(const TileGeo &tg) {
+    return TileFrame{0.5 * (tg.lox + tg.hix), 0.5 * (tg.loy + tg.hiy), 0.5 * (tg.loz + tg.hiz), __double2float_ru(tg.rho)};
+}
 template <class Emit>
-__device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, const TileGeo &tg, const double *sx, const double *sy,
-                                                 const double *sz, int np, Emit emit) {
+__device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, const TileGeo &tg, const TileFrame &fr, const float *fx,
+                                                 const float *fy, const float *fz, int np, Emit emit) {
     const int lane = threadIdx.x & 31;
     const int at = base + lane;
     // All tile-level tests compare SQUARED distances with (radius + 1e-9)^2 (precomputed): a shell is kept if (thr + 1e-9)^2 >= d2, a
-    // superset of the per-point test sqrt(r2) <= thr of k_basis (the margin 2e-9 thr dwarfs the rounding of the squares).  The double
-    // sqrt these tests used to take was 35 % of k_tile_split's instructions (profiles/r02_ncu_tile_split.txt).
-    double x = 0.0, y = 0.0, z = 0.0, mx = 0.0;
+    // superset of the per-point test sqrt(r2) <= thr of k_basis (the margin 2e-9 thr dwarfs the rounding of the squares).
+    float ax_ = 0.f, ay_ = 0.f, az_ = 0.f;
+    double mx = 0.0;
     int s0 = 0, s1 = 0, f0 = 0, f1 = 0;
     bool pass = false;
     if (at < B.natoms) {
-        x = B.atom_xyz[3 * at]; y = B.atom_xyz[3 * at + 1]; z = B.atom_xyz[3 * at + 2];
+        const double x = B.atom_xyz[3 * at], y = B.atom_xyz[3 * at + 1], z = B.atom_xyz[3 * at + 2];
         mx = B.atom_maxthr2e[at];
         s0 = B.atom_shell_off[at]; s1 = B.atom_shell_off[at + 1]; f0 = B.atom_func_off[at]; f1 = B.atom_func_off[at + 1];
         const double dx = fmax(fmax(tg.lox - x, x - tg.hix), 0.0), dy = fmax(fmax(tg.loy - y, y - tg.hiy), 0.0),
                      dz = fmax(fmax(tg.loz - z, z - tg.hiz), 0.0);
         pass = !(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx))) > mx);
+        ax_ = __double2float_rn(x - fr.cx); ay_ = __double2float_rn(y - fr.cy); az_ = __double2float_rn(z - fr.cz);
     }
     unsigned bal = __ballot_sync(0xffffffffu, pass);
     while (bal) {
         const int src = __ffs(bal) - 1;
         bal &= bal - 1;
-        const double ax = __shfl_sync(0xffffffffu, x, src), ay = __shfl_sync(0xffffffffu, y, src), az = __shfl_sync(0xffffffffu, z, src);
+        const float ax = __shfl_sync(0xffffffffu, ax_, src), ay = __shfl_sync(0xffffffffu, ay_, src), az = __shfl_sync(0xffffffffu, az_, src);
         const double amx = __shfl_sync(0xffffffffu, mx, src);
         const int as0 = __shfl_sync(0xffffffffu, s0, src), as1 = __shfl_sync(0xffffffffu, s1, src);
         const int af0 = __shfl_sync(0xffffffffu, f0, src), af1 = __shfl_sync(0xffffffffu, f1, src);
-        double d2 = 1e300;
+        float m = 3.0e38f;
         for (int p = lane; p < np; p += 32) {
-            const double ex = sx[p] - ax, ey = sy[p] - ay, ez = sz[p] - az;
-            d2 = fmin(d2, __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
+            const float ex = __fsub_rn(fx[p], ax), ey = __fsub_rn(fy[p], ay), ez = __fsub_rn(fz[p], az);
+            m = fminf(m, __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex))));
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d2 = fmin(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float dd = __fsqrt_ru(m), D = __fmul_ru(2.5e-7f, __fmaf_ru(2.0f, fr.rho, dd));
+        const float slack = __fmaf_ru(3.0e-7f, m, __fmaf_ru(D, D, __fmul_ru(__fmul_ru(2.0f, dd), D)));
+        const double d2 = (double)fmaxf(__fsub_rd(m, __fmul_ru(1.01f, slack)), 0.0f);      // <= the exact minimum squared distance
         if (d2 > amx) continue;
         // shells are sorted by descending radius inside an atom: the active ones are a prefix
         int cnt = 0, fend = af0;                  // active shells, function index after the last active shell
@@ -171,37 +187,31 @@ __device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, co
 // run (bounding box, radius, largest consecutive gap, active slots / atoms / functions); a piece wider than split_radius whose
 // largest gap exceeds half its radius is cut there (thin / planar point sets, cluster boundaries: a Hilbert run that leaves and
 // re-enters the point cloud would otherwise drag in the active sets of both ends), everything else is emitted in order.
-__device__ __forceinline__ void block_min6(double (&v)[6], double (*s_red)[6]) {   // 128 threads; result broadcast
+// minimum of 6 values over the 128 threads, in single precision: the callers pass values rounded DOWN, so the result bounds the exact
+// minimum from below (the tile's box may grow by one float ulp per side, never shrink); result broadcast
+__device__ __forceinline__ void block_min6(float (&v)[6], float (*s_red)[6]) {
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[i] = fmin(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+        for (int o = 16; o > 0; o >>= 1) v[i] = fminf(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
     __syncthreads();
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
         for (int i = 0; i < 6; ++i) s_red[threadIdx.x >> 5][i] = v[i];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 6; ++i) v[i] = fmin(fmin(s_red[0][i], s_red[1][i]), fmin(s_red[2][i], s_red[3][i]));
+    for (int i = 0; i < 6; ++i) v[i] = fminf(fminf(s_red[0][i], s_red[1][i]), fminf(s_red[2][i], s_red[3][i]));
 }
 
 struct PieceEval { TileGeo tg; float rho, gmax; int imax, nraw, natom, nreal; };
-// what a piece costs the contraction (one DMMA column step = 1): MMA k-steps x columns (4 planes) + GIAO taps + the tile's share of
-// k_basis + a fixed part.  A tile costs the same whether its 128 rows are all points or not: letting the consumer warps without
-// valid rows skip their MMAs was measured (round 2, calls L/M) -- the extra branch cost the full-tile loop 4.5 % and a 36x36 plane
-// gained nothing.
-__host__ __device__ __forceinline__ long long piece_cost(int npts, int nraw, int nreal, int natom) {
-    const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
-    (void)npts;
-    return 4LL * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
-}
 __global__ void __launch_bounds__(128, 6) k_tile_split(DevBasis B, const double *__restrict__ rsx, const double *__restrict__ rsy,
                                                     const double *__restrict__ rsz, long n, double split_radius,
                                                     TileSeg *__restrict__ slot_seg, TileGeo *__restrict__ slot_geo,
                                                     TileInfo *__restrict__ slot_info, int *__restrict__ cnt_out) {
     constexpr int NSTACK = MAXSUB + SPLIT_DEPTH + 2;
     __shared__ double sx[MT], sy[MT], sz[MT];
-    __shared__ double s_red[4][6];
+    __shared__ float fx[MT], fy[MT], fz[MT];    // the piece in hand, relative to its centre
+    __shared__ float s_red[4][6];
     __shared__ unsigned long long s_u[4];
     __shared__ int s_cnt[3];
     __shared__ int s_stack[NSTACK][4];          // first point, end, depth, "already evaluated"
@@ -221,11 +231,14 @@ __global__ void __launch_bounds__(128, 6) k_tile_split(DevBasis B, const double 
         PieceEval e;
         const bool in = tid >= a && tid < b;
         const double x = sx[tid], y = sy[tid], z = sz[tid];
-        double v[6] = {in ? x : 1e300, in ? y : 1e300, in ? z : 1e300, in ? -x : 1e300, in ? -y : 1e300, in ? -z : 1e300};
+        const float big = 3.0e38f;
+        float v[6] = {in ? __double2float_rd(x) : big, in ? __double2float_rd(y) : big, in ? __double2float_rd(z) : big,
+                      in ? __double2float_rd(-x) : big, in ? __double2float_rd(-y) : big, in ? __double2float_rd(-z) : big};
         block_min6(v, s_red);
         TileGeo &tg = e.tg;
-        tg.lox = v[0]; tg.loy = v[1]; tg.loz = v[2]; tg.hix = -v[3]; tg.hiy = -v[4]; tg.hiz = -v[5];
+        tg.lox = v[0]; tg.loy = v[1]; tg.loz = v[2]; tg.hix = -(double)v[3]; tg.hiy = -(double)v[4]; tg.hiz = -(double)v[5];
         const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
+        fx[tid] = __double2float_rn(x - cx); fy[tid] = __double2float_rn(y - cy); fz[tid] = __double2float_rn(z - cz);   // visible after the barriers below
         // radius about the centre and the largest gap between consecutive points, packed as (float bits << 32 | index): one max-reduction
         // (squared distances as floats: monotone, so the maxima are those of the distances; the two square roots are taken once, below)
         unsigned long long key = 0;
@@ -256,10 +269,11 @@ __global__ void __launch_bounds__(128, 6) k_tile_split(DevBasis B, const double 
         e.imax = (int)(gap & 0xffffffffu);
         tg.rho = (double)e.rho; tg.pad_ = 0.0;
         // active slots (atom runs aligned), atoms, functions
+        const TileFrame fr = tile_frame(tg);
+        int c0 = 0, c1 = 0, c2 = 0;
         for (int base = wid * 32; base < B.natoms; base += 128)
-            for_active_atoms(B, base, tg, sx + a, sy + a, sz + a, b - a, [&](int, int, int nfun) {
-                if (lane == 0) { atomicAdd(&s_cnt[0], (nfun + al) & ~al); atomicAdd(&s_cnt[1], 1); atomicAdd(&s_cnt[2], nfun); }
-            });
+            for_active_atoms(B, base, tg, fr, fx + a, fy + a, fz + a, b - a, [&](int, int, int nfun) { c0 += (nfun + al) & ~al; c1 += 1; c2 += nfun; });
+        if (lane == 0 && c1) { atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); atomicAdd(&s_cnt[2], c2); }
         __syncthreads();
         e.nraw = s_cnt[0]; e.natom = s_cnt[1]; e.nreal = s_cnt[2];
         if (tid == 0) *dst = e;
@@ -482,21 +496,21 @@ __global__ void k_tile_gather(const TileDesc *__restrict__ desc, const int *__re
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nt) out[i] = desc[ord[i]];
 }
-// work items of sliced tiles: item i*S + s contracts columns [s*w, min(nn, (s+1)*w)) of tile i, w = the tile's columns / S rounded up to
-// SLICE_COLS; slices past the last column are empty (col1 <= col0: every role skips them)
-__global__ void k_tile_slices(const TileDesc *__restrict__ tiles, int nt, int S, TileDesc *__restrict__ items) {
+// work items of sliced tiles: item i*S + s contracts columns [s*w, min(nn, (s+1)*w)) of tile i, w = slice_width (kernels.cuh); slices
+// past the last column are empty (col1 <= col0: every role skips them)
+__global__ void k_tile_slices(const TileDesc *__restrict__ tiles, int nt, int S, long long item_cost, TileDesc *__restrict__ items) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nt * S) return;
     const int i = j / S, s = j - i * S;
     TileDesc td = tiles[i];
     if (td.nact == 0) { if (s) { td.col0 = 0; td.col1 = 0; td.part = j; } items[j] = td; return; }     // slice 0 stores the zeros, the others do nothing
-    const int w = ((td.nn + S - 1) / S + SLICE_COLS - 1) / SLICE_COLS * SLICE_COLS;
+    const int w = slice_width(td, S, item_cost);
     td.col0 = min(s * w, td.nn); td.col1 = min(td.nn, td.col0 + w); td.part = j;
     items[j] = td;
 }
-void launch_tile_slices(const TileDesc *tiles, int nt, int S, TileDesc *items, cudaStream_t s) {
+void launch_tile_slices(const TileDesc *tiles, int nt, int S, long long item_cost, TileDesc *items, cudaStream_t s) {
     if (nt <= 0) return;
-    k_tile_slices<<<(unsigned)((nt * S + 255) / 256), 256, 0, s>>>(tiles, nt, S, items);
+    k_tile_slices<<<(unsigned)((nt * S + 255) / 256), 256, 0, s>>>(tiles, nt, S, item_cost, items);
 }
 
 __global__ void k_perm_index(const int *__restrict__ perm, long n, long *__restrict__ index) {
@@ -597,6 +611,7 @@ __global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__r
     __shared__ int s_zero;            // a K slot whose panel rows are zero (padding), for the N-side padding columns
     const TileDesc td = tiles[blockIdx.x / Q];
     const int part = blockIdx.x % Q;
+    const int gy = blockIdx.y, G = gridDim.y;      // few tiles: the active atoms of a tile are dealt to G CTAs (launch_basis)
     if (td.nact == 0) return;
     const TileGeo tg = geo[td.geo];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -605,13 +620,20 @@ __global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__r
     const long plane = (long)td.nact * LDP;
 
     __shared__ double sx[MT], sy[MT], sz[MT];
-    for (int i = tid; i < MT; i += NT) { const long p = td.pt0 + (i < td.npts ? i : 0); sx[i] = rsx[p]; sy[i] = rsy[p]; sz[i] = rsz[p]; }
+    __shared__ float fx[MT], fy[MT], fz[MT];          // the same points relative to the tile centre (for_active_atoms)
+    const TileFrame fr = tile_frame(tg);
+    for (int i = tid; i < MT; i += NT) {
+        const long p = td.pt0 + (i < td.npts ? i : 0);
+        const double x = rsx[p], y = rsy[p], z = rsz[p];
+        sx[i] = x; sy[i] = y; sz[i] = z;
+        fx[i] = __double2float_rn(x - fr.cx); fy[i] = __double2float_rn(y - fr.cy); fz[i] = __double2float_rn(z - fr.cz);
+    }
     if (tid == 0) { s_base[0] = 0; s_base[1] = 0; s_base[2] = 0; s_zero = td.nraw < td.nact ? td.nraw : 0x7fffffff; }
     for (int a = tid; a < B.natoms; a += NT) s_atom[a] = 0;
     __syncthreads();
     // phase A1: active prefix of every atom (same arithmetic as k_tile_split => the counts the descriptors were sized with)
     for (int base = wid * 32; base < B.natoms; base += NT)
-        for_active_atoms(B, base, tg, sx, sy, sz, td.npts, [&](int aa, int nsh, int nfun) { if (lane == 0) s_atom[aa] = (nsh << 20) | nfun; });
+        for_active_atoms(B, base, tg, fr, fx, fy, fz, td.npts, [&](int aa, int nsh, int nfun) { if (lane == 0) s_atom[aa] = (nsh << 20) | nfun; });
     __syncthreads();
     const int al = B.slot_align - 1;
     for (int a0 = 0; a0 < B.natoms; a0 += NT) {
@@ -640,7 +662,8 @@ __global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__r
     const int nruns = s_base[1];
     // slot -> internal function index; pad slots point at a valid function (their Phi is zero)
     int *nlist = fidx + td.nact;   // N column -> K slot
-    for (int rn = 0; rn < nruns && part == 0; ++rn) {
+    const bool lists = part == 0 && gy == 0;       // one CTA of the tile writes the index lists and the atom table
+    for (int rn = 0; rn < nruns && lists; ++rn) {
         int a = s_runs[4 * rn], nsh = s_runs[4 * rn + 1], slot0 = s_runs[4 * rn + 2], col0 = s_runs[4 * rn + 3];
         int f0 = B.atom_func_off[a];
         int s_last = B.atom_shell_off[a] + nsh - 1, ll = B.sh_l[s_last];
@@ -648,10 +671,10 @@ __global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__r
         for (int c = tid; c < nslot; c += NT) fidx[slot0 + c] = f0 + (c < nfun ? c : 0);
         for (int c = tid; c < nfun; c += NT) nlist[col0 + c] = slot0 + c;
     }
-    for (int c = td.nraw + tid; c < td.nact && part == 0; c += NT) fidx[c] = 0;
-    for (int c = td.nreal + tid; c < td.nn && part == 0; c += NT) nlist[c] = s_zero;   // nn > nreal implies that a padding slot exists
+    for (int c = td.nraw + tid; c < td.nact && lists; c += NT) fidx[c] = 0;
+    for (int c = td.nreal + tid; c < td.nn && lists; c += NT) nlist[c] = s_zero;   // nn > nreal implies that a padding slot exists
     // atom table for the GIAO taps of k_jtensor (see TileAtom)
-    if (atab_pool && part == 0) {
+    if (atab_pool && lists) {
         TileAtom *atab = atab_pool + td.atab_off;
         const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
         for (int rn = tid; rn < nruns; rn += NT) {
@@ -672,7 +695,7 @@ __global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__r
     const double x = rsx[pt], y = rsy[pt], z = rsz[pt];
     const bool tm = B.turbomole != 0;
 
-    for (int rn = 0; rn < nruns; ++rn) {
+    for (int rn = gy; rn < nruns; rn += G) {
         const int a = s_runs[4 * rn], nsh = s_runs[4 * rn + 1], slot0 = s_runs[4 * rn + 2];
         const double rx = x - B.atom_xyz[3 * a], ry = y - B.atom_xyz[3 * a + 1], rz = z - B.atom_xyz[3 * a + 2];
         const double r2 = rx * rx + ry * ry + rz * rz;
@@ -709,7 +732,7 @@ __global__ void __launch_bounds__(NT, 5) k_basis(DevBasis B, const TileDesc *__r
             }
         }
     }
-    for (int c = td.nraw; c < td.nact; ++c) {
+    for (int c = td.nraw; c < td.nact && gy == 0; ++c) {
         const long o = (long)c * LDP + row;
         panel[o] = 0.0; panel[plane + o] = 0.0; panel[2 * plane + o] = 0.0; panel[3 * plane + o] = 0.0;
     }
@@ -784,7 +807,12 @@ void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_
     if (ntiles <= 0) return;
     size_t smem = ((size_t)B.natoms + (size_t)4 * (max_nruns > 0 ? max_nruns : 1)) * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_basis<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
-    k_basis<128><<<ntiles, 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
+    // one CTA per tile evaluates ~nact functions per thread one after the other: with fewer tiles than SMs (a plane of an integral)
+    // the atoms of a tile are dealt to G CTAs instead, two CTAs' worth of work per SM (36x36 plane: 424 us with 15 CTAs)
+    int nsm = 148, dev = 0;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int G = ntiles >= nsm ? 1 : std::min(16, (2 * nsm + ntiles - 1) / ntiles);
+    k_basis<128><<<dim3((unsigned)ntiles, (unsigned)G), 128, smem, s>>>(B, tiles, geo, rsx, rsy, rsz, panel_pool, fidx_pool, atab_pool);
 }
 
 }  // namespace gb

@@ -133,8 +133,29 @@ void launch_jtensor(const JtensorArgs &a, bool giao, int nsm, cudaStream_t s);
 constexpr int PART_LD = 13;          // doubles per row of a partial block
 constexpr int SLICE_COLS = 32;       // slice boundaries are multiples of this many columns (the widest nu chunk of the kernels)
 bool jtensor_supports_slices();      // the epilogue-warpgroup kernels do; the round-1 mapping (GIMIC_B200_EPI=0) does not
-void launch_tile_slices(const TileDesc *tiles, int nt, int S, TileDesc *items, cudaStream_t s);
-void launch_slice_reduce(const JtensorArgs &a, const TileDesc *tiles, int nt, int S, bool giao, cudaStream_t s);
+// what a tile costs the contraction (one DMMA column step = 1): MMA k-steps x columns (4 planes) + GIAO taps + the tile's share of
+// k_basis + a fixed part.  A tile costs the same whether its 128 rows are all points or not: letting the consumer warps without
+// valid rows skip their MMAs was measured (round 2, calls L/M) -- the extra branch cost the full-tile loop 4.5 % and a 36x36 plane
+// gained nothing.
+__host__ __device__ inline long long piece_cost(int npts, int nraw, int nreal, int natom) {
+    const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
+    (void)npts;
+    return 4LL * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
+}
+// Column slices of a tile (few tiles in the whole point set): a tile gets as many slices as its cost holds `item_cost` units, at most
+// S (the item slots per tile) and at most one per SLICE_COLS columns -- every work item then costs about the same, whatever the
+// spread of active-set sizes between the tiles.  Returns the slice width in columns; slice s covers [s*w, min(nn, (s+1)*w)).
+__host__ __device__ inline int slice_width(const TileDesc &td, int S, long long item_cost) {
+    const long long c = piece_cost(td.npts, td.nraw, td.nreal, td.nruns);
+    long long k = (c + item_cost - 1) / item_cost;
+    const int kmax = td.nn / SLICE_COLS > 1 ? td.nn / SLICE_COLS : 1;
+    if (k > S) k = S;
+    if (k > kmax) k = kmax;
+    if (k < 1) k = 1;
+    return ((td.nn + (int)k - 1) / (int)k + SLICE_COLS - 1) / SLICE_COLS * SLICE_COLS;
+}
+void launch_tile_slices(const TileDesc *tiles, int nt, int S, long long item_cost, TileDesc *items, cudaStream_t s);
+void launch_slice_reduce(const JtensorArgs &a, const TileDesc *tiles, int nt, int S, long long item_cost, bool giao, cudaStream_t s);
 size_t jtensor_smem_bytes();
 
 void launch_build_operand(double *out, int nbf, int ldb, long long plane_stride, const double *srcA, const double *srcB, double signB,

@@ -41,15 +41,18 @@ void emulate_gather_points(void **a) {              // k_gather_points(r, perm, 
 }
 // ---- the device-side tile plan (k_prepare.cu), restated serially: the semantic model the CUDA kernels are written against ----------
 struct Piece { gb::TileGeo tg; float rho, gmax; int imax, nraw, natom, nreal; };
+// double -> float rounded toward -inf (__double2float_rd)
+float f_rd(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; }
 Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, const double *sz, long p0, int npts) {
     Piece P{};
-    gb::TileGeo tg{1e300, 1e300, 1e300, -1e300, -1e300, -1e300, 0.0, 0.0};
+    // bounding box in single precision, rounded outwards (the kernel reduces floats: lo = min rd(x), hi = -min rd(-x))
+    float lo[3] = {3e38f, 3e38f, 3e38f}, nhi[3] = {3e38f, 3e38f, 3e38f};
     for (int p = 0; p < npts; ++p) {
         const long q = p0 + p;
-        tg.lox = std::fmin(tg.lox, sx[q]); tg.hix = std::fmax(tg.hix, sx[q]);
-        tg.loy = std::fmin(tg.loy, sy[q]); tg.hiy = std::fmax(tg.hiy, sy[q]);
-        tg.loz = std::fmin(tg.loz, sz[q]); tg.hiz = std::fmax(tg.hiz, sz[q]);
+        const double c[3] = {sx[q], sy[q], sz[q]};
+        for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], f_rd(c[k])); nhi[k] = std::fmin(nhi[k], f_rd(-c[k])); }
     }
+    gb::TileGeo tg{lo[0], lo[1], lo[2], -(double)nhi[0], -(double)nhi[1], -(double)nhi[2], 0.0, 0.0};
     const double cx = 0.5 * (tg.lox + tg.hix), cy = 0.5 * (tg.loy + tg.hiy), cz = 0.5 * (tg.loz + tg.hiz);
     float rho = 0.f, gmax = 0.f; int imax = 0;
     for (int p = 0; p < npts; ++p) {
@@ -68,11 +71,16 @@ Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, cons
         const double dx = std::fmax(std::fmax(tg.lox - x, x - tg.hix), 0.0), dy = std::fmax(std::fmax(tg.loy - y, y - tg.hiy), 0.0),
                      dz = std::fmax(std::fmax(tg.loz - z, z - tg.hiz), 0.0);
         if (dx * dx + dy * dy + dz * dz > B.atom_maxthr2e[at]) continue;
-        double d2 = 1e300;
+        // minimum squared distance in single precision about the tile centre, turned into a lower bound (for_active_atoms, k_prepare.cu)
+        const float ax = (float)(x - cx), ay = (float)(y - cy), az = (float)(z - cz);
+        float m = 3e38f;
         for (int p = 0; p < npts; ++p) {
             const long q = p0 + p;
-            d2 = std::fmin(d2, (sx[q] - x) * (sx[q] - x) + (sy[q] - y) * (sy[q] - y) + (sz[q] - z) * (sz[q] - z));
+            const float ex = (float)(sx[q] - cx) - ax, ey = (float)(sy[q] - cy) - ay, ez = (float)(sz[q] - cz) - az;
+            m = std::fmin(m, std::fmaf(ez, ez, std::fmaf(ey, ey, ex * ex)));
         }
+        const double dd = std::sqrt((double)m), D = 2.5e-7 * (2.0 * rho + dd), slack = 3.0e-7 * m + D * D + 2.0 * dd * D;
+        const double d2 = std::fmax((double)m - 1.0101 * slack, 0.0);
         if (d2 > B.atom_maxthr2e[at]) continue;
         int nfun = 0;
         for (int s = B.atom_shell_off[at]; s < B.atom_shell_off[at + 1] && B.sh_thr2e[s] >= d2; ++s) nfun += (B.sh_l[s] + 1) * (B.sh_l[s] + 2) / 2;
@@ -81,11 +89,7 @@ Piece eval_piece(const gb::DevBasis &B, const double *sx, const double *sy, cons
     P.tg = tg; P.rho = rho; P.gmax = gmax; P.imax = imax;
     return P;
 }
-long long piece_cost(int npts, int nraw, int nreal, int natom) {
-    const long long nact = (nraw + 7) & ~7, nn = (nreal + 7) & ~7;
-    (void)npts;
-    return 4LL * nact * nn + 3LL * nn * natom + 110LL * nact + (nact ? 8192 : 256);
-}
+using gb::piece_cost;      // kernels.cuh
 void split_piece(const gb::DevBasis &B, const double *sx, const double *sy, const double *sz, long p0, int npts, int depth, double split_radius,
                  long run, int &emitted, int pending, gb::TileSeg *seg, gb::TileGeo *geo, gb::TileInfo *info) {
     const Piece P = eval_piece(B, sx, sy, sz, p0, npts);
