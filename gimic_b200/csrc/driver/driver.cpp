@@ -242,8 +242,8 @@ class Run {
             if (summary[3]) out.say("INFO: Reordering densities [TURBOMOLE]");
         }
         for (const std::string &line : grid.log) out.raw(line + "\n");
-        write_mol_xyz(join_path(workdir, "mol.xyz"), symbols, xyz);
-        write_grid_xyz(join_path(workdir, "grid.xyz"), grid, symbols, xyz);
+        if (root()) write_mol_xyz(join_path(workdir, "mol.xyz"), symbols, xyz);
+        if (root()) write_grid_xyz(join_path(workdir, "grid.xyz"), grid, symbols, xyz);
         out.say("*** Grid plot in grid.xyz");
         field_line();
         out.say(std::string("INFO: ") + (uhf ? "Open-shell calculation" : "Closed-shell calculation"));
@@ -266,9 +266,18 @@ class Run {
     // Runs fn(handle, device index, lo, hi) for one contiguous slab of range(n) per device, each on its own host thread (the C ABI is thread-safe
     // per handle, errors are thread-local).  Slabs are the block partition of schedule() (parallel.F90:66-84); outputs go to
     // disjoint parts of caller-owned host arrays, so the devices exchange nothing.
+    // One process per GPU (opt.nranks > 1): this rank's slab only, as device 0; the caller completes the result with a collective.
     template <class Fn>
-    void over_devices(long n, Fn fn) const {
+    void over_devices(long n, Fn fn, long *my_lo = nullptr, long *my_hi = nullptr) const {
         const size_t nd = 1 + peers.size();
+        if (my_lo) { *my_lo = 0; *my_hi = n; }
+        if (ranked()) {
+            const long base = n / opt.nranks, rem = n % opt.nranks;
+            const long lo = opt.rank * base + std::min<long>(opt.rank, rem), hi = lo + base + (opt.rank < rem ? 1 : 0);
+            if (my_lo) { *my_lo = lo; *my_hi = hi; }
+            if (hi > lo) check(fn(ctx->h, (size_t)0, lo, hi));
+            return;
+        }
         if (nd == 1) { check(fn(ctx->h, (size_t)0, 0L, n)); return; }
         std::vector<std::string> errs(nd);
         std::vector<std::thread> th;
@@ -286,9 +295,31 @@ class Run {
     // Several devices: every device tiles the whole point set and evaluates its equal-COST share of the tiles (gimic_b200_partition_*;
     // the equal-count slabs of schedule() leave the devices far from the molecule idle on a planar system); the rows come back with
     // their point indices and are scattered into the caller's arrays -- disjoint index sets, so the host threads exchange nothing.
+    bool ranked() const { return opt.nranks > 1; }
+    bool root() const { return opt.rank == 0; }
+    // rows [index[i]] of a [n][ncols] array are this rank's: complete `full` on every rank
+    void gather_rows(long n, int ncols, const std::vector<long> &index, const std::vector<double> &rows, double *full) const {
+        if (!opt.allgather_rows) throw DriverError("a run over several processes needs the allgather_rows callback (gimic_b200_run_opts)");
+        if (opt.allgather_rows(opt.user, n, ncols, (long)index.size(), index.data(), rows.data(), full) < 0)
+            throw DriverError("the launcher's allgather_rows callback failed");
+    }
     void partitioned(const double *rp, long n, const gimic_b200_grid *g, int spincase, double *tens, double *jvec, double *jmod, double *edens) const {
         const size_t nd = 1 + peers.size();
         const double *B = magnet.data();
+        if (ranked()) {
+            long cnt = 0;
+            check(g ? gimic_b200_partition_grid(ctx->h, g, opt.rank, opt.nranks, &cnt) : gimic_b200_partition_points(ctx->h, n, rp, 0, opt.rank, opt.nranks, &cnt));
+            std::vector<long> idx((size_t)cnt);
+            std::vector<double> t(tens ? (size_t)cnt * 9 : 0), v(jvec ? (size_t)cnt * 3 : 0), m(jmod ? (size_t)cnt : 0), e(edens ? (size_t)cnt : 0);
+            if (cnt > 0)
+                check(gimic_b200_partition_calc(ctx->h, B, spincase, idx.data(), tens ? t.data() : nullptr, jvec ? v.data() : nullptr, jmod ? m.data() : nullptr,
+                                                nullptr, edens ? e.data() : nullptr, 0));
+            if (tens) gather_rows(n, 9, idx, t, tens);
+            if (jvec) gather_rows(n, 3, idx, v, jvec);
+            if (jmod) gather_rows(n, 1, idx, m, jmod);
+            if (edens) gather_rows(n, 1, idx, e, edens);
+            return;
+        }
         std::vector<std::string> errs(nd);
         std::vector<std::thread> th;
         for (size_t d = 0; d < nd; ++d) {
@@ -322,11 +353,11 @@ class Run {
         double *tp = t.data();
         if (grid.is_file()) {
             const double *xp = grid.xdata.data();
-            if (peers.empty()) check(gimic_b200_calc_jtensors(ctx->h, n, xp, spincase, tp, 0));
+            if (peers.empty() && !ranked()) check(gimic_b200_calc_jtensors(ctx->h, n, xp, spincase, tp, 0));
             else partitioned(xp, n, nullptr, spincase, tp, nullptr, nullptr, nullptr);
         } else {
             const gimic_b200_grid g = grid.cstruct();
-            if (peers.empty()) check(gimic_b200_calc_jtensors_grid(ctx->h, &g, 0, n, spincase, tp, 0));
+            if (peers.empty() && !ranked()) check(gimic_b200_calc_jtensors_grid(ctx->h, &g, 0, n, spincase, tp, 0));
             else partitioned(nullptr, n, &g, spincase, tp, nullptr, nullptr, nullptr);
         }
         return t;
@@ -335,11 +366,19 @@ class Run {
     // J (and signed |J|, rho, div J) straight from the contraction; div J (central differences, 6 more passes) keeps the slab split
     void point_fields(const std::vector<double> &r, int spincase, double *jvec, double *jmod, double *edens, double *divj) const {
         const double *rp = r.data(), *B = magnet.data();
-        if (!peers.empty() && !divj) { partitioned(rp, (long)r.size() / 3, nullptr, spincase, nullptr, jvec, jmod, edens); return; }
-        over_devices((long)r.size() / 3, [=](gimic_b200_handle h, size_t, long lo, long hi) {
+        if ((!peers.empty() || ranked()) && !divj) { partitioned(rp, (long)r.size() / 3, nullptr, spincase, nullptr, jvec, jmod, edens); return; }
+        const long n = (long)r.size() / 3;
+        long lo = 0, hi = n;
+        over_devices(n, [=](gimic_b200_handle h, size_t, long lo, long hi) {
             return gimic_b200_calc_fields(h, hi - lo, rp + 3 * lo, B, spincase, nullptr, jvec ? jvec + 3 * lo : nullptr, jmod ? jmod + lo : nullptr, nullptr,
                                           edens ? edens + lo : nullptr, divj ? divj + lo : nullptr, 1e-3, 0);
-        });
+        }, &lo, &hi);
+        if (ranked()) {            // every rank filled its slab of the arrays in place: exchange the slabs
+            std::vector<long> idx((size_t)(hi - lo));
+            for (long i = lo; i < hi; ++i) idx[(size_t)(i - lo)] = i;
+            auto slab = [&](double *a, int nc) { if (a) { const std::vector<double> mine(a + nc * lo, a + nc * hi); gather_rows(n, nc, idx, mine, a); } };
+            slab(jvec, 3); slab(jmod, 1); slab(edens, 1); slab(divj, 1);
+        }
     }
 
     static std::vector<double> combine(const std::vector<double> &a, const std::vector<double> &b, double sign) {
@@ -401,17 +440,17 @@ class Run {
             out.raw(" magnetic field\n" + ld_real(magnet[0]) + ld_real(magnet[1]) + ld_real(magnet[2]) + "\n \n");
             const bool regular = grid.mode == "std" || grid.mode == "base" || grid.mode == "bond";
             if (grid.gauss && !grid.is_file())
-                write_jmod_txt(join_path(workdir, "jmod" + tag + ".txt"), grid, jv, regular && (grid.mode == "bond" || grid.gtype == "even"));
+                if (root()) write_jmod_txt(join_path(workdir, "jmod" + tag + ".txt"), grid, jv, regular && (grid.mode == "bond" || grid.gtype == "even"));
             if (grid.is_3d()) {
-                if (inp.flag("Essential.acid")) write_vti_scalar(join_path(workdir, "acid.vti"), grid, acid, opt.vtk_appended);
-                if (inp.flag("Essential.jmod")) write_vti_scalar(join_path(workdir, "jmod" + tag + ".vti"), grid, jmod, opt.vtk_appended);
+                if (root() && inp.flag("Essential.acid")) write_vti_scalar(join_path(workdir, "acid.vti"), grid, acid, opt.vtk_appended);
+                if (root() && inp.flag("Essential.jmod")) write_vti_scalar(join_path(workdir, "jmod" + tag + ".vti"), grid, jmod, opt.vtk_appended);
             }
             if (prop) run_property(tens);
             if (regular && grid.gtype == "even") {
-                write_vti_vector(join_path(workdir, "jvec" + tag + ".vti"), grid, radius_masked_vectors(grid, jv), opt.vtk_appended);
+                if (root()) write_vti_vector(join_path(workdir, "jvec" + tag + ".vti"), grid, radius_masked_vectors(grid, jv), opt.vtk_appended);
             } else if (((grid.mode == "std" || grid.mode == "base") && grid.gauss) || grid.is_file()) {
                 const std::string ele = join_path(workdir, "grid.1.ele");
-                if (file_exists(ele)) write_vtu(join_path(workdir, "jvec.vtu"), r, "vectors", 3, jv, read_ele(ele));
+                if (root() && file_exists(ele)) write_vtu(join_path(workdir, "jvec.vtu"), r, "vectors", 3, jv, read_ele(ele));
                 else out.raw(" not writing a vtu file, because the file grid.1.ele was not found.\n");
             }
         }
@@ -470,7 +509,7 @@ class Run {
             const int cols[4] = {3, 0, 1, 2};
             for (int q = 0; q < 4; ++q) {
                 for (long i = 0; i < n; ++i) col[(size_t)i] = f4[4 * (size_t)i + cols[q]];
-                write_vtu(join_path(workdir, names[(size_t)q]), grd, "scalars", 1, col, cells);
+                if (root()) write_vtu(join_path(workdir, names[(size_t)q]), grd, "scalars", 1, col, cells);
             }
         };
         // write(*,*) " " before the shielding tables, write(*,*) "" before the chi table (jfield.f90:762,890)
@@ -547,6 +586,10 @@ class Run {
                 });
                 Sums s = part[0];
                 for (size_t d = 1; d < nd; ++d) for (int k = 0; k < 7; ++k) s[(size_t)k] += part[d][(size_t)k];
+                if (ranked()) {
+                    if (!opt.allreduce_sum) throw DriverError("a run over several processes needs the allreduce_sum callback (gimic_b200_run_opts)");
+                    if (opt.allreduce_sum(opt.user, s.data(), 7) < 0) throw DriverError("the launcher's allreduce_sum callback failed");
+                }
                 results[sc] = s;
             }
         }
@@ -609,6 +652,7 @@ class Run {
         std::vector<double> v((size_t)n, 0.0);
         const bool ed = calc == "edens";
         point_fields(r, GIMIC_B200_TOTAL, nullptr, nullptr, ed ? v.data() : nullptr, ed ? nullptr : v.data());
+        if (!root()) return;
         if (!grid.is_file() && grid.gtype == "even" && grid.npts[0] > 1 && grid.npts[1] > 1)
             write_vti_scalar(join_path(workdir, calc + ".vti"), grid, v, opt.vtk_appended);
         else
@@ -865,13 +909,21 @@ int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts) {
     if (!o.devices.empty()) o.device = o.devices[0];
     if (d.title) o.title = d.title;
     if (d.workdir) o.workdir = d.workdir;
+    if (d.nranks > 1) {
+        if (d.rank < 0 || d.rank >= d.nranks) { gbd::g_error = "bad argument: rank outside [0, nranks)"; return GIMIC_B200_EINVAL; }
+        if (!o.devices.empty() && o.devices.size() > 1) { gbd::g_error = "bad argument: a rank of a multi-process run drives one device"; return GIMIC_B200_EINVAL; }
+        if (!o.dryrun && (!d.allgather_rows || !d.allreduce_sum)) { gbd::g_error = "bad argument: nranks > 1 needs both collective callbacks"; return GIMIC_B200_EINVAL; }
+        o.devices.clear();
+        o.rank = d.rank; o.nranks = d.nranks; o.allgather_rows = d.allgather_rows; o.allreduce_sum = d.allreduce_sum; o.user = d.user;
+    }
     FILE *out = stdout;
-    if (d.report_path) {
-        out = std::fopen(d.report_path, "w");
-        if (!out) { gbd::g_error = std::string("cannot write ") + d.report_path; return GIMIC_B200_EIO; }
+    const char *report = o.rank > 0 ? "/dev/null" : d.report_path;       // rank 0 alone reports
+    if (report) {
+        out = std::fopen(report, "w");
+        if (!out) { gbd::g_error = std::string("cannot write ") + report; return GIMIC_B200_EIO; }
     }
     const int rc = gbd::run_input(inpfile, o, out);
-    if (d.report_path) std::fclose(out); else std::fflush(out);
+    if (report) std::fclose(out); else std::fflush(out);
     return rc;
 }
 

@@ -139,6 +139,11 @@ struct RunOptions {
     std::vector<int> devices;    // more than one entry: single-process multi-device run (one context per listed GPU, one host
                                  // thread each); point slabs / plane rows are split like schedule() of parallel.F90:66-84
     std::string workdir;         // default: the directory of the input file
+    // one process per GPU (gimic_b200_run_opts::rank / nranks): the two collectives of the run, supplied by the launcher
+    int rank = 0, nranks = 1;
+    int (*allgather_rows)(void *user, long n_total, int ncols, long count, const long *index, const double *rows, double *full) = nullptr;
+    int (*allreduce_sum)(void *user, double *v, int n) = nullptr;
+    void *user = nullptr;
 };
 
 // one gimic.inp: returns 0 or a negative GIMIC_B200_E* code (message from last_error_message())

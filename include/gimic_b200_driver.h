@@ -38,8 +38,8 @@ int gimic_b200_run_input(const char *inpfile, const char *workdir, int device, i
  *   ndevices > 0 (list in `devices`) or ndevices < 0 (every GPU of the node): the run uses several GPUs from ONE process -- a
  *   context per device (densities replicated), one host thread each; cdens splits the flat point index into contiguous slabs,
  *   integral mode splits the plane rows j -- the block partition of schedule() (src/fgimic/parallel.F90:66-84) -- and the <= 7
- *   partial sums are added on the host in device order.  Nothing is exchanged between the devices.  (The torchrun entry
- *   `python -m gimic_b200` is the one-process-per-GPU form of the same partition, with an NCCL all-reduce for the integrals.)
+ *   partial sums are added on the host in device order.  Nothing is exchanged between the devices.  (rank / nranks below are
+ *   the one-process-per-GPU form of the same run: `python -m gimic_b200` under torchrun, collectives over NCCL.)
  *   title: the -t switch of the front end (src/gimic.in:135-136), overrides the `title` keyword. */
 typedef struct {
     int flags;                /* GIMIC_B200_RUN_* */
@@ -49,6 +49,17 @@ typedef struct {
     const char *workdir;      /* NULL: the directory of the input file */
     const char *title;        /* NULL: the `title` keyword */
     const char *report_path;  /* NULL: the report goes to stdout */
+    /* nranks > 1: this process is rank `rank` of `nranks` cooperating processes, one per GPU (torchrun; `python -m gimic_b200` fills
+     * these in).  Every rank parses the input and builds its own context; cdens / edens evaluate the rank's equal-COST share of
+     * the tiles (gimic_b200_partition_*), div J its slab of points, integral mode its slab of plane rows (schedule(),
+     * parallel.F90:66-84).  The two callbacks are the only communication: allgather_rows completes a [n_total][ncols] array of
+     * which this rank holds `count` rows (row numbers in `index`, values in `rows`) on every rank; allreduce_sum adds v[0..n) over
+     * the ranks (the collect_sum of integral.f90:157-161).  Both return 0 or a negative code.  Rank 0 alone writes the report and
+     * the files (like the reference's MPI path, jfield.f90:90-137). */
+    int rank, nranks;
+    int (*allgather_rows)(void *user, long n_total, int ncols, long count, const long *index, const double *rows, double *full);
+    int (*allreduce_sum)(void *user, double *v, int n);
+    void *user;
 } gimic_b200_run_opts;
 int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts);
 

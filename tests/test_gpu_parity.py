@@ -515,7 +515,10 @@ def test_random_molecules_vs_oracle(gb, seed):
             assert_close(res["edens"], eo, what + " edens")
         Bf = np.array([0.3, -0.2, 0.9])
         # J = sum_b T(m,b) B_b cancels once more between the b terms: floor at 1e-2 of the point's tensor scale (1e-12 relative)
-        jerr = np.abs(g.fields(r, Bf, sc, jvec=True)["jvec"] - O.jvectors(to, Bf)) / (RTOL * np.maximum(np.abs(O.jvectors(to, Bf)), 1e-2 * scale) + ATOL)
+        jbound = RTOL * np.maximum(np.abs(O.jvectors(to, Bf)), 1e-2 * scale) + ATOL
+        if uhf and sc in ("total", "spindens"):      # the sum of the alpha and beta bounds, as for the tensor above
+            jbound = RTOL * (np.maximum(np.abs(O.jvectors(ta, Bf)), 1e-2 * sa) + np.maximum(np.abs(O.jvectors(tb, Bf)), 1e-2 * sb)) + ATOL
+        jerr = np.abs(g.fields(r, Bf, sc, jvec=True)["jvec"] - O.jvectors(to, Bf)) / jbound
         assert jerr.max() <= 1.0, f"{what} J path: {jerr.max():.3g}"
     g.close()
 
