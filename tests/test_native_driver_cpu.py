@@ -303,10 +303,11 @@ def test_multi_device_switch_without_gpus(D, tmp_path):
         for devs in ("all", "0,1"):
             q = subprocess.run([EXE, "--devices", devs, str(d / "gimic.inp")], capture_output=True, text=True, timeout=120)
             assert q.returncode == 1 and ("CUDA" in q.stderr or "cuda" in q.stderr) and "Induced current" not in q.stdout
-        class RunOpts(C.Structure):
-            _fields_ = [("flags", C.c_int), ("device", C.c_int), ("ndevices", C.c_int), ("devices", C.POINTER(C.c_int)), ("workdir", C.c_char_p),
-                        ("title", C.c_char_p), ("report_path", C.c_char_p)]
+        from gimic_b200.driver import RunOpts                  # gimic_b200_run_opts
         D.gimic_b200_run.argtypes = [C.c_char_p, C.POINTER(RunOpts)]
+        # a rank of a multi-process run without the two collective callbacks is a usage error, not a crash
+        o = RunOpts(flags=0, device=-1, rank=1, nranks=2, report_path=os.fsencode(tmp_path / "rep"))
+        assert D.gimic_b200_run(os.fsencode(d / "gimic.inp"), C.byref(o)) == -1 and b"callbacks" in D.gimic_b200_driver_last_error()
         o = RunOpts(flags=0, device=-1, ndevices=-1, report_path=os.fsencode(tmp_path / "rep"))
         assert D.gimic_b200_run(os.fsencode(d / "gimic.inp"), C.byref(o)) == -3          # GIMIC_B200_ECUDA
         o = RunOpts(flags=1, device=-1, ndevices=-1, title=b"via the struct", report_path=os.fsencode(tmp_path / "rep"))
