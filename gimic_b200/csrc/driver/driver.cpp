@@ -874,10 +874,52 @@ int write_field(const std::string &inpfile, const std::string &workdir_in, const
     });
 }
 
+// The grid and the field direction a gimic.inp describes (grid.f90 new_grid + magnet.f90 get_magnet), for a caller that feeds the
+// batched C ABI itself.  Host only.
+int input_grid(const std::string &inpfile, const std::string &workdir_in, gimic_b200_grid_info *info, double *pts, double *wgt, long cap) {
+    return guarded([&] {
+        const std::string workdir = workdir_in.empty() ? dirname_of(inpfile) : workdir_in;
+        const Input inp = parse_file(inpfile);
+        const std::string basis = inp.str("basis");
+        const std::string mol = (!basis.empty() && basis[0] == '/') ? basis : join_path(workdir, basis);
+        const int natoms = gimic_b200_mol_geometry(mol.c_str(), 0, nullptr, nullptr);
+        check(natoms);
+        std::vector<double> xyz((size_t)natoms * 3, 0.0);
+        check(gimic_b200_mol_geometry(mol.c_str(), natoms, xyz.data(), nullptr));
+        const GridSpec grid = grid_from_input(inp, xyz, workdir);
+        const Vec3 b = get_magnet(grid, inp.str("magnet_axis"), inp.vec3("magnet"));
+        std::memset(info, 0, sizeof *info);
+        info->is_file = grid.is_file() ? 1 : 0;
+        info->npoints = grid.n();
+        for (int k = 0; k < 3; ++k) {
+            info->npts[k] = grid.npts[k]; info->origin[k] = grid.origin[(size_t)k]; info->magnet[k] = b[(size_t)k];
+            info->lengths[k] = grid.lengths[(size_t)k]; info->center_bond[k] = grid.center_bond[(size_t)k];
+            for (int c = 0; c < 3; ++c) info->basv[3 * k + c] = grid.basv[k][c];
+        }
+        info->radius = grid.radius; info->has_center_bond = grid.has_center_bond ? 1 : 0;
+        // axis coordinates and weights one axis after the other (npts[0] + npts[1] + npts[2] values each); file grids: the 3 x n points in pts
+        const long need = grid.is_file() ? 3 * grid.n() : (long)grid.npts[0] + grid.npts[1] + grid.npts[2];
+        if (pts || wgt) {
+            if (cap < need) throw DriverError("input_grid: room for " + std::to_string(cap) + " values, the grid needs " + std::to_string(need));
+            if (grid.is_file()) { if (pts) std::copy(grid.xdata.begin(), grid.xdata.end(), pts); }
+            else {
+                long o = 0;
+                for (int k = 0; k < 3; ++k)
+                    for (int i = 0; i < grid.npts[k]; ++i, ++o) { if (pts) pts[o] = grid.pts[k][(size_t)i]; if (wgt) wgt[o] = grid.wgt[k][(size_t)i]; }
+            }
+        }
+    });
+}
+
 }  // namespace gbd
 
 // ------------------------------------------------------------------------------------------------------- C ABI
 extern "C" {
+
+int gimic_b200_input_grid(const char *inpfile, const char *workdir, gimic_b200_grid_info *info, double *pts, double *wgt, long cap) {
+    if (!inpfile || !info) { gbd::g_error = "null argument"; return GIMIC_B200_EINVAL; }
+    return gbd::input_grid(inpfile, workdir ? workdir : "", info, pts, wgt, cap);
+}
 
 int gimic_b200_run(const char *inpfile, const gimic_b200_run_opts *opts);
 

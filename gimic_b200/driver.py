@@ -37,7 +37,7 @@ def driver_lib():
     global _D
     if _D is None:
         _lib.lib()                                                   # libgimic_b200.so first (RTLD_GLOBAL): the driver links against it
-        D = C.CDLL(os.path.join(os.path.dirname(_lib.SO_PATH), "libgimic_b200_driver.so"))
+        D = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgimic_b200_driver.so"))
         D.gimic_b200_driver_last_error.restype = C.c_char_p
         D.gimic_b200_run.argtypes = [C.c_char_p, C.POINTER(RunOpts)]
         D.gimic_b200_run_scan.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int]
@@ -157,6 +157,43 @@ class Driver:
 def run_scan(infiles, device=-1):
     """a current-profile scan: reports go to <input stem>.out, the table to current_profile.dat (gimic_b200_run_scan)"""
     return run(list(infiles), device=device)
+
+
+class GridInfo(C.Structure):
+    """gimic_b200_grid_info, include/gimic_b200_driver.h"""
+    _fields_ = [("is_file", C.c_int), ("npts", C.c_int * 3), ("npoints", C.c_long), ("origin", C.c_double * 3), ("basv", C.c_double * 9),
+                ("lengths", C.c_double * 3), ("magnet", C.c_double * 3), ("radius", C.c_double), ("has_center_bond", C.c_int),
+                ("center_bond", C.c_double * 3)]
+
+
+def input_grid(inpfile, workdir=None):
+    """The grid and field direction a gimic.inp describes (gimic_b200_input_grid; host only): (grid, magnet, info) with grid a
+    gimic_b200.Grid for std / base / bond grids or an (n, 3) array of points for Grid(file), magnet the unit field vector and info
+    the remaining GridInfo fields as a dict."""
+    from .gimic import Grid
+    D = driver_lib()
+    D.gimic_b200_input_grid.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(GridInfo), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long]
+    gi = GridInfo()
+    wd = os.fsencode(workdir) if workdir else None
+
+    def call(p, w, cap):
+        if D.gimic_b200_input_grid(os.fsencode(str(inpfile)), wd, C.byref(gi), p, w, cap) != 0:
+            raise RuntimeError("gimic_b200 driver error: " + D.gimic_b200_driver_last_error().decode(errors="replace"))
+    call(None, None, 0)
+    npts = tuple(gi.npts)
+    need = 3 * gi.npoints if gi.is_file else sum(npts)
+    pts, wgt = np.zeros(need), np.zeros(need)
+    dp = C.POINTER(C.c_double)
+    call(pts.ctypes.data_as(dp), wgt.ctypes.data_as(dp), need)
+    info = dict(is_file=bool(gi.is_file), npts=npts, npoints=int(gi.npoints), lengths=np.array(gi.lengths), radius=float(gi.radius),
+                center_bond=np.array(gi.center_bond) if gi.has_center_bond else None)
+    magnet = np.array(gi.magnet)
+    if gi.is_file:
+        return pts.reshape(-1, 3), magnet, info
+    cuts = np.cumsum((0,) + npts)
+    axes = [pts[cuts[k]:cuts[k + 1]] for k in range(3)]
+    weights = [wgt[cuts[k]:cuts[k + 1]] for k in range(3)]
+    return Grid(np.array(gi.origin), np.array(gi.basv).reshape(3, 3), axes, weights, radius=float(gi.radius)), magnet, info
 
 
 def mol_geometry(mol):

@@ -77,6 +77,25 @@ int gimic_b200_run_scan(int n, const char *const *inpfiles, int device, int flag
 int gimic_b200_write_field(const char *inpfile, const char *workdir, const char *kind, const double *data, long n,
                            const char *filename, int flags);
 
+/* The grid and the field direction that gimic.inp describes (grid.f90 new_grid: std / base / bond / file grids, even / gauss /
+ * lobatto axes, rotation; magnet.f90 get_magnet incl. the bond-grid default and the check_field reversal), for a caller that feeds
+ * the batched C ABI itself (gimic_b200_grid takes exactly these arrays).  Host only.  pts / wgt (each may be NULL) receive the axis
+ * coordinates and weights, axis 0 first (npts[0] + npts[1] + npts[2] values); for a file grid pts receives the 3 x npoints
+ * coordinates instead.  Call with pts = wgt = NULL first to size them. */
+typedef struct {
+    int is_file;              /* 1: Grid(file), explicit points */
+    int npts[3];
+    long npoints;
+    double origin[3];
+    double basv[9];           /* basv[3*v + c]: component c of basis vector v (orthonormal) */
+    double lengths[3];
+    double magnet[3];         /* unit vector of the external field */
+    double radius;            /* integration cut-off of bond grids (1e10: none), integral.f90:93 */
+    int has_center_bond;
+    double center_bond[3];
+} gimic_b200_grid_info;
+int gimic_b200_input_grid(const char *inpfile, const char *workdir, gimic_b200_grid_info *info, double *pts, double *wgt, long cap);
+
 /* Parse the text XDENS named in gimic.inp once (threaded) and write the binary cache <xdens>.bin beside it, sized from the input's
  * basis / openshell / Advanced.spherical settings; point `xdens=` at the .bin afterwards (gimic_b200_create recognises it).  Replaces
  * the 4 x nbf^2 (8 x for open shell) list-directed reads of read_dens (src/libgimic/dens.f90:56-135) on every later run.  Host only.

@@ -43,7 +43,6 @@ WRAPPER_SCRIPT = r'''
 import sys, numpy as np
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
 import gimic_b200, fixtures
-from gimic_b200 import grids
 mol, xd, molu, xdu = sys.argv[1:5]
 g = gimic_b200.Gimic(mol, xd, screening_thrs=1e-8)
 assert (g.nbf, g.natoms, g.uhf) == (168, 8, False)
@@ -60,7 +59,9 @@ assert g.fields_from_tensors(r, t, [0, 0, 1.0], jvec=True, jmod=True, acid=True)
 bf, dr = g.basis(r[:5])
 assert bf.shape == (5, 168) and dr.shape == (5, 3, 168) and g.jmod_from_jvec(r, f["jvec"], [0, 0, 1.0]).shape == (1000,)
 xyz = g.atom_coords()
-gr = grids.bond_grid(xyz[0], xyz[1], xyz[2], 1.0, [-2.0, 2.0], [-1.0, 3.0], "gauss", grid_points=[9, 9, 0], gauss_order=9)
+p0, w0, p1, w1 = np.zeros(9), np.zeros(9), np.zeros(9), np.zeros(9)
+gimic_b200.gausspoints(0.0, 4.0, 9, p0, w0); gimic_b200.gausspoints(0.0, 4.0, 9, p1, w1)
+gr = gimic_b200.Grid(xyz[0] - [2.0, 1.0, 0.0], np.eye(3), [p0, p1, np.zeros(1)], [w0, w1, np.ones(1)])      # a 9 x 9 Gauss plane
 assert g.integrate(gr, [0, 0, 1.0], "total", 7).shape == (7,) and g.integrate_batch([gr, gr, gr], [0, 0, 1.0]).shape == (3, 7)
 assert g.jtensors_grid(gr).shape == (81, 9) and g.jtensors_grid(gr, 10, 30).shape == (20, 9)
 res = g.property(r, np.full(1000, 0.01), t, xyz, [400, 600])

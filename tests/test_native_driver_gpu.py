@@ -1,6 +1,7 @@
-"""The native (C++) driver on the GPU: `gimic-b200 gimic.inp` must write the same report and the same files as the Python driver
-above the same C ABI -- which tests/test_gpu_driver.py pins against the reference's goldens and the oracle.  Runs last among the
-GPU tests (file name order)."""
+"""The `gimic-b200` program on the GPU: it must write the same report and the same files as the driver library called through the
+Python launcher (gimic_b200.driver.Driver -> gimic_b200_run), which tests/test_gpu_driver.py pins against the reference's goldens and
+the oracle; plus the reference's goldens straight from the program, the scan mode and the single-process multi-device partition.
+Runs last among the GPU tests (file name order)."""
 import filecmp
 import io
 import os
@@ -122,7 +123,7 @@ def test_native_open_shell_cases(tmp_path, cases):
 
 @pytest.mark.parametrize("inp_name", sorted(f[:-4] for f in os.listdir(INPUTS) if f.startswith("benzene_")))
 def test_native_every_benzene_input(tmp_path, cases, inp_name):
-    """all 19 test/benzene inputs (synthetic densities, nbf = 252): native == Python driver, incl. the ACID / tensor path, jmod.txt on
+    """all 19 test/benzene inputs (synthetic densities, nbf = 252): program == library entry, incl. the ACID / tensor path, jmod.txt on
     Gauss grids, rotation / radius / spacing keywords and the property report of the magnetizability input"""
     xd = tmp_path / "XDENS"
     fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))
@@ -161,9 +162,9 @@ def test_native_appended_vtk_and_scalar_modes(tmp_path, cases):
         assert os.path.exists(dn / f"{calc}.vti")
 
 
-def test_native_scan_equals_python_scan(tmp_path, cases):
+def test_native_scan_equals_launcher_scan(tmp_path, cases):
     """a current-profile scan: `gimic-b200 gimic.0.inp ... gimic.5.inp` (one context, one batched tensor pass) writes the same
-    gimic.N.out reports as the Python scan and as separate native runs"""
+    gimic.N.out reports as gimic_b200_run_scan through the Python launcher and as separate runs of the program"""
     from gimic_b200.driver import run_scan
     dn, dp = _pair(tmp_path, "c4h4_integration", cases["c4h4"]["mol"], cases["c4h4"]["xdens"])
     base = open(dn / "gimic.inp").read()

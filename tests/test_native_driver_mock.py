@@ -1,12 +1,13 @@
-"""End-to-end runs of the host-side layers above the C ABI in a container WITHOUT a GPU: the native C++ driver (gimic-b200) and the
-Python driver are pointed at a TEST DOUBLE of libgimic_b200.so (tests/mock_backend/mock_api.cpp, compiled into a temporary
+"""End-to-end runs of the host-side layers above the C ABI in a container WITHOUT a GPU: the compiled driver (the gimic-b200 program,
+and libgimic_b200_driver.so through the Python launcher) is pointed at a TEST DOUBLE of libgimic_b200.so (tests/mock_backend/mock_api.cpp, compiled into a temporary
 directory, never in-tree) whose compute entry points are answered by the CPU oracle.
 
-Checked here: (1) gimic-b200 writes byte-identical reports and files to the Python driver for every run mode (cdens closed / open
+Checked here: (1) the program and the launcher path write byte-identical reports and files for every run mode (cdens closed / open
 shell, ACID, property, integrals, edens / divj, scan, appended VTK); (2) the single-process multi-device partition (two host
 threads, two contexts) reproduces the single-device run; (3) native driver + oracle backend reproduce the reference's own golden
-outputs (c4h4 jvec.vtu at 10 digits, the integration stdout windows, the eight open-shell .vti files); (4) the Python driver under
-torch.distributed with two ranks over gloo (slab gather for cdens, all-reduce for integrals) writes what a single process writes.
+outputs (c4h4 jvec.vtu at 10 digits, the integration stdout windows, the eight open-shell .vti files); (4) the launcher under
+torch.distributed with two ranks over gloo (the driver's rank mode: row gather for cdens, all-reduce for integrals through the two
+callbacks of gimic_b200_run_opts) writes what a single process writes.
 This says nothing about the CUDA kernels: tests/test_gpu_*.py hold those to the oracle on a B200."""
 import filecmp
 import io
@@ -176,7 +177,7 @@ def test_open_shell_3d_native_vs_python_and_golden(mock_dir, tmp_path, cases):
 def test_benzene_modes_native_vs_python(mock_dir, tmp_path, cases):
     """benzene inputs with synthetic densities (nbf = 252) on shrunken grids: the ACID / tensor path (3d), a Gauss bond grid in cdens
     mode (jmod.txt), the radius / rotation keywords, and the magnetizability input with prop=on (report + integrand plots)"""
-    from gimic_b200.driver import read_mol_geometry
+    from gimic_b200.driver import mol_geometry as read_mol_geometry
     xd = tmp_path / "XDENS"
     fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))
     shrink3 = lambda t: re.sub(r"grid_points=\[\s*\d+\s*,\s*\d+\s*,\s*\d+\s*\]", "grid_points=[6,5,4]", t)
@@ -302,9 +303,10 @@ def _dist_worker(rank, world, port, so, inpfile, outfile):
 
 @pytest.mark.parametrize("case,name,edit", [("open_shell", "open-shell_3d", lambda t: t.replace("spacing=[0.5, 0.5, 0.5]", "spacing=[2.0, 2.0, 4.0]")),
                                             ("c4h4", "c4h4_integration", None), ("c4h4", "c4h4_read-grid", None)])
-def test_python_driver_world2_gloo_equals_single_process(mock_dir, tmp_path, cases, case, name, edit):
-    """`torchrun -m gimic_b200 gimic.inp` semantics with two ranks over gloo (CPU): cdens splits the flat point index into slabs and
-    gathers the tensors on rank 0 (jfield.f90:90-137), integral mode splits the plane rows and all-reduces the <= 7 sums
+def test_launcher_world2_gloo_equals_single_process(mock_dir, tmp_path, cases, case, name, edit):
+    """`torchrun -m gimic_b200 gimic.inp` semantics with two ranks over gloo (CPU): the compiled driver in rank mode (gimic_b200_run_opts
+    rank / nranks): cdens evaluates each rank's share of the partition and gathers the rows on rank 0 through the launcher's
+    allgather_rows callback (jfield.f90:90-137), integral mode splits the plane rows and adds the <= 7 sums through allreduce_sum
     (parallel.F90:66-84).  Rank 0 must write what a single process writes."""
     import torch.multiprocessing as mp
     gold = fixtures.golden_npz("c4h4_readgrid.npz")
@@ -374,7 +376,7 @@ def test_report_equals_the_reference_stdout_line_by_line(mock_dir, tmp_path, cas
     property run.  Same lines in the same order, identical text, identical LENGTH of every line (all formats are fixed-width).  For the two
     cases whose densities exist (c4h4, open-shell) every number must also agree within one unit of its last printed digit; the benzene
     densities are missing from the reference tree, so there the numbers come from synthetic densities and only the layout is compared."""
-    from gimic_b200.driver import read_mol_geometry
+    from gimic_b200.driver import mol_geometry as read_mol_geometry
     if case == "benzene":
         xd = tmp_path / "XDENS"
         fixtures.write_xdens(str(xd), fixtures.dens_to_colmajor(fixtures.synthetic_density(252, seed=21)))

@@ -72,11 +72,8 @@ res = {"natoms": a.natoms, "nbf": nbf, "grid": a.grid, "vtk": a.vtk, "xdens_text
        "write_xdens_s": t_x}
 for rep in range(2):
     t0 = time.perf_counter()
-    drv = Driver(os.path.join(d, "gimic.inp"), out=io.StringIO(), vtk_appended=(a.vtk == "appended"))
+    Driver(os.path.join(d, "gimic.inp"), out=io.StringIO(), vtk_appended=(a.vtk == "appended")).run()
     t1 = time.perf_counter()
-    drv.run()
-    t2 = time.perf_counter()
-    res[f"rep{rep}"] = {"setup_parse_upload_s": t1 - t0, "run_compute_and_write_s": t2 - t1}
-    drv.g.close()
+    res[f"rep{rep}"] = {"run_parse_upload_compute_write_s": t1 - t0}
 res["files_MB"] = {n: os.path.getsize(os.path.join(d, n)) / 1e6 for n in sorted(os.listdir(d)) if n.endswith(".vti")}
 print(json.dumps(res, indent=1))
