@@ -131,7 +131,7 @@ def test_native_every_benzene_input(tmp_path, cases, inp_name):
     def extra(d):
         if inp_name != "benzene_magnetizability":
             return
-        from gimic_b200.driver import read_mol_geometry
+        from gimic_b200.driver import mol_geometry as read_mol_geometry
         _, coords = read_mol_geometry(str(d / "MOL"))
         rng = np.random.default_rng(5)
         counts = rng.integers(60, 120, size=coords.shape[0])

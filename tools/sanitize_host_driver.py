@@ -45,7 +45,7 @@ def rg(d):
 
 
 def prop(d):
-    from gimic_b200.driver import read_mol_geometry
+    from gimic_b200.driver import mol_geometry as read_mol_geometry
     _, coords = read_mol_geometry(d + "/MOL")
     rng = np.random.default_rng(5); counts = rng.integers(4, 8, size=coords.shape[0])
     pts = np.vstack([coords[a] + rng.normal(scale=1.5, size=(c, 3)) for a, c in enumerate(counts)])
