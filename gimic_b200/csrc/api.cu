@@ -994,13 +994,22 @@ int integrate_many(gimic_b200_ctx *c, int ng, const gimic_b200_grid *grids, cons
             c->stats.launches += 1;
         }
     }
-    { Outputs o; o.tens = c->tens_tmp.as<double>(); if (int rc = run_tensors(c, (long)n, d_r, spincase, o)) return rc; }
+    // current and |J| only need J = T.B: when every plane has the same field direction the contraction forms it itself (operands
+    // (D, sum_b B_b P_b): half the planes, half the flops); the ACID integral needs the tensor
+    bool jpath = !(what & 4);
+    for (int g = 1; g < ng && jpath; ++g) for (int d = 0; d < 3; ++d) jpath = jpath && B3s[3 * g + d] == B3s[d];
+    {
+        Outputs o;
+        if (jpath) { o.jvec = c->tens_tmp.as<double>(); o.B3 = B3s; o.jpath = true; } else o.tens = c->tens_tmp.as<double>();
+        if (int rc = run_tensors(c, (long)n, d_r, spincase, o)) return rc;
+    }
     for (int g = 0; g < ng; ++g) {
         const gimic_b200_grid &G = grids[g];
         const int p1 = G.npts[0], p2 = G.npts[1], nrows = (int)(rowoff[g + 1] - rowoff[g]);
         if (nrows == 0) continue;
         gb::QuadArgs q;
-        q.tens = c->tens_tmp.as<double>() + 9 * roff[g]; q.p1 = p1; q.nrows = nrows; q.r = d_r + 3 * roff[g];
+        q.tens = jpath ? nullptr : c->tens_tmp.as<double>() + 9 * roff[g]; q.jvec = jpath ? c->tens_tmp.as<double>() + 3 * roff[g] : nullptr;
+        q.p1 = p1; q.nrows = nrows; q.r = d_r + 3 * roff[g];
         q.w1 = c->gridbuf.as<double>() + goff[g] + 12 + p1 + p2 + G.npts[2]; q.wrow = d_wrow + rowoff[g];
         auto gp = [&](int i, int j, int k, double *r) {   // gridpoint, grid.f90:498-511 (0-based here)
             for (int d = 0; d < 3; ++d) r[d] = G.origin[d] + G.pts[0][i] * G.basv[d] + G.pts[1][j] * G.basv[3 + d] + G.pts[2][k] * G.basv[6 + d];

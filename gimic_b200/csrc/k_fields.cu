@@ -140,13 +140,17 @@ __global__ void __launch_bounds__(128) k_quad_rows(QuadArgs q) {
     double s[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int i = lane; i < q.p1; i += 32) {
         const long p = (long)row * q.p1 + i;
-        const double *t = q.tens + 9 * p;
+        const double *t = q.jvec ? nullptr : q.tens + 9 * p;
         const double dx = q.r[3 * p] - q.center[0], dy = q.r[3 * p + 1] - q.center[1], dz = q.r[3 * p + 2] - q.center[2];
         const bool inside = !(sqrt(dx * dx + dy * dy + dz * dz) > q.radius);      // integral.f90:125,128
         const double w = inside ? q.w1[i] : 0.0;
-        const double vx = t[0] * q.B[0] + t[3] * q.B[1] + t[6] * q.B[2];
-        const double vy = t[1] * q.B[0] + t[4] * q.B[1] + t[7] * q.B[2];
-        const double vz = t[2] * q.B[0] + t[5] * q.B[1] + t[8] * q.B[2];
+        double vx, vy, vz;
+        if (q.jvec) { vx = q.jvec[3 * p]; vy = q.jvec[3 * p + 1]; vz = q.jvec[3 * p + 2]; }      // formed inside the contraction
+        else {
+            vx = t[0] * q.B[0] + t[3] * q.B[1] + t[6] * q.B[2];
+            vy = t[1] * q.B[0] + t[4] * q.B[1] + t[7] * q.B[2];
+            vz = t[2] * q.B[0] + t[5] * q.B[1] + t[8] * q.B[2];
+        }
         const double nj = q.normal[0] * vx + q.normal[1] * vy + q.normal[2] * vz;
         if (q.what & 1) {                                                         // integrate_current
             const double jp = inside ? nj * w : 0.0;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(128) k_quad_rows(QuadArgs q) {
             s[3] += jp * w;
             if (jp > 0.0) s[4] += jp * w; else s[5] += jp * w;
         }
-        if (q.what & 4) {                                                         // integrate_acid
+        if ((q.what & 4) && t) {                                                  // integrate_acid (needs the tensor)
             const double xxmyy = (t[0] - t[4]) * (t[0] - t[4]), yymzz = (t[4] - t[8]) * (t[4] - t[8]), zzmxx = (t[8] - t[0]) * (t[8] - t[0]);
             const double xypyx = (t[3] + t[1]) * (t[3] + t[1]), xzpzx = (t[6] + t[2]) * (t[6] + t[2]), yzpzy = (t[7] + t[5]) * (t[7] + t[5]);
             s[6] += (0.3333333 * (xxmyy + yymzz + zzmxx) + 0.5 * (xypyx + xzpzx + yzpzy)) * w;

@@ -169,6 +169,7 @@ void launch_divj(long n, const double *jv6 /* [6][n][3] shifted jvecs */, double
 void launch_shift_points(long n, const double *r, double h, double *r6, cudaStream_t s);
 struct QuadArgs {
     const double *tens; int p1, nrows;            // rows = (j,k) pairs handled by this call, i fastest
+    const double *jvec = nullptr;                 // if set: J = T.B as delivered by the contraction's J path (3 per point), tens unused
     const double *r;                              // points (3 x p1*nrows)
     const double *w1, *wrow;                      // w_i [p1]; per-row weight w_j*w_k [nrows]
     double B[3], normal[3], center[3], radius; int what;

@@ -253,4 +253,9 @@ def main(argv=None):
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
         else:
             dist.init_process_group("gloo")
-    return run(a.infile, workdir=a.workdir, dryrun=a.dryrun, vtk_appended=(a.vtk == "appended"), title=a.title, device=device, devices=devices)
+    try:
+        return run(a.infile, workdir=a.workdir, dryrun=a.dryrun, vtk_appended=(a.vtk == "appended"), title=a.title, device=device, devices=devices)
+    finally:
+        dist, _, _ = _dist()
+        if dist is not None:
+            dist.destroy_process_group()
