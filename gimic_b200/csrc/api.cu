@@ -31,6 +31,12 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(GIMIC_B200_ECUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")"); \
     } while (0)
 
+// GIMIC_B200_POISON=1 (debugging): every fresh workspace allocation is filled with 0xFF bytes (NaN as doubles, -1 as ints), so that a
+// read of memory nobody wrote shows up as NaN in the results instead of depending on what the allocator handed out.
+bool poison_workspaces() {
+    static const bool on = [] { const char *e = std::getenv("GIMIC_B200_POISON"); return e && e[0] != '0'; }();
+    return on;
+}
 struct Buf {
     void *p = nullptr; size_t cap = 0;
     int ensure(size_t bytes) {
@@ -40,6 +46,7 @@ struct Buf {
         size_t want = bytes + bytes / 8 + 256;
         if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; } want = bytes; }
         cap = want;
+        if (poison_workspaces()) cudaMemset(p, 0xFF, want);
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -118,7 +125,12 @@ int upload(gimic_b200_ctx *c, const std::vector<T> &v, const T **out) {
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
     CUDA_TRY(cudaMalloc(&p, bytes));
     c->owned.push_back(p);
-    if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // On the context's stream: a plain cudaMemcpy from pageable memory may return while the DMA of its last staging chunk is still in
+    // flight, and the context's streams are non-blocking (not ordered behind the legacy stream that copy runs on).
+    if (!v.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     *out = reinterpret_cast<const T *>(p);
     return 0;
 }
@@ -301,7 +313,10 @@ int finish_create(gimic_b200_ctx *c, const double *dens_a, const double *dens_b,
         const double *d_src = src;
         if (!dens_on_device) {
             CUDA_TRY(cudaMalloc((void **)&c->d_dens[sp], 4 * nn * sizeof(double)));
-            CUDA_TRY(cudaMemcpy(c->d_dens[sp], src, 4 * nn * sizeof(double), cudaMemcpyHostToDevice));
+            // stream-ordered before k_build_operand (a plain cudaMemcpy from pageable memory returns before its DMA has landed, and
+            // c->stream is non-blocking: round 2 found the beta operand of a small open-shell case built from a partly stale buffer
+            // once in ~4 runs of the whole parity file)
+            CUDA_TRY(cudaMemcpyAsync(c->d_dens[sp], src, 4 * nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             d_src = c->d_dens[sp];
         }
         void *p = nullptr;

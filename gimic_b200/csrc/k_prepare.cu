@@ -13,7 +13,10 @@ namespace gb {
 
 __constant__ signed char c_lmn[2][6][21][3];
 
-void upload_component_tables(const signed char *host_tab) { cudaMemcpyToSymbol(c_lmn, host_tab, 2 * 6 * 21 * 3); }
+void upload_component_tables(const signed char *host_tab) {
+    cudaMemcpyToSymbol(c_lmn, host_tab, 2 * 6 * 21 * 3);
+    cudaDeviceSynchronize();       // the copy runs on the legacy stream; the kernels that read the table run on non-blocking streams
+}
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t spread16(uint32_t v) {   // 16 bits -> every third bit of 48

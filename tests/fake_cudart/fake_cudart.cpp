@@ -303,10 +303,12 @@ cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyToSymbol(const void *, const void *, size_t, size_t, cudaMemcpyKind) { return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if (n) std::memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
 
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)&g_dummy_stream; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)&g_dummy_event; return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)&g_dummy_event; return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }

@@ -21,7 +21,11 @@ def scaled_err(a, ref):
 
 
 def assert_close(a, ref, what=""):
-    e = scaled_err(np.asarray(a), np.asarray(ref))
+    a, ref = np.asarray(a), np.asarray(ref)
+    e = scaled_err(a, ref)
+    if e > 1.0 and a.ndim >= 2:         # which rows (points): one tile, a stripe, everything?
+        rows = np.flatnonzero((np.abs(a - ref) / (RTOL * np.abs(ref) + ATOL)).reshape(a.shape[0], -1).max(1) > 1.0)
+        what += f" [{rows.size} of {a.shape[0]} rows off, first {rows[:12].tolist()}, nan {int(np.isnan(a).sum())}]"
     assert e <= 1.0, f"{what}: max |a-ref| / (1e-10|ref| + 1e-12) = {e:.3g}"
 
 

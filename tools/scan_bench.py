@@ -25,7 +25,7 @@ for nsl in (50, 400):
     mid = 0.5 * (xyz[0] + xyz[1])
     gs = [gauss_plane(mid + [0.0, edges[i], -5.0], [[0, 1, 0], [0, 0, 1], [1, 0, 0]], edges[i + 1] - edges[i], 10.0, 9, 36) for i in range(nsl)]
     B = np.array([0.0, 0.0, 1.0])
-    g.integrate_batch(gs[:4], B, "total", 3); g.integrate(gs[0], B, "total", 3)
+    g.integrate_batch(gs, B, "total", 3); g.integrate(gs[0], B, "total", 3)      # warm: workspace growth, lazily loaded kernels (0.9 s the first time)
     t0 = time.perf_counter(); single = np.array([g.integrate(x, B, "total", 3) for x in gs]); t1 = time.perf_counter()
     batch = g.integrate_batch(gs, B, "total", 3); t2 = time.perf_counter()
     out[f"{nsl}_slices"] = {"points_per_slice": gs[0].n, "loop_of_integrate_s": t1 - t0, "integrate_batch_s": t2 - t1,
