@@ -205,3 +205,16 @@ def test_native_multi_device_partition_equals_single_device(tmp_path, cases, nam
     for f in sorted(os.listdir(dn)):
         if not filecmp.cmp(dn / f, dp / f, shallow=False):
             _same_text(open(dn / f, errors="replace").read(), open(dp / f, errors="replace").read(), f, floor_rel=1e-9)
+
+
+def test_rank_mode_over_nccl_when_two_gpus():
+    """`torchrun --nproc-per-node 2 -m gimic_b200` semantics on hardware: the compiled driver in rank mode, rows gathered and integral sums
+    reduced over NCCL through the launcher's two callbacks; rank 0's files and report against the reference's goldens
+    (tools/dist_driver_check.py).  The same glue runs on CPU over gloo in tests/test_native_driver_mock.py."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (recorded on a 2-GPU box in profiles/r02_dist_driver_check_n2.txt)")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29573", os.path.join(ROOT, "tools", "dist_driver_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and '"cdens_open_shell_files_match_golden": true' in p.stdout and '"integral_matches_golden": true' in p.stdout, \
+        p.stdout[-2000:] + p.stderr[-2000:]
