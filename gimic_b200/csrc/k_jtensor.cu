@@ -49,8 +49,27 @@ __device__ __forceinline__ void mma_16x8x4_f64(double (&c)[4], double a0, double
                  : "d"(a0), "d"(a1), "d"(b0));
 }
 // ---- async-copy / mbarrier primitives (sm_90+ PTX; SASS: LDGSTS, UBLKCP, SYNCS) ---------------------
+// L2_HINTS (A/B builds, tools/gpu_r02_z.sh): 1 = the Phi panels a CTA streams once per nu chunk are loaded with an evict_last L2 policy;
+// 2 = additionally the density gathers with evict_first.  0 (the shipped build) = no hints.
+#ifndef L2_HINTS
+#define L2_HINTS 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void cp_async_16(uint32_t smem, const void *gmem) {
+#if L2_HINTS >= 2
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "l"(l2_policy_evict_first()));
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem));
+#endif
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t mbar) {   // arrive when this thread's prior cp.async land
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar));
@@ -75,8 +94,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 }
 // 1-D bulk TMA copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t smem_dst, const void *gmem, uint32_t bytes, uint32_t mbar) {
+#if L2_HINTS >= 1
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_dst), "l"(gmem), "r"(bytes), "r"(mbar), "l"(l2_policy_evict_last()) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gmem), "r"(bytes), "r"(mbar) : "memory");
+#endif
 }
 
 constexpr int ROWLD = 17;   // doubles per row-table entry: 13 sums + 3 coordinates, padded to an odd stride (bank-conflict-free)

@@ -5,6 +5,7 @@
 // times), integer powers by repeated multiplication, and the *same* screening test
 // sqrt(|r-R|^2) <= thr  so screened functions are exact zeros as in the reference.
 #include <algorithm>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
 
 // offsets inside the batch, scheduling keys (batch, longest first) and the statistics of the range
 __global__ void __launch_bounds__(256) k_plan_finalize(TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, long long pool_doubles,
-                                                       PlanSummary *sum, unsigned long long *__restrict__ keys, int *__restrict__ ord) {
+                                                       PlanSummary *sum, unsigned long long *__restrict__ keys, int *__restrict__ ord, int order_bits) {
     const int tlo = sum->tlo, thi = sum->thi;
     const int t = tlo + blockIdx.x * blockDim.x + threadIdx.x;
     double st[6] = {0, 0, 0, 0, 0, 0};
@@ -472,7 +473,16 @@ __global__ void __launch_bounds__(256) k_plan_finalize(TileDesc *__restrict__ de
         td.panel_off = cum[t].panel - cum[t0].panel; td.fidx_off = cum[t].fidx - cum[t0].fidx; td.atab_off = cum[t].atab - cum[t0].atab;
         desc[t] = td;
         const long long c = cum[t + 1].cost - cum[t].cost;
-        const unsigned c32 = (unsigned)(c > 0xffffffffLL ? 0xffffffffLL : c);
+        // Processing order inside a batch: costliest first (the contraction pulls tiles from an atomic counter: short tiles fill the
+        // tail).  order_bits >= 0 (GIMIC_B200_ORDER_BITS, A/B runs): cost classes of 2^-order_bits relative width instead of exact costs;
+        // the sort is stable, so tiles of one class keep their Hilbert order and spatial neighbours -- which gather nearly the same
+        // density elements -- run at the same time.
+        unsigned c32 = (unsigned)(c > 0xffffffffLL ? 0xffffffffLL : c);
+        if (order_bits >= 0 && c > 0) {
+            const int e = 63 - __clzll(c);
+            const unsigned m = e > order_bits ? (unsigned)((c >> (e - order_bits)) & ((1LL << order_bits) - 1)) : (unsigned)(c & ((1LL << order_bits) - 1));
+            c32 = ((unsigned)e << order_bits) | m;
+        }
         keys[t - tlo] = ((unsigned long long)b << 32) | (0xffffffffu - c32);
         ord[t - tlo] = t;
         st[0] = td.nact; st[1] = 2.0 * MT * 4.0 * td.nact * td.nn; st[2] = 2.0 * MT * 2.0 * td.nact * td.nn;
@@ -537,7 +547,8 @@ void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, 
     k_scan_tops_c<<<1, 1024, 0, s>>>(pb.tops_c, pb.summary);
     k_scan_add_c<<<nbc, SCAN_TPB, 0, s>>>(pb.cum, pb.summary, pb.tops_c);
     k_plan_range<<<64, 256, 0, s>>>(pb.desc, pb.cum, rank, nranks, pool_doubles, pb.summary);
-    k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0);
+    static const int order_bits = [] { const char *e = std::getenv("GIMIC_B200_ORDER_BITS"); return e ? std::atoi(e) : -1; }();
+    k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0, order_bits);
 }
 size_t plan_sort_temp_bytes(int nt) {
     size_t bytes = 0;
