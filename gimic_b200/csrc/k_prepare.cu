@@ -110,12 +110,13 @@ void launch_grid_points(const double *ob, const double *p0, const double *p1, co
 
 // ---------------------------------------------------------------------------------------------
 // Screening of one atom against a tile: a shell can only be non-zero at some point p of the tile if |p - R| <= thr.
-// Cheap reject by the distance to the tile's bounding box (one atom per lane), then, one atom per warp, the exact minimum
-// distance over the tile's points (staged in shared memory), so the active set is the exact union over the tile's points at
-// shell granularity.  Shells are sorted by descending thr inside each atom, so the active set of an atom is a prefix.
-// k_tile_split and k_basis call this with identical inputs; every product below is written with explicit intrinsics so that
-// both kernels compute bit-identical distances (no context-dependent FMA contraction) => identical counts.  The per-point
-// test sqrt(r2) <= thr is applied again in k_basis (filter_screened, basis.f90:118-136).
+// Cheap reject by the distance to the tile's bounding box (one atom per lane), then, one atom per warp, a lower bound of the
+// minimum distance over the tile's points (staged in shared memory, single precision about the tile centre, see below), so the
+// active set is the union over the tile's points at shell granularity plus a ~1e-6 margin.  Shells are sorted by descending thr
+// inside each atom, so the active set of an atom is a prefix.
+// k_tile_split and k_basis call this with identical inputs; every operation below is written with explicit rounding-mode
+// intrinsics so that both kernels compute bit-identical bounds (no context-dependent FMA contraction) => identical counts.  The
+// exact per-point test sqrt(r2) <= thr is applied in k_basis (filter_screened, basis.f90:118-136).
 // for_active_atoms: warp-cooperative sweep over the 32 atoms [base, base + 32).  Lane i loads atom base+i (position, largest radius,
 // shell / function ranges) and tests its bounding box; the surviving atoms are then processed one at a time with their data broadcast
 // by shuffles, so that the only dependent global-memory round per candidate is the one that fetches the shell radii.
@@ -189,8 +190,10 @@ __device__ __forceinline__ void for_active_atoms(const DevBasis &B, int base, co
 // ---- k_tile_split -----------------------------------------------------------------------------------------------------------
 // One CTA (128 threads) per run of MT consecutive sorted points.  Depth-first, left piece first: evaluate a piece [a, b) of the
 // run (bounding box, radius, largest consecutive gap, active slots / atoms / functions); a piece wider than split_radius whose
-// largest gap exceeds half its radius is cut there (thin / planar point sets, cluster boundaries: a Hilbert run that leaves and
-// re-enters the point cloud would otherwise drag in the active sets of both ends), everything else is emitted in order.
+// largest gap exceeds half its radius is a candidate for a cut there (thin / planar point sets, cluster boundaries: a Hilbert run
+// that leaves and re-enters the point cloud would otherwise drag in the active sets of both ends) and is cut if the two pieces
+// cost the contraction less than the whole (piece_cost, kernels.cuh); everything else is emitted in order.
+//
 // minimum of 6 values over the 128 threads, in single precision: the callers pass values rounded DOWN, so the result bounds the exact
 // minimum from below (the tile's box may grow by one float ulp per side, never shrink); result broadcast
 __device__ __forceinline__ void block_min6(float (&v)[6], float (*s_red)[6]) {
