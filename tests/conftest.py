@@ -15,8 +15,8 @@ _GPU_ORDER = {"test_gpu_parity.py": 0, "test_gpu_driver.py": 1, "test_native_dri
 
 
 def pytest_collection_modifyitems(config, items):
-    """GPU run order: the kernel parity gate (C ABI vs oracle / goldens) first, then the Python driver above it, then the native
-    driver, which is held to the Python one.  Stable sort: everything else keeps its collection order."""
+    """GPU run order: the kernel parity gate (C ABI vs oracle / goldens) first, then the driver through its library entry (Python launcher), then the
+    gimic-b200 program, which is held to the library entry.  Stable sort: everything else keeps its collection order."""
     items.sort(key=lambda it: _GPU_ORDER.get(os.path.basename(str(it.fspath)), -1))
     # a plain `pytest tests` on a host without a CUDA device (or without the built library) skips the GPU tests instead of erroring
     if any("gpu" in it.keywords for it in items) and not _have_gpu():

@@ -1,8 +1,8 @@
 """CPU-side checks of the native (C++) run-mode driver, libgimic_b200_driver.so + the gimic-b200 program
 (include/gimic_b200_driver.h): the compiled counterpart of `gimic gimic.inp` (src/gimic.in:25-159 + src/fgimic/gimic.F90).
-Input parsing, grid geometry, field direction, report text and every file format must equal the Python driver above the same
-C ABI (which the other tests pin against the oracle and the reference's goldens) byte for byte; what needs the GPU is in
-tests/test_native_driver_gpu.py."""
+Input parsing against an independent reader of the grammar, grid geometry and field direction against the oracle's grid code, report
+text against snapshots and the reference's stdout goldens, every file format against the skeletons of the reference's own files and a
+round trip through the parser of the goldens; what needs the GPU is in tests/test_native_driver_gpu.py."""
 import ctypes as C
 import filecmp
 import io

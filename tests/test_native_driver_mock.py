@@ -76,7 +76,7 @@ else:
 
 
 def _python(mock_dir, args, timeout=900):
-    """the Python driver in a fresh interpreter bound to the test double (this process keeps the real library)"""
+    """the driver library through the Python launcher, in a fresh interpreter bound to the test double (this process keeps the real library)"""
     code = PY_RUNNER.format(root=ROOT, so=str(mock_dir / "libgimic_b200.so"))
     p = subprocess.run([sys.executable, "-c", code, *[str(a) for a in args]], capture_output=True, text=True, timeout=timeout, env=_env(mock_dir))
     assert p.returncode == 0, p.stderr[-2000:]
@@ -107,7 +107,7 @@ def _same_dirs(dn, dp):
 
 
 def test_c4h4_read_grid_native_vs_python_and_golden(mock_dir, tmp_path, cases):
-    """test/c4h4/read-grid through gimic-b200: jvec.vtu equals the Python driver's bytes and the reference's golden at its 10 digits"""
+    """test/c4h4/read-grid through gimic-b200: jvec.vtu equals the launcher path's bytes and the reference's golden at its 10 digits"""
     from make_golden import read_vtu_vectors
     gold = fixtures.golden_npz("c4h4_readgrid.npz")
 
@@ -132,7 +132,7 @@ def test_c4h4_read_grid_native_vs_python_and_golden(mock_dir, tmp_path, cases):
                                                   ("open_shell", "open-shell_integration", "open_shell_integration.json")])
 def test_integration_reports_native_vs_python_and_golden(mock_dir, tmp_path, cases, case, name, gold_json):
     """test/c4h4/integration and test/open-shell/integration (36 x 36 Gauss plane, all spin cases): the gimic-b200 report is the
-    Python driver's, and its numbers are the ones the reference printed"""
+    launcher path's, and its numbers are the ones the reference printed"""
     dn, dp = _pair(tmp_path, name, cases[case]["mol"], cases[case]["xdens"])
     a = _native(mock_dir, [dn / "gimic.inp"])
     b = _python(mock_dir, [dp / "gimic.inp"])
@@ -238,7 +238,7 @@ def test_scalar_modes_appended_vtk_and_scan_native_vs_python(mock_dir, tmp_path,
         (d / "calculation.dat").write_text("atom1=1\natom2=2\nin=0.0 out=7.0\ndelta=1.209357 nsteps=6\n")
     _native(mock_dir, names["nat"])
     _python(mock_dir, names["py"])
-    # current_profile.dat (what jobscripts/src/gradient.sh.in pastes together from the gimic.N.out files): same bytes from both drivers,
+    # current_profile.dat (what jobscripts/src/gradient.sh.in pastes together from the gimic.N.out files): same bytes from the program and the launcher path,
     # and its columns are the numbers printed in the reports (there rounded to 6 decimals)
     assert filecmp.cmp(dn / "current_profile.dat", dp / "current_profile.dat", shallow=False)
     prof = np.loadtxt(dn / "current_profile.dat")

@@ -1,6 +1,6 @@
 """Rehearsal of the driver-level GPU tests' CODE in a container without a GPU: tests/test_gpu_driver.py and tests/test_native_driver_gpu.py
 are run against the oracle-backed TEST DOUBLE of libgimic_b200.so (tests/mock_backend/, built into a temporary directory).  This checks
-the tests themselves (paths, regular expressions, golden comparisons, both drivers' orchestration) -- it is NOT a GPU result: on a B200
+the tests themselves (paths, regular expressions, golden comparisons, the driver's orchestration) -- it is NOT a GPU result: on a B200
 the same tests run against the CUDA library.  Usage: python tools/rehearse_gpu_driver_tests.py"""
 import os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
