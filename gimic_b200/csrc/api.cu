@@ -78,7 +78,7 @@ struct gimic_b200_ctx {
     double opj_B[4][3] = {};
     int nq = gb::NQ, ldb = 0; long long plane_stride = 0;
     double bbox_lo[3] = {0, 0, 0}; double inv_cell = 1.0;
-    size_t pool_max_bytes = (size_t)8 << 30;
+    size_t pool_max_bytes = (size_t)8 << 30;      // set per device in create_common
     // workspaces
     Buf keys0, keys1, vals0, vals1, sorttmp, rs, panel, fidx, atab, misc, r_in, r_in2, tens_tmp, tens_tmp2, f_tmp, f_tmp2, shift, jv6, gridbuf, quad;
     Buf p_seg, p_geo, p_info, p_cnt, p_off, geo, desc, cum, pkeys0, pkeys1, pord0, pord1, tiles, d_summary, p_tops;   // tile plan (k_prepare.cu)
@@ -229,7 +229,10 @@ int init_device(gimic_b200_ctx *c) {
     CUDA_TRY(cudaMallocHost((void **)&c->h_summary, sizeof(gb::PlanSummary)));
     // panel pool: one batch (one k_basis + one k_jtensor launch) per ~pool of Phi/dPhi panels.  8 GB is the configuration of the
     // committed ncu captures and launch lists; GIMIC_B200_POOL_MB=24576 (one launch per 2M-point step) measured +1 %.
-    c->pool_max_bytes = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, prop.totalGlobalMem / 8));
+    // panel pool of one batch: an eighth of the device memory, at most 24 GB (B200: 22 GB).  Fewer, larger batches mean fewer launch tails:
+    // whole 256^3 grid at nbf = 10^4: 4 GB 758.7 ms, 8 GB 747.3 ms, 24 GB 743.8 ms, 48 GB 742.6 ms (profiles/r02_pool_sweep.txt).  The pool is
+    // allocated at the size the point set needs, never more.
+    c->pool_max_bytes = std::min<size_t>((size_t)24 << 30, std::max<size_t>((size_t)1 << 30, prop.totalGlobalMem / 8));
     if (const char *mb = std::getenv("GIMIC_B200_POOL_MB")) { long v = std::atol(mb); if (v > 0) c->pool_max_bytes = (size_t)v << 20; }
     return 0;
 }
