@@ -485,14 +485,42 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
         a.tens = o.tens; a.edens = o.edens; a.jvec = o.jvec; a.jmod = o.jmod; a.acid = o.acid; a.jpath = o.jpath ? 1 : 0;
         for (int k = 0; k < 3; ++k) a.B[k] = o.B3 ? o.B3[k] : 0.0;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
-        launch_jtensor(a, giao, c->nsm, st);
-        if (nsl > 1) launch_slice_reduce(a, c->tiles.as<TileDesc>() + t0, nb, nsl, item_cost, giao, st);
-        CUDA_TRY(cudaGetLastError());
-        c->stats.launches += 2;
-        c->stats.contract_launches += 1;
-        if (prof) cudaEventRecord(c->evpool[3 * b + 2], st);
-        // a batch is a contiguous run of Hilbert-ordered tiles = of compact output rows: the caller may start draining them
-        if (after_batch) if (int rc = (*after_batch)(b, (long)(S.batch_pt[b] - S.pt_lo), (long)(S.batch_pt[b + 1] - S.pt_lo))) return rc;
+        // A caller that drains the rows to the host while the GPU works (after_batch) gets them group by group when the range has few
+        // batches: the tiles of a batch are ordered (drain group, costliest first), a group is a contiguous run of Hilbert-ordered tiles =
+        // of compact output rows, and each group is its own launch.  Otherwise one launch per batch.
+        const bool grouped = after_batch && nsl == 1 && b < DRAIN_BATCHES && S.drain_chunk < pool_cap;
+        if (!grouped) {
+            launch_jtensor(a, giao, c->nsm, st);
+            if (nsl > 1) launch_slice_reduce(a, c->tiles.as<TileDesc>() + t0, nb, nsl, item_cost, giao, st);
+            CUDA_TRY(cudaGetLastError());
+            c->stats.launches += 2;
+            c->stats.contract_launches += 1;
+            if (prof) cudaEventRecord(c->evpool[3 * b + 2], st);
+            // a batch is a contiguous run of Hilbert-ordered tiles = of compact output rows: the caller may start draining them
+            if (after_batch) if (int rc = (*after_batch)(b, (long)(S.batch_pt[b] - S.pt_lo), (long)(S.batch_pt[b + 1] - S.pt_lo))) return rc;
+        } else {
+            int done = 0;
+            for (int g = 0; g < DRAIN_GROUPS; ++g) {
+                const int gt = S.group_tile[b * DRAIN_GROUPS + g];
+                if (gt < 0) continue;
+                int next_tile = S.batch_start[b + 1]; long long next_pt = S.batch_pt[b + 1];
+                for (int g2 = g + 1; g2 < DRAIN_GROUPS; ++g2)
+                    if (S.group_tile[b * DRAIN_GROUPS + g2] >= 0) { next_tile = S.group_tile[b * DRAIN_GROUPS + g2]; next_pt = S.group_pt[b * DRAIN_GROUPS + g2]; break; }
+                const int ng = next_tile - gt;
+                if (ng <= 0) continue;
+                if (done) CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
+                a.tiles = c->tiles.as<TileDesc>() + t0 + done; a.ntiles = ng;
+                launch_jtensor(a, giao, c->nsm, st);
+                CUDA_TRY(cudaGetLastError());
+                c->stats.launches += 1;
+                c->stats.contract_launches += 1;
+                done += ng;
+                if (int rc = (*after_batch)(b * DRAIN_GROUPS + g, (long)(S.group_pt[b * DRAIN_GROUPS + g] - S.pt_lo), (long)(next_pt - S.pt_lo))) return rc;
+            }
+            c->stats.launches += 1;
+            if (done != nb) return fail(GIMIC_B200_EINVAL, "internal error: drain groups do not cover the batch");
+            if (prof) cudaEventRecord(c->evpool[3 * b + 2], st);
+        }
     }
     if (prof) {
         CUDA_TRY(cudaStreamSynchronize(st));

@@ -428,6 +428,12 @@ __global__ void k_tile_emit(const TileSeg *__restrict__ slot_seg, const TileGeo 
     }
 }
 
+// drain group of a tile inside its batch (PlanSummary::drain_chunk): its panel offset in the batch over the chunk size
+__host__ __device__ inline int drain_group(long long panel_prefix_in_range, long long pool_doubles, long long chunk) {
+    const long long off = panel_prefix_in_range % pool_doubles;
+    const long long g = off / chunk;
+    return (int)(g < DRAIN_GROUPS - 1 ? g : DRAIN_GROUPS - 1);
+}
 // this rank's share: tiles whose exclusive cost prefix falls into [rank, rank + 1) x total / nranks; panel-pool batches of that range
 __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, int rank, int nranks,
                                                     long long pool_doubles, PlanSummary *sum) {
@@ -452,13 +458,25 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
         sum->max_nruns = 0; sum->max_tile_panel = 0;
         sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
         if (nb <= MAX_BATCH) { sum->batch_start[nb] = thi; sum->batch_pt[nb] = sum->pt_hi; }
+        // drain groups: quarters of the (fullest) batch, never less than 128 MB of panels; none if the range has many batches anyway or
+        // fewer tiles than a few per SM (the slices path)
+        const long long full = sum->panel_range < pool_doubles ? sum->panel_range : pool_doubles;
+        long long chunk = (full + DRAIN_GROUPS - 1) / DRAIN_GROUPS;
+        if (chunk < (16LL << 20)) chunk = 16LL << 20;
+        sum->drain_chunk = (nb <= DRAIN_BATCHES && thi - tlo >= 2048) ? chunk : pool_doubles;
+        for (int i = 0; i <= DRAIN_BATCHES * DRAIN_GROUPS; ++i) { sum->group_tile[i] = -1; sum->group_pt[i] = 0; }
     }
     __syncthreads();
     const int tlo = s_lo, thi = s_hi;
-    const long long base = cum[tlo].panel;
+    const long long base = cum[tlo].panel, chunk = sum->drain_chunk;
     for (int t = tlo + threadIdx.x + blockIdx.x * blockDim.x; t < thi; t += blockDim.x * gridDim.x) {
         const long long b = (cum[t].panel - base) / pool_doubles;
         if (b < MAX_BATCH && (t == tlo || (cum[t - 1].panel - base) / pool_doubles != b)) { sum->batch_start[b] = t; sum->batch_pt[b] = desc[t].pt0; }
+        if (b < DRAIN_BATCHES) {
+            const int g = drain_group(cum[t].panel - base, pool_doubles, chunk);
+            const bool first = t == tlo || (cum[t - 1].panel - base) / pool_doubles != b || drain_group(cum[t - 1].panel - base, pool_doubles, chunk) != g;
+            if (first) { sum->group_tile[b * DRAIN_GROUPS + g] = t; sum->group_pt[b * DRAIN_GROUPS + g] = desc[t].pt0; }
+        }
     }
 }
 
@@ -486,7 +504,8 @@ __global__ void __launch_bounds__(256) k_plan_finalize(TileDesc *__restrict__ de
             const unsigned m = e > order_bits ? (unsigned)((c >> (e - order_bits)) & ((1LL << order_bits) - 1)) : (unsigned)(c & ((1LL << order_bits) - 1));
             c32 = ((unsigned)e << order_bits) | m;
         }
-        keys[t - tlo] = ((unsigned long long)b << 32) | (0xffffffffu - c32);
+        const unsigned long long g = b < DRAIN_BATCHES ? (unsigned long long)drain_group(cum[t].panel - cum[tlo].panel, pool_doubles, sum->drain_chunk) : 0ull;
+        keys[t - tlo] = ((unsigned long long)b << 36) | (g << 32) | (0xffffffffu - c32);
         ord[t - tlo] = t;
         st[0] = td.nact; st[1] = 2.0 * MT * 4.0 * td.nact * td.nn; st[2] = 2.0 * MT * 2.0 * td.nact * td.nn;
         st[3] = 2.0 * MT * (double)td.nn * td.nruns;                       // per tap weight (x3 tensor path, x1 J path)

@@ -71,6 +71,7 @@ constexpr int MAXSUB = 16;
 constexpr int SPLIT_DEPTH = 7;
 constexpr int MAX_BATCH = 4096;     // panel-pool batches one call may need
 struct TileCum { long long cost, panel, fidx, atab; };   // per tile: scheduling cost, panel doubles, index ints, atom-table entries (and their exclusive prefix sums)
+constexpr int DRAIN_BATCHES = 4, DRAIN_GROUPS = 4;
 struct PlanSummary {                // device -> host, once per plan
     int ntiles;                     // tiles of the whole point set (Hilbert order)
     int tlo, thi;                   // the tile range this rank owns: equal shares of the cumulative cost
@@ -80,6 +81,12 @@ struct PlanSummary {                // device -> host, once per plan
     long long max_tile_panel;
     long long cost_total, cost_range;
     double sum_nact, flops4, flops2, taps, useful_mm, useful_taps;   // statistics of the range (see gimic_b200_stats)
+    // Drain groups (only when the range has at most DRAIN_BATCHES batches): a batch is cut into up to DRAIN_GROUPS runs of Hilbert-ordered
+    // tiles of `drain_chunk` panel doubles each; the processing order is (batch, group, costliest first), so a caller that wants its
+    // rows on the host can launch the contraction group by group and copy a finished group's rows out while the next one runs.
+    long long drain_chunk;
+    int group_tile[DRAIN_BATCHES * DRAIN_GROUPS + 1];        // first tile (Hilbert order, absolute) of group g of batch b at [b * DRAIN_GROUPS + g]; -1 = empty
+    long long group_pt[DRAIN_BATCHES * DRAIN_GROUPS + 1];    // its first sorted point
     int batch_start[MAX_BATCH + 1]; // tile index (Hilbert order, absolute) where each batch begins; [nbatch] = thi
     long long batch_pt[MAX_BATCH + 1];   // first sorted point of each batch; [nbatch] = pt_hi (a batch is a contiguous run of compact output rows)
 };

@@ -93,6 +93,12 @@ int main(int argc, char **argv) {
             EXPECT(gimic_b200_partition_info(h, info) == 0 && info[0] == n && info[1] == cnt && info[3] <= info[2] && info[5] <= info[4]);
             EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), tens.data(), jv.data(), jm.data(), ac.data(), ed.data(), 0) == 0);
             EXPECT(gimic_b200_partition_calc(h, B, GIMIC_B200_TOTAL, idx.data(), nullptr, jv.data(), jm.data(), nullptr, nullptr, 0) == 0);   // plan reused, J path
+            if (std::getenv("FAKE_DRAIN_CHUNK") && info[3] > 1) {      // host outputs + drain groups: one contraction launch per group of tiles
+                gimic_b200_stats st;
+                const bool every_tile_its_own = std::atol(std::getenv("FAKE_DRAIN_CHUNK")) < 50000;     // a c4h4 tile holds ~88 000 panel doubles
+                EXPECT(gimic_b200_get_stats(h, &st) == 0 && st.contract_launches >= (every_tile_its_own ? 2 : 1) && st.contract_launches <= 4);
+                if (std::getenv("FAKE_DEBUG")) std::printf("rank %d tiles %ld contract launches %ld\n", rk, info[3], (long)st.contract_launches);
+            }
             total += cnt; cost_sum += info[5]; tiles_sum += info[3];
             // balanced to within one tile: no share is more than the mean + the largest tile cost (bounded here by the total / 2)
             EXPECT(3 * info[5] <= info[4] + 3 * (info[4] / 2));

@@ -184,9 +184,19 @@ void emulate_plan_range(void **a) {
     sum->max_nruns = 0; sum->max_tile_panel = 0;
     sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
     if (nb <= gb::MAX_BATCH) { sum->batch_start[nb] = thi; sum->batch_pt[nb] = sum->pt_hi; }
+    const long long full = sum->panel_range < pool ? sum->panel_range : pool;
+    long long chunk = (full + gb::DRAIN_GROUPS - 1) / gb::DRAIN_GROUPS;
+    if (chunk < (16LL << 20)) chunk = 16LL << 20;
+    if (const char *e = std::getenv("FAKE_DRAIN_CHUNK")) chunk = std::atoll(e);          // tests: groups on small point sets
+    const bool groups = std::getenv("FAKE_DRAIN_CHUNK") ? nb <= gb::DRAIN_BATCHES : (nb <= gb::DRAIN_BATCHES && thi - tlo >= 2048);
+    sum->drain_chunk = groups ? chunk : pool;
+    for (int i = 0; i <= gb::DRAIN_BATCHES * gb::DRAIN_GROUPS; ++i) { sum->group_tile[i] = -1; sum->group_pt[i] = 0; }
+    auto group_of = [&](int t) { const long long off = (cum[t].panel - cum[tlo].panel) % pool; const long long g = off / sum->drain_chunk; return (int)(g < gb::DRAIN_GROUPS - 1 ? g : gb::DRAIN_GROUPS - 1); };
     for (int t = tlo; t < thi; ++t) {
         const long long b = (cum[t].panel - cum[tlo].panel) / pool;
-        if (b < gb::MAX_BATCH && (t == tlo || (cum[t - 1].panel - cum[tlo].panel) / pool != b)) { sum->batch_start[b] = t; sum->batch_pt[b] = desc[t].pt0; }
+        const bool newb = t == tlo || (cum[t - 1].panel - cum[tlo].panel) / pool != b;
+        if (b < gb::MAX_BATCH && newb) { sum->batch_start[b] = t; sum->batch_pt[b] = desc[t].pt0; }
+        if (b < gb::DRAIN_BATCHES && (newb || group_of(t - 1) != group_of(t))) { sum->group_tile[b * gb::DRAIN_GROUPS + group_of(t)] = t; sum->group_pt[b * gb::DRAIN_GROUPS + group_of(t)] = desc[t].pt0; }
     }
 }
 const int *g_last_ord0 = nullptr;

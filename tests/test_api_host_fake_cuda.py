@@ -33,6 +33,11 @@ def test_every_entry_point_runs_on_the_fake_cuda_runtime(tmp_path, cases):
     p = subprocess.run([str(exe), cases["c4h4"]["mol"], cases["c4h4"]["xdens"], cases["open_shell"]["mol"], cases["open_shell"]["xdens"]],
                        capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 0 and "api harness: 0 failure(s)" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    # drain groups forced onto the small point sets of the harness (the emulated plan takes the chunk size from the environment): a call
+    # with host outputs launches the contraction group by group and the groups cover every batch
+    for chunk in ("30000", "200000"):
+        g = subprocess.run(p.args, capture_output=True, text=True, timeout=300, env=dict(env, FAKE_DRAIN_CHUNK=chunk, GIMIC_B200_SLICES="0"))   # few tiles: no column slices here
+        assert g.returncode == 0 and "api harness: 0 failure(s)" in g.stdout, (chunk, g.stdout[-2000:] + g.stderr[-2000:])
     # and with no device reported, creation fails loudly instead of computing anything
     q = subprocess.run([str(exe), cases["c4h4"]["mol"], cases["c4h4"]["xdens"], cases["open_shell"]["mol"], cases["open_shell"]["xdens"]],
                        capture_output=True, text=True, timeout=300, env=dict(env, FAKE_CUDA_NO_DEVICE="1"))
