@@ -383,7 +383,11 @@ __global__ void __launch_bounds__(1024) k_scan_tops_i(int *tops, int n) {
 }
 __global__ void __launch_bounds__(SCAN_TPB) k_scan_add_i(int *out, int n, const int *__restrict__ tops, PlanSummary *sum, int cap) {
     scan_add_body<int>(out, n, AddI(), tops);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { const int tot = tops[(n + SCAN_TILE - 1) / SCAN_TILE]; sum->ntiles = tot < cap ? tot : cap; sum->overflow = tot > cap; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int tot = tops[(n + SCAN_TILE - 1) / SCAN_TILE]; sum->ntiles = tot < cap ? tot : cap; sum->overflow = tot > cap;
+        // the drain-group table is filled by ALL blocks of k_plan_range: it is cleared here, by one thread of an earlier kernel
+        for (int i = 0; i <= DRAIN_BATCHES * DRAIN_GROUPS; ++i) { sum->group_tile[i] = -1; sum->group_pt[i] = 0; }
+    }
 }
 __global__ void __launch_bounds__(SCAN_TPB) k_scan_partial_c(const TileCum *in, TileCum *out, const PlanSummary *sum, TileCum *__restrict__ tops) {
     __shared__ TileCum s_part[SCAN_TPB];
@@ -439,6 +443,7 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
                                                     long long pool_doubles, PlanSummary *sum) {
     const int ntiles = sum->ntiles;
     __shared__ int s_lo, s_hi;
+    __shared__ long long s_chunk;
     if (threadIdx.x == 0) {
         const long long total = cum[ntiles].cost;
         auto first_at_least = [&](long long target) {     // first t with cum[t].cost * nranks >= target (cum is non-decreasing)
@@ -463,12 +468,12 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
         const long long full = sum->panel_range < pool_doubles ? sum->panel_range : pool_doubles;
         long long chunk = (full + DRAIN_GROUPS - 1) / DRAIN_GROUPS;
         if (chunk < (16LL << 20)) chunk = 16LL << 20;
-        sum->drain_chunk = (nb <= DRAIN_BATCHES && thi - tlo >= 2048) ? chunk : pool_doubles;
-        for (int i = 0; i <= DRAIN_BATCHES * DRAIN_GROUPS; ++i) { sum->group_tile[i] = -1; sum->group_pt[i] = 0; }
+        s_chunk = (nb <= DRAIN_BATCHES && thi - tlo >= 2048) ? chunk : pool_doubles;
+        sum->drain_chunk = s_chunk;          // every block writes the same values here; the group table below was cleared by k_scan_add_i
     }
     __syncthreads();
     const int tlo = s_lo, thi = s_hi;
-    const long long base = cum[tlo].panel, chunk = sum->drain_chunk;
+    const long long base = cum[tlo].panel, chunk = s_chunk;
     for (int t = tlo + threadIdx.x + blockIdx.x * blockDim.x; t < thi; t += blockDim.x * gridDim.x) {
         const long long b = (cum[t].panel - base) / pool_doubles;
         if (b < MAX_BATCH && (t == tlo || (cum[t - 1].panel - base) / pool_doubles != b)) { sum->batch_start[b] = t; sum->batch_pt[b] = desc[t].pt0; }
