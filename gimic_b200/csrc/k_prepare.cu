@@ -440,7 +440,7 @@ __host__ __device__ inline int drain_group(long long panel_prefix_in_range, long
 }
 // this rank's share: tiles whose exclusive cost prefix falls into [rank, rank + 1) x total / nranks; panel-pool batches of that range
 __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, int rank, int nranks,
-                                                    long long pool_doubles, PlanSummary *sum) {
+                                                    long long pool_doubles, PlanSummary *sum, int drain_batches, int drain_min_tiles) {
     const int ntiles = sum->ntiles;
     __shared__ int s_lo, s_hi;
     __shared__ long long s_chunk;
@@ -463,12 +463,13 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
         sum->max_nruns = 0; sum->max_tile_panel = 0;
         sum->sum_nact = sum->flops4 = sum->flops2 = sum->taps = sum->useful_mm = sum->useful_taps = 0.0;
         if (nb <= MAX_BATCH) { sum->batch_start[nb] = thi; sum->batch_pt[nb] = sum->pt_hi; }
-        // drain groups: quarters of the (fullest) batch, never less than 128 MB of panels; none if the range has many batches anyway or
-        // fewer tiles than a few per SM (the slices path)
+        // drain groups: quarters of the (fullest) batch, never less than 128 MB of panels; only if the range has at most drain_batches
+        // batches (with more, finished batches are drained while later ones run: measured at N = 2, 4 batches per rank, extra groups
+        // only add launch tails) and at least drain_min_tiles tiles
         const long long full = sum->panel_range < pool_doubles ? sum->panel_range : pool_doubles;
         long long chunk = (full + DRAIN_GROUPS - 1) / DRAIN_GROUPS;
         if (chunk < (16LL << 20)) chunk = 16LL << 20;
-        s_chunk = (nb <= DRAIN_BATCHES && thi - tlo >= 2048) ? chunk : pool_doubles;
+        s_chunk = (nb <= drain_batches && thi - tlo >= drain_min_tiles) ? chunk : pool_doubles;
         sum->drain_chunk = s_chunk;          // every block writes the same values here; the group table below was cleared by k_scan_add_i
     }
     __syncthreads();
@@ -573,7 +574,10 @@ void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, 
     k_scan_partial_c<<<nbc, SCAN_TPB, 0, s>>>(pb.cum, pb.cum, pb.summary, pb.tops_c);
     k_scan_tops_c<<<1, 1024, 0, s>>>(pb.tops_c, pb.summary);
     k_scan_add_c<<<nbc, SCAN_TPB, 0, s>>>(pb.cum, pb.summary, pb.tops_c);
-    k_plan_range<<<64, 256, 0, s>>>(pb.desc, pb.cum, rank, nranks, pool_doubles, pb.summary);
+    // GIMIC_B200_DRAIN_BATCHES (default 1; 0 = never group, up to DRAIN_BATCHES), GIMIC_B200_DRAIN_MIN_TILES (default 2048): see PlanSummary
+    const char *edb = std::getenv("GIMIC_B200_DRAIN_BATCHES"), *edt = std::getenv("GIMIC_B200_DRAIN_MIN_TILES");
+    const int drain_batches = edb ? std::min(std::max(std::atoi(edb), 0), DRAIN_BATCHES) : 1, drain_min_tiles = edt ? std::max(std::atoi(edt), 1) : 2048;
+    k_plan_range<<<64, 256, 0, s>>>(pb.desc, pb.cum, rank, nranks, pool_doubles, pb.summary, drain_batches, drain_min_tiles);
     static const int order_bits = [] { const char *e = std::getenv("GIMIC_B200_ORDER_BITS"); return e ? std::atoi(e) : -1; }();
     k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0, order_bits);
 }

@@ -188,7 +188,8 @@ void emulate_plan_range(void **a) {
     long long chunk = (full + gb::DRAIN_GROUPS - 1) / gb::DRAIN_GROUPS;
     if (chunk < (16LL << 20)) chunk = 16LL << 20;
     if (const char *e = std::getenv("FAKE_DRAIN_CHUNK")) chunk = std::atoll(e);          // tests: groups on small point sets
-    const bool groups = std::getenv("FAKE_DRAIN_CHUNK") ? nb <= gb::DRAIN_BATCHES : (nb <= gb::DRAIN_BATCHES && thi - tlo >= 2048);
+    const int drain_batches = *(const int *)a[6], drain_min_tiles = *(const int *)a[7];
+    const bool groups = std::getenv("FAKE_DRAIN_CHUNK") ? nb <= gb::DRAIN_BATCHES : (nb <= drain_batches && thi - tlo >= drain_min_tiles);
     sum->drain_chunk = groups ? chunk : pool;
     for (int i = 0; i <= gb::DRAIN_BATCHES * gb::DRAIN_GROUPS; ++i) { sum->group_tile[i] = -1; sum->group_pt[i] = 0; }
     auto group_of = [&](int t) { const long long off = (cum[t].panel - cum[tlo].panel) % pool; const long long g = off / sum->drain_chunk; return (int)(g < gb::DRAIN_GROUPS - 1 ? g : gb::DRAIN_GROUPS - 1); };

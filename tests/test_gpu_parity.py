@@ -876,3 +876,34 @@ def test_column_sliced_tiles_equal_whole_tiles(gb, monkeypatch):
         _jscale_close(ja["jvec"], O.jvectors(ref, B), ref, "J path sliced vs oracle")
         assert_close(a["acid"], O.acid_field(ref), "acid (sliced)")
     g.close()
+
+
+def test_drain_groups_copy_out_the_right_rows(gb, monkeypatch):
+    """A partition call with HOST outputs on a range of one panel batch launches the contraction per drain group (a run of
+    Hilbert-ordered tiles = of compact output rows) and copies a finished group's rows out while the next group runs.  Same rows,
+    bit for bit, as the one-launch path with device outputs and as the ungrouped host path; two ranks too (a rank's first tile is
+    not tile 0).  64^3 points at nbf = 540: 2048+ tiles, 4 groups."""
+    import torch
+    sh, dens, nbf = fixtures.synthetic_case(15, "flake", seed=77)
+    g = gb.Gimic.from_arrays(screening_thrs=1e-8, dens_alpha=fixtures.dens_to_colmajor(dens), **sh)
+    lo, hi = sh["coords"].min(0) - 6.0, sh["coords"].max(0) + 6.0
+    n = 64
+    grid = gb.Grid(lo, np.eye(3), [np.linspace(0.0, hi[d] - lo[d], n) for d in range(3)])
+    B = np.array([0.2, -0.1, 0.95])
+    monkeypatch.setenv("GIMIC_B200_DRAIN_MIN_TILES", "256")
+    for rank, world in ((0, 1), (1, 2)):
+        monkeypatch.setenv("GIMIC_B200_DRAIN_BATCHES", "1")
+        cnt = g.partition(grid, rank, world)
+        host = g.partition_calc(B, "total", tens=True, jvec=True, jmod=True)
+        launches_grouped = g.stats()["contract_launches"]
+        dev = g.partition_calc(B, "total", tens=True, jvec=True, jmod=True, device=torch.device("cuda", 0))
+        assert launches_grouped >= 2 and g.stats()["contract_launches"] == 1
+        monkeypatch.setenv("GIMIC_B200_DRAIN_BATCHES", "0")
+        g.partition(grid, rank, world)
+        plain = g.partition_calc(B, "total", tens=True, jvec=True, jmod=True)
+        assert g.stats()["contract_launches"] == 1
+        for k in ("index", "tens", "jvec", "jmod"):
+            d = dev[k].cpu().numpy() if hasattr(dev[k], "cpu") else dev[k]
+            assert host[k].shape[0] == cnt and np.array_equal(host[k], d), (rank, k)
+            assert np.array_equal(host[k], plain[k]), (rank, k, "grouped vs ungrouped host path")
+    g.close()
