@@ -83,6 +83,7 @@ struct gimic_b200_ctx {
     Buf keys0, keys1, vals0, vals1, sorttmp, rs, panel, fidx, atab, misc, r_in, r_in2, tens_tmp, tens_tmp2, f_tmp, f_tmp2, shift, jv6, gridbuf, quad;
     Buf p_seg, p_geo, p_info, p_cnt, p_off, geo, desc, cum, pkeys0, pkeys1, pord0, pord1, tiles, d_summary, p_tops;   // tile plan (k_prepare.cu)
     Buf items, part;                   // work items / partial row sums of sliced tiles (few tiles: see launch_tile_slices)
+    Buf gtiles, pgkeys0;               // the plan's tiles in (batch, drain group, cost) order and their sort keys
     gb::PlanSummary *h_summary = nullptr;   // pinned
     Plan plan;
     double split_radius = 2.5;   // bohr: tiles wider than this are cut at their largest consecutive gap if that shrinks them
@@ -104,7 +105,7 @@ struct gimic_b200_ctx {
         for (int i = 0; i < 4; ++i) if (d_opj[i]) cudaFree(d_opj[i]);
         for (Buf *b : {&keys0, &keys1, &vals0, &vals1, &sorttmp, &rs, &panel, &fidx, &atab, &misc, &r_in, &r_in2, &tens_tmp, &tens_tmp2, &f_tmp, &f_tmp2,
                        &shift, &jv6, &gridbuf, &quad, &p_seg, &p_geo, &p_info, &p_cnt, &p_off, &geo, &desc, &cum, &pkeys0, &pkeys1, &pord0, &pord1,
-                       &tiles, &d_summary, &p_tops, &items, &part}) b->release();
+                       &tiles, &d_summary, &p_tops, &items, &part, &gtiles, &pgkeys0}) b->release();
         if (h_summary) cudaFreeHost(h_summary);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : evpool) cudaEventDestroy(e);
@@ -380,13 +381,14 @@ int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nrank
             c->p_info.ensure((size_t)nrun0 * MAXSUB * sizeof(TileInfo)) || c->p_cnt.ensure((size_t)nrun0 * 4) || c->p_off.ensure((size_t)(nrun0 + 1) * 4) ||
             c->geo.ensure((size_t)cap * sizeof(TileGeo)) || c->desc.ensure((size_t)cap * sizeof(TileDesc)) || c->cum.ensure((size_t)(cap + 1) * sizeof(TileCum)) ||
             c->pkeys0.ensure((size_t)cap * 8) || c->pkeys1.ensure((size_t)cap * 8) || c->pord0.ensure((size_t)cap * 4) || c->pord1.ensure((size_t)cap * 4) ||
-            c->tiles.ensure((size_t)cap * sizeof(TileDesc)) || c->p_tops.ensure((size_t)(nrun0 * MAXSUB / 2048 + 4) * (sizeof(TileCum) + sizeof(int))))
+            c->tiles.ensure((size_t)cap * sizeof(TileDesc)) || c->gtiles.ensure((size_t)cap * sizeof(TileDesc)) || c->pgkeys0.ensure((size_t)cap * 8) || c->p_tops.ensure((size_t)(nrun0 * MAXSUB / 2048 + 4) * (sizeof(TileCum) + sizeof(int))))
             return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tiles)");
         PlanBuffers pb;
         pb.slot_seg = c->p_seg.as<TileSeg>(); pb.slot_geo = c->p_geo.as<TileGeo>(); pb.slot_info = c->p_info.as<TileInfo>();
         pb.cnt = c->p_cnt.as<int>(); pb.off = c->p_off.as<int>(); pb.geo = c->geo.as<TileGeo>(); pb.desc = c->desc.as<TileDesc>();
         pb.cum = c->cum.as<TileCum>(); pb.keys0 = c->pkeys0.as<unsigned long long>(); pb.keys1 = c->pkeys1.as<unsigned long long>();
         pb.ord0 = c->pord0.as<int>(); pb.ord1 = c->pord1.as<int>(); pb.tiles = c->tiles.as<TileDesc>();
+        pb.gkeys0 = c->pgkeys0.as<unsigned long long>(); pb.gtiles = c->gtiles.as<TileDesc>();
         pb.summary = c->d_summary.as<PlanSummary>(); pb.cap = (int)cap;
         pb.tops_c = c->p_tops.as<TileCum>(); pb.tops_i = reinterpret_cast<int *>(pb.tops_c + (nrun0 * MAXSUB / 2048 + 4));
         launch_plan_tiles(c->db, rsx, rsy, rsz, n, c->split_radius, rank, nranks, pool_doubles, pb, st);
@@ -401,9 +403,9 @@ int build_plan(gimic_b200_ctx *c, long n, const double *d_r, int rank, int nrank
             if (nt > 0) {
                 const size_t sb = plan_sort_temp_bytes(nt);
                 if (c->sorttmp.ensure(sb)) return fail(GIMIC_B200_ENOMEM, "device workspace allocation failed (tile sort)");
-                launch_plan_order(pb, S.tlo, nt, c->sorttmp.p, sb, st);
+                launch_plan_order(pb, S.tlo, nt, S.drain_chunk < pool_doubles, c->sorttmp.p, sb, st);
                 CUDA_TRY(cudaGetLastError());
-                c->stats.launches += 2;
+                c->stats.launches += S.drain_chunk < pool_doubles ? 4 : 2;
             }
             break;
         }
@@ -486,8 +488,8 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
         for (int k = 0; k < 3; ++k) a.B[k] = o.B3 ? o.B3[k] : 0.0;
         a.paramag = c->opts.paramag; a.diamag = c->opts.diamag;
         // A caller that drains the rows to the host while the GPU works (after_batch) gets them group by group when the range has few
-        // batches: the tiles of a batch are ordered (drain group, costliest first), a group is a contiguous run of Hilbert-ordered tiles =
-        // of compact output rows, and each group is its own launch.  Otherwise one launch per batch.
+        // batches: a second tile list is ordered (batch, drain group, costliest first), a group is a contiguous run of Hilbert-ordered
+        // tiles = of compact output rows, and each group is its own launch.  Otherwise one launch per batch over the (batch, cost) list.
         const bool grouped = after_batch && nsl == 1 && b < DRAIN_BATCHES && S.drain_chunk < pool_cap;
         if (!grouped) {
             launch_jtensor(a, giao, c->nsm, st);
@@ -509,7 +511,7 @@ int exec_plan(gimic_b200_ctx *c, int spincase, const Outputs &o, bool compact, c
                 const int ng = next_tile - gt;
                 if (ng <= 0) continue;
                 if (done) CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 4, st));
-                a.tiles = c->tiles.as<TileDesc>() + t0 + done; a.ntiles = ng;
+                a.tiles = c->gtiles.as<TileDesc>() + t0 + done; a.ntiles = ng;
                 launch_jtensor(a, giao, c->nsm, st);
                 CUDA_TRY(cudaGetLastError());
                 c->stats.launches += 1;

@@ -488,7 +488,8 @@ __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__
 
 // offsets inside the batch, scheduling keys (batch, longest first) and the statistics of the range
 __global__ void __launch_bounds__(256) k_plan_finalize(TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, long long pool_doubles,
-                                                       PlanSummary *sum, unsigned long long *__restrict__ keys, int *__restrict__ ord, int order_bits) {
+                                                       PlanSummary *sum, unsigned long long *__restrict__ keys, int *__restrict__ ord, int order_bits,
+                                                       unsigned long long *__restrict__ gkeys) {
     const int tlo = sum->tlo, thi = sum->thi;
     const int t = tlo + blockIdx.x * blockDim.x + threadIdx.x;
     double st[6] = {0, 0, 0, 0, 0, 0};
@@ -510,8 +511,10 @@ __global__ void __launch_bounds__(256) k_plan_finalize(TileDesc *__restrict__ de
             const unsigned m = e > order_bits ? (unsigned)((c >> (e - order_bits)) & ((1LL << order_bits) - 1)) : (unsigned)(c & ((1LL << order_bits) - 1));
             c32 = ((unsigned)e << order_bits) | m;
         }
+        keys[t - tlo] = ((unsigned long long)b << 32) | (0xffffffffu - c32);
+        // second order, used only when host outputs are drained group by group: (batch, drain group, costliest first)
         const unsigned long long g = b < DRAIN_BATCHES ? (unsigned long long)drain_group(cum[t].panel - cum[tlo].panel, pool_doubles, sum->drain_chunk) : 0ull;
-        keys[t - tlo] = ((unsigned long long)b << 36) | (g << 32) | (0xffffffffu - c32);
+        gkeys[t - tlo] = ((unsigned long long)b << 36) | (g << 32) | (0xffffffffu - c32);
         ord[t - tlo] = t;
         st[0] = td.nact; st[1] = 2.0 * MT * 4.0 * td.nact * td.nn; st[2] = 2.0 * MT * 2.0 * td.nact * td.nn;
         st[3] = 2.0 * MT * (double)td.nn * td.nruns;                       // per tap weight (x3 tensor path, x1 J path)
@@ -579,7 +582,7 @@ void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, 
     const int drain_batches = edb ? std::min(std::max(std::atoi(edb), 0), DRAIN_BATCHES) : 1, drain_min_tiles = edt ? std::max(std::atoi(edt), 1) : 2048;
     k_plan_range<<<64, 256, 0, s>>>(pb.desc, pb.cum, rank, nranks, pool_doubles, pb.summary, drain_batches, drain_min_tiles);
     static const int order_bits = [] { const char *e = std::getenv("GIMIC_B200_ORDER_BITS"); return e ? std::atoi(e) : -1; }();
-    k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0, order_bits);
+    k_plan_finalize<<<(unsigned)((pb.cap + 255) / 256), 256, 0, s>>>(pb.desc, pb.cum, pool_doubles, pb.summary, pb.keys0, pb.ord0, order_bits, pb.gkeys0);
 }
 size_t plan_sort_temp_bytes(int nt) {
     size_t bytes = 0;
@@ -587,11 +590,15 @@ size_t plan_sort_temp_bytes(int nt) {
     return bytes;
 }
 // processing order of this rank's nt tiles: batch by batch, longest first inside a batch (the contraction kernel pulls tiles from an atomic counter)
-void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, void *sorttmp, size_t sorttmp_bytes, cudaStream_t s) {
+void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, bool grouped, void *sorttmp, size_t sorttmp_bytes, cudaStream_t s) {
     if (nt <= 0) return;
     (void)tlo;
     cub::DeviceRadixSort::SortPairs(sorttmp, sorttmp_bytes, pb.keys0, pb.keys1, pb.ord0, pb.ord1, nt, 0, 64, s);
     k_tile_gather<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(pb.desc, pb.ord1, nt, pb.tiles);
+    if (grouped) {       // the drain-group order of the same tiles (keys1 / ord1 are free again: stream order)
+        cub::DeviceRadixSort::SortPairs(sorttmp, sorttmp_bytes, pb.gkeys0, pb.keys1, pb.ord0, pb.ord1, nt, 0, 64, s);
+        k_tile_gather<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(pb.desc, pb.ord1, nt, pb.gtiles);
+    }
 }
 void launch_perm_index(const int *perm, long n, long *index, cudaStream_t s) {
     if (n <= 0) return;

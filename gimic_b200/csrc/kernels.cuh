@@ -82,8 +82,8 @@ struct PlanSummary {                // device -> host, once per plan
     long long cost_total, cost_range;
     double sum_nact, flops4, flops2, taps, useful_mm, useful_taps;   // statistics of the range (see gimic_b200_stats)
     // Drain groups (only when the range has at most DRAIN_BATCHES batches): a batch is cut into up to DRAIN_GROUPS runs of Hilbert-ordered
-    // tiles of `drain_chunk` panel doubles each; the processing order is (batch, group, costliest first), so a caller that wants its
-    // rows on the host can launch the contraction group by group and copy a finished group's rows out while the next one runs.
+    // tiles of `drain_chunk` panel doubles each; a second tile list is ordered (batch, group, costliest first), so a caller that wants
+    // its rows on the host can launch the contraction group by group and copy a finished group's rows out while the next one runs.
     long long drain_chunk;
     int group_tile[DRAIN_BATCHES * DRAIN_GROUPS + 1];        // first tile (Hilbert order, absolute) of group g of batch b at [b * DRAIN_GROUPS + g]; -1 = empty
     long long group_pt[DRAIN_BATCHES * DRAIN_GROUPS + 1];    // its first sorted point
@@ -103,13 +103,14 @@ struct PlanBuffers {                // device workspaces of one plan (all sized 
     TileCum *cum;                                                // [cap + 1] sizes -> exclusive prefix sums (in place), [ntiles] = totals
     unsigned long long *keys0, *keys1; int *ord0, *ord1;         // [cap] scheduling keys / tile order (CUB sort)
     TileDesc *tiles;                                             // [cap] this rank's tiles in processing order (batch by batch, longest first)
+    unsigned long long *gkeys0; TileDesc *gtiles;                // [cap] the same tiles ordered (batch, drain group, longest first): only used when host outputs are drained group by group
     PlanSummary *summary;                                        // device copy
     int *tops_i; TileCum *tops_c;                                // [cap / 2048 + 2] tile totals of the prefix sums
     int cap;
 };
 void launch_plan_tiles(const DevBasis &B, const double *rsx, const double *rsy, const double *rsz, long n, double split_radius,
                        int rank, int nranks, long long pool_doubles, const PlanBuffers &pb, cudaStream_t s);
-void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, void *sorttmp, size_t sorttmp_bytes, cudaStream_t s);
+void launch_plan_order(const PlanBuffers &pb, int tlo, int nt, bool grouped, void *sorttmp, size_t sorttmp_bytes, cudaStream_t s);
 size_t plan_sort_temp_bytes(int nt);
 void launch_perm_index(const int *perm, long n, long *index, cudaStream_t s);
 void launch_basis(const DevBasis &B, const TileDesc *tiles, int ntiles, int max_nruns, const TileGeo *geo, const double *rsx, const double *rsy,
