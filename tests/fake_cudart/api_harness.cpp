@@ -97,7 +97,6 @@ int main(int argc, char **argv) {
                 gimic_b200_stats st;
                 const bool every_tile_its_own = std::atol(std::getenv("FAKE_DRAIN_CHUNK")) < 50000;     // a c4h4 tile holds ~88 000 panel doubles
                 EXPECT(gimic_b200_get_stats(h, &st) == 0 && st.contract_launches >= (every_tile_its_own ? 2 : 1) && st.contract_launches <= 4);
-                if (std::getenv("FAKE_DEBUG")) std::printf("rank %d tiles %ld contract launches %ld\n", rk, info[3], (long)st.contract_launches);
             }
             total += cnt; cost_sum += info[5]; tiles_sum += info[3];
             // balanced to within one tile: no share is more than the mean + the largest tile cost (bounded here by the total / 2)
