@@ -432,12 +432,6 @@ __global__ void k_tile_emit(const TileSeg *__restrict__ slot_seg, const TileGeo 
     }
 }
 
-// drain group of a tile inside its batch (PlanSummary::drain_chunk): its panel offset in the batch over the chunk size
-__host__ __device__ inline int drain_group(long long panel_prefix_in_range, long long pool_doubles, long long chunk) {
-    const long long off = panel_prefix_in_range % pool_doubles;
-    const long long g = off / chunk;
-    return (int)(g < DRAIN_GROUPS - 1 ? g : DRAIN_GROUPS - 1);
-}
 // this rank's share: tiles whose exclusive cost prefix falls into [rank, rank + 1) x total / nranks; panel-pool batches of that range
 __global__ void __launch_bounds__(256) k_plan_range(const TileDesc *__restrict__ desc, const TileCum *__restrict__ cum, int rank, int nranks,
                                                     long long pool_doubles, PlanSummary *sum, int drain_batches, int drain_min_tiles) {

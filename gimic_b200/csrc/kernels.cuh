@@ -91,6 +91,13 @@ struct PlanSummary {                // device -> host, once per plan
     long long batch_pt[MAX_BATCH + 1];   // first sorted point of each batch; [nbatch] = pt_hi (a batch is a contiguous run of compact output rows)
 };
 
+// drain group of a tile inside its batch (PlanSummary::drain_chunk): its panel offset in the batch over the chunk size
+__host__ __device__ inline int drain_group(long long panel_prefix_in_range, long long pool_doubles, long long chunk) {
+    const long long off = panel_prefix_in_range % pool_doubles;
+    const long long g = off / chunk;
+    return (int)(g < DRAIN_GROUPS - 1 ? g : DRAIN_GROUPS - 1);
+}
+
 // ---- launch wrappers (defined in k_prepare.cu / k_jtensor.cu / k_fields.cu) ----------------------
 void launch_morton_keys(const double *r, long n, const double *bbox_lo, double inv_cell, uint32_t *keys, int *vals, cudaStream_t s);
 void launch_gather_points(const double *r, const int *perm, long n, double *rsx, double *rsy, double *rsz, cudaStream_t s);

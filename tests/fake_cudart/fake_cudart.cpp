@@ -192,7 +192,7 @@ void emulate_plan_range(void **a) {
     const bool groups = std::getenv("FAKE_DRAIN_CHUNK") ? nb <= gb::DRAIN_BATCHES : (nb <= drain_batches && thi - tlo >= drain_min_tiles);
     sum->drain_chunk = groups ? chunk : pool;
     for (int i = 0; i <= gb::DRAIN_BATCHES * gb::DRAIN_GROUPS; ++i) { sum->group_tile[i] = -1; sum->group_pt[i] = 0; }
-    auto group_of = [&](int t) { const long long off = (cum[t].panel - cum[tlo].panel) % pool; const long long g = off / sum->drain_chunk; return (int)(g < gb::DRAIN_GROUPS - 1 ? g : gb::DRAIN_GROUPS - 1); };
+    auto group_of = [&](int t) { return gb::drain_group(cum[t].panel - cum[tlo].panel, pool, sum->drain_chunk); };
     for (int t = tlo; t < thi; ++t) {
         const long long b = (cum[t].panel - cum[tlo].panel) / pool;
         const bool newb = t == tlo || (cum[t - 1].panel - cum[tlo].panel) / pool != b;

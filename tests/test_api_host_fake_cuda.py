@@ -110,3 +110,15 @@ def test_python_wrapper_signatures_on_the_fake_cuda_runtime(tmp_path, cases):
     p = subprocess.run([sys.executable, "-c", code, cases["c4h4"]["mol"], cases["c4h4"]["xdens"], cases["open_shell"]["mol"], cases["open_shell"]["xdens"]],
                        capture_output=True, text=True, timeout=300, env=dict(os.environ, LD_LIBRARY_PATH=str(fake)))
     assert p.returncode == 0 and "python wrapper ok" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
+
+
+def test_plan_helper_properties(tmp_path):
+    """slice_width / piece_cost / drain_group (kernels.cuh, shared by the plan kernels, the contraction and the host): slices cover a tile's
+    columns exactly once in multiples of 32, follow the tile's cost and never exceed the slot count; costs are monotone; drain groups are
+    ordered along a batch (tests/fake_cudart/plan_props.cpp, 20 000 random tiles)."""
+    if not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("CUDA headers not installed")
+    exe = tmp_path / "plan_props"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-o", str(exe), os.path.join(ROOT, "tests", "fake_cudart", "plan_props.cpp")])
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "plan props: 0 failure(s)" in p.stdout, p.stdout[-2000:]
